@@ -1,0 +1,298 @@
+// TEST INFRASTRUCTURE (oracle side) -- never linked or executed by the product.
+//
+// Links the UNMODIFIED reference objects built by oracle/Makefile and writes what the reference holds
+// in memory right before / while it simulates, as a flat tagged binary ("RSQFLAT1"), so that
+//   * the product's own profile loader + table flattening can be byte-compared with the reference's
+//     (DataStats::Load + PrepareProcessing, ProbabilityEstimates::Estimate + PrepareResult), and
+//   * the device kernels for the master-stream systematic errors / block seeds / bias normalisation
+//     have per-stage ground truth (Simulator::Simulate prologue, Simulator.cpp:2687-2826).
+//
+//   dump_tables profile <stats.reseq> <out.flat>                      profile + LogArrayResult tables
+//   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat>   + normalisation, thresholds, seeds, sys-errors
+//
+// Private members are reached by re-declaring access for this translation unit only.
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <random>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+#include <seqan/bam_io.h>
+#include <seqan/seq_io.h>
+#include <seqan/vcf_io.h>
+#include <seqan/modifier.h>
+#include <boost/archive/text_iarchive.hpp>
+#include <boost/archive/text_oarchive.hpp>
+#include <gtest/gtest.h>
+
+#define private public
+#define protected public
+#include "Simulator.h"
+#undef private
+#undef protected
+
+namespace reseq{ uint16_t kVerbosityLevel = 1; } // defined in main.cpp:22 in the reference binary
+using namespace reseq;
+
+namespace {
+struct FlatWriter {
+	FILE *f;
+	explicit FlatWriter(const char *path) : f(fopen(path, "wb")) {
+		if(!f){ perror(path); exit(2); }
+		fwrite("RSQFLAT1", 1, 8, f);
+	}
+	~FlatWriter(){ fclose(f); }
+	void raw(const std::string &name, uint32_t dtype, uint64_t count, const void *data, size_t elem){
+		uint32_t nl = name.size();
+		fwrite(&nl, 4, 1, f); fwrite(name.data(), 1, nl, f);
+		fwrite(&dtype, 4, 1, f); fwrite(&count, 8, 1, f);
+		if(count){ fwrite(data, elem, count, f); }
+	}
+	void u8(const std::string &n, const std::vector<uint8_t> &v){ raw(n, 0, v.size(), v.data(), 1); }
+	void u32(const std::string &n, const std::vector<uint32_t> &v){ raw(n, 1, v.size(), v.data(), 4); }
+	void u64(const std::string &n, const std::vector<uint64_t> &v){ raw(n, 2, v.size(), v.data(), 8); }
+	void f64(const std::string &n, const std::vector<double> &v){ raw(n, 3, v.size(), v.data(), 8); }
+	void i64(const std::string &n, const std::vector<int64_t> &v){ raw(n, 4, v.size(), v.data(), 8); }
+	void str(const std::string &n, const std::string &s){ raw(n, 0, s.size(), s.data(), 1); }
+	void s64(const std::string &n, int64_t v){ i64(n, std::vector<int64_t>{v}); }
+	void d(const std::string &n, double v){ f64(n, std::vector<double>{v}); }
+	// Vect<T> as {from, values...}
+	template<class T> void vect(const std::string &n, const Vect<T> &v){
+		s64(n + ".from", v.from());
+		std::vector<uint64_t> vals;
+		for(auto i=v.from(); i<v.to(); ++i){ vals.push_back(v[i]); }
+		u64(n, vals);
+	}
+	void vectd(const std::string &n, const Vect<double> &v){
+		s64(n + ".from", v.from());
+		std::vector<double> vals;
+		for(auto i=v.from(); i<v.to(); ++i){ vals.push_back(v[i]); }
+		f64(n, vals);
+	}
+	// Vect<Vect<u64>> as rows: from, per-row {from, count} + concatenated values
+	void vect2(const std::string &n, const Vect<Vect<uint64_t>> &v){
+		s64(n + ".from", v.from());
+		std::vector<int64_t> rows; std::vector<uint64_t> vals;
+		for(auto i=v.from(); i<v.to(); ++i){
+			rows.push_back(v[i].from()); rows.push_back(v[i].to() - v[i].from());
+			for(auto j=v[i].from(); j<v[i].to(); ++j){ vals.push_back(v[i][j]); }
+		}
+		i64(n + ".rows", rows);
+		u64(n, vals);
+	}
+};
+
+struct TableDump {
+	std::vector<int64_t> desc;   // per table: n0, nm, from[4], to[4], off[4] (doubles), par0_off  -> 15 entries (+1 pad)
+	std::vector<double> blob;
+	std::vector<uint32_t> par0;
+	template<uintMarginId N> void add(const ProbabilityEstimatesSubClasses::LogArrayResult<N> &r){
+		int64_t e[16] = {0};
+		e[0] = r.par0_indeces_.size();
+		e[1] = N-1;
+		for(uintMarginId n=0; n<N-1; ++n){
+			e[2+n] = r.limits_.at(n).first;
+			e[6+n] = r.limits_.at(n).second;
+			e[10+n] = blob.size();
+			blob.insert(blob.end(), r.dim2_.at(n).begin(), r.dim2_.at(n).end());
+		}
+		e[14] = par0.size();
+		for(auto p : r.par0_indeces_){ par0.push_back(p); }
+		desc.insert(desc.end(), e, e+16);
+	}
+};
+
+void DumpProfile(FlatWriter &w, const DataStats &stats, const ProbabilityEstimates &est){
+	// ---- DataStats members the simulation reads (Simulator.cpp, FragmentDistributionStats.cpp:3504-3627) ----
+	for(int seg=0; seg<2; ++seg){
+		std::string s = std::to_string(seg);
+		w.vect("read_lengths." + s, stats.ReadLengths(seg));
+		w.vect2("read_lengths_by_fragment_length." + s, stats.ReadLengthsByFragmentLength(seg));
+		w.vect2("non_mapped_read_lengths_by_fragment_length." + s, stats.NonMappedReadLengthsByFragmentLength(seg));
+		std::vector<uint64_t> counts(stats.Adapters().Counts(seg).begin(), stats.Adapters().Counts(seg).end());
+		w.u64("adapter.count_sum." + s, counts);
+		std::vector<uint64_t> sig(stats.Adapters().SignificantCounts(seg).begin(), stats.Adapters().SignificantCounts(seg).end());
+		w.u64("adapter.significant_count." + s, sig);
+		w.s64("adapter.n." + s, stats.adapters_.seqs_.at(seg).size());
+		for(size_t a=0; a<stats.adapters_.seqs_.at(seg).size(); ++a){
+			std::string seq;
+			for(auto c : stats.adapters_.seqs_.at(seg).at(a)){ seq += static_cast<char>(c); }
+			w.str("adapter.seq." + s + "." + std::to_string(a), seq);
+			w.vect("adapter.start_cut." + s + "." + std::to_string(a), stats.Adapters().StartCut(seg, a));
+		}
+	}
+	w.vect("adapter.polya_tail_length", stats.Adapters().PolyATailLength());
+	w.u64("adapter.overrun_bases", std::vector<uint64_t>(stats.Adapters().OverrunBases().begin(), stats.Adapters().OverrunBases().end()));
+	w.s64("phred_quality_offset", stats.PhredQualityOffset());
+	w.s64("total_number_reads", stats.TotalNumberReads());
+	w.d("corrected_coverage", stats.CorrectedCoverage());
+	w.s64("creation_time", stats.CreationTime());
+	w.s64("reset_distance", stats.Coverage().reset_distance_);
+	w.s64("max_len_deletion", stats.Errors().MaxLenDeletion());
+	w.u64("tiles.tiles", std::vector<uint64_t>(stats.Tiles().Tiles().begin(), stats.Tiles().Tiles().end()));
+	w.u64("tiles.abundance", std::vector<uint64_t>(stats.Tiles().Abundance().begin(), stats.Tiles().Abundance().end()));
+
+	const auto &fd = stats.FragmentDistribution();
+	w.vect("insert_lengths", fd.insert_lengths_);
+	w.f64("ref_seq_bias", fd.ref_seq_bias_);
+	w.vectd("insert_lengths_bias", fd.insert_lengths_bias_);
+	w.vectd("gc_fragment_content_bias", fd.gc_fragment_content_bias_);
+	for(int b=0; b<3; ++b){
+		w.f64("fragment_surroundings_bias." + std::to_string(b), fd.fragment_surroundings_bias_.bias_.at(b));
+	}
+	w.f64("dispersion_parameters", std::vector<double>(fd.dispersion_parameters_.begin(), fd.dispersion_parameters_.end()));
+
+	// ---- LogArrayResult tables in the fixed family order used by the engine ----
+	TableDump t;
+	const size_t tiles = est.quality_result_.at(0).size();
+	w.s64("tab.num_tiles", tiles);
+	for(int seg=0; seg<2; ++seg) for(size_t tile=0; tile<tiles; ++tile) for(int b=0; b<4; ++b) t.add(est.quality_result_.at(seg).at(tile).at(b));
+	for(int seg=0; seg<2; ++seg) for(size_t tile=0; tile<tiles; ++tile) t.add(est.sequence_quality_result_.at(seg).at(tile));
+	for(int seg=0; seg<2; ++seg) for(size_t tile=0; tile<tiles; ++tile) for(int b=0; b<4; ++b) for(int d=0; d<5; ++d) t.add(est.base_call_result_.at(seg).at(tile).at(b).at(d));
+	for(int b=0; b<4; ++b) for(int l=0; l<5; ++l) for(int d=0; d<5; ++d) t.add(est.dom_error_result_.at(b).at(l).at(d));
+	for(int b=0; b<4; ++b) for(int d=0; d<5; ++d) t.add(est.error_rate_result_.at(b).at(d));
+	for(int ty=0; ty<2; ++ty) for(int c=0; c<6; ++c) t.add(est.indels_result_.at(ty).at(c));
+	w.i64("tab.desc", t.desc);
+	w.f64("tab.blob", t.blob);
+	w.u32("tab.par0", t.par0);
+}
+
+bool LoadAll(DataStats &stats, ProbabilityEstimates &est, const std::string &stats_file){
+	if(!stats.Load(stats_file.c_str())){ return false; }
+	stats.PrepareProcessing();
+	std::string ipf = stats_file + ".ipf";
+	// same call main.cpp:841 makes for `--ipfIterations 0` with an existing .ipf
+	if(!est.Estimate(stats, 0, 5, 1, ipf.c_str(), ipf.c_str())){ return false; }
+	est.PrepareResult();
+	return true;
+}
+}
+
+int main(int argc, char **argv){
+	if(argc < 4){
+		std::cerr << "usage: dump_tables profile <stats.reseq> <out> | sim <stats.reseq> <ref.fa> <seed> <coverage> <out> [max_blocks]" << std::endl;
+		return 2;
+	}
+	std::string mode = argv[1];
+	kVerbosityLevel = 1;
+	if(mode == "profile"){
+		DataStats stats(NULL);
+		ProbabilityEstimates est;
+		if(!LoadAll(stats, est, argv[2])){ return 1; }
+		FlatWriter w(argv[3]);
+		DumpProfile(w, stats, est);
+		return 0;
+	}
+	if(mode == "sim" && argc >= 7){
+		Reference ref;
+		if(!ref.ReadFasta(argv[3])){ return 1; }
+		DataStats stats(NULL);
+		ProbabilityEstimates est;
+		if(!LoadAll(stats, est, argv[2])){ return 1; }
+		uintSeed seed = std::stoull(argv[4]);
+		double coverage = std::stod(argv[5]);
+		size_t max_blocks = argc > 7 ? std::stoull(argv[7]) : static_cast<size_t>(-1);
+		FlatWriter w(argv[6]);
+
+		// --- Simulator::Simulate prologue, statement by statement (Simulator.cpp:2687-2797) ---
+		Simulator sim;
+		sim.block_seed_gen_.seed(seed);
+		ref.ReplaceN(seed);
+		if(!stats.FragmentDistribution().UpdateRefSeqBias(RefSeqBiasSimulation::kNo, "", ref, sim.block_seed_gen_)){ return 1; }
+		DumpProfile(w, stats, est); // after UpdateRefSeqBias so ref_seq_bias matches the simulated reference
+		sim.record_base_identifier_ = "ReseqRead";
+		uintFragCount reads(0);
+		uintRefLenCalc sum_read_length(0);
+		for(auto seg=2; seg--;){
+			for(auto len = stats.ReadLengths(seg).from(); len < stats.ReadLengths(seg).to(); ++len){
+				reads += stats.ReadLengths(seg).at(len);
+				sum_read_length += stats.ReadLengths(seg).at(len) * len;
+			}
+		}
+		double average_read_length = static_cast<double>(sum_read_length)/reads;
+		auto total_ref_size = ref.TotalSize();
+		double adapter_part = Simulator::CoveragePropLostFromAdapters(stats);
+		sim.total_pairs_ = Simulator::CoverageToNumberPairs(coverage, total_ref_size, average_read_length, adapter_part);
+		sim.num_adapter_only_pairs_ = round( static_cast<double>(sim.total_pairs_)*stats.FragmentDistribution().InsertLengths()[0]/(stats.TotalNumberReads()/2) );
+		sim.total_pairs_ -= sim.num_adapter_only_pairs_;
+		sim.simulation_error_ = false;
+		sim.bias_normalization_ = stats.FragmentDistribution().CalculateBiasNormalization(sim.coverage_groups_, sim.non_zero_thresholds_, ref, 1, sim.total_pairs_);
+		sim.sys_gc_range_ = utilities::Divide(sum_read_length,reads)/2;
+		for(auto seg=2; seg--;){
+			sim.adapter_sys_error_.at(seg).resize( stats.Adapters().Counts(seg).size() );
+			for(auto seq=stats.Adapters().Counts(seg).size(); seq--;){
+				if( stats.Adapters().Counts(seg).at(seq) ){
+					sim.ResetSystematicErrorCounters(ref);
+					sim.SetSystematicErrors(sim.adapter_sys_error_.at(seg).at(seq), stats.Adapters().Sequence(seg, seq), 0, length(stats.Adapters().Sequence(seg, seq)), stats, est);
+				}
+			}
+		}
+		sim.sys_from_file_ = false;
+
+		w.d("sim.average_read_length", average_read_length);
+		w.d("sim.adapter_part", adapter_part);
+		w.s64("sim.total_pairs", sim.total_pairs_);
+		w.s64("sim.num_adapter_only_pairs", sim.num_adapter_only_pairs_);
+		w.d("sim.bias_normalization", sim.bias_normalization_);
+		w.s64("sim.sys_gc_range", sim.sys_gc_range_);
+		w.u32("sim.coverage_groups", std::vector<uint32_t>(sim.coverage_groups_.begin(), sim.coverage_groups_.end()));
+		w.s64("sim.num_groups", sim.non_zero_thresholds_.size());
+		for(size_t g=0; g<sim.non_zero_thresholds_.size(); ++g){
+			std::vector<double> thr;
+			for(auto &t : sim.non_zero_thresholds_.at(g)){ thr.push_back(t.at(0)); thr.push_back(t.at(1)); }
+			w.f64("sim.thresholds." + std::to_string(g), thr);
+		}
+		for(int seg=0; seg<2; ++seg){
+			for(size_t a=0; a<sim.adapter_sys_error_.at(seg).size(); ++a){
+				std::vector<uint8_t> e;
+				for(auto &p : sim.adapter_sys_error_.at(seg).at(a)){ e.push_back(static_cast<uint8_t>(p.first)); e.push_back(p.second); }
+				w.u8("sim.adapter_sys_error." + std::to_string(seg) + "." + std::to_string(a), e);
+			}
+		}
+		// replaced reference (after ReplaceN), concatenated codes
+		for(uintRefSeqId s=0; s<ref.NumberSequences(); ++s){
+			std::vector<uint8_t> codes;
+			codes.reserve(ref.SequenceLength(s));
+			for(auto c : ref.ReferenceSequence(s)){ codes.push_back(static_cast<uint8_t>(c)); }
+			w.u8("sim.ref." + std::to_string(s), codes);
+		}
+
+		// --- all blocks, in creation order (Simulator.cpp:2823-2826 + GetNextBlock) ---
+		std::vector<uint64_t> seeds; std::vector<int64_t> ids, starts, refids;
+		std::vector<uint8_t> fwd, rev;
+		size_t nblocks = 0;
+		while(nblocks < max_blocks && sim.CreateBlock(ref, stats, est)){
+			++nblocks;
+		}
+		for(auto unit = sim.first_unit_; unit; unit = unit->next_unit_){
+			for(Simulator::SimBlock *b = unit->first_block_; b; b = b->next_block_){
+				seeds.push_back(b->seed_); ids.push_back(b->id_); starts.push_back(b->start_pos_); refids.push_back(unit->ref_seq_id_);
+				for(auto &p : b->sys_errors_){ fwd.push_back(static_cast<uint8_t>(p.first)); fwd.push_back(p.second); }
+				// partner (reverse) block: its sys_errors_ run in reverse-strand order for the same forward interval
+				for(auto &p : b->partner_block_->sys_errors_){ rev.push_back(static_cast<uint8_t>(p.first)); rev.push_back(p.second); }
+			}
+		}
+		w.u64("sim.block_seed", seeds);
+		w.i64("sim.block_id", ids);
+		w.i64("sim.block_start", starts);
+		w.i64("sim.block_ref", refids);
+		w.u8("sim.sys_fwd", fwd);
+		w.u8("sim.sys_rev", rev);
+		w.s64("sim.adapter_only_seed_next", 0);
+		return 0;
+	}
+	return 2;
+}

@@ -1,0 +1,696 @@
+// The per-read simulation hot path, restated for a lane group (warp):
+//   Simulator::SimulateFromGivenBlock  (reference Simulator.cpp:2249-2357)   -> simulate_block
+//   Simulator::CreateReads             (Simulator.cpp:634-721)              -> create_reads
+//   Simulator::FillRead / FillReadPart (Simulator.cpp:454-594, 294-452)     -> fill_read / fill_read_part
+//   Simulator::CreateReadId            (Simulator.cpp:596-632)              -> format_read_id
+//   FragmentDistributionStats::GetFragmentCounts / NegativeBinomial / Binomial (FragmentDistributionStats.cpp:3584-3627)
+//   Simulator::SetSystematicErrors / DrawSystematicError (Simulator.h:337-382), CoverageStats::UpdateDistances
+//   Simulator::ApplyErrorsAndQualityToFastaInput (Simulator.cpp:2403-2512)  -> error_model_batch
+//
+// One lane group owns one 1000-bp SimBlock: the block's mt19937_64 stream is consumed strictly in the
+// reference's order (scan draw per (position, fragment length), then the draws of every fragment hit),
+// lanes only share the work *inside* a step: 32 scan draws at a time, the candidates of a Draw, byte copies.
+// Variants (VCF) and methylation are not handled by this revision; the host refuses such runs.
+#pragma once
+#include "core.cuh"
+
+namespace rsq {
+
+struct BlockDesc {
+	uint32_t ref_id;
+	uint32_t start_pos;
+	uint32_t block_id;   // id printed in the read names (forward SimBlock::id_)
+	uint32_t pad;
+	uint64_t seed;
+};
+
+struct AdapterSet {            // per template segment
+	uint32_t n;                // number of adapters
+	const uint32_t *off;       // [n+1] offsets into adapter_seq / adapter_sys
+	Discrete pick;             // discrete_distribution over SignificantCounts(seg)
+	const Discrete *start_cut; // [n]
+	const uint32_t *start_cut_from; // [n] StartCut(seg,id).from()
+};
+
+struct SimCtx {
+	Tables tab;
+	// --- profile (DataStats getters used by Simulator) ---
+	uint32_t phred_offset;
+	uint32_t max_len_deletion;
+	uint32_t insert_from;              // max(1, InsertLengths().from())
+	uint32_t insert_to;                // InsertLengths().to()
+	uint32_t read_len_from[2];         // ReadLengths(seg).from()
+	uint32_t read_len_to[2];           // ReadLengths(seg).to()
+	uint32_t read_len_count[2];        // ReadLengths(seg).size()
+	// ReadLengthsByFragmentLength(seg) for profiles with several read lengths (GeneralRandomDistributions::ReadLength)
+	const uint32_t *rlbf_row_from[2];  // per fragment length: row.from()
+	const uint32_t *rlbf_row_off[2];   // per fragment length: offset of row values; [n_rows+1]
+	const uint64_t *rlbf_val[2];
+	uint32_t rlbf_from[2], rlbf_to[2];
+	const uint64_t *insert_lengths;    // dense [0, insert_to)
+	uint32_t num_tiles;
+	const uint16_t *tile_names;
+	Discrete tile_pick;
+	AdapterSet adapters[2];
+	const uint8_t *adapter_seq;        // base codes
+	const uint8_t *adapter_sys;        // (dominant error, rate) pairs, same offsets * 2
+	Discrete polya_pick;
+	uint32_t polya_from;
+	Discrete overrun_pick;
+	// --- fragment count model ---
+	const double *ref_seq_bias;        // [n_seqs]
+	const double *il_bias;             // dense [0, insert_to)
+	const double *gc_bias;             // dense [0, 101)
+	double disp_a, disp_b;
+	double bias_normalization;
+	const uint32_t *coverage_group;    // [n_seqs]
+	const double *thr;                 // [group][insert_to][2]  non_zero_thresholds_
+	const uint64_t *thr_int;           // [group][insert_to]     smallest raw draw x with canonical(x) >= thr[..][1] (filter only)
+	const double *binom_p0;            // [group][insert_to]     pow(1-(1-thr0), 2) (Binomial's first term, host libm)
+	// --- reference ---
+	uint32_t n_seqs;
+	const uint64_t *seq_off;           // [n_seqs] start of each sequence in the concatenated per-position arrays
+	const uint32_t *seq_len;
+	const uint8_t *ref;                // base codes 0..3 (after ReplaceN)
+	const uint32_t *gc_prefix;         // [total + n_seqs] per sequence: prefix count of G/C, entry i = #GC in [0,i)
+	const double *sur_start;           // SurroundingBias::Bias(forward surrounding at p)
+	const double *sur_end;             // SurroundingBias::Bias(reverse surrounding at p)
+	const uint8_t *sys_fwd;            // 2 bytes / position, forward strand order
+	const uint8_t *sys_rev;            // 2 bytes / position, reverse-strand order (index L-1-p)
+	const char *name_blob;             // ReferenceIdFirstPart per sequence
+	const uint32_t *name_off;          // [n_seqs+1]
+	const char *base_id;               // record_base_identifier_
+	uint32_t base_id_len;
+	uint32_t max_read_len;             // capacity of the per-read scratch
+	uint32_t max_org_len;
+	uint32_t *error_flag;              // set non-zero on unsupported situations (cigar overflow, runaway count)
+};
+
+enum : uint32_t { kErrCigarOverflow = 1, kErrCountRunaway = 2, kErrArenaFull = 4, kErrOrgOverflow = 8, kErrRecordTooLong = 16 };
+
+constexpr int kCigarCap = 192;
+constexpr int kIdCap = 384;
+
+struct Scratch {          // group-shared memory
+	uint64_t *mt;         // kMtN
+	double *prob;         // max n0
+	uint8_t *org;         // max_org_len     original bases of the current part
+	uint8_t *sdom;        // max_org_len     dominant systematic error per original base
+	uint8_t *srate;       // max_org_len     systematic error rate per original base
+	uint8_t *seq;         // max_read_len    called bases (codes)
+	uint8_t *qual;        // max_read_len    qualities (already + phred offset)
+	char *cigar;          // kCigarCap
+	char *id;             // kIdCap
+};
+
+RSQ_HD size_t scratch_bytes(uint32_t max_n0, uint32_t max_org_len, uint32_t max_read_len){
+	size_t b = kMtN * 8 + ((max_n0 + 1) & ~1u) * 8;
+	b += 3 * ((max_org_len + 7) & ~7u) + 2 * ((max_read_len + 7) & ~7u) + kCigarCap + kIdCap;
+	return (b + 15) & ~static_cast<size_t>(15);
+}
+RSQ_HD Scratch carve_scratch(unsigned char *base, uint32_t max_n0, uint32_t max_org_len, uint32_t max_read_len){
+	Scratch s;
+	s.mt = reinterpret_cast<uint64_t *>(base); base += kMtN * 8;
+	s.prob = reinterpret_cast<double *>(base); base += ((max_n0 + 1) & ~1u) * 8;
+	const uint32_t o = (max_org_len + 7) & ~7u, r = (max_read_len + 7) & ~7u;
+	s.org = base; base += o;
+	s.sdom = base; base += o;
+	s.srate = base; base += o;
+	s.seq = base; base += r;
+	s.qual = base; base += r;
+	s.cigar = reinterpret_cast<char *>(base); base += kCigarCap;
+	s.id = reinterpret_cast<char *>(base);
+	return s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small text helpers (lane-uniform; every lane computes the same lengths, lane 0 stores)
+// ---------------------------------------------------------------------------------------------------
+template<class G> RSQ_HD int put_uint(const G &g, char *dst, int pos, int cap, uint64_t v){
+	char tmp[20];
+	int n = 0;
+	do{ tmp[n++] = static_cast<char>('0' + v % 10); v /= 10; }while(v);
+	if(g.lane() == 0){
+		for(int i = 0; i < n && pos + i < cap; ++i){ dst[pos + i] = tmp[n - 1 - i]; }
+	}
+	return pos + n;
+}
+template<class G> RSQ_HD int put_char(const G &g, char *dst, int pos, int cap, char c){
+	if(g.lane() == 0 && pos < cap){ dst[pos] = c; }
+	return pos + 1;
+}
+template<class G> RSQ_HD int put_str(const G &g, char *dst, int pos, int cap, const char *src, int n){
+	if(g.lane() == 0){
+		for(int i = 0; i < n && pos + i < cap; ++i){ dst[pos + i] = src[i]; }
+	}
+	return pos + n;
+}
+
+struct ReadState {               // Simulator::ReadFillParameter (Simulator.h:215-240) + cigar bookkeeping
+	uint32_t read_length;
+	uint32_t read_pos;
+	uint32_t previous_indel_type;
+	uint32_t indel_pos;
+	uint32_t base_call;
+	uint32_t gc_seq;
+	uint32_t seq_qual;
+	uint32_t qual;
+	uint32_t error_rate;
+	uint32_t num_errors;
+	int cigar_len;               // bytes used in Scratch::cigar
+};
+
+template<class G> RSQ_HD void cigar_append(const G &g, const Scratch &s, ReadState &par, char op, uint32_t count){
+	par.cigar_len = put_uint(g, s.cigar, par.cigar_len, kCigarCap, count);
+	par.cigar_len = put_char(g, s.cigar, par.cigar_len, kCigarCap, op);
+}
+
+// Simulator::FillReadPart without variants.  `org_len` bases are staged in s.org / s.sdom / s.srate.
+template<class G>
+RSQ_HD void fill_read_part(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, ReadState &par,
+                           uint32_t seg, uint32_t tile, uint32_t org_pos, uint32_t org_len, char base_cigar_element){
+	uint32_t cigar_element_length = 0;
+	char cigar_element = base_cigar_element;
+	bool zero;
+	while(par.read_pos < par.read_length && org_pos < org_len){
+		const uint32_t ref_base = s.org[org_pos];
+		double u = mt_uniform(g, mt);
+		uint32_t indel = draw(g, c.tab, c.tab.indel(par.previous_indel_type, par.base_call), par.indel_pos, par.read_pos, par.gc_seq, 0, u, s.prob, zero);
+		if(zero){ indel = 0; }
+
+		if(indel == 0){
+			const uint32_t dom_error = s.sdom[org_pos];
+			par.error_rate = s.srate[org_pos];
+
+			u = mt_uniform(g, mt);
+			const uint32_t qtab = c.tab.quality(seg, tile, ref_base);
+			uint32_t q = draw(g, c.tab, qtab, par.seq_qual, par.qual, par.read_pos, par.error_rate, u, s.prob, zero);
+			if(zero){
+				if(par.read_pos){ q = (s.qual[par.read_pos - 1] - c.phred_offset) & 0xffu; }
+				else{ q = table_max_value(c.tab, qtab); }
+			}
+			par.qual = q & 0xffu;
+			g.sync();
+			if(g.lane() == 0){ s.qual[par.read_pos] = static_cast<uint8_t>(par.qual + c.phred_offset); }
+
+			u = mt_uniform(g, mt);
+			uint32_t call = draw(g, c.tab, c.tab.base_call(seg, tile, ref_base, dom_error), par.qual, par.read_pos, par.num_errors, par.error_rate, u, s.prob, zero);
+			if(zero){ call = ref_base; }
+			par.base_call = call;
+			if(g.lane() == 0){ s.seq[par.read_pos] = static_cast<uint8_t>(call); }
+
+			if(base_cigar_element == cigar_element){
+				++cigar_element_length;
+			}
+			else{
+				cigar_append(g, s, par, cigar_element, cigar_element_length);
+				cigar_element = base_cigar_element;
+				cigar_element_length = 1;
+				par.indel_pos = 0;
+				par.previous_indel_type = 0;
+			}
+			if(call != ref_base){ ++par.num_errors; }
+			++par.read_pos;
+			++org_pos;
+		}
+		else if(indel == 1){
+			par.error_rate = s.srate[org_pos];
+			if('D' == cigar_element){
+				++cigar_element_length;
+				++par.indel_pos;
+			}
+			else{
+				cigar_append(g, s, par, cigar_element, cigar_element_length);
+				cigar_element = 'D';
+				cigar_element_length = 1;
+				par.indel_pos = 1;
+				par.previous_indel_type = 1;
+			}
+			++par.num_errors;
+			++org_pos;
+		}
+		else{
+			u = mt_uniform(g, mt);
+			uint32_t q = draw(g, c.tab, c.tab.quality(seg, tile, ref_base), par.seq_qual, par.qual, par.read_pos, par.error_rate, u, s.prob, zero);
+			if(zero){ q = par.qual; }
+			g.sync();
+			if(g.lane() == 0){
+				s.qual[par.read_pos] = static_cast<uint8_t>(c.phred_offset + q);
+				s.seq[par.read_pos] = static_cast<uint8_t>(indel - 2);
+			}
+			if('I' == cigar_element){
+				++cigar_element_length;
+				++par.indel_pos;
+			}
+			else{
+				cigar_append(g, s, par, cigar_element, cigar_element_length);
+				cigar_element = 'I';
+				cigar_element_length = 1;
+				par.indel_pos = 1;
+				par.previous_indel_type = 0;
+			}
+			++par.num_errors;
+			++par.read_pos;
+		}
+	}
+	if(cigar_element_length){
+		cigar_append(g, s, par, cigar_element, cigar_element_length);
+	}
+}
+
+// GeneralRandomDistributions::ReadLength (Simulator.h:185-198)
+template<class G> RSQ_HD uint32_t draw_read_length(const G &g, const SimCtx &c, Mt &mt, uint32_t seg, uint32_t fragment_length){
+	if(1 == c.read_len_count[seg]){ return c.read_len_from[seg]; }
+	const double ins = (fragment_length < c.insert_to) ? static_cast<double>(c.insert_lengths[fragment_length]) : 0.0;
+	const double random_value = mul_rn(mt_uniform(g, mt), ins);
+	double counter = 0.0;
+	uint32_t row_from = 0, row_n = 0;
+	const uint64_t *vals = nullptr;
+	if(fragment_length >= c.rlbf_from[seg] && fragment_length < c.rlbf_to[seg]){
+		const uint32_t r = fragment_length - c.rlbf_from[seg];
+		row_from = c.rlbf_row_from[seg][r];
+		row_n = c.rlbf_row_off[seg][r + 1] - c.rlbf_row_off[seg][r];
+		vals = c.rlbf_val[seg] + c.rlbf_row_off[seg][r];
+	}
+	uint32_t read_len = row_from + row_n;   // .to()
+	while(counter <= random_value && (read_len-- > row_from)){
+		counter = add_rn(counter, static_cast<double>(vals[read_len - row_from]));
+	}
+	return read_len & 0xffffu;
+}
+
+// Stage an adapter (bases + its systematic errors) as the current original sequence.
+template<class G> RSQ_HD uint32_t stage_adapter(const G &g, const SimCtx &c, const Scratch &s, uint32_t seg, uint32_t adapter_id){
+	const uint32_t off = c.adapters[seg].off[adapter_id];
+	uint32_t len = c.adapters[seg].off[adapter_id + 1] - off;
+	if(len > c.max_org_len){ len = c.max_org_len; if(g.lane() == 0){ *c.error_flag |= kErrOrgOverflow; } }
+	g.sync();
+	for(uint32_t i = g.lane(); i < len; i += G::kSize){
+		s.org[i] = c.adapter_seq[off + i];
+		s.sdom[i] = c.adapter_sys[2 * (off + i)];
+		s.srate[i] = c.adapter_sys[2 * (off + i) + 1];
+	}
+	g.sync();
+	return len;
+}
+
+// Simulator::FillRead.  On entry s.org/sdom/srate hold `org_len` bases of the fragment as this read sees it.
+template<class G>
+RSQ_HD void fill_read(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, ReadState &par,
+                      uint32_t seg, uint32_t tile, uint32_t fragment_length, uint32_t org_len){
+	par.read_pos = 0; par.previous_indel_type = 0; par.indel_pos = 0; par.base_call = 5; par.gc_seq = 0;
+	par.qual = 1; par.error_rate = 0; par.num_errors = 0; par.cigar_len = 0; par.seq_qual = 0;
+	par.read_length = draw_read_length(g, c, mt, seg, fragment_length);
+	if(par.read_length > c.max_read_len){ par.read_length = c.max_read_len; if(g.lane() == 0){ *c.error_flag |= kErrOrgOverflow; } }
+
+	uint32_t adapter_id = 0;
+	const uint32_t seq_length = par.read_length < org_len ? par.read_length : org_len;
+	uint32_t mean_error_rate = 0;
+	if(seq_length){
+		uint32_t gc = 0, err = 0;
+		for(uint32_t i = g.lane(); i < seq_length; i += G::kSize){
+			const uint32_t b = s.org[i];
+			gc += (b == 1 || b == 2) ? 1u : 0u;
+			err += s.srate[i];
+		}
+		gc = g.reduce_add(gc);
+		err = g.reduce_add(err);
+		par.gc_seq = percent_u16(gc, seq_length);
+		mean_error_rate = divide_u32(err, seq_length);
+	}
+	else{
+		adapter_id = discrete_draw(g, mt, c.adapters[seg].pick);
+		const uint32_t alen = stage_adapter(g, c, s, seg, adapter_id);
+		uint32_t gc = 0, err = 0;
+		for(uint32_t i = g.lane(); i < alen; i += G::kSize){
+			const uint32_t b = s.org[i];
+			gc += (b == 1 || b == 2) ? 1u : 0u;
+			err += s.srate[i];
+		}
+		gc = g.reduce_add(gc);
+		err = g.reduce_add(err);
+		par.gc_seq = percent_u16(gc, alen);
+		mean_error_rate = divide_u32(err, alen);
+	}
+
+	bool zero;
+	{
+		const uint32_t tid = c.tab.seq_quality(seg, tile);
+		const double u = mt_uniform(g, mt);
+		uint32_t sq = draw(g, c.tab, tid, par.gc_seq, mean_error_rate, fragment_length / 10, 0, u, s.prob, zero);
+		if(zero){ sq = table_most_likely(c.tab, tid); }
+		par.seq_qual = sq & 0xffu;
+	}
+
+	fill_read_part(g, c, s, mt, par, seg, tile, 0, org_len, 'M');
+
+	if(par.read_pos < par.read_length){
+		if(0 == adapter_id){
+			adapter_id = discrete_draw(g, mt, c.adapters[seg].pick);
+		}
+		uint32_t adapter_pos = 0;
+		if(0 == par.read_pos){
+			adapter_pos = discrete_draw(g, mt, c.adapters[seg].start_cut[adapter_id]) + c.adapters[seg].start_cut_from[adapter_id];
+		}
+		const uint32_t alen = stage_adapter(g, c, s, seg, adapter_id);
+		fill_read_part(g, c, s, mt, par, seg, tile, adapter_pos, alen, 'S');
+
+		if(par.read_pos < par.read_length){
+			cigar_append(g, s, par, 'H', par.read_length - par.read_pos);
+			const uint32_t qtab = c.tab.quality(seg, tile, 0);
+			const uint32_t tail_length = (discrete_draw(g, mt, c.polya_pick) + c.polya_from) & 0xffffu;
+			for(uint32_t pos_tail = 0; pos_tail < tail_length && par.read_pos < par.read_length; ++pos_tail){
+				const double u = mt_uniform(g, mt);
+				uint32_t q = draw(g, c.tab, qtab, par.seq_qual, par.qual, par.read_pos, par.error_rate, u, s.prob, zero);
+				g.sync();
+				if(zero){ q = (s.qual[par.read_pos - 1] - c.phred_offset) & 0xffu; }
+				par.qual = q & 0xffu;
+				if(g.lane() == 0){
+					s.qual[par.read_pos] = static_cast<uint8_t>(par.qual + c.phred_offset);
+					s.seq[par.read_pos] = 0;
+				}
+				++par.read_pos;
+			}
+			while(par.read_pos < par.read_length){
+				const double u = mt_uniform(g, mt);
+				uint32_t q = draw(g, c.tab, qtab, par.seq_qual, par.qual, par.read_pos, par.error_rate, u, s.prob, zero);
+				g.sync();
+				if(zero){ q = (s.qual[par.read_pos - 1] - c.phred_offset) & 0xffu; }
+				par.qual = q & 0xffu;
+				const uint32_t b = discrete_draw(g, mt, c.overrun_pick);
+				if(g.lane() == 0){
+					s.qual[par.read_pos] = static_cast<uint8_t>(par.qual + c.phred_offset);
+					s.seq[par.read_pos] = static_cast<uint8_t>(b);
+				}
+				++par.read_pos;
+			}
+		}
+	}
+	if(par.cigar_len > kCigarCap && g.lane() == 0){ *c.error_flag |= kErrCigarOverflow; }
+	g.sync();
+}
+
+// FragmentDistributionStats::Binomial with the first term pow(1-p, N) supplied by the host
+RSQ_HD uint32_t binomial_count(uint32_t N, double p, double pow_term, double probability_chosen){
+	double probability_count = pow_term;
+	double probability_left = sub_rn(probability_chosen, probability_count);
+	uint32_t count = 0;
+	const double one_minus_p = sub_rn(1.0, p);
+	while(0.0 < probability_left && count < N){
+		++count;
+		const double f = mul_rn(static_cast<double>(static_cast<int>(N + 1 - count)) / static_cast<double>(static_cast<int>(count)), p) / one_minus_p;
+		probability_count = mul_rn(probability_count, f);
+		probability_left = sub_rn(probability_left, probability_count);
+	}
+	return count;
+}
+
+// FragmentDistributionStats::GetFragmentCounts + NegativeBinomial + BiasCalculationVectors::GetDispersion
+RSQ_HD uint32_t fragment_counts(const SimCtx &c, uint32_t ref_id, uint32_t fragment_length, uint32_t gc, double sur_start, double sur_end,
+                                double probability_chosen, bool &runaway){
+	double bias = mul_rn(c.ref_seq_bias[ref_id], c.il_bias[fragment_length]);   // Reference::Bias (Reference.h:167-169, 283-285)
+	bias = mul_rn(bias, c.gc_bias[gc]);
+	bias = mul_rn(bias, sur_start);
+	bias = mul_rn(bias, sur_end);
+	if(!(0.0 < bias)){ return 0; }
+	double mean = mul_rn(bias, c.bias_normalization);
+	double r = mean / add_rn(c.disp_a, mul_rn(c.disp_b, mean));
+	const double cap = mul_rn(mean, 1e10);
+	if(r > cap){ r = cap; }
+	// num_alleles == 1: the two divisions by the allele count are exact
+	const double p = mean / add_rn(mean, r);
+	double probability_count = pow_glibc(sub_rn(1.0, p), r);
+	double probability_left = sub_rn(probability_chosen, probability_count);
+	uint32_t count = 0;
+	while(0.0 < probability_left){
+		count = (count + 1) & 0xffffu;   // uintDupCount
+		probability_count = mul_rn(probability_count, mul_rn(p, add_rn(sub_rn(r, 1.0) / static_cast<double>(static_cast<int>(count)), 1.0)));
+		probability_left = sub_rn(probability_left, probability_count);
+		if(count == 0xffffu){ runaway = true; break; }
+	}
+	return count;
+}
+
+// Simulator::CreateReadId
+template<class G>
+RSQ_HD int format_read_id(const G &g, const SimCtx &c, const Scratch &s, uint32_t block_number, uint64_t read_number,
+                          uint32_t start_pos, uint32_t end_pos, uint32_t tile, uint32_t ref_id, const ReadState &par){
+	int n = 0;
+	n = put_str(g, s.id, n, kIdCap, c.base_id, c.base_id_len);
+	n = put_uint(g, s.id, n, kIdCap, block_number);
+	n = put_char(g, s.id, n, kIdCap, '_');
+	n = put_uint(g, s.id, n, kIdCap, read_number);
+	n = put_char(g, s.id, n, kIdCap, ':');
+	n = put_uint(g, s.id, n, kIdCap, start_pos);
+	n = put_char(g, s.id, n, kIdCap, ':');
+	if(start_pos){
+		n = put_str(g, s.id, n, kIdCap, c.name_blob + c.name_off[ref_id], c.name_off[ref_id + 1] - c.name_off[ref_id]);
+	}
+	else{
+		n = put_str(g, s.id, n, kIdCap, "Adapter", 7);
+	}
+	n = put_char(g, s.id, n, kIdCap, ':');
+	n = put_uint(g, s.id, n, kIdCap, end_pos);
+	n = put_char(g, s.id, n, kIdCap, ':');
+	n = put_uint(g, s.id, n, kIdCap, tile);
+	n = put_str(g, s.id, n, kIdCap, ":1337:1337 ", 11);
+	g.sync();
+	n = put_str(g, s.id, n, kIdCap, s.cigar, par.cigar_len < kCigarCap ? par.cigar_len : kCigarCap);
+	n = put_str(g, s.id, n, kIdCap, " E", 2);
+	n = put_uint(g, s.id, n, kIdCap, par.num_errors);
+	if(n > kIdCap){ if(g.lane() == 0){ *c.error_flag |= kErrRecordTooLong; } n = kIdCap; }
+	g.sync();
+	return n;
+}
+
+// Stage the original sequence + systematic errors of one read of a fragment (Simulator::GetOrgSeq without
+// variants + the block/partner-block lookup of CreateReads): forward read = prefix of the fragment on the
+// forward strand, reverse read = reverse complement of its suffix with the reverse-strand errors.
+template<class G>
+RSQ_HD uint32_t stage_fragment_read(const G &g, const SimCtx &c, const Scratch &s, uint32_t ref_id, uint32_t seg, bool reversed,
+                                    uint32_t start_pos, uint32_t end_pos, uint32_t fragment_length){
+	uint32_t org_len = c.read_len_to[seg] + c.max_len_deletion;
+	if(fragment_length < org_len){ org_len = fragment_length; }
+	if(org_len > c.max_org_len){ org_len = c.max_org_len; if(g.lane() == 0){ *c.error_flag |= kErrOrgOverflow; } }
+	const uint64_t off = c.seq_off[ref_id];
+	const uint32_t L = c.seq_len[ref_id];
+	g.sync();
+	if(!reversed){
+		const uint8_t *ref = c.ref + off + start_pos;
+		const uint8_t *sys = c.sys_fwd + 2 * (off + start_pos);
+		for(uint32_t i = g.lane(); i < org_len; i += G::kSize){
+			s.org[i] = ref[i];
+			s.sdom[i] = sys[2 * i];
+			s.srate[i] = sys[2 * i + 1];
+		}
+	}
+	else{
+		const uint8_t *ref = c.ref + off;
+		const uint8_t *sys = c.sys_rev + 2 * (off + (L - end_pos));
+		for(uint32_t i = g.lane(); i < org_len; i += G::kSize){
+			s.org[i] = static_cast<uint8_t>(3 - ref[end_pos - 1 - i]);
+			s.sdom[i] = sys[2 * i];
+			s.srate[i] = sys[2 * i + 1];
+		}
+	}
+	g.sync();
+	return org_len;
+}
+
+// Simulator::CreateReads for `counts` copies of one fragment (start_block != NULL case), or for the
+// adapter-only pairs (fragment_length == 0).
+template<class G, class Sink>
+RSQ_HD void create_reads(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, Sink &sink, uint32_t counts, bool strand,
+                         uint32_t ref_id, uint32_t fragment_length, uint64_t &read_number, uint32_t block_id,
+                         uint32_t start_position_forward, uint32_t end_position_forward){
+	uint32_t print_start = 0, print_end = 0;
+	if(fragment_length){
+		if(strand){ print_start = end_position_forward; print_end = start_position_forward + 1; }
+		else{ print_start = start_position_forward + 1; print_end = end_position_forward; }
+	}
+	for(uint32_t n = counts; n--; ){
+		++read_number;
+		uint32_t tile = 0;
+		if(1 < c.num_tiles){ tile = discrete_draw(g, mt, c.tile_pick); }
+		for(uint32_t seg = 2; seg--; ){
+			uint32_t org_len = 0;
+			if(fragment_length){
+				// block.at(strand) is the forward start block, block.at(!strand) the reverse partner of the end block
+				const bool reversed = (seg != static_cast<uint32_t>(strand));
+				org_len = stage_fragment_read(g, c, s, ref_id, seg, reversed, start_position_forward, end_position_forward, fragment_length);
+			}
+			ReadState par;
+			fill_read(g, c, s, mt, par, seg, tile, fragment_length, org_len);
+			const int id_len = format_read_id(g, c, s, block_id, read_number, print_start, print_end, c.tile_names[tile], ref_id, par);
+			sink.write_record(g, seg, s.id, id_len, s.seq, s.qual, par.read_length);
+		}
+		sink.pair_done(g);
+	}
+}
+
+// Simulator::SimulateFromGivenBlock without variants / methylation
+template<class G, class Sink>
+RSQ_HD void simulate_block(const G &g, const SimCtx &c, const Scratch &s, Sink &sink, const BlockDesc &b,
+                           unsigned long long *scan_draws){
+	Mt mt; mt.s = s.mt; mt.idx = kMtN;
+	mt_seed(g, mt, b.seed);
+	const uint32_t L = c.seq_len[b.ref_id];
+	const uint64_t off = c.seq_off[b.ref_id];
+	const uint32_t group = c.coverage_group[b.ref_id];
+	const double *thr = c.thr + static_cast<size_t>(group) * c.insert_to * 2;
+	const uint64_t *thr_int = c.thr_int + static_cast<size_t>(group) * c.insert_to;
+	const double *binom_p0 = c.binom_p0 + static_cast<size_t>(group) * c.insert_to;
+	const uint32_t *gcp = c.gc_prefix + off + b.ref_id;
+	uint64_t read_number = 0;
+	unsigned long long draws = 0;
+	uint32_t end = b.start_pos + 1000u;
+	if(end > L){ end = L; }
+	for(uint32_t pos = b.start_pos; pos < end; ++pos){
+		uint32_t len = c.insert_from;
+		while(len < c.insert_to){
+			if(mt.idx >= kMtN){ mt_regen(g, mt); }
+			uint32_t n = c.insert_to - len;
+			if(n > static_cast<uint32_t>(G::kSize)){ n = G::kSize; }
+			if(n > static_cast<uint32_t>(kMtN - mt.idx)){ n = kMtN - mt.idx; }
+			const uint32_t lane = g.lane();
+			uint64_t x = 0;
+			bool hit = false;
+			if(lane < n){
+				x = mt_temper(mt.s[mt.idx + lane]);
+				hit = x >= thr_int[len + lane];
+			}
+			const unsigned mask = g.ballot(hit);
+			if(mask == 0){
+				mt.idx += n; len += n; draws += n;
+				continue;
+			}
+#if defined(__CUDA_ARCH__)
+			const uint32_t first = __ffs(mask) - 1;
+#else
+			const uint32_t first = 0;
+#endif
+			const uint32_t fragment_length = len + first;
+			x = mt_temper(mt.s[mt.idx + first]);
+			mt.idx += first + 1; len = fragment_length + 1; draws += first + 1;
+
+			const double probability_chosen = canonical(x);
+			const double thr0 = thr[2 * fragment_length], thr1 = thr[2 * fragment_length + 1];
+			if(!(probability_chosen >= thr1)){ continue; }   // exact ProbabilityAboveThreshold
+			// DrawNumberNonZeroStrands: Binomial(2*#alleles, 1-thr0, u)
+			const uint32_t non_zero_strands = binomial_count(2, sub_rn(1.0, thr0), binom_p0[fragment_length], probability_chosen);
+			if(!non_zero_strands){ continue; }
+			// ChooseAlleles with possible_strands == 2
+			uint32_t chosen[2]; uint32_t n_chosen;
+			if(non_zero_strands <= 1){
+				const double rv = mt_uniform(g, mt);
+				chosen[0] = static_cast<uint32_t>(mul_rn(rv, 2.0)) & 0xffffu;   // SelectAllele with nothing chosen yet
+				n_chosen = 1;
+			}
+			else{
+				chosen[0] = 0; chosen[1] = 1; n_chosen = 2;
+			}
+			for(uint32_t ci = 0; ci < n_chosen; ++ci){
+				const bool strand = chosen[ci] & 1u;
+				const uint32_t cur_end = pos + fragment_length;
+				if(cur_end < L){
+					const uint32_t gc_perc = percent_u32(gcp[cur_end] - gcp[pos], fragment_length);
+					const double rv = mt_uniform(g, mt);
+					const double adjusted_random = add_rn(thr0, mul_rn(rv, sub_rn(1.0, thr0)));
+					bool runaway = false;
+					const uint32_t counts = fragment_counts(c, b.ref_id, fragment_length, gc_perc, c.sur_start[off + pos], c.sur_end[off + cur_end - 1], adjusted_random, runaway);
+					if(runaway && g.lane() == 0){ *c.error_flag |= kErrCountRunaway; }
+					if(counts){
+						create_reads(g, c, s, mt, sink, counts, strand, b.ref_id, fragment_length, read_number, b.block_id, pos, cur_end);
+					}
+				}
+			}
+		}
+	}
+	if(scan_draws && g.lane() == 0){ *scan_draws = draws; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Systematic errors (master stream).  One chain = Simulator::SetSystematicErrors over [begin,end) of a
+// strand, starting from `state`; raw[] holds the two pre-generated master draws of every position.
+// ---------------------------------------------------------------------------------------------------
+struct SysState {
+	uint32_t distance;     // distance_to_start_of_error_region_
+	uint32_t start_rate;   // start_error_rate_
+};
+
+// strand base at coordinate p of a chain (forward: ref[p]; reverse: complement of ref[L-1-p]; adapter: seq[p])
+RSQ_HD uint32_t chain_base(const uint8_t *seq, uint32_t L, bool reverse, uint32_t p){
+	return reverse ? 3u - seq[L - 1 - p] : seq[p];
+}
+
+// utilities::DominantBase state right before position p is drawn == after Update at p-1
+// (utilities.hpp:229-293): counts over the previous min(p,5) bases, ties -> base closest to p.
+RSQ_HD uint32_t dominant_before(const uint8_t *seq, uint32_t L, bool reverse, uint32_t p, uint32_t carried){
+	if(p == 0){ return carried; }
+	uint32_t cnt[4] = {0, 0, 0, 0};
+	const uint32_t lo = p > 5 ? p - 5 : 0;
+	for(uint32_t q = lo; q < p; ++q){ ++cnt[chain_base(seq, L, reverse, q)]; }
+	uint32_t mx = cnt[0];
+	for(int b = 1; b < 4; ++b){ if(cnt[b] > mx){ mx = cnt[b]; } }
+	uint32_t q = p;
+	uint32_t base;
+	do{ base = chain_base(seq, L, reverse, --q); }while(cnt[base] != mx);
+	return base;
+}
+
+// raw draw k (0: dominant error, 1: error rate) of chain coordinate p.  Reverse-strand and adapter chains own a
+// contiguous run of the master stream (2 draws per base); the forward strand is interleaved with one block
+// seed per 1000 bases (Simulator::CreateBlock draws the seed, then the block's 2*1000 values).
+RSQ_HD uint64_t chain_raw(const uint64_t *raw, bool seed_interleaved, uint32_t p, uint32_t k){
+	const size_t i = seed_interleaved ? static_cast<size_t>(p / 1000u) * 2001u + 1u + 2u * (p % 1000u) + k : 2u * static_cast<size_t>(p) + k;
+	return raw[i];
+}
+
+template<class G>
+RSQ_HD SysState sys_error_chain(const G &g, const Tables &tab, double *prob, const uint8_t *seq, uint32_t L, bool reverse,
+                                uint32_t begin, uint32_t end, SysState st, uint32_t carried_dom, uint32_t sys_gc_range, uint32_t reset_distance,
+                                const uint64_t *raw, bool seed_interleaved, uint8_t *out /* indexed by chain coordinate; null: warm-up only */){
+	// GC window state before `begin` (Simulator::UpdateGC): previous min(begin, range) bases
+	uint32_t gc_bases = begin < sys_gc_range ? begin : sys_gc_range;
+	uint32_t gc = 0;
+	for(uint32_t q = begin - gc_bases; q < begin; ++q){
+		const uint32_t b = chain_base(seq, L, reverse, q);
+		gc += (b == 1 || b == 2) ? 1u : 0u;
+	}
+	uint32_t last_base = begin ? chain_base(seq, L, reverse, begin - 1) : 4u;
+	bool zero;
+	for(uint32_t p = begin; p < end; ++p){
+		const uint32_t ref_base = chain_base(seq, L, reverse, p);
+		const uint32_t dom_base = dominant_before(seq, L, reverse, p, carried_dom);
+		const uint32_t gc_percent = gc_bases ? percent_u16(gc, gc_bases) : 50u;
+		const uint32_t dist = (st.distance + 9) / 10;
+		const double u1 = canonical(chain_raw(raw, seed_interleaved, p, 0));
+		const double u2 = canonical(chain_raw(raw, seed_interleaved, p, 1));
+		uint32_t dom_error = draw(g, tab, tab.dom_error(ref_base, last_base, dom_base), dist, gc_percent, st.start_rate, 0, u1, prob, zero);
+		if(zero){ dom_error = 4; }
+		uint32_t error_rate = draw(g, tab, tab.error_rate(ref_base, dom_error), dist, gc_percent, st.start_rate, 0, u2, prob, zero);
+		if(zero){ error_rate = 0; }
+		error_rate &= 0xffu;
+		if(out && g.lane() == 0){
+			out[2 * static_cast<size_t>(p)] = static_cast<uint8_t>(dom_error);
+			out[2 * static_cast<size_t>(p) + 1] = static_cast<uint8_t>(error_rate);
+		}
+		last_base = ref_base;
+		// CoverageStats::UpdateDistances (CoverageStats.cpp:379-396)
+		if(st.distance){
+			if(st.start_rate < error_rate){ st.distance = 0; st.start_rate = error_rate; }
+			else if(++st.distance >= reset_distance){ st.distance = 0; st.start_rate = 0; }
+		}
+		else if(error_rate){ st.distance = 1; st.start_rate = error_rate; }
+		// UpdateGC
+		if(ref_base == 1 || ref_base == 2){ ++gc; }
+		if(gc_bases < sys_gc_range){ ++gc_bases; }
+		else{
+			const uint32_t ob = chain_base(seq, L, reverse, p - gc_bases);
+			if(ob == 1 || ob == 2){ --gc; }
+		}
+	}
+	return st;
+}
+
+}  // namespace rsq

@@ -1,0 +1,283 @@
+// TEST HARNESS (not part of the product): runs the lane-group templates of reseq_b200/csrc/*.cuh with a
+// one-lane group on the CPU, so that their logic can be checked against the reference-built oracle without
+// a GPU.  The shipped library never contains or calls this; the GPU tests check the very same templates
+// instantiated for 32-lane warps.
+//
+//   twin <stage.flat from oracle/_ref/dump_tables sim> <seed> <out_prefix> [max_blocks]
+// Recomputes: ReplaceN'd reference (taken from the dump), surroundings bias + normalisation + thresholds,
+// master stream -> adapter / reverse / forward systematic errors + block seeds, then simulates every block
+// and writes <out_prefix>_1.fq / _2.fq.  Prints mismatches against the dump's stage values.
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include "../../reseq_b200/csrc/host_profile.hpp"
+#include "../../reseq_b200/csrc/sim_core.cuh"
+#include "../../reseq_b200/csrc/bias_core.cuh"
+
+using namespace rsq;
+
+struct StringSink {
+	std::string out[2];
+	uint64_t pairs = 0;
+	template<class G> void write_record(const G &, uint32_t seg, const char *id, int id_len, const uint8_t *seq, const uint8_t *qual, uint32_t n){
+		std::string &o = out[seg];
+		o += '@'; o.append(id, id_len); o += '\n';
+		for(uint32_t i = 0; i < n; ++i){ o += "ACGTN"[seq[i] > 4 ? 4 : seq[i]]; }
+		o += "\n+\n";
+		o.append(reinterpret_cast<const char *>(qual), n);
+		o += '\n';
+	}
+	template<class G> void pair_done(const G &){ ++pairs; }
+};
+
+struct DeviceLikeStorage {   // owns everything SimCtx points to
+	std::vector<TableDesc> desc; std::vector<double> blob; std::vector<uint32_t> par0;
+	std::vector<double> cps;  // all discrete cumulative arrays
+	std::vector<Discrete> start_cut[2]; std::vector<uint32_t> start_cut_from[2], adapter_off[2];
+	std::vector<uint8_t> adapter_seq, adapter_sys;
+	std::vector<double> il_bias, gc_bias;
+	std::vector<uint64_t> insert_lengths, seq_off; std::vector<uint32_t> seq_len, gc_prefix, name_off;
+	std::vector<uint8_t> ref, sys_fwd, sys_rev;
+	std::vector<double> sur_start, sur_end;
+	std::string names;
+	std::vector<uint16_t> tile_names;
+	std::vector<uint32_t> rlbf_row_from[2], rlbf_row_off[2]; std::vector<uint64_t> rlbf_val[2];
+	uint32_t error_flag = 0;
+	uint32_t max_n0 = 0;
+};
+
+static Discrete add_cp(DeviceLikeStorage &st, std::vector<std::vector<double>> &keep, const std::vector<double> &cp){
+	keep.push_back(cp);
+	Discrete d; d.n = cp.size(); d.cp = keep.back().data();
+	(void)st;
+	return d;
+}
+
+int main(int argc, char **argv){
+	if(argc < 4){ fprintf(stderr, "usage: twin <stage.flat> <seed> <out_prefix> [max_blocks]\n"); return 2; }
+	FlatFile f; f.load(argv[1]);
+	const uint64_t seed = strtoull(argv[2], nullptr, 10);
+	const std::string prefix = argv[3];
+	const size_t max_blocks = argc > 4 ? strtoull(argv[4], nullptr, 10) : static_cast<size_t>(-1);
+	Profile p; p.from_flat(f);
+	int bad = 0;
+
+	// ---- reference (already N-replaced by the oracle dump) ----
+	Genome g;
+	for(size_t s = 0; f.has("sim.ref." + std::to_string(s)); ++s){
+		const auto &a = f.get("sim.ref." + std::to_string(s));
+		g.seqs.emplace_back(a.as<uint8_t>(), a.as<uint8_t>() + a.count);
+		g.ids.push_back("synth" + std::to_string(s + 1) + " synthetic contig");
+	}
+	DeviceLikeStorage st;
+	std::vector<std::vector<double>> cp_keep; cp_keep.reserve(4096);
+	SimCtx c{};
+	// tables
+	for(const auto &h : p.tables){
+		TableDesc d{}; d.n0 = h.par0.size(); d.nm = h.nm;
+		for(uint32_t n = 0; n < h.nm; ++n){ d.from[n] = h.from[n]; d.span[n] = h.to[n] - h.from[n]; d.off[n] = st.blob.size(); st.blob.insert(st.blob.end(), h.dim2[n].begin(), h.dim2[n].end()); }
+		d.par0_off = st.par0.size(); st.par0.insert(st.par0.end(), h.par0.begin(), h.par0.end());
+		st.desc.push_back(d);
+		if(d.n0 > st.max_n0){ st.max_n0 = d.n0; }
+	}
+	const uint32_t T = p.num_tiles;
+	c.tab.desc = st.desc.data(); c.tab.blob = st.blob.data(); c.tab.par0 = st.par0.data(); c.tab.num_tiles = T;
+	c.tab.quality_base = 0; c.tab.seqq_base = 8 * T; c.tab.basecall_base = 10 * T; c.tab.domerr_base = 50 * T;
+	c.tab.errrate_base = 50 * T + 100; c.tab.indel_base = 50 * T + 120;
+	c.phred_offset = p.phred_quality_offset; c.max_len_deletion = p.max_len_deletion;
+	c.insert_from = std::max<uint64_t>(1, p.insert_lengths.from); c.insert_to = p.insert_lengths.to();
+	for(int seg = 0; seg < 2; ++seg){
+		c.read_len_from[seg] = p.read_lengths[seg].from; c.read_len_to[seg] = p.read_lengths[seg].to(); c.read_len_count[seg] = p.read_lengths[seg].size();
+		const auto &rl = p.read_lengths_by_fragment_length[seg];
+		c.rlbf_from[seg] = rl.from; c.rlbf_to[seg] = rl.to();
+		st.rlbf_row_off[seg].push_back(0);
+		for(const auto &row : rl.v){ st.rlbf_row_from[seg].push_back(row.from); st.rlbf_val[seg].insert(st.rlbf_val[seg].end(), row.v.begin(), row.v.end()); st.rlbf_row_off[seg].push_back(st.rlbf_val[seg].size()); }
+		c.rlbf_row_from[seg] = st.rlbf_row_from[seg].data(); c.rlbf_row_off[seg] = st.rlbf_row_off[seg].data(); c.rlbf_val[seg] = st.rlbf_val[seg].data();
+	}
+	st.insert_lengths.assign(c.insert_to, 0); st.il_bias.assign(c.insert_to, 0.0); st.gc_bias.assign(101, 0.0);
+	for(uint32_t i = 0; i < c.insert_to; ++i){ st.insert_lengths[i] = p.insert_lengths[i]; st.il_bias[i] = p.insert_lengths_bias[i]; }
+	for(uint32_t i = 0; i < 101; ++i){ st.gc_bias[i] = p.gc_fragment_content_bias[i]; }
+	c.insert_lengths = st.insert_lengths.data(); c.il_bias = st.il_bias.data(); c.gc_bias = st.gc_bias.data();
+	c.num_tiles = p.tiles.size(); st.tile_names = p.tiles; c.tile_names = st.tile_names.data();
+	c.tile_pick = add_cp(st, cp_keep, discrete_cp(p.tile_abundance.begin(), p.tile_abundance.end()));
+	c.polya_pick = add_cp(st, cp_keep, discrete_cp(p.polya_tail_length.v.begin(), p.polya_tail_length.v.end()));
+	c.polya_from = p.polya_tail_length.from;
+	c.overrun_pick = add_cp(st, cp_keep, discrete_cp(p.overrun_bases.begin(), p.overrun_bases.end() - 1));
+	for(int seg = 0; seg < 2; ++seg){
+		st.adapter_off[seg].push_back(st.adapter_seq.size());
+		for(size_t a = 0; a < p.adapter_seqs[seg].size(); ++a){
+			for(char ch : p.adapter_seqs[seg][a]){ st.adapter_seq.push_back(Genome::code(ch) & 3); }
+			st.adapter_off[seg].push_back(st.adapter_seq.size());
+			st.start_cut[seg].push_back(add_cp(st, cp_keep, discrete_cp(p.adapter_start_cut[seg][a].v.begin(), p.adapter_start_cut[seg][a].v.end())));
+			st.start_cut_from[seg].push_back(p.adapter_start_cut[seg][a].from);
+		}
+	}
+	st.adapter_sys.assign(2 * st.adapter_seq.size(), 0);
+	for(int seg = 0; seg < 2; ++seg){
+		c.adapters[seg].n = p.adapter_seqs[seg].size(); c.adapters[seg].off = st.adapter_off[seg].data();
+		c.adapters[seg].pick = add_cp(st, cp_keep, discrete_cp(p.adapter_significant_count[seg].begin(), p.adapter_significant_count[seg].end()));
+		c.adapters[seg].start_cut = st.start_cut[seg].data(); c.adapters[seg].start_cut_from = st.start_cut_from[seg].data();
+	}
+	c.adapter_seq = st.adapter_seq.data(); c.adapter_sys = st.adapter_sys.data();
+	c.ref_seq_bias = p.ref_seq_bias.data(); c.disp_a = p.dispersion_parameters[0]; c.disp_b = p.dispersion_parameters[1];
+	// reference arrays
+	c.n_seqs = g.seqs.size();
+	uint64_t total = 0;
+	st.name_off.push_back(0);
+	for(size_t s = 0; s < g.seqs.size(); ++s){
+		st.seq_off.push_back(total); st.seq_len.push_back(g.seqs[s].size()); total += g.seqs[s].size();
+		st.ref.insert(st.ref.end(), g.seqs[s].begin(), g.seqs[s].end());
+		st.names += g.first_part(s); st.name_off.push_back(st.names.size());
+	}
+	// gc_prefix of sequence s occupies L+1 entries starting at seq_off[s]+s
+	st.gc_prefix.resize(total + g.seqs.size() + 1);
+	for(size_t s = 0; s < g.seqs.size(); ++s){
+		uint32_t *gp = st.gc_prefix.data() + st.seq_off[s] + s;
+		uint32_t acc = 0; gp[0] = 0;
+		for(size_t i = 0; i < g.seqs[s].size(); ++i){ uint8_t b = g.seqs[s][i]; acc += (b == 1 || b == 2); gp[i + 1] = acc; }
+	}
+	st.sur_start.assign(total, 0.0); st.sur_end.assign(total, 0.0);
+	for(size_t s = 0; s < g.seqs.size(); ++s){
+		const uint8_t *seq = g.seqs[s].data(); const uint32_t L = g.seqs[s].size();
+		for(uint32_t pos = 0; pos < L; ++pos){
+			uint32_t code[3];
+			forward_surrounding(seq, L, pos, code);
+			st.sur_start[st.seq_off[s] + pos] = surrounding_bias(p.fragment_surroundings_bias[0].data(), p.fragment_surroundings_bias[1].data(), p.fragment_surroundings_bias[2].data(), code);
+			reverse_surrounding(seq, L, pos, code);
+			st.sur_end[st.seq_off[s] + pos] = surrounding_bias(p.fragment_surroundings_bias[0].data(), p.fragment_surroundings_bias[1].data(), p.fragment_surroundings_bias[2].data(), code);
+		}
+	}
+	c.seq_off = st.seq_off.data(); c.seq_len = st.seq_len.data(); c.ref = st.ref.data(); c.gc_prefix = st.gc_prefix.data();
+	c.sur_start = st.sur_start.data(); c.sur_end = st.sur_end.data();
+	c.name_blob = st.names.data(); c.name_off = st.name_off.data();
+	c.base_id = "ReseqRead"; c.base_id_len = 9;
+	c.max_read_len = std::max(c.read_len_to[0], c.read_len_to[1]); c.max_org_len = c.max_read_len + c.max_len_deletion + 64;
+	c.error_flag = &st.error_flag;
+
+	// ---- normalisation (CalculateBiasNormalization) ----
+	const uint64_t total_pairs = f.scalar_i("sim.total_pairs");
+	Spline spline;
+	if(!spline.get_sample_positions(p.insert_lengths)){ fprintf(stderr, "no sample positions\n"); return 1; }
+	std::vector<BiasParam> params;
+	for(uint32_t r = p.ref_seq_bias.size(); r--; ){
+		if(0.0 != p.ref_seq_bias[r]){
+			for(auto fl : spline.sample_positions){ if(fl <= g.seqs[r].size()){ params.push_back({r, fl}); } }
+		}
+	}
+	std::vector<double> sums(params.size()), maxb(params.size(), 0.0);
+	for(size_t i = 0; i < params.size(); ++i){
+		const uint32_t r = params[i].ref_id, fl = params[i].fragment_length;
+		double mx = 0.0;
+		sums[i] = sum_bias_chain(c.sur_start + st.seq_off[r], c.sur_end + st.seq_off[r], c.gc_prefix + st.seq_off[r] + r, g.seqs[r].size(), fl,
+		                         p.ref_seq_bias[r] * p.insert_lengths_bias[fl], c.gc_bias, mx);
+		maxb[i] = mx;
+	}
+	Normalization norm;
+	finish_normalization(norm, p, spline, params, sums, maxb, total_pairs);
+	{
+		const double ref_norm = f.scalar_d("sim.bias_normalization");
+		if(ref_norm != norm.bias_normalization){ printf("MISMATCH bias_normalization: oracle %a twin %a\n", ref_norm, norm.bias_normalization); ++bad; }
+		for(uint32_t grp = 0; grp < norm.num_groups; ++grp){
+			auto rt = f.vec_f64("sim.thresholds." + std::to_string(grp));
+			size_t nbad = 0;
+			for(size_t i = 0; i < rt.size(); ++i){ if(rt[i] != norm.thresholds[static_cast<size_t>(grp) * c.insert_to * 2 + i]){ if(nbad < 3){ printf("MISMATCH threshold[%u][%zu]: %a vs %a\n", grp, i, rt[i], norm.thresholds[static_cast<size_t>(grp) * c.insert_to * 2 + i]); } ++nbad; } }
+			if(nbad){ printf("MISMATCH thresholds group %u: %zu entries\n", grp, nbad); ++bad; }
+		}
+	}
+	c.bias_normalization = norm.bias_normalization; c.coverage_group = norm.coverage_groups.data();
+	c.thr = norm.thresholds.data(); c.thr_int = norm.thr_int.data(); c.binom_p0 = norm.binom_p0.data();
+
+	// ---- master stream ----
+	const uint32_t sys_gc_range = f.scalar_i("sim.sys_gc_range");
+	{
+		uint64_t reads = 0, sum_len = 0;
+		for(int seg = 2; seg--; ){ for(auto len = p.read_lengths[seg].from; len < p.read_lengths[seg].to(); ++len){ reads += p.read_lengths[seg][len]; sum_len += p.read_lengths[seg][len] * len; } }
+		const uint32_t mine = ((sum_len + reads / 2) / reads) / 2;
+		if(mine != sys_gc_range){ printf("MISMATCH sys_gc_range %u vs %u\n", mine, sys_gc_range); ++bad; }
+	}
+	std::mt19937_64 master(seed);
+	SingleLane lane;
+	std::vector<double> prob(st.max_n0 + 2);
+	uint32_t carried = 0;
+	for(int seg = 2; seg--; ){
+		for(size_t a = p.adapter_count_sum[seg].size(); a--; ){
+			if(!p.adapter_count_sum[seg][a]){ continue; }
+			const uint32_t off = st.adapter_off[seg][a], len = st.adapter_off[seg][a + 1] - off;
+			std::vector<uint64_t> raw(2 * len);
+			for(auto &r : raw){ r = master(); }
+			sys_error_chain(lane, c.tab, prob.data(), st.adapter_seq.data() + off, len, false, 0, len, SysState{0, 0}, carried, sys_gc_range, p.reset_distance, raw.data(), false, st.adapter_sys.data() + 2 * off);
+			carried = dominant_before(st.adapter_seq.data() + off, len, false, len, carried);
+			const auto &ra = f.get("sim.adapter_sys_error." + std::to_string(seg) + "." + std::to_string(a));
+			if(ra.count != 2 * len || memcmp(ra.as<uint8_t>(), st.adapter_sys.data() + 2 * off, 2 * len) != 0){ printf("MISMATCH adapter sys error seg %d adapter %zu\n", seg, a); ++bad; }
+		}
+	}
+	st.sys_fwd.assign(2 * total, 0); st.sys_rev.assign(2 * total, 0);
+	std::vector<BlockDesc> blocks;
+	uint32_t next_block_id = 1;
+	for(size_t s = 0; s < g.seqs.size(); ++s){
+		const uint32_t L = g.seqs[s].size();
+		if(L < c.insert_to){ continue; }
+		const uint32_t nb = (L + 999) / 1000;
+		std::vector<uint64_t> raw(2 * static_cast<size_t>(nb) + 4 * static_cast<size_t>(L));
+		for(auto &r : raw){ r = master(); }
+		const uint8_t *seq = g.seqs[s].data();
+		SysState end_rev = sys_error_chain(lane, c.tab, prob.data(), seq, L, true, 0, L, SysState{0, 0}, carried, sys_gc_range, p.reset_distance, raw.data() + nb, false, st.sys_rev.data() + 2 * st.seq_off[s]);
+		(void)end_rev;
+		carried = dominant_before(seq, L, true, L, carried);
+		sys_error_chain(lane, c.tab, prob.data(), seq, L, false, 0, L, SysState{0, 0}, carried, sys_gc_range, p.reset_distance, raw.data() + nb + 2 * static_cast<size_t>(L), true, st.sys_fwd.data() + 2 * st.seq_off[s]);
+		carried = dominant_before(seq, L, false, L, carried);
+		for(uint32_t b = 0; b < nb; ++b){
+			BlockDesc d{}; d.ref_id = s; d.start_pos = b * 1000; d.block_id = next_block_id++; d.seed = raw[nb + 2 * static_cast<size_t>(L) + static_cast<size_t>(b) * 2001];
+			blocks.push_back(d);
+		}
+	}
+	c.sys_fwd = st.sys_fwd.data(); c.sys_rev = st.sys_rev.data();
+	{
+		const auto &rs = f.get("sim.block_seed"); const auto &rf = f.get("sim.sys_fwd"); const auto &rr = f.get("sim.sys_rev");
+		size_t nb = std::min<size_t>(rs.count, blocks.size()), sb = 0;
+		for(size_t i = 0; i < nb; ++i){ if(rs.as<uint64_t>()[i] != blocks[i].seed){ ++sb; } }
+		if(sb || rs.count != blocks.size()){ printf("MISMATCH block seeds: %zu of %zu differ (oracle %" PRIu64 " blocks, twin %zu)\n", sb, nb, rs.count, blocks.size()); ++bad; }
+		// oracle dump: forward errors concatenated block by block (= position order); reverse errors per forward block interval in reverse-strand order
+		size_t fb = 0;
+		for(size_t i = 0; i < std::min<size_t>(rf.count, st.sys_fwd.size()); ++i){ if(rf.as<uint8_t>()[i] != st.sys_fwd[i]){ if(fb < 5){ printf("  sys_fwd diff at byte %zu: oracle %u twin %u\n", i, rf.as<uint8_t>()[i], st.sys_fwd[i]); } ++fb; } }
+		if(fb || rf.count != st.sys_fwd.size()){ printf("MISMATCH sys_fwd: %zu bytes differ\n", fb); ++bad; }
+		size_t rb = 0, ri = 0;
+		for(const auto &bd : blocks){
+			const uint32_t L = st.seq_len[bd.ref_id]; const uint32_t e = std::min(bd.start_pos + 1000, L);
+			for(uint32_t q = L - e; q < L - bd.start_pos; ++q){
+				for(int k = 0; k < 2; ++k, ++ri){
+					if(ri < rr.count && rr.as<uint8_t>()[ri] != st.sys_rev[2 * (st.seq_off[bd.ref_id] + q) + k]){ ++rb; }
+				}
+			}
+		}
+		if(rb || ri != rr.count){ printf("MISMATCH sys_rev: %zu bytes differ (%zu vs %" PRIu64 ")\n", rb, ri, rr.count); ++bad; }
+	}
+
+	// ---- simulate ----
+	std::vector<unsigned char> scratch_mem(scratch_bytes(st.max_n0, c.max_org_len, c.max_read_len));
+	Scratch s = carve_scratch(scratch_mem.data(), st.max_n0, c.max_org_len, c.max_read_len);
+	StringSink sink;
+	FILE *o1 = fopen((prefix + "_1.fq").c_str(), "wb"), *o2 = fopen((prefix + "_2.fq").c_str(), "wb");
+	size_t nsim = std::min(max_blocks, blocks.size());
+	unsigned long long total_draws = 0;
+	for(size_t i = 0; i < nsim; ++i){
+		unsigned long long d = 0;
+		simulate_block(lane, c, s, sink, blocks[i], &d);
+		total_draws += d;
+		fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
+		sink.out[0].clear(); sink.out[1].clear();
+	}
+	const int64_t n_adapter_only = f.scalar_i("sim.num_adapter_only_pairs");
+	if(n_adapter_only && nsim == blocks.size()){
+		Mt mt; mt.s = s.mt; mt.idx = kMtN;
+		mt_seed(lane, mt, master());
+		uint64_t read_number = 0;
+		create_reads(lane, c, s, mt, sink, n_adapter_only, false, 0, 0, read_number, 0, 0, 0);
+		fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
+	}
+	fclose(o1); fclose(o2);
+	printf("blocks=%zu pairs=%" PRIu64 " scan_draws=%llu error_flag=%u stage_mismatches=%d\n", nsim, sink.pairs, total_draws, st.error_flag, bad);
+	return bad ? 1 : 0;
+}
