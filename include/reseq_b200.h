@@ -1,0 +1,104 @@
+/* reseq_b200 -- C ABI of the B200 engine for ReSeq's per-read simulation hot path.
+ *
+ * The reference (schmeing/ReSeq, C++) has no FFI; its seam is the Simulator class
+ * (reseq/Simulator.h:456-458).  Every entry point below names the reference interface it stands in for, so a
+ * maintainer can bind it from reseq/main.cpp.  Plain pointers and sizes only; functions
+ * return 0 on success (or a handle / NULL), never throw, and leave a message for rsq_last_error().
+ * There is no CPU fallback: engine creation fails when no CUDA device is usable.
+ */
+#ifndef RESEQ_B200_H
+#define RESEQ_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rsq_profile rsq_profile;     /* DataStats + ProbabilityEstimates state the simulation reads */
+typedef struct rsq_reference rsq_reference; /* reseq::Reference: ids + Dna5 sequences */
+typedef struct rsq_engine rsq_engine;       /* one CUDA device: tables, reference, systematic errors, output arena */
+
+/* printErr-style diagnostics of the last failing call on this thread (reportingUtils.hpp:262-273) */
+const char *rsq_last_error(void);
+int rsq_device_count(void);
+
+/* --- profile -------------------------------------------------------------------------------------
+ * rsq_profile_load: DataStats::Load + PrepareProcessing (DataStats.cpp:1280-1328) and
+ * ProbabilityEstimates::Load + PrepareResult (ProbabilityEstimates.cpp:961-1045) for a converged profile;
+ * stats_path = X.reseq, ipf_path = X.reseq.ipf.
+ * rsq_profile_load_flat / rsq_profile_save_flat: the same state as a binary cache (RSQFLAT1). */
+rsq_profile *rsq_profile_load(const char *stats_path, const char *ipf_path);
+rsq_profile *rsq_profile_load_flat(const char *flat_path);
+int rsq_profile_save_flat(const rsq_profile *profile, const char *flat_path);
+void rsq_profile_free(rsq_profile *profile);
+
+/* --- reference -----------------------------------------------------------------------------------
+ * Reference::ReadFasta (Reference.cpp:758-811): IUPAC text -> Dna5 (ACGT/acgt/U -> 0..3, anything else N). */
+rsq_reference *rsq_reference_load_fasta(const char *fasta_path);
+rsq_reference *rsq_reference_from_memory(uint32_t n_seqs, const char *const *ids, const char *const *bases, const uint64_t *lengths);
+uint64_t rsq_reference_total_size(const rsq_reference *ref);       /* Reference::TotalSize */
+uint32_t rsq_reference_num_sequences(const rsq_reference *ref);    /* Reference::NumberSequences */
+void rsq_reference_free(rsq_reference *ref);
+
+/* --- simulation ----------------------------------------------------------------------------------
+ * Arguments of Simulator::Simulate (Simulator.h:457) that this revision supports. */
+typedef struct rsq_sim_options {
+	uint64_t seed;                 /* uintSeed seed */
+	double coverage;               /* 0 = DataStats::CorrectedCoverage() */
+	uint64_t num_read_pairs;       /* 0 = derive from coverage */
+	int32_t ref_bias_model;        /* RefSeqBiasSimulation: 0 kKeep, 1 kNo (kDraw / kFile: not yet) */
+	const char *record_base_identifier; /* NULL/"" = "ReseqRead" */
+	/* sharding (one engine per GPU): simulate forward blocks [shard_index*n/shard_count, ...) of the run;
+	 * shard_count 0 or 1 = whole run.  Block seeds and systematic errors are identical in every shard. */
+	uint32_t shard_index;
+	uint32_t shard_count;
+} rsq_sim_options;
+
+typedef struct rsq_sim_report {
+	uint64_t total_pairs_aim;      /* total_pairs_ after removing adapter-only pairs */
+	uint64_t adapter_only_pairs;   /* num_adapter_only_pairs_ */
+	uint64_t pairs;                /* read pairs written by this engine (shard) */
+	uint64_t bytes[2];             /* FASTQ bytes of first / second reads */
+	uint64_t blocks;               /* SimBlocks simulated by this engine */
+	uint64_t blocks_total;         /* SimBlocks of the run (incl. the look-ahead blocks the reference never simulates) */
+	uint64_t positions;            /* reference positions scanned */
+	uint64_t scan_draws;           /* mt19937_64 draws consumed by the (position, fragment length) scan */
+	double bias_normalization;
+	uint32_t syserr_passes;        /* speculative passes of the systematic-error chains */
+	uint32_t kernel_launches;      /* launches of this library's kernels during prepare + simulate */
+	/* device time in milliseconds (CUDA events on the engine's stream) */
+	float ms_upload, ms_bias, ms_syserr, ms_simulate, ms_gather, ms_download;
+} rsq_sim_report;
+
+rsq_engine *rsq_engine_create(const rsq_profile *profile, int device);
+void rsq_engine_destroy(rsq_engine *engine);
+
+/* Simulator::Simulate prologue (Simulator.cpp:2687-2826): ReplaceN, UpdateRefSeqBias, pair counts,
+ * CalculateBiasNormalization, adapter + genome systematic errors, block seeds.  Copies `ref`; uploads to HBM. */
+int rsq_engine_prepare(rsq_engine *engine, const rsq_reference *ref, const rsq_sim_options *opt, rsq_sim_report *report);
+/* SimulationThread / SimulateFromGivenBlock / CreateReads over this shard's blocks (Simulator.cpp:2249-2401).
+ * FASTQ text ends up device-resident, ordered like the reference's 1-thread run. */
+int rsq_engine_simulate(rsq_engine *engine, rsq_sim_report *report);
+/* Copies the FASTQ text of segment 0 (first reads) / 1 (second reads) to engine-owned pinned host memory. */
+int rsq_engine_download(rsq_engine *engine, rsq_sim_report *report);
+int rsq_engine_output(const rsq_engine *engine, int segment, const char **data, uint64_t *bytes);
+/* Output()/Flush() (Simulator.cpp:114-230): append the downloaded text to the two files. */
+int rsq_engine_write(const rsq_engine *engine, const char *first_reads_path, const char *second_reads_path);
+
+/* Drop-in for `bool Simulator::Simulate(R1, R2, ref, stats, estimates, ...)`: prepare + simulate + download +
+ * write on device `device`; on failure the output files are removed like the reference does (Simulator.cpp:2888-2893). */
+int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq_sim_options *opt, int device,
+                 const char *first_reads_path, const char *second_reads_path, rsq_sim_report *report);
+
+/* Drop-in for `bool Simulator::SimulateErrorModelOnly(out, in, stats, estimates, threads, seed)`
+ * (Simulator.cpp:2900-3014): FASTA records "<id> <1|2>;<fraglen>;<dom-err>;<err-rate>" -> FASTQ. */
+int rsq_apply_error_model(rsq_engine *engine, const char *fasta_in_path, const char *fastq_out_path, uint64_t seed, rsq_sim_report *report);
+
+/* Stage introspection for parity tests: copies a named device/host array ("sys_fwd", "sys_rev", "adapter_sys",
+ * "block_seed", "thresholds", "sur_start", "sur_end", "reference") into dst (up to capacity bytes). */
+int rsq_engine_fetch(const rsq_engine *engine, const char *name, void *dst, uint64_t capacity, uint64_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -8,6 +8,7 @@
 //     have per-stage ground truth (Simulator::Simulate prologue, Simulator.cpp:2687-2826).
 //
 //   dump_tables profile <stats.reseq> <out.flat>                      profile + LogArrayResult tables
+//   dump_tables patch <in.reseq> <out.reseq> <seed>                    synthetic GC / surroundings / dispersion biases
 //   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat>   + normalisation, thresholds, seeds, sys-errors
 //
 // Private members are reached by re-declaring access for this translation unit only.
@@ -194,6 +195,25 @@ int main(int argc, char **argv){
 		if(!LoadAll(stats, est, argv[2])){ return 1; }
 		FlatWriter w(argv[3]);
 		DumpProfile(w, stats, est);
+		return 0;
+	}
+	if(mode == "patch" && argc >= 5){
+		// Replace the (failed / uniform) bias fit of a tiny synthetic data set by a deterministic non-trivial one and
+		// write the profile back with the reference's own DataStats::Save, so that the fragment-count model
+		// (GC spline values, surroundings, dispersion) is exercised by the parity tests.
+		DataStats stats(NULL);
+		if(!stats.Load(argv[2])){ return 1; }
+		std::mt19937_64 gen(std::stoull(argv[4]));
+		auto &fd = stats.fragment_distribution_;
+		for(uint32_t gc = 0; gc <= 100; ++gc){
+			double x = (static_cast<double>(gc) - 48.0) / 22.0;
+			fd.gc_fragment_content_bias_[gc] = std::round((0.15 + 1.6 * std::exp(-x * x)) * 256.0) / 256.0;
+		}
+		std::array<double, 4*Surrounding::Length()> separated;
+		for(auto &v : separated){ v = (static_cast<double>(gen() % 17) - 8.0) / 16.0; }
+		fd.fragment_surroundings_bias_.CombinePositions(separated);
+		fd.dispersion_parameters_ = {{0.25, 0.75}};
+		if(!stats.Save(argv[3])){ return 1; }
 		return 0;
 	}
 	if(mode == "sim" && argc >= 7){

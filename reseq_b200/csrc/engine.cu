@@ -1,0 +1,1146 @@
+// CUDA engine behind include/reseq_b200.h: kernels (sm_100a) + host orchestration of the Simulate() path.
+//
+// Device data layout (all in HBM, per engine):
+//   tables      TableDesc[] + FP64 blob + par0 (every LogArrayResult, ~1-7 MB: L2 resident)
+//   reference   1 byte / base (Dna codes after ReplaceN), concatenated sequences
+//   gc_prefix   u32 / base (+1 per sequence)          -> fragment GC in O(1)
+//   sur_start, sur_end  f64 / base                    -> SurroundingBias::Bias per fragment end
+//   sys_fwd, sys_rev    2 bytes / base / strand       -> (dominant error, rate) of SetSystematicErrors
+//   master      raw mt19937_64 outputs of one SimUnit (2*blocks + 4*L words), reused per sequence
+//   blocks      BlockDesc[] (seed, ref, start, id)
+//   arena       fixed-size chunks of FASTQ text, per (block, segment) chains; gathered into two
+//               contiguous buffers in block order, then copied to pinned host memory.
+// Kernels: k_surroundings, k_sum_bias, k_master_stream, k_sys_chunks (+k_sys_check), k_adapter_sys,
+//          k_build_blocks, k_simulate (warp per SimBlock), k_block_offsets, k_gather, k_error_model.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../../include/reseq_b200.h"
+#include "host_profile.hpp"
+#include "sim_core.cuh"
+#include "bias_core.cuh"
+#include "archive_reader.hpp"
+
+namespace rsq {
+
+static thread_local std::string g_last_error;
+static void set_error(const char *fmt, ...){
+	char buf[2048];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+	g_last_error = buf;
+}
+
+#define RSQ_CUDA(call) do{ cudaError_t e_ = (call); if(e_ != cudaSuccess){ throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); } }while(0)
+
+template<class T> struct DevBuf {
+	T *p = nullptr; size_t n = 0;
+	DevBuf() = default;
+	DevBuf(const DevBuf &) = delete; DevBuf &operator=(const DevBuf &) = delete;
+	~DevBuf(){ release(); }
+	void release(){ if(p){ cudaFree(p); p = nullptr; n = 0; } }
+	void alloc(size_t count){ release(); if(count){ RSQ_CUDA(cudaMalloc(&p, count * sizeof(T))); } n = count; }
+	void upload(const std::vector<T> &v, cudaStream_t s){ alloc(v.size()); if(v.size()){ RSQ_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s)); } }
+	void upload(const T *v, size_t count, cudaStream_t s){ alloc(count); if(count){ RSQ_CUDA(cudaMemcpyAsync(p, v, count * sizeof(T), cudaMemcpyHostToDevice, s)); } }
+	void zero(cudaStream_t s){ if(n){ RSQ_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); } }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kNone = 0xffffffffu;
+constexpr int kWarpsPerCta = 4;
+
+__global__ void k_surroundings(const uint8_t *seq, uint32_t L, const double *t0, const double *t1, const double *t2,
+                               double *sur_start, double *sur_end){
+	const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+	if(pos >= L){ return; }
+	uint32_t code[3];
+	forward_surrounding(seq, L, pos, code);
+	sur_start[pos] = surrounding_bias(t0, t1, t2, code);
+	reverse_surrounding(seq, L, pos, code);
+	sur_end[pos] = surrounding_bias(t0, t1, t2, code);
+}
+
+struct BiasParamDev { uint32_t ref_id, fragment_length; double general; };
+
+__global__ void k_sum_bias(const BiasParamDev *params, uint32_t n_params, const uint64_t *seq_off, const uint32_t *seq_len,
+                           const double *sur_start, const double *sur_end, const uint32_t *gc_prefix, const double *gc_bias,
+                           double *sums, double *max_bias){
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_params){ return; }
+	const BiasParamDev p = params[i];
+	const uint64_t off = seq_off[p.ref_id];
+	double mx = 0.0;
+	sums[i] = sum_bias_chain(sur_start + off, sur_end + off, gc_prefix + off + p.ref_id, seq_len[p.ref_id], p.fragment_length, p.general, gc_bias, mx);
+	max_bias[i] = mx;
+}
+
+// Serial continuation of the master mt19937_64: state[0..311] + state[312] = index, `n` outputs appended to out.
+__global__ void k_master_stream(uint64_t *state, uint64_t *out, uint64_t n){
+	__shared__ uint64_t s[kMtN];
+	WarpGroup g;
+	for(int i = threadIdx.x; i < kMtN; i += 32){ s[i] = state[i]; }
+	Mt mt; mt.s = s; mt.idx = static_cast<int>(state[kMtN]);
+	__syncwarp();
+	uint64_t done = 0;
+	while(done < n){
+		if(mt.idx >= kMtN){ mt_regen(g, mt); }
+		uint64_t take = kMtN - mt.idx;
+		if(take > n - done){ take = n - done; }
+		for(uint64_t i = threadIdx.x; i < take; i += 32){ out[done + i] = mt_temper(s[mt.idx + i]); }
+		mt.idx += static_cast<int>(take);
+		done += take;
+	}
+	__syncwarp();
+	for(int i = threadIdx.x; i < kMtN; i += 32){ state[i] = s[i]; }
+	if(threadIdx.x == 0){ state[kMtN] = static_cast<uint64_t>(mt.idx); }
+}
+
+__global__ void k_master_seed(uint64_t *state, uint64_t seed){
+	if(threadIdx.x == 0 && blockIdx.x == 0){
+		uint64_t x = seed;
+		state[0] = x;
+		for(int i = 1; i < kMtN; ++i){ x = 6364136223846793005ull * (x ^ (x >> 62)) + static_cast<uint64_t>(i); state[i] = x; }
+		state[kMtN] = kMtN;
+	}
+}
+
+struct SysChain {
+	const uint8_t *seq; uint32_t L; uint32_t reverse; const uint64_t *raw; uint32_t seed_interleaved; uint8_t *out; uint32_t carried_dom; uint32_t pad;
+};
+struct SysChunk {
+	uint32_t chain; uint32_t begin; uint32_t end; uint32_t warm_from;
+	uint32_t in_dist, in_rate, out_dist, out_rate;
+	uint32_t dirty; uint32_t first_of_chain; uint32_t pad0, pad1;
+};
+
+__global__ void k_sys_chunks(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_t n_chunks, uint32_t max_n0,
+                             uint32_t sys_gc_range, uint32_t reset_distance){
+	extern __shared__ double prob_all[];
+	WarpGroup g;
+	const uint32_t warp = threadIdx.x >> 5;
+	double *prob = prob_all + static_cast<size_t>(warp) * ((max_n0 + 1) & ~1u);
+	const uint32_t c = blockIdx.x * (blockDim.x >> 5) + warp;
+	if(c >= n_chunks){ return; }
+	SysChunk ck = chunks[c];
+	if(!ck.dirty){ return; }
+	const SysChain ch = chains[ck.chain];
+	SysState st{ck.in_dist, ck.in_rate};
+	if(ck.warm_from < ck.begin){
+		st = sys_error_chain(g, tab, prob, ch.seq, ch.L, ch.reverse != 0, ck.warm_from, ck.begin, SysState{0, 0}, ch.carried_dom, sys_gc_range, reset_distance, ch.raw, ch.seed_interleaved != 0, nullptr);
+		if(g.lane() == 0){ chunks[c].in_dist = st.distance; chunks[c].in_rate = st.start_rate; chunks[c].warm_from = ck.begin; }
+	}
+	st = sys_error_chain(g, tab, prob, ch.seq, ch.L, ch.reverse != 0, ck.begin, ck.end, st, ch.carried_dom, sys_gc_range, reset_distance, ch.raw, ch.seed_interleaved != 0, ch.out);
+	if(g.lane() == 0){ chunks[c].out_dist = st.distance; chunks[c].out_rate = st.start_rate; chunks[c].dirty = 0; }
+}
+
+// After a pass: a chunk whose assumed start state differs from its predecessor's end state must be redone.
+__global__ void k_sys_check(SysChunk *chunks, uint32_t n_chunks, uint32_t *n_dirty){
+	const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= n_chunks || chunks[c].first_of_chain){ return; }
+	const SysChunk prev = chunks[c - 1];
+	SysChunk &me = chunks[c];
+	if(me.in_dist != prev.out_dist || me.in_rate != prev.out_rate){
+		me.in_dist = prev.out_dist; me.in_rate = prev.out_rate; me.dirty = 1;
+		atomicAdd(n_dirty, 1u);
+	}
+}
+
+__global__ void k_build_blocks(BlockDesc *blocks, uint32_t first, uint32_t nb, uint32_t ref_id, uint32_t first_block_id, const uint64_t *fwd_raw){
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if(b >= nb){ return; }
+	BlockDesc d; d.ref_id = ref_id; d.start_pos = b * 1000u; d.block_id = first_block_id + b; d.pad = 0;
+	d.seed = fwd_raw[static_cast<size_t>(b) * 2001u];
+	blocks[first + b] = d;
+}
+
+struct Arena {
+	unsigned char *data; uint32_t chunk_bytes; uint32_t n_chunks;
+	uint32_t *next_free; uint32_t *chunk_next; uint32_t *chunk_used; uint32_t *error_flag;
+};
+
+struct DeviceSink {
+	Arena a;
+	uint32_t cur[2], used[2], head[2];
+	unsigned long long bytes[2];
+	uint32_t pairs;
+	__device__ void init(const Arena &arena){ a = arena; cur[0] = cur[1] = kNone; used[0] = used[1] = 0; head[0] = head[1] = kNone; bytes[0] = bytes[1] = 0; pairs = 0; }
+	__device__ void write_record(const WarpGroup &g, uint32_t seg, const char *id, int id_len, const uint8_t *seq, const uint8_t *qual, uint32_t n){
+		const uint32_t rec = 1u + id_len + 1u + n + 3u + n + 1u;
+		if(rec > a.chunk_bytes){ if(g.lane() == 0){ atomicOr(a.error_flag, kErrRecordTooLong); } return; }
+		if(cur[seg] == kNone || used[seg] + rec > a.chunk_bytes){
+			uint32_t idx = kNone;
+			if(g.lane() == 0){
+				idx = atomicAdd(a.next_free, 1u);
+				if(idx >= a.n_chunks){ atomicOr(a.error_flag, kErrArenaFull); idx = kNone; }
+				else{
+					a.chunk_next[idx] = kNone; a.chunk_used[idx] = 0;
+					if(cur[seg] != kNone){ a.chunk_next[cur[seg]] = idx; }
+				}
+			}
+			idx = __shfl_sync(0xffffffffu, idx, 0);
+			if(idx == kNone){ return; }
+			if(cur[seg] == kNone){ head[seg] = idx; }
+			cur[seg] = idx; used[seg] = 0;
+		}
+		unsigned char *dst = a.data + static_cast<size_t>(cur[seg]) * a.chunk_bytes + used[seg];
+		const uint32_t o_seq = 2u + id_len, o_plus = o_seq + n, o_qual = o_plus + 3u;
+		for(uint32_t i = g.lane(); i < rec; i += 32){
+			unsigned char ch;
+			if(i == 0){ ch = '@'; }
+			else if(i < 1u + id_len){ ch = static_cast<unsigned char>(id[i - 1]); }
+			else if(i < o_seq){ ch = '\n'; }
+			else if(i < o_plus){ const uint8_t b = seq[i - o_seq]; ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'G' : b == 3 ? 'T' : 'N'; }
+			else if(i < o_qual){ ch = (i == o_plus + 1u) ? '+' : '\n'; }
+			else if(i < o_qual + n){ ch = qual[i - o_qual]; }
+			else{ ch = '\n'; }
+			dst[i] = ch;
+		}
+		used[seg] += rec; bytes[seg] += rec;
+		if(g.lane() == 0){ a.chunk_used[cur[seg]] = used[seg]; }
+		g.sync();
+	}
+	__device__ void pair_done(const WarpGroup &){ ++pairs; }
+};
+
+struct BlockOut { uint32_t head[2]; unsigned long long bytes[2]; uint32_t pairs; uint32_t pad; unsigned long long scan_draws; };
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_simulate(SimCtx c, const BlockDesc *blocks, uint32_t first_block, uint32_t n_blocks, Arena arena, BlockOut *out, uint32_t *next_block,
+           uint32_t max_n0, uint32_t scratch_per_warp){
+	extern __shared__ __align__(16) unsigned char smem[];
+	WarpGroup g;
+	const uint32_t warp = threadIdx.x >> 5;
+	Scratch s = carve_scratch(smem + static_cast<size_t>(warp) * scratch_per_warp, max_n0, c.max_org_len, c.max_read_len);
+	while(true){
+		uint32_t i = 0;
+		if(g.lane() == 0){ i = atomicAdd(next_block, 1u); }
+		i = __shfl_sync(0xffffffffu, i, 0);
+		if(i >= n_blocks){ break; }
+		DeviceSink sink; sink.init(arena);
+		unsigned long long draws = 0;
+		const BlockDesc b = blocks[first_block + i];
+		simulate_block(g, c, s, sink, b, &draws);
+		draws = __shfl_sync(0xffffffffu, draws, 0);
+		if(g.lane() == 0){
+			BlockOut o; o.head[0] = sink.head[0]; o.head[1] = sink.head[1]; o.bytes[0] = sink.bytes[0]; o.bytes[1] = sink.bytes[1];
+			o.pairs = sink.pairs; o.pad = 0; o.scan_draws = draws;
+			out[i] = o;
+		}
+	}
+}
+
+// Adapter-only pairs (Simulator::SimulateAdapterOnlyPairs): one stream, one warp, appended as slot `slot`.
+__global__ void k_adapter_only(SimCtx c, uint64_t seed, uint32_t count, Arena arena, BlockOut *out, uint32_t slot, uint32_t max_n0){
+	extern __shared__ __align__(16) unsigned char smem[];
+	WarpGroup g;
+	Scratch s = carve_scratch(smem, max_n0, c.max_org_len, c.max_read_len);
+	DeviceSink sink; sink.init(arena);
+	Mt mt; mt.s = s.mt; mt.idx = kMtN;
+	mt_seed(g, mt, seed);
+	uint64_t read_number = 0;
+	create_reads(g, c, s, mt, sink, count, false, 0, 0, read_number, 0, 0, 0);
+	if(g.lane() == 0){
+		BlockOut o; o.head[0] = sink.head[0]; o.head[1] = sink.head[1]; o.bytes[0] = sink.bytes[0]; o.bytes[1] = sink.bytes[1];
+		o.pairs = sink.pairs; o.pad = 0; o.scan_draws = 0;
+		out[slot] = o;
+	}
+}
+
+// Exclusive prefix sums of the per-slot byte counts (one CTA; slots <= a few million).
+__global__ void k_block_offsets(const BlockOut *out, uint32_t n, unsigned long long *offsets /*[2][n+1]*/, unsigned long long *totals /*[4]: bytes0, bytes1, pairs, draws*/){
+	__shared__ unsigned long long part[4][1024];
+	const uint32_t t = threadIdx.x, nt = blockDim.x;
+	const uint32_t per = (n + nt - 1) / nt;
+	const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+	unsigned long long s0 = 0, s1 = 0, sp = 0, sd = 0;
+	for(uint32_t i = lo; i < hi; ++i){ s0 += out[i].bytes[0]; s1 += out[i].bytes[1]; sp += out[i].pairs; sd += out[i].scan_draws; }
+	part[0][t] = s0; part[1][t] = s1; part[2][t] = sp; part[3][t] = sd;
+	__syncthreads();
+	if(t == 0){
+		unsigned long long a0 = 0, a1 = 0, ap = 0, ad = 0;
+		for(uint32_t k = 0; k < nt; ++k){
+			unsigned long long v0 = part[0][k], v1 = part[1][k];
+			part[0][k] = a0; part[1][k] = a1; a0 += v0; a1 += v1; ap += part[2][k]; ad += part[3][k];
+		}
+		totals[0] = a0; totals[1] = a1; totals[2] = ap; totals[3] = ad;
+		offsets[n] = a0; offsets[(n + 1) + n] = a1;
+	}
+	__syncthreads();
+	unsigned long long a0 = part[0][t], a1 = part[1][t];
+	for(uint32_t i = lo; i < hi; ++i){
+		offsets[i] = a0; offsets[(n + 1) + i] = a1;
+		a0 += out[i].bytes[0]; a1 += out[i].bytes[1];
+	}
+}
+
+__global__ void k_gather(const BlockOut *out, uint32_t n, Arena arena, const unsigned long long *offsets, unsigned char *dst0, unsigned char *dst1){
+	const uint32_t slot = blockIdx.x >> 1, seg = blockIdx.x & 1u;
+	if(slot >= n){ return; }
+	unsigned char *dst = (seg ? dst1 : dst0) + offsets[static_cast<size_t>(seg) * (n + 1) + slot];
+	uint32_t chunk = out[slot].head[seg];
+	while(chunk != kNone){
+		const uint32_t used = arena.chunk_used[chunk];
+		const unsigned char *src = arena.data + static_cast<size_t>(chunk) * arena.chunk_bytes;
+		for(uint32_t i = threadIdx.x; i < used; i += blockDim.x){ dst[i] = src[i]; }
+		dst += used;
+		chunk = arena.chunk_next[chunk];
+	}
+}
+
+// seqToIllumina: one warp per batch of records (Simulator::ErrorModelOnlyThread + ApplyErrorsAndQualityToFastaInput)
+struct EmRecord { uint64_t seq_off; uint32_t len; uint32_t seg; uint32_t fragment_length; uint32_t id_off; uint32_t id_len; uint32_t pad; };
+
+struct EmSink {
+	DeviceSink inner;
+	__device__ void write_record(const WarpGroup &g, uint32_t, const char *id, int id_len, const uint8_t *seq, const uint8_t *qual, uint32_t n){ inner.write_record(g, 0, id, id_len, seq, qual, n); }
+};
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_error_model(SimCtx c, const EmRecord *recs, uint32_t n_recs, uint32_t batch_size, const uint64_t *batch_seeds, uint32_t n_batches,
+              const uint8_t *seqs, const uint8_t *sdom, const uint8_t *srate, const char *ids, Arena arena, BlockOut *out, uint32_t *next_batch,
+              uint32_t max_n0, uint32_t scratch_per_warp){
+	extern __shared__ __align__(16) unsigned char smem[];
+	WarpGroup g;
+	const uint32_t warp = threadIdx.x >> 5;
+	Scratch s = carve_scratch(smem + static_cast<size_t>(warp) * scratch_per_warp, max_n0, c.max_org_len, c.max_read_len);
+	while(true){
+		uint32_t bi = 0;
+		if(g.lane() == 0){ bi = atomicAdd(next_batch, 1u); }
+		bi = __shfl_sync(0xffffffffu, bi, 0);
+		if(bi >= n_batches){ break; }
+		DeviceSink sink; sink.init(arena);
+		Mt mt; mt.s = s.mt; mt.idx = kMtN;
+		mt_seed(g, mt, batch_seeds[bi]);
+		const uint32_t lo = bi * batch_size, hi = min(n_recs, lo + batch_size);
+		for(uint32_t r = lo; r < hi; ++r){
+			const EmRecord rec = recs[r];
+			uint32_t org_len = rec.len;
+			if(org_len > c.max_org_len){ org_len = c.max_org_len; if(g.lane() == 0){ atomicOr(c.error_flag, kErrOrgOverflow); } }
+			g.sync();
+			for(uint32_t i = g.lane(); i < org_len; i += 32){
+				s.org[i] = seqs[rec.seq_off + i]; s.sdom[i] = sdom[rec.seq_off + i]; s.srate[i] = srate[rec.seq_off + i];
+			}
+			g.sync();
+			uint32_t tile = 0;
+			if(1 < c.num_tiles){ tile = discrete_draw(g, mt, c.tile_pick); }
+			ReadState par;
+			fill_read(g, c, s, mt, par, rec.seg, tile, rec.fragment_length, org_len);
+			// id + " " + cigar + " E" + errors
+			int n = 0;
+			n = put_str(g, s.id, n, kIdCap, ids + rec.id_off, rec.id_len);
+			n = put_char(g, s.id, n, kIdCap, ' ');
+			n = put_str(g, s.id, n, kIdCap, s.cigar, par.cigar_len < kCigarCap ? par.cigar_len : kCigarCap);
+			n = put_str(g, s.id, n, kIdCap, " E", 2);
+			n = put_uint(g, s.id, n, kIdCap, par.num_errors);
+			if(n > kIdCap){ if(g.lane() == 0){ atomicOr(c.error_flag, kErrRecordTooLong); } n = kIdCap; }
+			g.sync();
+			sink.write_record(g, 0, s.id, n, s.seq, s.qual, par.read_length);
+			sink.pair_done(g);
+		}
+		if(g.lane() == 0){
+			BlockOut o; o.head[0] = sink.head[0]; o.head[1] = kNone; o.bytes[0] = sink.bytes[0]; o.bytes[1] = 0; o.pairs = sink.pairs; o.pad = 0; o.scan_draws = 0;
+			out[bi] = o;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct PinnedBuf {
+	char *p = nullptr; size_t cap = 0;
+	~PinnedBuf(){ if(p){ cudaFreeHost(p); } }
+	void ensure(size_t n){ if(n > cap){ if(p){ cudaFreeHost(p); p = nullptr; } RSQ_CUDA(cudaMallocHost(&p, n ? n : 1)); cap = n; } }
+};
+
+struct EventTimer {
+	cudaEvent_t a, b; cudaStream_t s;
+	explicit EventTimer(cudaStream_t st) : s(st){ cudaEventCreate(&a); cudaEventCreate(&b); }
+	~EventTimer(){ cudaEventDestroy(a); cudaEventDestroy(b); }
+	void start(){ cudaEventRecord(a, s); }
+	float stop(){ cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+}  // namespace rsq
+
+using namespace rsq;
+
+struct rsq_profile { Profile p; };
+struct rsq_reference { Genome g; };
+
+struct rsq_engine {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	Profile prof;
+	uint32_t max_n0 = 0;
+	uint32_t launches = 0;
+	// tables + profile on device
+	DevBuf<TableDesc> d_desc; DevBuf<double> d_blob; DevBuf<uint32_t> d_par0;
+	DevBuf<double> d_cp; DevBuf<Discrete> d_start_cut[2]; DevBuf<uint32_t> d_start_cut_from[2], d_adapter_off[2];
+	DevBuf<uint8_t> d_adapter_seq, d_adapter_sys;
+	DevBuf<double> d_il_bias, d_gc_bias, d_ref_seq_bias, d_sur_tab[3];
+	DevBuf<uint64_t> d_insert_lengths;
+	DevBuf<uint16_t> d_tile_names;
+	DevBuf<uint32_t> d_rlbf_row_from[2], d_rlbf_row_off[2]; DevBuf<uint64_t> d_rlbf_val[2];
+	DevBuf<char> d_base_id;
+	DevBuf<uint32_t> d_error_flag;
+	std::vector<uint32_t> h_adapter_off[2];
+	std::vector<uint8_t> h_adapter_seq;
+	SimCtx ctx{};
+	// run state
+	Genome genome;
+	std::vector<double> run_ref_seq_bias;
+	Normalization norm;
+	DevBuf<uint64_t> d_seq_off; DevBuf<uint32_t> d_seq_len, d_gc_prefix, d_name_off, d_cov_group;
+	DevBuf<uint8_t> d_ref, d_sys_fwd, d_sys_rev;
+	DevBuf<double> d_sur_start, d_sur_end, d_thr, d_binom_p0;
+	DevBuf<uint64_t> d_thr_int;
+	DevBuf<char> d_names;
+	DevBuf<uint64_t> d_master_state, d_master;
+	DevBuf<BlockDesc> d_blocks;
+	std::vector<uint64_t> h_seq_off;
+	uint64_t total_size = 0;
+	uint32_t n_blocks_total = 0, n_blocks_sim = 0, shard_first = 0, shard_n = 0;
+	bool shard_has_adapter_only = false;
+	uint64_t adapter_only_seed = 0;
+	uint64_t total_pairs = 0, adapter_only_pairs = 0;
+	uint32_t sys_gc_range = 0, syserr_passes = 0;
+	bool prepared = false;
+	// output
+	DevBuf<unsigned char> d_arena, d_out[2];
+	DevBuf<uint32_t> d_chunk_next, d_chunk_used, d_next_free, d_next_block;
+	DevBuf<BlockOut> d_block_out;
+	DevBuf<unsigned long long> d_offsets, d_totals;
+	uint64_t out_bytes[2] = {0, 0};
+	uint64_t out_pairs = 0, out_draws = 0;
+	PinnedBuf h_out[2];
+	bool downloaded = false;
+
+	~rsq_engine(){ if(stream){ cudaStreamDestroy(stream); } }
+};
+
+namespace rsq {
+
+static const uint32_t kChunkBytes = 4096;
+
+static void upload_profile(rsq_engine &e){
+	const Profile &p = e.prof;
+	cudaStream_t s = e.stream;
+	std::vector<TableDesc> desc; std::vector<double> blob; std::vector<uint32_t> par0;
+	e.max_n0 = 0;
+	for(const auto &h : p.tables){
+		TableDesc d{}; d.n0 = h.par0.size(); d.nm = h.nm;
+		for(uint32_t n = 0; n < h.nm; ++n){ d.from[n] = h.from[n]; d.span[n] = h.to[n] - h.from[n]; d.off[n] = blob.size(); blob.insert(blob.end(), h.dim2[n].begin(), h.dim2[n].end()); }
+		d.par0_off = par0.size(); par0.insert(par0.end(), h.par0.begin(), h.par0.end());
+		desc.push_back(d);
+		e.max_n0 = std::max(e.max_n0, d.n0);
+	}
+	e.d_desc.upload(desc, s); e.d_blob.upload(blob, s); e.d_par0.upload(par0, s);
+	SimCtx &c = e.ctx;
+	const uint32_t T = p.num_tiles;
+	c.tab.desc = e.d_desc.p; c.tab.blob = e.d_blob.p; c.tab.par0 = e.d_par0.p; c.tab.num_tiles = T;
+	c.tab.quality_base = 0; c.tab.seqq_base = 8 * T; c.tab.basecall_base = 10 * T; c.tab.domerr_base = 50 * T;
+	c.tab.errrate_base = 50 * T + 100; c.tab.indel_base = 50 * T + 120;
+	c.phred_offset = p.phred_quality_offset; c.max_len_deletion = p.max_len_deletion;
+	c.insert_from = std::max<uint64_t>(1, p.insert_lengths.from); c.insert_to = p.insert_lengths.to();
+
+	// discrete distributions: all cumulative arrays in one device buffer
+	std::vector<double> cps;
+	struct Pending { Discrete *target; size_t off; uint32_t n; };
+	std::vector<Discrete> sc[2];
+	auto add = [&](const std::vector<double> &cp) -> std::pair<size_t, uint32_t> { size_t off = cps.size(); cps.insert(cps.end(), cp.begin(), cp.end()); return {off, static_cast<uint32_t>(cp.size())}; };
+	auto tile_cp = add(discrete_cp(p.tile_abundance.begin(), p.tile_abundance.end()));
+	auto polya_cp = add(discrete_cp(p.polya_tail_length.v.begin(), p.polya_tail_length.v.end()));
+	auto overrun_cp = add(discrete_cp(p.overrun_bases.begin(), p.overrun_bases.end() - 1));
+	std::pair<size_t, uint32_t> pick_cp[2];
+	std::vector<std::pair<size_t, uint32_t>> sc_cp[2];
+	std::vector<uint32_t> sc_from[2];
+	e.h_adapter_seq.clear();
+	for(int seg = 0; seg < 2; ++seg){
+		pick_cp[seg] = add(discrete_cp(p.adapter_significant_count[seg].begin(), p.adapter_significant_count[seg].end()));
+		e.h_adapter_off[seg].clear();
+		e.h_adapter_off[seg].push_back(e.h_adapter_seq.size());
+		for(size_t a = 0; a < p.adapter_seqs[seg].size(); ++a){
+			for(char ch : p.adapter_seqs[seg][a]){ e.h_adapter_seq.push_back(Genome::code(ch) & 3); }
+			e.h_adapter_off[seg].push_back(e.h_adapter_seq.size());
+			sc_cp[seg].push_back(add(discrete_cp(p.adapter_start_cut[seg][a].v.begin(), p.adapter_start_cut[seg][a].v.end())));
+			sc_from[seg].push_back(p.adapter_start_cut[seg][a].from);
+		}
+	}
+	e.d_cp.upload(cps, s);
+	auto mk = [&](std::pair<size_t, uint32_t> x){ Discrete d; d.cp = e.d_cp.p + x.first; d.n = x.second; return d; };
+	c.tile_pick = mk(tile_cp); c.polya_pick = mk(polya_cp); c.overrun_pick = mk(overrun_cp);
+	c.polya_from = p.polya_tail_length.from;
+	e.d_adapter_seq.upload(e.h_adapter_seq, s);
+	e.d_adapter_sys.alloc(2 * e.h_adapter_seq.size() + 2); e.d_adapter_sys.zero(s);
+	for(int seg = 0; seg < 2; ++seg){
+		for(auto x : sc_cp[seg]){ sc[seg].push_back(mk(x)); }
+		e.d_start_cut[seg].upload(sc[seg], s); e.d_start_cut_from[seg].upload(sc_from[seg], s); e.d_adapter_off[seg].upload(e.h_adapter_off[seg], s);
+		c.adapters[seg].n = p.adapter_seqs[seg].size(); c.adapters[seg].off = e.d_adapter_off[seg].p; c.adapters[seg].pick = mk(pick_cp[seg]);
+		c.adapters[seg].start_cut = e.d_start_cut[seg].p; c.adapters[seg].start_cut_from = e.d_start_cut_from[seg].p;
+		c.read_len_from[seg] = p.read_lengths[seg].from; c.read_len_to[seg] = p.read_lengths[seg].to(); c.read_len_count[seg] = p.read_lengths[seg].size();
+		const auto &rl = p.read_lengths_by_fragment_length[seg];
+		c.rlbf_from[seg] = rl.from; c.rlbf_to[seg] = rl.to();
+		std::vector<uint32_t> row_from, row_off{0}; std::vector<uint64_t> vals;
+		for(const auto &row : rl.v){ row_from.push_back(row.from); vals.insert(vals.end(), row.v.begin(), row.v.end()); row_off.push_back(vals.size()); }
+		e.d_rlbf_row_from[seg].upload(row_from, s); e.d_rlbf_row_off[seg].upload(row_off, s); e.d_rlbf_val[seg].upload(vals, s);
+		c.rlbf_row_from[seg] = e.d_rlbf_row_from[seg].p; c.rlbf_row_off[seg] = e.d_rlbf_row_off[seg].p; c.rlbf_val[seg] = e.d_rlbf_val[seg].p;
+	}
+	c.adapter_seq = e.d_adapter_seq.p; c.adapter_sys = e.d_adapter_sys.p;
+	std::vector<uint64_t> il(c.insert_to, 0); std::vector<double> ilb(c.insert_to, 0.0), gcb(101, 0.0);
+	for(uint32_t i = 0; i < c.insert_to; ++i){ il[i] = p.insert_lengths[i]; ilb[i] = p.insert_lengths_bias[i]; }
+	for(uint32_t i = 0; i < 101; ++i){ gcb[i] = p.gc_fragment_content_bias[i]; }
+	e.d_insert_lengths.upload(il, s); e.d_il_bias.upload(ilb, s); e.d_gc_bias.upload(gcb, s);
+	c.insert_lengths = e.d_insert_lengths.p; c.il_bias = e.d_il_bias.p; c.gc_bias = e.d_gc_bias.p;
+	for(int b = 0; b < 3; ++b){ e.d_sur_tab[b].upload(p.fragment_surroundings_bias[b], s); }
+	c.num_tiles = p.tiles.size(); e.d_tile_names.upload(p.tiles, s); c.tile_names = e.d_tile_names.p;
+	c.disp_a = p.dispersion_parameters[0]; c.disp_b = p.dispersion_parameters[1];
+	c.max_read_len = std::max(c.read_len_to[0], c.read_len_to[1]);
+	uint32_t max_adapter = 0;
+	for(int seg = 0; seg < 2; ++seg){ for(const auto &a : p.adapter_seqs[seg]){ max_adapter = std::max<uint32_t>(max_adapter, a.size()); } }
+	c.max_org_len = std::max(c.max_read_len + c.max_len_deletion, max_adapter) + 8;
+	e.d_error_flag.alloc(1); e.d_error_flag.zero(s);
+	c.error_flag = e.d_error_flag.p;
+	RSQ_CUDA(cudaStreamSynchronize(s));
+}
+
+static uint32_t read_error_flag(rsq_engine &e){
+	uint32_t f = 0;
+	RSQ_CUDA(cudaMemcpyAsync(&f, e.d_error_flag.p, 4, cudaMemcpyDeviceToHost, e.stream));
+	RSQ_CUDA(cudaStreamSynchronize(e.stream));
+	return f;
+}
+
+static std::string describe_flag(uint32_t f){
+	std::string s;
+	if(f & kErrCigarOverflow){ s += "CIGAR text exceeds the per-read buffer; "; }
+	if(f & kErrCountRunaway){ s += "fragment count did not terminate (uintDupCount overflow); "; }
+	if(f & kErrArenaFull){ s += "output arena exhausted; "; }
+	if(f & kErrOrgOverflow){ s += "read or adapter longer than the staged buffers; "; }
+	if(f & kErrRecordTooLong){ s += "FASTQ record longer than an output chunk; "; }
+	return s;
+}
+
+// Systematic errors of a set of chains: speculative chunks + exact fix-up passes.
+static void run_sys_chains(rsq_engine &e, const std::vector<SysChain> &chains, const std::vector<std::pair<uint32_t, uint32_t>> &chain_len_known,
+                           uint32_t chunk_len, uint32_t warmup, uint32_t &passes){
+	std::vector<SysChunk> chunks;
+	for(uint32_t ci = 0; ci < chains.size(); ++ci){
+		const uint32_t L = chain_len_known[ci].first;
+		for(uint32_t b = 0; b < L; b += chunk_len){
+			SysChunk k{}; k.chain = ci; k.begin = b; k.end = std::min(L, b + chunk_len);
+			k.warm_from = b > warmup ? b - warmup : 0; if(b == 0){ k.warm_from = 0; }
+			k.dirty = 1; k.first_of_chain = (b == 0);
+			chunks.push_back(k);
+		}
+	}
+	if(chunks.empty()){ return; }
+	DevBuf<SysChain> d_chains; d_chains.upload(chains, e.stream);
+	DevBuf<SysChunk> d_chunks; d_chunks.upload(chunks, e.stream);
+	DevBuf<uint32_t> d_dirty; d_dirty.alloc(1);
+	const uint32_t n = chunks.size();
+	const int warps = 4;
+	const size_t shmem = static_cast<size_t>(warps) * ((e.max_n0 + 1) & ~1u) * 8;
+	uint32_t dirty = n;
+	passes = 0;
+	while(dirty){
+		k_sys_chunks<<<(n + warps - 1) / warps, warps * 32, shmem, e.stream>>>(e.ctx.tab, d_chains.p, d_chunks.p, n, e.max_n0, e.sys_gc_range, e.prof.reset_distance);
+		d_dirty.zero(e.stream);
+		k_sys_check<<<(n + 255) / 256, 256, 0, e.stream>>>(d_chunks.p, n, d_dirty.p);
+		e.launches += 2;
+		RSQ_CUDA(cudaMemcpyAsync(&dirty, d_dirty.p, 4, cudaMemcpyDeviceToHost, e.stream));
+		RSQ_CUDA(cudaStreamSynchronize(e.stream));
+		RSQ_CUDA(cudaGetLastError());
+		++passes;
+		if(passes > n + 2){ throw std::runtime_error("systematic error chains did not converge"); }
+	}
+}
+
+static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &opt, rsq_sim_report *rep){
+	cudaStream_t s = e.stream;
+	const Profile &p = e.prof;
+	SimCtx &c = e.ctx;
+	EventTimer tm(s);
+	e.prepared = false; e.downloaded = false; e.launches = 0;
+	e.d_error_flag.zero(s);
+
+	// --- host: ReplaceN, ref-seq bias, pair counts (Simulator.cpp:2687-2743) ---
+	e.genome = ref_in;
+	e.genome.replace_n(opt.seed);
+	Genome &g = e.genome;
+	e.run_ref_seq_bias = p.ref_seq_bias;
+	if(opt.ref_bias_model == 1 || e.run_ref_seq_bias.size() != g.seqs.size()){
+		e.run_ref_seq_bias.assign(g.seqs.size(), 1.0);   // kNo, or kKeep falling through on mismatch
+	}
+	else if(opt.ref_bias_model != 0){ throw std::runtime_error("refBias models draw/file are not supported by this revision"); }
+	uint64_t reads = 0, sum_read_length = 0;
+	for(int seg = 2; seg--; ){
+		for(auto len = p.read_lengths[seg].from; len < p.read_lengths[seg].to(); ++len){ reads += p.read_lengths[seg][len]; sum_read_length += p.read_lengths[seg][len] * len; }
+	}
+	const double average_read_length = static_cast<double>(sum_read_length) / reads;
+	e.total_size = g.total_size();
+	const double adapter_part = coverage_prop_lost_from_adapters(p);
+	double coverage = opt.coverage;
+	if(opt.num_read_pairs){ e.total_pairs = opt.num_read_pairs; }
+	else{
+		if(0.0 == coverage){ coverage = p.corrected_coverage; }
+		e.total_pairs = coverage_to_number_pairs(coverage, e.total_size, average_read_length, adapter_part);
+	}
+	e.adapter_only_pairs = std::round(static_cast<double>(e.total_pairs) * p.insert_lengths[0] / (p.total_number_reads / 2));
+	e.total_pairs -= e.adapter_only_pairs;
+	e.sys_gc_range = static_cast<uint32_t>((sum_read_length + reads / 2) / reads) / 2;
+
+	// --- upload reference ---
+	tm.start();
+	std::vector<uint64_t> seq_off; std::vector<uint32_t> seq_len, name_off{0}; std::string names;
+	uint64_t total = 0;
+	for(size_t i = 0; i < g.seqs.size(); ++i){
+		seq_off.push_back(total); seq_len.push_back(g.seqs[i].size()); total += g.seqs[i].size();
+		names += g.first_part(i); name_off.push_back(names.size());
+	}
+	e.h_seq_off = seq_off;
+	std::vector<uint8_t> flat(total);
+	std::vector<uint32_t> gcp(total + g.seqs.size() + 1, 0);
+	for(size_t i = 0; i < g.seqs.size(); ++i){
+		std::memcpy(flat.data() + seq_off[i], g.seqs[i].data(), g.seqs[i].size());
+		uint32_t *gp = gcp.data() + seq_off[i] + i;
+		uint32_t acc = 0; gp[0] = 0;
+		for(size_t k = 0; k < g.seqs[i].size(); ++k){ const uint8_t b = g.seqs[i][k]; acc += (b == 1 || b == 2); gp[k + 1] = acc; }
+	}
+	e.d_ref.upload(flat, s); e.d_gc_prefix.upload(gcp, s);
+	e.d_seq_off.upload(seq_off, s); e.d_seq_len.upload(seq_len, s); e.d_name_off.upload(name_off, s);
+	e.d_names.upload(names.data(), names.size() + 1, s);
+	e.d_ref_seq_bias.upload(e.run_ref_seq_bias, s);
+	std::string base_id = (opt.record_base_identifier && opt.record_base_identifier[0]) ? opt.record_base_identifier : "ReseqRead";
+	e.d_base_id.upload(base_id.data(), base_id.size() + 1, s);
+	c.n_seqs = g.seqs.size(); c.seq_off = e.d_seq_off.p; c.seq_len = e.d_seq_len.p; c.ref = e.d_ref.p; c.gc_prefix = e.d_gc_prefix.p;
+	c.name_blob = e.d_names.p; c.name_off = e.d_name_off.p; c.base_id = e.d_base_id.p; c.base_id_len = base_id.size();
+	c.ref_seq_bias = e.d_ref_seq_bias.p;
+	e.d_sur_start.alloc(total); e.d_sur_end.alloc(total);
+	c.sur_start = e.d_sur_start.p; c.sur_end = e.d_sur_end.p;
+	if(rep){ rep->ms_upload = tm.stop(); } else { tm.stop(); }
+
+	// --- CalculateBiasNormalization: surroundings + per (ref, sampled length) sums on device ---
+	tm.start();
+	for(size_t i = 0; i < g.seqs.size(); ++i){
+		const uint32_t L = g.seqs[i].size();
+		if(!L){ continue; }
+		k_surroundings<<<(L + 255) / 256, 256, 0, s>>>(e.d_ref.p + seq_off[i], L, e.d_sur_tab[0].p, e.d_sur_tab[1].p, e.d_sur_tab[2].p, e.d_sur_start.p + seq_off[i], e.d_sur_end.p + seq_off[i]);
+		++e.launches;
+	}
+	Spline spline;
+	if(!spline.get_sample_positions(p.insert_lengths)){ throw std::runtime_error("Sampling insert lengths did not find at least two usable lengths."); }
+	std::vector<BiasParam> params; std::vector<BiasParamDev> dparams;
+	const std::vector<double> &rsb = e.run_ref_seq_bias;
+	for(uint32_t r = rsb.size(); r--; ){
+		if(0.0 != rsb[r]){
+			for(auto fl : spline.sample_positions){
+				if(fl <= g.seqs[r].size()){ params.push_back({r, fl}); dparams.push_back({r, fl, rsb[r] * p.insert_lengths_bias[fl]}); }
+			}
+		}
+	}
+	std::vector<double> sums(params.size(), 0.0), maxb(params.size(), 0.0);
+	if(!params.empty()){
+		DevBuf<BiasParamDev> d_params; d_params.upload(dparams, s);
+		DevBuf<double> d_sums, d_max; d_sums.alloc(params.size()); d_max.alloc(params.size());
+		k_sum_bias<<<(params.size() + 31) / 32, 32, 0, s>>>(d_params.p, params.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
+		++e.launches;
+		RSQ_CUDA(cudaMemcpyAsync(sums.data(), d_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, s));
+		RSQ_CUDA(cudaMemcpyAsync(maxb.data(), d_max.p, maxb.size() * 8, cudaMemcpyDeviceToHost, s));
+		RSQ_CUDA(cudaStreamSynchronize(s));
+	}
+	if(!finish_normalization(e.norm, p, rsb, spline, params, sums, maxb, e.total_pairs)){ throw std::runtime_error("bias normalisation is zero"); }
+	e.d_thr.upload(e.norm.thresholds, s); e.d_thr_int.upload(e.norm.thr_int, s); e.d_binom_p0.upload(e.norm.binom_p0, s); e.d_cov_group.upload(e.norm.coverage_groups, s);
+	c.thr = e.d_thr.p; c.thr_int = e.d_thr_int.p; c.binom_p0 = e.d_binom_p0.p; c.coverage_group = e.d_cov_group.p; c.bias_normalization = e.norm.bias_normalization;
+	if(rep){ rep->ms_bias = tm.stop(); rep->bias_normalization = e.norm.bias_normalization; } else { tm.stop(); }
+
+	// --- master stream: adapter systematic errors, then per unit reverse strand / seeds / forward strand ---
+	tm.start();
+	e.d_master_state.alloc(kMtN + 1);
+	k_master_seed<<<1, 32, 0, s>>>(e.d_master_state.p, opt.seed); ++e.launches;
+	uint32_t carried = 0;
+	uint32_t passes_total = 0;
+	{
+		std::vector<SysChain> chains; std::vector<std::pair<uint32_t, uint32_t>> lens;
+		uint64_t n_draws = 0;
+		struct Ad { int seg; size_t a; uint64_t raw_off; };
+		std::vector<Ad> order;
+		for(int seg = 2; seg--; ){
+			for(size_t a = p.adapter_count_sum[seg].size(); a--; ){
+				if(!p.adapter_count_sum[seg][a]){ continue; }
+				const uint32_t len = e.h_adapter_off[seg][a + 1] - e.h_adapter_off[seg][a];
+				order.push_back({seg, a, n_draws});
+				n_draws += 2ull * len;
+			}
+		}
+		if(n_draws){
+			e.d_master.alloc(n_draws);
+			k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
+			for(const auto &o : order){
+				const uint32_t off = e.h_adapter_off[o.seg][o.a], len = e.h_adapter_off[o.seg][o.a + 1] - off;
+				SysChain ch{}; ch.seq = e.d_adapter_seq.p + off; ch.L = len; ch.reverse = 0; ch.raw = e.d_master.p + o.raw_off; ch.seed_interleaved = 0;
+				ch.out = e.d_adapter_sys.p + 2 * off; ch.carried_dom = carried;
+				chains.push_back(ch); lens.push_back({len, 0});
+				carried = dominant_before(e.h_adapter_seq.data() + off, len, false, len, carried);
+			}
+			uint32_t passes = 0;
+			run_sys_chains(e, chains, lens, 1u << 30, 0, passes);
+		}
+	}
+	e.d_sys_fwd.alloc(2 * total + 2); e.d_sys_rev.alloc(2 * total + 2);
+	c.sys_fwd = e.d_sys_fwd.p; c.sys_rev = e.d_sys_rev.p;
+	uint64_t max_unit_draws = 0; uint32_t nb_total = 0;
+	for(size_t i = 0; i < g.seqs.size(); ++i){
+		const uint32_t L = g.seqs[i].size();
+		if(L < c.insert_to){ continue; }
+		const uint32_t nb = (L + 999) / 1000;
+		nb_total += nb;
+		max_unit_draws = std::max<uint64_t>(max_unit_draws, 2ull * nb + 4ull * L);
+	}
+	if(!nb_total){ throw std::runtime_error("All reference sequences are too short for simulating."); }
+	e.d_master.alloc(max_unit_draws + 1);
+	e.d_blocks.alloc(nb_total);
+	uint32_t next_block_id = 1, first = 0;
+	for(size_t i = 0; i < g.seqs.size(); ++i){
+		const uint32_t L = g.seqs[i].size();
+		if(L < c.insert_to){ continue; }
+		const uint32_t nb = (L + 999) / 1000;
+		const uint64_t n_draws = 2ull * nb + 4ull * L;
+		k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
+		const uint8_t *hseq = g.seqs[i].data();
+		std::vector<SysChain> chains(2); std::vector<std::pair<uint32_t, uint32_t>> lens{{L, 0}, {L, 0}};
+		chains[0].seq = e.d_ref.p + seq_off[i]; chains[0].L = L; chains[0].reverse = 1; chains[0].raw = e.d_master.p + nb; chains[0].seed_interleaved = 0;
+		chains[0].out = e.d_sys_rev.p + 2 * seq_off[i]; chains[0].carried_dom = carried;
+		carried = dominant_before(hseq, L, true, L, carried);
+		chains[1].seq = e.d_ref.p + seq_off[i]; chains[1].L = L; chains[1].reverse = 0; chains[1].raw = e.d_master.p + nb + 2ull * L; chains[1].seed_interleaved = 1;
+		chains[1].out = e.d_sys_fwd.p + 2 * seq_off[i]; chains[1].carried_dom = carried;
+		carried = dominant_before(hseq, L, false, L, carried);
+		uint32_t passes = 0;
+		run_sys_chains(e, chains, lens, 8192, 1024, passes);
+		passes_total = std::max(passes_total, passes);
+		k_build_blocks<<<(nb + 127) / 128, 128, 0, s>>>(e.d_blocks.p, first, nb, i, next_block_id, e.d_master.p + nb + 2ull * L); ++e.launches;
+		RSQ_CUDA(cudaStreamSynchronize(s));   // d_master is reused by the next unit
+		next_block_id += nb; first += nb;
+	}
+	e.n_blocks_total = nb_total;
+	const uint32_t lookahead = 1 + c.insert_to / 1000;    // blocks the reference creates but never hands to a worker (Simulator.cpp:1298-1303)
+	e.n_blocks_sim = nb_total > lookahead ? nb_total - lookahead : 0;
+	e.adapter_only_seed = 0;
+	if(e.adapter_only_pairs){
+		k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, e.d_master.p, 1); ++e.launches;
+		RSQ_CUDA(cudaMemcpyAsync(&e.adapter_only_seed, e.d_master.p, 8, cudaMemcpyDeviceToHost, s));
+		RSQ_CUDA(cudaStreamSynchronize(s));
+	}
+	e.syserr_passes = passes_total;
+	const uint32_t sc = opt.shard_count ? opt.shard_count : 1, si = opt.shard_index;
+	if(si >= sc){ throw std::runtime_error("shard_index out of range"); }
+	e.shard_first = static_cast<uint64_t>(e.n_blocks_sim) * si / sc;
+	e.shard_n = static_cast<uint64_t>(e.n_blocks_sim) * (si + 1) / sc - e.shard_first;
+	e.shard_has_adapter_only = (si + 1 == sc) && e.adapter_only_pairs;
+	if(rep){ rep->ms_syserr = tm.stop(); } else { tm.stop(); }
+	RSQ_CUDA(cudaGetLastError());
+	const uint32_t flag = read_error_flag(e);
+	if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
+	if(rep){
+		rep->total_pairs_aim = e.total_pairs; rep->adapter_only_pairs = e.adapter_only_pairs; rep->blocks_total = e.n_blocks_total;
+		rep->syserr_passes = e.syserr_passes; rep->kernel_launches = e.launches;
+	}
+	e.prepared = true;
+}
+
+static void setup_arena(rsq_engine &e, Arena &a, uint64_t expected_bytes, uint32_t slots){
+	uint64_t n_chunks = expected_bytes / kChunkBytes + 2ull * slots + 64;
+	e.d_arena.alloc(n_chunks * kChunkBytes);
+	e.d_chunk_next.alloc(n_chunks); e.d_chunk_used.alloc(n_chunks);
+	e.d_next_free.alloc(1); e.d_next_free.zero(e.stream);
+	a.data = e.d_arena.p; a.chunk_bytes = kChunkBytes; a.n_chunks = n_chunks; a.next_free = e.d_next_free.p;
+	a.chunk_next = e.d_chunk_next.p; a.chunk_used = e.d_chunk_used.p; a.error_flag = e.d_error_flag.p;
+}
+
+static void gather(rsq_engine &e, const Arena &a, uint32_t slots, rsq_sim_report *rep){
+	cudaStream_t s = e.stream;
+	EventTimer tm(s);
+	tm.start();
+	e.d_offsets.alloc(2ull * (slots + 1)); e.d_totals.alloc(4);
+	k_block_offsets<<<1, 1024, 0, s>>>(e.d_block_out.p, slots, e.d_offsets.p, e.d_totals.p); ++e.launches;
+	unsigned long long totals[4];
+	RSQ_CUDA(cudaMemcpyAsync(totals, e.d_totals.p, sizeof totals, cudaMemcpyDeviceToHost, s));
+	RSQ_CUDA(cudaStreamSynchronize(s));
+	e.out_bytes[0] = totals[0]; e.out_bytes[1] = totals[1]; e.out_pairs = totals[2]; e.out_draws = totals[3];
+	e.d_out[0].alloc(totals[0] + 1); e.d_out[1].alloc(totals[1] + 1);
+	if(slots){ k_gather<<<2 * slots, 128, 0, s>>>(e.d_block_out.p, slots, a, e.d_offsets.p, e.d_out[0].p, e.d_out[1].p); ++e.launches; }
+	const float ms = tm.stop();
+	if(rep){ rep->ms_gather = ms; }
+	RSQ_CUDA(cudaGetLastError());
+}
+
+static void simulate(rsq_engine &e, rsq_sim_report *rep){
+	if(!e.prepared){ throw std::runtime_error("rsq_engine_prepare has not been called"); }
+	cudaStream_t s = e.stream;
+	SimCtx &c = e.ctx;
+	e.downloaded = false;
+	const uint32_t slots = e.shard_n + (e.shard_has_adapter_only ? 1 : 0);
+	const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, c.max_read_len);
+	const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta;
+	RSQ_CUDA(cudaFuncSetAttribute(k_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
+	RSQ_CUDA(cudaFuncSetAttribute(k_adapter_only, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scratch)));
+	int dev_sms = 0; RSQ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e.device));
+	int ctas_per_sm = 0; RSQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_simulate, kWarpsPerCta * 32, shmem));
+	if(ctas_per_sm < 1){ throw std::runtime_error("k_simulate does not fit on an SM"); }
+	// expected output: this shard's share of the pairs, generously padded
+	const double share = e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0;
+	uint64_t expected = static_cast<uint64_t>((e.total_pairs * share + e.adapter_only_pairs + 1000) * (2.0 * (2.0 * c.max_read_len + 160.0)) * 1.3);
+	float ms_sim = 0;
+	for(int attempt = 0; ; ++attempt){
+		Arena a;
+		setup_arena(e, a, expected, slots);
+		e.d_block_out.alloc(slots + 1);
+		RSQ_CUDA(cudaMemsetAsync(e.d_block_out.p, 0, (slots + 1) * sizeof(BlockOut), s));
+		e.d_next_block.alloc(1); e.d_next_block.zero(s);
+		EventTimer tm(s);
+		tm.start();
+		if(e.shard_n){
+			const uint32_t ctas = std::min<uint32_t>((e.shard_n + kWarpsPerCta - 1) / kWarpsPerCta, dev_sms * ctas_per_sm);
+			k_simulate<<<ctas, kWarpsPerCta * 32, shmem, s>>>(c, e.d_blocks.p, e.shard_first, e.shard_n, a, e.d_block_out.p, e.d_next_block.p, e.max_n0, scratch);
+			++e.launches;
+		}
+		if(e.shard_has_adapter_only){
+			k_adapter_only<<<1, 32, scratch, s>>>(c, e.adapter_only_seed, e.adapter_only_pairs, a, e.d_block_out.p, e.shard_n, e.max_n0);
+			++e.launches;
+		}
+		ms_sim = tm.stop();
+		RSQ_CUDA(cudaGetLastError());
+		const uint32_t flag = read_error_flag(e);
+		if(flag == kErrArenaFull && attempt < 3){
+			expected *= 2; e.d_error_flag.zero(s);
+			continue;
+		}
+		if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
+		gather(e, a, slots, rep);
+		break;
+	}
+	if(rep){
+		rep->ms_simulate = ms_sim; rep->pairs = e.out_pairs; rep->bytes[0] = e.out_bytes[0]; rep->bytes[1] = e.out_bytes[1];
+		rep->blocks = e.shard_n; rep->scan_draws = e.out_draws; rep->kernel_launches = e.launches;
+		uint64_t positions = 0;
+		std::vector<BlockDesc> hb(e.shard_n);
+		if(e.shard_n){ RSQ_CUDA(cudaMemcpy(hb.data(), e.d_blocks.p + e.shard_first, e.shard_n * sizeof(BlockDesc), cudaMemcpyDeviceToHost)); }
+		for(const auto &b : hb){ positions += std::min<uint32_t>(1000, e.genome.seqs[b.ref_id].size() - b.start_pos); }
+		rep->positions = positions;
+	}
+}
+
+static void download(rsq_engine &e, rsq_sim_report *rep){
+	cudaStream_t s = e.stream;
+	EventTimer tm(s);
+	tm.start();
+	for(int seg = 0; seg < 2; ++seg){
+		e.h_out[seg].ensure(e.out_bytes[seg] + 1);
+		if(e.out_bytes[seg]){ RSQ_CUDA(cudaMemcpyAsync(e.h_out[seg].p, e.d_out[seg].p, e.out_bytes[seg], cudaMemcpyDeviceToHost, s)); }
+	}
+	const float ms = tm.stop();
+	if(rep){ rep->ms_download = ms; }
+	e.downloaded = true;
+}
+
+// seqToIllumina host part: FASTA records -> device batches
+static void apply_error_model(rsq_engine &e, const char *in_path, const char *out_path, uint64_t seed, rsq_sim_report *rep){
+	cudaStream_t s = e.stream;
+	const Profile &p = e.prof;
+	SimCtx &c = e.ctx;
+	e.launches = 0; e.d_error_flag.zero(s);
+	// read records (SeqAn FASTA semantics: id = header without '>', sequence = DnaString: non-ACGTU -> A)
+	std::ifstream f(in_path);
+	if(!f){ throw std::runtime_error(std::string("Could not open '") + in_path + "' for reading."); }
+	std::vector<std::string> ids; std::vector<std::string> seqs;
+	{
+		std::string line;
+		while(std::getline(f, line)){
+			if(!line.empty() && line.back() == '\r'){ line.pop_back(); }
+			if(!line.empty() && line[0] == '>'){ ids.push_back(line.substr(1)); seqs.emplace_back(); }
+			else if(!seqs.empty()){ for(char ch : line){ if(ch != ' ' && ch != '\t'){ seqs.back().push_back(ch); } } }
+		}
+	}
+	if(ids.empty()){ throw std::runtime_error(std::string(in_path) + " does not contain any sequences."); }
+	std::vector<EmRecord> recs(ids.size());
+	std::vector<uint8_t> hseq, hdom, hrate; std::string hid;
+	uint32_t max_len = 0;
+	for(size_t i = 0; i < ids.size(); ++i){
+		const std::string &id = ids[i]; const size_t L = seqs[i].size();
+		if(id.size() <= 2 * L + 2){ throw std::runtime_error("Read description is too short to contain systematic error information and a sequence id: " + id); }
+		size_t end_pos = id.size() - 2 * L - 3;
+		if(';' != id[end_pos + 1] || ';' != id[end_pos + 2 + L]){ throw std::runtime_error("The two systematic error entries are not separated by a semicolon from themselves or the rest of the ReSeq information: " + id); }
+		EmRecord r{}; r.seq_off = hseq.size(); r.len = L;
+		for(size_t pos = 0; pos < L; ++pos){
+			hseq.push_back(Genome::code(seqs[i][pos]) & 3);
+			hdom.push_back(Genome::code(id[end_pos + 2 + pos]));
+			uint8_t rate = static_cast<uint8_t>(id[id.size() - L + pos] - 33);
+			if(86 < rate){ rate += rate - 86; }
+			hrate.push_back(rate);
+		}
+		while(end_pos && ' ' != id[end_pos]){ --end_pos; }
+		if(0 == end_pos){ throw std::runtime_error("No sequence id found that is separated by a space from the ReSeq information: " + id); }
+		r.id_off = hid.size(); r.id_len = end_pos; hid.append(id, 0, end_pos);
+		if('1' == id[end_pos + 1]){ r.seg = 0; }
+		else if('2' == id[end_pos + 1]){ r.seg = 1; }
+		else{ throw std::runtime_error(std::string("Template segment is ") + id[end_pos + 1] + " not 1 or 2: " + id); }
+		if(';' != id[end_pos + 2]){ throw std::runtime_error("The template segment and fragment length are not separated by a semicolon: " + id); }
+		const std::string fl = id.substr(end_pos + 3, id.size() - 2 * L - 2 - (end_pos + 3));
+		size_t used = 0; int v = 0;
+		try{ v = std::stoi(fl, &used); }catch(...){ used = 0; }
+		if(used < fl.size() || fl.empty()){ throw std::runtime_error("Fragment length '" + fl + "' is not a pure integer: " + id); }
+		r.fragment_length = v;
+		recs[i] = r;
+		max_len = std::max<uint32_t>(max_len, L);
+	}
+	if(max_len + 8 > c.max_org_len){ c.max_org_len = max_len + 8; }
+	// sys_gc_range + adapter systematic errors from the master stream, then one seed per 10000-record batch
+	uint64_t reads = 0, sum_read_length = 0;
+	for(int seg = 2; seg--; ){ for(auto len = p.read_lengths[seg].from; len < p.read_lengths[seg].to(); ++len){ reads += p.read_lengths[seg][len]; sum_read_length += p.read_lengths[seg][len] * len; } }
+	e.sys_gc_range = static_cast<uint32_t>((sum_read_length + reads / 2) / reads) / 2;
+	e.d_master_state.alloc(kMtN + 1);
+	k_master_seed<<<1, 32, 0, s>>>(e.d_master_state.p, seed); ++e.launches;
+	uint32_t carried = 0;
+	{
+		std::vector<SysChain> chains; std::vector<std::pair<uint32_t, uint32_t>> lens; uint64_t n_draws = 0;
+		struct Ad { int seg; size_t a; uint64_t raw_off; }; std::vector<Ad> order;
+		for(int seg = 2; seg--; ){ for(size_t a = p.adapter_count_sum[seg].size(); a--; ){ if(!p.adapter_count_sum[seg][a]){ continue; } order.push_back({seg, a, n_draws}); n_draws += 2ull * (e.h_adapter_off[seg][a + 1] - e.h_adapter_off[seg][a]); } }
+		if(n_draws){
+			e.d_master.alloc(n_draws);
+			k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
+			for(const auto &o : order){
+				const uint32_t off = e.h_adapter_off[o.seg][o.a], len = e.h_adapter_off[o.seg][o.a + 1] - off;
+				SysChain ch{}; ch.seq = e.d_adapter_seq.p + off; ch.L = len; ch.raw = e.d_master.p + o.raw_off; ch.out = e.d_adapter_sys.p + 2 * off; ch.carried_dom = carried;
+				chains.push_back(ch); lens.push_back({len, 0});
+				carried = dominant_before(e.h_adapter_seq.data() + off, len, false, len, carried);
+			}
+			uint32_t passes = 0;
+			run_sys_chains(e, chains, lens, 1u << 30, 0, passes);
+		}
+	}
+	const uint32_t batch = 10000;
+	const uint32_t n_batches = (recs.size() + batch - 1) / batch;
+	DevBuf<uint64_t> d_seeds; d_seeds.alloc(n_batches);
+	k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, d_seeds.p, n_batches); ++e.launches;
+	DevBuf<EmRecord> d_recs; d_recs.upload(recs, s);
+	DevBuf<uint8_t> d_seq, d_dom, d_rate; d_seq.upload(hseq, s); d_dom.upload(hdom, s); d_rate.upload(hrate, s);
+	DevBuf<char> d_ids; d_ids.upload(hid.data(), hid.size() + 1, s);
+	const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, std::max(c.max_read_len, max_len + 8));
+	const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta;
+	RSQ_CUDA(cudaFuncSetAttribute(k_error_model, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
+	Arena a;
+	uint64_t expected = static_cast<uint64_t>(recs.size() * (2.0 * c.max_read_len + 200.0 + hid.size() / std::max<size_t>(1, recs.size())) * 1.3);
+	float ms_sim = 0;
+	for(int attempt = 0; ; ++attempt){
+		setup_arena(e, a, expected, n_batches);
+		e.d_block_out.alloc(n_batches + 1);
+		RSQ_CUDA(cudaMemsetAsync(e.d_block_out.p, 0, (n_batches + 1) * sizeof(BlockOut), s));
+		e.d_next_block.alloc(1); e.d_next_block.zero(s);
+		EventTimer tm(s); tm.start();
+		k_error_model<<<(n_batches + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, shmem, s>>>(c, d_recs.p, recs.size(), batch, d_seeds.p, n_batches, d_seq.p, d_dom.p, d_rate.p, d_ids.p, a, e.d_block_out.p, e.d_next_block.p, e.max_n0, scratch);
+		++e.launches;
+		ms_sim = tm.stop();
+		RSQ_CUDA(cudaGetLastError());
+		const uint32_t flag = read_error_flag(e);
+		if(flag == kErrArenaFull && attempt < 3){ expected *= 2; e.d_error_flag.zero(s); continue; }
+		if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
+		break;
+	}
+	gather(e, a, n_batches, rep);
+	download(e, rep);
+	RSQ_CUDA(cudaStreamSynchronize(s));
+	FILE *o = fopen(out_path, "wb");
+	if(!o){ throw std::runtime_error(std::string("Could not open '") + out_path + "' for writing."); }
+	fwrite(e.h_out[0].p, 1, e.out_bytes[0], o);
+	fclose(o);
+	if(rep){ rep->ms_simulate = ms_sim; rep->pairs = e.out_pairs; rep->bytes[0] = e.out_bytes[0]; rep->bytes[1] = 0; rep->blocks = n_batches; rep->kernel_launches = e.launches; }
+}
+
+}  // namespace rsq
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+#define RSQ_TRY try{
+#define RSQ_CATCH(ret) }catch(const std::exception &ex){ set_error("%s", ex.what()); return ret; }catch(...){ set_error("unknown error"); return ret; }
+
+extern "C" {
+
+const char *rsq_last_error(void){ return g_last_error.c_str(); }
+
+int rsq_device_count(void){ int n = 0; if(cudaGetDeviceCount(&n) != cudaSuccess){ return 0; } return n; }
+
+rsq_profile *rsq_profile_load_flat(const char *flat_path){
+	RSQ_TRY
+	std::unique_ptr<rsq_profile> p(new rsq_profile);
+	FlatFile f; f.load(flat_path);
+	p->p.from_flat(f);
+	return p.release();
+	RSQ_CATCH(nullptr)
+}
+
+rsq_profile *rsq_profile_load(const char *stats_path, const char *ipf_path){
+	RSQ_TRY
+	std::unique_ptr<rsq_profile> p(new rsq_profile);
+	load_reseq_profile(p->p, stats_path, ipf_path);
+	return p.release();
+	RSQ_CATCH(nullptr)
+}
+
+int rsq_profile_save_flat(const rsq_profile *profile, const char *flat_path){
+	RSQ_TRY
+	FlatFile f; profile->p.to_flat(f); f.save(flat_path);
+	return 0;
+	RSQ_CATCH(1)
+}
+
+void rsq_profile_free(rsq_profile *profile){ delete profile; }
+
+rsq_reference *rsq_reference_load_fasta(const char *fasta_path){
+	RSQ_TRY
+	std::unique_ptr<rsq_reference> r(new rsq_reference);
+	r->g.read_fasta(fasta_path);
+	return r.release();
+	RSQ_CATCH(nullptr)
+}
+
+rsq_reference *rsq_reference_from_memory(uint32_t n_seqs, const char *const *ids, const char *const *bases, const uint64_t *lengths){
+	RSQ_TRY
+	std::unique_ptr<rsq_reference> r(new rsq_reference);
+	for(uint32_t i = 0; i < n_seqs; ++i){
+		r->g.ids.emplace_back(ids[i]);
+		std::vector<uint8_t> s(lengths[i]);
+		for(uint64_t k = 0; k < lengths[i]; ++k){ s[k] = Genome::code(bases[i][k]); }
+		r->g.seqs.push_back(std::move(s));
+	}
+	if(!n_seqs){ throw std::runtime_error("reference does not contain any sequences"); }
+	return r.release();
+	RSQ_CATCH(nullptr)
+}
+
+uint64_t rsq_reference_total_size(const rsq_reference *ref){ return ref->g.total_size(); }
+uint32_t rsq_reference_num_sequences(const rsq_reference *ref){ return ref->g.seqs.size(); }
+void rsq_reference_free(rsq_reference *ref){ delete ref; }
+
+rsq_engine *rsq_engine_create(const rsq_profile *profile, int device){
+	RSQ_TRY
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess || n <= device || device < 0){ throw std::runtime_error("no usable CUDA device (this engine has no CPU path)"); }
+	RSQ_CUDA(cudaSetDevice(device));
+	std::unique_ptr<rsq_engine> e(new rsq_engine);
+	e->device = device;
+	RSQ_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	e->prof = profile->p;
+	upload_profile(*e);
+	return e.release();
+	RSQ_CATCH(nullptr)
+}
+
+void rsq_engine_destroy(rsq_engine *engine){ if(engine){ cudaSetDevice(engine->device); delete engine; } }
+
+int rsq_engine_prepare(rsq_engine *engine, const rsq_reference *ref, const rsq_sim_options *opt, rsq_sim_report *report){
+	RSQ_TRY
+	RSQ_CUDA(cudaSetDevice(engine->device));
+	if(report){ std::memset(report, 0, sizeof *report); }
+	prepare(*engine, ref->g, *opt, report);
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_engine_simulate(rsq_engine *engine, rsq_sim_report *report){
+	RSQ_TRY
+	RSQ_CUDA(cudaSetDevice(engine->device));
+	simulate(*engine, report);
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_engine_download(rsq_engine *engine, rsq_sim_report *report){
+	RSQ_TRY
+	RSQ_CUDA(cudaSetDevice(engine->device));
+	download(*engine, report);
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_engine_output(const rsq_engine *engine, int segment, const char **data, uint64_t *bytes){
+	RSQ_TRY
+	if(!engine->downloaded){ throw std::runtime_error("rsq_engine_download has not been called"); }
+	if(segment < 0 || segment > 1){ throw std::runtime_error("segment must be 0 or 1"); }
+	*data = engine->h_out[segment].p; *bytes = engine->out_bytes[segment];
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_engine_write(const rsq_engine *engine, const char *first_reads_path, const char *second_reads_path){
+	RSQ_TRY
+	if(!engine->downloaded){ throw std::runtime_error("rsq_engine_download has not been called"); }
+	const char *paths[2] = {first_reads_path, second_reads_path};
+	for(int seg = 0; seg < 2; ++seg){
+		FILE *o = fopen(paths[seg], "ab");
+		if(!o){ throw std::runtime_error(std::string("Could not open '") + paths[seg] + "' for writing."); }
+		const size_t w = fwrite(engine->h_out[seg].p, 1, engine->out_bytes[seg], o);
+		fclose(o);
+		if(w != engine->out_bytes[seg]){ throw std::runtime_error(std::string("Could not write records to '") + paths[seg] + "'"); }
+	}
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq_sim_options *opt, int device,
+                 const char *first_reads_path, const char *second_reads_path, rsq_sim_report *report){
+	rsq_engine *e = rsq_engine_create(profile, device);
+	if(!e){ return 1; }
+	for(const char *path : {first_reads_path, second_reads_path}){ FILE *o = fopen(path, "wb"); if(!o){ set_error("Could not open '%s' for writing.", path); rsq_engine_destroy(e); return 1; } fclose(o); }
+	rsq_sim_report local; rsq_sim_report *rep = report ? report : &local;
+	int rc = rsq_engine_prepare(e, ref, opt, rep);
+	if(!rc){ rc = rsq_engine_simulate(e, rep); }
+	if(!rc){ rc = rsq_engine_download(e, rep); }
+	if(!rc){ rc = rsq_engine_write(e, first_reads_path, second_reads_path); }
+	if(rc){ remove(first_reads_path); remove(second_reads_path); }
+	rsq_engine_destroy(e);
+	return rc;
+}
+
+int rsq_apply_error_model(rsq_engine *engine, const char *fasta_in_path, const char *fastq_out_path, uint64_t seed, rsq_sim_report *report){
+	RSQ_TRY
+	RSQ_CUDA(cudaSetDevice(engine->device));
+	if(report){ std::memset(report, 0, sizeof *report); }
+	try{ apply_error_model(*engine, fasta_in_path, fastq_out_path, seed, report); }
+	catch(...){ remove(fastq_out_path); throw; }
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_engine_fetch(const rsq_engine *engine, const char *name, void *dst, uint64_t capacity, uint64_t *bytes){
+	RSQ_TRY
+	RSQ_CUDA(cudaSetDevice(engine->device));
+	const std::string n = name;
+	const void *src = nullptr; uint64_t nb = 0; bool host = false;
+	std::vector<uint64_t> seeds;
+	if(n == "sys_fwd"){ src = engine->d_sys_fwd.p; nb = 2 * engine->total_size; }
+	else if(n == "sys_rev"){ src = engine->d_sys_rev.p; nb = 2 * engine->total_size; }
+	else if(n == "adapter_sys"){ src = engine->d_adapter_sys.p; nb = 2 * engine->h_adapter_seq.size(); }
+	else if(n == "sur_start"){ src = engine->d_sur_start.p; nb = 8 * engine->total_size; }
+	else if(n == "sur_end"){ src = engine->d_sur_end.p; nb = 8 * engine->total_size; }
+	else if(n == "reference"){ src = engine->d_ref.p; nb = engine->total_size; }
+	else if(n == "thresholds"){ src = engine->norm.thresholds.data(); nb = 8 * engine->norm.thresholds.size(); host = true; }
+	else if(n == "blocks"){ src = engine->d_blocks.p; nb = sizeof(BlockDesc) * engine->n_blocks_total; }
+	else{ throw std::runtime_error("unknown stage array '" + n + "'"); }
+	if(bytes){ *bytes = nb; }
+	const uint64_t cnt = std::min(nb, capacity);
+	if(dst && cnt){
+		if(host){ std::memcpy(dst, src, cnt); }
+		else{ RSQ_CUDA(cudaMemcpy(dst, src, cnt, cudaMemcpyDeviceToHost)); }
+	}
+	return 0;
+	RSQ_CATCH(1)
+}
+
+}  // extern "C"

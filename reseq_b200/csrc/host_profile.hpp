@@ -606,11 +606,11 @@ inline uint64_t raw_threshold(double thr){
 
 // Everything of CalculateBiasNormalization after the per-(ref, length) sums are known.
 // sums/max_bias are indexed like `params` (1-thread order: ref id descending, sample length ascending).
-inline bool finish_normalization(Normalization &out, const Profile &p, const Spline &spline_in, const std::vector<BiasParam> &params,
+inline bool finish_normalization(Normalization &out, const Profile &p, const std::vector<double> &ref_seq_bias, const Spline &spline_in, const std::vector<BiasParam> &params,
                                  const std::vector<double> &sums, const std::vector<double> &max_bias, uint64_t total_reads){
 	Spline spline = spline_in;
 	const uint32_t to = p.insert_lengths.to();
-	out.num_groups = split_coverage_groups(out.coverage_groups, p.ref_seq_bias);
+	out.num_groups = split_coverage_groups(out.coverage_groups, ref_seq_bias);
 	std::vector<std::vector<std::array<double, 2>>> thr(out.num_groups, std::vector<std::array<double, 2>>(to, {{0.0, 0.0}}));
 	std::vector<double> norm_by_len(to, 0.0), tmp_norm(to, 0.0);
 	for(size_t i = 0; i < params.size(); ++i){

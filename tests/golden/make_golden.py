@@ -1,0 +1,88 @@
+#!/usr/bin/env python3
+"""Regenerates the committed fixtures of tests/golden/ with the reference's own code (oracle/_ref).
+
+Run in the build container (needs /root/reference for the TruSeq adapter files and a built oracle):
+    python tests/golden/make_golden.py
+
+  profile150.reseq.xz / .reseq.ipf.xz   2x150 profile: synthetic SAM -> `reseq illuminaPE --statsOnly` +
+                                        `--stopAfterEstimation` (reference stats + IPF code), bias fit replaced
+                                        by deterministic non-trivial values (dump_tables patch)
+  profile150.flat.xz                    what the reference holds in memory after Load + PrepareProcessing +
+                                        Estimate + PrepareResult for that profile (dump_tables profile)
+  simref_small.fa                       small multi-contig reference with N runs and one too-short contig
+  sim_small_seed42_R{1,2}.fq.xz         `reseq illuminaPE -j 1 --seed 42 -c 20` on simref_small.fa
+  em_frags.fa.xz / em_seed7.fq.xz       seqToIllumina input and its output.  9000 records = ONE 10000-record batch on purpose:
+                                        the reference never increments written_blocks_ (Simulator.cpp:184-213), so its second
+                                        batch waits forever in WriteSingleReads -- larger inputs cannot be pinned against it
+"""
+import lzma
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+ORACLE = os.path.join(ROOT, "oracle", "_ref", "reseq_oracle")
+DUMP = os.path.join(ROOT, "oracle", "_ref", "dump_tables")
+SYN = os.path.join(ROOT, "tools", "make_synthetic.py")
+ADAPTERS = "/root/reference/adapters/TruSeq_single"
+
+
+def run(cmd, **kw):
+    print("+", " ".join(cmd), flush=True)
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, **kw)
+    if res.returncode:
+        sys.stderr.write(res.stdout)
+        raise SystemExit(f"command failed: {cmd}")
+    return res.stdout
+
+
+def xz(src, dst):
+    with open(src, "rb") as f, lzma.open(dst, "wb", preset=9 | lzma.PRESET_EXTREME) as o:
+        shutil.copyfileobj(f, o)
+
+
+def main():
+    tmp = tempfile.mkdtemp(prefix="rsq_golden_")
+    py = sys.executable
+    ref = os.path.join(tmp, "prof_ref.fa")
+    run([py, SYN, "reference", ref, "--sizes", "200000,120000", "--seed", "7"])
+    sam = os.path.join(tmp, "prof.sam")
+    run([py, SYN, "sam", ref, sam, "--pairs", "20000", "--seed", "11"])
+    raw = os.path.join(tmp, "raw.reseq")
+    run([ORACLE, "illuminaPE", "-j", "8", "-b", sam, "-r", ref, "--adapterFile", ADAPTERS + ".fa", "--adapterMatrix", ADAPTERS + ".mat",
+         "--statsOnly", "-S", raw])
+    log = run([ORACLE, "illuminaPE", "-j", "8", "-s", raw, "-r", ref, "--stopAfterEstimation"])
+    if "did not reach precision aim" in log:
+        raise SystemExit("IPF did not converge for every table; the profile would be refitted on load")
+    prof = os.path.join(tmp, "profile150.reseq")
+    run([DUMP, "patch", raw, prof, "5"])
+    shutil.copy(raw + ".ipf", prof + ".ipf")
+    flat = os.path.join(tmp, "profile150.flat")
+    run([DUMP, "profile", prof, flat])
+    xz(prof, os.path.join(HERE, "profile150.reseq.xz"))
+    xz(prof + ".ipf", os.path.join(HERE, "profile150.reseq.ipf.xz"))
+    xz(flat, os.path.join(HERE, "profile150.flat.xz"))
+
+    small = os.path.join(HERE, "simref_small.fa")
+    run([py, SYN, "reference", small, "--sizes", "30000,22000,800,15000", "--seed", "21", "--n-rate", "0.004", "--prefix", "chr"])
+    r1, r2 = os.path.join(tmp, "r1.fq"), os.path.join(tmp, "r2.fq")
+    run([ORACLE, "illuminaPE", "-j", "1", "-s", prof, "-R", small, "--ipfIterations", "0", "--seed", "42", "-c", "20", "-1", r1, "-2", r2])
+    xz(r1, os.path.join(HERE, "sim_small_seed42_R1.fq.xz"))
+    xz(r2, os.path.join(HERE, "sim_small_seed42_R2.fq.xz"))
+
+    frags = os.path.join(tmp, "em_frags.fa")
+    run([py, SYN, "fragments", ref, "-", frags, "--n", "9000", "--len", "120", "--seed", "3"])
+    emq = os.path.join(tmp, "em.fq")
+    run([ORACLE, "seqToIllumina", "-j", "1", "-i", frags, "-s", prof, "--ipfIterations", "0", "--seed", "7", "-o", emq])
+    xz(frags, os.path.join(HERE, "em_frags.fa.xz"))
+    xz(emq, os.path.join(HERE, "em_seed7.fq.xz"))
+    shutil.rmtree(tmp)
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -175,7 +175,7 @@ int main(int argc, char **argv){
 		maxb[i] = mx;
 	}
 	Normalization norm;
-	finish_normalization(norm, p, spline, params, sums, maxb, total_pairs);
+	finish_normalization(norm, p, p.ref_seq_bias, spline, params, sums, maxb, total_pairs);
 	{
 		const double ref_norm = f.scalar_d("sim.bias_normalization");
 		if(ref_norm != norm.bias_normalization){ printf("MISMATCH bias_normalization: oracle %a twin %a\n", ref_norm, norm.bias_normalization); ++bad; }
