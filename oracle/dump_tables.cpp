@@ -288,6 +288,7 @@ int main(int argc, char **argv){
 			codes.reserve(ref.SequenceLength(s));
 			for(auto c : ref.ReferenceSequence(s)){ codes.push_back(static_cast<uint8_t>(c)); }
 			w.u8("sim.ref." + std::to_string(s), codes);
+			w.str("sim.ref_id." + std::to_string(s), std::string(seqan::toCString(ref.ReferenceId(s))));
 		}
 
 		// --- all blocks, in creation order (Simulator.cpp:2823-2826 + GetNextBlock) ---

@@ -69,7 +69,8 @@ int main(int argc, char **argv){
 	for(size_t s = 0; f.has("sim.ref." + std::to_string(s)); ++s){
 		const auto &a = f.get("sim.ref." + std::to_string(s));
 		g.seqs.emplace_back(a.as<uint8_t>(), a.as<uint8_t>() + a.count);
-		g.ids.push_back("synth" + std::to_string(s + 1) + " synthetic contig");
+		const auto &idr = f.get("sim.ref_id." + std::to_string(s));
+		g.ids.emplace_back(reinterpret_cast<const char *>(idr.bytes.data()), idr.count);
 	}
 	DeviceLikeStorage st;
 	std::vector<std::vector<double>> cp_keep; cp_keep.reserve(4096);
@@ -240,9 +241,16 @@ int main(int argc, char **argv){
 		for(size_t i = 0; i < nb; ++i){ if(rs.as<uint64_t>()[i] != blocks[i].seed){ ++sb; } }
 		if(sb || rs.count != blocks.size()){ printf("MISMATCH block seeds: %zu of %zu differ (oracle %" PRIu64 " blocks, twin %zu)\n", sb, nb, rs.count, blocks.size()); ++bad; }
 		// oracle dump: forward errors concatenated block by block (= position order); reverse errors per forward block interval in reverse-strand order
-		size_t fb = 0;
-		for(size_t i = 0; i < std::min<size_t>(rf.count, st.sys_fwd.size()); ++i){ if(rf.as<uint8_t>()[i] != st.sys_fwd[i]){ if(fb < 5){ printf("  sys_fwd diff at byte %zu: oracle %u twin %u\n", i, rf.as<uint8_t>()[i], st.sys_fwd[i]); } ++fb; } }
-		if(fb || rf.count != st.sys_fwd.size()){ printf("MISMATCH sys_fwd: %zu bytes differ\n", fb); ++bad; }
+		size_t fb = 0, fi = 0;
+		for(const auto &bd : blocks){
+			const uint32_t L = st.seq_len[bd.ref_id]; const uint32_t e = std::min(bd.start_pos + 1000, L);
+			for(uint32_t q = bd.start_pos; q < e; ++q){
+				for(int k = 0; k < 2; ++k, ++fi){
+					if(fi < rf.count && rf.as<uint8_t>()[fi] != st.sys_fwd[2 * (st.seq_off[bd.ref_id] + q) + k]){ if(fb < 5){ printf("  sys_fwd diff at ref %u pos %u\n", bd.ref_id, q); } ++fb; }
+				}
+			}
+		}
+		if(fb || fi != rf.count){ printf("MISMATCH sys_fwd: %zu bytes differ (%zu vs %" PRIu64 ")\n", fb, fi, rf.count); ++bad; }
 		size_t rb = 0, ri = 0;
 		for(const auto &bd : blocks){
 			const uint32_t L = st.seq_len[bd.ref_id]; const uint32_t e = std::min(bd.start_pos + 1000, L);

@@ -1,0 +1,171 @@
+"""GPU parity tests: everything goes through the C ABI (libreseq_b200.so); the checker is the committed golden
+FASTQ made by the reference's own code and, when oracle/_ref travelled to this box, the reference binary itself."""
+import hashlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import run_oracle_sim
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def rb(library):
+    import reseq_b200
+    if library.rsq_device_count() < 1:
+        pytest.fail("no CUDA device: the engine has no CPU path")
+    return reseq_b200
+
+
+@pytest.fixture(scope="module")
+def engine(rb, golden):
+    eng = rb.Engine(rb.Profile.load_flat(golden["flat"]), 0)
+    yield eng
+    eng.close()
+
+
+def _simulate(eng, ref, **kw):
+    eng.prepare(ref, **kw)
+    rep = eng.simulate()
+    eng.download()
+    return eng.output(0), eng.output(1), rep
+
+
+def test_small_golden_bit_exact(rb, engine, golden):
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    r1, r2, rep = _simulate(engine, ref, seed=42, coverage=20.0)
+    assert r1 == open(golden["r1"], "rb").read()
+    assert r2 == open(golden["r2"], "rb").read()
+    assert rep.pairs == r1.count(b"\n") // 4 and rep.blocks == rep.blocks_total - 1
+    assert rep.kernel_launches > 0
+
+
+def test_dropin_simulate_call_writes_files(rb, golden, workdir):
+    prof = rb.Profile.load_flat(golden["flat"])
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    o1, o2 = os.path.join(workdir, "d1.fq"), os.path.join(workdir, "d2.fq")
+    rb.simulate(prof, ref, o1, o2, seed=42, coverage=20.0)
+    assert open(o1, "rb").read() == open(golden["r1"], "rb").read()
+    assert open(o2, "rb").read() == open(golden["r2"], "rb").read()
+
+
+def test_error_model_bit_exact(engine, golden, workdir):
+    out = os.path.join(workdir, "em_gpu.fq")
+    rep = engine.apply_error_model(golden["em_in"], out, 7)
+    assert open(out, "rb").read() == open(golden["em_out"], "rb").read()
+    assert rep.pairs == 9000
+
+
+def test_error_model_rejects_malformed_header(engine, workdir):
+    import reseq_b200
+    bad = os.path.join(workdir, "bad_em.fa")
+    open(bad, "w").write(">x 1;10;ACGT;!!!!\nACGTACGT\n")
+    with pytest.raises(reseq_b200.RsqError):
+        engine.apply_error_model(bad, os.path.join(workdir, "bad_em.fq"), 1)
+    assert not os.path.exists(os.path.join(workdir, "bad_em.fq"))
+
+
+def test_stage_arrays_match_reference(rb, engine, golden, oracle, workdir):
+    """Systematic errors (both strands, adapters) and thresholds against the reference's in-memory values."""
+    from reseq_b200.flatfile import read_flat
+    stage = os.path.join(workdir, "stage_gpu.flat")
+    subprocess.run([oracle["dump"], "sim", golden["reseq"], golden["small_ref"], "42", "20", stage], check=True, timeout=600,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    st = read_flat(stage)
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    rep = engine.prepare(ref, seed=42, coverage=20.0)
+    assert rep.bias_normalization == st["sim.bias_normalization"][0]
+    assert rep.total_pairs_aim == st["sim.total_pairs"][0]
+    thr = engine.fetch("thresholds", "float64")
+    assert np.array_equal(thr, st["sim.thresholds.0"])
+    blocks = engine.fetch("blocks", "uint64").reshape(-1, 3)
+    assert np.array_equal(blocks[:, 2], st["sim.block_seed"])
+    fwd = engine.fetch("sys_fwd").reshape(-1, 2)
+    rev = engine.fetch("sys_rev").reshape(-1, 2)
+    lens = [len(st[f"sim.ref.{i}"]) for i in range(4)]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    exp_f, exp_r = [], []
+    for rid, start in zip(st["sim.block_ref"], st["sim.block_start"]):
+        L = lens[rid]
+        e = min(start + 1000, L)
+        exp_f.append(fwd[offs[rid] + start: offs[rid] + e])
+        exp_r.append(rev[offs[rid] + L - e: offs[rid] + L - start])
+    assert np.array_equal(np.concatenate(exp_f).ravel(), st["sim.sys_fwd"])
+    assert np.array_equal(np.concatenate(exp_r).ravel(), st["sim.sys_rev"])
+    refseq = engine.fetch("reference")
+    assert np.array_equal(refseq, np.concatenate([st[f"sim.ref.{i}"] for i in range(4)]))
+
+
+@pytest.mark.parametrize("seed,coverage", [(7, 6.0), (123456789, 35.0)])
+def test_against_reference_binary(rb, engine, golden, oracle, workdir, seed, coverage):
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    r1, r2, _ = _simulate(engine, ref, seed=seed, coverage=coverage)
+    o1, o2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], seed, coverage, os.path.join(workdir, f"ora{seed}"))
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+
+
+def test_other_reference_and_prefix_against_reference_binary(rb, engine, golden, oracle, workdir):
+    fa = os.path.join(workdir, "other.fa")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic.py"), "reference", fa, "--sizes", "61000,1001,2500", "--seed", "99",
+                    "--n-rate", "0.01", "--prefix", "ctg"], check=True)
+    ref = rb.Reference.load_fasta(fa)
+    r1, r2, _ = _simulate(engine, ref, seed=5, coverage=12.0, record_base_identifier="Sim")
+    o1, o2 = run_oracle_sim(oracle, golden["reseq"], fa, 5, 12.0, os.path.join(workdir, "ora_other"), extra=("--recordBaseIdentifier", "Sim"))
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+
+
+def test_num_read_pairs_option_against_reference_binary(rb, engine, golden, oracle, workdir):
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    r1, r2, _ = _simulate(engine, ref, seed=3, num_read_pairs=2500)
+    o1, o2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], 3, 0, os.path.join(workdir, "ora_np"), extra=("--numReads", "2500"))
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+
+
+def test_shards_concatenate_to_the_whole_run(rb, engine, golden):
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    whole = _simulate(engine, ref, seed=42, coverage=20.0)
+    parts1, parts2, pairs = b"", b"", 0
+    for i in range(3):
+        a, b, rep = _simulate(engine, ref, seed=42, coverage=20.0, shard_index=i, shard_count=3)
+        parts1 += a
+        parts2 += b
+        pairs += rep.pairs
+    assert parts1 == whole[0] and parts2 == whole[1] and pairs == whole[2].pairs
+
+
+def test_too_short_reference_is_an_error(rb, engine):
+    ref = rb.Reference.from_memory(["tiny"], [b"ACGT" * 50])
+    with pytest.raises(rb.RsqError, match="too short"):
+        engine.prepare(ref, seed=1, coverage=5.0)
+
+
+def test_full_size_properties(rb, engine, workdir):
+    """BASELINE config 2 size (4.64 Mbp, 30x): determinism, record structure, pairing, pair count near the aim."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synthetic
+    seq = make_synthetic.gen_reference([4_641_652], 1234)[0]
+    ref = rb.Reference.from_memory(["ecoli_sized synthetic"], [seq.encode()])
+    r1, r2, rep = _simulate(engine, ref, seed=42, coverage=30.0)
+    assert abs(rep.pairs - rep.total_pairs_aim) < 0.02 * rep.total_pairs_aim
+    l1, l2 = r1.split(b"\n"), r2.split(b"\n")
+    assert len(l1) == len(l2) == 4 * rep.pairs + 1
+    ids1 = [x.split(b" ")[0] for x in l1[0:-1:4]]
+    ids2 = [x.split(b" ")[0] for x in l2[0:-1:4]]
+    assert ids1 == ids2 and all(i.startswith(b"@ReseqRead") for i in ids1[:1000])
+    assert all(len(s) == 150 for s in l1[1:-1:4]) and all(len(q) == 150 for q in l2[3:-1:4])
+    assert set(b"".join(l1[1:2000:4])) <= set(b"ACGTN")
+    blocks = [int(i[len(b"@ReseqRead"):].split(b"_")[0]) for i in ids1]
+    assert blocks == sorted(blocks), "records must come in block order like the reference's 1-thread run"
+    h = hashlib.sha256(r1).hexdigest(), hashlib.sha256(r2).hexdigest()
+    r1b, r2b, _ = _simulate(engine, ref, seed=42, coverage=30.0)
+    assert (hashlib.sha256(r1b).hexdigest(), hashlib.sha256(r2b).hexdigest()) == h
+    r1c, _, _ = _simulate(engine, ref, seed=43, coverage=30.0)
+    assert hashlib.sha256(r1c).hexdigest() != h[0]

@@ -1,0 +1,65 @@
+"""CPU-side parity: the committed fixtures really come from the reference, the glibc exp/pow port is bit exact, and
+the lane-group templates (instantiated with one lane) reproduce the reference's stages and FASTQ byte for byte."""
+import filecmp
+import os
+import subprocess
+
+import pytest
+
+from conftest import run_oracle_sim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TWIN_DIR = os.path.join(ROOT, "tests", "host_twin")
+
+
+def _compile(src, out, extra=()):
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", *extra, "-o", out, os.path.join(TWIN_DIR, src)], check=True)
+    return out
+
+
+def test_exp_pow_port_matches_libm(workdir):
+    """mathx.cuh vs the system libm the reference links (utilities.hpp:506, FragmentDistributionStats.cpp:3586,3604)."""
+    exe = _compile("mathx_check.cpp", os.path.join(workdir, "mathx_check"), ["-mfma"])
+    out = subprocess.run([exe, "3000000", "11"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "exp_mismatch=0 logit_mismatch=0 pow_mismatch=0" in out.stdout
+
+
+def test_golden_fastq_is_what_the_reference_writes(oracle, golden, workdir):
+    r1, r2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], 42, 20, os.path.join(workdir, "pin"))
+    assert filecmp.cmp(r1, golden["r1"], shallow=False)
+    assert filecmp.cmp(r2, golden["r2"], shallow=False)
+
+
+def test_golden_error_model_is_what_the_reference_writes(oracle, golden, workdir):
+    out = os.path.join(workdir, "pin_em.fq")
+    subprocess.run([oracle["reseq"], "seqToIllumina", "-j", "1", "--verbosity", "1", "-i", golden["em_in"], "-s", golden["reseq"],
+                    "--ipfIterations", "0", "--seed", "7", "-o", out], check=True, timeout=600, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert filecmp.cmp(out, golden["em_out"], shallow=False)
+
+
+@pytest.fixture(scope="module")
+def twin(workdir):
+    return _compile("twin.cpp", os.path.join(workdir, "twin"))
+
+
+@pytest.mark.parametrize("seed,coverage", [(42, 20), (7, 6)])
+def test_templates_match_reference_stages_and_fastq(oracle, golden, twin, workdir, seed, coverage):
+    """Normalisation, thresholds, block seeds, adapter/forward/reverse systematic errors and the final FASTQ."""
+    stage = os.path.join(workdir, f"stage_{seed}.flat")
+    subprocess.run([oracle["dump"], "sim", golden["reseq"], golden["small_ref"], str(seed), str(coverage), stage], check=True, timeout=600,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    if (seed, coverage) == (42, 20):
+        r1, r2 = golden["r1"], golden["r2"]
+    else:
+        r1, r2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], seed, coverage, os.path.join(workdir, f"o{seed}"))
+    from reseq_b200.flatfile import read_flat
+    st = read_flat(stage)
+    n_blocks = len(st["sim.block_seed"])
+    lookahead = 1 + (int(st["insert_lengths.from"][0]) + len(st["insert_lengths"])) // 1000
+    prefix = os.path.join(workdir, f"twin_{seed}")
+    res = subprocess.run([twin, stage, str(seed), prefix, str(n_blocks - lookahead)], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout
+    assert "stage_mismatches=0" in res.stdout and "error_flag=0" in res.stdout
+    assert filecmp.cmp(prefix + "_1.fq", r1, shallow=False)
+    assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
