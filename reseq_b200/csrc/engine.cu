@@ -38,12 +38,16 @@ static void set_error(const char *fmt, ...){
 #define RSQ_CUDA(call) do{ cudaError_t e_ = (call); if(e_ != cudaSuccess){ throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); } }while(0)
 
 template<class T> struct DevBuf {
-	T *p = nullptr; size_t n = 0;
+	T *p = nullptr; size_t n = 0, cap = 0;
 	DevBuf() = default;
 	DevBuf(const DevBuf &) = delete; DevBuf &operator=(const DevBuf &) = delete;
 	~DevBuf(){ release(); }
-	void release(){ if(p){ cudaFree(p); p = nullptr; n = 0; } }
-	void alloc(size_t count){ release(); if(count){ RSQ_CUDA(cudaMalloc(&p, count * sizeof(T))); } n = count; }
+	void release(){ if(p){ cudaFree(p); p = nullptr; n = 0; cap = 0; } }
+	// Buffers are recycled between runs: cudaMalloc/cudaFree synchronise the device and cost milliseconds each.
+	void alloc(size_t count){
+		if(count > cap){ release(); RSQ_CUDA(cudaMalloc(&p, count * sizeof(T))); cap = count; }
+		n = count;
+	}
 	void upload(const std::vector<T> &v, cudaStream_t s){ alloc(v.size()); if(v.size()){ RSQ_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s)); } }
 	void upload(const T *v, size_t count, cudaStream_t s){ alloc(count); if(count){ RSQ_CUDA(cudaMemcpyAsync(p, v, count * sizeof(T), cudaMemcpyHostToDevice, s)); } }
 	void zero(cudaStream_t s){ if(n){ RSQ_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); } }
@@ -66,18 +70,97 @@ __global__ void k_surroundings(const uint8_t *seq, uint32_t L, const double *t0,
 	sur_end[pos] = surrounding_bias(t0, t1, t2, code);
 }
 
+// G/C prefix counts of one sequence: entry i = number of G/C in [0, i).  Three small passes
+// (tile counts, scan of the tile counts, tile-local scan) instead of shipping 4 bytes/base over PCIe.
+constexpr uint32_t kGcTile = 4096;
+__global__ void k_gc_tile_counts(const uint8_t *seq, uint32_t L, uint32_t *tile_sums){
+	__shared__ uint32_t red[8];
+	const uint32_t lo = blockIdx.x * kGcTile;
+	uint32_t cnt = 0;
+	for(uint32_t i = lo + threadIdx.x; i < min(L, lo + kGcTile); i += blockDim.x){ const uint8_t b = seq[i]; cnt += (b == 1 || b == 2); }
+	cnt = __reduce_add_sync(0xffffffffu, cnt);
+	if((threadIdx.x & 31) == 0){ red[threadIdx.x >> 5] = cnt; }
+	__syncthreads();
+	if(threadIdx.x == 0){ uint32_t t = 0; for(uint32_t w = 0; w < (blockDim.x >> 5); ++w){ t += red[w]; } tile_sums[blockIdx.x] = t; }
+}
+__global__ void k_gc_scan_tiles(uint32_t *tile_sums, uint32_t n_tiles){
+	// single CTA, sequential over chunks of blockDim.x tiles
+	__shared__ uint32_t buf[1024];
+	__shared__ uint32_t carry;
+	if(threadIdx.x == 0){ carry = 0; }
+	__syncthreads();
+	for(uint32_t base = 0; base < n_tiles; base += blockDim.x){
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = i < n_tiles ? tile_sums[i] : 0;
+		buf[threadIdx.x] = v;
+		__syncthreads();
+		for(uint32_t o = 1; o < blockDim.x; o <<= 1){
+			const uint32_t add = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+			__syncthreads();
+			buf[threadIdx.x] += add;
+			__syncthreads();
+		}
+		if(i < n_tiles){ tile_sums[i] = carry + buf[threadIdx.x] - v; }   // exclusive
+		__syncthreads();
+		if(threadIdx.x == blockDim.x - 1){ carry += buf[threadIdx.x]; }
+		__syncthreads();
+	}
+}
+__global__ void k_gc_prefix(const uint8_t *seq, uint32_t L, const uint32_t *tile_offsets, uint32_t *prefix /*L+1*/){
+	// one warp per tile: 32 positions at a time, warp-inclusive scan by shuffles
+	const uint32_t lo = blockIdx.x * kGcTile, hi = min(L, lo + kGcTile);
+	const uint32_t lane = threadIdx.x;
+	uint32_t run = tile_offsets[blockIdx.x];
+	if(blockIdx.x == 0 && lane == 0){ prefix[0] = 0; }
+	for(uint32_t base = lo; base < hi; base += 32){
+		const uint32_t i = base + lane;
+		uint32_t v = 0;
+		if(i < hi){ const uint8_t b = seq[i]; v = (b == 1 || b == 2); }
+		for(int o = 1; o < 32; o <<= 1){ const uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if(lane >= o){ v += t; } }
+		if(i < hi){ prefix[i + 1] = run + v; }
+		run += __shfl_sync(0xffffffffu, v, 31);
+	}
+}
+
 struct BiasParamDev { uint32_t ref_id, fragment_length; double general; };
 
+// One warp per (sequence, sampled fragment length): lanes evaluate 32 consecutive start positions (coalesced
+// loads), the warp then adds the 32 terms in position order - the FP64 sum has to follow the reference's
+// sequential order (Reference::SumBias), only the term evaluation is parallel.
 __global__ void k_sum_bias(const BiasParamDev *params, uint32_t n_params, const uint64_t *seq_off, const uint32_t *seq_len,
                            const double *sur_start, const double *sur_end, const uint32_t *gc_prefix, const double *gc_bias,
                            double *sums, double *max_bias){
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
 	if(i >= n_params){ return; }
 	const BiasParamDev p = params[i];
 	const uint64_t off = seq_off[p.ref_id];
-	double mx = 0.0;
-	sums[i] = sum_bias_chain(sur_start + off, sur_end + off, gc_prefix + off + p.ref_id, seq_len[p.ref_id], p.fragment_length, p.general, gc_bias, mx);
-	max_bias[i] = mx;
+	const uint32_t L = seq_len[p.ref_id], fl = p.fragment_length;
+	const double *ss = sur_start + off, *se = sur_end + off + fl - 1;
+	const uint32_t *gp = gc_prefix + off + p.ref_id;
+	const uint32_t n_pos = L - fl + 1;
+	double tot = 0.0, mx = 0.0;
+	for(uint32_t base = 0; base < n_pos; base += 32){
+		const uint32_t pos = base + lane;
+		double bias = 0.0;
+		if(pos < n_pos){
+			const uint32_t gc = gp[pos + fl] - gp[pos];
+			bias = mul_rn(p.general, gc_bias[percent_u32(gc, fl)]);
+			bias = mul_rn(bias, ss[pos]);
+			bias = mul_rn(bias, se[pos]);
+			if(bias > mx){ mx = bias; }
+		}
+		const uint32_t cnt = min(32u, n_pos - base);
+		if(cnt == 32u){
+#pragma unroll
+			for(int k = 0; k < 32; ++k){ tot = add_rn(tot, __shfl_sync(0xffffffffu, bias, k)); }
+		}
+		else{
+			for(uint32_t k = 0; k < cnt; ++k){ tot = add_rn(tot, __shfl_sync(0xffffffffu, bias, k)); }
+		}
+	}
+	for(int o = 16; o; o >>= 1){ mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+	if(lane == 0){ sums[i] = tot; max_bias[i] = mx; }
 }
 
 // Serial continuation of the master mt19937_64: state[0..311] + state[312] = index, `n` outputs appended to out.
@@ -404,6 +487,9 @@ struct rsq_engine {
 	DevBuf<char> d_names;
 	DevBuf<uint64_t> d_master_state, d_master;
 	DevBuf<BlockDesc> d_blocks;
+	DevBuf<SysChain> d_sys_chains; DevBuf<SysChunk> d_sys_chunks; DevBuf<uint32_t> d_sys_dirty, d_gc_tiles;
+	DevBuf<BiasParamDev> d_bias_params; DevBuf<double> d_bias_sums, d_bias_max;
+	PinnedBuf h_ref_stage;
 	std::vector<uint64_t> h_seq_off;
 	uint64_t total_size = 0;
 	uint32_t n_blocks_total = 0, n_blocks_sim = 0, shard_first = 0, shard_n = 0;
@@ -541,9 +627,9 @@ static void run_sys_chains(rsq_engine &e, const std::vector<SysChain> &chains, c
 		}
 	}
 	if(chunks.empty()){ return; }
-	DevBuf<SysChain> d_chains; d_chains.upload(chains, e.stream);
-	DevBuf<SysChunk> d_chunks; d_chunks.upload(chunks, e.stream);
-	DevBuf<uint32_t> d_dirty; d_dirty.alloc(1);
+	DevBuf<SysChain> &d_chains = e.d_sys_chains; d_chains.upload(chains, e.stream);
+	DevBuf<SysChunk> &d_chunks = e.d_sys_chunks; d_chunks.upload(chunks, e.stream);
+	DevBuf<uint32_t> &d_dirty = e.d_sys_dirty; d_dirty.alloc(1);
 	const uint32_t n = chunks.size();
 	const int warps = 4;
 	const size_t shmem = static_cast<size_t>(warps) * ((e.max_n0 + 1) & ~1u) * 8;
@@ -605,15 +691,22 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		names += g.first_part(i); name_off.push_back(names.size());
 	}
 	e.h_seq_off = seq_off;
-	std::vector<uint8_t> flat(total);
-	std::vector<uint32_t> gcp(total + g.seqs.size() + 1, 0);
+	e.h_ref_stage.ensure(total + 1);
+	for(size_t i = 0; i < g.seqs.size(); ++i){ std::memcpy(e.h_ref_stage.p + seq_off[i], g.seqs[i].data(), g.seqs[i].size()); }
+	e.d_ref.alloc(total + 1);
+	RSQ_CUDA(cudaMemcpyAsync(e.d_ref.p, e.h_ref_stage.p, total, cudaMemcpyHostToDevice, s));
+	e.d_gc_prefix.alloc(total + g.seqs.size() + 1);
+	{ uint32_t max_tiles = 1; for(const auto &q : g.seqs){ max_tiles = std::max<uint32_t>(max_tiles, (q.size() + kGcTile - 1) / kGcTile); } e.d_gc_tiles.alloc(max_tiles); }
 	for(size_t i = 0; i < g.seqs.size(); ++i){
-		std::memcpy(flat.data() + seq_off[i], g.seqs[i].data(), g.seqs[i].size());
-		uint32_t *gp = gcp.data() + seq_off[i] + i;
-		uint32_t acc = 0; gp[0] = 0;
-		for(size_t k = 0; k < g.seqs[i].size(); ++k){ const uint8_t b = g.seqs[i][k]; acc += (b == 1 || b == 2); gp[k + 1] = acc; }
+		const uint32_t L = g.seqs[i].size();
+		const uint32_t tiles = (L + kGcTile - 1) / kGcTile;
+		uint32_t *gp = e.d_gc_prefix.p + seq_off[i] + i;
+		if(!tiles){ RSQ_CUDA(cudaMemsetAsync(gp, 0, 4, s)); continue; }
+		k_gc_tile_counts<<<tiles, 256, 0, s>>>(e.d_ref.p + seq_off[i], L, e.d_gc_tiles.p);
+		k_gc_scan_tiles<<<1, 1024, 0, s>>>(e.d_gc_tiles.p, tiles);
+		k_gc_prefix<<<tiles, 32, 0, s>>>(e.d_ref.p + seq_off[i], L, e.d_gc_tiles.p, gp);
+		e.launches += 3;
 	}
-	e.d_ref.upload(flat, s); e.d_gc_prefix.upload(gcp, s);
 	e.d_seq_off.upload(seq_off, s); e.d_seq_len.upload(seq_len, s); e.d_name_off.upload(name_off, s);
 	e.d_names.upload(names.data(), names.size() + 1, s);
 	e.d_ref_seq_bias.upload(e.run_ref_seq_bias, s);
@@ -647,9 +740,9 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	}
 	std::vector<double> sums(params.size(), 0.0), maxb(params.size(), 0.0);
 	if(!params.empty()){
-		DevBuf<BiasParamDev> d_params; d_params.upload(dparams, s);
-		DevBuf<double> d_sums, d_max; d_sums.alloc(params.size()); d_max.alloc(params.size());
-		k_sum_bias<<<(params.size() + 31) / 32, 32, 0, s>>>(d_params.p, params.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
+		DevBuf<BiasParamDev> &d_params = e.d_bias_params; d_params.upload(dparams, s);
+		DevBuf<double> &d_sums = e.d_bias_sums, &d_max = e.d_bias_max; d_sums.alloc(params.size()); d_max.alloc(params.size());
+		k_sum_bias<<<(params.size() + 3) / 4, 128, 0, s>>>(d_params.p, params.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
 		++e.launches;
 		RSQ_CUDA(cudaMemcpyAsync(sums.data(), d_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, s));
 		RSQ_CUDA(cudaMemcpyAsync(maxb.data(), d_max.p, maxb.size() * 8, cudaMemcpyDeviceToHost, s));
