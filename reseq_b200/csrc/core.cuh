@@ -65,45 +65,48 @@ struct Tables {
 // Likelihood products run lane-parallel; the two sums run in the reference's exact sequential order
 // (forward over ind0 for prob_sum, backwards for the cumulative search) because FP64 addition is not
 // associative and the result must be bit-identical.
+// AdjustIndeces (ProbabilityEstimates.h:368-380) for one margin
+RSQ_HD uint32_t adjust_index(uint32_t v, uint32_t from, uint32_t span){
+	return v < from ? 0u : (v >= from + span ? span - 1u : v - from);
+}
+
 template<class G>
 RSQ_HD uint32_t draw(const G &g, const Tables &t, uint32_t table_id, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3,
                      double random_number, double *prob, bool &zero_sum){
+	// only constant member indices below: the descriptor must stay in registers
 	const TableDesc d = t.desc[table_id];
-	if(d.n0 == 0){
+	const uint32_t n0 = d.n0;
+	if(n0 == 0){
 		zero_sum = true;
 		return 0;
 	}
-	uint32_t idx[4] = {i0, i1, i2, i3};
-	const double *row[4];
-#pragma unroll
-	for(int n = 0; n < 4; ++n){
-		uint32_t v = idx[n];
-		if(n < static_cast<int>(d.nm)){
-			// AdjustIndeces (ProbabilityEstimates.h:368-380)
-			if(v < d.from[n]){ v = 0; }
-			else if(v >= d.from[n] + d.span[n]){ v = d.span[n] - 1; }
-			else{ v -= d.from[n]; }
-		}
-		else{ v = 0; }
-		row[n] = t.blob + d.off[n < static_cast<int>(d.nm) ? n : 0] + static_cast<size_t>(v) * d.n0;
-	}
+	const bool four = d.nm > 3;
+	const double *r0 = t.blob + (d.off[0] + adjust_index(i0, d.from[0], d.span[0]) * n0);
+	const double *r1 = t.blob + (d.off[1] + adjust_index(i1, d.from[1], d.span[1]) * n0);
+	const double *r2 = t.blob + (d.off[2] + adjust_index(i2, d.from[2], d.span[2]) * n0);
+	const double *r3 = four ? t.blob + (d.off[3] + adjust_index(i3, d.from[3], d.span[3]) * n0) : r0;
 	g.sync();  // previous consumer of `prob` is done
-	for(uint32_t i = g.lane(); i < d.n0; i += G::kSize){
-		double p = row[0][i];
-		p = mul_rn(p, row[1][i]);
-		p = mul_rn(p, row[2][i]);
-		if(d.nm > 3){ p = mul_rn(p, row[3][i]); }
+	for(uint32_t i = g.lane(); i < n0; i += G::kSize){
+		double p = r0[i];
+		p = mul_rn(p, r1[i]);
+		p = mul_rn(p, r2[i]);
+		if(four){ p = mul_rn(p, r3[i]); }
 		prob[i] = p;
 	}
 	g.sync();
 	double prob_sum = 0.0;
-	for(uint32_t i = 0; i < d.n0; ++i){
+	uint32_t i = 0;
+	for(; i + 4 <= n0; i += 4){   // same left-to-right order, four loads per trip
+		const double a = prob[i], b = prob[i + 1], c = prob[i + 2], e = prob[i + 3];
+		prob_sum = add_rn(add_rn(add_rn(add_rn(prob_sum, a), b), c), e);
+	}
+	for(; i < n0; ++i){
 		prob_sum = add_rn(prob_sum, prob[i]);
 	}
 	zero_sum = (0.0 == prob_sum);
 	const double r = mul_rn(random_number, prob_sum);
 	double sum = 0.0;
-	uint32_t ind0 = d.n0;
+	uint32_t ind0 = n0;
 	while(sum <= r && --ind0){
 		sum = add_rn(sum, prob[ind0]);
 	}

@@ -140,16 +140,19 @@ __global__ void k_sum_bias(const BiasParamDev *params, uint32_t n_params, const 
 	const uint32_t *gp = gc_prefix + off + p.ref_id;
 	const uint32_t n_pos = L - fl + 1;
 	double tot = 0.0, mx = 0.0;
+	// software pipeline: the loads of tile t+1 are in flight while tile t is being added up
+	auto term = [&](uint32_t pos) -> double {
+		if(pos >= n_pos){ return 0.0; }
+		const uint32_t gc = gp[pos + fl] - gp[pos];
+		double bias = mul_rn(p.general, gc_bias[percent_u32(gc, fl)]);
+		bias = mul_rn(bias, ss[pos]);
+		return mul_rn(bias, se[pos]);
+	};
+	double next = term(lane);
 	for(uint32_t base = 0; base < n_pos; base += 32){
-		const uint32_t pos = base + lane;
-		double bias = 0.0;
-		if(pos < n_pos){
-			const uint32_t gc = gp[pos + fl] - gp[pos];
-			bias = mul_rn(p.general, gc_bias[percent_u32(gc, fl)]);
-			bias = mul_rn(bias, ss[pos]);
-			bias = mul_rn(bias, se[pos]);
-			if(bias > mx){ mx = bias; }
-		}
+		const double bias = next;
+		next = term(base + 32 + lane);
+		if(bias > mx){ mx = bias; }
 		const uint32_t cnt = min(32u, n_pos - base);
 		if(cnt == 32u){
 #pragma unroll
@@ -163,25 +166,49 @@ __global__ void k_sum_bias(const BiasParamDev *params, uint32_t n_params, const 
 	if(lane == 0){ sums[i] = tot; max_bias[i] = mx; }
 }
 
-// Serial continuation of the master mt19937_64: state[0..311] + state[312] = index, `n` outputs appended to out.
-__global__ void k_master_stream(uint64_t *state, uint64_t *out, uint64_t n){
-	__shared__ uint64_t s[kMtN];
-	WarpGroup g;
-	for(int i = threadIdx.x; i < kMtN; i += 32){ s[i] = state[i]; }
-	Mt mt; mt.s = s; mt.idx = static_cast<int>(state[kMtN]);
-	__syncwarp();
+// Continuation of the master mt19937_64 (Simulator::block_seed_gen_): state[0..311] is any window of 312
+// consecutive words of the MT sequence x[], state[312] how many of them were already handed out; `n` further
+// outputs are appended to out.  x[m+312] = x[m+156] ^ twist(x[m], x[m+1]) only looks >= 156 words back, so one
+// CTA advances 156 words per step through a 4 x 156 word ring in shared memory (one barrier per step).
+constexpr int kMasterThreads = 160;
+__global__ void __launch_bounds__(kMasterThreads) k_master_stream(uint64_t *state, uint64_t *out, uint64_t n){
+	__shared__ uint64_t ring[4 * kMtM];
+	const uint32_t j = threadIdx.x;
+	for(uint32_t i = j; i < kMtN; i += blockDim.x){ ring[i] = state[i]; }
+	uint32_t idx = static_cast<uint32_t>(state[kMtN]);
+	__syncthreads();
 	uint64_t done = 0;
-	while(done < n){
-		if(mt.idx >= kMtN){ mt_regen(g, mt); }
-		uint64_t take = kMtN - mt.idx;
-		if(take > n - done){ take = n - done; }
-		for(uint64_t i = threadIdx.x; i < take; i += 32){ out[done + i] = mt_temper(s[mt.idx + i]); }
-		mt.idx += static_cast<int>(take);
-		done += take;
+	{
+		const uint64_t avail = kMtN - idx;
+		const uint64_t take = avail < n ? avail : n;
+		for(uint64_t i = j; i < take; i += blockDim.x){ out[i] = mt_temper(ring[idx + i]); }
+		done = take; idx += static_cast<uint32_t>(take);
 	}
-	__syncwarp();
-	for(int i = threadIdx.x; i < kMtN; i += 32){ state[i] = s[i]; }
-	if(threadIdx.x == 0){ state[kMtN] = static_cast<uint64_t>(mt.idx); }
+	uint32_t k = 0, last_take = 0;
+	while(done < n){
+		const uint32_t s0 = (k & 3u) * kMtM, s1 = ((k + 1u) & 3u) * kMtM, s2 = ((k + 2u) & 3u) * kMtM;
+		const uint64_t left = n - done;
+		last_take = left < static_cast<uint64_t>(kMtM) ? static_cast<uint32_t>(left) : kMtM;
+		if(j < kMtM){
+			const uint64_t a = ring[s0 + j];
+			const uint64_t b = (j + 1u < kMtM) ? ring[s0 + j + 1u] : ring[s1];
+			const uint64_t c = ring[s1 + j];
+			const uint64_t w = (a & 0xFFFFFFFF80000000ull) | (b & 0x7FFFFFFFull);
+			const uint64_t v = c ^ (w >> 1) ^ ((w & 1ull) ? 0xB5026F5AA96619E9ull : 0ull);
+			ring[s2 + j] = v;
+			if(j < last_take){ out[done + j] = mt_temper(v); }
+		}
+		done += last_take;
+		++k;
+		__syncthreads();
+	}
+	// persist the window made of the two most recent segments
+	if(k){
+		const uint32_t s0 = (k & 3u) * kMtM, s1 = ((k + 1u) & 3u) * kMtM;
+		for(uint32_t i = j; i < kMtM; i += blockDim.x){ state[i] = ring[s0 + i]; state[kMtM + i] = ring[s1 + i]; }
+		if(j == 0){ state[kMtN] = kMtM + last_take; }
+	}
+	else if(j == 0){ state[kMtN] = idx; }
 }
 
 __global__ void k_master_seed(uint64_t *state, uint64_t seed){
@@ -249,43 +276,46 @@ struct Arena {
 
 struct DeviceSink {
 	Arena a;
-	uint32_t cur[2], used[2], head[2];
-	unsigned long long bytes[2];
+	// per segment state kept in scalars (no dynamically indexed arrays -> stays in registers)
+	uint32_t cur0, cur1, used0, used1, head0, head1;
+	unsigned long long bytes0, bytes1;
 	uint32_t pairs;
-	__device__ void init(const Arena &arena){ a = arena; cur[0] = cur[1] = kNone; used[0] = used[1] = 0; head[0] = head[1] = kNone; bytes[0] = bytes[1] = 0; pairs = 0; }
+	__device__ void init(const Arena &arena){ a = arena; cur0 = cur1 = kNone; used0 = used1 = 0; head0 = head1 = kNone; bytes0 = bytes1 = 0; pairs = 0; }
 	__device__ void write_record(const WarpGroup &g, uint32_t seg, const char *id, int id_len, const uint8_t *seq, const uint8_t *qual, uint32_t n){
 		const uint32_t rec = 1u + id_len + 1u + n + 3u + n + 1u;
 		if(rec > a.chunk_bytes){ if(g.lane() == 0){ atomicOr(a.error_flag, kErrRecordTooLong); } return; }
-		if(cur[seg] == kNone || used[seg] + rec > a.chunk_bytes){
+		uint32_t cur = seg ? cur1 : cur0, used = seg ? used1 : used0;
+		if(cur == kNone || used + rec > a.chunk_bytes){
 			uint32_t idx = kNone;
 			if(g.lane() == 0){
 				idx = atomicAdd(a.next_free, 1u);
 				if(idx >= a.n_chunks){ atomicOr(a.error_flag, kErrArenaFull); idx = kNone; }
 				else{
 					a.chunk_next[idx] = kNone; a.chunk_used[idx] = 0;
-					if(cur[seg] != kNone){ a.chunk_next[cur[seg]] = idx; }
+					if(cur != kNone){ a.chunk_next[cur] = idx; }
 				}
 			}
 			idx = __shfl_sync(0xffffffffu, idx, 0);
 			if(idx == kNone){ return; }
-			if(cur[seg] == kNone){ head[seg] = idx; }
-			cur[seg] = idx; used[seg] = 0;
+			if(cur == kNone){ if(seg){ head1 = idx; } else{ head0 = idx; } }
+			cur = idx; used = 0;
 		}
-		unsigned char *dst = a.data + static_cast<size_t>(cur[seg]) * a.chunk_bytes + used[seg];
+		unsigned char *dst = a.data + static_cast<size_t>(cur) * a.chunk_bytes + used;
 		const uint32_t o_seq = 2u + id_len, o_plus = o_seq + n, o_qual = o_plus + 3u;
 		for(uint32_t i = g.lane(); i < rec; i += 32){
 			unsigned char ch;
 			if(i == 0){ ch = '@'; }
 			else if(i < 1u + id_len){ ch = static_cast<unsigned char>(id[i - 1]); }
 			else if(i < o_seq){ ch = '\n'; }
-			else if(i < o_plus){ const uint8_t b = seq[i - o_seq]; ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'G' : b == 3 ? 'T' : 'N'; }
+			else if(i < o_plus){ const uint32_t b = seq[i - o_seq]; ch = static_cast<unsigned char>(b > 3u ? 'N' : (0x54474341u >> (8u * b)) & 0xffu); }
 			else if(i < o_qual){ ch = (i == o_plus + 1u) ? '+' : '\n'; }
 			else if(i < o_qual + n){ ch = qual[i - o_qual]; }
 			else{ ch = '\n'; }
 			dst[i] = ch;
 		}
-		used[seg] += rec; bytes[seg] += rec;
-		if(g.lane() == 0){ a.chunk_used[cur[seg]] = used[seg]; }
+		used += rec;
+		if(seg){ cur1 = cur; used1 = used; bytes1 += rec; } else{ cur0 = cur; used0 = used; bytes0 += rec; }
+		if(g.lane() == 0){ a.chunk_used[cur] = used; }
 		g.sync();
 	}
 	__device__ void pair_done(const WarpGroup &){ ++pairs; }
@@ -311,7 +341,7 @@ k_simulate(SimCtx c, const BlockDesc *blocks, uint32_t first_block, uint32_t n_b
 		simulate_block(g, c, s, sink, b, &draws);
 		draws = __shfl_sync(0xffffffffu, draws, 0);
 		if(g.lane() == 0){
-			BlockOut o; o.head[0] = sink.head[0]; o.head[1] = sink.head[1]; o.bytes[0] = sink.bytes[0]; o.bytes[1] = sink.bytes[1];
+			BlockOut o; o.head[0] = sink.head0; o.head[1] = sink.head1; o.bytes[0] = sink.bytes0; o.bytes[1] = sink.bytes1;
 			o.pairs = sink.pairs; o.pad = 0; o.scan_draws = draws;
 			out[i] = o;
 		}
@@ -329,7 +359,7 @@ __global__ void k_adapter_only(SimCtx c, uint64_t seed, uint32_t count, Arena ar
 	uint64_t read_number = 0;
 	create_reads(g, c, s, mt, sink, count, false, 0, 0, read_number, 0, 0, 0);
 	if(g.lane() == 0){
-		BlockOut o; o.head[0] = sink.head[0]; o.head[1] = sink.head[1]; o.bytes[0] = sink.bytes[0]; o.bytes[1] = sink.bytes[1];
+		BlockOut o; o.head[0] = sink.head0; o.head[1] = sink.head1; o.bytes[0] = sink.bytes0; o.bytes[1] = sink.bytes1;
 		o.pairs = sink.pairs; o.pad = 0; o.scan_draws = 0;
 		out[slot] = o;
 	}
@@ -427,7 +457,7 @@ k_error_model(SimCtx c, const EmRecord *recs, uint32_t n_recs, uint32_t batch_si
 			sink.pair_done(g);
 		}
 		if(g.lane() == 0){
-			BlockOut o; o.head[0] = sink.head[0]; o.head[1] = kNone; o.bytes[0] = sink.bytes[0]; o.bytes[1] = 0; o.pairs = sink.pairs; o.pad = 0; o.scan_draws = 0;
+			BlockOut o; o.head[0] = sink.head0; o.head[1] = kNone; o.bytes[0] = sink.bytes0; o.bytes[1] = 0; o.pairs = sink.pairs; o.pad = 0; o.scan_draws = 0;
 			out[bi] = o;
 		}
 	}
@@ -774,7 +804,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		}
 		if(n_draws){
 			e.d_master.alloc(n_draws);
-			k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
+			k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
 			for(const auto &o : order){
 				const uint32_t off = e.h_adapter_off[o.seg][o.a], len = e.h_adapter_off[o.seg][o.a + 1] - off;
 				SysChain ch{}; ch.seq = e.d_adapter_seq.p + off; ch.L = len; ch.reverse = 0; ch.raw = e.d_master.p + o.raw_off; ch.seed_interleaved = 0;
@@ -805,7 +835,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
 		const uint64_t n_draws = 2ull * nb + 4ull * L;
-		k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
+		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
 		const uint8_t *hseq = g.seqs[i].data();
 		std::vector<SysChain> chains(2); std::vector<std::pair<uint32_t, uint32_t>> lens{{L, 0}, {L, 0}};
 		chains[0].seq = e.d_ref.p + seq_off[i]; chains[0].L = L; chains[0].reverse = 1; chains[0].raw = e.d_master.p + nb; chains[0].seed_interleaved = 0;
@@ -826,7 +856,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	e.n_blocks_sim = nb_total > lookahead ? nb_total - lookahead : 0;
 	e.adapter_only_seed = 0;
 	if(e.adapter_only_pairs){
-		k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, e.d_master.p, 1); ++e.launches;
+		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, 1); ++e.launches;
 		RSQ_CUDA(cudaMemcpyAsync(&e.adapter_only_seed, e.d_master.p, 8, cudaMemcpyDeviceToHost, s));
 		RSQ_CUDA(cudaStreamSynchronize(s));
 	}
@@ -1006,7 +1036,7 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 		for(int seg = 2; seg--; ){ for(size_t a = p.adapter_count_sum[seg].size(); a--; ){ if(!p.adapter_count_sum[seg][a]){ continue; } order.push_back({seg, a, n_draws}); n_draws += 2ull * (e.h_adapter_off[seg][a + 1] - e.h_adapter_off[seg][a]); } }
 		if(n_draws){
 			e.d_master.alloc(n_draws);
-			k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
+			k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
 			for(const auto &o : order){
 				const uint32_t off = e.h_adapter_off[o.seg][o.a], len = e.h_adapter_off[o.seg][o.a + 1] - off;
 				SysChain ch{}; ch.seq = e.d_adapter_seq.p + off; ch.L = len; ch.raw = e.d_master.p + o.raw_off; ch.out = e.d_adapter_sys.p + 2 * off; ch.carried_dom = carried;
@@ -1020,7 +1050,7 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 	const uint32_t batch = 10000;
 	const uint32_t n_batches = (recs.size() + batch - 1) / batch;
 	DevBuf<uint64_t> d_seeds; d_seeds.alloc(n_batches);
-	k_master_stream<<<1, 32, 0, s>>>(e.d_master_state.p, d_seeds.p, n_batches); ++e.launches;
+	k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, d_seeds.p, n_batches); ++e.launches;
 	DevBuf<EmRecord> d_recs; d_recs.upload(recs, s);
 	DevBuf<uint8_t> d_seq, d_dom, d_rate; d_seq.upload(hseq, s); d_dom.upload(hdom, s); d_rate.upload(hrate, s);
 	DevBuf<char> d_ids; d_ids.upload(hid.data(), hid.size() + 1, s);

@@ -127,11 +127,19 @@ RSQ_HD Scratch carve_scratch(unsigned char *base, uint32_t max_n0, uint32_t max_
 // small text helpers (lane-uniform; every lane computes the same lengths, lane 0 stores)
 // ---------------------------------------------------------------------------------------------------
 template<class G> RSQ_HD int put_uint(const G &g, char *dst, int pos, int cap, uint64_t v){
-	char tmp[20];
-	int n = 0;
-	do{ tmp[n++] = static_cast<char>('0' + v % 10); v /= 10; }while(v);
-	if(g.lane() == 0){
-		for(int i = 0; i < n && pos + i < cap; ++i){ dst[pos + i] = tmp[n - 1 - i]; }
+	int n = 1;
+	if(v <= 0xffffffffull){
+		uint32_t w = static_cast<uint32_t>(v);
+		for(uint32_t t = w; t >= 10u; t /= 10u){ ++n; }
+		if(g.lane() == 0){
+			for(int i = n - 1; i >= 0; --i){ if(pos + i < cap){ dst[pos + i] = static_cast<char>('0' + w % 10u); } w /= 10u; }
+		}
+	}
+	else{
+		for(uint64_t t = v; t >= 10u; t /= 10u){ ++n; }
+		if(g.lane() == 0){
+			for(int i = n - 1; i >= 0; --i){ if(pos + i < cap){ dst[pos + i] = static_cast<char>('0' + v % 10u); } v /= 10u; }
+		}
 	}
 	return pos + n;
 }
@@ -625,17 +633,26 @@ RSQ_HD uint32_t chain_base(const uint8_t *seq, uint32_t L, bool reverse, uint32_
 
 // utilities::DominantBase state right before position p is drawn == after Update at p-1
 // (utilities.hpp:229-293): counts over the previous min(p,5) bases, ties -> base closest to p.
-RSQ_HD uint32_t dominant_before(const uint8_t *seq, uint32_t L, bool reverse, uint32_t p, uint32_t carried){
-	if(p == 0){ return carried; }
-	uint32_t cnt[4] = {0, 0, 0, 0};
-	const uint32_t lo = p > 5 ? p - 5 : 0;
-	for(uint32_t q = lo; q < p; ++q){ ++cnt[chain_base(seq, L, reverse, q)]; }
-	uint32_t mx = cnt[0];
-	for(int b = 1; b < 4; ++b){ if(cnt[b] > mx){ mx = cnt[b]; } }
-	uint32_t q = p;
+// hist: the previous min(p,5) bases, 2 bits each, most recent in the low bits; n: how many are valid
+RSQ_HD uint32_t dominant_from_window(uint32_t hist, uint32_t n, uint32_t carried){
+	if(n == 0){ return carried; }
+	uint32_t cnt = 0;   // four 8-bit counters
+	for(uint32_t k = 0; k < n; ++k){ cnt += 1u << (8u * ((hist >> (2u * k)) & 3u)); }
+	uint32_t mx = cnt & 0xffu;
+	for(uint32_t b = 1; b < 4; ++b){ const uint32_t v = (cnt >> (8u * b)) & 0xffu; if(v > mx){ mx = v; } }
 	uint32_t base;
-	do{ base = chain_base(seq, L, reverse, --q); }while(cnt[base] != mx);
+	do{ base = hist & 3u; hist >>= 2; }while(((cnt >> (8u * base)) & 0xffu) != mx);
 	return base;
+}
+RSQ_HD void window_before(const uint8_t *seq, uint32_t L, bool reverse, uint32_t p, uint32_t &hist, uint32_t &n){
+	const uint32_t lo = p > 5 ? p - 5 : 0;
+	hist = 0; n = p - lo;
+	for(uint32_t q = lo; q < p; ++q){ hist = ((hist << 2) | chain_base(seq, L, reverse, q)) & 0x3ffu; }
+}
+RSQ_HD uint32_t dominant_before(const uint8_t *seq, uint32_t L, bool reverse, uint32_t p, uint32_t carried){
+	uint32_t hist, n;
+	window_before(seq, L, reverse, p, hist, n);
+	return dominant_from_window(hist, n, carried);
 }
 
 // raw draw k (0: dominant error, 1: error rate) of chain coordinate p.  Reverse-strand and adapter chains own a
@@ -658,10 +675,12 @@ RSQ_HD SysState sys_error_chain(const G &g, const Tables &tab, double *prob, con
 		gc += (b == 1 || b == 2) ? 1u : 0u;
 	}
 	uint32_t last_base = begin ? chain_base(seq, L, reverse, begin - 1) : 4u;
+	uint32_t hist, nwin;
+	window_before(seq, L, reverse, begin, hist, nwin);
 	bool zero;
 	for(uint32_t p = begin; p < end; ++p){
 		const uint32_t ref_base = chain_base(seq, L, reverse, p);
-		const uint32_t dom_base = dominant_before(seq, L, reverse, p, carried_dom);
+		const uint32_t dom_base = dominant_from_window(hist, nwin, carried_dom);
 		const uint32_t gc_percent = gc_bases ? percent_u16(gc, gc_bases) : 50u;
 		const uint32_t dist = (st.distance + 9) / 10;
 		const double u1 = canonical(chain_raw(raw, seed_interleaved, p, 0));
@@ -676,6 +695,8 @@ RSQ_HD SysState sys_error_chain(const G &g, const Tables &tab, double *prob, con
 			out[2 * static_cast<size_t>(p) + 1] = static_cast<uint8_t>(error_rate);
 		}
 		last_base = ref_base;
+		hist = ((hist << 2) | ref_base) & 0x3ffu;
+		if(nwin < 5){ ++nwin; }
 		// CoverageStats::UpdateDistances (CoverageStats.cpp:379-396)
 		if(st.distance){
 			if(st.start_rate < error_rate){ st.distance = 0; st.start_rate = error_rate; }
