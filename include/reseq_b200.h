@@ -31,6 +31,11 @@ rsq_profile *rsq_profile_load(const char *stats_path, const char *ipf_path);
 rsq_profile *rsq_profile_load_flat(const char *flat_path);
 int rsq_profile_save_flat(const rsq_profile *profile, const char *flat_path);
 void rsq_profile_free(rsq_profile *profile);
+/* ProbabilityEstimates::RemoveInDelErrors / RemoveSubstitutionErrors / ChangeErrorRate (ProbabilityEstimates.h:1516-1549),
+ * i.e. the CLI switches --noInDelErrors, --noSubstitutionErrors, --errorMutliplier; apply before rsq_engine_create. */
+int rsq_profile_remove_indel_errors(rsq_profile *profile);
+int rsq_profile_remove_substitution_errors(rsq_profile *profile);
+int rsq_profile_change_error_rate(rsq_profile *profile, double error_multiplier);
 
 /* --- reference -----------------------------------------------------------------------------------
  * Reference::ReadFasta (Reference.cpp:758-811): IUPAC text -> Dna5 (ACGT/acgt/U -> 0..3, anything else N). */

@@ -41,6 +41,9 @@ SIGNATURES = {
     "rsq_profile_load_flat": (C.c_void_p, [C.c_char_p]),
     "rsq_profile_save_flat": (C.c_int, [C.c_void_p, C.c_char_p]),
     "rsq_profile_free": (None, [C.c_void_p]),
+    "rsq_profile_remove_indel_errors": (C.c_int, [C.c_void_p]),
+    "rsq_profile_remove_substitution_errors": (C.c_int, [C.c_void_p]),
+    "rsq_profile_change_error_rate": (C.c_int, [C.c_void_p, C.c_double]),
     "rsq_reference_load_fasta": (C.c_void_p, [C.c_char_p]),
     "rsq_reference_from_memory": (C.c_void_p, [C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_uint64)]),
     "rsq_reference_total_size": (C.c_uint64, [C.c_void_p]),
@@ -103,6 +106,21 @@ class Profile:
         if not h:
             raise _err(lib)
         return cls(h)
+
+    def remove_indel_errors(self):
+        """ProbabilityEstimates::RemoveInDelErrors (--noInDelErrors)."""
+        if load_library().rsq_profile_remove_indel_errors(self._h):
+            raise _err(load_library())
+
+    def remove_substitution_errors(self):
+        """ProbabilityEstimates::RemoveSubstitutionErrors (--noSubstitutionErrors)."""
+        if load_library().rsq_profile_remove_substitution_errors(self._h):
+            raise _err(load_library())
+
+    def change_error_rate(self, error_multiplier):
+        """ProbabilityEstimates::ChangeErrorRate (--errorMutliplier)."""
+        if load_library().rsq_profile_change_error_rate(self._h, error_multiplier):
+            raise _err(load_library())
 
     def save_flat(self, path):
         lib = load_library()

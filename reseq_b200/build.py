@@ -9,6 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libreseq_b200.so")
+CLI = os.path.join(HERE, "reseq-b200")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -35,8 +36,18 @@ def needs_build():
     return os.path.getmtime(inc) > t
 
 
+def build_cli():
+    """reseq-b200: the `reseq illuminaPE` / `reseq seqToIllumina` command line over the C ABI."""
+    cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-o", CLI, os.path.join(CSRC, "cli_main.cpp"),
+           "-L" + HERE, "-lreseq_b200", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building reseq-b200")
+
+
 def build(force=False, verbose=False):
-    if not force and not needs_build():
+    if not force and not needs_build() and os.path.exists(CLI):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
@@ -45,6 +56,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode:
         raise RuntimeError("nvcc failed building libreseq_b200.so")
+    build_cli()
     return LIB
 
 

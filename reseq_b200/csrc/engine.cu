@@ -1125,6 +1125,43 @@ int rsq_profile_save_flat(const rsq_profile *profile, const char *flat_path){
 
 void rsq_profile_free(rsq_profile *profile){ delete profile; }
 
+// LogArrayResult::SetPar0 (ProbabilityEstimates.h:547-556)
+static void set_par0(HostTable &h, uint32_t value){
+	h.par0.assign(1, value);
+	for(uint32_t n = 0; n < h.nm; ++n){ h.dim2[n].assign(h.to[n] - h.from[n], 1.0); }
+}
+
+int rsq_profile_remove_indel_errors(rsq_profile *profile){
+	RSQ_TRY
+	const uint32_t T = profile->p.num_tiles, base = 50 * T + 120;
+	for(uint32_t i = 0; i < 12; ++i){ set_par0(profile->p.tables.at(base + i), 0); }
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_profile_remove_substitution_errors(rsq_profile *profile){
+	RSQ_TRY
+	const uint32_t T = profile->p.num_tiles, base = 10 * T;
+	for(uint32_t st = 0; st < 2 * T; ++st){ for(uint32_t b = 0; b < 4; ++b){ for(uint32_t d = 0; d < 5; ++d){ set_par0(profile->p.tables.at(base + (st * 4 + b) * 5 + d), b); } } }
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_profile_change_error_rate(rsq_profile *profile, double error_multiplier){
+	RSQ_TRY
+	if(!(error_multiplier > 0.0)){ throw std::runtime_error("--error_multiplier must be a positive value."); }
+	const uint32_t T = profile->p.num_tiles, base = 10 * T;
+	const double multiplier = 1.0 / error_multiplier;
+	for(uint32_t st = 0; st < 2 * T; ++st){ for(uint32_t b = 0; b < 4; ++b){ for(uint32_t d = 0; d < 5; ++d){
+		HostTable &h = profile->p.tables.at(base + (st * 4 + b) * 5 + d);   // LogArrayResult::ModifyPar0(ref_base, 1/multiplier)
+		size_t col = 0;
+		while(col < h.par0.size() && h.par0[col] != b){ ++col; }
+		if(col < h.par0.size()){ for(size_t i = col; i < h.dim2[0].size(); i += h.par0.size()){ h.dim2[0][i] *= multiplier; } }
+	} } }
+	return 0;
+	RSQ_CATCH(1)
+}
+
 rsq_reference *rsq_reference_load_fasta(const char *fasta_path){
 	RSQ_TRY
 	std::unique_ptr<rsq_reference> r(new rsq_reference);

@@ -76,3 +76,31 @@ def test_flat_profile_roundtrip(library, golden, workdir):
     assert set(a) == set(b)
     for k in a:
         assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+
+
+def test_reseq_archive_loader_matches_reference_memory_image(library, golden, workdir):
+    """rsq_profile_load(X.reseq, X.reseq.ipf) == what the reference holds after DataStats::Load + PrepareProcessing +
+    ProbabilityEstimates::Estimate(0 iterations) + PrepareResult (golden flat file written by oracle/dump_tables)."""
+    import numpy as np
+    import reseq_b200 as rb
+    from reseq_b200.flatfile import read_flat
+    prof = rb.Profile.load(golden["reseq"], golden["ipf"])
+    out = os.path.join(workdir, "from_archive.flat")
+    prof.save_flat(out)
+    a, b = read_flat(golden["flat"]), read_flat(out)
+    assert set(a) == set(b)
+    for k in a:
+        assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+
+
+def test_archive_loader_rejects_foreign_ipf(library, golden, workdir):
+    import reseq_b200 as rb
+    bad = os.path.join(workdir, "foreign.ipf")
+    text = open(golden["ipf"]).read()
+    head, rest = text.split(" ", 3)[:3], text.split(" ", 3)[3]
+    # third token after the header is stats_creation_time_: change it
+    toks = rest.split(" ", 3)
+    toks[2] = str(int(toks[2]) + 1)
+    open(bad, "w").write(" ".join(head) + " " + " ".join(toks))
+    with pytest.raises(rb.RsqError, match="creation time"):
+        rb.Profile.load(golden["reseq"], bad)

@@ -129,6 +129,43 @@ def test_num_read_pairs_option_against_reference_binary(rb, engine, golden, orac
     assert r2 == open(o2, "rb").read()
 
 
+@pytest.mark.parametrize("switch", ["noInDelErrors", "noSubstitutionErrors", "errorMutliplier"])
+def test_error_switches_against_reference_binary(rb, golden, oracle, workdir, switch):
+    """--noInDelErrors / --noSubstitutionErrors / --errorMutliplier 2.5 (ProbabilityEstimates.h:1516-1549)."""
+    prof = rb.Profile.load(golden["reseq"], golden["ipf"])
+    extra = ("--" + switch,)
+    if switch == "noInDelErrors":
+        prof.remove_indel_errors()
+    elif switch == "noSubstitutionErrors":
+        prof.remove_substitution_errors()
+    else:
+        prof.change_error_rate(2.5)
+        extra = ("--errorMutliplier", "2.5")
+    eng = rb.Engine(prof, 0)
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    r1, r2, _ = _simulate(eng, ref, seed=11, coverage=8.0)
+    eng.close()
+    o1, o2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], 11, 8.0, os.path.join(workdir, "ora_" + switch), extra=extra)
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+
+
+def test_cli_dropin(golden, workdir, library):
+    """reseq-b200 illuminaPE / seqToIllumina with the reference's own option names, reading X.reseq + X.reseq.ipf."""
+    from reseq_b200 import build
+    o1, o2 = os.path.join(workdir, "cli1.fq"), os.path.join(workdir, "cli2.fq")
+    subprocess.run([build.CLI, "illuminaPE", "-j", "4", "-s", golden["reseq"], "-R", golden["small_ref"], "--ipfIterations", "0", "--seed", "42",
+                    "-c", "20", "-1", o1, "-2", o2, "--verbosity", "1"], check=True, timeout=600)
+    assert open(o1, "rb").read() == open(golden["r1"], "rb").read()
+    assert open(o2, "rb").read() == open(golden["r2"], "rb").read()
+    em = os.path.join(workdir, "cli_em.fq")
+    subprocess.run([build.CLI, "seqToIllumina", "-i", golden["em_in"], "-o", em, "-s", golden["reseq"], "--ipfIterations", "0", "--seed", "7",
+                    "--verbosity", "1"], check=True, timeout=600)
+    assert open(em, "rb").read() == open(golden["em_out"], "rb").read()
+    res = subprocess.run([build.CLI, "illuminaPE", "-s", golden["reseq"], "-R", golden["small_ref"], "-V", "x.vcf"], capture_output=True, text=True)
+    assert res.returncode == 1 and "does not replace" in res.stderr
+
+
 def test_shards_concatenate_to_the_whole_run(rb, engine, golden):
     ref = rb.Reference.load_fasta(golden["small_ref"])
     w1, w2, rep = _simulate(engine, ref, seed=42, coverage=20.0)
