@@ -94,6 +94,23 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def shard_range(n_blocks, shard_index, shard_count):
+    """Block range an engine simulates for (shard_index, shard_count): mirrors prepare() in csrc/engine.cu."""
+    first = n_blocks * shard_index // shard_count
+    return first, n_blocks * (shard_index + 1) // shard_count - first
+
+
+def aggregate(dist, world, maxima, sums, device):
+    """Max over ranks of the timings, sum over ranks of the counts (the only cross-rank traffic of the path)."""
+    import torch
+    t = torch.tensor(maxima, dtype=torch.float64, device=device)
+    s = torch.tensor(sums, dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return t.tolist(), s.tolist()
+
+
 def time_reference_cpu(length, coverage, threads, tmp):
     """Runs the reference binary on `length` bases of the workload; returns (pairs, seconds of read generation, total seconds)."""
     prof = unxz("profile150.reseq.xz", tmp)
@@ -205,13 +222,8 @@ def run_b200(args):
     positions = sum(r["positions"] for r in reps)
     launches = sum(r["kernel_launches"] for r in reps)
     d2h = sum(r["bytes"][0] + r["bytes"][1] for r in reps)
-    t = torch.tensor([dev_ms, wall, sim_ms], dtype=torch.float64, device="cuda")
-    s = torch.tensor([pairs, positions, launches, d2h], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    dev_ms, wall, sim_ms_max = t.tolist()
-    pairs_all, positions_all, launches_all, d2h_all = s.tolist()
+    (dev_ms, wall, sim_ms_max), (pairs_all, positions_all, launches_all, d2h_all) = aggregate(
+        dist, world, [dev_ms, wall, sim_ms], [pairs, positions, launches, d2h], "cuda")
 
     if rank == 0:
         peak, peak_src = hbm_peak()
