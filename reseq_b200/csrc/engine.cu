@@ -132,27 +132,37 @@ __global__ void k_sum_bias(const BiasParamDev *params, uint32_t n_params, const 
                            double *sums, double *max_bias){
 	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t lane = threadIdx.x & 31;
-	if(i >= n_params){ return; }
-	const BiasParamDev p = params[i];
+	const bool active = i < n_params;
+	const BiasParamDev p = params[active ? i : 0];
 	const uint64_t off = seq_off[p.ref_id];
 	const uint32_t L = seq_len[p.ref_id], fl = p.fragment_length;
 	const double *ss = sur_start + off, *se = sur_end + off + fl - 1;
 	const uint32_t *gp = gc_prefix + off + p.ref_id;
-	const uint32_t n_pos = L - fl + 1;
+	const uint32_t n_pos = active ? L - fl + 1 : 0;
 	double tot = 0.0, mx = 0.0;
-	// software pipeline: the loads of tile t+1 are in flight while tile t is being added up
-	auto term = [&](uint32_t pos) -> double {
-		if(pos >= n_pos){ return 0.0; }
-		const uint32_t gc = gp[pos + fl] - gp[pos];
-		double bias = mul_rn(p.general, gc_bias[percent_u32(gc, fl)]);
-		bias = mul_rn(bias, ss[pos]);
-		return mul_rn(bias, se[pos]);
+	// gc_bias lives in shared memory so that a term needs one level of global loads only; the raw operands of the
+	// next two tiles are in flight while the current tile is added up (the add chain is ~400 cycles per tile).
+	__shared__ double s_gc[101];
+	for(uint32_t k = threadIdx.x; k < 101; k += blockDim.x){ s_gc[k] = gc_bias[k]; }
+	__syncthreads();
+	struct Raw { uint32_t g0, g1; double a, b; };
+	auto fetch = [&](uint32_t pos) -> Raw {
+		Raw r{0, 0, 0.0, 0.0};
+		if(pos < n_pos){ r.g0 = gp[pos]; r.g1 = gp[pos + fl]; r.a = ss[pos]; r.b = se[pos]; }
+		return r;
 	};
-	double next = term(lane);
+	Raw r1 = fetch(lane), r2 = fetch(32 + lane);
 	for(uint32_t base = 0; base < n_pos; base += 32){
-		const double bias = next;
-		next = term(base + 32 + lane);
-		if(bias > mx){ mx = bias; }
+		const Raw cur = r1;
+		r1 = r2;
+		r2 = fetch(base + 64 + lane);
+		double bias = 0.0;
+		if(base + lane < n_pos){
+			bias = mul_rn(p.general, s_gc[percent_u32(cur.g1 - cur.g0, fl)]);
+			bias = mul_rn(bias, cur.a);
+			bias = mul_rn(bias, cur.b);
+			if(bias > mx){ mx = bias; }
+		}
 		const uint32_t cnt = min(32u, n_pos - base);
 		if(cnt == 32u){
 #pragma unroll
@@ -163,7 +173,7 @@ __global__ void k_sum_bias(const BiasParamDev *params, uint32_t n_params, const 
 		}
 	}
 	for(int o = 16; o; o >>= 1){ mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-	if(lane == 0){ sums[i] = tot; max_bias[i] = mx; }
+	if(lane == 0 && active){ sums[i] = tot; max_bias[i] = mx; }
 }
 
 // Continuation of the master mt19937_64 (Simulator::block_seed_gen_): state[0..311] is any window of 312
@@ -323,7 +333,7 @@ struct DeviceSink {
 
 struct BlockOut { uint32_t head[2]; unsigned long long bytes[2]; uint32_t pairs; uint32_t pad; unsigned long long scan_draws; };
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8)   // 8 CTAs x 4 warps = 32 blocks in flight per SM (<= 64 registers)
 k_simulate(SimCtx c, const BlockDesc *blocks, uint32_t first_block, uint32_t n_blocks, Arena arena, BlockOut *out, uint32_t *next_block,
            uint32_t max_n0, uint32_t scratch_per_warp){
 	extern __shared__ __align__(16) unsigned char smem[];
