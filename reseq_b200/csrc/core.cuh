@@ -65,12 +65,16 @@ struct Tables {
 // Likelihood products run lane-parallel; the two sums run in the reference's exact sequential order
 // (forward over ind0 for prob_sum, backwards for the cumulative search) because FP64 addition is not
 // associative and the result must be bit-identical.
-// AdjustIndeces (ProbabilityEstimates.h:368-380) for one margin
+// AdjustIndeces (ProbabilityEstimates.h:368-380) for one margin: clamp into [from, from+span) and rebase
 RSQ_HD uint32_t adjust_index(uint32_t v, uint32_t from, uint32_t span){
-	return v < from ? 0u : (v >= from + span ? span - 1u : v - from);
+	const uint32_t hi = from + span - 1u;
+	const uint32_t c = v < from ? from : (v > hi ? hi : v);
+	return c - from;
 }
 
 // (A __noinline__ variant was measured: 128 registers and a 624-byte stack frame in k_simulate - worse.)
+// `prob` must hold round_up(n0, 4) doubles: the tail is padded with +0.0 so that the ordered sum can run four
+// candidates per trip without a remainder loop (x + 0.0 == x exactly for the non-negative likelihoods).
 template<class G>
 RSQ_HD uint32_t draw(const G &g, const Tables &t, uint32_t table_id, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3,
                      double random_number, double *prob, bool &zero_sum){
@@ -86,23 +90,23 @@ RSQ_HD uint32_t draw(const G &g, const Tables &t, uint32_t table_id, uint32_t i0
 	const double *r1 = t.blob + (d.off[1] + adjust_index(i1, d.from[1], d.span[1]) * n0);
 	const double *r2 = t.blob + (d.off[2] + adjust_index(i2, d.from[2], d.span[2]) * n0);
 	const double *r3 = four ? t.blob + (d.off[3] + adjust_index(i3, d.from[3], d.span[3]) * n0) : r0;
+	const uint32_t n4 = (n0 + 3u) & ~3u;
 	g.sync();  // previous consumer of `prob` is done
-	for(uint32_t i = g.lane(); i < n0; i += G::kSize){
-		double p = r0[i];
-		p = mul_rn(p, r1[i]);
-		p = mul_rn(p, r2[i]);
-		if(four){ p = mul_rn(p, r3[i]); }
+	for(uint32_t i = g.lane(); i < n4; i += G::kSize){
+		double p = 0.0;
+		if(i < n0){
+			p = r0[i];
+			p = mul_rn(p, r1[i]);
+			p = mul_rn(p, r2[i]);
+			if(four){ p = mul_rn(p, r3[i]); }
+		}
 		prob[i] = p;
 	}
 	g.sync();
 	double prob_sum = 0.0;
-	uint32_t i = 0;
-	for(; i + 4 <= n0; i += 4){   // same left-to-right order, four loads per trip
+	for(uint32_t i = 0; i < n4; i += 4){   // left-to-right like the reference, four candidates per trip
 		const double a = prob[i], b = prob[i + 1], c = prob[i + 2], e = prob[i + 3];
 		prob_sum = add_rn(add_rn(add_rn(add_rn(prob_sum, a), b), c), e);
-	}
-	for(; i < n0; ++i){
-		prob_sum = add_rn(prob_sum, prob[i]);
 	}
 	zero_sum = (0.0 == prob_sum);
 	const double r = mul_rn(random_number, prob_sum);

@@ -244,7 +244,7 @@ __global__ void k_sys_chunks(Tables tab, const SysChain *chains, SysChunk *chunk
 	extern __shared__ double prob_all[];
 	WarpGroup g;
 	const uint32_t warp = threadIdx.x >> 5;
-	double *prob = prob_all + static_cast<size_t>(warp) * ((max_n0 + 1) & ~1u);
+	double *prob = prob_all + static_cast<size_t>(warp) * ((max_n0 + 3) & ~3u);
 	const uint32_t c = blockIdx.x * (blockDim.x >> 5) + warp;
 	if(c >= n_chunks){ return; }
 	SysChunk ck = chunks[c];
@@ -627,10 +627,15 @@ static void upload_profile(rsq_engine &e){
 	for(int b = 0; b < 3; ++b){ e.d_sur_tab[b].upload(p.fragment_surroundings_bias[b], s); }
 	c.num_tiles = p.tiles.size(); e.d_tile_names.upload(p.tiles, s); c.tile_names = e.d_tile_names.p;
 	c.disp_a = p.dispersion_parameters[0]; c.disp_b = p.dispersion_parameters[1];
-	c.max_read_len = std::max(c.read_len_to[0], c.read_len_to[1]);
 	uint32_t max_adapter = 0;
 	for(int seg = 0; seg < 2; ++seg){ for(const auto &a : p.adapter_seqs[seg]){ max_adapter = std::max<uint32_t>(max_adapter, a.size()); } }
-	c.max_org_len = std::max(c.max_read_len + c.max_len_deletion, max_adapter) + 8;
+	const uint32_t need_read = std::max(c.read_len_to[0], c.read_len_to[1]);
+	if(e.max_n0 > kMaxN0 || need_read > kMaxReadLen || std::max(need_read + c.max_len_deletion, max_adapter) > kMaxOrgLen){
+		throw std::runtime_error("profile exceeds the engine's compile-time limits (candidates per table <= " + std::to_string(kMaxN0) + ", read length < " +
+		                         std::to_string(kMaxReadLen) + ", read + longest deletion / adapter length <= " + std::to_string(kMaxOrgLen) + ")");
+	}
+	c.max_read_len = kMaxReadLen;   // capacities of the per-warp scratch (sim_core.cuh)
+	c.max_org_len = kMaxOrgLen;
 	e.d_error_flag.alloc(1); e.d_error_flag.zero(s);
 	c.error_flag = e.d_error_flag.p;
 	RSQ_CUDA(cudaStreamSynchronize(s));
@@ -672,7 +677,7 @@ static void run_sys_chains(rsq_engine &e, const std::vector<SysChain> &chains, c
 	DevBuf<uint32_t> &d_dirty = e.d_sys_dirty; d_dirty.alloc(1);
 	const uint32_t n = chunks.size();
 	const int warps = 4;
-	const size_t shmem = static_cast<size_t>(warps) * ((e.max_n0 + 1) & ~1u) * 8;
+	const size_t shmem = static_cast<size_t>(warps) * ((e.max_n0 + 3) & ~3u) * 8;
 	uint32_t dirty = n;
 	passes = 0;
 	while(dirty){
@@ -1032,7 +1037,7 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 		recs[i] = r;
 		max_len = std::max<uint32_t>(max_len, L);
 	}
-	if(max_len + 8 > c.max_org_len){ c.max_org_len = max_len + 8; }
+	if(max_len > kMaxOrgLen){ throw std::runtime_error("input fragments longer than " + std::to_string(kMaxOrgLen) + " bases are not supported by this build"); }
 	// sys_gc_range + adapter systematic errors from the master stream, then one seed per 10000-record batch
 	uint64_t reads = 0, sum_read_length = 0;
 	for(int seg = 2; seg--; ){ for(auto len = p.read_lengths[seg].from; len < p.read_lengths[seg].to(); ++len){ reads += p.read_lengths[seg][len]; sum_read_length += p.read_lengths[seg][len] * len; } }
@@ -1064,7 +1069,7 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 	DevBuf<EmRecord> d_recs; d_recs.upload(recs, s);
 	DevBuf<uint8_t> d_seq, d_dom, d_rate; d_seq.upload(hseq, s); d_dom.upload(hdom, s); d_rate.upload(hrate, s);
 	DevBuf<char> d_ids; d_ids.upload(hid.data(), hid.size() + 1, s);
-	const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, std::max(c.max_read_len, max_len + 8));
+	const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, c.max_read_len);
 	const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta;
 	RSQ_CUDA(cudaFuncSetAttribute(k_error_model, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
 	Arena a;

@@ -91,35 +91,39 @@ enum : uint32_t { kErrCigarOverflow = 1, kErrCountRunaway = 2, kErrArenaFull = 4
 constexpr int kCigarCap = 192;
 constexpr int kIdCap = 384;
 
+// Group-shared scratch with a compile-time layout (constant offsets keep the pointers out of registers).
+constexpr uint32_t kMaxN0 = 128;       // largest candidate count of any table (error-rate tables: <= 101)
+constexpr uint32_t kMaxOrgLen = 384;   // read length + longest deletion, adapters, seqToIllumina fragments
+constexpr uint32_t kMaxReadLen = 320;
+constexpr uint32_t kScratchBytes = kMtN * 8 + kMaxN0 * 8 + 3 * kMaxOrgLen + 2 * kMaxReadLen + kCigarCap + kIdCap;
+
 struct Scratch {          // group-shared memory
+	unsigned char *base;
+	RSQ_HD uint64_t *mt_words() const { return reinterpret_cast<uint64_t *>(base); }
 	uint64_t *mt;         // kMtN
-	double *prob;         // max n0
-	uint8_t *org;         // max_org_len     original bases of the current part
-	uint8_t *sdom;        // max_org_len     dominant systematic error per original base
-	uint8_t *srate;       // max_org_len     systematic error rate per original base
-	uint8_t *seq;         // max_read_len    called bases (codes)
-	uint8_t *qual;        // max_read_len    qualities (already + phred offset)
+	double *prob;         // kMaxN0
+	uint8_t *org;         // kMaxOrgLen      original bases of the current part
+	uint8_t *sdom;        // kMaxOrgLen      dominant systematic error per original base
+	uint8_t *srate;       // kMaxOrgLen      systematic error rate per original base
+	uint8_t *seq;         // kMaxReadLen     called bases (codes)
+	uint8_t *qual;        // kMaxReadLen     qualities (already + phred offset)
 	char *cigar;          // kCigarCap
 	char *id;             // kIdCap
 };
 
-RSQ_HD size_t scratch_bytes(uint32_t max_n0, uint32_t max_org_len, uint32_t max_read_len){
-	size_t b = kMtN * 8 + ((max_n0 + 1) & ~1u) * 8;
-	b += 3 * ((max_org_len + 7) & ~7u) + 2 * ((max_read_len + 7) & ~7u) + kCigarCap + kIdCap;
-	return (b + 15) & ~static_cast<size_t>(15);
-}
-RSQ_HD Scratch carve_scratch(unsigned char *base, uint32_t max_n0, uint32_t max_org_len, uint32_t max_read_len){
+RSQ_HD size_t scratch_bytes(uint32_t, uint32_t, uint32_t){ return kScratchBytes; }
+RSQ_HD Scratch carve_scratch(unsigned char *base, uint32_t, uint32_t, uint32_t){
 	Scratch s;
-	s.mt = reinterpret_cast<uint64_t *>(base); base += kMtN * 8;
-	s.prob = reinterpret_cast<double *>(base); base += ((max_n0 + 1) & ~1u) * 8;
-	const uint32_t o = (max_org_len + 7) & ~7u, r = (max_read_len + 7) & ~7u;
-	s.org = base; base += o;
-	s.sdom = base; base += o;
-	s.srate = base; base += o;
-	s.seq = base; base += r;
-	s.qual = base; base += r;
-	s.cigar = reinterpret_cast<char *>(base); base += kCigarCap;
-	s.id = reinterpret_cast<char *>(base);
+	s.base = base;
+	s.mt = reinterpret_cast<uint64_t *>(base);
+	s.prob = reinterpret_cast<double *>(base + kMtN * 8);
+	s.org = base + kMtN * 8 + kMaxN0 * 8;
+	s.sdom = s.org + kMaxOrgLen;
+	s.srate = s.sdom + kMaxOrgLen;
+	s.seq = s.srate + kMaxOrgLen;
+	s.qual = s.seq + kMaxReadLen;
+	s.cigar = reinterpret_cast<char *>(s.qual + kMaxReadLen);
+	s.id = s.cigar + kCigarCap;
 	return s;
 }
 

@@ -154,7 +154,7 @@ int main(int argc, char **argv){
 	c.sur_start = st.sur_start.data(); c.sur_end = st.sur_end.data();
 	c.name_blob = st.names.data(); c.name_off = st.name_off.data();
 	c.base_id = "ReseqRead"; c.base_id_len = 9;
-	c.max_read_len = std::max(c.read_len_to[0], c.read_len_to[1]); c.max_org_len = c.max_read_len + c.max_len_deletion + 64;
+	c.max_read_len = kMaxReadLen; c.max_org_len = kMaxOrgLen;
 	c.error_flag = &st.error_flag;
 
 	// ---- normalisation (CalculateBiasNormalization) ----
@@ -200,7 +200,7 @@ int main(int argc, char **argv){
 	}
 	std::mt19937_64 master(seed);
 	SingleLane lane;
-	std::vector<double> prob(st.max_n0 + 2);
+	std::vector<double> prob(st.max_n0 + 4);
 	uint32_t carried = 0;
 	for(int seg = 2; seg--; ){
 		for(size_t a = p.adapter_count_sum[seg].size(); a--; ){
