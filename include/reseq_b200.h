@@ -41,6 +41,9 @@ int rsq_profile_change_error_rate(rsq_profile *profile, double error_multiplier)
  * Reference::ReadFasta (Reference.cpp:758-811): IUPAC text -> Dna5 (ACGT/acgt/U -> 0..3, anything else N). */
 rsq_reference *rsq_reference_load_fasta(const char *fasta_path);
 rsq_reference *rsq_reference_from_memory(uint32_t n_seqs, const char *const *ids, const char *const *bases, const uint64_t *lengths);
+/* Reference::PrepareMethylationFile + ReadMethylation (Reference.cpp:1132-1322), `--methylation <bed>`: extended bedGraph
+ * "<sequence> <start> <end> <methylation>"; reads simulated from this reference get bisulfite C->T conversions. */
+int rsq_reference_load_methylation(rsq_reference *ref, const char *bed_path);
 uint64_t rsq_reference_total_size(const rsq_reference *ref);       /* Reference::TotalSize */
 uint32_t rsq_reference_num_sequences(const rsq_reference *ref);    /* Reference::NumberSequences */
 void rsq_reference_free(rsq_reference *ref);

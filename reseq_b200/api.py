@@ -46,6 +46,7 @@ SIGNATURES = {
     "rsq_profile_change_error_rate": (C.c_int, [C.c_void_p, C.c_double]),
     "rsq_reference_load_fasta": (C.c_void_p, [C.c_char_p]),
     "rsq_reference_from_memory": (C.c_void_p, [C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_uint64)]),
+    "rsq_reference_load_methylation": (C.c_int, [C.c_void_p, C.c_char_p]),
     "rsq_reference_total_size": (C.c_uint64, [C.c_void_p]),
     "rsq_reference_num_sequences": (C.c_uint32, [C.c_void_p]),
     "rsq_reference_free": (None, [C.c_void_p]),
@@ -158,6 +159,12 @@ class Reference:
         if not h:
             raise _err(lib)
         return cls(h)
+
+    def load_methylation(self, bed_path):
+        """Reference::PrepareMethylationFile/ReadMethylation (--methylation)."""
+        lib = load_library()
+        if lib.rsq_reference_load_methylation(self._h, os.fsencode(bed_path)):
+            raise _err(lib)
 
     @property
     def total_size(self):

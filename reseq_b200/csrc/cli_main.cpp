@@ -67,7 +67,7 @@ void usage(){
 }
 
 int reject_unsupported(const Args &a){
-	for(const char *k : {"bamIn", "vcfSim", "methylation", "readSysError", "writeSysError", "refBiasFile", "vcfIn", "adapterFile", "adapterMatrix"}){
+	for(const char *k : {"bamIn", "vcfSim", "readSysError", "writeSysError", "refBiasFile", "vcfIn", "adapterFile", "adapterMatrix"}){
 		if(a.has(k)){ return err(std::string("option --") + k + " belongs to a part of ReSeq this engine does not replace (stats creation, variants, methylation, systematic-error files); run it with the reference implementation"); }
 	}
 	for(const char *k : {"statsOnly", "stopAfterEstimation"}){ if(a.flags.count(k)){ return err(std::string("option --") + k + " is a stats/IPF step; use the reference implementation"); } }
@@ -113,6 +113,7 @@ int run_illumina_pe(const Args &a){
 	info("Reading reference from " + ref_path);
 	rsq_reference *ref = rsq_reference_load_fasta(ref_path.c_str());
 	if(!ref){ return err(rsq_last_error()); }
+	if(a.has("methylation") && rsq_reference_load_methylation(ref, a.get("methylation").c_str())){ rsq_reference_free(ref); return err(rsq_last_error()); }
 	rsq_profile *prof = load_profile(a);
 	if(!prof){ rsq_reference_free(ref); return 1; }
 	rsq_sim_options opt{};

@@ -271,10 +271,11 @@ __global__ void k_sys_check(SysChunk *chunks, uint32_t n_chunks, uint32_t *n_dir
 	}
 }
 
-__global__ void k_build_blocks(BlockDesc *blocks, uint32_t first, uint32_t nb, uint32_t ref_id, uint32_t first_block_id, const uint64_t *fwd_raw){
+__global__ void k_build_blocks(BlockDesc *blocks, uint32_t first, uint32_t nb, uint32_t ref_id, uint32_t first_block_id, const uint64_t *fwd_raw,
+                               const int32_t *first_meth /* per block of the run, or null */){
 	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
 	if(b >= nb){ return; }
-	BlockDesc d; d.ref_id = ref_id; d.start_pos = b * 1000u; d.block_id = first_block_id + b; d.pad = 0;
+	BlockDesc d; d.ref_id = ref_id; d.start_pos = b * 1000u; d.block_id = first_block_id + b; d.first_meth = first_meth ? first_meth[first + b] : 0;
 	d.seed = fwd_raw[static_cast<size_t>(b) * 2001u];
 	blocks[first + b] = d;
 }
@@ -333,6 +334,7 @@ struct DeviceSink {
 
 struct BlockOut { uint32_t head[2]; unsigned long long bytes[2]; uint32_t pairs; uint32_t pad; unsigned long long scan_draws; };
 
+template<bool kMeth>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 8)   // 8 CTAs x 4 warps = 32 blocks in flight per SM (<= 64 registers)
 k_simulate(SimCtx c, const BlockDesc *blocks, uint32_t first_block, uint32_t n_blocks, Arena arena, BlockOut *out, uint32_t *next_block,
            uint32_t max_n0, uint32_t scratch_per_warp){
@@ -348,7 +350,7 @@ k_simulate(SimCtx c, const BlockDesc *blocks, uint32_t first_block, uint32_t n_b
 		DeviceSink sink; sink.init(arena);
 		unsigned long long draws = 0;
 		const BlockDesc b = blocks[first_block + i];
-		simulate_block(g, c, s, sink, b, &draws);
+		simulate_block<kMeth>(g, c, s, sink, b, &draws);
 		draws = __shfl_sync(0xffffffffu, draws, 0);
 		if(g.lane() == 0){
 			BlockOut o; o.head[0] = sink.head0; o.head[1] = sink.head1; o.bytes[0] = sink.bytes0; o.bytes[1] = sink.bytes1;
@@ -529,6 +531,7 @@ struct rsq_engine {
 	DevBuf<BlockDesc> d_blocks;
 	DevBuf<SysChain> d_sys_chains; DevBuf<SysChunk> d_sys_chunks; DevBuf<uint32_t> d_sys_dirty, d_gc_tiles;
 	DevBuf<BiasParamDev> d_bias_params; DevBuf<double> d_bias_sums, d_bias_max;
+	DevBuf<uint32_t> d_meth_off, d_meth_start, d_meth_end; DevBuf<double> d_meth_rate; DevBuf<int32_t> d_block_meth;
 	PinnedBuf h_ref_stage;
 	std::vector<uint64_t> h_seq_off;
 	uint64_t total_size = 0;
@@ -655,6 +658,7 @@ static std::string describe_flag(uint32_t f){
 	if(f & kErrArenaFull){ s += "output arena exhausted; "; }
 	if(f & kErrOrgOverflow){ s += "read or adapter longer than the staged buffers; "; }
 	if(f & kErrRecordTooLong){ s += "FASTQ record longer than an output chunk; "; }
+	if(f & kErrReferenceOutOfRange){ s += "the reference implementation indexes its methylation regions out of range for this input (std::out_of_range in Simulator::CTConversion); "; }
 	return s;
 }
 
@@ -798,6 +802,28 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	c.thr = e.d_thr.p; c.thr_int = e.d_thr_int.p; c.binom_p0 = e.d_binom_p0.p; c.coverage_group = e.d_cov_group.p; c.bias_normalization = e.norm.bias_normalization;
 	if(rep){ rep->ms_bias = tm.stop(); rep->bias_normalization = e.norm.bias_normalization; } else { tm.stop(); }
 
+	// --- methylation regions (Reference::ReadMethylation) ---
+	c.meth_loaded = g.methylation_loaded ? 1u : 0u;
+	std::vector<int32_t> block_meth;
+	if(g.methylation_loaded){
+		std::vector<uint32_t> moff{0}, mstart, mend; std::vector<double> mrate;
+		for(size_t i = 0; i < g.seqs.size(); ++i){
+			for(size_t r = 0; r < g.unmethylated_regions[i].size(); ++r){
+				mstart.push_back(g.unmethylated_regions[i][r].first); mend.push_back(g.unmethylated_regions[i][r].second); mrate.push_back(g.unmethylation[i].at(r));
+			}
+			moff.push_back(mstart.size());
+		}
+		mstart.push_back(0); mend.push_back(0); mrate.push_back(0.0);
+		e.d_meth_off.upload(moff, s); e.d_meth_start.upload(mstart, s); e.d_meth_end.upload(mend, s); e.d_meth_rate.upload(mrate, s);
+		c.meth_off = e.d_meth_off.p; c.meth_start = e.d_meth_start.p; c.meth_end = e.d_meth_end.p; c.meth_rate = e.d_meth_rate.p;
+		for(size_t i = 0; i < g.seqs.size(); ++i){
+			const uint32_t L = g.seqs[i].size();
+			if(L < c.insert_to){ continue; }
+			for(uint32_t b = 0; b < (L + 999) / 1000; ++b){ block_meth.push_back(g.first_methylation_id(i, b * 1000)); }
+		}
+		e.d_block_meth.upload(block_meth, s);
+	}
+
 	// --- master stream: adapter systematic errors, then per unit reverse strand / seeds / forward strand ---
 	tm.start();
 	e.d_master_state.alloc(kMtN + 1);
@@ -862,7 +888,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		uint32_t passes = 0;
 		run_sys_chains(e, chains, lens, 8192, 1024, passes);
 		passes_total = std::max(passes_total, passes);
-		k_build_blocks<<<(nb + 127) / 128, 128, 0, s>>>(e.d_blocks.p, first, nb, i, next_block_id, e.d_master.p + nb + 2ull * L); ++e.launches;
+		k_build_blocks<<<(nb + 127) / 128, 128, 0, s>>>(e.d_blocks.p, first, nb, i, next_block_id, e.d_master.p + nb + 2ull * L, g.methylation_loaded ? e.d_block_meth.p : nullptr); ++e.launches;
 		RSQ_CUDA(cudaStreamSynchronize(s));   // d_master is reused by the next unit
 		next_block_id += nb; first += nb;
 	}
@@ -926,10 +952,12 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	const uint32_t slots = e.shard_n + (e.shard_has_adapter_only ? 1 : 0);
 	const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, c.max_read_len);
 	const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta;
-	RSQ_CUDA(cudaFuncSetAttribute(k_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
+	const bool meth = c.meth_loaded != 0;
+	auto kernel = meth ? k_simulate<true> : k_simulate<false>;
+	RSQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
 	RSQ_CUDA(cudaFuncSetAttribute(k_adapter_only, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scratch)));
 	int dev_sms = 0; RSQ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e.device));
-	int ctas_per_sm = 0; RSQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_simulate, kWarpsPerCta * 32, shmem));
+	int ctas_per_sm = 0; RSQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kWarpsPerCta * 32, shmem));
 	if(ctas_per_sm < 1){ throw std::runtime_error("k_simulate does not fit on an SM"); }
 	// expected output: this shard's share of the pairs, generously padded
 	const double share = e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0;
@@ -945,7 +973,7 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 		tm.start();
 		if(e.shard_n){
 			const uint32_t ctas = std::min<uint32_t>((e.shard_n + kWarpsPerCta - 1) / kWarpsPerCta, dev_sms * ctas_per_sm);
-			k_simulate<<<ctas, kWarpsPerCta * 32, shmem, s>>>(c, e.d_blocks.p, e.shard_first, e.shard_n, a, e.d_block_out.p, e.d_next_block.p, e.max_n0, scratch);
+			kernel<<<ctas, kWarpsPerCta * 32, shmem, s>>>(c, e.d_blocks.p, e.shard_first, e.shard_n, a, e.d_block_out.p, e.d_next_block.p, e.max_n0, scratch);
 			++e.launches;
 		}
 		if(e.shard_has_adapter_only){
@@ -1197,6 +1225,13 @@ rsq_reference *rsq_reference_from_memory(uint32_t n_seqs, const char *const *ids
 	if(!n_seqs){ throw std::runtime_error("reference does not contain any sequences"); }
 	return r.release();
 	RSQ_CATCH(nullptr)
+}
+
+int rsq_reference_load_methylation(rsq_reference *ref, const char *bed_path){
+	RSQ_TRY
+	ref->g.read_methylation(bed_path);
+	return 0;
+	RSQ_CATCH(1)
 }
 
 uint64_t rsq_reference_total_size(const rsq_reference *ref){ return ref->g.total_size(); }

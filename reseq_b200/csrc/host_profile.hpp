@@ -313,6 +313,83 @@ struct Genome {
 	std::vector<std::string> ids;               // full header lines
 	std::vector<std::vector<uint8_t>> seqs;     // Dna5 codes: A0 C1 G2 T3 N4
 
+	// Reference::unmethylated_regions_ / unmethylation_ (allele 0), filled by read_methylation()
+	bool methylation_loaded = false;
+	std::vector<std::vector<std::pair<uint32_t, uint32_t>>> unmethylated_regions;
+	std::vector<std::vector<double>> unmethylation;
+
+	// Reference::PrepareMethylationFile + ReadMethylation (Reference.cpp:1132-1322) for a single-allele run:
+	// extended bedGraph lines "<sequence> <start> <end> <methylation>", grouped by sequence in reference order.
+	void read_methylation(const std::string &path){
+		std::ifstream f(path);
+		if(!f){ throw std::runtime_error("Unable to open methylation file " + path); }
+		std::string line;
+		if(!std::getline(f, line)){ throw std::runtime_error("Methylation file is empty: " + path); }
+		while((line.empty() || !line.compare(0, 5, "track")) && std::getline(f, line));
+		if(f.fail()){ throw std::runtime_error("Methylation file only contains track lines: " + path); }
+		std::string cur_seq = line.substr(0, line.find_first_of(" \t"));
+		unmethylated_regions.assign(seqs.size(), {});
+		unmethylation.assign(seqs.size(), {});
+		bool eof = false;
+		for(size_t sid = 0; sid < seqs.size(); ++sid){
+			if(eof || first_part(sid) != cur_seq){ continue; }
+			auto &regions = unmethylated_regions[sid];
+			while(!f.fail()){
+				size_t first_space = line.find_first_not_of(" \t", cur_seq.size() + 1);
+				size_t second_space = line.find_first_of(" \t", first_space);
+				long long v;
+				try{ v = std::stoll(line.substr(first_space, second_space)); }
+				catch(const std::exception &e){ throw std::runtime_error("Could not convert second field to int for line:\n" + line); }
+				if(regions.empty()){ if(v < 0){ throw std::runtime_error("Second field is negative in line:\n" + line); } }
+				else if(v < regions.back().second){ throw std::runtime_error("Region is overlapping with previous region in line:\n" + line); }
+				if(v >= static_cast<long long>(seqs[sid].size())){ throw std::runtime_error("Second field is larger than sequence length:\n" + line); }
+				const uint32_t region_start = v;
+				first_space = line.find_first_not_of(" \t", second_space);
+				second_space = line.find_first_of(" \t", first_space);
+				try{ v = std::stoll(line.substr(first_space, second_space)); }
+				catch(const std::exception &e){ throw std::runtime_error("Could not convert third field to int for line:\n" + line); }
+				if(v <= region_start){ throw std::runtime_error("Third field is smaller than second field in line:\n" + line); }
+				if(v > static_cast<long long>(seqs[sid].size())){ throw std::runtime_error("Third field is larger than sequence length:\n" + line); }
+				regions.emplace_back(region_start, static_cast<uint32_t>(v));
+				uint32_t allele = 0;
+				first_space = line.find_first_not_of(" \t", second_space);
+				while(first_space < line.size()){
+					if(allele >= 1){ throw std::runtime_error("More alleles specified than in variant file [1] in line:\n" + line); }
+					second_space = line.find_first_of(" \t", first_space);
+					double d;
+					try{ d = std::stod(line.substr(first_space, second_space)); }
+					catch(const std::exception &e){ throw std::runtime_error("Could not convert field 4 to double for line:\n" + line); }
+					if(0.0 > d || d > 1.0){ throw std::runtime_error("Field 4 is not between 0 and 1:\n" + line); }
+					unmethylation[sid].push_back(1.0 - d);
+					++allele;
+					first_space = line.find_first_not_of(" \t", second_space);
+				}
+				if(1 != allele){ throw std::runtime_error("0 alleles specified (must be either 1 or same as in variant file[1]) in line:\n" + line); }
+				while(std::getline(f, line) && line.empty());
+				if(!f.fail()){
+					const size_t sp = line.find_first_of(" \t");
+					if(line.compare(0, sp, cur_seq)){ cur_seq = line.substr(0, sp); break; }
+				}
+			}
+			if(f.fail()){
+				if(!f.eof()){ throw std::runtime_error("Could not read methylation file for reference sequence: " + first_part(sid)); }
+				eof = true;
+			}
+		}
+		methylation_loaded = true;
+	}
+
+	// SimBlock::first_methylation_id_ of the forward block starting at `start_pos` (Simulator.cpp:965-977, 1214-1220)
+	int32_t first_methylation_id(size_t sid, uint32_t start_pos) const {
+		if(!methylation_loaded || 0 == start_pos){ return 0; }
+		const auto &regions = unmethylated_regions[sid];
+		int32_t first_meth = 0;   // reverse partner of the previous block: last region starting before start_pos
+		while(static_cast<size_t>(first_meth) < regions.size() && regions[first_meth].first < start_pos){ ++first_meth; }
+		int32_t id = first_meth - 1;
+		if(0 > id || regions.at(id).second <= start_pos){ ++id; }
+		return id;
+	}
+
 	static uint8_t code(char ch){
 		switch(ch){
 		case 'A': case 'a': return 0;

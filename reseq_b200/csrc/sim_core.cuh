@@ -20,7 +20,7 @@ struct BlockDesc {
 	uint32_t ref_id;
 	uint32_t start_pos;
 	uint32_t block_id;   // id printed in the read names (forward SimBlock::id_)
-	uint32_t pad;
+	int32_t first_meth;  // SimBlock::first_methylation_id_
 	uint64_t seed;
 };
 
@@ -84,9 +84,15 @@ struct SimCtx {
 	uint32_t max_read_len;             // capacity of the per-read scratch
 	uint32_t max_org_len;
 	uint32_t *error_flag;              // set non-zero on unsupported situations (cigar overflow, runaway count)
+	// --- methylation (Reference::unmethylated_regions_ / unmethylation_, allele 0) ---
+	uint32_t meth_loaded;              // Reference::MethylationLoaded()
+	const uint32_t *meth_off;          // [n_seqs+1] first region of each sequence
+	const uint32_t *meth_start;        // region.first
+	const uint32_t *meth_end;          // region.second
+	const double *meth_rate;           // 1 - methylation = C->T conversion probability
 };
 
-enum : uint32_t { kErrCigarOverflow = 1, kErrCountRunaway = 2, kErrArenaFull = 4, kErrOrgOverflow = 8, kErrRecordTooLong = 16 };
+enum : uint32_t { kErrCigarOverflow = 1, kErrCountRunaway = 2, kErrArenaFull = 4, kErrOrgOverflow = 8, kErrRecordTooLong = 16, kErrReferenceOutOfRange = 32 };
 
 constexpr int kCigarCap = 192;
 constexpr int kIdCap = 384;
@@ -95,7 +101,7 @@ constexpr int kIdCap = 384;
 constexpr uint32_t kMaxN0 = 128;       // largest candidate count of any table (error-rate tables: <= 101)
 constexpr uint32_t kMaxOrgLen = 384;   // read length + longest deletion, adapters, seqToIllumina fragments
 constexpr uint32_t kMaxReadLen = 320;
-constexpr uint32_t kScratchBytes = kMtN * 8 + kMaxN0 * 8 + 3 * kMaxOrgLen + 2 * kMaxReadLen + kCigarCap + kIdCap;
+constexpr uint32_t kScratchBytes = kMtN * 8 + kMaxN0 * 8 + 5 * kMaxOrgLen + 2 * kMaxReadLen + kCigarCap + kIdCap;
 
 struct Scratch {          // group-shared memory
 	unsigned char *base;
@@ -109,6 +115,7 @@ struct Scratch {          // group-shared memory
 	uint8_t *qual;        // kMaxReadLen     qualities (already + phred offset)
 	char *cigar;          // kCigarCap
 	char *id;             // kIdCap
+	uint8_t *frag[2];     // 2 x kMaxOrgLen  bisulfite-converted forward / reverse fragment ends (methylation runs only)
 };
 
 RSQ_HD size_t scratch_bytes(uint32_t, uint32_t, uint32_t){ return kScratchBytes; }
@@ -124,6 +131,8 @@ RSQ_HD Scratch carve_scratch(unsigned char *base, uint32_t, uint32_t, uint32_t){
 	s.qual = s.seq + kMaxReadLen;
 	s.cigar = reinterpret_cast<char *>(s.qual + kMaxReadLen);
 	s.id = s.cigar + kCigarCap;
+	s.frag[0] = reinterpret_cast<uint8_t *>(s.id + kIdCap);
+	s.frag[1] = s.frag[0] + kMaxOrgLen;
 	return s;
 }
 
@@ -480,7 +489,7 @@ RSQ_HD int format_read_id(const G &g, const SimCtx &c, const Scratch &s, uint32_
 // forward strand, reverse read = reverse complement of its suffix with the reverse-strand errors.
 template<class G>
 RSQ_HD uint32_t stage_fragment_read(const G &g, const SimCtx &c, const Scratch &s, uint32_t ref_id, uint32_t seg, bool reversed,
-                                    uint32_t start_pos, uint32_t end_pos, uint32_t fragment_length){
+                                    uint32_t start_pos, uint32_t end_pos, uint32_t fragment_length, const uint8_t *converted = nullptr){
 	uint32_t org_len = c.read_len_to[seg] + c.max_len_deletion;
 	if(fragment_length < org_len){ org_len = fragment_length; }
 	if(org_len > c.max_org_len){ org_len = c.max_org_len; if(g.lane() == 0){ *c.error_flag |= kErrOrgOverflow; } }
@@ -491,7 +500,7 @@ RSQ_HD uint32_t stage_fragment_read(const G &g, const SimCtx &c, const Scratch &
 		const uint8_t *ref = c.ref + off + start_pos;
 		const uint8_t *sys = c.sys_fwd + 2 * (off + start_pos);
 		for(uint32_t i = g.lane(); i < org_len; i += G::kSize){
-			s.org[i] = ref[i];
+			s.org[i] = converted ? converted[i] : ref[i];
 			s.sdom[i] = sys[2 * i];
 			s.srate[i] = sys[2 * i + 1];
 		}
@@ -500,7 +509,7 @@ RSQ_HD uint32_t stage_fragment_read(const G &g, const SimCtx &c, const Scratch &
 		const uint8_t *ref = c.ref + off;
 		const uint8_t *sys = c.sys_rev + 2 * (off + (L - end_pos));
 		for(uint32_t i = g.lane(); i < org_len; i += G::kSize){
-			s.org[i] = static_cast<uint8_t>(3 - ref[end_pos - 1 - i]);
+			s.org[i] = converted ? converted[i] : static_cast<uint8_t>(3 - ref[end_pos - 1 - i]);
 			s.sdom[i] = sys[2 * i];
 			s.srate[i] = sys[2 * i + 1];
 		}
@@ -514,7 +523,7 @@ RSQ_HD uint32_t stage_fragment_read(const G &g, const SimCtx &c, const Scratch &
 template<class G, class Sink>
 RSQ_HD void create_reads(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, Sink &sink, uint32_t counts, bool strand,
                          uint32_t ref_id, uint32_t fragment_length, uint64_t &read_number, uint32_t block_id,
-                         uint32_t start_position_forward, uint32_t end_position_forward){
+                         uint32_t start_position_forward, uint32_t end_position_forward, bool converted = false){
 	uint32_t print_start = 0, print_end = 0;
 	if(fragment_length){
 		if(strand){ print_start = end_position_forward; print_end = start_position_forward + 1; }
@@ -529,7 +538,7 @@ RSQ_HD void create_reads(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, 
 			if(fragment_length){
 				// block.at(strand) is the forward start block, block.at(!strand) the reverse partner of the end block
 				const bool reversed = (seg != static_cast<uint32_t>(strand));
-				org_len = stage_fragment_read(g, c, s, ref_id, seg, reversed, start_position_forward, end_position_forward, fragment_length);
+				org_len = stage_fragment_read(g, c, s, ref_id, seg, reversed, start_position_forward, end_position_forward, fragment_length, converted ? s.frag[reversed ? 1 : 0] : nullptr);
 			}
 			ReadState par;
 			fill_read(g, c, s, mt, par, seg, tile, fragment_length, org_len);
@@ -540,8 +549,80 @@ RSQ_HD void create_reads(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, 
 	}
 }
 
+// Simulator::CTConversion without variants (Simulator.cpp:1925-2003): bisulfite C->T on one fragment end, one draw per
+// C inside an unmethylated region.  `read` holds `read_len` bases; regions/rates are those of the sequence.
+template<class G>
+RSQ_HD void ct_conversion(const G &g, const SimCtx &c, Mt &mt, uint8_t *read, uint32_t read_len, uint32_t seq_id, uint32_t start_pos,
+                          int32_t cur_methylation_start, bool reversed){
+	const uint32_t r0 = c.meth_off[seq_id];
+	const uint32_t n_regions = c.meth_off[seq_id + 1] - r0;
+	const uint32_t *first = c.meth_start + r0, *second = c.meth_end + r0;
+	const double *rate = c.meth_rate + r0;
+	int32_t cur_meth = cur_methylation_start;
+	uint32_t read_pos = 0;   // uintReadLen
+	uint32_t ref_pos = start_pos;
+	auto in_range = [&](int32_t i) -> bool {   // regions.at(i) of the reference throws otherwise
+		if(static_cast<uint32_t>(i) < n_regions){ return true; }
+		if(g.lane() == 0){ *c.error_flag |= kErrReferenceOutOfRange; }
+		return false;
+	};
+	auto convert = [&](){
+		if(1 == read[read_pos]){
+			const double u = mt_uniform(g, mt);
+			if(u < rate[cur_meth]){
+				g.sync();
+				if(g.lane() == 0){ read[read_pos] = 3; }
+				g.sync();
+			}
+		}
+	};
+	if(reversed){
+		while(static_cast<uint32_t>(cur_meth) < n_regions && cur_meth >= 0 && first[cur_meth] <= ref_pos){ ++cur_meth; }
+		--cur_meth;
+		if(cur_meth){
+			if(!in_range(cur_meth)){ return; }
+			if(second[cur_meth] <= ref_pos){
+				read_pos = (read_pos + ref_pos - (second[cur_meth] - 1)) & 0xffffu;
+				ref_pos = second[cur_meth] - 1;
+			}
+		}
+		while(cur_meth && read_pos < read_len){
+			if(!in_range(cur_meth)){ return; }
+			while(ref_pos >= first[cur_meth] && read_pos < read_len){
+				convert();
+				--ref_pos;
+				read_pos = (read_pos + 1) & 0xffffu;
+			}
+			if(--cur_meth){
+				if(!in_range(cur_meth)){ return; }
+				if(second[cur_meth] <= ref_pos){
+					read_pos = (read_pos + ref_pos - (second[cur_meth] - 1)) & 0xffffu;
+					ref_pos = second[cur_meth] - 1;
+				}
+			}
+		}
+	}
+	else{
+		if(cur_meth >= 0 && static_cast<uint32_t>(cur_meth) < n_regions && first[cur_meth] > ref_pos){
+			read_pos = (read_pos + first[cur_meth] - ref_pos) & 0xffffu;
+			ref_pos = first[cur_meth];
+		}
+		while(cur_meth >= 0 && static_cast<uint32_t>(cur_meth) < n_regions && read_pos < read_len){
+			while(ref_pos < second[cur_meth] && read_pos < read_len){
+				convert();
+				++ref_pos;
+				read_pos = (read_pos + 1) & 0xffffu;
+			}
+			if(static_cast<uint32_t>(++cur_meth) < n_regions){
+				read_pos = (read_pos + first[cur_meth] - ref_pos) & 0xffffu;
+				ref_pos = first[cur_meth];
+			}
+		}
+	}
+}
+
 // Simulator::SimulateFromGivenBlock without variants / methylation
-template<class G, class Sink>
+template<bool kMeth, class G, class Sink>
 RSQ_HD void simulate_block(const G &g, const SimCtx &c, const Scratch &s, Sink &sink, const BlockDesc &b,
                            unsigned long long *scan_draws){
 	Mt mt; mt.s = s.mt; mt.idx = kMtN;
@@ -557,7 +638,12 @@ RSQ_HD void simulate_block(const G &g, const SimCtx &c, const Scratch &s, Sink &
 	unsigned long long draws = 0;
 	uint32_t end = b.start_pos + 1000u;
 	if(end > L){ end = L; }
+	int32_t cur_methylation_start = b.first_meth;
 	for(uint32_t pos = b.start_pos; pos < end; ++pos){
+		if(kMeth){
+			const uint32_t r0 = c.meth_off[b.ref_id], nr = c.meth_off[b.ref_id + 1] - r0;
+			if(cur_methylation_start >= 0 && static_cast<uint32_t>(cur_methylation_start) < nr && c.meth_end[r0 + cur_methylation_start] <= pos){ ++cur_methylation_start; }
+		}
 		uint32_t len = c.insert_from;
 		while(len < c.insert_to){
 			if(mt.idx >= kMtN){ mt_regen(g, mt); }
@@ -612,7 +698,23 @@ RSQ_HD void simulate_block(const G &g, const SimCtx &c, const Scratch &s, Sink &
 					const uint32_t counts = fragment_counts(c, b.ref_id, fragment_length, gc_perc, c.sur_start[off + pos], c.sur_end[off + cur_end - 1], adjusted_random, runaway);
 					if(runaway && g.lane() == 0){ *c.error_flag |= kErrCountRunaway; }
 					if(counts){
-						create_reads(g, c, s, mt, sink, counts, strand, b.ref_id, fragment_length, read_number, b.block_id, pos, cur_end);
+						if(kMeth){
+							// GetOrgSeq + CTConversion: forward end of the `strand` read first, then the reverse end
+							for(uint32_t rev = 0; rev < 2; ++rev){
+								const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
+								uint32_t n = c.read_len_to[seg] + c.max_len_deletion;
+								if(fragment_length < n){ n = fragment_length; }
+								if(n > c.max_org_len){ n = c.max_org_len; }
+								g.sync();
+								for(uint32_t i = g.lane(); i < n; i += G::kSize){
+									s.frag[rev][i] = rev ? static_cast<uint8_t>(3 - c.ref[off + cur_end - 1 - i]) : c.ref[off + pos + i];
+								}
+								g.sync();
+								ct_conversion(g, c, mt, s.frag[rev], n, b.ref_id, rev ? cur_end : pos, cur_methylation_start, rev != 0);
+							}
+							g.sync();
+						}
+						create_reads(g, c, s, mt, sink, counts, strand, b.ref_id, fragment_length, read_number, b.block_id, pos, cur_end, kMeth);
 					}
 				}
 			}

@@ -31,10 +31,11 @@ def workdir(tmp_path_factory):
 @pytest.fixture(scope="session")
 def golden(workdir):
     """Decompressed committed fixtures (tests/golden/make_golden.py made them with the reference's own code)."""
-    out = {"dir": GOLDEN, "small_ref": os.path.join(GOLDEN, "simref_small.fa")}
+    out = {"dir": GOLDEN, "small_ref": os.path.join(GOLDEN, "simref_small.fa"), "meth_bed": os.path.join(GOLDEN, "simref_small_meth.bed")}
     for key, name in (("flat", "profile150.flat.xz"), ("reseq", "profile150.reseq.xz"), ("ipf", "profile150.reseq.ipf.xz"),
                       ("r1", "sim_small_seed42_R1.fq.xz"), ("r2", "sim_small_seed42_R2.fq.xz"),
-                      ("em_in", "em_frags.fa.xz"), ("em_out", "em_seed7.fq.xz")):
+                      ("em_in", "em_frags.fa.xz"), ("em_out", "em_seed7.fq.xz"),
+                      ("meth_r1", "sim_small_meth_seed42_R1.fq.xz"), ("meth_r2", "sim_small_meth_seed42_R2.fq.xz")):
         out[key] = _unxz(name, workdir)
     return out
 

@@ -11,6 +11,7 @@ Run in the build container (needs /root/reference for the TruSeq adapter files a
                                         Estimate + PrepareResult for that profile (dump_tables profile)
   simref_small.fa                       small multi-contig reference with N runs and one too-short contig
   sim_small_seed42_R{1,2}.fq.xz         `reseq illuminaPE -j 1 --seed 42 -c 20` on simref_small.fa
+  simref_small_meth.bed, sim_small_meth_seed42_R{1,2}.fq.xz   same run with `--methylation` (bisulfite C->T conversions)
   em_frags.fa.xz / em_seed7.fq.xz       seqToIllumina input and its output.  9000 records = ONE 10000-record batch on purpose:
                                         the reference never increments written_blocks_ (Simulator.cpp:184-213), so its second
                                         batch waits forever in WriteSingleReads -- larger inputs cannot be pinned against it
@@ -44,6 +45,21 @@ def xz(src, dst):
         shutil.copyfileobj(f, o)
 
 
+def write_bed(path):
+    """Unmethylated-region file for simref_small.fa: touching, separated and far-apart regions; chr2 does not start at 0."""
+    import random
+    rnd = random.Random(3)
+    lines = ["track type=bedGraph name=x"]
+    for name, length in (("chr1", 30000), ("chr2", 22000), ("chr4", 15000)):
+        pos = 0 if name != "chr2" else 137
+        while pos < length - 600:
+            end = min(length, pos + rnd.randint(1, 900))
+            lines.append(f"{name}\t{pos}\t{end}\t{rnd.random():.3f}")
+            pos = end + rnd.choice([0, 0, 1, 50, 700, 2500])
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
 def main():
     tmp = tempfile.mkdtemp(prefix="rsq_golden_")
     py = sys.executable
@@ -72,6 +88,15 @@ def main():
     run([ORACLE, "illuminaPE", "-j", "1", "-s", prof, "-R", small, "--ipfIterations", "0", "--seed", "42", "-c", "20", "-1", r1, "-2", r2])
     xz(r1, os.path.join(HERE, "sim_small_seed42_R1.fq.xz"))
     xz(r2, os.path.join(HERE, "sim_small_seed42_R2.fq.xz"))
+
+    # methylation (bisulfite) run on the same reference
+    bed = os.path.join(HERE, "simref_small_meth.bed")
+    write_bed(bed)
+    m1, m2 = os.path.join(tmp, "m1.fq"), os.path.join(tmp, "m2.fq")
+    run([ORACLE, "illuminaPE", "-j", "1", "-s", prof, "-R", small, "--ipfIterations", "0", "--seed", "42", "-c", "20", "--methylation", bed,
+         "-1", m1, "-2", m2])
+    xz(m1, os.path.join(HERE, "sim_small_meth_seed42_R1.fq.xz"))
+    xz(m2, os.path.join(HERE, "sim_small_meth_seed42_R2.fq.xz"))
 
     frags = os.path.join(tmp, "em_frags.fa")
     run([py, SYN, "fragments", ref, "-", frags, "--n", "9000", "--len", "120", "--seed", "3"])

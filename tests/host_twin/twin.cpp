@@ -3,7 +3,7 @@
 // a GPU.  The shipped library never contains or calls this; the GPU tests check the very same templates
 // instantiated for 32-lane warps.
 //
-//   twin <stage.flat from oracle/_ref/dump_tables sim> <seed> <out_prefix> [max_blocks]
+//   twin <stage.flat from oracle/_ref/dump_tables sim> <seed> <out_prefix> [max_blocks] [methylation.bed]
 // Recomputes: ReplaceN'd reference (taken from the dump), surroundings bias + normalisation + thresholds,
 // master stream -> adapter / reverse / forward systematic errors + block seeds, then simulates every block
 // and writes <out_prefix>_1.fq / _2.fq.  Prints mismatches against the dump's stage values.
@@ -61,6 +61,7 @@ int main(int argc, char **argv){
 	const uint64_t seed = strtoull(argv[2], nullptr, 10);
 	const std::string prefix = argv[3];
 	const size_t max_blocks = argc > 4 ? strtoull(argv[4], nullptr, 10) : static_cast<size_t>(-1);
+	const char *bed = argc > 5 ? argv[5] : nullptr;
 	Profile p; p.from_flat(f);
 	int bad = 0;
 
@@ -72,7 +73,9 @@ int main(int argc, char **argv){
 		const auto &idr = f.get("sim.ref_id." + std::to_string(s));
 		g.ids.emplace_back(reinterpret_cast<const char *>(idr.bytes.data()), idr.count);
 	}
+	if(bed){ g.read_methylation(bed); }
 	DeviceLikeStorage st;
+	std::vector<uint32_t> moff{0}, mstart, mend; std::vector<double> mrate;
 	std::vector<std::vector<double>> cp_keep; cp_keep.reserve(4096);
 	SimCtx c{};
 	// tables
@@ -157,6 +160,15 @@ int main(int argc, char **argv){
 	c.max_read_len = kMaxReadLen; c.max_org_len = kMaxOrgLen;
 	c.error_flag = &st.error_flag;
 
+	if(bed){
+		for(size_t i = 0; i < g.seqs.size(); ++i){
+			for(size_t r = 0; r < g.unmethylated_regions[i].size(); ++r){ mstart.push_back(g.unmethylated_regions[i][r].first); mend.push_back(g.unmethylated_regions[i][r].second); mrate.push_back(g.unmethylation[i].at(r)); }
+			moff.push_back(mstart.size());
+		}
+		mstart.push_back(0); mend.push_back(0); mrate.push_back(0.0);
+		c.meth_loaded = 1; c.meth_off = moff.data(); c.meth_start = mstart.data(); c.meth_end = mend.data(); c.meth_rate = mrate.data();
+	}
+
 	// ---- normalisation (CalculateBiasNormalization) ----
 	const uint64_t total_pairs = f.scalar_i("sim.total_pairs");
 	Spline spline;
@@ -230,7 +242,7 @@ int main(int argc, char **argv){
 		sys_error_chain(lane, c.tab, prob.data(), seq, L, false, 0, L, SysState{0, 0}, carried, sys_gc_range, p.reset_distance, raw.data() + nb + 2 * static_cast<size_t>(L), true, st.sys_fwd.data() + 2 * st.seq_off[s]);
 		carried = dominant_before(seq, L, false, L, carried);
 		for(uint32_t b = 0; b < nb; ++b){
-			BlockDesc d{}; d.ref_id = s; d.start_pos = b * 1000; d.block_id = next_block_id++; d.seed = raw[nb + 2 * static_cast<size_t>(L) + static_cast<size_t>(b) * 2001];
+			BlockDesc d{}; d.ref_id = s; d.start_pos = b * 1000; d.block_id = next_block_id++; d.first_meth = g.first_methylation_id(s, b * 1000); d.seed = raw[nb + 2 * static_cast<size_t>(L) + static_cast<size_t>(b) * 2001];
 			blocks.push_back(d);
 		}
 	}
@@ -272,7 +284,7 @@ int main(int argc, char **argv){
 	unsigned long long total_draws = 0;
 	for(size_t i = 0; i < nsim; ++i){
 		unsigned long long d = 0;
-		simulate_block(lane, c, s, sink, blocks[i], &d);
+		if(bed){ simulate_block<true>(lane, c, s, sink, blocks[i], &d); } else{ simulate_block<false>(lane, c, s, sink, blocks[i], &d); }
 		total_draws += d;
 		fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
 		sink.out[0].clear(); sink.out[1].clear();

@@ -45,6 +45,33 @@ def test_small_golden_bit_exact(rb, engine, golden):
     assert rep.kernel_launches > 0
 
 
+def test_methylation_golden_bit_exact(rb, engine, golden):
+    """--methylation: bisulfite C->T conversions per unmethylated region (Simulator::CTConversion)."""
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    ref.load_methylation(golden["meth_bed"])
+    r1, r2, _ = _simulate(engine, ref, seed=42, coverage=20.0)
+    assert r1 == open(golden["meth_r1"], "rb").read()
+    assert r2 == open(golden["meth_r2"], "rb").read()
+
+
+def test_methylation_against_reference_binary(rb, engine, golden, oracle, workdir):
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    ref.load_methylation(golden["meth_bed"])
+    r1, r2, _ = _simulate(engine, ref, seed=77, coverage=9.0)
+    o1, o2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], 77, 9.0, os.path.join(workdir, "ora_meth"),
+                            extra=("--methylation", golden["meth_bed"]))
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+
+
+def test_malformed_methylation_file_is_an_error(rb, golden, workdir):
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    bad = os.path.join(workdir, "bad.bed")
+    open(bad, "w").write("chr1\t10\t5\t0.5\n")
+    with pytest.raises(rb.RsqError, match="Third field"):
+        ref.load_methylation(bad)
+
+
 def test_dropin_simulate_call_writes_files(rb, golden, workdir):
     prof = rb.Profile.load_flat(golden["flat"])
     ref = rb.Reference.load_fasta(golden["small_ref"])

@@ -63,3 +63,22 @@ def test_templates_match_reference_stages_and_fastq(oracle, golden, twin, workdi
     assert "stage_mismatches=0" in res.stdout and "error_flag=0" in res.stdout
     assert filecmp.cmp(prefix + "_1.fq", r1, shallow=False)
     assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
+
+
+def test_methylation_golden_is_what_the_reference_writes(oracle, golden, workdir):
+    r1, r2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], 42, 20, os.path.join(workdir, "pin_meth"),
+                            extra=("--methylation", golden["meth_bed"]))
+    assert filecmp.cmp(r1, golden["meth_r1"], shallow=False)
+    assert filecmp.cmp(r2, golden["meth_r2"], shallow=False)
+
+
+def test_templates_match_reference_with_methylation(oracle, golden, twin, workdir):
+    """CTConversion (bisulfite C->T per unmethylated region, Simulator.cpp:1925-2003) through the one-lane twin."""
+    stage = os.path.join(workdir, "stage_meth.flat")
+    subprocess.run([oracle["dump"], "sim", golden["reseq"], golden["small_ref"], "42", "20", stage], check=True, timeout=600,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    prefix = os.path.join(workdir, "twin_meth")
+    res = subprocess.run([twin, stage, "42", prefix, "66", golden["meth_bed"]], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout
+    assert filecmp.cmp(prefix + "_1.fq", golden["meth_r1"], shallow=False)
+    assert filecmp.cmp(prefix + "_2.fq", golden["meth_r2"], shallow=False)
