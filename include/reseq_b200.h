@@ -54,12 +54,17 @@ typedef struct rsq_sim_options {
 	uint64_t seed;                 /* uintSeed seed */
 	double coverage;               /* 0 = DataStats::CorrectedCoverage() */
 	uint64_t num_read_pairs;       /* 0 = derive from coverage */
-	int32_t ref_bias_model;        /* RefSeqBiasSimulation: 0 kKeep, 1 kNo (kDraw / kFile: not yet) */
+	int32_t ref_bias_model;        /* RefSeqBiasSimulation: 0 kKeep, 1 kNo, 2 kDraw, 3 kFile (ref_bias_file) */
 	const char *record_base_identifier; /* NULL/"" = "ReseqRead" */
 	/* sharding (one engine per GPU): simulate forward blocks [shard_index*n/shard_count, ...) of the run;
 	 * shard_count 0 or 1 = whole run.  Block seeds and systematic errors are identical in every shard. */
 	uint32_t shard_index;
 	uint32_t shard_count;
+	/* `sys_error_file` of Simulator::Simulate (--readSysError): FASTQ written by rsq_create_systematic_error_profile /
+	 * `--writeSysError` (per sequence a "reverse" and a "forward" record: seq = dominant error, qual = error rate + 33,
+	 * Simulator.cpp:326-335, 2562-2576).  NULL/"" = draw the systematic errors from the master stream. */
+	const char *sys_error_file;
+	const char *ref_bias_file;     /* `--refBiasFile`: one "<sequence id> <bias>" line per reference sequence (ref_bias_model 3) */
 } rsq_sim_options;
 
 typedef struct rsq_sim_report {
@@ -97,6 +102,10 @@ int rsq_engine_write(const rsq_engine *engine, const char *first_reads_path, con
  * write on device `device`; on failure the output files are removed like the reference does (Simulator.cpp:2888-2893). */
 int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq_sim_options *opt, int device,
                  const char *first_reads_path, const char *second_reads_path, rsq_sim_report *report);
+
+/* Drop-in for `bool Simulator::CreateSystematicErrorProfile(out, ref, stats, estimates, seed)` (Simulator.cpp:2597-2653,
+ * `--writeSysError`): per sequence the systematic errors of the whole reverse strand, then of the whole forward strand. */
+int rsq_create_systematic_error_profile(rsq_engine *engine, const rsq_reference *ref, uint64_t seed, const char *fastq_out_path);
 
 /* Drop-in for `bool Simulator::SimulateErrorModelOnly(out, in, stats, estimates, threads, seed)`
  * (Simulator.cpp:2900-3014): FASTA records "<id> <1|2>;<fraglen>;<dom-err>;<err-rate>" -> FASTQ. */

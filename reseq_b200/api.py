@@ -13,7 +13,8 @@ class RsqError(RuntimeError):
 
 class SimOptions(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("coverage", C.c_double), ("num_read_pairs", C.c_uint64), ("ref_bias_model", C.c_int32),
-                ("record_base_identifier", C.c_char_p), ("shard_index", C.c_uint32), ("shard_count", C.c_uint32)]
+                ("record_base_identifier", C.c_char_p), ("shard_index", C.c_uint32), ("shard_count", C.c_uint32),
+                ("sys_error_file", C.c_char_p), ("ref_bias_file", C.c_char_p)]
 
 
 class SimReport(C.Structure):
@@ -58,6 +59,7 @@ SIGNATURES = {
     "rsq_engine_output": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "rsq_engine_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "rsq_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SimOptions), C.c_int, C.c_char_p, C.c_char_p, C.POINTER(SimReport)]),
+    "rsq_create_systematic_error_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p]),
     "rsq_apply_error_model": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(SimReport)]),
     "rsq_engine_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
@@ -201,9 +203,11 @@ class Engine:
         self.close()
 
     def prepare(self, reference, seed, coverage=0.0, num_read_pairs=0, ref_bias_model=1, record_base_identifier=None,
-                shard_index=0, shard_count=1):
+                shard_index=0, shard_count=1, sys_error_file=None, ref_bias_file=None):
         opt = SimOptions(seed, coverage, num_read_pairs, ref_bias_model,
-                         record_base_identifier.encode() if record_base_identifier else None, shard_index, shard_count)
+                         record_base_identifier.encode() if record_base_identifier else None, shard_index, shard_count,
+                         os.fsencode(sys_error_file) if sys_error_file else None,
+                         os.fsencode(ref_bias_file) if ref_bias_file else None)
         if self._lib.rsq_engine_prepare(self._h, reference._h, C.byref(opt), C.byref(self.report)):
             raise _err(self._lib)
         return self.report
@@ -230,6 +234,11 @@ class Engine:
         if self._lib.rsq_engine_write(self._h, os.fsencode(first_reads_path), os.fsencode(second_reads_path)):
             raise _err(self._lib)
 
+    def create_systematic_error_profile(self, reference, seed, fastq_out):
+        """Simulator::CreateSystematicErrorProfile (--writeSysError)."""
+        if self._lib.rsq_create_systematic_error_profile(self._h, reference._h, seed, os.fsencode(fastq_out)):
+            raise _err(self._lib)
+
     def apply_error_model(self, fasta_in, fastq_out, seed):
         rep = SimReport()
         if self._lib.rsq_apply_error_model(self._h, os.fsencode(fasta_in), os.fsencode(fastq_out), seed, C.byref(rep)):
@@ -252,7 +261,7 @@ def simulate(profile, reference, first_reads_path, second_reads_path, seed, cove
     """Drop-in for Simulator::Simulate(R1, R2, ref, stats, estimates, threads, seed, num_read_pairs, coverage, ...)."""
     lib = load_library()
     opt = SimOptions(seed, coverage, num_read_pairs, ref_bias_model,
-                     record_base_identifier.encode() if record_base_identifier else None, 0, 1)
+                     record_base_identifier.encode() if record_base_identifier else None, 0, 1, None, None)
     rep = SimReport()
     if lib.rsq_simulate(profile._h, reference._h, C.byref(opt), device, os.fsencode(first_reads_path), os.fsencode(second_reads_path), C.byref(rep)):
         raise _err(lib)

@@ -1,6 +1,6 @@
 // reseq-b200: command line shell over libreseq_b200.so that keeps the reference's `reseq illuminaPE` /
 // `reseq seqToIllumina` simulation options (reference reseq/main.cpp:694-1137; README.md:133-231) for the hot path.
-// Profile creation (-b/--bamIn), IPF fitting, variants (-V) and methylation are outside this path: those options are
+// Profile creation (-b/--bamIn), IPF fitting and variants (-V) are outside this path: those options are
 // rejected with a message instead of being silently ignored.
 #include <chrono>
 #include <cstdio>
@@ -67,8 +67,8 @@ void usage(){
 }
 
 int reject_unsupported(const Args &a){
-	for(const char *k : {"bamIn", "vcfSim", "readSysError", "writeSysError", "refBiasFile", "vcfIn", "adapterFile", "adapterMatrix"}){
-		if(a.has(k)){ return err(std::string("option --") + k + " belongs to a part of ReSeq this engine does not replace (stats creation, variants, methylation, systematic-error files); run it with the reference implementation"); }
+	for(const char *k : {"bamIn", "vcfSim", "vcfIn", "adapterFile", "adapterMatrix"}){
+		if(a.has(k)){ return err(std::string("option --") + k + " belongs to a part of ReSeq this engine does not replace (stats creation, variants); run it with the reference implementation"); }
 	}
 	for(const char *k : {"statsOnly", "stopAfterEstimation"}){ if(a.flags.count(k)){ return err(std::string("option --") + k + " is a stats/IPF step; use the reference implementation"); } }
 	if(a.has("ipfIterations") && a.get("ipfIterations") != "0"){ return err("this engine does not fit probabilities: pass a converged X.reseq.ipf (and --ipfIterations 0)"); }
@@ -120,14 +120,33 @@ int run_illumina_pe(const Args &a){
 	opt.seed = pick_seed(a);
 	opt.coverage = atof(a.get("coverage", "0").c_str());
 	opt.num_read_pairs = strtoull(a.get("numReads", "0").c_str(), nullptr, 10);
-	const std::string bias = a.get("refBias", a.has("refSim") ? "no" : "keep");
-	if(bias == "keep"){ opt.ref_bias_model = 0; } else if(bias == "no"){ opt.ref_bias_model = 1; }
-	else{ rsq_profile_free(prof); rsq_reference_free(ref); return err("refBias '" + bias + "' is not supported by this engine (keep/no)"); }
+	const std::string bias_file = a.get("refBiasFile");
+	const std::string bias = a.get("refBias", a.has("refBiasFile") ? "file" : (a.has("refSim") ? "no" : "keep"));   // main.cpp:863-908
+	if(bias == "keep"){ opt.ref_bias_model = 0; } else if(bias == "no"){ opt.ref_bias_model = 1; } else if(bias == "draw"){ opt.ref_bias_model = 2; }
+	else if(bias == "file"){ opt.ref_bias_model = 3; }
+	else{ rsq_profile_free(prof); rsq_reference_free(ref); return err("Unknown option for refBias: " + bias); }
+	if(opt.ref_bias_model == 3 && bias_file.empty()){ rsq_profile_free(prof); rsq_reference_free(ref); return err("refBiasFile option mandatory if for refBias option file was chosen"); }
+	if(opt.ref_bias_model != 3 && !bias_file.empty()){ rsq_profile_free(prof); rsq_reference_free(ref); return err("refBiasFile option only allowed if for refBias option file was chosen"); }
+	opt.ref_bias_file = bias_file.empty() ? nullptr : bias_file.c_str();
 	const std::string base_id = a.get("recordBaseIdentifier", "ReseqRead");
 	opt.record_base_identifier = base_id.c_str();
 	int gpus = atoi(a.get("gpus", "1").c_str());
 	if(gpus < 1){ gpus = 1; }
 	if(gpus > rsq_device_count()){ rsq_profile_free(prof); rsq_reference_free(ref); return err("requested " + std::to_string(gpus) + " GPUs but only " + std::to_string(rsq_device_count()) + " CUDA devices are usable (there is no CPU path)"); }
+	if(a.has("readSysError") && a.has("writeSysError")){ rsq_profile_free(prof); rsq_reference_free(ref); return err("writeSysError and readSysError option are mutually exclusive. Specify the one or the other."); }
+	std::string sys_error_file = a.get("readSysError");
+	if(a.has("writeSysError")){
+		// main.cpp:379-391: create the profile with this seed, then simulate from the file
+		sys_error_file = a.get("writeSysError");
+		rsq_engine *w = rsq_engine_create(prof, 0);
+		if(!w || rsq_create_systematic_error_profile(w, ref, opt.seed, sys_error_file.c_str())){
+			if(w){ rsq_engine_destroy(w); }
+			rsq_profile_free(prof); rsq_reference_free(ref);
+			return err(rsq_last_error());
+		}
+		rsq_engine_destroy(w);
+	}
+	opt.sys_error_file = sys_error_file.empty() ? nullptr : sys_error_file.c_str();
 	info("Storing simulated data in " + out1 + " and " + out2);
 	for(const std::string &o : {out1, out2}){ FILE *f = fopen(o.c_str(), "wb"); if(!f){ return err("Could not open '" + o + "' for writing."); } fclose(f); }
 

@@ -272,11 +272,11 @@ __global__ void k_sys_check(SysChunk *chunks, uint32_t n_chunks, uint32_t *n_dir
 }
 
 __global__ void k_build_blocks(BlockDesc *blocks, uint32_t first, uint32_t nb, uint32_t ref_id, uint32_t first_block_id, const uint64_t *fwd_raw,
-                               const int32_t *first_meth /* per block of the run, or null */){
+                               const int32_t *first_meth /* per block of the run, or null */, uint32_t seed_stride /* 2001, or 1 with --readSysError */){
 	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
 	if(b >= nb){ return; }
 	BlockDesc d; d.ref_id = ref_id; d.start_pos = b * 1000u; d.block_id = first_block_id + b; d.first_meth = first_meth ? first_meth[first + b] : 0;
-	d.seed = fwd_raw[static_cast<size_t>(b) * 2001u];
+	d.seed = fwd_raw[static_cast<size_t>(b) * seed_stride];
 	blocks[first + b] = d;
 }
 
@@ -697,6 +697,32 @@ static void run_sys_chains(rsq_engine &e, const std::vector<SysChain> &chains, c
 	}
 }
 
+// FASTQ written by CreateSystematicErrorProfile: (id, dominant errors, compressed rates) per record
+struct SysErrorRecord { std::string id, dom, rate; };
+static std::vector<SysErrorRecord> read_sys_error_file(const std::string &path){
+	std::ifstream f(path);
+	if(!f){ throw std::runtime_error("Could not open '" + path + "' for reading."); }
+	std::vector<SysErrorRecord> recs;
+	std::string id, seq, plus, qual;
+	while(std::getline(f, id)){
+		if(id.empty()){ continue; }
+		if(id[0] != '@' || !std::getline(f, seq) || !std::getline(f, plus) || !std::getline(f, qual) || plus.empty() || plus[0] != '+'){
+			throw std::runtime_error("Could not read systematic error profile '" + path + "': malformed fastq record");
+		}
+		recs.push_back({id.substr(1), seq, qual});
+	}
+	return recs;
+}
+// Simulator::ReadSystematicErrors (Simulator.h:326-335)
+static void decode_sys_errors(const SysErrorRecord &r, uint8_t *out){
+	for(size_t pos = 0; pos < r.dom.size(); ++pos){
+		uint8_t rate = static_cast<uint8_t>(r.rate[pos] - 33);
+		if(86 < rate){ rate += rate - 86; }
+		out[2 * pos] = Genome::code(r.dom[pos]);
+		out[2 * pos + 1] = rate;
+	}
+}
+
 static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &opt, rsq_sim_report *rep){
 	cudaStream_t s = e.stream;
 	const Profile &p = e.prof;
@@ -709,11 +735,68 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	e.genome = ref_in;
 	e.genome.replace_n(opt.seed);
 	Genome &g = e.genome;
+	// FragmentDistributionStats::UpdateRefSeqBias (FragmentDistributionStats.cpp:3352-3502)
 	e.run_ref_seq_bias = p.ref_seq_bias;
-	if(opt.ref_bias_model == 1 || e.run_ref_seq_bias.size() != g.seqs.size()){
-		e.run_ref_seq_bias.assign(g.seqs.size(), 1.0);   // kNo, or kKeep falling through on mismatch
+	uint64_t master_draws_before = 0;     // master-stream outputs consumed on the host (kDraw only)
+	switch(opt.ref_bias_model){
+	case 0:   // kKeep, falling through to kNo when the biases do not match the reference
+		if(e.run_ref_seq_bias.size() == g.seqs.size()){ break; }
+		// fallthrough
+	case 1:   // kNo
+		e.run_ref_seq_bias.assign(g.seqs.size(), 1.0);
+		break;
+	case 2: { // kDraw: with replacement from the old biases, one draw per sequence (descending), from the MASTER stream
+		struct CountingMt {
+			std::mt19937_64 gen; uint64_t n = 0;
+			typedef uint64_t result_type;
+			static constexpr result_type min(){ return std::mt19937_64::min(); }
+			static constexpr result_type max(){ return std::mt19937_64::max(); }
+			result_type operator()(){ ++n; return gen(); }
+		} cm;
+		cm.gen.seed(opt.seed);
+		const std::vector<double> old_bias = e.run_ref_seq_bias;
+		e.run_ref_seq_bias.assign(g.seqs.size(), 0.0);
+		std::uniform_int_distribution<uint32_t> rdist(0, old_bias.size());
+		for(auto seq = e.run_ref_seq_bias.size(); seq--; ){
+			const uint32_t pick = rdist(cm);
+			if(pick >= old_bias.size()){ throw std::runtime_error("refBias draw: the reference draws index " + std::to_string(pick) + " of " + std::to_string(old_bias.size()) + " stored biases (std::out_of_range in UpdateRefSeqBias) for this seed"); }
+			e.run_ref_seq_bias[seq] = old_bias[pick];
+		}
+		master_draws_before = cm.n;
+		break;
 	}
-	else if(opt.ref_bias_model != 0){ throw std::runtime_error("refBias models draw/file are not supported by this revision"); }
+	case 3: { // kFile: "<identifier> <bias>" per line
+		e.run_ref_seq_bias.assign(g.seqs.size(), 0.0);
+		const std::string bias_file = opt.ref_bias_file ? opt.ref_bias_file : "";
+		std::ifstream fbias(bias_file);
+		if(!fbias.is_open()){ throw std::runtime_error("Unable to open reference bias file " + bias_file); }
+		std::map<std::string, uint32_t> ids;
+		for(size_t i = 0; i < g.seqs.size(); ++i){ ids.emplace(g.first_part(i), i); }
+		std::vector<bool> found(g.seqs.size(), false);
+		std::string line; uint32_t nline = 0; bool empty_line = false; uint32_t errors = 0;
+		while(std::getline(fbias, line)){
+			if(empty_line){ ++errors; continue; }
+			++nline;
+			if(line.empty()){ empty_line = true; continue; }
+			const auto sep = line.find_last_of(" \t");
+			if(sep == std::string::npos){ ++errors; continue; }
+			double bias = 0.0;
+			try{ bias = std::stod(line.substr(sep + 1)); }catch(...){ ++errors; bias = 0.0; }
+			if(0.0 > bias){ ++errors; }
+			auto id_len = line.find(' ');
+			if(id_len == std::string::npos){ id_len = sep; }
+			uint16_t id_start = 0;
+			if('>' == line.at(0)){ ++id_start; --id_len; }
+			auto it = ids.find(line.substr(id_start, id_len));
+			if(it != ids.end()){ e.run_ref_seq_bias.at(it->second) = bias; found.at(it->second) = true; }
+		}
+		for(size_t i = 0; i < g.seqs.size(); ++i){ if(!found[i]){ ++errors; } }
+		if(errors){ throw std::runtime_error("Error reading in reference sequence biases from " + bias_file + " (malformed line, negative bias or missing reference sequence)"); }
+		break;
+	}
+	default:
+		throw std::runtime_error("Unknown option chosen for reference sequence bias");
+	}
 	uint64_t reads = 0, sum_read_length = 0;
 	for(int seg = 2; seg--; ){
 		for(auto len = p.read_lengths[seg].from; len < p.read_lengths[seg].to(); ++len){ reads += p.read_lengths[seg][len]; sum_read_length += p.read_lengths[seg][len] * len; }
@@ -828,6 +911,10 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	tm.start();
 	e.d_master_state.alloc(kMtN + 1);
 	k_master_seed<<<1, 32, 0, s>>>(e.d_master_state.p, opt.seed); ++e.launches;
+	if(master_draws_before){   // outputs the host consumed for --refBias draw
+		e.d_master.alloc(master_draws_before);
+		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, master_draws_before); ++e.launches;
+	}
 	uint32_t carried = 0;
 	uint32_t passes_total = 0;
 	{
@@ -859,36 +946,59 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	}
 	e.d_sys_fwd.alloc(2 * total + 2); e.d_sys_rev.alloc(2 * total + 2);
 	c.sys_fwd = e.d_sys_fwd.p; c.sys_rev = e.d_sys_rev.p;
+	const bool from_file = opt.sys_error_file && opt.sys_error_file[0];
+	std::vector<SysErrorRecord> sys_records;
+	if(from_file){ sys_records = read_sys_error_file(opt.sys_error_file); }
+	size_t next_record = 0;
 	uint64_t max_unit_draws = 0; uint32_t nb_total = 0;
 	for(size_t i = 0; i < g.seqs.size(); ++i){
 		const uint32_t L = g.seqs[i].size();
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
 		nb_total += nb;
-		max_unit_draws = std::max<uint64_t>(max_unit_draws, 2ull * nb + 4ull * L);
+		max_unit_draws = std::max<uint64_t>(max_unit_draws, 2ull * nb + (from_file ? 0ull : 4ull * L));
 	}
 	if(!nb_total){ throw std::runtime_error("All reference sequences are too short for simulating."); }
 	e.d_master.alloc(max_unit_draws + 1);
 	e.d_blocks.alloc(nb_total);
 	uint32_t next_block_id = 1, first = 0;
+	std::vector<uint8_t> decoded;
 	for(size_t i = 0; i < g.seqs.size(); ++i){
 		const uint32_t L = g.seqs[i].size();
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
-		const uint64_t n_draws = 2ull * nb + 4ull * L;
+		const uint64_t n_draws = 2ull * nb + (from_file ? 0ull : 4ull * L);
 		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
-		const uint8_t *hseq = g.seqs[i].data();
-		std::vector<SysChain> chains(2); std::vector<std::pair<uint32_t, uint32_t>> lens{{L, 0}, {L, 0}};
-		chains[0].seq = e.d_ref.p + seq_off[i]; chains[0].L = L; chains[0].reverse = 1; chains[0].raw = e.d_master.p + nb; chains[0].seed_interleaved = 0;
-		chains[0].out = e.d_sys_rev.p + 2 * seq_off[i]; chains[0].carried_dom = carried;
-		carried = dominant_before(hseq, L, true, L, carried);
-		chains[1].seq = e.d_ref.p + seq_off[i]; chains[1].L = L; chains[1].reverse = 0; chains[1].raw = e.d_master.p + nb + 2ull * L; chains[1].seed_interleaved = 1;
-		chains[1].out = e.d_sys_fwd.p + 2 * seq_off[i]; chains[1].carried_dom = carried;
-		carried = dominant_before(hseq, L, false, L, carried);
-		uint32_t passes = 0;
-		run_sys_chains(e, chains, lens, 8192, 1024, passes);
-		passes_total = std::max(passes_total, passes);
-		k_build_blocks<<<(nb + 127) / 128, 128, 0, s>>>(e.d_blocks.p, first, nb, i, next_block_id, e.d_master.p + nb + 2ull * L, g.methylation_loaded ? e.d_block_meth.p : nullptr); ++e.launches;
+		if(from_file){
+			// CreateUnit: LoadSysErrorRecord (reverse strand) ... LoadSysErrorRecord (forward strand), strictly in file order
+			for(int strand = 0; strand < 2; ++strand){
+				if(next_record >= sys_records.size()){ throw std::runtime_error("Could not read systematic error profile for reference sequence '" + g.ids[i] + "': end of file"); }
+				const SysErrorRecord &r = sys_records[next_record++];
+				if(r.dom.size() != L || r.rate.size() != L){
+					throw std::runtime_error("Systematic error profile '" + r.id + "' (length " + std::to_string(r.dom.size()) + ") does not match reference sequence '" + g.ids[i] +
+					                         "' (length " + std::to_string(L) + "). Wrong file or order incorrect?");
+				}
+				decoded.resize(2ull * L);
+				decode_sys_errors(r, decoded.data());
+				RSQ_CUDA(cudaMemcpyAsync((strand ? e.d_sys_fwd.p : e.d_sys_rev.p) + 2 * seq_off[i], decoded.data(), 2ull * L, cudaMemcpyHostToDevice, s));
+				RSQ_CUDA(cudaStreamSynchronize(s));
+			}
+			k_build_blocks<<<(nb + 127) / 128, 128, 0, s>>>(e.d_blocks.p, first, nb, i, next_block_id, e.d_master.p + nb, g.methylation_loaded ? e.d_block_meth.p : nullptr, 1u); ++e.launches;
+		}
+		else{
+			const uint8_t *hseq = g.seqs[i].data();
+			std::vector<SysChain> chains(2); std::vector<std::pair<uint32_t, uint32_t>> lens{{L, 0}, {L, 0}};
+			chains[0].seq = e.d_ref.p + seq_off[i]; chains[0].L = L; chains[0].reverse = 1; chains[0].raw = e.d_master.p + nb; chains[0].seed_interleaved = 0;
+			chains[0].out = e.d_sys_rev.p + 2 * seq_off[i]; chains[0].carried_dom = carried;
+			carried = dominant_before(hseq, L, true, L, carried);
+			chains[1].seq = e.d_ref.p + seq_off[i]; chains[1].L = L; chains[1].reverse = 0; chains[1].raw = e.d_master.p + nb + 2ull * L; chains[1].seed_interleaved = 1;
+			chains[1].out = e.d_sys_fwd.p + 2 * seq_off[i]; chains[1].carried_dom = carried;
+			carried = dominant_before(hseq, L, false, L, carried);
+			uint32_t passes = 0;
+			run_sys_chains(e, chains, lens, 8192, 1024, passes);
+			passes_total = std::max(passes_total, passes);
+			k_build_blocks<<<(nb + 127) / 128, 128, 0, s>>>(e.d_blocks.p, first, nb, i, next_block_id, e.d_master.p + nb + 2ull * L, g.methylation_loaded ? e.d_block_meth.p : nullptr, 2001u); ++e.launches;
+		}
 		RSQ_CUDA(cudaStreamSynchronize(s));   // d_master is reused by the next unit
 		next_block_id += nb; first += nb;
 	}
@@ -916,6 +1026,64 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		rep->syserr_passes = e.syserr_passes; rep->kernel_launches = e.launches;
 	}
 	e.prepared = true;
+}
+
+// Simulator::CreateSystematicErrorProfile: every sequence, whole reverse strand then whole forward strand, each chain from
+// reset counters with a contiguous run of the master stream (no block seeds, no adapters).
+static void create_sys_profile(rsq_engine &e, const Genome &g, uint64_t seed, const char *out_path){
+	cudaStream_t s = e.stream;
+	const Profile &p = e.prof;
+	e.launches = 0; e.d_error_flag.zero(s);
+	for(const auto &q : g.seqs){ for(uint8_t b : q){ if(b > 3){ throw std::runtime_error("Reference contains ambiguous bases(e.g. N). Please replace them, remove them from the scaffolds or split scaffolds into contigs."); } } }
+	uint64_t reads = 0, sum_read_length = 0;
+	for(int seg = 2; seg--; ){ for(auto len = p.read_lengths[seg].from; len < p.read_lengths[seg].to(); ++len){ reads += p.read_lengths[seg][len]; sum_read_length += p.read_lengths[seg][len] * len; } }
+	e.sys_gc_range = static_cast<uint32_t>((sum_read_length + reads / 2) / reads) / 2;
+	FILE *o = fopen(out_path, "wb");
+	if(!o){ throw std::runtime_error(std::string("Could not open '") + out_path + "' for writing."); }
+	try{
+		e.d_master_state.alloc(kMtN + 1);
+		k_master_seed<<<1, 32, 0, s>>>(e.d_master_state.p, seed); ++e.launches;
+		uint32_t carried = 0;
+		std::vector<uint8_t> host; std::string text;
+		for(size_t i = 0; i < g.seqs.size(); ++i){
+			const uint32_t L = g.seqs[i].size();
+			if(!L){ fprintf(o, "@%s reverse\n\n+\n\n@%s forward\n\n+\n\n", g.ids[i].c_str(), g.ids[i].c_str()); continue; }
+			e.d_ref.alloc(L + 1);
+			RSQ_CUDA(cudaMemcpyAsync(e.d_ref.p, g.seqs[i].data(), L, cudaMemcpyHostToDevice, s));
+			e.d_master.alloc(4ull * L);
+			k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, 4ull * L); ++e.launches;
+			e.d_sys_rev.alloc(2ull * L + 2); e.d_sys_fwd.alloc(2ull * L + 2);
+			std::vector<SysChain> chains(2); std::vector<std::pair<uint32_t, uint32_t>> lens{{L, 0}, {L, 0}};
+			chains[0].seq = e.d_ref.p; chains[0].L = L; chains[0].reverse = 1; chains[0].raw = e.d_master.p; chains[0].out = e.d_sys_rev.p; chains[0].carried_dom = carried;
+			carried = dominant_before(g.seqs[i].data(), L, true, L, carried);
+			chains[1].seq = e.d_ref.p; chains[1].L = L; chains[1].reverse = 0; chains[1].raw = e.d_master.p + 2ull * L; chains[1].out = e.d_sys_fwd.p; chains[1].carried_dom = carried;
+			carried = dominant_before(g.seqs[i].data(), L, false, L, carried);
+			uint32_t passes = 0;
+			run_sys_chains(e, chains, lens, 8192, 1024, passes);
+			host.resize(2ull * L);
+			for(int strand = 0; strand < 2; ++strand){
+				RSQ_CUDA(cudaMemcpyAsync(host.data(), strand ? e.d_sys_fwd.p : e.d_sys_rev.p, 2ull * L, cudaMemcpyDeviceToHost, s));
+				RSQ_CUDA(cudaStreamSynchronize(s));
+				text.assign(1, '@'); text += g.ids[i]; text += strand ? " forward\n" : " reverse\n";
+				const size_t seq_at = text.size();
+				text.resize(seq_at + 2ull * L + 4);
+				char *dom = &text[seq_at], *qual = dom + L + 3;
+				for(uint32_t pos = 0; pos < L; ++pos){
+					dom[pos] = "ACGTN"[host[2 * pos] > 4 ? 4 : host[2 * pos]];
+					uint8_t q = host[2 * pos + 1];
+					if(86 < q){ q -= (q - 85) / 2; }      // WriteOutSystematicErrorProfile (Simulator.cpp:2569-2575)
+					qual[pos] = static_cast<char>(q + 33);
+				}
+				dom[L] = '\n'; dom[L + 1] = '+'; dom[L + 2] = '\n'; qual[L] = '\n';
+				if(fwrite(text.data(), 1, text.size(), o) != text.size()){ throw std::runtime_error("Could not write systematic error profile"); }
+			}
+		}
+		const uint32_t flag = read_error_flag(e);
+		if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
+	}
+	catch(...){ fclose(o); throw; }
+	fclose(o);
+	e.prepared = false;
 }
 
 static void setup_arena(rsq_engine &e, Arena &a, uint64_t expected_bytes, uint32_t slots){
@@ -1316,6 +1484,15 @@ int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq
 	if(rc){ remove(first_reads_path); remove(second_reads_path); }
 	rsq_engine_destroy(e);
 	return rc;
+}
+
+int rsq_create_systematic_error_profile(rsq_engine *engine, const rsq_reference *ref, uint64_t seed, const char *fastq_out_path){
+	RSQ_TRY
+	RSQ_CUDA(cudaSetDevice(engine->device));
+	try{ create_sys_profile(*engine, ref->g, seed, fastq_out_path); }
+	catch(...){ remove(fastq_out_path); throw; }
+	return 0;
+	RSQ_CATCH(1)
 }
 
 int rsq_apply_error_model(rsq_engine *engine, const char *fasta_in_path, const char *fastq_out_path, uint64_t seed, rsq_sim_report *report){

@@ -72,6 +72,46 @@ def test_malformed_methylation_file_is_an_error(rb, golden, workdir):
         ref.load_methylation(bad)
 
 
+def test_systematic_error_profile_write_and_read_against_reference_binary(rb, engine, golden, oracle, workdir):
+    """--writeSysError (Simulator::CreateSystematicErrorProfile) and --readSysError (ReadSystematicErrors)."""
+    fa = os.path.join(workdir, "sysref.fa")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic.py"), "reference", fa, "--sizes", "21000,9000,12500", "--seed", "5",
+                    "--prefix", "s"], check=True)
+    ref = rb.Reference.load_fasta(fa)
+    mine = os.path.join(workdir, "sys_mine.fq")
+    engine.create_systematic_error_profile(ref, 9, mine)
+    theirs = os.path.join(workdir, "sys_ref.fq")
+    o1, o2 = run_oracle_sim(oracle, golden["reseq"], fa, 9, 10.0, os.path.join(workdir, "ora_sys"), extra=("--writeSysError", theirs))
+    assert open(mine, "rb").read() == open(theirs, "rb").read()
+    r1, r2, _ = _simulate(engine, ref, seed=9, coverage=10.0, sys_error_file=mine)
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+    # a different seed with the same error file (plain --readSysError)
+    o1, o2 = run_oracle_sim(oracle, golden["reseq"], fa, 10, 10.0, os.path.join(workdir, "ora_sys2"), extra=("--readSysError", theirs))
+    r1, r2, _ = _simulate(engine, ref, seed=10, coverage=10.0, sys_error_file=theirs)
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+
+
+def test_ref_bias_models_against_reference_binary(rb, engine, golden, oracle, workdir):
+    """--refBias draw (consumes master-stream draws first) and --refBias file (several coverage groups)."""
+    fa = os.path.join(workdir, "biasref.fa")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic.py"), "reference", fa, "--sizes", "18000,14000,9000", "--seed", "8",
+                    "--prefix", "b"], check=True)
+    ref = rb.Reference.load_fasta(fa)
+    r1, r2, _ = _simulate(engine, ref, seed=21, coverage=10.0, ref_bias_model=2)
+    o1, o2 = run_oracle_sim(oracle, golden["reseq"], fa, 21, 10.0, os.path.join(workdir, "ora_draw"), extra=("--refBias", "draw"))
+    assert r1 == open(o1, "rb").read() and r2 == open(o2, "rb").read()
+    bias_file = os.path.join(workdir, "bias.txt")
+    open(bias_file, "w").write("b1 0.4\n>b2 some description 2.5\nb3\t1.0\n")
+    r1, r2, _ = _simulate(engine, ref, seed=22, coverage=10.0, ref_bias_model=3, ref_bias_file=bias_file)
+    o1, o2 = run_oracle_sim(oracle, golden["reseq"], fa, 22, 10.0, os.path.join(workdir, "ora_file"), extra=("--refBias", "file", "--refBiasFile", bias_file))
+    assert r1 == open(o1, "rb").read() and r2 == open(o2, "rb").read()
+    with pytest.raises(rb.RsqError, match="reference sequence biases"):
+        open(bias_file, "w").write("b1 0.4\n")
+        engine.prepare(ref, seed=22, coverage=10.0, ref_bias_model=3, ref_bias_file=bias_file)
+
+
 def test_dropin_simulate_call_writes_files(rb, golden, workdir):
     prof = rb.Profile.load_flat(golden["flat"])
     ref = rb.Reference.load_fasta(golden["small_ref"])
