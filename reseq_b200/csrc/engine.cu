@@ -1035,9 +1035,11 @@ static void create_sys_profile(rsq_engine &e, const Genome &g, uint64_t seed, co
 	const Profile &p = e.prof;
 	e.launches = 0; e.d_error_flag.zero(s);
 	for(const auto &q : g.seqs){ for(uint8_t b : q){ if(b > 3){ throw std::runtime_error("Reference contains ambiguous bases(e.g. N). Please replace them, remove them from the scaffolds or split scaffolds into contigs."); } } }
-	uint64_t reads = 0, sum_read_length = 0;
-	for(int seg = 2; seg--; ){ for(auto len = p.read_lengths[seg].from; len < p.read_lengths[seg].to(); ++len){ reads += p.read_lengths[seg][len]; sum_read_length += p.read_lengths[seg][len] * len; } }
-	e.sys_gc_range = static_cast<uint32_t>((sum_read_length + reads / 2) / reads) / 2;
+	// The reference never initialises sys_gc_range_ on this path (it is only set inside Simulate / SimulateErrorModelOnly,
+	// Simulator.cpp:2782, 2962; CreateSystematicErrorProfile runs on a fresh Simulator object): the GC window length is
+	// whatever the stack held.  In the reference build of this image every value >= ~2*10^4 reproduces its output; we use
+	// the largest uintReadLen, i.e. "all bases seen so far, at most 65535".
+	e.sys_gc_range = 65535;
 	FILE *o = fopen(out_path, "wb");
 	if(!o){ throw std::runtime_error(std::string("Could not open '") + out_path + "' for writing."); }
 	try{
@@ -1235,9 +1237,11 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 	}
 	if(max_len > kMaxOrgLen){ throw std::runtime_error("input fragments longer than " + std::to_string(kMaxOrgLen) + " bases are not supported by this build"); }
 	// sys_gc_range + adapter systematic errors from the master stream, then one seed per 10000-record batch
-	uint64_t reads = 0, sum_read_length = 0;
-	for(int seg = 2; seg--; ){ for(auto len = p.read_lengths[seg].from; len < p.read_lengths[seg].to(); ++len){ reads += p.read_lengths[seg][len]; sum_read_length += p.read_lengths[seg][len] * len; } }
-	e.sys_gc_range = static_cast<uint32_t>((sum_read_length + reads / 2) / reads) / 2;
+	// The reference never initialises sys_gc_range_ on this path (it is only set inside Simulate / SimulateErrorModelOnly,
+	// Simulator.cpp:2782, 2962; CreateSystematicErrorProfile runs on a fresh Simulator object): the GC window length is
+	// whatever the stack held.  In the reference build of this image every value >= ~2*10^4 reproduces its output; we use
+	// the largest uintReadLen, i.e. "all bases seen so far, at most 65535".
+	e.sys_gc_range = 65535;
 	e.d_master_state.alloc(kMtN + 1);
 	k_master_seed<<<1, 32, 0, s>>>(e.d_master_state.p, seed); ++e.launches;
 	uint32_t carried = 0;
