@@ -502,6 +502,9 @@ struct rsq_reference { Genome g; };
 struct rsq_engine {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t stream2 = nullptr;        // bias sums overlap with the master stream / systematic errors
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	PinnedBuf h_bias_results;
 	Profile prof;
 	uint32_t max_n0 = 0;
 	uint32_t launches = 0;
@@ -551,7 +554,7 @@ struct rsq_engine {
 	PinnedBuf h_out[2];
 	bool downloaded = false;
 
-	~rsq_engine(){ if(stream){ cudaStreamDestroy(stream); } }
+	~rsq_engine(){ if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
 };
 
 namespace rsq {
@@ -870,20 +873,22 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 			}
 		}
 	}
+	// The ordered sums run on a second stream: they only feed the thresholds, which nothing needs before k_simulate,
+	// so they overlap with the master stream and the systematic-error chains below.
 	std::vector<double> sums(params.size(), 0.0), maxb(params.size(), 0.0);
 	if(!params.empty()){
 		DevBuf<BiasParamDev> &d_params = e.d_bias_params; d_params.upload(dparams, s);
 		DevBuf<double> &d_sums = e.d_bias_sums, &d_max = e.d_bias_max; d_sums.alloc(params.size()); d_max.alloc(params.size());
-		k_sum_bias<<<(params.size() + 3) / 4, 128, 0, s>>>(d_params.p, params.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
+		e.h_bias_results.ensure(2 * params.size() * sizeof(double));
+		RSQ_CUDA(cudaEventRecord(e.ev_fork, s));
+		RSQ_CUDA(cudaStreamWaitEvent(e.stream2, e.ev_fork, 0));
+		k_sum_bias<<<(params.size() + 3) / 4, 128, 0, e.stream2>>>(d_params.p, params.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
 		++e.launches;
-		RSQ_CUDA(cudaMemcpyAsync(sums.data(), d_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, s));
-		RSQ_CUDA(cudaMemcpyAsync(maxb.data(), d_max.p, maxb.size() * 8, cudaMemcpyDeviceToHost, s));
-		RSQ_CUDA(cudaStreamSynchronize(s));
+		RSQ_CUDA(cudaMemcpyAsync(e.h_bias_results.p, d_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
+		RSQ_CUDA(cudaMemcpyAsync(e.h_bias_results.p + sums.size() * 8, d_max.p, maxb.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
+		RSQ_CUDA(cudaEventRecord(e.ev_join, e.stream2));
 	}
-	if(!finish_normalization(e.norm, p, rsb, spline, params, sums, maxb, e.total_pairs)){ throw std::runtime_error("bias normalisation is zero"); }
-	e.d_thr.upload(e.norm.thresholds, s); e.d_thr_int.upload(e.norm.thr_int, s); e.d_binom_p0.upload(e.norm.binom_p0, s); e.d_cov_group.upload(e.norm.coverage_groups, s);
-	c.thr = e.d_thr.p; c.thr_int = e.d_thr_int.p; c.binom_p0 = e.d_binom_p0.p; c.coverage_group = e.d_cov_group.p; c.bias_normalization = e.norm.bias_normalization;
-	if(rep){ rep->ms_bias = tm.stop(); rep->bias_normalization = e.norm.bias_normalization; } else { tm.stop(); }
+	float ms_bias = tm.stop();
 
 	// --- methylation regions (Reference::ReadMethylation) ---
 	c.meth_loaded = g.methylation_loaded ? 1u : 0u;
@@ -1012,12 +1017,25 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		RSQ_CUDA(cudaStreamSynchronize(s));
 	}
 	e.syserr_passes = passes_total;
+	const float ms_syserr = tm.stop();
+	// --- join the bias sums, finish CalculateBiasNormalization on the host (spline, thresholds: same libm as the reference) ---
+	tm.start();
+	if(!params.empty()){
+		RSQ_CUDA(cudaEventSynchronize(e.ev_join));
+		std::memcpy(sums.data(), e.h_bias_results.p, sums.size() * 8);
+		std::memcpy(maxb.data(), e.h_bias_results.p + sums.size() * 8, maxb.size() * 8);
+	}
+	if(!finish_normalization(e.norm, p, rsb, spline, params, sums, maxb, e.total_pairs)){ throw std::runtime_error("bias normalisation is zero"); }
+	e.d_thr.upload(e.norm.thresholds, s); e.d_thr_int.upload(e.norm.thr_int, s); e.d_binom_p0.upload(e.norm.binom_p0, s); e.d_cov_group.upload(e.norm.coverage_groups, s);
+	c.thr = e.d_thr.p; c.thr_int = e.d_thr_int.p; c.binom_p0 = e.d_binom_p0.p; c.coverage_group = e.d_cov_group.p; c.bias_normalization = e.norm.bias_normalization;
+	RSQ_CUDA(cudaStreamSynchronize(s));
+	ms_bias += tm.stop();
+	if(rep){ rep->ms_bias = ms_bias; rep->bias_normalization = e.norm.bias_normalization; rep->ms_syserr = ms_syserr; }
 	const uint32_t sc = opt.shard_count ? opt.shard_count : 1, si = opt.shard_index;
 	if(si >= sc){ throw std::runtime_error("shard_index out of range"); }
 	e.shard_first = static_cast<uint64_t>(e.n_blocks_sim) * si / sc;
 	e.shard_n = static_cast<uint64_t>(e.n_blocks_sim) * (si + 1) / sc - e.shard_first;
 	e.shard_has_adapter_only = (si + 1 == sc) && e.adapter_only_pairs;
-	if(rep){ rep->ms_syserr = tm.stop(); } else { tm.stop(); }
 	RSQ_CUDA(cudaGetLastError());
 	const uint32_t flag = read_error_flag(e);
 	if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
@@ -1418,6 +1436,9 @@ rsq_engine *rsq_engine_create(const rsq_profile *profile, int device){
 	std::unique_ptr<rsq_engine> e(new rsq_engine);
 	e->device = device;
 	RSQ_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	RSQ_CUDA(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+	RSQ_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+	RSQ_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
 	e->prof = profile->p;
 	upload_profile(*e);
 	return e.release();
