@@ -81,6 +81,8 @@ typedef struct rsq_sim_report {
 	uint32_t kernel_launches;      /* launches of this library's kernels during prepare + simulate */
 	/* device time in milliseconds (CUDA events on the engine's stream) */
 	float ms_upload, ms_bias, ms_syserr, ms_simulate, ms_gather, ms_download;
+	/* speculative two-phase simulation (0/0 when the serial kernel ran): rounds of scan + read kernels, reads emitted per unit and round */
+	uint32_t spec_rounds, spec_depth;
 } rsq_sim_report;
 
 rsq_engine *rsq_engine_create(const rsq_profile *profile, int device);

@@ -22,7 +22,8 @@ class SimReport(C.Structure):
                 ("blocks", C.c_uint64), ("blocks_total", C.c_uint64), ("positions", C.c_uint64), ("scan_draws", C.c_uint64),
                 ("bias_normalization", C.c_double), ("syserr_passes", C.c_uint32), ("kernel_launches", C.c_uint32),
                 ("ms_upload", C.c_float), ("ms_bias", C.c_float), ("ms_syserr", C.c_float), ("ms_simulate", C.c_float),
-                ("ms_gather", C.c_float), ("ms_download", C.c_float)]
+                ("ms_gather", C.c_float), ("ms_download", C.c_float),
+                ("spec_rounds", C.c_uint32), ("spec_depth", C.c_uint32)]
 
     def as_dict(self):
         out = {}

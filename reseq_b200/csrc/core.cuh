@@ -26,10 +26,10 @@ struct WarpGroup {
 #endif
 struct SingleLane {
 	static constexpr int kSize = 1;
-	int lane() const { return 0; }
-	void sync() const {}
-	unsigned ballot(bool p) const { return p ? 1u : 0u; }
-	uint32_t reduce_add(uint32_t v) const { return v; }
+	RSQ_HD int lane() const { return 0; }
+	RSQ_HD void sync() const {}
+	RSQ_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+	RSQ_HD uint32_t reduce_add(uint32_t v) const { return v; }
 };
 
 // ----------------------------------------------------------------------------------------------

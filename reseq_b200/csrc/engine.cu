@@ -23,6 +23,7 @@
 #include "../../include/reseq_b200.h"
 #include "host_profile.hpp"
 #include "sim_core.cuh"
+#include "spec_core.cuh"
 #include "bias_core.cuh"
 #include "archive_reader.hpp"
 
@@ -334,6 +335,15 @@ struct DeviceSink {
 
 struct BlockOut { uint32_t head[2]; unsigned long long bytes[2]; uint32_t pairs; uint32_t pad; unsigned long long scan_draws; };
 
+__global__ void k_spec_block_out(SpecCtx sp, BlockOut *out){
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if(u >= sp.n_units){ return; }
+	const SpecBlock &b = sp.blocks[u];
+	BlockOut o; o.head[0] = b.chain_head; o.head[1] = b.chain_head; o.bytes[0] = b.bytes[0]; o.bytes[1] = b.bytes[1];
+	o.pairs = b.reads / 2u; o.pad = b.rounds; o.scan_draws = b.scan_draws;
+	out[u] = o;
+}
+
 template<bool kMeth>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 8)   // 8 CTAs x 4 warps = 32 blocks in flight per SM (<= 64 registers)
 k_simulate(SimCtx c, const BlockDesc *blocks, uint32_t first_block, uint32_t n_blocks, Arena arena, BlockOut *out, uint32_t *next_block,
@@ -357,6 +367,169 @@ k_simulate(SimCtx c, const BlockDesc *blocks, uint32_t first_block, uint32_t n_b
 			o.pairs = sink.pairs; o.pad = 0; o.scan_draws = draws;
 			out[i] = o;
 		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Speculative two-phase path (spec_core.cuh): k_spec_scan (warp per unit) and k_spec_reads (lane per read) alternate
+// in rounds until every unit has verified all its reads; k_spec_gather assembles the FASTQ text from the record slots.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_spec_init(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32_t first_desc){
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if(u < sp.n_units){ spec_init_unit(c, sp, descs, first_desc, u); }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_spec_scan(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32_t first_desc){
+	__shared__ uint64_t rings[kWarpsPerCta][2 * kMtN];
+	WarpGroup g;
+	const uint32_t warp = threadIdx.x >> 5;
+	const uint32_t u = blockIdx.x * kWarpsPerCta + warp;
+	if(u >= sp.n_units){ return; }
+	scan_window(g, c, sp, descs, first_desc, u, rings[warp]);
+}
+
+// LogArrayResult::Draw for 32 independent reads at once.  The likelihood products of every read are computed
+// cooperatively (the lanes of a group of 8/16/32 take consecutive candidates of one read: coalesced table rows) and
+// parked in shared memory; each lane then runs the two strictly ordered FP64 sums of its own read.
+__device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint32_t stride, bool active, uint32_t table_id,
+                                               uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, double u, bool &zero){
+	const unsigned amask = __ballot_sync(0xffffffffu, active);
+	zero = false;
+	if(amask == 0){ return 0; }
+	const uint32_t lane = threadIdx.x & 31;
+	uint32_t n0 = 0, nm = 0, par0_off = 0, o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+	if(active){
+		const TableDesc d = t.desc[table_id];
+		n0 = d.n0; nm = d.nm; par0_off = d.par0_off;
+		o0 = d.off[0] + adjust_index(i0, d.from[0], d.span[0]) * n0;
+		o1 = d.off[1] + adjust_index(i1, d.from[1], d.span[1]) * n0;
+		o2 = d.off[2] + adjust_index(i2, d.from[2], d.span[2]) * n0;
+		o3 = nm > 3 ? d.off[3] + adjust_index(i3, d.from[3], d.span[3]) * n0 : o0;
+	}
+	const uint32_t maxn = __reduce_max_sync(0xffffffffu, n0);
+	if(maxn == 0){ zero = true; return 0; }
+	const uint32_t n4 = (maxn + 3u) & ~3u;
+	const uint32_t shift = maxn <= 8u ? 3u : (maxn <= 16u ? 4u : 5u);   // lanes per read: 8, 16 or 32
+	const uint32_t gs = 1u << shift, per = 32u >> shift;
+	const uint32_t sub = lane >> shift, i = lane & (gs - 1u);
+	const unsigned gmask = per == 1u ? 1u : (per == 2u ? 3u : 15u);
+	__syncwarp();
+	for(uint32_t base = 0; base < 32u; base += per){
+		if(((amask >> base) & gmask) == 0u){ continue; }
+		const uint32_t src = base + sub;
+		const uint32_t sn0 = __shfl_sync(0xffffffffu, n0, src);
+		const uint32_t s0 = __shfl_sync(0xffffffffu, o0, src), s1 = __shfl_sync(0xffffffffu, o1, src);
+		const uint32_t s2 = __shfl_sync(0xffffffffu, o2, src), s3 = __shfl_sync(0xffffffffu, o3, src);
+		const bool four = __shfl_sync(0xffffffffu, nm, src) > 3u;
+		double *row = buf + src * stride;
+		for(uint32_t idx = i; idx < n4; idx += gs){
+			double p = 0.0;
+			if(idx < sn0){
+				p = t.blob[s0 + idx];
+				p = mul_rn(p, t.blob[s1 + idx]);
+				p = mul_rn(p, t.blob[s2 + idx]);
+				if(four){ p = mul_rn(p, t.blob[s3 + idx]); }
+			}
+			row[idx] = p;
+		}
+	}
+	__syncwarp();
+	const double *row = buf + lane * stride;
+	uint32_t result = 0;
+	if(active){
+		double prob_sum = 0.0;
+		for(uint32_t k = 0; k < n4; k += 4){
+			const double a = row[k], b = row[k + 1], cc = row[k + 2], e = row[k + 3];
+			prob_sum = add_rn(add_rn(add_rn(add_rn(prob_sum, a), b), cc), e);
+		}
+		zero = (0.0 == prob_sum) || n0 == 0u;
+		if(n0){
+			const double r = mul_rn(u, prob_sum);
+			double sum = 0.0;
+			uint32_t ind0 = n0;
+			while(sum <= r && --ind0){ sum = add_rn(sum, row[ind0]); }
+			result = t.par0[par0_off + ind0];
+		}
+	}
+	return result;
+}
+
+constexpr int kSpecReadWarps = 4;
+__global__ void __launch_bounds__(kSpecReadWarps * 32)
+k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride){
+	extern __shared__ __align__(16) unsigned char smem[];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	double *buf = reinterpret_cast<double *>(smem) + static_cast<size_t>(warp) * 32u * stride;
+	const size_t tile = static_cast<size_t>(blockIdx.x) * kSpecReadWarps + warp;
+	const size_t gidx = tile * 32u + lane;
+	const size_t total = static_cast<size_t>(sp.n_units) * sp.depth;
+	bool have = false;
+	ReadJob job{};
+	if(gidx < total){
+		const uint32_t u = static_cast<uint32_t>(gidx / sp.depth), k = static_cast<uint32_t>(gidx % sp.depth);
+		const SpecBlock &b = sp.blocks[u];
+		have = !b.done && k < b.n_jobs;
+		if(have){ job = sp.jobs[gidx]; }
+	}
+	if(!__any_sync(0xffffffffu, have)){ return; }
+	const uint64_t *slice = sp.words + tile * sp.words_per_job * 32u + lane;
+	unsigned char *slot = sp.slots + static_cast<size_t>(have ? job.slot : 0u) * sp.slot_stride;
+	uint32_t consumed = 0, rec_len = 0;
+	auto draw_fn = [&](bool active, uint32_t table, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, double u, bool &zero) -> uint32_t {
+		return coop_draw(c.tab, buf, stride, active, table, i0, i1, i2, i3, u, zero);
+	};
+	auto any_fn = [](bool p) -> bool { return __any_sync(0xffffffffu, p); };
+	run_read_machine(c, sp, have, job, slice, slot, draw_fn, any_fn, consumed, rec_len);
+	if(have){ sp.jobs[gidx].consumed = consumed; sp.jobs[gidx].rec_len = rec_len; }
+}
+
+// FASTQ text of one (unit, segment): walks the unit's slab chain, a warp assembles one record at a time.
+__global__ void __launch_bounds__(128)
+k_spec_gather(SpecCtx sp, const unsigned long long *offsets, unsigned char *dst0, unsigned char *dst1){
+	__shared__ uint32_t rec_off[33];
+	const uint32_t n = sp.n_units;
+	const uint32_t unit = blockIdx.x >> 1, seg = blockIdx.x & 1u;
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned char *dst = (seg ? dst1 : dst0) + offsets[static_cast<size_t>(seg) * (n + 1) + unit];
+	for(uint32_t slab = sp.blocks[unit].chain_head; slab != kSpecNone; slab = sp.slab_next[slab]){
+		const uint32_t count = sp.slab_count[slab];
+		const unsigned char *base = sp.slots + static_cast<size_t>(slab) * 32u * sp.slot_stride;
+		if(warp == 0){
+			uint32_t len = 0;
+			if(lane < count){
+				const uint32_t *hdr = reinterpret_cast<const uint32_t *>(base + static_cast<size_t>(lane) * sp.slot_stride);
+				if(hdr[2] == seg){ len = 1u + hdr[0] + 1u + hdr[1] + 3u + hdr[1] + 1u; }
+			}
+			uint32_t incl = len;
+			for(int o = 1; o < 32; o <<= 1){ const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if(lane >= static_cast<uint32_t>(o)){ incl += v; } }
+			rec_off[lane] = incl - len;
+			if(lane == 31){ rec_off[32] = incl; }
+		}
+		__syncthreads();
+		for(uint32_t k = warp; k < count; k += 4){
+			const unsigned char *slot = base + static_cast<size_t>(k) * sp.slot_stride;
+			const uint32_t *hdr = reinterpret_cast<const uint32_t *>(slot);
+			if(hdr[2] != seg){ continue; }
+			const uint32_t id_len = hdr[0], rl = hdr[1];
+			const uint32_t rec = 1u + id_len + 1u + rl + 3u + rl + 1u;
+			const uint32_t o_seq = 2u + id_len, o_plus = o_seq + rl, o_qual = o_plus + 3u;
+			const unsigned char *id = slot + 16, *seq = slot + sp.seq_off, *qual = slot + sp.qual_off;
+			unsigned char *d = dst + rec_off[k];
+			for(uint32_t i = lane; i < rec; i += 32){
+				unsigned char ch;
+				if(i == 0){ ch = '@'; }
+				else if(i < 1u + id_len){ ch = id[i - 1]; }
+				else if(i < o_seq){ ch = '\n'; }
+				else if(i < o_plus){ const uint32_t b = seq[i - o_seq]; ch = static_cast<unsigned char>(b > 3u ? 'N' : (0x54474341u >> (8u * b)) & 0xffu); }
+				else if(i < o_qual){ ch = (i == o_plus + 1u) ? '+' : '\n'; }
+				else if(i < o_qual + rl){ ch = qual[i - o_qual]; }
+				else{ ch = '\n'; }
+				d[i] = ch;
+			}
+		}
+		dst += rec_off[32];
+		__syncthreads();
 	}
 }
 
@@ -553,6 +726,13 @@ struct rsq_engine {
 	uint64_t out_pairs = 0, out_draws = 0;
 	PinnedBuf h_out[2];
 	bool downloaded = false;
+	// speculative two-phase path
+	uint32_t max_n0_reads = 0;             // largest candidate count of the tables FillRead draws from
+	uint32_t max_name_len = 0;
+	DevBuf<SpecBlock> d_spec_blocks; DevBuf<SpecSnap> d_spec_snaps; DevBuf<ReadJob> d_spec_jobs; DevBuf<uint32_t> d_spec_corr;
+	DevBuf<uint64_t> d_spec_words; DevBuf<unsigned char> d_spec_slots; DevBuf<uint32_t> d_slab_next, d_slab_count, d_spec_counters;
+	PinnedBuf h_spec_counters;
+	uint32_t spec_rounds = 0, spec_depth = 0;
 
 	~rsq_engine(){ if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
 };
@@ -572,6 +752,10 @@ static void upload_profile(rsq_engine &e){
 		d.par0_off = par0.size(); par0.insert(par0.end(), h.par0.begin(), h.par0.end());
 		desc.push_back(d);
 		e.max_n0 = std::max(e.max_n0, d.n0);
+	}
+	e.max_n0_reads = 0;
+	for(size_t i = 0; i < desc.size(); ++i){   // every family but dom_error_result_ / error_rate_result_ (systematic errors only)
+		if(i < 50u * p.num_tiles || i >= 50u * p.num_tiles + 120u){ e.max_n0_reads = std::max(e.max_n0_reads, desc[i].n0); }
 	}
 	e.d_desc.upload(desc, s); e.d_blob.upload(blob, s); e.d_par0.upload(par0, s);
 	SimCtx &c = e.ctx;
@@ -844,6 +1028,8 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	}
 	e.d_seq_off.upload(seq_off, s); e.d_seq_len.upload(seq_len, s); e.d_name_off.upload(name_off, s);
 	e.d_names.upload(names.data(), names.size() + 1, s);
+	e.max_name_len = 0;
+	for(size_t i = 0; i + 1 < name_off.size(); ++i){ e.max_name_len = std::max(e.max_name_len, name_off[i + 1] - name_off[i]); }
 	e.d_ref_seq_bias.upload(e.run_ref_seq_bias, s);
 	std::string base_id = (opt.record_base_identifier && opt.record_base_identifier[0]) ? opt.record_base_identifier : "ReseqRead";
 	e.d_base_id.upload(base_id.data(), base_id.size() + 1, s);
@@ -1132,15 +1318,128 @@ static void gather(rsq_engine &e, const Arena &a, uint32_t slots, rsq_sim_report
 	RSQ_CUDA(cudaGetLastError());
 }
 
+static void fill_simulate_report(rsq_engine &e, rsq_sim_report *rep, float ms_sim){
+	if(!rep){ return; }
+	rep->ms_simulate = ms_sim; rep->pairs = e.out_pairs; rep->bytes[0] = e.out_bytes[0]; rep->bytes[1] = e.out_bytes[1];
+	rep->blocks = e.shard_n; rep->scan_draws = e.out_draws; rep->kernel_launches = e.launches;
+	rep->spec_rounds = e.spec_rounds; rep->spec_depth = e.spec_depth;
+	uint64_t positions = 0;
+	std::vector<BlockDesc> hb(e.shard_n);
+	if(e.shard_n){ RSQ_CUDA(cudaMemcpy(hb.data(), e.d_blocks.p + e.shard_first, e.shard_n * sizeof(BlockDesc), cudaMemcpyDeviceToHost)); }
+	for(const auto &b : hb){ positions += std::min<uint32_t>(1000, e.genome.seqs[b.ref_id].size() - b.start_pos); }
+	rep->positions = positions;
+}
+
+// Speculative two-phase path: rounds of k_spec_scan + k_spec_reads until every unit is done (see spec_core.cuh).
+static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
+	cudaStream_t s = e.stream;
+	SimCtx &c = e.ctx;
+	int dev_sms = 0; RSQ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e.device));
+	SpecCtx sp{};
+	sp.n_blocks = e.shard_n;
+	sp.n_units = e.shard_n + (e.shard_has_adapter_only ? 1 : 0);
+	sp.adapter_only_pairs = e.shard_has_adapter_only ? e.adapter_only_pairs : 0;
+	sp.adapter_only_seed = e.adapter_only_seed;
+	const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);   // ReadLengths().to(): one past the longest read
+	sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
+	// depth: enough reads in flight to fill the machine, as few as possible beyond that (every read behind a wrong assumption is redone)
+	uint32_t depth = 2;
+	const uint64_t capacity = static_cast<uint64_t>(dev_sms) * 16 * 32;
+	while(depth < 32 && static_cast<uint64_t>(sp.n_units) * depth * 2 <= capacity){ depth *= 2; }
+	if(const char *env = getenv("RSQ_SPEC_DEPTH")){ depth = std::min(32, std::max(1, atoi(env))); }
+	sp.depth = depth; e.spec_depth = depth;
+	const size_t n_jobs = static_cast<size_t>(sp.n_units) * depth;
+	const size_t n_tiles = (n_jobs + 31) / 32;
+	e.d_spec_blocks.alloc(sp.n_units); e.d_spec_snaps.alloc(2 * static_cast<size_t>(sp.n_units)); e.d_spec_jobs.alloc(n_tiles * 32); e.d_spec_corr.alloc(n_jobs);
+	e.d_spec_words.alloc(n_tiles * sp.words_per_job * 32);
+	sp.blocks = e.d_spec_blocks.p; sp.snaps = e.d_spec_snaps.p; sp.jobs = e.d_spec_jobs.p; sp.corr = e.d_spec_corr.p; sp.words = e.d_spec_words.p;
+	const uint32_t id_prefix = c.base_id_len + 10 + 1 + 20 + 1 + 10 + 1 + std::max<uint32_t>(e.max_name_len, 7) + 1 + 10 + 1 + 5 + 11;
+	sp.id_cap = std::min<uint32_t>(kIdCap, (id_prefix + kCigarCap + 2 + 10 + 15) & ~15u);
+	sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
+	e.d_spec_counters.alloc(4); e.h_spec_counters.ensure(4 * sizeof(uint32_t));
+	sp.next_slab = e.d_spec_counters.p; sp.n_active = e.d_spec_counters.p + 1;
+	const uint32_t stride = ((e.max_n0_reads + 3u) & ~3u) + 1u;
+	const size_t shmem_reads = static_cast<size_t>(kSpecReadWarps) * 32 * stride * sizeof(double);
+	RSQ_CUDA(cudaFuncSetAttribute(k_spec_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem_reads)));
+	const double share = e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0;
+	uint64_t expected_reads = static_cast<uint64_t>(2.0 * (e.total_pairs * share + sp.adapter_only_pairs) * 1.15) + 2048;
+	float ms_sim = 0;
+	uint32_t rounds = 0;
+	for(int attempt = 0; ; ++attempt){
+		sp.n_slabs = static_cast<uint32_t>(expected_reads / 32 + 2ull * sp.n_units + 64);
+		e.d_spec_slots.alloc(static_cast<size_t>(sp.n_slabs) * 32 * sp.slot_stride);
+		e.d_slab_next.alloc(sp.n_slabs); e.d_slab_count.alloc(sp.n_slabs);
+		sp.slots = e.d_spec_slots.p; sp.slab_next = e.d_slab_next.p; sp.slab_count = e.d_slab_count.p;
+		e.d_spec_counters.zero(s);
+		EventTimer tm(s);
+		tm.start();
+		rounds = 0;
+		if(sp.n_units){
+			k_spec_init<<<(sp.n_units + 127) / 128, 128, 0, s>>>(c, sp, e.d_blocks.p, e.shard_first); ++e.launches;
+			volatile uint32_t *h_active = reinterpret_cast<volatile uint32_t *>(e.h_spec_counters.p);
+			while(true){
+				RSQ_CUDA(cudaMemsetAsync(sp.n_active, 0, sizeof(uint32_t), s));
+				k_spec_scan<<<(sp.n_units + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, s>>>(c, sp, e.d_blocks.p, e.shard_first); ++e.launches;
+				RSQ_CUDA(cudaMemcpyAsync(e.h_spec_counters.p, sp.n_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+				k_spec_reads<<<static_cast<unsigned>((n_tiles + kSpecReadWarps - 1) / kSpecReadWarps), kSpecReadWarps * 32, shmem_reads, s>>>(c, sp, stride); ++e.launches;
+				RSQ_CUDA(cudaStreamSynchronize(s));
+				if(0 == *h_active){ break; }
+				++rounds;
+				if(rounds > 100000000u){ throw std::runtime_error("speculative simulation does not terminate"); }
+			}
+		}
+		ms_sim = tm.stop();
+		RSQ_CUDA(cudaGetLastError());
+		const uint32_t flag = read_error_flag(e);
+		if(flag == kErrArenaFull && attempt < 3){
+			expected_reads *= 2; e.d_error_flag.zero(s);
+			continue;
+		}
+		if(flag & kErrSpecOverflow){
+			// a read drew more InDels than the look-ahead margin covers: redo the run on the serial kernel
+			e.d_error_flag.zero(s);
+			return false;
+		}
+		if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
+		break;
+	}
+	e.spec_rounds = rounds;
+	// ordered FASTQ text
+	EventTimer tm(s);
+	tm.start();
+	const uint32_t slots = sp.n_units;
+	e.d_block_out.alloc(slots + 1);
+	e.d_offsets.alloc(2ull * (slots + 1)); e.d_totals.alloc(4);
+	if(slots){ k_spec_block_out<<<(slots + 127) / 128, 128, 0, s>>>(sp, e.d_block_out.p); ++e.launches; }
+	k_block_offsets<<<1, 1024, 0, s>>>(e.d_block_out.p, slots, e.d_offsets.p, e.d_totals.p); ++e.launches;
+	unsigned long long totals[4];
+	RSQ_CUDA(cudaMemcpyAsync(totals, e.d_totals.p, sizeof totals, cudaMemcpyDeviceToHost, s));
+	RSQ_CUDA(cudaStreamSynchronize(s));
+	e.out_bytes[0] = totals[0]; e.out_bytes[1] = totals[1]; e.out_pairs = totals[2]; e.out_draws = totals[3];
+	e.d_out[0].alloc(totals[0] + 1); e.d_out[1].alloc(totals[1] + 1);
+	if(slots){ k_spec_gather<<<2 * slots, 128, 0, s>>>(sp, e.d_offsets.p, e.d_out[0].p, e.d_out[1].p); ++e.launches; }
+	const float ms_gather = tm.stop();
+	if(rep){ rep->ms_gather = ms_gather; }
+	RSQ_CUDA(cudaGetLastError());
+	fill_simulate_report(e, rep, ms_sim);
+	return true;
+}
+
 static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	if(!e.prepared){ throw std::runtime_error("rsq_engine_prepare has not been called"); }
 	cudaStream_t s = e.stream;
 	SimCtx &c = e.ctx;
 	e.downloaded = false;
+	e.spec_rounds = 0; e.spec_depth = 0;
+	const bool meth = c.meth_loaded != 0;
+	{
+		// RSQ_SIM_PATH=serial keeps the one-warp-per-SimBlock kernel (parity tests run both); bisulfite runs always use it
+		const char *path = getenv("RSQ_SIM_PATH");
+		if(!meth && !(path && std::string(path) == "serial") && simulate_spec(e, rep)){ return; }
+	}
 	const uint32_t slots = e.shard_n + (e.shard_has_adapter_only ? 1 : 0);
 	const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, c.max_read_len);
 	const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta;
-	const bool meth = c.meth_loaded != 0;
 	auto kernel = meth ? k_simulate<true> : k_simulate<false>;
 	RSQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
 	RSQ_CUDA(cudaFuncSetAttribute(k_adapter_only, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scratch)));
@@ -1179,15 +1478,7 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 		gather(e, a, slots, rep);
 		break;
 	}
-	if(rep){
-		rep->ms_simulate = ms_sim; rep->pairs = e.out_pairs; rep->bytes[0] = e.out_bytes[0]; rep->bytes[1] = e.out_bytes[1];
-		rep->blocks = e.shard_n; rep->scan_draws = e.out_draws; rep->kernel_launches = e.launches;
-		uint64_t positions = 0;
-		std::vector<BlockDesc> hb(e.shard_n);
-		if(e.shard_n){ RSQ_CUDA(cudaMemcpy(hb.data(), e.d_blocks.p + e.shard_first, e.shard_n * sizeof(BlockDesc), cudaMemcpyDeviceToHost)); }
-		for(const auto &b : hb){ positions += std::min<uint32_t>(1000, e.genome.seqs[b.ref_id].size() - b.start_pos); }
-		rep->positions = positions;
-	}
+	fill_simulate_report(e, rep, ms_sim);
 }
 
 static void download(rsq_engine &e, rsq_sim_report *rep){

@@ -1,0 +1,827 @@
+// Speculative two-phase form of the per-read simulation hot path.
+//
+// The reference consumes ONE mt19937_64 stream per 1000-bp SimBlock strictly in order: a scan draw per (position,
+// fragment length), then - for every fragment hit - the draws of its read pairs (Simulator.cpp:2249-2357, 634-721,
+// 454-594, 294-452).  The raw stream is independent of who consumes it, and a read consumes a *predictable* number of
+// draws unless an InDel is drawn.  That allows splitting the work so that reads of many blocks advance in lock step:
+//
+//   phase A  scan_window()   lane group per block: scans, evaluates hits/fragment counts exactly as the reference does and,
+//                            for every read, *assumes* its consumption (plan_read: no InDel), copies the read's slice of
+//                            the stream to HBM and continues scanning behind it.  Emits <= D new reads per round.
+//   phase B  ReadMachine     one lane per read, 32 reads (of several blocks) in lock step: FillRead/FillReadPart as a state
+//                            machine with three draw points per base; reports the consumption it really had.
+//   verify   next scan_window() call: the reads up to and including the first one whose consumption differs from the
+//                            assumption are final (its own start was exact).  The stream is brought to the state right
+//                            behind that prefix (replay with the measured consumptions), which becomes the committed
+//                            snapshot; everything emitted behind it is discarded and scanned again from there.
+//
+// Results are therefore bit-identical to the serial order by construction; a wrong assumption only costs a replay.
+// The same templates run in tests/host_twin with a one-lane group (CPU), the product instantiates them for warps.
+#pragma once
+#include "sim_core.cuh"
+
+namespace rsq {
+
+constexpr uint32_t kSpecNone = 0xffffffffu;
+constexpr uint32_t kSpecOverflow = 0xffffffffu;   // ReadJob::consumed when the slice (assumed + margin) was too short
+constexpr uint32_t kSpecMargin = 32;              // extra stream words copied behind the assumed consumption
+constexpr uint32_t kErrSpecOverflow = 64;         // error flag: a read needed more than assumed + margin draws
+
+// ----------------------------------------------------------------------------------------------------------------
+// mt19937_64 as a two-generation ring: look-ahead of up to 312 words without consuming them
+// ----------------------------------------------------------------------------------------------------------------
+struct MtRing {
+	uint64_t *w;       // 2 * kMtN words, group-shared
+	uint32_t cur;      // next word, [0, 624)
+	uint32_t avail;    // generated words from cur on; (cur + avail) % 312 == 0
+};
+
+template<class G> RSQ_HD void ring_generate(const G &g, MtRing &r){
+	const uint32_t end = r.cur + r.avail;
+	const uint32_t dst = (end >= 2u * kMtN ? end - 2u * kMtN : end) ? kMtN : 0u;   // end is 0, 312 or 624
+	const uint32_t src = dst ? 0u : kMtN;
+	g.sync();
+	for(uint32_t base = 0; base < kMtN; base += G::kSize){
+		const uint32_t i = base + g.lane();
+		if(i < kMtN){
+			const uint64_t x = r.w[src + i];
+			const uint64_t y = (i + 1u < kMtN) ? r.w[src + i + 1u] : r.w[dst];
+			const uint64_t z = (i < kMtM) ? r.w[src + i + kMtM] : r.w[dst + i - kMtM];
+			const uint64_t v = (x & 0xFFFFFFFF80000000ull) | (y & 0x7FFFFFFFull);
+			r.w[dst + i] = z ^ (v >> 1) ^ ((v & 1ull) ? 0xB5026F5AA96619E9ull : 0ull);
+		}
+		g.sync();
+	}
+	r.avail += kMtN;
+}
+template<class G> RSQ_HD void ring_ensure(const G &g, MtRing &r, uint32_t n){   // n <= 312
+	if(r.avail < n){ ring_generate(g, r); }
+}
+RSQ_HD uint64_t ring_raw(const MtRing &r, uint32_t i){   // i < avail
+	uint32_t p = r.cur + i;
+	if(p >= 2u * kMtN){ p -= 2u * kMtN; }
+	return r.w[p];
+}
+RSQ_HD void ring_advance(MtRing &r, uint32_t n){
+	r.cur += n; if(r.cur >= 2u * kMtN){ r.cur -= 2u * kMtN; }
+	r.avail -= n;
+}
+template<class G> RSQ_HD void ring_skip(const G &g, MtRing &r, uint32_t n){
+	while(n){
+		const uint32_t m = n < static_cast<uint32_t>(kMtN) ? n : kMtN;
+		ring_ensure(g, r, m);
+		ring_advance(r, m);
+		n -= m;
+	}
+}
+template<class G> RSQ_HD uint64_t ring_next(const G &g, MtRing &r){
+	ring_ensure(g, r, 1);
+	const uint64_t x = mt_temper(ring_raw(r, 0));
+	ring_advance(r, 1);
+	return x;
+}
+// seed state in the first half; nothing generated yet
+template<class G> RSQ_HD void ring_seed(const G &g, MtRing &r, uint64_t seed){
+	g.sync();
+	if(g.lane() == 0){
+		uint64_t x = seed;
+		r.w[0] = x;
+		for(int i = 1; i < kMtN; ++i){ x = 6364136223846793005ull * (x ^ (x >> 62)) + static_cast<uint64_t>(i); r.w[i] = x; }
+	}
+	r.cur = kMtN; r.avail = 0;
+	g.sync();
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Shared data of the two phases
+// ----------------------------------------------------------------------------------------------------------------
+struct ReadJob {
+	uint32_t ref_id;
+	uint32_t start_pos, end_pos;   // fragment [start, end) on the forward strand (0,0: adapter-only pair)
+	uint32_t fragment_length;
+	uint32_t block_id;             // id printed in the record name
+	uint32_t flags;                // bit 0 segment, bit 1 strand, bits 8.. tile index
+	uint64_t read_number;
+	uint32_t assumed;              // draws the scan assumed this read consumes
+	uint32_t consumed;             // draws it consumed (phase B)
+	uint32_t rec_len;              // bytes of its FASTQ record (phase B)
+	uint32_t slot;                 // output slot
+};
+
+struct SpecHit {                   // where inside SimulateFromGivenBlock's / CreateReads' loop nest the stream stands
+	uint32_t active, in_reads, fragment_length, n_chosen, chosen0, chosen1, ci, counts_left, strand;
+	uint32_t pair_stage;           // reads of the current pair already handled (0..2)
+	uint32_t tile;                 // tile drawn for the current pair
+};
+struct SpecSnap {                  // resumable state of one unit's stream
+	uint32_t pos, len;
+	uint32_t finished, mt_off;
+	SpecHit hit;
+	int32_t cur_meth;
+	uint64_t read_number, scan_draws;
+	uint64_t mt[kMtN];
+};
+struct SpecBlock {
+	uint32_t done, committed;      // committed: which of the two snapshots is the verified one
+	uint32_t n_jobs;               // reads emitted in the last round (speculative until verified)
+	uint32_t fill;                 // verified records in cur_slab
+	uint32_t cur_slab, next_slab;  // output slabs (32 slots) being filled
+	uint32_t chain_head, chain_tail;
+	uint32_t reads, rounds;
+	unsigned long long bytes[2];
+	unsigned long long scan_draws;
+};
+
+struct SpecCtx {
+	uint32_t depth;                // D: reads emitted per unit and round beyond the verified ones (<= 32)
+	uint32_t words_per_job;        // K: capacity of a read's stream slice
+	uint32_t n_units;              // blocks (+ the adapter-only pseudo block) of this batch
+	SpecBlock *blocks;             // [n_units]
+	SpecSnap *snaps;               // [2 * n_units]
+	ReadJob *jobs;                 // [n_units * D]
+	uint32_t *corr;                // [n_units * D] measured consumptions of the verified prefix
+	uint64_t *words;               // [ceil(n_units * D / 32)][K][32] tempered stream words, lane-interleaved per tile of 32 reads
+	// output slots, handed out in slabs of 32
+	unsigned char *slots; uint32_t slot_stride, id_cap, seq_off, qual_off;
+	uint32_t n_slabs; uint32_t *next_slab; uint32_t *slab_next; uint32_t *slab_count;
+	uint32_t *n_active;            // units that still have work after this round
+	// adapter-only pseudo block (Simulator::SimulateAdapterOnlyPairs), unit index n_blocks when present
+	uint32_t n_blocks; uint32_t adapter_only_pairs; uint64_t adapter_only_seed;
+};
+
+RSQ_HD uint32_t spec_alloc_slab(const SpecCtx &sp){
+#if defined(__CUDA_ARCH__)
+	const uint32_t t = atomicAdd(sp.next_slab, 1u);
+#else
+	const uint32_t t = (*sp.next_slab)++;
+#endif
+	return t < sp.n_slabs ? t : kSpecNone;
+}
+RSQ_HD void spec_flag(const SimCtx &c, uint32_t f){
+#if defined(__CUDA_ARCH__)
+	atomicOr(c.error_flag, f);
+#else
+	*c.error_flag |= f;
+#endif
+}
+
+RSQ_HD uint32_t discrete_lookup(const Discrete &d, double p){   // std::lower_bound part of discrete_draw
+	uint32_t lo = 0, len = d.n;
+	while(len > 0){
+		uint32_t half = len >> 1;
+		if(d.cp[lo + half] < p){ lo += half + 1; len -= half + 1; }
+		else{ len = half; }
+	}
+	return lo;
+}
+// GeneralRandomDistributions::ReadLength with the uniform variate supplied (Simulator.h:185-198)
+RSQ_HD uint32_t read_length_from(const SimCtx &c, uint32_t seg, uint32_t fragment_length, double u){
+	const double ins = (fragment_length < c.insert_to) ? static_cast<double>(c.insert_lengths[fragment_length]) : 0.0;
+	const double random_value = mul_rn(u, ins);
+	double counter = 0.0;
+	uint32_t row_from = 0, row_n = 0;
+	const uint64_t *vals = nullptr;
+	if(fragment_length >= c.rlbf_from[seg] && fragment_length < c.rlbf_to[seg]){
+		const uint32_t r = fragment_length - c.rlbf_from[seg];
+		row_from = c.rlbf_row_from[seg][r];
+		row_n = c.rlbf_row_off[seg][r + 1] - c.rlbf_row_off[seg][r];
+		vals = c.rlbf_val[seg] + c.rlbf_row_off[seg][r];
+	}
+	uint32_t read_len = row_from + row_n;
+	while(counter <= random_value && (read_len-- > row_from)){
+		counter = add_rn(counter, static_cast<double>(vals[read_len - row_from]));
+	}
+	return read_len & 0xffffu;
+}
+RSQ_HD uint32_t adapter_length(const SimCtx &c, uint32_t seg, uint32_t adapter_id){
+	uint32_t len = c.adapters[seg].off[adapter_id + 1] - c.adapters[seg].off[adapter_id];
+	return len > c.max_org_len ? c.max_org_len : len;
+}
+RSQ_HD uint32_t fragment_org_len(const SimCtx &c, uint32_t seg, uint32_t fragment_length){
+	uint32_t org_len = c.read_len_to[seg] + c.max_len_deletion;
+	if(fragment_length < org_len){ org_len = fragment_length; }
+	if(org_len > c.max_org_len){ org_len = c.max_org_len; }
+	return org_len;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Phase A
+// ----------------------------------------------------------------------------------------------------------------
+// Copies n stream words to the slice (word k of the read lives at dst[k * 32]), consuming them; returns the last one.
+template<class G> RSQ_HD uint64_t emit_words(const G &g, MtRing &r, uint64_t *dst, uint32_t &k, uint32_t cap, uint32_t n, bool consume = true){
+	uint64_t last = 0;
+	uint32_t kk = k;
+	while(n){
+		const uint32_t m = n < static_cast<uint32_t>(kMtN) ? n : kMtN;
+		ring_ensure(g, r, m);
+		for(uint32_t i = g.lane(); i < m; i += G::kSize){
+			if(kk + i < cap){ dst[static_cast<size_t>(kk + i) * 32u] = mt_temper(ring_raw(r, i)); }
+		}
+		last = mt_temper(ring_raw(r, m - 1u));
+		if(consume){ ring_advance(r, m); }
+		kk += m; n -= m;
+	}
+	if(consume){ k = kk; }
+	return last;
+}
+
+// Emits the slice of one read under the no-InDel hypothesis (mirrors the draw order of Simulator::FillRead) and returns
+// the assumed consumption.  Any deviation of the real read is caught by the verification, so this only has to be right
+// in the common case.
+template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing &r, uint64_t *dst, uint32_t cap, uint32_t seg, uint32_t fragment_length){
+	uint32_t k = 0;
+	uint32_t read_length = c.read_len_from[seg];
+	if(1 != c.read_len_count[seg]){
+		const double u = canonical(emit_words(g, r, dst, k, cap, 1));
+		read_length = read_length_from(c, seg, fragment_length, u);
+	}
+	if(read_length > c.max_read_len){ read_length = c.max_read_len; }
+	const uint32_t org_len = fragment_length ? fragment_org_len(c, seg, fragment_length) : 0u;
+	const uint32_t n_part = read_length < org_len ? read_length : org_len;
+	uint32_t adapter_id = 0;
+	const AdapterSet &as = c.adapters[seg];
+	if(0 == n_part && as.pick.n){ adapter_id = discrete_lookup(as.pick, canonical(emit_words(g, r, dst, k, cap, 1))); }
+	emit_words(g, r, dst, k, cap, 1u + 3u * n_part);      // sequence quality + (InDel, quality, base call) per base
+	if(n_part < read_length){
+		if(0 == adapter_id && as.pick.n){ adapter_id = discrete_lookup(as.pick, canonical(emit_words(g, r, dst, k, cap, 1))); }
+		uint32_t adapter_pos = 0;
+		if(0 == n_part){
+			const Discrete &sc = as.start_cut[adapter_id];
+			adapter_pos = (sc.n ? discrete_lookup(sc, canonical(emit_words(g, r, dst, k, cap, 1))) : 0u) + as.start_cut_from[adapter_id];
+		}
+		const uint32_t alen = adapter_length(c, seg, adapter_id);
+		uint32_t n_ad = alen > adapter_pos ? alen - adapter_pos : 0u;
+		if(n_ad > read_length - n_part){ n_ad = read_length - n_part; }
+		emit_words(g, r, dst, k, cap, 3u * n_ad);
+		if(n_part + n_ad < read_length){
+			const uint32_t rem = read_length - n_part - n_ad;
+			uint32_t tail = c.polya_from;
+			if(c.polya_pick.n){ tail += discrete_lookup(c.polya_pick, canonical(emit_words(g, r, dst, k, cap, 1))); }
+			tail &= 0xffffu;
+			const uint32_t n_tail = tail < rem ? tail : rem;
+			emit_words(g, r, dst, k, cap, n_tail + (rem - n_tail) * (c.overrun_pick.n ? 2u : 1u));
+		}
+	}
+	uint32_t km = k;
+	emit_words(g, r, dst, km, cap, kSpecMargin, false);   // look-ahead only: the next consumer starts at k
+	return k;
+}
+
+template<class G> RSQ_HD uint32_t first_lane(const G &g, unsigned mask){
+#if defined(__CUDA_ARCH__)
+	(void)g; return __ffs(mask) - 1;
+#else
+	(void)g; (void)mask; return 0;
+#endif
+}
+
+template<class G> RSQ_HD void save_snapshot(const G &g, MtRing &ring, SpecSnap &out, uint32_t pos, uint32_t len, bool finished, const SpecHit &hit,
+                                            int32_t cur_meth, uint64_t read_number, uint64_t draws){
+	ring_ensure(g, ring, 1);
+	const uint32_t half = ring.cur >= static_cast<uint32_t>(kMtN) ? kMtN : 0u;
+	g.sync();
+	for(uint32_t i = g.lane(); i < static_cast<uint32_t>(kMtN); i += G::kSize){ out.mt[i] = ring.w[half + i]; }
+	if(g.lane() == 0){
+		out.pos = pos; out.len = len; out.finished = finished ? 1u : 0u; out.mt_off = ring.cur - half; out.hit = hit; out.cur_meth = cur_meth;
+		out.read_number = read_number; out.scan_draws = draws;
+	}
+	g.sync();
+}
+
+// Links a full (or final) slab into the unit's chain.  Lane 0 only.
+RSQ_HD void spec_link_slab(const SpecCtx &sp, SpecBlock &blk, uint32_t slab, uint32_t count){
+	sp.slab_count[slab] = count; sp.slab_next[slab] = kSpecNone;
+	if(blk.chain_tail == kSpecNone){ blk.chain_head = slab; } else{ sp.slab_next[blk.chain_tail] = slab; }
+	blk.chain_tail = slab;
+}
+
+// One round of one unit (SimBlock, or the adapter-only pseudo block):
+//   1. verify the reads phase B just ran: the prefix up to and including the first read whose consumption differs
+//      from the assumption is final; commit its records,
+//   2. bring the stream to the state behind that prefix (the tentative snapshot if everything held, else a replay of
+//      the prefix with the measured consumptions) and make it the committed snapshot,
+//   3. scan on and emit up to `depth` new reads; leave a tentative snapshot behind them.
+template<class G>
+RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t u, uint64_t *ring_mem){
+	SpecBlock &blk = sp.blocks[u];
+	if(blk.done){ return; }
+	const uint32_t D = sp.depth;
+	ReadJob *jobs = sp.jobs + static_cast<size_t>(u) * D;
+	uint32_t *corr = sp.corr + static_cast<size_t>(u) * D;
+	const uint32_t n_prev = blk.n_jobs;
+	uint32_t committed = blk.committed, fill = blk.fill, cur_slab = blk.cur_slab, next_slab = blk.next_slab;
+	uint32_t v = 0;            // verified reads of the previous round
+	bool all_ok = true;
+	g.sync();
+	if(n_prev){
+		uint32_t first_bad = kSpecNone;
+		for(uint32_t base = 0; base < n_prev && first_bad == kSpecNone; base += G::kSize){
+			const uint32_t j = base + g.lane();
+			bool bad = false;
+			if(j < n_prev){
+				const uint32_t cons = jobs[j].consumed;
+				corr[j] = cons;
+				bad = cons != jobs[j].assumed;
+			}
+			const unsigned mask = g.ballot(bad);
+			if(mask){ first_bad = base + first_lane(g, mask); }
+		}
+		g.sync();
+		all_ok = first_bad == kSpecNone;
+		v = all_ok ? n_prev : first_bad + 1u;
+		if(!all_ok && corr[first_bad] == kSpecOverflow){
+			if(g.lane() == 0){ spec_flag(c, kErrSpecOverflow); blk.done = 1; }
+			return;
+		}
+		// commit the records of the verified prefix: slots fill .. fill + v - 1
+		uint32_t b0 = 0, b1 = 0;
+		for(uint32_t j = g.lane(); j < v; j += G::kSize){
+			if(jobs[j].flags & 1u){ b1 += jobs[j].rec_len; } else{ b0 += jobs[j].rec_len; }
+		}
+		b0 = g.reduce_add(b0); b1 = g.reduce_add(b1);
+		fill += v;
+		if(g.lane() == 0){
+			blk.bytes[0] += b0; blk.bytes[1] += b1; blk.reads += v;
+			if(fill >= 32u){ spec_link_slab(sp, blk, cur_slab, 32u); }
+		}
+		if(fill >= 32u){ cur_slab = next_slab; next_slab = kSpecNone; fill -= 32u; }
+		if(all_ok){ committed ^= 1u; }
+	}
+	// ---- restore the committed snapshot ----
+	const SpecSnap &snap = sp.snaps[2 * static_cast<size_t>(u) + committed];
+	MtRing ring; ring.w = ring_mem;
+	g.sync();
+	for(uint32_t i = g.lane(); i < static_cast<uint32_t>(kMtN); i += G::kSize){ ring.w[i] = snap.mt[i]; }
+	ring.cur = snap.mt_off; ring.avail = kMtN - snap.mt_off;
+	uint32_t pos = snap.pos, len = snap.len;
+	SpecHit hit = snap.hit;
+	int32_t cur_meth = snap.cur_meth;
+	uint64_t read_number = snap.read_number, draws = snap.scan_draws;
+	bool finished = snap.finished != 0;
+	g.sync();
+	const uint32_t replay = all_ok ? 0u : v;   // reads to walk over again with their measured consumption
+	if(finished && !replay){
+		if(g.lane() == 0){
+			if(fill){ spec_link_slab(sp, blk, cur_slab, fill); }
+			blk.scan_draws = draws; blk.committed = committed; blk.n_jobs = 0; blk.fill = 0; blk.done = 1;
+		}
+		return;
+	}
+	finished = false;
+	const bool adapter_only = u >= sp.n_blocks;
+	BlockDesc b{};
+	if(!adapter_only){ b = descs[first_desc + u]; }
+	const uint32_t L = adapter_only ? 0u : c.seq_len[b.ref_id];
+	const uint64_t off = adapter_only ? 0u : c.seq_off[b.ref_id];
+	const uint32_t group = adapter_only ? 0u : c.coverage_group[b.ref_id];
+	const double *thr = c.thr + static_cast<size_t>(group) * c.insert_to * 2;
+	const uint64_t *thr_int = c.thr_int + static_cast<size_t>(group) * c.insert_to;
+	const double *binom_p0 = c.binom_p0 + static_cast<size_t>(group) * c.insert_to;
+	const uint32_t *gcp = c.gc_prefix + off + b.ref_id;
+	uint32_t end = b.start_pos + 1000u;
+	if(end > L){ end = L; }
+	uint32_t jw = 0;           // reads walked: the first `replay` are known, the rest are new
+	uint32_t emitted = 0;
+	bool full = false, failed = false;
+	while(!finished && !full){
+		if(hit.active && hit.in_reads){
+			while(hit.counts_left && !full && !failed){
+				if(hit.pair_stage == 0u){
+					if(jw >= replay && emitted >= D){ full = true; break; }
+					++read_number;
+					hit.tile = 0;
+					if(1 < c.num_tiles){ hit.tile = discrete_lookup(c.tile_pick, canonical(ring_next(g, ring))); }
+				}
+				while(hit.pair_stage < 2u){
+					const uint32_t seg = 1u - hit.pair_stage;
+					if(jw < replay){ ring_skip(g, ring, corr[jw]); }
+					else{
+						if(emitted >= D){ full = true; break; }
+						const uint32_t p = fill + emitted;
+						uint32_t slab = p < 32u ? cur_slab : next_slab;
+						if(slab == kSpecNone){
+							if(g.lane() == 0){ slab = spec_alloc_slab(sp); }
+#if defined(__CUDA_ARCH__)
+							slab = __shfl_sync(0xffffffffu, slab, 0);
+#endif
+							if(slab == kSpecNone){ failed = true; break; }
+							if(p < 32u){ cur_slab = slab; } else{ next_slab = slab; }
+						}
+						const size_t gidx = static_cast<size_t>(u) * D + emitted;
+						uint64_t *dst = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
+						const uint32_t assumed = plan_read(g, c, ring, dst, sp.words_per_job, seg, hit.fragment_length);
+						if(g.lane() == 0){
+							ReadJob j;
+							j.ref_id = b.ref_id; j.start_pos = adapter_only ? 0u : pos; j.end_pos = adapter_only ? 0u : pos + hit.fragment_length;
+							j.fragment_length = hit.fragment_length; j.block_id = b.block_id; j.flags = seg | (hit.strand << 1) | (hit.tile << 8);
+							j.read_number = read_number; j.assumed = assumed; j.consumed = kSpecOverflow; j.rec_len = 0; j.slot = slab * 32u + (p & 31u);
+							jobs[emitted] = j;
+						}
+						++emitted;
+					}
+					++jw; ++hit.pair_stage;
+					if(replay && jw == replay){
+						// the stream now stands right behind the verified prefix: this is the new committed state
+						committed ^= 1u;
+						save_snapshot(g, ring, sp.snaps[2 * static_cast<size_t>(u) + committed], pos, len, false, hit, cur_meth, read_number, draws);
+					}
+				}
+				if(full || failed){ break; }
+				hit.pair_stage = 0; --hit.counts_left;
+			}
+			if(full || failed){ break; }
+			hit.in_reads = 0; ++hit.ci;
+			if(adapter_only){ finished = true; break; }
+		}
+		if(hit.active){
+			if(hit.ci < hit.n_chosen){
+				const uint32_t strand = (hit.ci ? hit.chosen1 : hit.chosen0) & 1u;
+				const uint32_t fl = hit.fragment_length;
+				const uint32_t cur_end = pos + fl;
+				if(cur_end < L){
+					const double thr0 = thr[2 * fl];
+					const uint32_t gc_perc = percent_u32(gcp[cur_end] - gcp[pos], fl);
+					const double rv = canonical(ring_next(g, ring));
+					const double adjusted_random = add_rn(thr0, mul_rn(rv, sub_rn(1.0, thr0)));
+					bool runaway = false;
+					const uint32_t counts = fragment_counts(c, b.ref_id, fl, gc_perc, c.sur_start[off + pos], c.sur_end[off + cur_end - 1], adjusted_random, runaway);
+					if(runaway && g.lane() == 0){ spec_flag(c, kErrCountRunaway); }
+					if(counts){ hit.in_reads = 1; hit.counts_left = counts; hit.strand = strand; hit.pair_stage = 0; continue; }
+				}
+				++hit.ci;
+				continue;
+			}
+			hit.active = 0;
+		}
+		// ---- scanning ----
+		if(len >= c.insert_to){
+			++pos; len = c.insert_from;
+			if(pos >= end){ finished = true; break; }
+			continue;
+		}
+		ring_ensure(g, ring, G::kSize);
+		uint32_t n = c.insert_to - len;
+		if(n > static_cast<uint32_t>(G::kSize)){ n = G::kSize; }
+		const uint32_t lane = g.lane();
+		uint64_t x = 0;
+		bool is_hit = false;
+		if(lane < n){
+			x = mt_temper(ring_raw(ring, lane));
+			is_hit = x >= thr_int[len + lane];
+		}
+		const unsigned mask = g.ballot(is_hit);
+		if(mask == 0){
+			ring_advance(ring, n); len += n; draws += n;
+			continue;
+		}
+		const uint32_t first = first_lane(g, mask);
+		const uint32_t fragment_length = len + first;
+		x = mt_temper(ring_raw(ring, first));
+		ring_advance(ring, first + 1u); len = fragment_length + 1u; draws += first + 1u;
+		const double probability_chosen = canonical(x);
+		const double thr0 = thr[2 * fragment_length], thr1 = thr[2 * fragment_length + 1];
+		if(!(probability_chosen >= thr1)){ continue; }
+		const uint32_t non_zero_strands = binomial_count(2, sub_rn(1.0, thr0), binom_p0[fragment_length], probability_chosen);
+		if(!non_zero_strands){ continue; }
+		hit.active = 1; hit.in_reads = 0; hit.fragment_length = fragment_length; hit.ci = 0; hit.counts_left = 0; hit.strand = 0; hit.pair_stage = 0; hit.tile = 0;
+		if(non_zero_strands <= 1){
+			const double rv = canonical(ring_next(g, ring));
+			hit.chosen0 = static_cast<uint32_t>(mul_rn(rv, 2.0)) & 0xffffu; hit.chosen1 = 0; hit.n_chosen = 1;
+		}
+		else{
+			hit.chosen0 = 0; hit.chosen1 = 1; hit.n_chosen = 2;
+		}
+	}
+	if(failed){
+		if(g.lane() == 0){ spec_flag(c, kErrArenaFull); blk.done = 1; }
+		return;
+	}
+	// ---- tentative snapshot behind the new reads ----
+	save_snapshot(g, ring, sp.snaps[2 * static_cast<size_t>(u) + (committed ^ 1u)], pos, len, finished, hit, cur_meth, read_number, draws);
+	if(g.lane() == 0){
+		blk.committed = committed; blk.n_jobs = emitted; blk.fill = fill; blk.cur_slab = cur_slab; blk.next_slab = next_slab; blk.rounds += 1;
+		if(0 == emitted){
+			// nothing left to verify: the tentative snapshot is exact
+			if(fill){ spec_link_slab(sp, blk, cur_slab, fill); }
+			blk.scan_draws = draws; blk.fill = 0; blk.done = 1;
+		}
+		else{
+#if defined(__CUDA_ARCH__)
+			atomicAdd(sp.n_active, 1u);
+#else
+			*sp.n_active += 1;
+#endif
+		}
+	}
+}
+
+// Initial snapshot of a unit: freshly seeded stream, scan at the block start (or, for the adapter-only pseudo block,
+// inside CreateReads with all its pairs left).
+RSQ_HD void spec_init_unit(const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t u){
+	SpecBlock &blk = sp.blocks[u];
+	blk.done = 0; blk.committed = 0; blk.n_jobs = 0; blk.fill = 0; blk.cur_slab = kSpecNone; blk.next_slab = kSpecNone;
+	blk.chain_head = kSpecNone; blk.chain_tail = kSpecNone;
+	blk.reads = 0; blk.rounds = 0; blk.bytes[0] = 0; blk.bytes[1] = 0; blk.scan_draws = 0;
+	SpecSnap &s = sp.snaps[2 * static_cast<size_t>(u)];
+	const bool adapter_only = u >= sp.n_blocks;
+	uint64_t x = adapter_only ? sp.adapter_only_seed : descs[first_desc + u].seed;
+	s.mt[0] = x;
+	for(int i = 1; i < kMtN; ++i){ x = 6364136223846793005ull * (x ^ (x >> 62)) + static_cast<uint64_t>(i); s.mt[i] = x; }
+	s.mt_off = kMtN;   // the whole generation is consumed: the first ring_ensure produces generation 1
+	s.finished = 0; s.read_number = 0; s.scan_draws = 0; s.cur_meth = adapter_only ? 0 : descs[first_desc + u].first_meth;
+	SpecHit h{};
+	if(adapter_only){
+		s.pos = 0; s.len = 0;
+		h.active = 1; h.in_reads = 1; h.fragment_length = 0; h.n_chosen = 1; h.counts_left = sp.adapter_only_pairs;
+		if(0 == sp.adapter_only_pairs){ blk.done = 1; }
+	}
+	else{
+		s.pos = descs[first_desc + u].start_pos; s.len = c.insert_from;
+		const uint32_t L = c.seq_len[descs[first_desc + u].ref_id];
+		if(s.pos >= L){ blk.done = 1; }
+	}
+	s.hit = h;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Phase B: Simulator::FillRead / FillReadPart / CreateReadId for ONE read per lane (Simulator.cpp:454-594, 294-452, 596-632)
+// ----------------------------------------------------------------------------------------------------------------
+enum : uint32_t { kPhFrag = 0, kPhAdapter = 1, kPhTail = 2, kPhOverrun = 3, kPhDone = 4 };
+
+struct ReadMachine {
+	// stream slice
+	const uint64_t *words; uint32_t k, kcap; uint32_t overflow;
+	// output
+	uint8_t *seq_out, *qual_out; char *id; int id_len, id_cap, cigar_len;
+	// job
+	uint32_t seg, tile, fragment_length;
+	// original sequence of the current part: base = comp ? 3 - org[step * pos] : org[step * pos]; sys[2 * pos] / [2 * pos + 1]
+	const uint8_t *org; int32_t org_step; uint32_t org_comp; const uint8_t *sys;
+	uint32_t org_pos, org_len;
+	// Simulator::ReadFillParameter
+	uint32_t read_length, read_pos, previous_indel_type, indel_pos, base_call, gc_seq, seq_qual, qual, error_rate, num_errors;
+	// FillReadPart locals
+	uint32_t phase; char base_cigar, cigar_element; uint32_t cigar_element_length;
+	uint32_t adapter_id, tail_left;
+	// per step
+	uint32_t ref_base, dom_error, indel;
+
+	RSQ_HD double next_u(){
+		if(k >= kcap){ overflow = 1; return 0.5; }
+		return canonical(words[static_cast<size_t>(k++) * 32u]);
+	}
+	RSQ_HD uint32_t org_base(uint32_t p) const {
+		const uint32_t b = org[static_cast<int64_t>(org_step) * static_cast<int64_t>(p)];
+		return org_comp ? 3u - b : b;
+	}
+	RSQ_HD void cigar_append(char op, uint32_t count){
+		SingleLane one;
+		int n = put_uint(one, id, id_len + cigar_len, id_len + kCigarCap < id_cap ? id_len + kCigarCap : id_cap, count);
+		n = put_char(one, id, n, id_len + kCigarCap < id_cap ? id_len + kCigarCap : id_cap, op);
+		cigar_len = n - id_len;
+	}
+	RSQ_HD void stage_adapter(const SimCtx &c){
+		const uint32_t off = c.adapters[seg].off[adapter_id];
+		org = c.adapter_seq + off; org_step = 1; org_comp = 0; sys = c.adapter_sys + 2 * static_cast<size_t>(off);
+		org_len = adapter_length(c, seg, adapter_id);
+		if(c.adapters[seg].off[adapter_id + 1] - off > c.max_org_len){ spec_flag(c, kErrOrgOverflow); }
+	}
+	RSQ_HD void gc_and_error(uint32_t n, uint32_t &mean_error_rate){
+		uint32_t gc = 0, err = 0;
+		for(uint32_t i = 0; i < n; ++i){
+			const uint32_t b = org_base(i);
+			gc += (b == 1 || b == 2) ? 1u : 0u;
+			err += sys[2 * i + 1];
+		}
+		gc_seq = percent_u16(gc, n);
+		mean_error_rate = divide_u32(err, n);
+	}
+
+	// FillRead up to the sequence-quality draw; returns the mean systematic error rate (its second index)
+	RSQ_HD uint32_t begin(const SimCtx &c, const SpecCtx &sp, const ReadJob &j, const uint64_t *slice, unsigned char *slot){
+		words = slice; k = 0; kcap = sp.words_per_job; overflow = 0;
+		seg = j.flags & 1u; tile = j.flags >> 8; fragment_length = j.fragment_length;
+		const bool strand = (j.flags >> 1) & 1u;
+		id = reinterpret_cast<char *>(slot + 16); id_cap = static_cast<int>(sp.id_cap); cigar_len = 0;
+		seq_out = slot + sp.seq_off; qual_out = slot + sp.qual_off;
+		read_pos = 0; previous_indel_type = 0; indel_pos = 0; base_call = 5; gc_seq = 0; qual = 1; error_rate = 0; num_errors = 0; seq_qual = 0;
+		read_length = c.read_len_from[seg];
+		if(1 != c.read_len_count[seg]){ read_length = read_length_from(c, seg, fragment_length, next_u()); }
+		if(read_length > c.max_read_len){ read_length = c.max_read_len; spec_flag(c, kErrOrgOverflow); }
+		// CreateReadId up to the CIGAR (everything the read itself does not change)
+		{
+			SingleLane one;
+			uint32_t print_start = 0, print_end = 0;
+			if(fragment_length){
+				if(strand){ print_start = j.end_pos; print_end = j.start_pos + 1; }
+				else{ print_start = j.start_pos + 1; print_end = j.end_pos; }
+			}
+			int n = 0;
+			n = put_str(one, id, n, id_cap, c.base_id, c.base_id_len);
+			n = put_uint(one, id, n, id_cap, j.block_id);
+			n = put_char(one, id, n, id_cap, '_');
+			n = put_uint(one, id, n, id_cap, j.read_number);
+			n = put_char(one, id, n, id_cap, ':');
+			n = put_uint(one, id, n, id_cap, print_start);
+			n = put_char(one, id, n, id_cap, ':');
+			if(print_start){ n = put_str(one, id, n, id_cap, c.name_blob + c.name_off[j.ref_id], c.name_off[j.ref_id + 1] - c.name_off[j.ref_id]); }
+			else{ n = put_str(one, id, n, id_cap, "Adapter", 7); }
+			n = put_char(one, id, n, id_cap, ':');
+			n = put_uint(one, id, n, id_cap, print_end);
+			n = put_char(one, id, n, id_cap, ':');
+			n = put_uint(one, id, n, id_cap, c.tile_names[tile]);
+			n = put_str(one, id, n, id_cap, ":1337:1337 ", 11);
+			id_len = n;
+		}
+		// GetOrgSeq without variants
+		org_len = 0; org_pos = 0; org = c.ref; org_step = 1; org_comp = 0; sys = c.sys_fwd;
+		if(fragment_length){
+			org_len = fragment_org_len(c, seg, fragment_length);
+			if(c.read_len_to[seg] + c.max_len_deletion > c.max_org_len && fragment_length > c.max_org_len){ spec_flag(c, kErrOrgOverflow); }
+			const uint64_t off = c.seq_off[j.ref_id];
+			const uint32_t L = c.seq_len[j.ref_id];
+			const bool reversed = (seg != static_cast<uint32_t>(strand));
+			if(!reversed){ org = c.ref + off + j.start_pos; sys = c.sys_fwd + 2 * (off + j.start_pos); }
+			else{ org = c.ref + off + j.end_pos - 1; org_step = -1; org_comp = 1; sys = c.sys_rev + 2 * (off + (L - j.end_pos)); }
+		}
+		adapter_id = 0; tail_left = 0;
+		const uint32_t seq_length = read_length < org_len ? read_length : org_len;
+		uint32_t mean_error_rate = 0;
+		if(seq_length){ gc_and_error(seq_length, mean_error_rate); }
+		else{
+			if(c.adapters[seg].pick.n){ adapter_id = discrete_lookup(c.adapters[seg].pick, next_u()); }
+			stage_adapter(c);
+			gc_and_error(org_len, mean_error_rate);
+			org_len = 0;   // FillReadPart over the (empty) fragment part
+		}
+		phase = kPhFrag; base_cigar = 'M'; cigar_element = 'M'; cigar_element_length = 0;
+		return mean_error_rate;
+	}
+
+	// Everything between two draw points: part ends, adapter choice, tails; leaves the lane at a state that needs a draw, or done.
+	RSQ_HD void settle(const SimCtx &c){
+		while(true){
+			if(overflow){ phase = kPhDone; return; }
+			if(phase <= kPhAdapter){
+				if(read_pos < read_length && org_pos < org_len){ return; }
+				if(cigar_element_length){ cigar_append(cigar_element, cigar_element_length); }
+				if(read_pos >= read_length){ phase = kPhDone; return; }
+				if(phase == kPhFrag){
+					const AdapterSet &as = c.adapters[seg];
+					if(0 == adapter_id && as.pick.n){ adapter_id = discrete_lookup(as.pick, next_u()); }
+					uint32_t adapter_pos = 0;
+					if(0 == read_pos){
+						const Discrete &sc = as.start_cut[adapter_id];
+						adapter_pos = (sc.n ? discrete_lookup(sc, next_u()) : 0u) + as.start_cut_from[adapter_id];
+					}
+					stage_adapter(c);
+					org_pos = adapter_pos;
+					phase = kPhAdapter; base_cigar = 'S'; cigar_element = 'S'; cigar_element_length = 0;
+				}
+				else{
+					cigar_append('H', read_length - read_pos);
+					uint32_t tail = c.polya_from;
+					if(c.polya_pick.n){ tail += discrete_lookup(c.polya_pick, next_u()); }
+					tail_left = tail & 0xffffu;
+					phase = kPhTail;
+				}
+			}
+			else if(phase == kPhTail){
+				if(tail_left && read_pos < read_length){ return; }
+				phase = kPhOverrun;
+			}
+			else if(phase == kPhOverrun){
+				if(read_pos < read_length){ return; }
+				phase = kPhDone; return;
+			}
+			else{ return; }
+		}
+	}
+
+	RSQ_HD uint32_t previous_quality(const SimCtx &c) const { return (qual_out[read_pos - 1] - c.phred_offset) & 0xffu; }
+
+	// CreateReadId tail + record header; returns the record length
+	RSQ_HD uint32_t finish(const SimCtx &c, unsigned char *slot){
+		SingleLane one;
+		if(cigar_len > kCigarCap){ spec_flag(c, kErrCigarOverflow); cigar_len = kCigarCap; }
+		int n = id_len + cigar_len;
+		n = put_str(one, id, n, id_cap, " E", 2);
+		n = put_uint(one, id, n, id_cap, num_errors);
+		if(n > id_cap){ spec_flag(c, kErrRecordTooLong); n = id_cap; }
+		uint32_t *hdr = reinterpret_cast<uint32_t *>(slot);
+		hdr[0] = static_cast<uint32_t>(n); hdr[1] = read_length; hdr[2] = seg; hdr[3] = 0;
+		return 1u + n + 1u + read_length + 3u + read_length + 1u;
+	}
+};
+
+// The lock-step body shared by the device kernel and the host twin.  DrawFn(active, table, i0, i1, i2, i3, u, zero) -> value
+// is LogArrayResult::Draw for every lane whose `active` is set (all lanes of a group call it together).
+template<class DrawFn, class AnyFn>
+RSQ_HD void run_read_machine(const SimCtx &c, const SpecCtx &sp, bool have_job, const ReadJob &job, const uint64_t *slice, unsigned char *slot,
+                             DrawFn &&draw_fn, AnyFn &&any_fn, uint32_t &consumed, uint32_t &rec_len){
+	ReadMachine m;
+	m.phase = kPhDone; m.overflow = 0; m.k = 0;
+	uint32_t mean_error_rate = 0;
+	if(have_job){ mean_error_rate = m.begin(c, sp, job, slice, slot); }
+	bool zero = false;
+	{
+		const uint32_t tid = have_job ? c.tab.seq_quality(m.seg, m.tile) : 0u;
+		const double u = have_job ? m.next_u() : 0.0;
+		uint32_t sq = draw_fn(have_job, tid, have_job ? m.gc_seq : 0u, mean_error_rate, have_job ? m.fragment_length / 10 : 0u, 0u, u, zero);
+		if(have_job){
+			if(zero){ sq = table_most_likely(c.tab, tid); }
+			m.seq_qual = sq & 0xffu;
+		}
+	}
+	while(true){
+		if(m.phase != kPhDone){ m.settle(c); }
+		if(!any_fn(m.phase != kPhDone)){ break; }
+		const bool part = m.phase <= kPhAdapter;
+		// --- InDel draw ---
+		uint32_t t1 = 0; double u1 = 0.0;
+		if(part){
+			m.ref_base = m.org_base(m.org_pos);
+			u1 = m.next_u();
+			t1 = c.tab.indel(m.previous_indel_type, m.base_call);
+		}
+		uint32_t indel = draw_fn(part, t1, m.indel_pos, m.read_pos, m.gc_seq, 0u, u1, zero);
+		if(part && zero){ indel = 0; }
+		// --- quality draw ---
+		const bool q_part = part && indel != 1u;
+		const bool q_any = q_part || m.phase == kPhTail || m.phase == kPhOverrun;
+		uint32_t t2 = 0; double u2 = 0.0;
+		if(part && indel == 0u){
+			m.dom_error = m.sys[2 * m.org_pos];
+			m.error_rate = m.sys[2 * m.org_pos + 1];
+		}
+		if(q_any){
+			u2 = m.next_u();
+			t2 = c.tab.quality(m.seg, m.tile, q_part ? m.ref_base : 0u);
+		}
+		uint32_t q = draw_fn(q_any, t2, m.seq_qual, m.qual, m.read_pos, m.error_rate, u2, zero);
+		bool need_call = false;
+		uint32_t t3 = 0; double u3 = 0.0;
+		if(q_any){
+			if(part){
+				if(indel == 0u){
+					if(zero){ q = m.read_pos ? m.previous_quality(c) : table_max_value(c.tab, t2); }
+					m.qual = q & 0xffu;
+					m.qual_out[m.read_pos] = static_cast<uint8_t>(m.qual + c.phred_offset);
+					need_call = true;
+					u3 = m.next_u();
+					t3 = c.tab.base_call(m.seg, m.tile, m.ref_base, m.dom_error);
+				}
+				else{   // insertion
+					if(zero){ q = m.qual; }
+					m.qual_out[m.read_pos] = static_cast<uint8_t>(c.phred_offset + q);
+					m.seq_out[m.read_pos] = static_cast<uint8_t>(indel - 2u);
+					if('I' == m.cigar_element){ ++m.cigar_element_length; ++m.indel_pos; }
+					else{
+						m.cigar_append(m.cigar_element, m.cigar_element_length);
+						m.cigar_element = 'I'; m.cigar_element_length = 1; m.indel_pos = 1; m.previous_indel_type = 0;
+					}
+					++m.num_errors; ++m.read_pos;
+				}
+			}
+			else{   // poly-A tail / overrun bases behind the adapter
+				if(zero){ q = m.previous_quality(c); }
+				m.qual = q & 0xffu;
+				uint32_t b = 0;
+				if(m.phase == kPhOverrun){ if(c.overrun_pick.n){ b = discrete_lookup(c.overrun_pick, m.next_u()); } }
+				else{ --m.tail_left; }
+				m.qual_out[m.read_pos] = static_cast<uint8_t>(m.qual + c.phred_offset);
+				m.seq_out[m.read_pos] = static_cast<uint8_t>(b);
+				++m.read_pos;
+			}
+		}
+		else if(part){   // deletion
+			m.error_rate = m.sys[2 * m.org_pos + 1];
+			if('D' == m.cigar_element){ ++m.cigar_element_length; ++m.indel_pos; }
+			else{
+				m.cigar_append(m.cigar_element, m.cigar_element_length);
+				m.cigar_element = 'D'; m.cigar_element_length = 1; m.indel_pos = 1; m.previous_indel_type = 1;
+			}
+			++m.num_errors; ++m.org_pos;
+		}
+		// --- base-call draw ---
+		uint32_t call = draw_fn(need_call, t3, m.qual, m.read_pos, m.num_errors, m.error_rate, u3, zero);
+		if(need_call){
+			if(zero){ call = m.ref_base; }
+			m.base_call = call;
+			m.seq_out[m.read_pos] = static_cast<uint8_t>(call);
+			if(m.base_cigar == m.cigar_element){ ++m.cigar_element_length; }
+			else{
+				m.cigar_append(m.cigar_element, m.cigar_element_length);
+				m.cigar_element = m.base_cigar; m.cigar_element_length = 1; m.indel_pos = 0; m.previous_indel_type = 0;
+			}
+			if(call != m.ref_base){ ++m.num_errors; }
+			++m.read_pos; ++m.org_pos;
+		}
+	}
+	if(have_job){
+		rec_len = m.finish(c, slot);
+		consumed = m.overflow ? kSpecOverflow : m.k;
+	}
+}
+
+}  // namespace rsq

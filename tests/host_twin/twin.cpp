@@ -14,6 +14,7 @@
 #include <vector>
 #include "../../reseq_b200/csrc/host_profile.hpp"
 #include "../../reseq_b200/csrc/sim_core.cuh"
+#include "../../reseq_b200/csrc/spec_core.cuh"
 #include "../../reseq_b200/csrc/bias_core.cuh"
 
 using namespace rsq;
@@ -282,20 +283,87 @@ int main(int argc, char **argv){
 	FILE *o1 = fopen((prefix + "_1.fq").c_str(), "wb"), *o2 = fopen((prefix + "_2.fq").c_str(), "wb");
 	size_t nsim = std::min(max_blocks, blocks.size());
 	unsigned long long total_draws = 0;
-	for(size_t i = 0; i < nsim; ++i){
-		unsigned long long d = 0;
-		if(bed){ simulate_block<true>(lane, c, s, sink, blocks[i], &d); } else{ simulate_block<false>(lane, c, s, sink, blocks[i], &d); }
-		total_draws += d;
-		fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
-		sink.out[0].clear(); sink.out[1].clear();
+	int64_t n_adapter_only = f.scalar_i("sim.num_adapter_only_pairs");
+	if(getenv("RSQ_TWIN_ADAPTER_ONLY")){ n_adapter_only = atoll(getenv("RSQ_TWIN_ADAPTER_ONLY")); }   // serial-vs-speculative consistency checks
+	const char *spec_env = getenv("RSQ_TWIN_SPEC");
+	if(spec_env && !bed){
+		// two-phase speculative form (spec_core.cuh) with one-lane groups: rounds of scan_window + ReadMachine
+		SpecCtx sp{};
+		sp.depth = std::max(1, atoi(spec_env));
+		const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);
+		sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
+		sp.n_blocks = nsim;
+		const bool with_adapter_only = n_adapter_only && nsim == blocks.size();
+		sp.n_units = nsim + (with_adapter_only ? 1 : 0);
+		sp.adapter_only_pairs = with_adapter_only ? n_adapter_only : 0;
+		sp.adapter_only_seed = with_adapter_only ? master() : 0;
+		std::vector<SpecBlock> sblocks(sp.n_units); std::vector<SpecSnap> snaps(2 * static_cast<size_t>(sp.n_units));
+		std::vector<ReadJob> jobs(static_cast<size_t>(sp.n_units) * sp.depth); std::vector<uint32_t> corr(jobs.size());
+		std::vector<uint64_t> words(((jobs.size() + 31) / 32) * sp.words_per_job * 32);
+		sp.blocks = sblocks.data(); sp.snaps = snaps.data(); sp.jobs = jobs.data(); sp.corr = corr.data(); sp.words = words.data();
+		sp.id_cap = kIdCap; sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
+		sp.n_slabs = sp.n_units * 8 + 64;
+		std::vector<unsigned char> slots(static_cast<size_t>(sp.n_slabs) * 32 * sp.slot_stride);
+		std::vector<uint32_t> slab_next(sp.n_slabs), slab_count(sp.n_slabs);
+		uint32_t next_slab = 0, n_active = 0;
+		sp.slots = slots.data(); sp.next_slab = &next_slab; sp.slab_next = slab_next.data(); sp.slab_count = slab_count.data(); sp.n_active = &n_active;
+		for(uint32_t u = 0; u < sp.n_units; ++u){ spec_init_unit(c, sp, blocks.data(), 0, u); }
+		std::vector<uint64_t> ring_mem(2 * kMtN);
+		uint32_t rounds = 0; uint64_t jobs_run = 0, jobs_ok = 0;
+		auto draw_fn = [&](bool active, uint32_t table, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, double u, bool &zero) -> uint32_t {
+			if(!active){ return 0; }
+			return draw(lane, c.tab, table, i0, i1, i2, i3, u, prob.data(), zero);
+		};
+		auto any_fn = [](bool p){ return p; };
+		while(true){
+			n_active = 0;
+			for(uint32_t u = 0; u < sp.n_units; ++u){ scan_window(lane, c, sp, blocks.data(), 0, u, ring_mem.data()); }
+			if(!n_active){ break; }
+			++rounds;
+			for(uint32_t u = 0; u < sp.n_units; ++u){
+				if(sblocks[u].done){ continue; }
+				for(uint32_t i = 0; i < sblocks[u].n_jobs; ++i){
+					const size_t gidx = static_cast<size_t>(u) * sp.depth + i;
+					ReadJob &j = jobs[gidx];
+					const uint64_t *slice = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
+					run_read_machine(c, sp, true, j, slice, sp.slots + static_cast<size_t>(j.slot) * sp.slot_stride, draw_fn, any_fn, j.consumed, j.rec_len);
+					++jobs_run; jobs_ok += j.consumed == j.assumed;
+				}
+			}
+		}
+		for(uint32_t u = 0; u < sp.n_units; ++u){
+			uint64_t bytes[2] = {0, 0};
+			for(uint32_t slab = sblocks[u].chain_head; slab != kSpecNone; slab = slab_next[slab]){
+				for(uint32_t k = 0; k < slab_count[slab]; ++k){
+					const unsigned char *slot = sp.slots + (static_cast<size_t>(slab) * 32 + k) * sp.slot_stride;
+					const uint32_t *hdr = reinterpret_cast<const uint32_t *>(slot);
+					sink.write_record(lane, hdr[2], reinterpret_cast<const char *>(slot + 16), hdr[0], slot + sp.seq_off, slot + sp.qual_off, hdr[1]);
+					bytes[hdr[2]] += 1 + hdr[0] + 1 + hdr[1] + 3 + hdr[1] + 1;
+					if(hdr[2] == 0){ ++sink.pairs; }
+				}
+			}
+			if(bytes[0] != sblocks[u].bytes[0] || bytes[1] != sblocks[u].bytes[1]){ printf("MISMATCH unit %u byte counts\n", u); ++bad; }
+			total_draws += sblocks[u].scan_draws;
+			fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
+			sink.out[0].clear(); sink.out[1].clear();
+		}
+		printf("spec: depth=%u rounds=%u reads_run=%llu assumption_held=%llu slabs=%u\n", sp.depth, rounds, (unsigned long long)jobs_run, (unsigned long long)jobs_ok, next_slab);
 	}
-	const int64_t n_adapter_only = f.scalar_i("sim.num_adapter_only_pairs");
-	if(n_adapter_only && nsim == blocks.size()){
-		Mt mt; mt.s = s.mt; mt.idx = kMtN;
-		mt_seed(lane, mt, master());
-		uint64_t read_number = 0;
-		create_reads(lane, c, s, mt, sink, n_adapter_only, false, 0, 0, read_number, 0, 0, 0);
-		fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
+	else{
+		for(size_t i = 0; i < nsim; ++i){
+			unsigned long long d = 0;
+			if(bed){ simulate_block<true>(lane, c, s, sink, blocks[i], &d); } else{ simulate_block<false>(lane, c, s, sink, blocks[i], &d); }
+			total_draws += d;
+			fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
+			sink.out[0].clear(); sink.out[1].clear();
+		}
+		if(n_adapter_only && nsim == blocks.size()){
+			Mt mt; mt.s = s.mt; mt.idx = kMtN;
+			mt_seed(lane, mt, master());
+			uint64_t read_number = 0;
+			create_reads(lane, c, s, mt, sink, n_adapter_only, false, 0, 0, read_number, 0, 0, 0);
+			fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
+		}
 	}
 	fclose(o1); fclose(o2);
 	printf("blocks=%zu pairs=%" PRIu64 " scan_draws=%llu error_flag=%u stage_mismatches=%d\n", nsim, sink.pairs, total_draws, st.error_flag, bad);

@@ -45,6 +45,24 @@ def test_small_golden_bit_exact(rb, engine, golden):
     assert rep.kernel_launches > 0
 
 
+@pytest.mark.parametrize("path,depth", [("serial", None), ("spec", 1), ("spec", 3), ("spec", 32)])
+def test_serial_and_speculative_paths_bit_exact(rb, engine, golden, monkeypatch, path, depth):
+    """The one-warp-per-SimBlock kernel (k_simulate) and the speculative two-phase kernels (k_spec_scan/k_spec_reads)
+    at several speculation depths write the same bytes; ~18% of this profile's reads draw an InDel, so the
+    verification/replay machinery runs on every block."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    if depth:
+        monkeypatch.setenv("RSQ_SPEC_DEPTH", str(depth))
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    r1, r2, rep = _simulate(engine, ref, seed=42, coverage=20.0)
+    assert r1 == open(golden["r1"], "rb").read()
+    assert r2 == open(golden["r2"], "rb").read()
+    if path == "serial":
+        assert rep.spec_rounds == 0 and rep.spec_depth == 0
+    else:
+        assert rep.spec_depth == depth and rep.spec_rounds > 0
+
+
 def test_methylation_golden_bit_exact(rb, engine, golden):
     """--methylation: bisulfite C->T conversions per unmethylated region (Simulator::CTConversion)."""
     ref = rb.Reference.load_fasta(golden["small_ref"])
