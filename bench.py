@@ -37,6 +37,9 @@ SEED = 42
 BYTES_PER_PAIR = 1420.0      # 740 B FASTQ out + 600 B systematic errors in + 80 B reference in
 BYTES_PER_POSITION = 8.25    # 0.25 B reference + 2 strands x 2 B systematic errors written and read once
 ORACLE = os.path.join(ROOT, "oracle", "_ref", "reseq_oracle")
+# profile150r: synthetic 2x150 profile fitted by the reference's own stats + IPF code from a synthetic SAM with a realistic InDel rate
+# (~5e-5 per base); RSQ_BENCH_PROFILE=profile150 selects the InDel stress profile of the parity tests (1.6e-3 per base)
+PROFILE = os.environ.get("RSQ_BENCH_PROFILE", "profile150r")
 
 
 def unxz(name, tmp):
@@ -113,8 +116,8 @@ def aggregate(dist, world, maxima, sums, device):
 
 def time_reference_cpu(length, coverage, threads, tmp):
     """Runs the reference binary on `length` bases of the workload; returns (pairs, seconds of read generation, total seconds)."""
-    prof = unxz("profile150.reseq.xz", tmp)
-    unxz("profile150.reseq.ipf.xz", tmp)
+    prof = unxz(PROFILE + ".reseq.xz", tmp)
+    unxz(PROFILE + ".reseq.ipf.xz", tmp)
     fa = os.path.join(tmp, f"slice_{length}.fa")
     if not os.path.exists(fa):
         seq = workload_sequence()[:length]
@@ -193,7 +196,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     tmp = tempfile.mkdtemp(prefix="rsq_bench_")
-    prof = rb.Profile.load_flat(unxz("profile150.flat.xz", tmp))
+    prof = rb.Profile.load_flat(unxz(PROFILE + ".flat.xz", tmp))
     seq = workload_sequence().encode()
     eng = rb.Engine(prof, local_rank)
 

@@ -14,6 +14,7 @@
 //          k_build_blocks, k_simulate (warp per SimBlock), k_block_offsets, k_gather, k_error_model.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -380,19 +381,20 @@ __global__ void k_spec_init(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_spec_scan(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32_t first_desc){
+k_spec_scan(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){
 	__shared__ uint64_t rings[kWarpsPerCta][2 * kMtN];
 	WarpGroup g;
 	const uint32_t warp = threadIdx.x >> 5;
-	const uint32_t u = blockIdx.x * kWarpsPerCta + warp;
-	if(u >= sp.n_units){ return; }
+	const uint32_t u = unit_first + blockIdx.x * kWarpsPerCta + warp;
+	if(u >= unit_end){ return; }
 	scan_window(g, c, sp, descs, first_desc, u, rings[warp]);
 }
 
-// LogArrayResult::Draw for 32 independent reads at once.  The likelihood products of every read are computed
-// cooperatively (the lanes of a group of 8/16/32 take consecutive candidates of one read: coalesced table rows) and
-// parked in shared memory; each lane then runs the two strictly ordered FP64 sums of its own read.
-__device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint32_t stride, bool active, uint32_t table_id,
+// LogArrayResult::Draw for up to 32 independent reads at once (lanes 0 .. n_rows-1 own one read each).  The likelihood
+// products of every read are computed cooperatively (the lanes of a group of 8/16/32 take consecutive candidates of one
+// read: coalesced table rows) and parked in shared memory; each lane then runs the two strictly ordered FP64 sums of
+// its own read.
+__device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint32_t stride, uint32_t n_rows, bool active, uint32_t table_id,
                                                uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, double u, bool &zero){
 	const unsigned amask = __ballot_sync(0xffffffffu, active);
 	zero = false;
@@ -415,23 +417,49 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 	const uint32_t sub = lane >> shift, i = lane & (gs - 1u);
 	const unsigned gmask = per == 1u ? 1u : (per == 2u ? 3u : 15u);
 	__syncwarp();
-	for(uint32_t base = 0; base < 32u; base += per){
-		if(((amask >> base) & gmask) == 0u){ continue; }
-		const uint32_t src = base + sub;
+	if(n_rows <= 16u){
+		// few reads per warp: 32 / n_rows lanes work on every read at the same time (one trip of shuffles, all reads in flight together)
+		const uint32_t lpr_shift = n_rows <= 8u ? 2u : 1u, lpr = 1u << lpr_shift;   // n_rows is 8 or 16
+		const uint32_t src = lane >> lpr_shift, i = lane & (lpr - 1u);
 		const uint32_t sn0 = __shfl_sync(0xffffffffu, n0, src);
 		const uint32_t s0 = __shfl_sync(0xffffffffu, o0, src), s1 = __shfl_sync(0xffffffffu, o1, src);
 		const uint32_t s2 = __shfl_sync(0xffffffffu, o2, src), s3 = __shfl_sync(0xffffffffu, o3, src);
 		const bool four = __shfl_sync(0xffffffffu, nm, src) > 3u;
 		double *row = buf + src * stride;
-		for(uint32_t idx = i; idx < n4; idx += gs){
-			double p = 0.0;
-			if(idx < sn0){
-				p = t.blob[s0 + idx];
-				p = mul_rn(p, t.blob[s1 + idx]);
-				p = mul_rn(p, t.blob[s2 + idx]);
-				if(four){ p = mul_rn(p, t.blob[s3 + idx]); }
+		if((amask >> src) & 1u){
+#pragma unroll 4
+			for(uint32_t idx = i; idx < n4; idx += lpr){
+				double p = 0.0;
+				if(idx < sn0){
+					p = __ldg(t.blob + s0 + idx);
+					p = mul_rn(p, __ldg(t.blob + s1 + idx));
+					p = mul_rn(p, __ldg(t.blob + s2 + idx));
+					if(four){ p = mul_rn(p, __ldg(t.blob + s3 + idx)); }
+				}
+				row[idx] = p;
 			}
-			row[idx] = p;
+		}
+	}
+	else{
+#pragma unroll 4
+		for(uint32_t base = 0; base < n_rows; base += per){
+			if(((amask >> base) & gmask) == 0u){ continue; }
+			const uint32_t src = base + sub;
+			const uint32_t sn0 = __shfl_sync(0xffffffffu, n0, src);
+			const uint32_t s0 = __shfl_sync(0xffffffffu, o0, src), s1 = __shfl_sync(0xffffffffu, o1, src);
+			const uint32_t s2 = __shfl_sync(0xffffffffu, o2, src), s3 = __shfl_sync(0xffffffffu, o3, src);
+			const bool four = __shfl_sync(0xffffffffu, nm, src) > 3u;
+			double *row = buf + src * stride;
+			for(uint32_t idx = i; idx < n4; idx += gs){
+				double p = 0.0;
+				if(idx < sn0){
+					p = __ldg(t.blob + s0 + idx);
+					p = mul_rn(p, __ldg(t.blob + s1 + idx));
+					p = mul_rn(p, __ldg(t.blob + s2 + idx));
+					if(four){ p = mul_rn(p, __ldg(t.blob + s3 + idx)); }
+				}
+				row[idx] = p;
+			}
 		}
 	}
 	__syncwarp();
@@ -448,36 +476,48 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 			const double r = mul_rn(u, prob_sum);
 			double sum = 0.0;
 			uint32_t ind0 = n0;
+			// reverse cumulative search, four candidates per trip: the loads leave the dependent add chain
+			while(ind0 >= 5u && sum <= r){
+				const double a = row[ind0 - 1u], b = row[ind0 - 2u], cc = row[ind0 - 3u], e = row[ind0 - 4u];
+				const double s1 = add_rn(sum, a), s2 = add_rn(s1, b), s3 = add_rn(s2, cc), s4 = add_rn(s3, e);
+				if(!(s1 <= r)){ ind0 -= 1u; sum = s1; }
+				else if(!(s2 <= r)){ ind0 -= 2u; sum = s2; }
+				else if(!(s3 <= r)){ ind0 -= 3u; sum = s3; }
+				else{ ind0 -= 4u; sum = s4; }
+			}
 			while(sum <= r && --ind0){ sum = add_rn(sum, row[ind0]); }
-			result = t.par0[par0_off + ind0];
+			result = __ldg(t.par0 + par0_off + ind0);
 		}
 	}
 	return result;
 }
 
+// Lanes 0 .. lanes_per_warp-1 of a warp own one read each; the other lanes only help with the likelihood products.
+// Few reads per warp = short latency per round (small genomes), 32 = fewest instructions per read (large ones).
 constexpr int kSpecReadWarps = 4;
 __global__ void __launch_bounds__(kSpecReadWarps * 32)
-k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride){
+k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){
 	extern __shared__ __align__(16) unsigned char smem[];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	double *buf = reinterpret_cast<double *>(smem) + static_cast<size_t>(warp) * 32u * stride;
-	const size_t tile = static_cast<size_t>(blockIdx.x) * kSpecReadWarps + warp;
-	const size_t gidx = tile * 32u + lane;
-	const size_t total = static_cast<size_t>(sp.n_units) * sp.depth;
+	double *buf = reinterpret_cast<double *>(smem) + static_cast<size_t>(warp) * lanes_per_warp * stride;
+	const size_t gwarp = static_cast<size_t>(blockIdx.x) * kSpecReadWarps + warp;
+	// dense over (unit, read of this round): reads beyond run_depth do not exist in this round
+	const size_t dense = gwarp * lanes_per_warp + lane;
+	const uint32_t u = unit_first + static_cast<uint32_t>(dense / sp.run_depth), k = static_cast<uint32_t>(dense % sp.run_depth);
+	const size_t gidx = static_cast<size_t>(u) * sp.depth + k;
 	bool have = false;
 	ReadJob job{};
-	if(gidx < total){
-		const uint32_t u = static_cast<uint32_t>(gidx / sp.depth), k = static_cast<uint32_t>(gidx % sp.depth);
+	if(lane < lanes_per_warp && u < unit_end){
 		const SpecBlock &b = sp.blocks[u];
 		have = !b.done && k < b.n_jobs;
 		if(have){ job = sp.jobs[gidx]; }
 	}
 	if(!__any_sync(0xffffffffu, have)){ return; }
-	const uint64_t *slice = sp.words + tile * sp.words_per_job * 32u + lane;
+	const uint64_t *slice = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
 	unsigned char *slot = sp.slots + static_cast<size_t>(have ? job.slot : 0u) * sp.slot_stride;
 	uint32_t consumed = 0, rec_len = 0;
 	auto draw_fn = [&](bool active, uint32_t table, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, double u, bool &zero) -> uint32_t {
-		return coop_draw(c.tab, buf, stride, active, table, i0, i1, i2, i3, u, zero);
+		return coop_draw(c.tab, buf, stride, lanes_per_warp, active, table, i0, i1, i2, i3, u, zero);
 	};
 	auto any_fn = [](bool p) -> bool { return __any_sync(0xffffffffu, p); };
 	run_read_machine(c, sp, have, job, slice, slot, draw_fn, any_fn, consumed, rec_len);
@@ -729,12 +769,13 @@ struct rsq_engine {
 	// speculative two-phase path
 	uint32_t max_n0_reads = 0;             // largest candidate count of the tables FillRead draws from
 	uint32_t max_name_len = 0;
-	DevBuf<SpecBlock> d_spec_blocks; DevBuf<SpecSnap> d_spec_snaps; DevBuf<ReadJob> d_spec_jobs; DevBuf<uint32_t> d_spec_corr;
+	DevBuf<SpecBlock> d_spec_blocks; DevBuf<SpecSnap> d_spec_snaps; DevBuf<ReadJob> d_spec_jobs;
 	DevBuf<uint64_t> d_spec_words; DevBuf<unsigned char> d_spec_slots; DevBuf<uint32_t> d_slab_next, d_slab_count, d_spec_counters;
 	PinnedBuf h_spec_counters;
 	uint32_t spec_rounds = 0, spec_depth = 0;
+	std::vector<cudaStream_t> spec_streams; std::vector<cudaEvent_t> spec_events;
 
-	~rsq_engine(){ if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
+	~rsq_engine(){ for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
 };
 
 namespace rsq {
@@ -1342,25 +1383,63 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 	sp.adapter_only_seed = e.adapter_only_seed;
 	const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);   // ReadLengths().to(): one past the longest read
 	sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
-	// depth: enough reads in flight to fill the machine, as few as possible beyond that (every read behind a wrong assumption is redone)
-	uint32_t depth = 2;
-	const uint64_t capacity = static_cast<uint64_t>(dev_sms) * 16 * 32;
-	while(depth < 32 && static_cast<uint64_t>(sp.n_units) * depth * 2 <= capacity){ depth *= 2; }
-	if(const char *env = getenv("RSQ_SPEC_DEPTH")){ depth = std::min(32, std::max(1, atoi(env))); }
-	sp.depth = depth; e.spec_depth = depth;
+	// Depth (reads speculated per unit and round) and reads per warp are chosen per batch of rounds from a cost model:
+	//   a round costs max(latency, throughput) with latency ~ 1.0 ms + 0.12 ms per read of depth (one lock-step pass over a read
+	//   + the scan in front of `depth` reads) and throughput ~ 5e-5 ms per read in flight on a B200;
+	//   it verifies (1 - p^d) / (1 - p) reads per unit, p = measured share of reads whose assumption held.
+	// Small runs are latency bound (deep speculation, few reads per warp), large ones throughput bound (shallow, 32 reads per warp).
+	const uint64_t warps_cap = static_cast<uint64_t>(dev_sms) * 16;
+	const int fixed_depth = getenv("RSQ_SPEC_DEPTH") ? std::min(32, std::max(1, atoi(getenv("RSQ_SPEC_DEPTH")))) : 0;
+	const int fixed_lanes = getenv("RSQ_SPEC_LANES") ? atoi(getenv("RSQ_SPEC_LANES")) : 0;
+	uint32_t depth = 32;   // capacity per unit (array stride)
+	if(static_cast<uint64_t>(sp.n_units) * 32 > 64 * warps_cap * 32){ depth = 8; }   // very large runs never speculate deep: keep the buffers small
+	if(fixed_depth){ depth = fixed_depth; }
+	if(const char *env = getenv("RSQ_SPEC_MAX_DEPTH")){ depth = std::max<uint32_t>(fixed_depth, std::min(32, std::max(1, atoi(env)))); }
+	sp.depth = depth;
+	const double draws_per_read = static_cast<double>(e.total_size) * (c.insert_to - c.insert_from) / (2.0 * std::max<uint64_t>(1, e.total_pairs));
+	const double budget_factor = getenv("RSQ_SPEC_BUDGET") ? atof(getenv("RSQ_SPEC_BUDGET")) : 1.5;
+	uint32_t lanes = 32;
+	auto choose = [&](uint64_t active, double p_hold){
+		uint32_t best_d = 2; double best = -1.0;
+		static const uint32_t cand[] = {2, 3, 4, 6, 8, 12, 16, 24, 32};
+		for(uint32_t d : cand){
+			if(d > depth){ break; }
+			const double prog = p_hold >= 0.9999 ? d : (1.0 - std::pow(p_hold, static_cast<double>(d))) / (1.0 - p_hold);
+			const double cost = std::max(1.0 + 0.12 * d, 5.0e-5 * static_cast<double>(active) * d);
+			if(prog / cost > best){ best = prog / cost; best_d = d; }
+		}
+		if(fixed_depth){ best_d = fixed_depth; }
+		sp.run_depth = best_d;
+		const double budget = budget_factor * best_d * draws_per_read + 4096.0;
+		sp.scan_budget = budget > 4.0e9 ? 4000000000u : static_cast<uint32_t>(budget);
+		// reads per warp: as few as keep all reads of the round resident at once
+		const uint64_t reads = active * best_d;
+		lanes = reads <= warps_cap * 8 ? 8 : (reads <= warps_cap * 16 * 2 ? 16 : 32);
+		if(fixed_lanes){ lanes = fixed_lanes >= 32 ? 32 : (fixed_lanes >= 16 ? 16 : 8); }
+	};
+	choose(sp.n_units, 0.95);
+	e.spec_depth = sp.run_depth;
 	const size_t n_jobs = static_cast<size_t>(sp.n_units) * depth;
 	const size_t n_tiles = (n_jobs + 31) / 32;
-	e.d_spec_blocks.alloc(sp.n_units); e.d_spec_snaps.alloc(2 * static_cast<size_t>(sp.n_units)); e.d_spec_jobs.alloc(n_tiles * 32); e.d_spec_corr.alloc(n_jobs);
+	e.d_spec_blocks.alloc(sp.n_units); e.d_spec_snaps.alloc(2 * static_cast<size_t>(sp.n_units) * (depth + 1)); e.d_spec_jobs.alloc(n_tiles * 32);
 	e.d_spec_words.alloc(n_tiles * sp.words_per_job * 32);
-	sp.blocks = e.d_spec_blocks.p; sp.snaps = e.d_spec_snaps.p; sp.jobs = e.d_spec_jobs.p; sp.corr = e.d_spec_corr.p; sp.words = e.d_spec_words.p;
+	sp.blocks = e.d_spec_blocks.p; sp.snaps = e.d_spec_snaps.p; sp.jobs = e.d_spec_jobs.p; sp.words = e.d_spec_words.p;
 	const uint32_t id_prefix = c.base_id_len + 10 + 1 + 20 + 1 + 10 + 1 + std::max<uint32_t>(e.max_name_len, 7) + 1 + 10 + 1 + 5 + 11;
 	sp.id_cap = std::min<uint32_t>(kIdCap, (id_prefix + kCigarCap + 2 + 10 + 15) & ~15u);
 	sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
-	e.d_spec_counters.alloc(4); e.h_spec_counters.ensure(4 * sizeof(uint32_t));
-	sp.next_slab = e.d_spec_counters.p; sp.n_active = e.d_spec_counters.p + 1;
+	e.d_spec_counters.alloc(8); e.h_spec_counters.ensure(8 * sizeof(uint32_t));
+	sp.next_slab = e.d_spec_counters.p; sp.n_done = e.d_spec_counters.p + 1; sp.stat = reinterpret_cast<unsigned long long *>(e.d_spec_counters.p + 2);
+	// units are split into independent groups on their own streams: the scan of one group overlaps the reads of another
+	uint32_t n_groups = 2;
+	if(const char *env = getenv("RSQ_SPEC_GROUPS")){ n_groups = std::min(4, std::max(1, atoi(env))); }
+	n_groups = std::max<uint32_t>(1, std::min<uint32_t>(n_groups, sp.n_units));
+	while(e.spec_streams.size() < n_groups){
+		cudaStream_t st; RSQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); e.spec_streams.push_back(st);
+		cudaEvent_t ev; RSQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e.spec_events.push_back(ev);
+	}
 	const uint32_t stride = ((e.max_n0_reads + 3u) & ~3u) + 1u;
-	const size_t shmem_reads = static_cast<size_t>(kSpecReadWarps) * 32 * stride * sizeof(double);
-	RSQ_CUDA(cudaFuncSetAttribute(k_spec_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem_reads)));
+	const size_t shmem_reads_max = static_cast<size_t>(kSpecReadWarps) * 32 * stride * sizeof(double);
+	RSQ_CUDA(cudaFuncSetAttribute(k_spec_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem_reads_max)));
 	const double share = e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0;
 	uint64_t expected_reads = static_cast<uint64_t>(2.0 * (e.total_pairs * share + sp.adapter_only_pairs) * 1.15) + 2048;
 	float ms_sim = 0;
@@ -1371,20 +1450,62 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 		e.d_slab_next.alloc(sp.n_slabs); e.d_slab_count.alloc(sp.n_slabs);
 		sp.slots = e.d_spec_slots.p; sp.slab_next = e.d_slab_next.p; sp.slab_count = e.d_slab_count.p;
 		e.d_spec_counters.zero(s);
+		choose(sp.n_units, 0.95);
 		EventTimer tm(s);
 		tm.start();
 		rounds = 0;
 		if(sp.n_units){
 			k_spec_init<<<(sp.n_units + 127) / 128, 128, 0, s>>>(c, sp, e.d_blocks.p, e.shard_first); ++e.launches;
-			volatile uint32_t *h_active = reinterpret_cast<volatile uint32_t *>(e.h_spec_counters.p);
+			RSQ_CUDA(cudaEventRecord(e.ev_fork, s));
+			for(uint32_t gi = 0; gi < n_groups; ++gi){ RSQ_CUDA(cudaStreamWaitEvent(e.spec_streams[gi], e.ev_fork, 0)); }
+			volatile uint32_t *h_done = reinterpret_cast<volatile uint32_t *>(e.h_spec_counters.p) + 1;
+			volatile unsigned long long *h_stat = reinterpret_cast<volatile unsigned long long *>(e.h_spec_counters.p + 8);
+			unsigned long long last_emitted = 0, last_verified = 0;
+			uint32_t rounds_per_poll = 2;   // the first poll comes early: it measures how often the consumption assumption holds
 			while(true){
-				RSQ_CUDA(cudaMemsetAsync(sp.n_active, 0, sizeof(uint32_t), s));
-				k_spec_scan<<<(sp.n_units + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, s>>>(c, sp, e.d_blocks.p, e.shard_first); ++e.launches;
-				RSQ_CUDA(cudaMemcpyAsync(e.h_spec_counters.p, sp.n_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-				k_spec_reads<<<static_cast<unsigned>((n_tiles + kSpecReadWarps - 1) / kSpecReadWarps), kSpecReadWarps * 32, shmem_reads, s>>>(c, sp, stride); ++e.launches;
+				for(uint32_t r = 0; r < rounds_per_poll; ++r){
+					for(uint32_t gi = 0; gi < n_groups; ++gi){
+						const uint32_t u0 = static_cast<uint64_t>(sp.n_units) * gi / n_groups, u1 = static_cast<uint64_t>(sp.n_units) * (gi + 1) / n_groups;
+						if(u1 == u0){ continue; }
+						cudaStream_t gs = e.spec_streams[gi];
+						k_spec_scan<<<(u1 - u0 + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, gs>>>(c, sp, e.d_blocks.p, e.shard_first, u0, u1);
+						const size_t warps = (static_cast<size_t>(u1 - u0) * sp.run_depth + lanes - 1) / lanes;
+						const size_t shmem_reads = static_cast<size_t>(kSpecReadWarps) * lanes * stride * sizeof(double);
+						k_spec_reads<<<static_cast<unsigned>((warps + kSpecReadWarps - 1) / kSpecReadWarps), kSpecReadWarps * 32, shmem_reads, gs>>>(c, sp, stride, lanes, u0, u1);
+						e.launches += 2;
+					}
+				}
+				rounds += rounds_per_poll;
+				rounds_per_poll = 4;
+				// every group has queued its rounds: join, then look at the number of finished units
+				for(uint32_t gi = 0; gi < n_groups; ++gi){
+					RSQ_CUDA(cudaEventRecord(e.spec_events[gi], e.spec_streams[gi]));
+					RSQ_CUDA(cudaStreamWaitEvent(s, e.spec_events[gi], 0));
+				}
+				RSQ_CUDA(cudaMemcpyAsync(e.h_spec_counters.p, e.d_spec_counters.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+				RSQ_CUDA(cudaEventRecord(e.ev_fork, s));
 				RSQ_CUDA(cudaStreamSynchronize(s));
-				if(0 == *h_active){ break; }
-				++rounds;
+				if(*h_done >= sp.n_units){ break; }
+				{
+					const unsigned long long em = h_stat[0], ve = h_stat[1];
+					// share of reads whose assumption held, from the reads behind the first one of each unit and round (that one is always exact)
+					double p_hold = 0.9;
+					if(em > last_emitted){
+						const double frac = static_cast<double>(ve - last_verified) / static_cast<double>(em - last_emitted);   // verified share at the depth just run
+						const double d = sp.run_depth;
+						// invert (1 - p^d) / ((1 - p) d) = frac by bisection
+						double lo = 0.0, hi = 1.0;
+						for(int it = 0; it < 40; ++it){
+							const double mid = 0.5 * (lo + hi);
+							const double f = mid >= 0.9999 ? 1.0 : (1.0 - std::pow(mid, d)) / ((1.0 - mid) * d);
+							if(f < frac){ lo = mid; } else{ hi = mid; }
+						}
+						p_hold = 0.5 * (lo + hi);
+					}
+					last_emitted = em; last_verified = ve;
+					choose(sp.n_units - *h_done, p_hold);
+				}
+				for(uint32_t gi = 0; gi < n_groups; ++gi){ RSQ_CUDA(cudaStreamWaitEvent(e.spec_streams[gi], e.ev_fork, 0)); }
 				if(rounds > 100000000u){ throw std::runtime_error("speculative simulation does not terminate"); }
 			}
 		}

@@ -122,7 +122,9 @@ struct SpecSnap {                  // resumable state of one unit's stream
 	uint64_t mt[kMtN];
 };
 struct SpecBlock {
-	uint32_t done, committed;      // committed: which of the two snapshots is the verified one
+	uint32_t done;
+	uint32_t snap_bank, snap_idx;  // committed snapshot: snaps[unit][bank][idx] ...
+	uint32_t pending_skip;         // ... plus this many stream words (the measured consumption of the read behind it)
 	uint32_t n_jobs;               // reads emitted in the last round (speculative until verified)
 	uint32_t fill;                 // verified records in cur_slab
 	uint32_t cur_slab, next_slab;  // output slabs (32 slots) being filled
@@ -133,18 +135,20 @@ struct SpecBlock {
 };
 
 struct SpecCtx {
-	uint32_t depth;                // D: reads emitted per unit and round beyond the verified ones (<= 32)
+	uint32_t depth;                // D: capacity per unit and round (reads emitted beyond the verified ones, <= 32); array stride
+	uint32_t run_depth;            // reads to emit per unit in this round (<= depth): grows when few units are left
+	uint32_t scan_budget;          // scan draws per unit and round after which the round ends even with < run_depth reads (bounds stragglers)
 	uint32_t words_per_job;        // K: capacity of a read's stream slice
 	uint32_t n_units;              // blocks (+ the adapter-only pseudo block) of this batch
 	SpecBlock *blocks;             // [n_units]
-	SpecSnap *snaps;               // [2 * n_units]
+	SpecSnap *snaps;               // [n_units][2 banks][D + 1]: in front of every emitted read + behind the last one
 	ReadJob *jobs;                 // [n_units * D]
-	uint32_t *corr;                // [n_units * D] measured consumptions of the verified prefix
 	uint64_t *words;               // [ceil(n_units * D / 32)][K][32] tempered stream words, lane-interleaved per tile of 32 reads
 	// output slots, handed out in slabs of 32
 	unsigned char *slots; uint32_t slot_stride, id_cap, seq_off, qual_off;
 	uint32_t n_slabs; uint32_t *next_slab; uint32_t *slab_next; uint32_t *slab_count;
-	uint32_t *n_active;            // units that still have work after this round
+	uint32_t *n_done;              // units that are through (monotonic; the host polls it between batches of rounds)
+	unsigned long long *stat;      // [0] reads emitted, [1] reads verified (the host tunes the depth with their ratio)
 	// adapter-only pseudo block (Simulator::SimulateAdapterOnlyPairs), unit index n_blocks when present
 	uint32_t n_blocks; uint32_t adapter_only_pairs; uint64_t adapter_only_seed;
 };
@@ -156,6 +160,14 @@ RSQ_HD uint32_t spec_alloc_slab(const SpecCtx &sp){
 	const uint32_t t = (*sp.next_slab)++;
 #endif
 	return t < sp.n_slabs ? t : kSpecNone;
+}
+RSQ_HD void spec_unit_done(const SpecCtx &sp, uint32_t *done_field){   // one lane
+	*done_field = 1;
+#if defined(__CUDA_ARCH__)
+	atomicAdd(sp.n_done, 1u);
+#else
+	*sp.n_done += 1;
+#endif
 }
 RSQ_HD void spec_flag(const SimCtx &c, uint32_t f){
 #if defined(__CUDA_ARCH__)
@@ -297,40 +309,47 @@ RSQ_HD void spec_link_slab(const SpecCtx &sp, SpecBlock &blk, uint32_t slab, uin
 
 // One round of one unit (SimBlock, or the adapter-only pseudo block):
 //   1. verify the reads phase B just ran: the prefix up to and including the first read whose consumption differs
-//      from the assumption is final; commit its records,
-//   2. bring the stream to the state behind that prefix (the tentative snapshot if everything held, else a replay of
-//      the prefix with the measured consumptions) and make it the committed snapshot,
-//   3. scan on and emit up to `depth` new reads; leave a tentative snapshot behind them.
+//      from the assumption is final (its own start was exact); commit its records,
+//   2. restore the stream behind that prefix: the tentative end snapshot if every assumption held, else the snapshot
+//      taken in front of the deviating read plus its measured consumption,
+//   3. scan on and emit up to `depth` new reads, leaving a snapshot in front of each and one behind the last.
+// Snapshots live in two banks of depth + 1 entries per unit; a round reads the committed one from one bank and writes the other.
 template<class G>
 RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t u, uint64_t *ring_mem){
 	SpecBlock &blk = sp.blocks[u];
 	if(blk.done){ return; }
 	const uint32_t D = sp.depth;
 	ReadJob *jobs = sp.jobs + static_cast<size_t>(u) * D;
-	uint32_t *corr = sp.corr + static_cast<size_t>(u) * D;
+	SpecSnap *unit_snaps = sp.snaps + static_cast<size_t>(u) * 2u * (D + 1u);
 	const uint32_t n_prev = blk.n_jobs;
-	uint32_t committed = blk.committed, fill = blk.fill, cur_slab = blk.cur_slab, next_slab = blk.next_slab;
-	uint32_t v = 0;            // verified reads of the previous round
-	bool all_ok = true;
+	uint32_t bank = blk.snap_bank, idx = blk.snap_idx, pending_skip = blk.pending_skip;
+	uint32_t fill = blk.fill, cur_slab = blk.cur_slab, next_slab = blk.next_slab;
 	g.sync();
 	if(n_prev){
-		uint32_t first_bad = kSpecNone;
+		uint32_t first_bad = kSpecNone, bad_consumed = 0;
 		for(uint32_t base = 0; base < n_prev && first_bad == kSpecNone; base += G::kSize){
 			const uint32_t j = base + g.lane();
 			bool bad = false;
+			uint32_t cons = 0;
 			if(j < n_prev){
-				const uint32_t cons = jobs[j].consumed;
-				corr[j] = cons;
+				cons = jobs[j].consumed;
 				bad = cons != jobs[j].assumed;
 			}
 			const unsigned mask = g.ballot(bad);
-			if(mask){ first_bad = base + first_lane(g, mask); }
+			if(mask){
+				const uint32_t fl = first_lane(g, mask);
+				first_bad = base + fl;
+#if defined(__CUDA_ARCH__)
+				bad_consumed = __shfl_sync(0xffffffffu, cons, fl);
+#else
+				bad_consumed = cons;
+#endif
+			}
 		}
-		g.sync();
-		all_ok = first_bad == kSpecNone;
-		v = all_ok ? n_prev : first_bad + 1u;
-		if(!all_ok && corr[first_bad] == kSpecOverflow){
-			if(g.lane() == 0){ spec_flag(c, kErrSpecOverflow); blk.done = 1; }
+		const bool all_ok = first_bad == kSpecNone;
+		const uint32_t v = all_ok ? n_prev : first_bad + 1u;
+		if(!all_ok && bad_consumed == kSpecOverflow){
+			if(g.lane() == 0){ spec_flag(c, kErrSpecOverflow); spec_unit_done(sp, &blk.done); }
 			return;
 		}
 		// commit the records of the verified prefix: slots fill .. fill + v - 1
@@ -341,14 +360,22 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		b0 = g.reduce_add(b0); b1 = g.reduce_add(b1);
 		fill += v;
 		if(g.lane() == 0){
+#if defined(__CUDA_ARCH__)
+			atomicAdd(sp.stat, static_cast<unsigned long long>(n_prev)); atomicAdd(sp.stat + 1, static_cast<unsigned long long>(v));
+#else
+			sp.stat[0] += n_prev; sp.stat[1] += v;
+#endif
 			blk.bytes[0] += b0; blk.bytes[1] += b1; blk.reads += v;
 			if(fill >= 32u){ spec_link_slab(sp, blk, cur_slab, 32u); }
 		}
 		if(fill >= 32u){ cur_slab = next_slab; next_slab = kSpecNone; fill -= 32u; }
-		if(all_ok){ committed ^= 1u; }
+		bank ^= 1u;   // the snapshots of the previous round are in the other bank
+		if(all_ok){ idx = D; pending_skip = 0; }
+		else{ idx = first_bad; pending_skip = bad_consumed; }
 	}
-	// ---- restore the committed snapshot ----
-	const SpecSnap &snap = sp.snaps[2 * static_cast<size_t>(u) + committed];
+	// ---- restore the committed state ----
+	const SpecSnap &snap = unit_snaps[bank * (D + 1u) + idx];
+	SpecSnap *out_snaps = unit_snaps + (bank ^ 1u) * (D + 1u);
 	MtRing ring; ring.w = ring_mem;
 	g.sync();
 	for(uint32_t i = g.lane(); i < static_cast<uint32_t>(kMtN); i += G::kSize){ ring.w[i] = snap.mt[i]; }
@@ -359,15 +386,18 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	uint64_t read_number = snap.read_number, draws = snap.scan_draws;
 	bool finished = snap.finished != 0;
 	g.sync();
-	const uint32_t replay = all_ok ? 0u : v;   // reads to walk over again with their measured consumption
-	if(finished && !replay){
+	if(pending_skip){
+		// the snapshot stands in front of the read whose assumption failed: walk over it with its measured consumption
+		ring_skip(g, ring, pending_skip);
+		++hit.pair_stage;
+	}
+	if(finished){
 		if(g.lane() == 0){
 			if(fill){ spec_link_slab(sp, blk, cur_slab, fill); }
-			blk.scan_draws = draws; blk.committed = committed; blk.n_jobs = 0; blk.fill = 0; blk.done = 1;
+			blk.scan_draws = draws; blk.n_jobs = 0; blk.fill = 0; spec_unit_done(sp, &blk.done);
 		}
 		return;
 	}
-	finished = false;
 	const bool adapter_only = u >= sp.n_blocks;
 	BlockDesc b{};
 	if(!adapter_only){ b = descs[first_desc + u]; }
@@ -378,25 +408,27 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	const uint64_t *thr_int = c.thr_int + static_cast<size_t>(group) * c.insert_to;
 	const double *binom_p0 = c.binom_p0 + static_cast<size_t>(group) * c.insert_to;
 	const uint32_t *gcp = c.gc_prefix + off + b.ref_id;
+	const uint32_t insert_from = c.insert_from, insert_to = c.insert_to;
 	uint32_t end = b.start_pos + 1000u;
 	if(end > L){ end = L; }
-	uint32_t jw = 0;           // reads walked: the first `replay` are known, the rest are new
 	uint32_t emitted = 0;
 	bool full = false, failed = false;
-	while(!finished && !full){
-		if(hit.active && hit.in_reads){
-			while(hit.counts_left && !full && !failed){
-				if(hit.pair_stage == 0u){
-					if(jw >= replay && emitted >= D){ full = true; break; }
-					++read_number;
-					hit.tile = 0;
-					if(1 < c.num_tiles){ hit.tile = discrete_lookup(c.tile_pick, canonical(ring_next(g, ring))); }
-				}
-				while(hit.pair_stage < 2u){
-					const uint32_t seg = 1u - hit.pair_stage;
-					if(jw < replay){ ring_skip(g, ring, corr[jw]); }
-					else{
-						if(emitted >= D){ full = true; break; }
+	const uint64_t draws_limit = draws + sp.scan_budget;
+	const uint32_t D_run = sp.run_depth < D ? sp.run_depth : D;
+	while(!finished && !full && !failed){
+		if(hit.active){
+			if(hit.in_reads){
+				// CreateReads: counts_left pairs of (second read, first read)
+				while(hit.counts_left && !full && !failed){
+					if(hit.pair_stage == 0u){
+						if(emitted >= D_run){ full = true; break; }
+						++read_number;
+						hit.tile = 0;
+						if(1 < c.num_tiles){ hit.tile = discrete_lookup(c.tile_pick, canonical(ring_next(g, ring))); }
+					}
+					while(hit.pair_stage < 2u){
+						if(emitted >= D_run){ full = true; break; }
+						const uint32_t seg = 1u - hit.pair_stage;
 						const uint32_t p = fill + emitted;
 						uint32_t slab = p < 32u ? cur_slab : next_slab;
 						if(slab == kSpecNone){
@@ -407,6 +439,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 							if(slab == kSpecNone){ failed = true; break; }
 							if(p < 32u){ cur_slab = slab; } else{ next_slab = slab; }
 						}
+						save_snapshot(g, ring, out_snaps[emitted], pos, len, false, hit, cur_meth, read_number, draws);
 						const size_t gidx = static_cast<size_t>(u) * D + emitted;
 						uint64_t *dst = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
 						const uint32_t assumed = plan_read(g, c, ring, dst, sp.words_per_job, seg, hit.fragment_length);
@@ -417,23 +450,15 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 							j.read_number = read_number; j.assumed = assumed; j.consumed = kSpecOverflow; j.rec_len = 0; j.slot = slab * 32u + (p & 31u);
 							jobs[emitted] = j;
 						}
-						++emitted;
+						++emitted; ++hit.pair_stage;
 					}
-					++jw; ++hit.pair_stage;
-					if(replay && jw == replay){
-						// the stream now stands right behind the verified prefix: this is the new committed state
-						committed ^= 1u;
-						save_snapshot(g, ring, sp.snaps[2 * static_cast<size_t>(u) + committed], pos, len, false, hit, cur_meth, read_number, draws);
-					}
+					if(full || failed){ break; }
+					hit.pair_stage = 0; --hit.counts_left;
 				}
 				if(full || failed){ break; }
-				hit.pair_stage = 0; --hit.counts_left;
+				hit.in_reads = 0; ++hit.ci;
+				if(adapter_only){ finished = true; break; }
 			}
-			if(full || failed){ break; }
-			hit.in_reads = 0; ++hit.ci;
-			if(adapter_only){ finished = true; break; }
-		}
-		if(hit.active){
 			if(hit.ci < hit.n_chosen){
 				const uint32_t strand = (hit.ci ? hit.chosen1 : hit.chosen0) & 1u;
 				const uint32_t fl = hit.fragment_length;
@@ -453,32 +478,44 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 			}
 			hit.active = 0;
 		}
-		// ---- scanning ----
-		if(len >= c.insert_to){
-			++pos; len = c.insert_from;
-			if(pos >= end){ finished = true; break; }
-			continue;
+		// ---- scan until the next candidate hit (tight loop: 32 (position, length) draws per trip) ----
+		uint32_t fragment_length = 0;
+		uint64_t x_hit = 0;
+		bool found = false;
+		while(true){
+			if(len >= insert_to){
+				++pos; len = insert_from;
+				if(pos >= end){ finished = true; break; }
+			}
+			ring_ensure(g, ring, G::kSize);
+			uint32_t n = insert_to - len;
+			if(n > static_cast<uint32_t>(G::kSize)){ n = G::kSize; }
+			const uint32_t lane = g.lane();
+			uint64_t x = 0;
+			bool is_hit = false;
+			if(lane < n){
+				x = mt_temper(ring_raw(ring, lane));
+				is_hit = x >= thr_int[len + lane];
+			}
+			const unsigned mask = g.ballot(is_hit);
+			if(mask == 0){
+				ring_advance(ring, n); len += n; draws += n;
+				if(draws >= draws_limit){ full = true; break; }
+				continue;
+			}
+			const uint32_t first = first_lane(g, mask);
+			fragment_length = len + first;
+#if defined(__CUDA_ARCH__)
+			x_hit = __shfl_sync(0xffffffffu, x, first);
+#else
+			x_hit = x;
+#endif
+			ring_advance(ring, first + 1u); len = fragment_length + 1u; draws += first + 1u;
+			found = true;
+			break;
 		}
-		ring_ensure(g, ring, G::kSize);
-		uint32_t n = c.insert_to - len;
-		if(n > static_cast<uint32_t>(G::kSize)){ n = G::kSize; }
-		const uint32_t lane = g.lane();
-		uint64_t x = 0;
-		bool is_hit = false;
-		if(lane < n){
-			x = mt_temper(ring_raw(ring, lane));
-			is_hit = x >= thr_int[len + lane];
-		}
-		const unsigned mask = g.ballot(is_hit);
-		if(mask == 0){
-			ring_advance(ring, n); len += n; draws += n;
-			continue;
-		}
-		const uint32_t first = first_lane(g, mask);
-		const uint32_t fragment_length = len + first;
-		x = mt_temper(ring_raw(ring, first));
-		ring_advance(ring, first + 1u); len = fragment_length + 1u; draws += first + 1u;
-		const double probability_chosen = canonical(x);
+		if(!found){ break; }
+		const double probability_chosen = canonical(x_hit);
 		const double thr0 = thr[2 * fragment_length], thr1 = thr[2 * fragment_length + 1];
 		if(!(probability_chosen >= thr1)){ continue; }
 		const uint32_t non_zero_strands = binomial_count(2, sub_rn(1.0, thr0), binom_p0[fragment_length], probability_chosen);
@@ -493,24 +530,24 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		}
 	}
 	if(failed){
-		if(g.lane() == 0){ spec_flag(c, kErrArenaFull); blk.done = 1; }
+		if(g.lane() == 0){ spec_flag(c, kErrArenaFull); spec_unit_done(sp, &blk.done); }
 		return;
 	}
 	// ---- tentative snapshot behind the new reads ----
-	save_snapshot(g, ring, sp.snaps[2 * static_cast<size_t>(u) + (committed ^ 1u)], pos, len, finished, hit, cur_meth, read_number, draws);
+	save_snapshot(g, ring, out_snaps[D], pos, len, finished, hit, cur_meth, read_number, draws);
 	if(g.lane() == 0){
-		blk.committed = committed; blk.n_jobs = emitted; blk.fill = fill; blk.cur_slab = cur_slab; blk.next_slab = next_slab; blk.rounds += 1;
-		if(0 == emitted){
-			// nothing left to verify: the tentative snapshot is exact
+		blk.snap_bank = bank; blk.snap_idx = idx; blk.pending_skip = pending_skip;
+		blk.n_jobs = emitted; blk.fill = fill; blk.cur_slab = cur_slab; blk.next_slab = next_slab; blk.rounds += 1;
+		if(0 == emitted && finished){
+			// nothing left to verify: the state behind the last verified read is exact and the unit is through
 			if(fill){ spec_link_slab(sp, blk, cur_slab, fill); }
-			blk.scan_draws = draws; blk.fill = 0; blk.done = 1;
+			blk.scan_draws = draws; blk.fill = 0; spec_unit_done(sp, &blk.done);
 		}
 		else{
-#if defined(__CUDA_ARCH__)
-			atomicAdd(sp.n_active, 1u);
-#else
-			*sp.n_active += 1;
-#endif
+			if(0 == emitted){
+				// scan budget used up without a read: the end snapshot has nothing unverified in front of it, so it is the committed one
+				blk.snap_bank = bank ^ 1u; blk.snap_idx = D; blk.pending_skip = 0;
+			}
 		}
 	}
 }
@@ -519,10 +556,10 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 // inside CreateReads with all its pairs left).
 RSQ_HD void spec_init_unit(const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t u){
 	SpecBlock &blk = sp.blocks[u];
-	blk.done = 0; blk.committed = 0; blk.n_jobs = 0; blk.fill = 0; blk.cur_slab = kSpecNone; blk.next_slab = kSpecNone;
+	blk.done = 0; blk.snap_bank = 0; blk.snap_idx = 0; blk.pending_skip = 0; blk.n_jobs = 0; blk.fill = 0; blk.cur_slab = kSpecNone; blk.next_slab = kSpecNone;
 	blk.chain_head = kSpecNone; blk.chain_tail = kSpecNone;
 	blk.reads = 0; blk.rounds = 0; blk.bytes[0] = 0; blk.bytes[1] = 0; blk.scan_draws = 0;
-	SpecSnap &s = sp.snaps[2 * static_cast<size_t>(u)];
+	SpecSnap &s = sp.snaps[static_cast<size_t>(u) * 2u * (sp.depth + 1u)];
 	const bool adapter_only = u >= sp.n_blocks;
 	uint64_t x = adapter_only ? sp.adapter_only_seed : descs[first_desc + u].seed;
 	s.mt[0] = x;
@@ -533,12 +570,12 @@ RSQ_HD void spec_init_unit(const SimCtx &c, const SpecCtx &sp, const BlockDesc *
 	if(adapter_only){
 		s.pos = 0; s.len = 0;
 		h.active = 1; h.in_reads = 1; h.fragment_length = 0; h.n_chosen = 1; h.counts_left = sp.adapter_only_pairs;
-		if(0 == sp.adapter_only_pairs){ blk.done = 1; }
+		if(0 == sp.adapter_only_pairs){ spec_unit_done(sp, &blk.done); }
 	}
 	else{
 		s.pos = descs[first_desc + u].start_pos; s.len = c.insert_from;
 		const uint32_t L = c.seq_len[descs[first_desc + u].ref_id];
-		if(s.pos >= L){ blk.done = 1; }
+		if(s.pos >= L){ spec_unit_done(sp, &blk.done); }
 	}
 	s.hit = h;
 }
@@ -551,6 +588,7 @@ enum : uint32_t { kPhFrag = 0, kPhAdapter = 1, kPhTail = 2, kPhOverrun = 3, kPhD
 struct ReadMachine {
 	// stream slice
 	const uint64_t *words; uint32_t k, kcap; uint32_t overflow;
+	uint64_t w0, w1, w2, w3;   // words k .. k+3, loaded ahead of their use (the slice streams from HBM/L2 exactly once)
 	// output
 	uint8_t *seq_out, *qual_out; char *id; int id_len, id_cap, cigar_len;
 	// job
@@ -566,9 +604,17 @@ struct ReadMachine {
 	// per step
 	uint32_t ref_base, dom_error, indel;
 
+	RSQ_HD void load_window(){
+		w0 = words[static_cast<size_t>(k) * 32u]; w1 = words[static_cast<size_t>(k + 1u) * 32u];
+		w2 = words[static_cast<size_t>(k + 2u) * 32u]; w3 = words[static_cast<size_t>(k + 3u) * 32u];
+	}
 	RSQ_HD double next_u(){
 		if(k >= kcap){ overflow = 1; return 0.5; }
-		return canonical(words[static_cast<size_t>(k++) * 32u]);
+		const uint64_t x = w0;
+		w0 = w1; w1 = w2; w2 = w3;
+		w3 = (k + 4u < kcap) ? words[static_cast<size_t>(k + 4u) * 32u] : 0ull;
+		++k;
+		return canonical(x);
 	}
 	RSQ_HD uint32_t org_base(uint32_t p) const {
 		const uint32_t b = org[static_cast<int64_t>(org_step) * static_cast<int64_t>(p)];
@@ -599,7 +645,9 @@ struct ReadMachine {
 
 	// FillRead up to the sequence-quality draw; returns the mean systematic error rate (its second index)
 	RSQ_HD uint32_t begin(const SimCtx &c, const SpecCtx &sp, const ReadJob &j, const uint64_t *slice, unsigned char *slot){
-		words = slice; k = 0; kcap = sp.words_per_job; overflow = 0;
+		// only assumed + margin words of the slice were written by the scan
+		words = slice; k = 0; kcap = j.assumed + kSpecMargin < sp.words_per_job ? j.assumed + kSpecMargin : sp.words_per_job; overflow = 0;
+		load_window();
 		seg = j.flags & 1u; tile = j.flags >> 8; fragment_length = j.fragment_length;
 		const bool strand = (j.flags >> 1) & 1u;
 		id = reinterpret_cast<char *>(slot + 16); id_cap = static_cast<int>(sp.id_cap); cigar_len = 0;

@@ -9,6 +9,8 @@ Run in the build container (needs /root/reference for the TruSeq adapter files a
                                         by deterministic non-trivial values (dump_tables patch)
   profile150.flat.xz                    what the reference holds in memory after Load + PrepareProcessing +
                                         Estimate + PrepareResult for that profile (dump_tables profile)
+  profile150r.{reseq,reseq.ipf,flat}.xz same pipeline with a realistic InDel rate in the synthetic SAM (2e-5 per base for insertions and
+                                        for deletions instead of 8e-4): the bench profile; profile150 stays the InDel stress profile
   simref_small.fa                       small multi-contig reference with N runs and one too-short contig
   sim_small_seed42_R{1,2}.fq.xz         `reseq illuminaPE -j 1 --seed 42 -c 20` on simref_small.fa
   simref_small_meth.bed, sim_small_meth_seed42_R{1,2}.fq.xz   same run with `--methylation` (bisulfite C->T conversions)
@@ -81,6 +83,22 @@ def main():
     xz(prof, os.path.join(HERE, "profile150.reseq.xz"))
     xz(prof + ".ipf", os.path.join(HERE, "profile150.reseq.ipf.xz"))
     xz(flat, os.path.join(HERE, "profile150.flat.xz"))
+
+    # bench profile: same pipeline, realistic InDel rate
+    sam_r = os.path.join(tmp, "prof_r.sam")
+    run([py, SYN, "sam", ref, sam_r, "--pairs", "20000", "--seed", "11", "--indel-rate", "0.00002"])
+    raw_r = os.path.join(tmp, "raw_r.reseq")
+    run([ORACLE, "illuminaPE", "-j", "8", "-b", sam_r, "-r", ref, "--adapterFile", ADAPTERS + ".fa", "--adapterMatrix", ADAPTERS + ".mat",
+         "--statsOnly", "-S", raw_r])
+    log = run([ORACLE, "illuminaPE", "-j", "8", "-s", raw_r, "-r", ref, "--stopAfterEstimation"])
+    if "did not reach precision aim" in log:
+        raise SystemExit("IPF did not converge for every table of the realistic profile")
+    prof_r = os.path.join(tmp, "profile150r.reseq")
+    run([DUMP, "patch", raw_r, prof_r, "5"])
+    shutil.copy(raw_r + ".ipf", prof_r + ".ipf")
+    run([DUMP, "profile", prof_r, os.path.join(tmp, "profile150r.flat")])
+    for name in ("profile150r.reseq", "profile150r.reseq.ipf", "profile150r.flat"):
+        xz(os.path.join(tmp, name), os.path.join(HERE, name + ".xz"))
 
     small = os.path.join(HERE, "simref_small.fa")
     run([py, SYN, "reference", small, "--sizes", "30000,22000,800,15000", "--seed", "21", "--n-rate", "0.004", "--prefix", "chr"])

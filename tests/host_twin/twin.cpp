@@ -290,6 +290,8 @@ int main(int argc, char **argv){
 		// two-phase speculative form (spec_core.cuh) with one-lane groups: rounds of scan_window + ReadMachine
 		SpecCtx sp{};
 		sp.depth = std::max(1, atoi(spec_env));
+		sp.run_depth = sp.depth;
+		sp.scan_budget = getenv("RSQ_TWIN_BUDGET") ? atoi(getenv("RSQ_TWIN_BUDGET")) : 4000000000u;
 		const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);
 		sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
 		sp.n_blocks = nsim;
@@ -297,16 +299,16 @@ int main(int argc, char **argv){
 		sp.n_units = nsim + (with_adapter_only ? 1 : 0);
 		sp.adapter_only_pairs = with_adapter_only ? n_adapter_only : 0;
 		sp.adapter_only_seed = with_adapter_only ? master() : 0;
-		std::vector<SpecBlock> sblocks(sp.n_units); std::vector<SpecSnap> snaps(2 * static_cast<size_t>(sp.n_units));
-		std::vector<ReadJob> jobs(static_cast<size_t>(sp.n_units) * sp.depth); std::vector<uint32_t> corr(jobs.size());
+		std::vector<SpecBlock> sblocks(sp.n_units); std::vector<SpecSnap> snaps(2 * static_cast<size_t>(sp.n_units) * (sp.depth + 1));
+		std::vector<ReadJob> jobs(static_cast<size_t>(sp.n_units) * sp.depth);
 		std::vector<uint64_t> words(((jobs.size() + 31) / 32) * sp.words_per_job * 32);
-		sp.blocks = sblocks.data(); sp.snaps = snaps.data(); sp.jobs = jobs.data(); sp.corr = corr.data(); sp.words = words.data();
+		sp.blocks = sblocks.data(); sp.snaps = snaps.data(); sp.jobs = jobs.data(); sp.words = words.data();
 		sp.id_cap = kIdCap; sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
 		sp.n_slabs = sp.n_units * 8 + 64;
 		std::vector<unsigned char> slots(static_cast<size_t>(sp.n_slabs) * 32 * sp.slot_stride);
 		std::vector<uint32_t> slab_next(sp.n_slabs), slab_count(sp.n_slabs);
-		uint32_t next_slab = 0, n_active = 0;
-		sp.slots = slots.data(); sp.next_slab = &next_slab; sp.slab_next = slab_next.data(); sp.slab_count = slab_count.data(); sp.n_active = &n_active;
+		uint32_t next_slab = 0, n_done = 0;
+		sp.slots = slots.data(); sp.next_slab = &next_slab; sp.slab_next = slab_next.data(); sp.slab_count = slab_count.data(); sp.n_done = &n_done; unsigned long long spec_stat[2] = {0, 0}; sp.stat = spec_stat;
 		for(uint32_t u = 0; u < sp.n_units; ++u){ spec_init_unit(c, sp, blocks.data(), 0, u); }
 		std::vector<uint64_t> ring_mem(2 * kMtN);
 		uint32_t rounds = 0; uint64_t jobs_run = 0, jobs_ok = 0;
@@ -316,9 +318,9 @@ int main(int argc, char **argv){
 		};
 		auto any_fn = [](bool p){ return p; };
 		while(true){
-			n_active = 0;
+			if(getenv("RSQ_TWIN_VARY_DEPTH")){ sp.run_depth = 1 + (rounds * 7) % sp.depth; }   // the product grows the depth as units finish
 			for(uint32_t u = 0; u < sp.n_units; ++u){ scan_window(lane, c, sp, blocks.data(), 0, u, ring_mem.data()); }
-			if(!n_active){ break; }
+			if(n_done == sp.n_units){ break; }
 			++rounds;
 			for(uint32_t u = 0; u < sp.n_units; ++u){
 				if(sblocks[u].done){ continue; }

@@ -195,6 +195,22 @@ def test_against_reference_binary(rb, engine, golden, oracle, workdir, seed, cov
     assert r2 == open(o2, "rb").read()
 
 
+@pytest.mark.parametrize("path", ["spec", "serial"])
+def test_realistic_indel_profile_against_reference_binary(rb, golden, oracle, workdir, monkeypatch, path):
+    """profile150r: the bench profile (InDel rate ~5e-5 per base as on real Illumina runs instead of the stress profile's 1.6e-3);
+    here nearly every speculated read verifies, so the deep-window code paths run."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    eng = rb.Engine(rb.Profile.load_flat(golden["flat_r"]), 0)
+    try:
+        ref = rb.Reference.load_fasta(golden["small_ref"])
+        r1, r2, _ = _simulate(eng, ref, seed=5, coverage=25.0)
+    finally:
+        eng.close()
+    o1, o2 = run_oracle_sim(oracle, golden["reseq_r"], golden["small_ref"], 5, 25.0, os.path.join(workdir, "ora_r_" + path))
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+
+
 def test_other_reference_and_prefix_against_reference_binary(rb, engine, golden, oracle, workdir):
     fa = os.path.join(workdir, "other.fa")
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic.py"), "reference", fa, "--sizes", "61000,1001,2500", "--seed", "99",

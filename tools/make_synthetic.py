@@ -80,6 +80,9 @@ def read_fasta(path):
 QUALS = np.array([2, 12, 16, 20, 24, 27, 30, 33, 36, 38, 40])
 
 
+INDEL_RATE = 0.0008   # per base, each of insertion and deletion (gen_sam --indel-rate overrides)
+
+
 def simulate_read(rng, template, read_len, seg):
     """template: the fragment strand this read is sequenced from (string, already oriented), followed by adapter.
     Returns (seq, qual, cigar-ops list of (op,len) relative to template consumption)."""
@@ -100,13 +103,13 @@ def simulate_read(rng, template, read_len, seg):
 
     while len(seq) < read_len and tpos < tl:
         r = rng.random()
-        if r < 0.0008 and 5 < len(seq) < read_len - 5:
+        if r < INDEL_RATE and 5 < len(seq) < read_len - 5:
             # insertion
             seq.append("ACGT"[int(rng.integers(0, 4))])
             qual.append(int(QUALS[max(0, state - 2)]))
             push("I")
             continue
-        if r < 0.0016 and 5 < len(seq) < read_len - 5:
+        if r < 2 * INDEL_RATE and 5 < len(seq) < read_len - 5:
             tpos += 1
             push("D")
             continue
@@ -237,6 +240,7 @@ def main():
     b.add_argument("--pairs", type=int, default=60000)
     b.add_argument("--read-len", type=int, default=150)
     b.add_argument("--seed", type=int, default=11)
+    b.add_argument("--indel-rate", type=float, default=0.0008, help="per-base rate of insertions, and of deletions")
     c = sub.add_parser("fragments")
     c.add_argument("ref")
     c.add_argument("sys")
@@ -248,6 +252,8 @@ def main():
     if args.cmd == "reference":
         write_fasta(args.out, gen_reference([int(x) for x in args.sizes.split(",")], args.seed, args.n_rate), args.prefix)
     elif args.cmd == "sam":
+        global INDEL_RATE
+        INDEL_RATE = args.indel_rate
         gen_sam(args.ref, args.out, args.pairs, args.read_len, args.seed)
     else:
         gen_fragments(args.ref, args.sys, args.out, args.n, args.len, args.seed)
