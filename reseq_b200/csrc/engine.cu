@@ -126,56 +126,76 @@ __global__ void k_gc_prefix(const uint8_t *seq, uint32_t L, const uint32_t *tile
 
 struct BiasParamDev { uint32_t ref_id, fragment_length; double general; };
 
-// One warp per (sequence, sampled fragment length): lanes evaluate 32 consecutive start positions (coalesced
-// loads), the warp then adds the 32 terms in position order - the FP64 sum has to follow the reference's
-// sequential order (Reference::SumBias), only the term evaluation is parallel.
-__global__ void k_sum_bias(const BiasParamDev *params, uint32_t n_params, const uint64_t *seq_off, const uint32_t *seq_len,
-                           const double *sur_start, const double *sur_end, const uint32_t *gc_prefix, const double *gc_bias,
-                           double *sums, double *max_bias){
-	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const uint32_t lane = threadIdx.x & 31;
-	const bool active = i < n_params;
-	const BiasParamDev p = params[active ? i : 0];
+// One CTA per (sequence, sampled fragment length).  The FP64 sum has to follow the reference's sequential order
+// (Reference::SumBias), so one warp adds the terms one after the other - a pure chain of dependent DADDs fed from shared
+// memory - while the other three warps evaluate the terms of the next 384 positions (coalesced loads, several tiles in
+// flight per warp: the chain never waits for HBM/L2 latency).
+constexpr uint32_t kBiasProducers = 3, kBiasTilesPerWarp = 4, kBiasSuper = kBiasProducers * kBiasTilesPerWarp * 32;   // 384 positions
+__global__ void __launch_bounds__(128)
+k_sum_bias(const BiasParamDev *params, uint32_t n_params, const uint64_t *seq_off, const uint32_t *seq_len,
+           const double *sur_start, const double *sur_end, const uint32_t *gc_prefix, const double *gc_bias,
+           double *sums, double *max_bias){
+	__shared__ double s_gc[101];
+	__shared__ __align__(16) double s_terms[2][kBiasSuper];
+	__shared__ double s_max[kBiasProducers];
+	const uint32_t i = blockIdx.x;
+	if(i >= n_params){ return; }
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const BiasParamDev p = params[i];
 	const uint64_t off = seq_off[p.ref_id];
 	const uint32_t L = seq_len[p.ref_id], fl = p.fragment_length;
 	const double *ss = sur_start + off, *se = sur_end + off + fl - 1;
 	const uint32_t *gp = gc_prefix + off + p.ref_id;
-	const uint32_t n_pos = active ? L - fl + 1 : 0;
-	double tot = 0.0, mx = 0.0;
-	// gc_bias lives in shared memory so that a term needs one level of global loads only; the raw operands of the
-	// next two tiles are in flight while the current tile is added up (the add chain is ~400 cycles per tile).
-	__shared__ double s_gc[101];
+	const uint32_t n_pos = L - fl + 1;
 	for(uint32_t k = threadIdx.x; k < 101; k += blockDim.x){ s_gc[k] = gc_bias[k]; }
 	__syncthreads();
-	struct Raw { uint32_t g0, g1; double a, b; };
-	auto fetch = [&](uint32_t pos) -> Raw {
-		Raw r{0, 0, 0.0, 0.0};
-		if(pos < n_pos){ r.g0 = gp[pos]; r.g1 = gp[pos + fl]; r.a = ss[pos]; r.b = se[pos]; }
-		return r;
-	};
-	Raw r1 = fetch(lane), r2 = fetch(32 + lane);
-	for(uint32_t base = 0; base < n_pos; base += 32){
-		const Raw cur = r1;
-		r1 = r2;
-		r2 = fetch(base + 64 + lane);
-		double bias = 0.0;
-		if(base + lane < n_pos){
-			bias = mul_rn(p.general, s_gc[percent_u32(cur.g1 - cur.g0, fl)]);
-			bias = mul_rn(bias, cur.a);
-			bias = mul_rn(bias, cur.b);
-			if(bias > mx){ mx = bias; }
-		}
-		const uint32_t cnt = min(32u, n_pos - base);
-		if(cnt == 32u){
+	double tot = 0.0, mx = 0.0;
+	auto produce = [&](uint32_t super_base, double *dst){   // warps 1..3: 4 tiles each
+		struct Raw { uint32_t g0, g1; double a, b; };
+		Raw r[kBiasTilesPerWarp];
 #pragma unroll
-			for(int k = 0; k < 32; ++k){ tot = add_rn(tot, __shfl_sync(0xffffffffu, bias, k)); }
+		for(uint32_t t = 0; t < kBiasTilesPerWarp; ++t){
+			const uint32_t pos = super_base + ((warp - 1u) * kBiasTilesPerWarp + t) * 32u + lane;
+			r[t] = Raw{0, 0, 0.0, 0.0};
+			if(pos < n_pos){ r[t].g0 = gp[pos]; r[t].g1 = gp[pos + fl]; r[t].a = ss[pos]; r[t].b = se[pos]; }
+		}
+#pragma unroll
+		for(uint32_t t = 0; t < kBiasTilesPerWarp; ++t){
+			const uint32_t slot = ((warp - 1u) * kBiasTilesPerWarp + t) * 32u + lane;
+			double bias = 0.0;   // positions behind the last one add +0.0: exact
+			if(super_base + slot < n_pos){
+				bias = mul_rn(p.general, s_gc[percent_u32(r[t].g1 - r[t].g0, fl)]);
+				bias = mul_rn(bias, r[t].a);
+				bias = mul_rn(bias, r[t].b);
+				if(bias > mx){ mx = bias; }
+			}
+			dst[slot] = bias;
+		}
+	};
+	if(warp){ produce(0, s_terms[0]); }
+	__syncthreads();
+	uint32_t buf = 0;
+	for(uint32_t base = 0; base < n_pos; base += kBiasSuper){
+		if(warp){
+			if(base + kBiasSuper < n_pos){ produce(base + kBiasSuper, s_terms[buf ^ 1u]); }
 		}
 		else{
-			for(uint32_t k = 0; k < cnt; ++k){ tot = add_rn(tot, __shfl_sync(0xffffffffu, bias, k)); }
+			const double2 *t2 = reinterpret_cast<const double2 *>(s_terms[buf]);
+			for(uint32_t k = 0; k < kBiasSuper / 2; k += 16){
+				double2 v[16];
+#pragma unroll
+				for(int q = 0; q < 16; ++q){ v[q] = t2[k + q]; }
+#pragma unroll
+				for(int q = 0; q < 16; ++q){ tot = add_rn(add_rn(tot, v[q].x), v[q].y); }
+			}
 		}
+		__syncthreads();
+		buf ^= 1u;
 	}
 	for(int o = 16; o; o >>= 1){ mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-	if(lane == 0 && active){ sums[i] = tot; max_bias[i] = mx; }
+	if(warp && lane == 0){ s_max[warp - 1u] = mx; }
+	__syncthreads();
+	if(threadIdx.x == 0){ sums[i] = tot; max_bias[i] = fmax(fmax(s_max[0], s_max[1]), s_max[2]); }
 }
 
 // Continuation of the master mt19937_64 (Simulator::block_seed_gen_): state[0..311] is any window of 312
@@ -893,6 +913,17 @@ static std::string describe_flag(uint32_t f){
 // Systematic errors of a set of chains: speculative chunks + exact fix-up passes.
 static void run_sys_chains(rsq_engine &e, const std::vector<SysChain> &chains, const std::vector<std::pair<uint32_t, uint32_t>> &chain_len_known,
                            uint32_t chunk_len, uint32_t warmup, uint32_t &passes){
+	{
+		// a pass lasts as long as one chunk: short chunks for small genomes (enough of them to fill the machine), long ones
+		// (less warm-up overhead) once there are plenty
+		uint64_t total = 0; for(const auto &cl : chain_len_known){ total += cl.first; }
+		int dev_sms = 0; RSQ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e.device));
+		const uint64_t want = total / (static_cast<uint64_t>(dev_sms) * 32) + 1;
+		uint32_t len = 1024; while(len < chunk_len && len < want){ len *= 2; }
+		if(const char *env = getenv("RSQ_SYS_CHUNK")){ len = std::max(256, atoi(env)); }
+		chunk_len = len; warmup = std::min(warmup, std::max<uint32_t>(len / 2, 512));
+		if(const char *env = getenv("RSQ_SYS_WARMUP")){ warmup = atoi(env); }
+	}
 	std::vector<SysChunk> chunks;
 	for(uint32_t ci = 0; ci < chains.size(); ++ci){
 		const uint32_t L = chain_len_known[ci].first;
@@ -1109,7 +1140,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		e.h_bias_results.ensure(2 * params.size() * sizeof(double));
 		RSQ_CUDA(cudaEventRecord(e.ev_fork, s));
 		RSQ_CUDA(cudaStreamWaitEvent(e.stream2, e.ev_fork, 0));
-		k_sum_bias<<<(params.size() + 3) / 4, 128, 0, e.stream2>>>(d_params.p, params.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
+		k_sum_bias<<<params.size(), 128, 0, e.stream2>>>(d_params.p, params.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
 		++e.launches;
 		RSQ_CUDA(cudaMemcpyAsync(e.h_bias_results.p, d_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
 		RSQ_CUDA(cudaMemcpyAsync(e.h_bias_results.p + sums.size() * 8, d_max.p, maxb.size() * 8, cudaMemcpyDeviceToHost, e.stream2));

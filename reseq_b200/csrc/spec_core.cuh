@@ -487,10 +487,26 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 				++pos; len = insert_from;
 				if(pos >= end){ finished = true; break; }
 			}
+			const uint32_t lane = g.lane();
+			if(insert_to - len >= 4u * G::kSize){
+				// four independent trips at once (hits are rare: ~1 in several thousand draws): the loads and the tempering of
+				// the four overlap instead of waiting on each other
+				ring_ensure(g, ring, 4u * G::kSize);
+				bool any_hit = false;
+#pragma unroll
+				for(uint32_t q = 0; q < 4u; ++q){
+					const uint64_t xq = mt_temper(ring_raw(ring, q * G::kSize + lane));
+					any_hit |= xq >= thr_int[len + q * G::kSize + lane];
+				}
+				if(g.ballot(any_hit) == 0){
+					ring_advance(ring, 4u * G::kSize); len += 4u * G::kSize; draws += 4u * G::kSize;
+					if(draws >= draws_limit){ full = true; break; }
+					continue;
+				}
+			}
 			ring_ensure(g, ring, G::kSize);
 			uint32_t n = insert_to - len;
 			if(n > static_cast<uint32_t>(G::kSize)){ n = G::kSize; }
-			const uint32_t lane = g.lane();
 			uint64_t x = 0;
 			bool is_hit = false;
 			if(lane < n){
