@@ -203,11 +203,16 @@ k_sum_bias(const BiasParamDev *params, uint32_t n_params, const uint64_t *seq_of
 // outputs are appended to out.  x[m+312] = x[m+156] ^ twist(x[m], x[m+1]) only looks >= 156 words back, so one
 // CTA advances 156 words per step through a 4 x 156 word ring in shared memory (one barrier per step).
 constexpr int kMasterThreads = 160;
-__global__ void __launch_bounds__(kMasterThreads) k_master_stream(uint64_t *state, uint64_t *out, uint64_t n){
+constexpr int kMasterStateWords = kMtN + 1;
+// CTA b continues the stream from state_in[b] for n words into out + b * n; the state behind them goes to state_out[b] (if given).
+__global__ void __launch_bounds__(kMasterThreads) k_master_stream(const uint64_t *state_in_all, uint64_t *state_out_all, uint64_t *out_all, uint64_t n){
 	__shared__ uint64_t ring[4 * kMtM];
+	const uint64_t *state_in = state_in_all + static_cast<size_t>(blockIdx.x) * kMasterStateWords;
+	uint64_t *state = state_out_all ? state_out_all + static_cast<size_t>(blockIdx.x) * kMasterStateWords : nullptr;
+	uint64_t *out = out_all + static_cast<size_t>(blockIdx.x) * n;
 	const uint32_t j = threadIdx.x;
-	for(uint32_t i = j; i < kMtN; i += blockDim.x){ ring[i] = state[i]; }
-	uint32_t idx = static_cast<uint32_t>(state[kMtN]);
+	for(uint32_t i = j; i < kMtN; i += blockDim.x){ ring[i] = state_in[i]; }
+	uint32_t idx = static_cast<uint32_t>(state_in[kMtN]);
 	__syncthreads();
 	uint64_t done = 0;
 	{
@@ -234,13 +239,58 @@ __global__ void __launch_bounds__(kMasterThreads) k_master_stream(uint64_t *stat
 		++k;
 		__syncthreads();
 	}
+	if(!state){ return; }
 	// persist the window made of the two most recent segments
 	if(k){
 		const uint32_t s0 = (k & 3u) * kMtM, s1 = ((k + 1u) & 3u) * kMtM;
 		for(uint32_t i = j; i < kMtM; i += blockDim.x){ state[i] = ring[s0 + i]; state[kMtM + i] = ring[s1 + i]; }
 		if(j == 0){ state[kMtN] = kMtM + last_take; }
 	}
-	else if(j == 0){ state[kMtN] = idx; }
+	else{
+		for(uint32_t i = j; i < kMtN; i += blockDim.x){ state[i] = ring[i]; }
+		if(j == 0){ state[kMtN] = idx; }
+	}
+}
+
+// Jump-ahead of the master stream by J = 2^k words (tools/gen_mt_jump.py): the window J steps ahead is the XOR of the
+// windows at the offsets given by the bits of g_J(t) = t^J mod phi(t).
+//   k_master_jump_gen  one CTA: the 19937 + 312 words behind the current window (128 dependent steps of 156 words, in shared
+//                      memory), copied to HBM/L2; clears the output window
+//   k_master_jump_xor  39 CTAs: CTA b takes 8 words (512 bits) of the polynomial, thread j XORs seq[i + j] over their set bits i
+//                      and merges its part into output word j with one atomic XOR
+constexpr int kJumpSeqWords = 19937 + kMtN + 7;
+constexpr int kJumpPolyWordsPerCta = 8;
+#include "mt_jump_tables.inc"
+__global__ void __launch_bounds__(kMasterThreads) k_master_jump_gen(const uint64_t *state_in, uint64_t *seq_out, uint64_t *state_out){
+	extern __shared__ __align__(16) uint64_t jump_seq[];
+	const uint32_t t = threadIdx.x;
+	for(uint32_t i = t; i < kMtN; i += blockDim.x){ jump_seq[i] = state_in[i]; state_out[i] = 0; }
+	if(t == 0){ state_out[kMtN] = state_in[kMtN]; }
+	__syncthreads();
+	for(uint32_t base = 0; base + kMtN < static_cast<uint32_t>(kJumpSeqWords); base += kMtM){
+		const uint32_t i = base + t;
+		if(t < kMtM && i + kMtN < static_cast<uint32_t>(kJumpSeqWords)){
+			const uint64_t w = (jump_seq[i] & 0xFFFFFFFF80000000ull) | (jump_seq[i + 1] & 0x7FFFFFFFull);
+			jump_seq[i + kMtN] = jump_seq[i + kMtM] ^ (w >> 1) ^ ((w & 1ull) ? 0xB5026F5AA96619E9ull : 0ull);
+		}
+		__syncthreads();
+	}
+	for(uint32_t i = t; i < static_cast<uint32_t>(kJumpSeqWords); i += blockDim.x){ seq_out[i] = jump_seq[i]; }
+}
+__global__ void __launch_bounds__(320) k_master_jump_xor(const uint64_t *seq, const uint64_t *poly, uint64_t *state_out){
+	const uint32_t j = threadIdx.x;
+	if(j >= kMtN){ return; }
+	uint64_t acc = 0;
+	const uint32_t w0 = blockIdx.x * kJumpPolyWordsPerCta;
+	for(uint32_t w = w0; w < w0 + kJumpPolyWordsPerCta && w < static_cast<uint32_t>(kMtN); ++w){
+		uint64_t bits = poly[w];
+		while(bits){
+			const uint32_t i = w * 64u + static_cast<uint32_t>(__ffsll(static_cast<long long>(bits)) - 1);
+			acc ^= seq[i + j];
+			bits &= bits - 1ull;
+		}
+	}
+	if(acc){ atomicXor(reinterpret_cast<unsigned long long *>(state_out + j), static_cast<unsigned long long>(acc)); }
 }
 
 __global__ void k_master_seed(uint64_t *state, uint64_t seed){
@@ -763,7 +813,7 @@ struct rsq_engine {
 	DevBuf<double> d_sur_start, d_sur_end, d_thr, d_binom_p0;
 	DevBuf<uint64_t> d_thr_int;
 	DevBuf<char> d_names;
-	DevBuf<uint64_t> d_master_state, d_master;
+	DevBuf<uint64_t> d_master_state, d_master, d_jump_states, d_jump_poly, d_jump_seq;
 	DevBuf<BlockDesc> d_blocks;
 	DevBuf<SysChain> d_sys_chains; DevBuf<SysChunk> d_sys_chunks; DevBuf<uint32_t> d_sys_dirty, d_gc_tiles;
 	DevBuf<BiasParamDev> d_bias_params; DevBuf<double> d_bias_sums, d_bias_max;
@@ -908,6 +958,53 @@ static std::string describe_flag(uint32_t f){
 	if(f & kErrRecordTooLong){ s += "FASTQ record longer than an output chunk; "; }
 	if(f & kErrReferenceOutOfRange){ s += "the reference implementation indexes its methylation regions out of range for this input (std::out_of_range in Simulator::CTConversion); "; }
 	return s;
+}
+
+// Appends n outputs of the master stream to `out` and leaves its state behind them.  Long runs are split into segments of
+// J = 2^k words whose start states come from jump-ahead (k_master_jump, one after the other: ~0.1 ms each) and which are then
+// generated by one CTA each at the same time; short runs and the remainder use the serial recurrence.
+static void master_generate(rsq_engine &e, uint64_t *out, uint64_t n){
+	cudaStream_t s = e.stream;
+	uint64_t min_words = 1ull << 20;
+	if(const char *env = getenv("RSQ_MASTER_JUMP_MIN")){ min_words = std::max<long long>(1 << 16, atoll(env)); }
+	if(n < min_words + 1024){
+		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, out, n); ++e.launches;
+		return;
+	}
+	// the first words come from the serial recurrence: afterwards the state window holds generated words only (the jump
+	// identity does not cover the unused low bits of the very first seed word)
+	const uint64_t head = 1024;
+	k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, out, head); ++e.launches;
+	out += head; n -= head;
+	// segment length: a jump costs ~40 us, a segment of J words ~J * 0.83 ns; tables exist for 2^16, 2^19, 2^22
+	int table = 0; double best = -1.0;
+	for(int t = 0; t < kMtJumpTables; ++t){
+		const double J = static_cast<double>(1ull << kMtJumpLog2[t]);
+		if(J > static_cast<double>(n)){ continue; }
+		const double cost = std::floor(n / J) * 40.0 + J * 0.00083;
+		if(best < 0.0 || cost < best){ best = cost; table = t; }
+	}
+	const uint64_t J = 1ull << kMtJumpLog2[table];
+	const uint64_t segments = n / J;
+	if(!e.d_jump_poly.p){
+		std::vector<uint64_t> polys(static_cast<size_t>(kMtJumpTables) * kMtN);
+		std::memcpy(polys.data(), kMtJumpPoly, polys.size() * 8);
+		e.d_jump_poly.upload(polys, s);
+		RSQ_CUDA(cudaFuncSetAttribute(k_master_jump_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, kJumpSeqWords * 8));
+		e.d_jump_seq.alloc(kJumpSeqWords);
+	}
+	e.d_jump_states.alloc((segments + 1) * kMasterStateWords);
+	RSQ_CUDA(cudaMemcpyAsync(e.d_jump_states.p, e.d_master_state.p, kMasterStateWords * 8, cudaMemcpyDeviceToDevice, s));
+	for(uint64_t g = 0; g < segments; ++g){
+		k_master_jump_gen<<<1, kMasterThreads, kJumpSeqWords * 8, s>>>(e.d_jump_states.p + g * kMasterStateWords, e.d_jump_seq.p, e.d_jump_states.p + (g + 1) * kMasterStateWords);
+		k_master_jump_xor<<<(kMtN + kJumpPolyWordsPerCta - 1) / kJumpPolyWordsPerCta, 320, 0, s>>>(e.d_jump_seq.p, e.d_jump_poly.p + static_cast<size_t>(table) * kMtN,
+		                                                                                          e.d_jump_states.p + (g + 1) * kMasterStateWords);
+	}
+	k_master_stream<<<static_cast<unsigned>(segments), kMasterThreads, 0, s>>>(e.d_jump_states.p, nullptr, out, J);
+	e.launches += 2 * static_cast<uint32_t>(segments) + 1;
+	// remainder from the state behind the last segment
+	RSQ_CUDA(cudaMemcpyAsync(e.d_master_state.p, e.d_jump_states.p + segments * kMasterStateWords, kMasterStateWords * 8, cudaMemcpyDeviceToDevice, s));
+	k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, out + segments * J, n - segments * J); ++e.launches;
 }
 
 // Systematic errors of a set of chains: speculative chunks + exact fix-up passes.
@@ -1176,7 +1273,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	k_master_seed<<<1, 32, 0, s>>>(e.d_master_state.p, opt.seed); ++e.launches;
 	if(master_draws_before){   // outputs the host consumed for --refBias draw
 		e.d_master.alloc(master_draws_before);
-		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, master_draws_before); ++e.launches;
+		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, e.d_master.p, master_draws_before); ++e.launches;
 	}
 	uint32_t carried = 0;
 	uint32_t passes_total = 0;
@@ -1195,7 +1292,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		}
 		if(n_draws){
 			e.d_master.alloc(n_draws);
-			k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
+			k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
 			for(const auto &o : order){
 				const uint32_t off = e.h_adapter_off[o.seg][o.a], len = e.h_adapter_off[o.seg][o.a + 1] - off;
 				SysChain ch{}; ch.seq = e.d_adapter_seq.p + off; ch.L = len; ch.reverse = 0; ch.raw = e.d_master.p + o.raw_off; ch.seed_interleaved = 0;
@@ -1231,7 +1328,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
 		const uint64_t n_draws = 2ull * nb + (from_file ? 0ull : 4ull * L);
-		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
+		master_generate(e, e.d_master.p, n_draws);
 		if(from_file){
 			// CreateUnit: LoadSysErrorRecord (reverse strand) ... LoadSysErrorRecord (forward strand), strictly in file order
 			for(int strand = 0; strand < 2; ++strand){
@@ -1270,7 +1367,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	e.n_blocks_sim = nb_total > lookahead ? nb_total - lookahead : 0;
 	e.adapter_only_seed = 0;
 	if(e.adapter_only_pairs){
-		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, 1); ++e.launches;
+		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, e.d_master.p, 1); ++e.launches;
 		RSQ_CUDA(cudaMemcpyAsync(&e.adapter_only_seed, e.d_master.p, 8, cudaMemcpyDeviceToHost, s));
 		RSQ_CUDA(cudaStreamSynchronize(s));
 	}
@@ -1329,7 +1426,7 @@ static void create_sys_profile(rsq_engine &e, const Genome &g, uint64_t seed, co
 			e.d_ref.alloc(L + 1);
 			RSQ_CUDA(cudaMemcpyAsync(e.d_ref.p, g.seqs[i].data(), L, cudaMemcpyHostToDevice, s));
 			e.d_master.alloc(4ull * L);
-			k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, 4ull * L); ++e.launches;
+			master_generate(e, e.d_master.p, 4ull * L);
 			e.d_sys_rev.alloc(2ull * L + 2); e.d_sys_fwd.alloc(2ull * L + 2);
 			std::vector<SysChain> chains(2); std::vector<std::pair<uint32_t, uint32_t>> lens{{L, 0}, {L, 0}};
 			chains[0].seq = e.d_ref.p; chains[0].L = L; chains[0].reverse = 1; chains[0].raw = e.d_master.p; chains[0].out = e.d_sys_rev.p; chains[0].carried_dom = carried;
@@ -1712,7 +1809,7 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 		for(int seg = 2; seg--; ){ for(size_t a = p.adapter_count_sum[seg].size(); a--; ){ if(!p.adapter_count_sum[seg][a]){ continue; } order.push_back({seg, a, n_draws}); n_draws += 2ull * (e.h_adapter_off[seg][a + 1] - e.h_adapter_off[seg][a]); } }
 		if(n_draws){
 			e.d_master.alloc(n_draws);
-			k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
+			k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, e.d_master.p, n_draws); ++e.launches;
 			for(const auto &o : order){
 				const uint32_t off = e.h_adapter_off[o.seg][o.a], len = e.h_adapter_off[o.seg][o.a + 1] - off;
 				SysChain ch{}; ch.seq = e.d_adapter_seq.p + off; ch.L = len; ch.raw = e.d_master.p + o.raw_off; ch.out = e.d_adapter_sys.p + 2 * off; ch.carried_dom = carried;
@@ -1726,7 +1823,7 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 	const uint32_t batch = 10000;
 	const uint32_t n_batches = (recs.size() + batch - 1) / batch;
 	DevBuf<uint64_t> d_seeds; d_seeds.alloc(n_batches);
-	k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, d_seeds.p, n_batches); ++e.launches;
+	k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, d_seeds.p, n_batches); ++e.launches;
 	DevBuf<EmRecord> d_recs; d_recs.upload(recs, s);
 	DevBuf<uint8_t> d_seq, d_dom, d_rate; d_seq.upload(hseq, s); d_dom.upload(hdom, s); d_rate.upload(hrate, s);
 	DevBuf<char> d_ids; d_ids.upload(hid.data(), hid.size() + 1, s);

@@ -155,7 +155,11 @@ def test_error_model_rejects_malformed_header(engine, workdir):
     assert not os.path.exists(os.path.join(workdir, "bad_em.fq"))
 
 
-def test_stage_arrays_match_reference(rb, engine, golden, oracle, workdir):
+@pytest.mark.parametrize("jump_min", [None, "65536"])
+def test_stage_arrays_match_reference(rb, engine, golden, oracle, workdir, monkeypatch, jump_min):
+    # jump_min: forces the jump-ahead form of the master stream (k_master_jump, segments generated in parallel) on this small genome
+    if jump_min:
+        monkeypatch.setenv("RSQ_MASTER_JUMP_MIN", jump_min)
     """Systematic errors (both strands, adapters) and thresholds against the reference's in-memory values."""
     from reseq_b200.flatfile import read_flat
     stage = os.path.join(workdir, "stage_gpu.flat")
@@ -286,7 +290,7 @@ def test_too_short_reference_is_an_error(rb, engine):
         engine.prepare(ref, seed=1, coverage=5.0)
 
 
-def test_full_size_properties(rb, engine, workdir):
+def test_full_size_properties(rb, engine, workdir, monkeypatch):
     """BASELINE config 2 size (4.64 Mbp, 30x): determinism, record structure, pairing, pair count near the aim."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import make_synthetic
@@ -304,7 +308,15 @@ def test_full_size_properties(rb, engine, workdir):
     blocks = [int(i[len(b"@ReseqRead"):].split(b"_")[0]) for i in ids1]
     assert blocks == sorted(blocks), "records must come in block order like the reference's 1-thread run"
     h = hashlib.sha256(r1).hexdigest(), hashlib.sha256(r2).hexdigest()
+    spec_rounds = rep.spec_rounds
     r1b, r2b, _ = _simulate(engine, ref, seed=42, coverage=30.0)
     assert (hashlib.sha256(r1b).hexdigest(), hashlib.sha256(r2b).hexdigest()) == h
     r1c, _, _ = _simulate(engine, ref, seed=43, coverage=30.0)
     assert hashlib.sha256(r1c).hexdigest() != h[0]
+    # the serial forms (one warp per SimBlock, master stream as one recurrence) write the same bytes as the
+    # speculative two-phase kernels fed by the jump-ahead master stream
+    monkeypatch.setenv("RSQ_SIM_PATH", "serial")
+    monkeypatch.setenv("RSQ_MASTER_JUMP_MIN", str(1 << 40))
+    r1d, r2d, repd = _simulate(engine, ref, seed=42, coverage=30.0)
+    assert repd.spec_rounds == 0 and spec_rounds > 0
+    assert (hashlib.sha256(r1d).hexdigest(), hashlib.sha256(r2d).hexdigest()) == h

@@ -25,6 +25,13 @@ def test_exp_pow_port_matches_libm(workdir):
     assert "exp_mismatch=0 logit_mismatch=0 pow_mismatch=0" in out.stdout
 
 
+def test_mt19937_64_jump_polynomials_match_discard(workdir):
+    """csrc/mt_jump_tables.inc (tools/gen_mt_jump.py): window 2^k outputs ahead == std::mt19937_64::discard(2^k)."""
+    exe = _compile("jump_check.cpp", os.path.join(workdir, "jump_check"))
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "jump_mismatches=0" in out.stdout, out.stdout
+
+
 def test_golden_fastq_is_what_the_reference_writes(oracle, golden, workdir):
     r1, r2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], 42, 20, os.path.join(workdir, "pin"))
     assert filecmp.cmp(r1, golden["r1"], shallow=False)
