@@ -1513,9 +1513,10 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 	sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
 	// Depth (reads speculated per unit and round) and reads per warp are chosen per batch of rounds from a cost model:
 	//   a round costs max(latency, throughput) with latency ~ 1.0 ms + 0.12 ms per read of depth (one lock-step pass over a read
-	//   + the scan in front of `depth` reads) and throughput ~ 5e-5 ms per read in flight on a B200;
+	//   + the scan in front of `depth` reads) and throughput ~ 5e-5 ms per read in flight plus 1.5 reads' worth of fixed work per
+	//   unit (verification, snapshot restore/save) on a B200 (measured at 4.6 and 60 Mbp);
 	//   it verifies (1 - p^d) / (1 - p) reads per unit, p = measured share of reads whose assumption held.
-	// Small runs are latency bound (deep speculation, few reads per warp), large ones throughput bound (shallow, 32 reads per warp).
+	// Small runs are latency bound (few reads per warp), large ones throughput bound; how deep to speculate mostly depends on p.
 	const uint64_t warps_cap = static_cast<uint64_t>(dev_sms) * 16;
 	const int fixed_depth = getenv("RSQ_SPEC_DEPTH") ? std::min(32, std::max(1, atoi(getenv("RSQ_SPEC_DEPTH")))) : 0;
 	const int fixed_lanes = getenv("RSQ_SPEC_LANES") ? atoi(getenv("RSQ_SPEC_LANES")) : 0;
@@ -1533,7 +1534,7 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 		for(uint32_t d : cand){
 			if(d > depth){ break; }
 			const double prog = p_hold >= 0.9999 ? d : (1.0 - std::pow(p_hold, static_cast<double>(d))) / (1.0 - p_hold);
-			const double cost = std::max(1.0 + 0.12 * d, 5.0e-5 * static_cast<double>(active) * d);
+			const double cost = std::max(1.0 + 0.12 * d, 5.0e-5 * static_cast<double>(active) * (1.5 + d));
 			if(prog / cost > best){ best = prog / cost; best_d = d; }
 		}
 		if(fixed_depth){ best_d = fixed_depth; }
@@ -1542,7 +1543,7 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 		sp.scan_budget = budget > 4.0e9 ? 4000000000u : static_cast<uint32_t>(budget);
 		// reads per warp: as few as keep all reads of the round resident at once
 		const uint64_t reads = active * best_d;
-		lanes = reads <= warps_cap * 8 ? 8 : (reads <= warps_cap * 16 * 2 ? 16 : 32);
+		lanes = reads <= warps_cap * 8 ? 8 : 16;   // 32 reads per warp (one lane each in every phase) measured slower than 16 at every size
 		if(fixed_lanes){ lanes = fixed_lanes >= 32 ? 32 : (fixed_lanes >= 16 ? 16 : 8); }
 	};
 	choose(sp.n_units, 0.95);

@@ -18,9 +18,14 @@ def main():
     configs = sys.argv[1:] or ["4,8", "8,8", "8,16", "2,32", "serial"]
     tmp = tempfile.mkdtemp(prefix="rsq_sweep_")
     prof = rb.Profile.load_flat(bench.unxz(bench.PROFILE + ".flat.xz", tmp))
-    seq = bench.workload_sequence().encode()
     eng = rb.Engine(prof, 0)
-    ref = rb.Reference.from_memory(["ecoli_sized synthetic"], [seq])
+    if os.environ.get("RSQ_SWEEP_MBP"):   # larger synthetic genome (4 sequences) instead of the bench workload
+        import make_synthetic
+        seqs = make_synthetic.gen_reference([int(float(os.environ["RSQ_SWEEP_MBP"]) * 1e6) // 4] * 4, 4321)
+        ref = rb.Reference.from_memory([f"chr{i + 1} synthetic" for i in range(4)], [s.encode() for s in seqs])
+    else:
+        seq = bench.workload_sequence().encode()
+        ref = rb.Reference.from_memory(["ecoli_sized synthetic"], [seq])
     for cfg in configs:
         for k in ("RSQ_SIM_PATH", "RSQ_SPEC_DEPTH", "RSQ_SPEC_LANES"):
             os.environ.pop(k, None)
@@ -30,7 +35,7 @@ def main():
             d, r = cfg.split(",")
             os.environ["RSQ_SPEC_DEPTH"], os.environ["RSQ_SPEC_LANES"] = d, r
         best = None
-        for _ in range(3):
+        for _ in range(int(os.environ.get("RSQ_SWEEP_REPEAT", "3"))):
             eng.prepare(ref, seed=bench.SEED, coverage=bench.COVERAGE)
             rep = eng.simulate().as_dict()
             if best is None or rep["ms_simulate"] < best["ms_simulate"]:
