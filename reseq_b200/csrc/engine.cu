@@ -18,6 +18,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <memory>
 #include <string>
 #include <vector>
@@ -562,6 +566,88 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 	return result;
 }
 
+// Simulator::SetSystematicErrors for `lanes_per_warp` chunks per warp in lock step (one lane per chunk, the other lanes
+// help with the likelihood products): the same chain as sys_error_chain() in sim_core.cuh - warm-up from a reset state,
+// then the chunk itself - with both Draws of a position going through coop_draw.
+__global__ void __launch_bounds__(128)
+k_sys_chunks_lanes(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_t n_chunks, uint32_t stride, uint32_t lanes_per_warp,
+                   uint32_t sys_gc_range, uint32_t reset_distance){
+	extern __shared__ __align__(16) unsigned char smem[];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	double *buf = reinterpret_cast<double *>(smem) + static_cast<size_t>(warp) * lanes_per_warp * stride;
+	const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + warp) * lanes_per_warp + lane;
+	bool have = lane < lanes_per_warp && c < n_chunks;
+	SysChunk ck{};
+	if(have){ ck = chunks[c]; have = ck.dirty != 0; }
+	if(!__any_sync(0xffffffffu, have)){ return; }
+	SysChain ch{};
+	if(have){ ch = chains[ck.chain]; }
+	const bool reverse = ch.reverse != 0, interleaved = ch.seed_interleaved != 0;
+	const bool warming = have && ck.warm_from < ck.begin;
+	uint32_t p = have ? ck.warm_from : 0u, end = have ? ck.end : 0u;
+	SysState st{warming ? 0u : ck.in_dist, warming ? 0u : ck.in_rate};
+	// state in front of p: GC window (Simulator::UpdateGC), last base, dominant-base window
+	uint32_t gc_bases = 0, gc = 0, last_base = 4u, hist = 0, nwin = 0;
+	if(have){
+		gc_bases = p < sys_gc_range ? p : sys_gc_range;
+		for(uint32_t q = p - gc_bases; q < p; ++q){
+			const uint32_t b = chain_base(ch.seq, ch.L, reverse, q);
+			gc += (b == 1 || b == 2) ? 1u : 0u;
+		}
+		last_base = p ? chain_base(ch.seq, ch.L, reverse, p - 1) : 4u;
+		window_before(ch.seq, ch.L, reverse, p, hist, nwin);
+	}
+	bool zero;
+	while(true){
+		const bool active = have && p < end;
+		if(!__any_sync(0xffffffffu, active)){ break; }
+		uint32_t ref_base = 0, dom_base = 0, gc_percent = 50u, dist = 0, t1 = 0;
+		double u1 = 0.0, u2 = 0.0;
+		if(active){
+			if(p == ck.begin && warming){ ck.in_dist = st.distance; ck.in_rate = st.start_rate; }
+			ref_base = chain_base(ch.seq, ch.L, reverse, p);
+			dom_base = dominant_from_window(hist, nwin, ch.carried_dom);
+			gc_percent = gc_bases ? percent_u16(gc, gc_bases) : 50u;
+			dist = (st.distance + 9) / 10;
+			u1 = canonical(chain_raw(ch.raw, interleaved, p, 0));
+			u2 = canonical(chain_raw(ch.raw, interleaved, p, 1));
+			t1 = tab.dom_error(ref_base, last_base, dom_base);
+		}
+		uint32_t dom_error = coop_draw(tab, buf, stride, lanes_per_warp, active, t1, dist, gc_percent, st.start_rate, 0, u1, zero);
+		if(zero){ dom_error = 4; }
+		const uint32_t t2 = active ? tab.error_rate(ref_base, dom_error) : 0u;
+		uint32_t error_rate = coop_draw(tab, buf, stride, lanes_per_warp, active, t2, dist, gc_percent, st.start_rate, 0, u2, zero);
+		if(zero){ error_rate = 0; }
+		error_rate &= 0xffu;
+		if(active){
+			if(p >= ck.begin){
+				ch.out[2 * static_cast<size_t>(p)] = static_cast<uint8_t>(dom_error);
+				ch.out[2 * static_cast<size_t>(p) + 1] = static_cast<uint8_t>(error_rate);
+			}
+			last_base = ref_base;
+			hist = ((hist << 2) | ref_base) & 0x3ffu;
+			if(nwin < 5){ ++nwin; }
+			if(st.distance){   // CoverageStats::UpdateDistances
+				if(st.start_rate < error_rate){ st.distance = 0; st.start_rate = error_rate; }
+				else if(++st.distance >= reset_distance){ st.distance = 0; st.start_rate = 0; }
+			}
+			else if(error_rate){ st.distance = 1; st.start_rate = error_rate; }
+			if(ref_base == 1 || ref_base == 2){ ++gc; }
+			if(gc_bases < sys_gc_range){ ++gc_bases; }
+			else{
+				const uint32_t ob = chain_base(ch.seq, ch.L, reverse, p - gc_bases);
+				if(ob == 1 || ob == 2){ --gc; }
+			}
+			++p;
+		}
+	}
+	if(have){
+		SysChunk &o = chunks[c];
+		if(warming){ o.in_dist = ck.in_dist; o.in_rate = ck.in_rate; o.warm_from = ck.begin; }
+		o.out_dist = st.distance; o.out_rate = st.start_rate; o.dirty = 0;
+	}
+}
+
 // Lanes 0 .. lanes_per_warp-1 of a warp own one read each; the other lanes only help with the likelihood products.
 // Few reads per warp = short latency per round (small genomes), 32 = fewest instructions per read (large ones).
 constexpr int kSpecReadWarps = 4;
@@ -828,7 +914,7 @@ struct rsq_engine {
 	uint32_t sys_gc_range = 0, syserr_passes = 0;
 	bool prepared = false;
 	// output
-	DevBuf<unsigned char> d_arena, d_out[2];
+	DevBuf<unsigned char> d_arena;
 	DevBuf<uint32_t> d_chunk_next, d_chunk_used, d_next_free, d_next_block;
 	DevBuf<BlockOut> d_block_out;
 	DevBuf<unsigned long long> d_offsets, d_totals;
@@ -836,6 +922,13 @@ struct rsq_engine {
 	uint64_t out_pairs = 0, out_draws = 0;
 	PinnedBuf h_out[2];
 	bool downloaded = false;
+	// batched output: device text of two batches in flight, copy stream, optional file sink (rsq_simulate)
+	DevBuf<unsigned char> d_out_batch[2][2];
+	PinnedBuf h_staging[4];
+	cudaStream_t copy_stream = nullptr; cudaEvent_t ev_out[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+	FILE *sink_files[2] = {nullptr, nullptr};
+	bool streamed_to_host = false; int last_par = 0;
+	double reusable_bytes() const;
 	// speculative two-phase path
 	uint32_t max_n0_reads = 0;             // largest candidate count of the tables FillRead draws from
 	uint32_t max_name_len = 0;
@@ -845,8 +938,16 @@ struct rsq_engine {
 	uint32_t spec_rounds = 0, spec_depth = 0;
 	std::vector<cudaStream_t> spec_streams; std::vector<cudaEvent_t> spec_events;
 
-	~rsq_engine(){ for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
+	~rsq_engine(){ for(int i = 0; i < 2; ++i){ if(ev_out[i]){ cudaEventDestroy(ev_out[i]); } if(ev_copied[i]){ cudaEventDestroy(ev_copied[i]); } } if(copy_stream){ cudaStreamDestroy(copy_stream); } for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
 };
+
+double rsq_engine::reusable_bytes() const {
+	double b = 0;
+	b += d_spec_blocks.cap * sizeof(rsq::SpecBlock) + d_spec_snaps.cap * sizeof(rsq::SpecSnap) + d_spec_jobs.cap * sizeof(rsq::ReadJob) + d_spec_words.cap * 8.0;
+	b += d_spec_slots.cap + (d_slab_next.cap + d_slab_count.cap) * 4.0 + d_arena.cap + (d_chunk_next.cap + d_chunk_used.cap) * 4.0;
+	for(int i = 0; i < 2; ++i){ for(int j = 0; j < 2; ++j){ b += d_out_batch[i][j].cap; } }
+	return b;
+}
 
 namespace rsq {
 
@@ -1036,12 +1137,23 @@ static void run_sys_chains(rsq_engine &e, const std::vector<SysChain> &chains, c
 	DevBuf<SysChunk> &d_chunks = e.d_sys_chunks; d_chunks.upload(chunks, e.stream);
 	DevBuf<uint32_t> &d_dirty = e.d_sys_dirty; d_dirty.alloc(1);
 	const uint32_t n = chunks.size();
+	// one lane per chunk (lock step, likelihood products shared by the warp); RSQ_SYS_PATH=warp keeps the one-warp-per-chunk kernel
+	const bool lanes_path = !(getenv("RSQ_SYS_PATH") && std::string(getenv("RSQ_SYS_PATH")) == "warp");
 	const int warps = 4;
-	const size_t shmem = static_cast<size_t>(warps) * ((e.max_n0 + 3) & ~3u) * 8;
+	const uint32_t lanes = n <= 2368u * 8u ? 8u : 16u;
+	const uint32_t stride = ((e.max_n0 + 3u) & ~3u) + 1u;
+	const size_t shmem = lanes_path ? static_cast<size_t>(warps) * lanes * stride * 8 : static_cast<size_t>(warps) * ((e.max_n0 + 3) & ~3u) * 8;
+	if(lanes_path){ RSQ_CUDA(cudaFuncSetAttribute(k_sys_chunks_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem))); }
 	uint32_t dirty = n;
 	passes = 0;
 	while(dirty){
-		k_sys_chunks<<<(n + warps - 1) / warps, warps * 32, shmem, e.stream>>>(e.ctx.tab, d_chains.p, d_chunks.p, n, e.max_n0, e.sys_gc_range, e.prof.reset_distance);
+		if(lanes_path){
+			const uint32_t per_cta = warps * lanes;
+			k_sys_chunks_lanes<<<(n + per_cta - 1) / per_cta, warps * 32, shmem, e.stream>>>(e.ctx.tab, d_chains.p, d_chunks.p, n, stride, lanes, e.sys_gc_range, e.prof.reset_distance);
+		}
+		else{
+			k_sys_chunks<<<(n + warps - 1) / warps, warps * 32, shmem, e.stream>>>(e.ctx.tab, d_chains.p, d_chunks.p, n, e.max_n0, e.sys_gc_range, e.prof.reset_distance);
+		}
 		d_dirty.zero(e.stream);
 		k_sys_check<<<(n + 255) / 256, 256, 0, e.stream>>>(d_chunks.p, n, d_dirty.p);
 		e.launches += 2;
@@ -1480,8 +1592,9 @@ static void gather(rsq_engine &e, const Arena &a, uint32_t slots, rsq_sim_report
 	RSQ_CUDA(cudaMemcpyAsync(totals, e.d_totals.p, sizeof totals, cudaMemcpyDeviceToHost, s));
 	RSQ_CUDA(cudaStreamSynchronize(s));
 	e.out_bytes[0] = totals[0]; e.out_bytes[1] = totals[1]; e.out_pairs = totals[2]; e.out_draws = totals[3];
-	e.d_out[0].alloc(totals[0] + 1); e.d_out[1].alloc(totals[1] + 1);
-	if(slots){ k_gather<<<2 * slots, 128, 0, s>>>(e.d_block_out.p, slots, a, e.d_offsets.p, e.d_out[0].p, e.d_out[1].p); ++e.launches; }
+	e.d_out_batch[0][0].alloc(totals[0] + 1); e.d_out_batch[0][1].alloc(totals[1] + 1);
+	e.last_par = 0; e.streamed_to_host = false;
+	if(slots){ k_gather<<<2 * slots, 128, 0, s>>>(e.d_block_out.p, slots, a, e.d_offsets.p, e.d_out_batch[0][0].p, e.d_out_batch[0][1].p); ++e.launches; }
 	const float ms = tm.stop();
 	if(rep){ rep->ms_gather = ms; }
 	RSQ_CUDA(cudaGetLastError());
@@ -1500,14 +1613,18 @@ static void fill_simulate_report(rsq_engine &e, rsq_sim_report *rep, float ms_si
 }
 
 // Speculative two-phase path: rounds of k_spec_scan + k_spec_reads until every unit is done (see spec_core.cuh).
-static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
+// One batch of this shard's blocks [u_begin, u_begin + u_count) (+ the adapter-only pairs behind the last one): on return the
+// FASTQ text of the batch is in e.d_out_batch[par][0/1], its sizes in `res`.  false: a read outran the speculation margin.
+struct BatchResult { uint64_t bytes[2] = {0, 0}; uint64_t pairs = 0, draws = 0; float ms_sim = 0, ms_gather = 0; uint32_t rounds = 0, depth = 0; };
+static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_count, bool with_adapter_only, uint32_t depth_cap, int par, BatchResult &res){
 	cudaStream_t s = e.stream;
 	SimCtx &c = e.ctx;
 	int dev_sms = 0; RSQ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e.device));
+	const uint32_t first_desc = e.shard_first + u_begin;
 	SpecCtx sp{};
-	sp.n_blocks = e.shard_n;
-	sp.n_units = e.shard_n + (e.shard_has_adapter_only ? 1 : 0);
-	sp.adapter_only_pairs = e.shard_has_adapter_only ? e.adapter_only_pairs : 0;
+	sp.n_blocks = u_count;
+	sp.n_units = u_count + (with_adapter_only ? 1 : 0);
+	sp.adapter_only_pairs = with_adapter_only ? e.adapter_only_pairs : 0;
 	sp.adapter_only_seed = e.adapter_only_seed;
 	const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);   // ReadLengths().to(): one past the longest read
 	sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
@@ -1520,8 +1637,7 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 	const uint64_t warps_cap = static_cast<uint64_t>(dev_sms) * 16;
 	const int fixed_depth = getenv("RSQ_SPEC_DEPTH") ? std::min(32, std::max(1, atoi(getenv("RSQ_SPEC_DEPTH")))) : 0;
 	const int fixed_lanes = getenv("RSQ_SPEC_LANES") ? atoi(getenv("RSQ_SPEC_LANES")) : 0;
-	uint32_t depth = 32;   // capacity per unit (array stride)
-	if(static_cast<uint64_t>(sp.n_units) * 32 > 64 * warps_cap * 32){ depth = 8; }   // very large runs never speculate deep: keep the buffers small
+	uint32_t depth = depth_cap;   // capacity per unit (array stride)
 	if(fixed_depth){ depth = fixed_depth; }
 	if(const char *env = getenv("RSQ_SPEC_MAX_DEPTH")){ depth = std::max<uint32_t>(fixed_depth, std::min(32, std::max(1, atoi(env)))); }
 	sp.depth = depth;
@@ -1547,7 +1663,7 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 		if(fixed_lanes){ lanes = fixed_lanes >= 32 ? 32 : (fixed_lanes >= 16 ? 16 : 8); }
 	};
 	choose(sp.n_units, 0.95);
-	e.spec_depth = sp.run_depth;
+	res.depth = sp.run_depth;
 	const size_t n_jobs = static_cast<size_t>(sp.n_units) * depth;
 	const size_t n_tiles = (n_jobs + 31) / 32;
 	e.d_spec_blocks.alloc(sp.n_units); e.d_spec_snaps.alloc(2 * static_cast<size_t>(sp.n_units) * (depth + 1)); e.d_spec_jobs.alloc(n_tiles * 32);
@@ -1569,7 +1685,7 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 	const uint32_t stride = ((e.max_n0_reads + 3u) & ~3u) + 1u;
 	const size_t shmem_reads_max = static_cast<size_t>(kSpecReadWarps) * 32 * stride * sizeof(double);
 	RSQ_CUDA(cudaFuncSetAttribute(k_spec_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem_reads_max)));
-	const double share = e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0;
+	const double share = e.n_blocks_sim ? static_cast<double>(u_count) / e.n_blocks_sim : 0.0;
 	uint64_t expected_reads = static_cast<uint64_t>(2.0 * (e.total_pairs * share + sp.adapter_only_pairs) * 1.15) + 2048;
 	float ms_sim = 0;
 	uint32_t rounds = 0;
@@ -1584,7 +1700,7 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 		tm.start();
 		rounds = 0;
 		if(sp.n_units){
-			k_spec_init<<<(sp.n_units + 127) / 128, 128, 0, s>>>(c, sp, e.d_blocks.p, e.shard_first); ++e.launches;
+			k_spec_init<<<(sp.n_units + 127) / 128, 128, 0, s>>>(c, sp, e.d_blocks.p, first_desc); ++e.launches;
 			RSQ_CUDA(cudaEventRecord(e.ev_fork, s));
 			for(uint32_t gi = 0; gi < n_groups; ++gi){ RSQ_CUDA(cudaStreamWaitEvent(e.spec_streams[gi], e.ev_fork, 0)); }
 			volatile uint32_t *h_done = reinterpret_cast<volatile uint32_t *>(e.h_spec_counters.p) + 1;
@@ -1597,7 +1713,7 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 						const uint32_t u0 = static_cast<uint64_t>(sp.n_units) * gi / n_groups, u1 = static_cast<uint64_t>(sp.n_units) * (gi + 1) / n_groups;
 						if(u1 == u0){ continue; }
 						cudaStream_t gs = e.spec_streams[gi];
-						k_spec_scan<<<(u1 - u0 + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, gs>>>(c, sp, e.d_blocks.p, e.shard_first, u0, u1);
+						k_spec_scan<<<(u1 - u0 + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, gs>>>(c, sp, e.d_blocks.p, first_desc, u0, u1);
 						const size_t warps = (static_cast<size_t>(u1 - u0) * sp.run_depth + lanes - 1) / lanes;
 						const size_t shmem_reads = static_cast<size_t>(kSpecReadWarps) * lanes * stride * sizeof(double);
 						k_spec_reads<<<static_cast<unsigned>((warps + kSpecReadWarps - 1) / kSpecReadWarps), kSpecReadWarps * 32, shmem_reads, gs>>>(c, sp, stride, lanes, u0, u1);
@@ -1653,7 +1769,7 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 		if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
 		break;
 	}
-	e.spec_rounds = rounds;
+	res.rounds = rounds; res.ms_sim = ms_sim;
 	// ordered FASTQ text
 	EventTimer tm(s);
 	tm.start();
@@ -1665,29 +1781,20 @@ static bool simulate_spec(rsq_engine &e, rsq_sim_report *rep){
 	unsigned long long totals[4];
 	RSQ_CUDA(cudaMemcpyAsync(totals, e.d_totals.p, sizeof totals, cudaMemcpyDeviceToHost, s));
 	RSQ_CUDA(cudaStreamSynchronize(s));
-	e.out_bytes[0] = totals[0]; e.out_bytes[1] = totals[1]; e.out_pairs = totals[2]; e.out_draws = totals[3];
-	e.d_out[0].alloc(totals[0] + 1); e.d_out[1].alloc(totals[1] + 1);
-	if(slots){ k_spec_gather<<<2 * slots, 128, 0, s>>>(sp, e.d_offsets.p, e.d_out[0].p, e.d_out[1].p); ++e.launches; }
-	const float ms_gather = tm.stop();
-	if(rep){ rep->ms_gather = ms_gather; }
+	res.bytes[0] = totals[0]; res.bytes[1] = totals[1]; res.pairs = totals[2]; res.draws = totals[3];
+	e.d_out_batch[par][0].alloc(totals[0] + 1); e.d_out_batch[par][1].alloc(totals[1] + 1);
+	if(slots){ k_spec_gather<<<2 * slots, 128, 0, s>>>(sp, e.d_offsets.p, e.d_out_batch[par][0].p, e.d_out_batch[par][1].p); ++e.launches; }
+	res.ms_gather = tm.stop();
 	RSQ_CUDA(cudaGetLastError());
-	fill_simulate_report(e, rep, ms_sim);
 	return true;
 }
 
-static void simulate(rsq_engine &e, rsq_sim_report *rep){
-	if(!e.prepared){ throw std::runtime_error("rsq_engine_prepare has not been called"); }
+// The same batch on the serial kernel (one warp per SimBlock): bisulfite runs, RSQ_SIM_PATH=serial, fallback of the speculative path.
+static void simulate_serial_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_count, bool with_adapter_only, int par, BatchResult &res){
 	cudaStream_t s = e.stream;
 	SimCtx &c = e.ctx;
-	e.downloaded = false;
-	e.spec_rounds = 0; e.spec_depth = 0;
 	const bool meth = c.meth_loaded != 0;
-	{
-		// RSQ_SIM_PATH=serial keeps the one-warp-per-SimBlock kernel (parity tests run both); bisulfite runs always use it
-		const char *path = getenv("RSQ_SIM_PATH");
-		if(!meth && !(path && std::string(path) == "serial") && simulate_spec(e, rep)){ return; }
-	}
-	const uint32_t slots = e.shard_n + (e.shard_has_adapter_only ? 1 : 0);
+	const uint32_t slots = u_count + (with_adapter_only ? 1 : 0);
 	const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, c.max_read_len);
 	const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta;
 	auto kernel = meth ? k_simulate<true> : k_simulate<false>;
@@ -1696,10 +1803,9 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	int dev_sms = 0; RSQ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e.device));
 	int ctas_per_sm = 0; RSQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kWarpsPerCta * 32, shmem));
 	if(ctas_per_sm < 1){ throw std::runtime_error("k_simulate does not fit on an SM"); }
-	// expected output: this shard's share of the pairs, generously padded
-	const double share = e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0;
-	uint64_t expected = static_cast<uint64_t>((e.total_pairs * share + e.adapter_only_pairs + 1000) * (2.0 * (2.0 * c.max_read_len + 160.0)) * 1.3);
-	float ms_sim = 0;
+	// expected output: this batch's share of the pairs, generously padded
+	const double share = e.n_blocks_sim ? static_cast<double>(u_count) / e.n_blocks_sim : 0.0;
+	uint64_t expected = static_cast<uint64_t>((e.total_pairs * share + (with_adapter_only ? e.adapter_only_pairs : 0) + 1000) * (2.0 * (2.0 * c.max_read_len + 160.0)) * 1.3);
 	for(int attempt = 0; ; ++attempt){
 		Arena a;
 		setup_arena(e, a, expected, slots);
@@ -1708,16 +1814,16 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 		e.d_next_block.alloc(1); e.d_next_block.zero(s);
 		EventTimer tm(s);
 		tm.start();
-		if(e.shard_n){
-			const uint32_t ctas = std::min<uint32_t>((e.shard_n + kWarpsPerCta - 1) / kWarpsPerCta, dev_sms * ctas_per_sm);
-			kernel<<<ctas, kWarpsPerCta * 32, shmem, s>>>(c, e.d_blocks.p, e.shard_first, e.shard_n, a, e.d_block_out.p, e.d_next_block.p, e.max_n0, scratch);
+		if(u_count){
+			const uint32_t ctas = std::min<uint32_t>((u_count + kWarpsPerCta - 1) / kWarpsPerCta, dev_sms * ctas_per_sm);
+			kernel<<<ctas, kWarpsPerCta * 32, shmem, s>>>(c, e.d_blocks.p, e.shard_first + u_begin, u_count, a, e.d_block_out.p, e.d_next_block.p, e.max_n0, scratch);
 			++e.launches;
 		}
-		if(e.shard_has_adapter_only){
-			k_adapter_only<<<1, 32, scratch, s>>>(c, e.adapter_only_seed, e.adapter_only_pairs, a, e.d_block_out.p, e.shard_n, e.max_n0);
+		if(with_adapter_only){
+			k_adapter_only<<<1, 32, scratch, s>>>(c, e.adapter_only_seed, e.adapter_only_pairs, a, e.d_block_out.p, u_count, e.max_n0);
 			++e.launches;
 		}
-		ms_sim = tm.stop();
+		res.ms_sim = tm.stop();
 		RSQ_CUDA(cudaGetLastError());
 		const uint32_t flag = read_error_flag(e);
 		if(flag == kErrArenaFull && attempt < 3){
@@ -1725,9 +1831,139 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 			continue;
 		}
 		if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
-		gather(e, a, slots, rep);
+		// ordered FASTQ text
+		EventTimer tg(s);
+		tg.start();
+		e.d_offsets.alloc(2ull * (slots + 1)); e.d_totals.alloc(4);
+		k_block_offsets<<<1, 1024, 0, s>>>(e.d_block_out.p, slots, e.d_offsets.p, e.d_totals.p); ++e.launches;
+		unsigned long long totals[4];
+		RSQ_CUDA(cudaMemcpyAsync(totals, e.d_totals.p, sizeof totals, cudaMemcpyDeviceToHost, s));
+		RSQ_CUDA(cudaStreamSynchronize(s));
+		res.bytes[0] = totals[0]; res.bytes[1] = totals[1]; res.pairs = totals[2]; res.draws = totals[3];
+		e.d_out_batch[par][0].alloc(totals[0] + 1); e.d_out_batch[par][1].alloc(totals[1] + 1);
+		if(slots){ k_gather<<<2 * slots, 128, 0, s>>>(e.d_block_out.p, slots, a, e.d_offsets.p, e.d_out_batch[par][0].p, e.d_out_batch[par][1].p); ++e.launches; }
+		res.ms_gather = tg.stop();
+		RSQ_CUDA(cudaGetLastError());
 		break;
 	}
+}
+
+// Host side of the output: batches arrive in order.  Without files (engine API) the text of every batch is copied to the
+// pinned buffers h_out right behind the previous one; with files (rsq_simulate) it goes through two pinned staging buffers
+// per segment and a writer thread appends it to the FASTQ files while the GPU is busy with the next batch.
+struct FileWriter {
+	FILE *f[2] = {nullptr, nullptr};
+	std::thread th;
+	std::mutex m; std::condition_variable cv;
+	struct Job { int par; uint64_t bytes[2]; cudaEvent_t ready; };
+	std::deque<Job> q; bool stop = false; std::string error;
+	int free_slots = 2;
+	PinnedBuf *staging = nullptr;   // [2 parities][2 segments]
+	void run(){
+		while(true){
+			Job j;
+			{ std::unique_lock<std::mutex> l(m); cv.wait(l, [&]{ return stop || !q.empty(); }); if(q.empty()){ return; } j = q.front(); q.pop_front(); }
+			cudaEventSynchronize(j.ready);
+			for(int seg = 0; seg < 2; ++seg){
+				if(error.empty() && j.bytes[seg] && fwrite(staging[j.par * 2 + seg].p, 1, j.bytes[seg], f[seg]) != j.bytes[seg]){ error = "Could not write records to the output file"; }
+			}
+			{ std::lock_guard<std::mutex> l(m); ++free_slots; }
+			cv.notify_all();
+		}
+	}
+};
+
+static void simulate(rsq_engine &e, rsq_sim_report *rep){
+	if(!e.prepared){ throw std::runtime_error("rsq_engine_prepare has not been called"); }
+	cudaStream_t s = e.stream;
+	SimCtx &c = e.ctx;
+	e.downloaded = false; e.streamed_to_host = false;
+	e.spec_rounds = 0; e.spec_depth = 0;
+	e.out_bytes[0] = e.out_bytes[1] = 0; e.out_pairs = 0; e.out_draws = 0;
+	const bool meth = c.meth_loaded != 0;
+	// RSQ_SIM_PATH=serial keeps the one-warp-per-SimBlock kernel (parity tests run both); bisulfite runs always use it
+	const char *path = getenv("RSQ_SIM_PATH");
+	bool spec = !meth && !(path && std::string(path) == "serial");
+	// ---- batches: as many blocks as HBM holds speculation state, record slots and two output buffers for ----
+	int dev_sms = 0; RSQ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e.device));
+	const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);
+	const double reads_per_block = e.n_blocks_sim ? 2.0 * e.total_pairs / e.n_blocks_sim : 0.0;
+	const double rec_bytes = 2.0 * max_rl + 160.0;
+	auto unit_bytes = [&](uint32_t depth){
+		return 2.0 * (depth + 1) * sizeof(SpecSnap) + depth * (sizeof(ReadJob) + 8.0 * (3 * max_rl + 8 + kSpecMargin))
+		       + 1.2 * reads_per_block * (rec_bytes + 250.0) + 2.0 * 1.1 * reads_per_block * rec_bytes + 256.0;
+	};
+	size_t free_b = 0, total_b = 0; RSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+	const double budget = 0.85 * (static_cast<double>(free_b) + e.reusable_bytes());
+	uint32_t depth_cap = 32;
+	uint64_t per_batch = e.shard_n;
+	if(unit_bytes(32) * e.shard_n > budget){ depth_cap = 16; per_batch = std::max<uint64_t>(1024, static_cast<uint64_t>(budget / unit_bytes(16))); }
+	if(const char *env = getenv("RSQ_BATCH_UNITS")){ per_batch = std::max(1, atoi(env)); }
+	const uint32_t n_batches = e.shard_n ? static_cast<uint32_t>((e.shard_n + per_batch - 1) / per_batch) : 1;
+	const bool to_files = e.sink_files[0] != nullptr;
+	const bool stream_host = !to_files && n_batches > 1;
+	if(!e.copy_stream){ RSQ_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking)); }
+	for(int i = 0; i < 2; ++i){ if(!e.ev_out[i]){ RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_out[i], cudaEventDisableTiming)); RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_copied[i], cudaEventDisableTiming)); } }
+	FileWriter writer;
+	if(to_files){ writer.f[0] = e.sink_files[0]; writer.f[1] = e.sink_files[1]; writer.staging = e.h_staging; writer.th = std::thread([&]{ writer.run(); }); }
+	struct Joiner { FileWriter &w; bool on; ~Joiner(){ if(on && w.th.joinable()){ { std::lock_guard<std::mutex> l(w.m); w.stop = true; } w.cv.notify_all(); w.th.join(); } } } joiner{writer, to_files};
+	if(stream_host){
+		const double est = (e.total_pairs * (e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0) + e.adapter_only_pairs) * (max_rl * 2.0 + 90.0) * 1.02 + (1 << 20);
+		for(int seg = 0; seg < 2; ++seg){ e.h_out[seg].ensure(static_cast<size_t>(est)); }
+	}
+	float ms_sim = 0, ms_gather = 0;
+	for(uint32_t b = 0; b < n_batches; ++b){
+		const uint32_t u_begin = static_cast<uint32_t>(std::min<uint64_t>(e.shard_n, b * per_batch));
+		const uint32_t u_count = static_cast<uint32_t>(std::min<uint64_t>(per_batch, e.shard_n - u_begin));
+		const bool with_ao = e.shard_has_adapter_only && b + 1 == n_batches;
+		const int par = b & 1;
+		if(b >= 2){ RSQ_CUDA(cudaEventSynchronize(e.ev_copied[par])); }   // the copy of batch b-2 has left this device buffer
+		BatchResult res;
+		bool done = false;
+		if(spec){
+			done = simulate_spec_batch(e, u_begin, u_count, with_ao, depth_cap, par, res);
+			if(done){ e.spec_rounds += res.rounds; if(!e.spec_depth){ e.spec_depth = res.depth; } }
+		}
+		if(!done){ simulate_serial_batch(e, u_begin, u_count, with_ao, par, res); }
+		ms_sim += res.ms_sim; ms_gather += res.ms_gather;
+		if(to_files || stream_host){
+			RSQ_CUDA(cudaEventRecord(e.ev_out[par], s));
+			RSQ_CUDA(cudaStreamWaitEvent(e.copy_stream, e.ev_out[par], 0));
+			if(to_files){
+				{ std::unique_lock<std::mutex> l(writer.m); writer.cv.wait(l, [&]{ return writer.free_slots > 0; }); --writer.free_slots; }
+				for(int seg = 0; seg < 2; ++seg){
+					e.h_staging[par * 2 + seg].ensure(res.bytes[seg] + 1);
+					if(res.bytes[seg]){ RSQ_CUDA(cudaMemcpyAsync(e.h_staging[par * 2 + seg].p, e.d_out_batch[par][seg].p, res.bytes[seg], cudaMemcpyDeviceToHost, e.copy_stream)); }
+				}
+				RSQ_CUDA(cudaEventRecord(e.ev_copied[par], e.copy_stream));
+				{ std::lock_guard<std::mutex> l(writer.m); writer.q.push_back({par, {res.bytes[0], res.bytes[1]}, e.ev_copied[par]}); }
+				writer.cv.notify_all();
+			}
+			else{
+				for(int seg = 0; seg < 2; ++seg){
+					if(e.out_bytes[seg] + res.bytes[seg] + 1 > e.h_out[seg].cap){   // the estimate was too small: grow, keeping what is there
+						RSQ_CUDA(cudaStreamSynchronize(e.copy_stream));
+						PinnedBuf bigger; bigger.ensure(static_cast<size_t>((e.out_bytes[seg] + res.bytes[seg]) * 1.5) + (1 << 20));
+						std::memcpy(bigger.p, e.h_out[seg].p, e.out_bytes[seg]);
+						std::swap(bigger.p, e.h_out[seg].p); std::swap(bigger.cap, e.h_out[seg].cap);
+					}
+					if(res.bytes[seg]){ RSQ_CUDA(cudaMemcpyAsync(e.h_out[seg].p + e.out_bytes[seg], e.d_out_batch[par][seg].p, res.bytes[seg], cudaMemcpyDeviceToHost, e.copy_stream)); }
+				}
+				RSQ_CUDA(cudaEventRecord(e.ev_copied[par], e.copy_stream));
+			}
+		}
+		e.out_bytes[0] += res.bytes[0]; e.out_bytes[1] += res.bytes[1]; e.out_pairs += res.pairs; e.out_draws += res.draws;
+		e.last_par = par;
+	}
+	if(to_files || stream_host){
+		RSQ_CUDA(cudaStreamSynchronize(e.copy_stream));
+		if(to_files){
+			{ std::unique_lock<std::mutex> l(writer.m); writer.cv.wait(l, [&]{ return writer.free_slots == 2 && writer.q.empty(); }); }
+			if(!writer.error.empty()){ throw std::runtime_error(writer.error); }
+		}
+		e.streamed_to_host = true;
+	}
+	if(rep){ rep->ms_gather = ms_gather; }
 	fill_simulate_report(e, rep, ms_sim);
 }
 
@@ -1735,9 +1971,11 @@ static void download(rsq_engine &e, rsq_sim_report *rep){
 	cudaStream_t s = e.stream;
 	EventTimer tm(s);
 	tm.start();
-	for(int seg = 0; seg < 2; ++seg){
-		e.h_out[seg].ensure(e.out_bytes[seg] + 1);
-		if(e.out_bytes[seg]){ RSQ_CUDA(cudaMemcpyAsync(e.h_out[seg].p, e.d_out[seg].p, e.out_bytes[seg], cudaMemcpyDeviceToHost, s)); }
+	if(!e.streamed_to_host){   // single batch: its text is still on the device
+		for(int seg = 0; seg < 2; ++seg){
+			e.h_out[seg].ensure(e.out_bytes[seg] + 1);
+			if(e.out_bytes[seg]){ RSQ_CUDA(cudaMemcpyAsync(e.h_out[seg].p, e.d_out_batch[e.last_par][seg].p, e.out_bytes[seg], cudaMemcpyDeviceToHost, s)); }
+		}
 	}
 	const float ms = tm.stop();
 	if(rep){ rep->ms_download = ms; }
@@ -2044,9 +2282,13 @@ int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq
 	for(const char *path : {first_reads_path, second_reads_path}){ FILE *o = fopen(path, "wb"); if(!o){ set_error("Could not open '%s' for writing.", path); rsq_engine_destroy(e); return 1; } fclose(o); }
 	rsq_sim_report local; rsq_sim_report *rep = report ? report : &local;
 	int rc = rsq_engine_prepare(e, ref, opt, rep);
-	if(!rc){ rc = rsq_engine_simulate(e, rep); }
-	if(!rc){ rc = rsq_engine_download(e, rep); }
-	if(!rc){ rc = rsq_engine_write(e, first_reads_path, second_reads_path); }
+	if(!rc){
+		// the batches of the run are appended to the two files by a writer thread while the GPU works on the next one
+		e->sink_files[0] = fopen(first_reads_path, "ab"); e->sink_files[1] = fopen(second_reads_path, "ab");
+		if(!e->sink_files[0] || !e->sink_files[1]){ set_error("Could not open '%s' for writing.", e->sink_files[0] ? second_reads_path : first_reads_path); rc = 1; }
+		if(!rc){ rc = rsq_engine_simulate(e, rep); }
+		for(int seg = 0; seg < 2; ++seg){ if(e->sink_files[seg]){ if(fclose(e->sink_files[seg]) && !rc){ set_error("Could not write records to '%s'", seg ? second_reads_path : first_reads_path); rc = 1; } e->sink_files[seg] = nullptr; } }
+	}
 	if(rc){ remove(first_reads_path); remove(second_reads_path); }
 	rsq_engine_destroy(e);
 	return rc;

@@ -63,6 +63,19 @@ def test_serial_and_speculative_paths_bit_exact(rb, engine, golden, monkeypatch,
         assert rep.spec_depth == depth and rep.spec_rounds > 0
 
 
+@pytest.mark.parametrize("path,batch", [("spec", 7), ("spec", 64), ("serial", 5)])
+def test_block_batches_concatenate_to_the_whole_run(rb, engine, golden, monkeypatch, path, batch):
+    """Runs whose state does not fit HBM are simulated in batches of SimBlocks whose text is copied out behind each other
+    (RSQ_BATCH_UNITS forces small batches here): the bytes must not depend on the batch size."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    monkeypatch.setenv("RSQ_BATCH_UNITS", str(batch))
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    r1, r2, rep = _simulate(engine, ref, seed=42, coverage=20.0)
+    assert r1 == open(golden["r1"], "rb").read()
+    assert r2 == open(golden["r2"], "rb").read()
+    assert rep.pairs == r1.count(b"\n") // 4
+
+
 def test_methylation_golden_bit_exact(rb, engine, golden):
     """--methylation: bisulfite C->T conversions per unmethylated region (Simulator::CTConversion)."""
     ref = rb.Reference.load_fasta(golden["small_ref"])
@@ -130,7 +143,10 @@ def test_ref_bias_models_against_reference_binary(rb, engine, golden, oracle, wo
         engine.prepare(ref, seed=22, coverage=10.0, ref_bias_model=3, ref_bias_file=bias_file)
 
 
-def test_dropin_simulate_call_writes_files(rb, golden, workdir):
+@pytest.mark.parametrize("batch", [None, "9"])
+def test_dropin_simulate_call_writes_files(rb, golden, workdir, monkeypatch, batch):
+    if batch:
+        monkeypatch.setenv("RSQ_BATCH_UNITS", batch)   # several batches through the staging buffers and the writer thread
     prof = rb.Profile.load_flat(golden["flat"])
     ref = rb.Reference.load_fasta(golden["small_ref"])
     o1, o2 = os.path.join(workdir, "d1.fq"), os.path.join(workdir, "d2.fq")
