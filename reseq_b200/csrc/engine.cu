@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <condition_variable>
 #include <deque>
@@ -39,6 +40,16 @@ static void set_error(const char *fmt, ...){
 	char buf[2048];
 	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
 	g_last_error = buf;
+}
+
+// RSQ_TIMING=1: wall-clock stage log on stderr (host-side costs are invisible to the CUDA-event times of the report)
+static void stage_log(const char *what){
+	static const bool on = getenv("RSQ_TIMING") != nullptr;
+	if(!on){ return; }
+	static auto last = std::chrono::steady_clock::now();
+	const auto now = std::chrono::steady_clock::now();
+	fprintf(stderr, "[rsq timing] %-40s +%.3f s\n", what, std::chrono::duration<double>(now - last).count());
+	last = now;
 }
 
 #define RSQ_CUDA(call) do{ cudaError_t e_ = (call); if(e_ != cudaSuccess){ throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); } }while(0)
@@ -924,7 +935,8 @@ struct rsq_engine {
 	bool downloaded = false;
 	// batched output: device text of two batches in flight, copy stream, optional file sink (rsq_simulate)
 	DevBuf<unsigned char> d_out_batch[2][2];
-	PinnedBuf h_staging[4];
+	PinnedBuf h_ring[4]; cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
+	std::vector<char> h_big[2];   // text of runs that arrive in several batches (ordinary memory: pinning tens of GB takes longer than the run)
 	cudaStream_t copy_stream = nullptr; cudaEvent_t ev_out[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 	FILE *sink_files[2] = {nullptr, nullptr};
 	bool streamed_to_host = false; int last_par = 0;
@@ -938,7 +950,7 @@ struct rsq_engine {
 	uint32_t spec_rounds = 0, spec_depth = 0;
 	std::vector<cudaStream_t> spec_streams; std::vector<cudaEvent_t> spec_events;
 
-	~rsq_engine(){ for(int i = 0; i < 2; ++i){ if(ev_out[i]){ cudaEventDestroy(ev_out[i]); } if(ev_copied[i]){ cudaEventDestroy(ev_copied[i]); } } if(copy_stream){ cudaStreamDestroy(copy_stream); } for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
+	~rsq_engine(){ for(int i = 0; i < 4; ++i){ if(ev_ring[i]){ cudaEventDestroy(ev_ring[i]); } } for(int i = 0; i < 2; ++i){ if(ev_out[i]){ cudaEventDestroy(ev_out[i]); } if(ev_copied[i]){ cudaEventDestroy(ev_copied[i]); } } if(copy_stream){ cudaStreamDestroy(copy_stream); } for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
 };
 
 double rsq_engine::reusable_bytes() const {
@@ -1200,8 +1212,10 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	e.d_error_flag.zero(s);
 
 	// --- host: ReplaceN, ref-seq bias, pair counts (Simulator.cpp:2687-2743) ---
+	stage_log("prepare: start");
 	e.genome = ref_in;
 	e.genome.replace_n(opt.seed);
+	stage_log("prepare: genome copy + ReplaceN");
 	Genome &g = e.genome;
 	// FragmentDistributionStats::UpdateRefSeqBias (FragmentDistributionStats.cpp:3352-3502)
 	e.run_ref_seq_bias = p.ref_seq_bias;
@@ -1283,6 +1297,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	e.sys_gc_range = static_cast<uint32_t>((sum_read_length + reads / 2) / reads) / 2;
 
 	// --- upload reference ---
+	stage_log("prepare: ref bias, counts");
 	tm.start();
 	std::vector<uint64_t> seq_off; std::vector<uint32_t> seq_len, name_off{0}; std::string names;
 	uint64_t total = 0;
@@ -1293,6 +1308,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	e.h_seq_off = seq_off;
 	e.h_ref_stage.ensure(total + 1);
 	for(size_t i = 0; i < g.seqs.size(); ++i){ std::memcpy(e.h_ref_stage.p + seq_off[i], g.seqs[i].data(), g.seqs[i].size()); }
+	stage_log("prepare: pinned staging of the reference");
 	e.d_ref.alloc(total + 1);
 	RSQ_CUDA(cudaMemcpyAsync(e.d_ref.p, e.h_ref_stage.p, total, cudaMemcpyHostToDevice, s));
 	e.d_gc_prefix.alloc(total + g.seqs.size() + 1);
@@ -1498,6 +1514,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	RSQ_CUDA(cudaStreamSynchronize(s));
 	ms_bias += tm.stop();
 	if(rep){ rep->ms_bias = ms_bias; rep->bias_normalization = e.norm.bias_normalization; rep->ms_syserr = ms_syserr; }
+	stage_log("prepare: device stages (bias, master stream, systematic errors)");
 	const uint32_t sc = opt.shard_count ? opt.shard_count : 1, si = opt.shard_index;
 	if(si >= sc){ throw std::runtime_error("shard_index out of range"); }
 	e.shard_first = static_cast<uint64_t>(e.n_blocks_sim) * si / sc;
@@ -1848,25 +1865,29 @@ static void simulate_serial_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_co
 	}
 }
 
-// Host side of the output: batches arrive in order.  Without files (engine API) the text of every batch is copied to the
-// pinned buffers h_out right behind the previous one; with files (rsq_simulate) it goes through two pinned staging buffers
-// per segment and a writer thread appends it to the FASTQ files while the GPU is busy with the next batch.
-struct FileWriter {
-	FILE *f[2] = {nullptr, nullptr};
+// Host side of the output: the text of the batches arrives in order, in chunks of <= kRingChunk bytes that travel through a
+// small ring of pinned staging buffers (pinning host memory costs ~0.6 s per GB, so the ring is allocated once and kept small).
+// A writer thread takes the chunks out of the ring: appended to the FASTQ files (rsq_simulate), or copied behind each other
+// into ordinary host memory (engine API, runs of several batches) - while the GPU is busy with the next batch.
+constexpr size_t kRingChunk = 64u << 20;
+constexpr int kRingSlots = 4;
+struct ChunkWriter {
+	FILE *f[2] = {nullptr, nullptr};            // file sink
+	std::vector<char> *mem[2] = {nullptr, nullptr};   // memory sink (sized in advance)
 	std::thread th;
 	std::mutex m; std::condition_variable cv;
-	struct Job { int par; uint64_t bytes[2]; cudaEvent_t ready; };
+	struct Job { int slot, seg; uint64_t bytes, dst_off; cudaEvent_t ready; };
 	std::deque<Job> q; bool stop = false; std::string error;
-	int free_slots = 2;
-	PinnedBuf *staging = nullptr;   // [2 parities][2 segments]
+	int free_slots = kRingSlots;
+	bool discard = getenv("RSQ_DISCARD_OUTPUT") != nullptr;   // throughput probes of runs larger than the disk: the text reaches host memory, not the file
+	PinnedBuf *ring = nullptr;
 	void run(){
 		while(true){
 			Job j;
 			{ std::unique_lock<std::mutex> l(m); cv.wait(l, [&]{ return stop || !q.empty(); }); if(q.empty()){ return; } j = q.front(); q.pop_front(); }
 			cudaEventSynchronize(j.ready);
-			for(int seg = 0; seg < 2; ++seg){
-				if(error.empty() && j.bytes[seg] && fwrite(staging[j.par * 2 + seg].p, 1, j.bytes[seg], f[seg]) != j.bytes[seg]){ error = "Could not write records to the output file"; }
-			}
+			if(mem[j.seg]){ std::memcpy(mem[j.seg]->data() + j.dst_off, ring[j.slot].p, j.bytes); }
+			else if(!discard && error.empty() && fwrite(ring[j.slot].p, 1, j.bytes, f[j.seg]) != j.bytes){ error = "Could not write records to the output file"; }
 			{ std::lock_guard<std::mutex> l(m); ++free_slots; }
 			cv.notify_all();
 		}
@@ -1904,13 +1925,21 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	const bool stream_host = !to_files && n_batches > 1;
 	if(!e.copy_stream){ RSQ_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking)); }
 	for(int i = 0; i < 2; ++i){ if(!e.ev_out[i]){ RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_out[i], cudaEventDisableTiming)); RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_copied[i], cudaEventDisableTiming)); } }
-	FileWriter writer;
-	if(to_files){ writer.f[0] = e.sink_files[0]; writer.f[1] = e.sink_files[1]; writer.staging = e.h_staging; writer.th = std::thread([&]{ writer.run(); }); }
-	struct Joiner { FileWriter &w; bool on; ~Joiner(){ if(on && w.th.joinable()){ { std::lock_guard<std::mutex> l(w.m); w.stop = true; } w.cv.notify_all(); w.th.join(); } } } joiner{writer, to_files};
-	if(stream_host){
-		const double est = (e.total_pairs * (e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0) + e.adapter_only_pairs) * (max_rl * 2.0 + 90.0) * 1.02 + (1 << 20);
-		for(int seg = 0; seg < 2; ++seg){ e.h_out[seg].ensure(static_cast<size_t>(est)); }
+	ChunkWriter writer;
+	const bool streaming = to_files || stream_host;
+	if(streaming){
+		for(int i = 0; i < kRingSlots; ++i){ e.h_ring[i].ensure(kRingChunk); if(!e.ev_ring[i]){ RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_ring[i], cudaEventDisableTiming)); } }
+		writer.ring = e.h_ring;
+		if(to_files){ writer.f[0] = e.sink_files[0]; writer.f[1] = e.sink_files[1]; }
+		else{
+			const double est = (e.total_pairs * (e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0) + e.adapter_only_pairs) * (max_rl * 2.0 + 90.0) * 1.02 + (1 << 20);
+			for(int seg = 0; seg < 2; ++seg){ e.h_big[seg].resize(static_cast<size_t>(est)); writer.mem[seg] = &e.h_big[seg]; }
+		}
+		writer.th = std::thread([&]{ writer.run(); });
 	}
+	struct Joiner { ChunkWriter &w; bool on; ~Joiner(){ if(on && w.th.joinable()){ { std::lock_guard<std::mutex> l(w.m); w.stop = true; } w.cv.notify_all(); w.th.join(); } } } joiner{writer, streaming};
+	auto drain = [&]{ std::unique_lock<std::mutex> l(writer.m); writer.cv.wait(l, [&]{ return writer.free_slots == kRingSlots && writer.q.empty(); }); };
+	int next_slot = 0;
 	float ms_sim = 0, ms_gather = 0;
 	for(uint32_t b = 0; b < n_batches; ++b){
 		const uint32_t u_begin = static_cast<uint32_t>(std::min<uint64_t>(e.shard_n, b * per_batch));
@@ -1920,51 +1949,48 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 		if(b >= 2){ RSQ_CUDA(cudaEventSynchronize(e.ev_copied[par])); }   // the copy of batch b-2 has left this device buffer
 		BatchResult res;
 		bool done = false;
+		stage_log("simulate: batch start");
 		if(spec){
 			done = simulate_spec_batch(e, u_begin, u_count, with_ao, depth_cap, par, res);
 			if(done){ e.spec_rounds += res.rounds; if(!e.spec_depth){ e.spec_depth = res.depth; } }
 		}
 		if(!done){ simulate_serial_batch(e, u_begin, u_count, with_ao, par, res); }
 		ms_sim += res.ms_sim; ms_gather += res.ms_gather;
-		if(to_files || stream_host){
+		stage_log("simulate: batch kernels done");
+		if(streaming){
 			RSQ_CUDA(cudaEventRecord(e.ev_out[par], s));
 			RSQ_CUDA(cudaStreamWaitEvent(e.copy_stream, e.ev_out[par], 0));
-			if(to_files){
-				{ std::unique_lock<std::mutex> l(writer.m); writer.cv.wait(l, [&]{ return writer.free_slots > 0; }); --writer.free_slots; }
-				for(int seg = 0; seg < 2; ++seg){
-					e.h_staging[par * 2 + seg].ensure(res.bytes[seg] + 1);
-					if(res.bytes[seg]){ RSQ_CUDA(cudaMemcpyAsync(e.h_staging[par * 2 + seg].p, e.d_out_batch[par][seg].p, res.bytes[seg], cudaMemcpyDeviceToHost, e.copy_stream)); }
+			for(int seg = 0; seg < 2; ++seg){
+				if(writer.mem[seg] && e.out_bytes[seg] + res.bytes[seg] > writer.mem[seg]->size()){   // the estimate was too small: grow once the writer is idle
+					drain();
+					writer.mem[seg]->resize(static_cast<size_t>((e.out_bytes[seg] + res.bytes[seg]) * 1.3) + (1 << 20));
 				}
-				RSQ_CUDA(cudaEventRecord(e.ev_copied[par], e.copy_stream));
-				{ std::lock_guard<std::mutex> l(writer.m); writer.q.push_back({par, {res.bytes[0], res.bytes[1]}, e.ev_copied[par]}); }
-				writer.cv.notify_all();
-			}
-			else{
-				for(int seg = 0; seg < 2; ++seg){
-					if(e.out_bytes[seg] + res.bytes[seg] + 1 > e.h_out[seg].cap){   // the estimate was too small: grow, keeping what is there
-						RSQ_CUDA(cudaStreamSynchronize(e.copy_stream));
-						PinnedBuf bigger; bigger.ensure(static_cast<size_t>((e.out_bytes[seg] + res.bytes[seg]) * 1.5) + (1 << 20));
-						std::memcpy(bigger.p, e.h_out[seg].p, e.out_bytes[seg]);
-						std::swap(bigger.p, e.h_out[seg].p); std::swap(bigger.cap, e.h_out[seg].cap);
-					}
-					if(res.bytes[seg]){ RSQ_CUDA(cudaMemcpyAsync(e.h_out[seg].p + e.out_bytes[seg], e.d_out_batch[par][seg].p, res.bytes[seg], cudaMemcpyDeviceToHost, e.copy_stream)); }
+				for(uint64_t off = 0; off < res.bytes[seg]; off += kRingChunk){
+					const uint64_t n = std::min<uint64_t>(kRingChunk, res.bytes[seg] - off);
+					{ std::unique_lock<std::mutex> l(writer.m); writer.cv.wait(l, [&]{ return writer.free_slots > 0; }); --writer.free_slots; }
+					const int slot = next_slot; next_slot = (next_slot + 1) % kRingSlots;   // jobs complete in order, so the oldest slot is the free one
+					RSQ_CUDA(cudaMemcpyAsync(e.h_ring[slot].p, e.d_out_batch[par][seg].p + off, n, cudaMemcpyDeviceToHost, e.copy_stream));
+					RSQ_CUDA(cudaEventRecord(e.ev_ring[slot], e.copy_stream));
+					{ std::lock_guard<std::mutex> l(writer.m); writer.q.push_back({slot, seg, n, e.out_bytes[seg] + off, e.ev_ring[slot]}); }
+					writer.cv.notify_all();
 				}
-				RSQ_CUDA(cudaEventRecord(e.ev_copied[par], e.copy_stream));
 			}
+			RSQ_CUDA(cudaEventRecord(e.ev_copied[par], e.copy_stream));
 		}
 		e.out_bytes[0] += res.bytes[0]; e.out_bytes[1] += res.bytes[1]; e.out_pairs += res.pairs; e.out_draws += res.draws;
 		e.last_par = par;
 	}
-	if(to_files || stream_host){
+	stage_log("simulate: last batch delivered");
+	if(streaming){
 		RSQ_CUDA(cudaStreamSynchronize(e.copy_stream));
-		if(to_files){
-			{ std::unique_lock<std::mutex> l(writer.m); writer.cv.wait(l, [&]{ return writer.free_slots == 2 && writer.q.empty(); }); }
-			if(!writer.error.empty()){ throw std::runtime_error(writer.error); }
-		}
+		drain();
+		if(!writer.error.empty()){ throw std::runtime_error(writer.error); }
 		e.streamed_to_host = true;
 	}
+	stage_log("simulate: copies and writer drained");
 	if(rep){ rep->ms_gather = ms_gather; }
 	fill_simulate_report(e, rep, ms_sim);
+	stage_log("simulate: report");
 }
 
 static void download(rsq_engine &e, rsq_sim_report *rep){
@@ -2255,7 +2281,7 @@ int rsq_engine_output(const rsq_engine *engine, int segment, const char **data, 
 	RSQ_TRY
 	if(!engine->downloaded){ throw std::runtime_error("rsq_engine_download has not been called"); }
 	if(segment < 0 || segment > 1){ throw std::runtime_error("segment must be 0 or 1"); }
-	*data = engine->h_out[segment].p; *bytes = engine->out_bytes[segment];
+	*data = engine->streamed_to_host ? engine->h_big[segment].data() : engine->h_out[segment].p; *bytes = engine->out_bytes[segment];
 	return 0;
 	RSQ_CATCH(1)
 }
@@ -2267,7 +2293,7 @@ int rsq_engine_write(const rsq_engine *engine, const char *first_reads_path, con
 	for(int seg = 0; seg < 2; ++seg){
 		FILE *o = fopen(paths[seg], "ab");
 		if(!o){ throw std::runtime_error(std::string("Could not open '") + paths[seg] + "' for writing."); }
-		const size_t w = fwrite(engine->h_out[seg].p, 1, engine->out_bytes[seg], o);
+		const size_t w = fwrite(engine->streamed_to_host ? engine->h_big[seg].data() : engine->h_out[seg].p, 1, engine->out_bytes[seg], o);
 		fclose(o);
 		if(w != engine->out_bytes[seg]){ throw std::runtime_error(std::string("Could not write records to '") + paths[seg] + "'"); }
 	}
@@ -2277,8 +2303,10 @@ int rsq_engine_write(const rsq_engine *engine, const char *first_reads_path, con
 
 int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq_sim_options *opt, int device,
                  const char *first_reads_path, const char *second_reads_path, rsq_sim_report *report){
+	stage_log("rsq_simulate: enter");
 	rsq_engine *e = rsq_engine_create(profile, device);
 	if(!e){ return 1; }
+	stage_log("rsq_simulate: engine created");
 	for(const char *path : {first_reads_path, second_reads_path}){ FILE *o = fopen(path, "wb"); if(!o){ set_error("Could not open '%s' for writing.", path); rsq_engine_destroy(e); return 1; } fclose(o); }
 	rsq_sim_report local; rsq_sim_report *rep = report ? report : &local;
 	int rc = rsq_engine_prepare(e, ref, opt, rep);
@@ -2291,6 +2319,7 @@ int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq
 	}
 	if(rc){ remove(first_reads_path); remove(second_reads_path); }
 	rsq_engine_destroy(e);
+	stage_log("rsq_simulate: engine destroyed");
 	return rc;
 }
 

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--seqs", type=int, default=4)
     ap.add_argument("--coverage", type=float, default=30.0)
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--files", action="store_true", help="drop-in call rsq_simulate (text streamed through the writer thread; set RSQ_DISCARD_OUTPUT=1 for runs larger than the disk)")
     args = ap.parse_args()
     tmp = tempfile.mkdtemp(prefix="rsq_scale_")
     prof = rb.Profile.load_flat(bench.unxz(bench.PROFILE + ".flat.xz", tmp))
@@ -36,6 +37,17 @@ def main():
         ref = rb.Reference.from_memory([f"chr{i + 1} synthetic" for i in range(len(seqs))], [s.encode() for s in seqs])
         t_gen = time.perf_counter() - t0
         best = None
+        if args.files:
+            out = [os.path.join(tmp, "probe_R1.fq"), os.path.join(tmp, "probe_R2.fq")]
+            t0 = time.perf_counter()
+            rep = rb.simulate(prof, ref, out[0], out[1], seed=42, coverage=args.coverage).as_dict()
+            wall = time.perf_counter() - t0
+            sizes_on_disk = [os.path.getsize(o) for o in out]
+            for o in out:
+                os.remove(o)
+            print(json.dumps({"mbp": mbp, "seqs": args.seqs, "coverage": args.coverage, "gen_ref_s": round(t_gen, 1), "wall_rsq_simulate_s": round(wall, 2),
+                              "pairs_per_s_e2e": round(rep["pairs"] / wall), "bytes_on_disk": sizes_on_disk, "report": rep}), flush=True)
+            continue
         for _ in range(args.repeat):
             t0 = time.perf_counter()
             eng.prepare(ref, seed=42, coverage=args.coverage)
