@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <chrono>
 #include <cstring>
+#include <sys/mman.h>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -497,15 +498,13 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 	const uint32_t maxn = __reduce_max_sync(0xffffffffu, n0);
 	if(maxn == 0){ zero = true; return 0; }
 	const uint32_t n4 = (maxn + 3u) & ~3u;
-	const uint32_t shift = maxn <= 8u ? 3u : (maxn <= 16u ? 4u : 5u);   // lanes per read: 8, 16 or 32
-	const uint32_t gs = 1u << shift, per = 32u >> shift;
-	const uint32_t sub = lane >> shift, i = lane & (gs - 1u);
-	const unsigned gmask = per == 1u ? 1u : (per == 2u ? 3u : 15u);
 	__syncwarp();
-	if(n_rows <= 16u){
-		// few reads per warp: 32 / n_rows lanes work on every read at the same time (one trip of shuffles, all reads in flight together)
-		const uint32_t lpr_shift = n_rows <= 8u ? 2u : 1u, lpr = 1u << lpr_shift;   // n_rows is 8 or 16
-		const uint32_t src = lane >> lpr_shift, i = lane & (lpr - 1u);
+	// 32 / rows-per-pass lanes work on every read of a pass at the same time (one trip of shuffles, all reads of the pass in
+	// flight together); 8 or 16 reads per pass, 32 reads per warp take two passes of 16
+	const uint32_t pass_rows = n_rows <= 8u ? 8u : 16u;
+	const uint32_t lpr_shift = pass_rows == 8u ? 2u : 1u, lpr = 1u << lpr_shift;
+	for(uint32_t first = 0; first < n_rows; first += pass_rows){
+		const uint32_t src = first + (lane >> lpr_shift), i = lane & (lpr - 1u);
 		const uint32_t sn0 = __shfl_sync(0xffffffffu, n0, src);
 		const uint32_t s0 = __shfl_sync(0xffffffffu, o0, src), s1 = __shfl_sync(0xffffffffu, o1, src);
 		const uint32_t s2 = __shfl_sync(0xffffffffu, o2, src), s3 = __shfl_sync(0xffffffffu, o3, src);
@@ -514,28 +513,6 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 		if((amask >> src) & 1u){
 #pragma unroll 4
 			for(uint32_t idx = i; idx < n4; idx += lpr){
-				double p = 0.0;
-				if(idx < sn0){
-					p = __ldg(t.blob + s0 + idx);
-					p = mul_rn(p, __ldg(t.blob + s1 + idx));
-					p = mul_rn(p, __ldg(t.blob + s2 + idx));
-					if(four){ p = mul_rn(p, __ldg(t.blob + s3 + idx)); }
-				}
-				row[idx] = p;
-			}
-		}
-	}
-	else{
-#pragma unroll 4
-		for(uint32_t base = 0; base < n_rows; base += per){
-			if(((amask >> base) & gmask) == 0u){ continue; }
-			const uint32_t src = base + sub;
-			const uint32_t sn0 = __shfl_sync(0xffffffffu, n0, src);
-			const uint32_t s0 = __shfl_sync(0xffffffffu, o0, src), s1 = __shfl_sync(0xffffffffu, o1, src);
-			const uint32_t s2 = __shfl_sync(0xffffffffu, o2, src), s3 = __shfl_sync(0xffffffffu, o3, src);
-			const bool four = __shfl_sync(0xffffffffu, nm, src) > 3u;
-			double *row = buf + src * stride;
-			for(uint32_t idx = i; idx < n4; idx += gs){
 				double p = 0.0;
 				if(idx < sn0){
 					p = __ldg(t.blob + s0 + idx);
@@ -858,6 +835,22 @@ k_error_model(SimCtx c, const EmRecord *recs, uint32_t n_recs, uint32_t batch_si
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+// Large host buffer that is neither pinned nor zero-filled (either costs longer than a run at this size); 2 MB pages where the kernel grants them.
+struct HostBig {
+	char *p = nullptr; size_t cap = 0;
+	HostBig() = default; HostBig(const HostBig &) = delete; HostBig &operator=(const HostBig &) = delete;
+	~HostBig(){ free(p); }
+	char *data(){ return p; } const char *data() const { return p; } size_t size() const { return cap; }
+	void resize(size_t n){   // keeps the old content
+		if(n <= cap){ return; }
+		void *q = nullptr;
+		if(posix_memalign(&q, 2u << 20, (n + (2u << 20) - 1) & ~static_cast<size_t>((2u << 20) - 1))){ throw std::runtime_error("out of host memory for the FASTQ text"); }
+		madvise(q, n, MADV_HUGEPAGE);
+		if(p){ std::memcpy(q, p, cap); free(p); }
+		p = static_cast<char *>(q); cap = n;
+	}
+};
+
 struct PinnedBuf {
 	char *p = nullptr; size_t cap = 0;
 	~PinnedBuf(){ if(p){ cudaFreeHost(p); } }
@@ -936,8 +929,8 @@ struct rsq_engine {
 	// batched output: device text of two batches in flight, copy stream, optional file sink (rsq_simulate)
 	DevBuf<unsigned char> d_out_batch[2][2];
 	PinnedBuf h_ring[4]; cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
-	std::vector<char> h_big[2];   // text of runs that arrive in several batches (ordinary memory: pinning tens of GB takes longer than the run)
-	cudaStream_t copy_stream = nullptr; cudaEvent_t ev_out[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+	HostBig h_big[2];   // text of runs that arrive in several batches (ordinary memory: pinning tens of GB takes longer than the run)
+	cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr; cudaEvent_t ev_out[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 	FILE *sink_files[2] = {nullptr, nullptr};
 	bool streamed_to_host = false; int last_par = 0;
 	double reusable_bytes() const;
@@ -950,7 +943,7 @@ struct rsq_engine {
 	uint32_t spec_rounds = 0, spec_depth = 0;
 	std::vector<cudaStream_t> spec_streams; std::vector<cudaEvent_t> spec_events;
 
-	~rsq_engine(){ for(int i = 0; i < 4; ++i){ if(ev_ring[i]){ cudaEventDestroy(ev_ring[i]); } } for(int i = 0; i < 2; ++i){ if(ev_out[i]){ cudaEventDestroy(ev_out[i]); } if(ev_copied[i]){ cudaEventDestroy(ev_copied[i]); } } if(copy_stream){ cudaStreamDestroy(copy_stream); } for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
+	~rsq_engine(){ for(int i = 0; i < 4; ++i){ if(ev_ring[i]){ cudaEventDestroy(ev_ring[i]); } } for(int i = 0; i < 2; ++i){ if(ev_out[i]){ cudaEventDestroy(ev_out[i]); } if(ev_copied[i]){ cudaEventDestroy(ev_copied[i]); } } if(copy_stream){ cudaStreamDestroy(copy_stream); } if(copy_stream2){ cudaStreamDestroy(copy_stream2); } for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
 };
 
 double rsq_engine::reusable_bytes() const {
@@ -1676,7 +1669,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 		sp.scan_budget = budget > 4.0e9 ? 4000000000u : static_cast<uint32_t>(budget);
 		// reads per warp: as few as keep all reads of the round resident at once
 		const uint64_t reads = active * best_d;
-		lanes = reads <= warps_cap * 8 ? 8 : 16;   // 32 reads per warp (one lane each in every phase) measured slower than 16 at every size
+		lanes = reads <= warps_cap * 8 ? 8 : (reads <= warps_cap * 16 ? 16 : 32);   // 32 once the reads of a round no longer fit one wave anyway
 		if(fixed_lanes){ lanes = fixed_lanes >= 32 ? 32 : (fixed_lanes >= 16 ? 16 : 8); }
 	};
 	choose(sp.n_units, 0.95);
@@ -1865,30 +1858,49 @@ static void simulate_serial_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_co
 	}
 }
 
-// Host side of the output: the text of the batches arrives in order, in chunks of <= kRingChunk bytes that travel through a
-// small ring of pinned staging buffers (pinning host memory costs ~0.6 s per GB, so the ring is allocated once and kept small).
-// A writer thread takes the chunks out of the ring: appended to the FASTQ files (rsq_simulate), or copied behind each other
-// into ordinary host memory (engine API, runs of several batches) - while the GPU is busy with the next batch.
+// Host side of the output: the text of the batches arrives in order.  A writer thread copies it out of the device buffers in
+// chunks of <= kRingChunk bytes through a small ring of pinned staging buffers (pinning host memory costs ~0.6 s per GB, so the
+// ring is allocated once and kept small; the copy of chunk k+1 runs while chunk k is consumed) and appends the chunks to the
+// FASTQ files (rsq_simulate) or copies them behind each other into ordinary host memory (engine API, runs of several batches)
+// - all of it while the GPU is busy with the next batch.
 constexpr size_t kRingChunk = 64u << 20;
 constexpr int kRingSlots = 4;
-struct ChunkWriter {
-	FILE *f[2] = {nullptr, nullptr};            // file sink
-	std::vector<char> *mem[2] = {nullptr, nullptr};   // memory sink (sized in advance)
+struct ChunkWriter {   // one per segment (first / second reads): two files, two threads
+	int device = 0;
+	cudaStream_t copy_stream = nullptr;
+	FILE *f = nullptr;                  // file sink
+	HostBig *mem = nullptr;             // memory sink (sized in advance)
 	std::thread th;
 	std::mutex m; std::condition_variable cv;
-	struct Job { int slot, seg; uint64_t bytes, dst_off; cudaEvent_t ready; };
-	std::deque<Job> q; bool stop = false; std::string error;
-	int free_slots = kRingSlots;
+	struct Batch { const unsigned char *src; uint64_t bytes, dst_off; cudaEvent_t ready; };
+	std::deque<Batch> q; bool stop = false; std::string error;
+	uint64_t batches_done = 0;
 	bool discard = getenv("RSQ_DISCARD_OUTPUT") != nullptr;   // throughput probes of runs larger than the disk: the text reaches host memory, not the file
-	PinnedBuf *ring = nullptr;
+	PinnedBuf *ring = nullptr; cudaEvent_t *ev = nullptr; int n_slots = 2;
+	void consume(int slot, uint64_t n, uint64_t dst){
+		if(cudaEventSynchronize(ev[slot]) != cudaSuccess){ error = "copying FASTQ text to the host failed"; return; }
+		if(mem){ std::memcpy(mem->data() + dst, ring[slot].p, n); }
+		else if(!discard && error.empty() && fwrite(ring[slot].p, 1, n, f) != n){ error = "Could not write records to the output file"; }
+	}
 	void run(){
+		cudaSetDevice(device);
 		while(true){
-			Job j;
+			Batch j;
 			{ std::unique_lock<std::mutex> l(m); cv.wait(l, [&]{ return stop || !q.empty(); }); if(q.empty()){ return; } j = q.front(); q.pop_front(); }
-			cudaEventSynchronize(j.ready);
-			if(mem[j.seg]){ std::memcpy(mem[j.seg]->data() + j.dst_off, ring[j.slot].p, j.bytes); }
-			else if(!discard && error.empty() && fwrite(ring[j.slot].p, 1, j.bytes, f[j.seg]) != j.bytes){ error = "Could not write records to the output file"; }
-			{ std::lock_guard<std::mutex> l(m); ++free_slots; }
+			cudaStreamWaitEvent(copy_stream, j.ready, 0);
+			struct Piece { int slot; uint64_t n, dst; };
+			std::deque<Piece> inflight;
+			int slot = 0;
+			for(uint64_t off = 0; off < j.bytes; off += kRingChunk){
+				const uint64_t n = std::min<uint64_t>(kRingChunk, j.bytes - off);
+				if(static_cast<int>(inflight.size()) == n_slots){ const Piece p = inflight.front(); inflight.pop_front(); consume(p.slot, p.n, p.dst); }
+				if(cudaMemcpyAsync(ring[slot].p, j.src + off, n, cudaMemcpyDeviceToHost, copy_stream) != cudaSuccess){ error = "copying FASTQ text to the host failed"; }
+				cudaEventRecord(ev[slot], copy_stream);
+				inflight.push_back({slot, n, j.dst_off + off});
+				slot = (slot + 1) % n_slots;
+			}
+			while(!inflight.empty()){ const Piece p = inflight.front(); inflight.pop_front(); consume(p.slot, p.n, p.dst); }
+			{ std::lock_guard<std::mutex> l(m); ++batches_done; }
 			cv.notify_all();
 		}
 	}
@@ -1925,28 +1937,29 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	const bool stream_host = !to_files && n_batches > 1;
 	if(!e.copy_stream){ RSQ_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking)); }
 	for(int i = 0; i < 2; ++i){ if(!e.ev_out[i]){ RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_out[i], cudaEventDisableTiming)); RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_copied[i], cudaEventDisableTiming)); } }
-	ChunkWriter writer;
+	ChunkWriter writer[2];
 	const bool streaming = to_files || stream_host;
 	if(streaming){
+		if(!e.copy_stream2){ RSQ_CUDA(cudaStreamCreateWithFlags(&e.copy_stream2, cudaStreamNonBlocking)); }
 		for(int i = 0; i < kRingSlots; ++i){ e.h_ring[i].ensure(kRingChunk); if(!e.ev_ring[i]){ RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_ring[i], cudaEventDisableTiming)); } }
-		writer.ring = e.h_ring;
-		if(to_files){ writer.f[0] = e.sink_files[0]; writer.f[1] = e.sink_files[1]; }
-		else{
-			const double est = (e.total_pairs * (e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0) + e.adapter_only_pairs) * (max_rl * 2.0 + 90.0) * 1.02 + (1 << 20);
-			for(int seg = 0; seg < 2; ++seg){ e.h_big[seg].resize(static_cast<size_t>(est)); writer.mem[seg] = &e.h_big[seg]; }
+		const double est = (e.total_pairs * (e.n_blocks_sim ? static_cast<double>(e.shard_n) / e.n_blocks_sim : 0.0) + e.adapter_only_pairs) * (max_rl * 2.0 + 90.0) * 1.02 + (1 << 20);
+		for(int seg = 0; seg < 2; ++seg){
+			ChunkWriter &w = writer[seg];
+			w.ring = e.h_ring + 2 * seg; w.ev = e.ev_ring + 2 * seg; w.device = e.device; w.copy_stream = seg ? e.copy_stream2 : e.copy_stream;
+			if(to_files){ w.f = e.sink_files[seg]; }
+			else{ e.h_big[seg].resize(static_cast<size_t>(est)); w.mem = &e.h_big[seg]; }
+			w.th = std::thread([&w]{ w.run(); });
 		}
-		writer.th = std::thread([&]{ writer.run(); });
 	}
-	struct Joiner { ChunkWriter &w; bool on; ~Joiner(){ if(on && w.th.joinable()){ { std::lock_guard<std::mutex> l(w.m); w.stop = true; } w.cv.notify_all(); w.th.join(); } } } joiner{writer, streaming};
-	auto drain = [&]{ std::unique_lock<std::mutex> l(writer.m); writer.cv.wait(l, [&]{ return writer.free_slots == kRingSlots && writer.q.empty(); }); };
-	int next_slot = 0;
+	struct Joiner { ChunkWriter *w; bool on; ~Joiner(){ for(int seg = 0; on && seg < 2; ++seg){ if(w[seg].th.joinable()){ { std::lock_guard<std::mutex> l(w[seg].m); w[seg].stop = true; } w[seg].cv.notify_all(); w[seg].th.join(); } } } } joiner{writer, streaming};
+	auto wait_batches = [&](uint64_t n){ for(int seg = 0; seg < 2; ++seg){ std::unique_lock<std::mutex> l(writer[seg].m); writer[seg].cv.wait(l, [&]{ return writer[seg].batches_done >= n; }); } };
 	float ms_sim = 0, ms_gather = 0;
 	for(uint32_t b = 0; b < n_batches; ++b){
 		const uint32_t u_begin = static_cast<uint32_t>(std::min<uint64_t>(e.shard_n, b * per_batch));
 		const uint32_t u_count = static_cast<uint32_t>(std::min<uint64_t>(per_batch, e.shard_n - u_begin));
 		const bool with_ao = e.shard_has_adapter_only && b + 1 == n_batches;
 		const int par = b & 1;
-		if(b >= 2){ RSQ_CUDA(cudaEventSynchronize(e.ev_copied[par])); }   // the copy of batch b-2 has left this device buffer
+		if(streaming && b >= 2){ wait_batches(b - 1); }   // the text of batch b-2 has left this device buffer
 		BatchResult res;
 		bool done = false;
 		stage_log("simulate: batch start");
@@ -1959,32 +1972,24 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 		stage_log("simulate: batch kernels done");
 		if(streaming){
 			RSQ_CUDA(cudaEventRecord(e.ev_out[par], s));
-			RSQ_CUDA(cudaStreamWaitEvent(e.copy_stream, e.ev_out[par], 0));
 			for(int seg = 0; seg < 2; ++seg){
-				if(writer.mem[seg] && e.out_bytes[seg] + res.bytes[seg] > writer.mem[seg]->size()){   // the estimate was too small: grow once the writer is idle
-					drain();
-					writer.mem[seg]->resize(static_cast<size_t>((e.out_bytes[seg] + res.bytes[seg]) * 1.3) + (1 << 20));
+				ChunkWriter &w = writer[seg];
+				if(w.mem && e.out_bytes[seg] + res.bytes[seg] > w.mem->size()){   // the estimate was too small: grow once the writer is idle
+					wait_batches(b);
+					w.mem->resize(static_cast<size_t>((e.out_bytes[seg] + res.bytes[seg]) * 1.3) + (1 << 20));
 				}
-				for(uint64_t off = 0; off < res.bytes[seg]; off += kRingChunk){
-					const uint64_t n = std::min<uint64_t>(kRingChunk, res.bytes[seg] - off);
-					{ std::unique_lock<std::mutex> l(writer.m); writer.cv.wait(l, [&]{ return writer.free_slots > 0; }); --writer.free_slots; }
-					const int slot = next_slot; next_slot = (next_slot + 1) % kRingSlots;   // jobs complete in order, so the oldest slot is the free one
-					RSQ_CUDA(cudaMemcpyAsync(e.h_ring[slot].p, e.d_out_batch[par][seg].p + off, n, cudaMemcpyDeviceToHost, e.copy_stream));
-					RSQ_CUDA(cudaEventRecord(e.ev_ring[slot], e.copy_stream));
-					{ std::lock_guard<std::mutex> l(writer.m); writer.q.push_back({slot, seg, n, e.out_bytes[seg] + off, e.ev_ring[slot]}); }
-					writer.cv.notify_all();
-				}
+				ChunkWriter::Batch job{e.d_out_batch[par][seg].p, res.bytes[seg], e.out_bytes[seg], e.ev_out[par]};
+				{ std::lock_guard<std::mutex> l(w.m); w.q.push_back(job); }
+				w.cv.notify_all();
 			}
-			RSQ_CUDA(cudaEventRecord(e.ev_copied[par], e.copy_stream));
 		}
 		e.out_bytes[0] += res.bytes[0]; e.out_bytes[1] += res.bytes[1]; e.out_pairs += res.pairs; e.out_draws += res.draws;
 		e.last_par = par;
 	}
 	stage_log("simulate: last batch delivered");
 	if(streaming){
-		RSQ_CUDA(cudaStreamSynchronize(e.copy_stream));
-		drain();
-		if(!writer.error.empty()){ throw std::runtime_error(writer.error); }
+		wait_batches(n_batches);
+		for(int seg = 0; seg < 2; ++seg){ if(!writer[seg].error.empty()){ throw std::runtime_error(writer[seg].error); } }
 		e.streamed_to_host = true;
 	}
 	stage_log("simulate: copies and writer drained");
