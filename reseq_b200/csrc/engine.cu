@@ -938,7 +938,7 @@ struct rsq_engine {
 	uint32_t max_n0_reads = 0;             // largest candidate count of the tables FillRead draws from
 	uint32_t max_name_len = 0;
 	DevBuf<SpecBlock> d_spec_blocks; DevBuf<SpecSnap> d_spec_snaps; DevBuf<ReadJob> d_spec_jobs;
-	DevBuf<uint64_t> d_spec_words; DevBuf<unsigned char> d_spec_slots; DevBuf<uint32_t> d_slab_next, d_slab_count, d_spec_counters;
+	DevBuf<uint64_t> d_spec_words; DevBuf<unsigned char> d_spec_slots; DevBuf<uint8_t> d_spec_conv; DevBuf<uint32_t> d_slab_next, d_slab_count, d_spec_counters;
 	PinnedBuf h_spec_counters;
 	uint32_t spec_rounds = 0, spec_depth = 0;
 	std::vector<cudaStream_t> spec_streams; std::vector<cudaEvent_t> spec_events;
@@ -1638,6 +1638,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	sp.adapter_only_seed = e.adapter_only_seed;
 	const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);   // ReadLengths().to(): one past the longest read
 	sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
+	sp.margin = getenv("RSQ_SPEC_MARGIN") ? std::min<uint32_t>(kSpecMargin, atoi(getenv("RSQ_SPEC_MARGIN"))) : kSpecMargin;   // tests: 0 forces the serial fallback
 	// Depth (reads speculated per unit and round) and reads per warp are chosen per batch of rounds from a cost model:
 	//   a round costs max(latency, throughput) with latency ~ 1.0 ms + 0.12 ms per read of depth (one lock-step pass over a read
 	//   + the scan in front of `depth` reads) and throughput ~ 5e-5 ms per read in flight plus 1.5 reads' worth of fixed work per
@@ -1679,6 +1680,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	e.d_spec_blocks.alloc(sp.n_units); e.d_spec_snaps.alloc(2 * static_cast<size_t>(sp.n_units) * (depth + 1)); e.d_spec_jobs.alloc(n_tiles * 32);
 	e.d_spec_words.alloc(n_tiles * sp.words_per_job * 32);
 	sp.blocks = e.d_spec_blocks.p; sp.snaps = e.d_spec_snaps.p; sp.jobs = e.d_spec_jobs.p; sp.words = e.d_spec_words.p;
+	if(c.meth_loaded){ e.d_spec_conv.alloc(static_cast<size_t>(sp.n_units) * kConvSlots * 2 * kMaxOrgLen); sp.conv = e.d_spec_conv.p; }
 	const uint32_t id_prefix = c.base_id_len + 10 + 1 + 20 + 1 + 10 + 1 + std::max<uint32_t>(e.max_name_len, 7) + 1 + 10 + 1 + 5 + 11;
 	sp.id_cap = std::min<uint32_t>(kIdCap, (id_prefix + kCigarCap + 2 + 10 + 15) & ~15u);
 	sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
@@ -1914,9 +1916,9 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	e.spec_rounds = 0; e.spec_depth = 0;
 	e.out_bytes[0] = e.out_bytes[1] = 0; e.out_pairs = 0; e.out_draws = 0;
 	const bool meth = c.meth_loaded != 0;
-	// RSQ_SIM_PATH=serial keeps the one-warp-per-SimBlock kernel (parity tests run both); bisulfite runs always use it
+	// RSQ_SIM_PATH=serial keeps the one-warp-per-SimBlock kernel (parity tests run both)
 	const char *path = getenv("RSQ_SIM_PATH");
-	bool spec = !meth && !(path && std::string(path) == "serial");
+	bool spec = !(path && std::string(path) == "serial");
 	// ---- batches: as many blocks as HBM holds speculation state, record slots and two output buffers for ----
 	int dev_sms = 0; RSQ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e.device));
 	const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);
@@ -1924,7 +1926,7 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	const double rec_bytes = 2.0 * max_rl + 160.0;
 	auto unit_bytes = [&](uint32_t depth){
 		return 2.0 * (depth + 1) * sizeof(SpecSnap) + depth * (sizeof(ReadJob) + 8.0 * (3 * max_rl + 8 + kSpecMargin))
-		       + 1.2 * reads_per_block * (rec_bytes + 250.0) + 2.0 * 1.1 * reads_per_block * rec_bytes + 256.0;
+		       + 1.2 * reads_per_block * (rec_bytes + 250.0) + 2.0 * 1.1 * reads_per_block * rec_bytes + 256.0 + (meth ? kConvSlots * 2.0 * kMaxOrgLen : 0.0);
 	};
 	size_t free_b = 0, total_b = 0; RSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
 	const double budget = 0.85 * (static_cast<double>(free_b) + e.reusable_bytes());

@@ -551,8 +551,12 @@ RSQ_HD void create_reads(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, 
 
 // Simulator::CTConversion without variants (Simulator.cpp:1925-2003): bisulfite C->T on one fragment end, one draw per
 // C inside an unmethylated region.  `read` holds `read_len` bases; regions/rates are those of the sequence.
-template<class G>
-RSQ_HD void ct_conversion(const G &g, const SimCtx &c, Mt &mt, uint8_t *read, uint32_t read_len, uint32_t seq_id, uint32_t start_pos,
+struct MtSource {                 // the block's stream as the serial kernel holds it
+	Mt &mt;
+	template<class G> RSQ_HD double next(const G &g){ return mt_uniform(g, mt); }
+};
+template<class G, class Rng>
+RSQ_HD void ct_conversion(const G &g, const SimCtx &c, Rng &rng, uint8_t *read, uint32_t read_len, uint32_t seq_id, uint32_t start_pos,
                           int32_t cur_methylation_start, bool reversed){
 	const uint32_t r0 = c.meth_off[seq_id];
 	const uint32_t n_regions = c.meth_off[seq_id + 1] - r0;
@@ -568,7 +572,7 @@ RSQ_HD void ct_conversion(const G &g, const SimCtx &c, Mt &mt, uint8_t *read, ui
 	};
 	auto convert = [&](){
 		if(1 == read[read_pos]){
-			const double u = mt_uniform(g, mt);
+			const double u = rng.next(g);
 			if(u < rate[cur_meth]){
 				g.sync();
 				if(g.lane() == 0){ read[read_pos] = 3; }
@@ -710,7 +714,8 @@ RSQ_HD void simulate_block(const G &g, const SimCtx &c, const Scratch &s, Sink &
 									s.frag[rev][i] = rev ? static_cast<uint8_t>(3 - c.ref[off + cur_end - 1 - i]) : c.ref[off + pos + i];
 								}
 								g.sync();
-								ct_conversion(g, c, mt, s.frag[rev], n, b.ref_id, rev ? cur_end : pos, cur_methylation_start, rev != 0);
+								MtSource rng{mt};
+								ct_conversion(g, c, rng, s.frag[rev], n, b.ref_id, rev ? cur_end : pos, cur_methylation_start, rev != 0);
 							}
 							g.sync();
 						}

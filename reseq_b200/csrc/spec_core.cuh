@@ -25,6 +25,7 @@ namespace rsq {
 constexpr uint32_t kSpecNone = 0xffffffffu;
 constexpr uint32_t kSpecOverflow = 0xffffffffu;   // ReadJob::consumed when the slice (assumed + margin) was too short
 constexpr uint32_t kSpecMargin = 32;              // extra stream words copied behind the assumed consumption
+constexpr uint32_t kConvSlots = 20;               // bisulfite-converted fragment ends kept per unit (>= depth / 2 + 3: one per hit of a round + the committed one)
 constexpr uint32_t kErrSpecOverflow = 64;         // error flag: a read needed more than assumed + margin draws
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -80,6 +81,10 @@ template<class G> RSQ_HD uint64_t ring_next(const G &g, MtRing &r){
 	ring_advance(r, 1);
 	return x;
 }
+struct RingSource {                // the unit's stream as the scan holds it
+	MtRing &r;
+	template<class G> RSQ_HD double next(const G &g){ return canonical(ring_next(g, r)); }
+};
 // seed state in the first half; nothing generated yet
 template<class G> RSQ_HD void ring_seed(const G &g, MtRing &r, uint64_t seed){
 	g.sync();
@@ -106,12 +111,15 @@ struct ReadJob {
 	uint32_t consumed;             // draws it consumed (phase B)
 	uint32_t rec_len;              // bytes of its FASTQ record (phase B)
 	uint32_t slot;                 // output slot
+	uint32_t conv_index;           // bisulfite runs: which converted fragment end this read starts from (kSpecNone: the reference itself)
+	uint32_t pad;
 };
 
 struct SpecHit {                   // where inside SimulateFromGivenBlock's / CreateReads' loop nest the stream stands
 	uint32_t active, in_reads, fragment_length, n_chosen, chosen0, chosen1, ci, counts_left, strand;
 	uint32_t pair_stage;           // reads of the current pair already handled (0..2)
 	uint32_t tile;                 // tile drawn for the current pair
+	uint32_t conv_slot, conv_next; // bisulfite runs: slot of this hit's converted fragment ends / next slot to hand out
 };
 struct SpecSnap {                  // resumable state of one unit's stream
 	uint32_t pos, len;
@@ -139,11 +147,13 @@ struct SpecCtx {
 	uint32_t run_depth;            // reads to emit per unit in this round (<= depth): grows when few units are left
 	uint32_t scan_budget;          // scan draws per unit and round after which the round ends even with < run_depth reads (bounds stragglers)
 	uint32_t words_per_job;        // K: capacity of a read's stream slice
+	uint32_t margin;               // stream words copied behind the assumed consumption (kSpecMargin; tests shrink it to force the fallback)
 	uint32_t n_units;              // blocks (+ the adapter-only pseudo block) of this batch
 	SpecBlock *blocks;             // [n_units]
 	SpecSnap *snaps;               // [n_units][2 banks][D + 1]: in front of every emitted read + behind the last one
 	ReadJob *jobs;                 // [n_units * D]
 	uint64_t *words;               // [ceil(n_units * D / 32)][K][32] tempered stream words, lane-interleaved per tile of 32 reads
+	uint8_t *conv;                 // bisulfite runs: [n_units][kConvSlots][2][kMaxOrgLen] converted forward / reverse fragment ends
 	// output slots, handed out in slabs of 32
 	unsigned char *slots; uint32_t slot_stride, id_cap, seq_off, qual_off;
 	uint32_t n_slabs; uint32_t *next_slab; uint32_t *slab_next; uint32_t *slab_count;
@@ -240,7 +250,7 @@ template<class G> RSQ_HD uint64_t emit_words(const G &g, MtRing &r, uint64_t *ds
 // Emits the slice of one read under the no-InDel hypothesis (mirrors the draw order of Simulator::FillRead) and returns
 // the assumed consumption.  Any deviation of the real read is caught by the verification, so this only has to be right
 // in the common case.
-template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing &r, uint64_t *dst, uint32_t cap, uint32_t seg, uint32_t fragment_length){
+template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing &r, uint64_t *dst, uint32_t cap, uint32_t margin, uint32_t seg, uint32_t fragment_length){
 	uint32_t k = 0;
 	uint32_t read_length = c.read_len_from[seg];
 	if(1 != c.read_len_count[seg]){
@@ -275,7 +285,7 @@ template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing 
 		}
 	}
 	uint32_t km = k;
-	emit_words(g, r, dst, km, cap, kSpecMargin, false);   // look-ahead only: the next consumer starts at k
+	if(margin){ emit_words(g, r, dst, km, cap, margin, false); }   // look-ahead only: the next consumer starts at k
 	return k;
 }
 
@@ -442,12 +452,13 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 						save_snapshot(g, ring, out_snaps[emitted], pos, len, false, hit, cur_meth, read_number, draws);
 						const size_t gidx = static_cast<size_t>(u) * D + emitted;
 						uint64_t *dst = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
-						const uint32_t assumed = plan_read(g, c, ring, dst, sp.words_per_job, seg, hit.fragment_length);
+						const uint32_t assumed = plan_read(g, c, ring, dst, sp.words_per_job, sp.margin, seg, hit.fragment_length);
 						if(g.lane() == 0){
 							ReadJob j;
 							j.ref_id = b.ref_id; j.start_pos = adapter_only ? 0u : pos; j.end_pos = adapter_only ? 0u : pos + hit.fragment_length;
 							j.fragment_length = hit.fragment_length; j.block_id = b.block_id; j.flags = seg | (hit.strand << 1) | (hit.tile << 8);
 							j.read_number = read_number; j.assumed = assumed; j.consumed = kSpecOverflow; j.rec_len = 0; j.slot = slab * 32u + (p & 31u);
+							j.conv_index = (c.meth_loaded && !adapter_only) ? static_cast<uint32_t>((static_cast<size_t>(u) * kConvSlots + hit.conv_slot) * 2u + ((seg != hit.strand) ? 1u : 0u)) : kSpecNone; j.pad = 0;
 							jobs[emitted] = j;
 						}
 						++emitted; ++hit.pair_stage;
@@ -471,7 +482,26 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 					bool runaway = false;
 					const uint32_t counts = fragment_counts(c, b.ref_id, fl, gc_perc, c.sur_start[off + pos], c.sur_end[off + cur_end - 1], adjusted_random, runaway);
 					if(runaway && g.lane() == 0){ spec_flag(c, kErrCountRunaway); }
-					if(counts){ hit.in_reads = 1; hit.counts_left = counts; hit.strand = strand; hit.pair_stage = 0; continue; }
+					if(counts){
+						if(c.meth_loaded){
+							// GetOrgSeq + CTConversion of both fragment ends (Simulator.cpp:2325-2340), once per (hit, strand), in front of its reads
+							hit.conv_slot = hit.conv_next; hit.conv_next = (hit.conv_next + 1u) % kConvSlots;
+							for(uint32_t rev = 0; rev < 2; ++rev){
+								const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
+								const uint32_t n = fragment_org_len(c, seg, fl);
+								uint8_t *frag = sp.conv + ((static_cast<size_t>(u) * kConvSlots + hit.conv_slot) * 2u + rev) * kMaxOrgLen;
+								g.sync();
+								for(uint32_t i = g.lane(); i < n; i += G::kSize){
+									frag[i] = rev ? static_cast<uint8_t>(3 - c.ref[off + cur_end - 1 - i]) : c.ref[off + pos + i];
+								}
+								g.sync();
+								RingSource rng{ring};
+								ct_conversion(g, c, rng, frag, n, b.ref_id, rev ? cur_end : pos, cur_meth, rev != 0);
+							}
+							g.sync();
+						}
+						hit.in_reads = 1; hit.counts_left = counts; hit.strand = strand; hit.pair_stage = 0; continue;
+					}
 				}
 				++hit.ci;
 				continue;
@@ -486,6 +516,10 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 			if(len >= insert_to){
 				++pos; len = insert_from;
 				if(pos >= end){ finished = true; break; }
+				if(c.meth_loaded){   // SimulateFromGivenBlock: the first region that does not end in front of this position
+					const uint32_t r0 = c.meth_off[b.ref_id], nr = c.meth_off[b.ref_id + 1] - r0;
+					if(cur_meth >= 0 && static_cast<uint32_t>(cur_meth) < nr && c.meth_end[r0 + cur_meth] <= pos){ ++cur_meth; }
+				}
 			}
 			const uint32_t lane = g.lane();
 			if(insert_to - len >= 4u * G::kSize){
@@ -590,6 +624,10 @@ RSQ_HD void spec_init_unit(const SimCtx &c, const SpecCtx &sp, const BlockDesc *
 	}
 	else{
 		s.pos = descs[first_desc + u].start_pos; s.len = c.insert_from;
+		if(c.meth_loaded){
+			const uint32_t rid = descs[first_desc + u].ref_id, r0 = c.meth_off[rid], nr = c.meth_off[rid + 1] - r0;
+			if(s.cur_meth >= 0 && static_cast<uint32_t>(s.cur_meth) < nr && c.meth_end[r0 + s.cur_meth] <= s.pos){ ++s.cur_meth; }
+		}
 		const uint32_t L = c.seq_len[descs[first_desc + u].ref_id];
 		if(s.pos >= L){ spec_unit_done(sp, &blk.done); }
 	}
@@ -662,7 +700,7 @@ struct ReadMachine {
 	// FillRead up to the sequence-quality draw; returns the mean systematic error rate (its second index)
 	RSQ_HD uint32_t begin(const SimCtx &c, const SpecCtx &sp, const ReadJob &j, const uint64_t *slice, unsigned char *slot){
 		// only assumed + margin words of the slice were written by the scan
-		words = slice; k = 0; kcap = j.assumed + kSpecMargin < sp.words_per_job ? j.assumed + kSpecMargin : sp.words_per_job; overflow = 0;
+		words = slice; k = 0; kcap = j.assumed + sp.margin < sp.words_per_job ? j.assumed + sp.margin : sp.words_per_job; overflow = 0;
 		load_window();
 		seg = j.flags & 1u; tile = j.flags >> 8; fragment_length = j.fragment_length;
 		const bool strand = (j.flags >> 1) & 1u;
@@ -707,6 +745,7 @@ struct ReadMachine {
 			const bool reversed = (seg != static_cast<uint32_t>(strand));
 			if(!reversed){ org = c.ref + off + j.start_pos; sys = c.sys_fwd + 2 * (off + j.start_pos); }
 			else{ org = c.ref + off + j.end_pos - 1; org_step = -1; org_comp = 1; sys = c.sys_rev + 2 * (off + (L - j.end_pos)); }
+			if(j.conv_index != kSpecNone){ org = sp.conv + static_cast<size_t>(j.conv_index) * kMaxOrgLen; org_step = 1; org_comp = 0; }   // bisulfite-converted end
 		}
 		adapter_id = 0; tail_left = 0;
 		const uint32_t seq_length = read_length < org_len ? read_length : org_len;

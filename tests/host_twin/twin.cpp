@@ -286,14 +286,14 @@ int main(int argc, char **argv){
 	int64_t n_adapter_only = f.scalar_i("sim.num_adapter_only_pairs");
 	if(getenv("RSQ_TWIN_ADAPTER_ONLY")){ n_adapter_only = atoll(getenv("RSQ_TWIN_ADAPTER_ONLY")); }   // serial-vs-speculative consistency checks
 	const char *spec_env = getenv("RSQ_TWIN_SPEC");
-	if(spec_env && !bed){
+	if(spec_env){
 		// two-phase speculative form (spec_core.cuh) with one-lane groups: rounds of scan_window + ReadMachine
 		SpecCtx sp{};
 		sp.depth = std::max(1, atoi(spec_env));
 		sp.run_depth = sp.depth;
 		sp.scan_budget = getenv("RSQ_TWIN_BUDGET") ? atoi(getenv("RSQ_TWIN_BUDGET")) : 4000000000u;
 		const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);
-		sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
+		sp.words_per_job = 3 * max_rl + 8 + kSpecMargin; sp.margin = kSpecMargin;
 		sp.n_blocks = nsim;
 		const bool with_adapter_only = n_adapter_only && nsim == blocks.size();
 		sp.n_units = nsim + (with_adapter_only ? 1 : 0);
@@ -302,7 +302,8 @@ int main(int argc, char **argv){
 		std::vector<SpecBlock> sblocks(sp.n_units); std::vector<SpecSnap> snaps(2 * static_cast<size_t>(sp.n_units) * (sp.depth + 1));
 		std::vector<ReadJob> jobs(static_cast<size_t>(sp.n_units) * sp.depth);
 		std::vector<uint64_t> words(((jobs.size() + 31) / 32) * sp.words_per_job * 32);
-		sp.blocks = sblocks.data(); sp.snaps = snaps.data(); sp.jobs = jobs.data(); sp.words = words.data();
+		std::vector<uint8_t> conv(bed ? static_cast<size_t>(sp.n_units) * kConvSlots * 2 * kMaxOrgLen : 0);
+		sp.blocks = sblocks.data(); sp.snaps = snaps.data(); sp.jobs = jobs.data(); sp.words = words.data(); sp.conv = conv.data();
 		sp.id_cap = kIdCap; sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
 		sp.n_slabs = sp.n_units * 8 + 64;
 		std::vector<unsigned char> slots(static_cast<size_t>(sp.n_slabs) * 32 * sp.slot_stride);

@@ -76,8 +76,23 @@ def test_block_batches_concatenate_to_the_whole_run(rb, engine, golden, monkeypa
     assert rep.pairs == r1.count(b"\n") // 4
 
 
-def test_methylation_golden_bit_exact(rb, engine, golden):
-    """--methylation: bisulfite C->T conversions per unmethylated region (Simulator::CTConversion)."""
+def test_speculation_overflow_falls_back_to_the_serial_kernel(rb, engine, golden, monkeypatch):
+    """A read that needs more draws than assumed + margin cannot be finished by the read kernel; the batch is then redone by
+    k_simulate.  With the margin forced to 0 the first deletion triggers that path (batches of 16 blocks: some fall back, some do not)."""
+    monkeypatch.setenv("RSQ_SPEC_MARGIN", "0")
+    monkeypatch.setenv("RSQ_BATCH_UNITS", "16")
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    r1, r2, rep = _simulate(engine, ref, seed=42, coverage=20.0)
+    assert r1 == open(golden["r1"], "rb").read()
+    assert r2 == open(golden["r2"], "rb").read()
+
+
+@pytest.mark.parametrize("path,depth", [("spec", None), ("spec", 3), ("serial", None)])
+def test_methylation_golden_bit_exact(rb, engine, golden, monkeypatch, path, depth):
+    """--methylation: bisulfite C->T conversions per unmethylated region (Simulator::CTConversion), on both kernel forms."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    if depth:
+        monkeypatch.setenv("RSQ_SPEC_DEPTH", str(depth))
     ref = rb.Reference.load_fasta(golden["small_ref"])
     ref.load_methylation(golden["meth_bed"])
     r1, r2, _ = _simulate(engine, ref, seed=42, coverage=20.0)

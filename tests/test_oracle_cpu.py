@@ -112,13 +112,15 @@ def test_methylation_golden_is_what_the_reference_writes(oracle, golden, workdir
     assert filecmp.cmp(r2, golden["meth_r2"], shallow=False)
 
 
-def test_templates_match_reference_with_methylation(oracle, golden, twin, workdir):
-    """CTConversion (bisulfite C->T per unmethylated region, Simulator.cpp:1925-2003) through the one-lane twin."""
+@pytest.mark.parametrize("spec_depth", [None, "5"])
+def test_templates_match_reference_with_methylation(oracle, golden, twin, workdir, spec_depth):
+    """CTConversion (bisulfite C->T per unmethylated region, Simulator.cpp:1925-2003) through the one-lane twin, serial and speculative form."""
     stage = os.path.join(workdir, "stage_meth.flat")
     subprocess.run([oracle["dump"], "sim", golden["reseq"], golden["small_ref"], "42", "20", stage], check=True, timeout=600,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     prefix = os.path.join(workdir, "twin_meth")
-    res = subprocess.run([twin, stage, "42", prefix, "66", golden["meth_bed"]], capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, RSQ_TWIN_SPEC=spec_depth) if spec_depth else dict(os.environ)
+    res = subprocess.run([twin, stage, "42", prefix, "66", golden["meth_bed"]], capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, res.stdout
     assert filecmp.cmp(prefix + "_1.fq", golden["meth_r1"], shallow=False)
     assert filecmp.cmp(prefix + "_2.fq", golden["meth_r2"], shallow=False)
