@@ -645,13 +645,18 @@ k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uin
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	double *buf = reinterpret_cast<double *>(smem) + static_cast<size_t>(warp) * lanes_per_warp * stride;
 	const size_t gwarp = static_cast<size_t>(blockIdx.x) * kSpecReadWarps + warp;
-	// dense over (unit, read of this round): reads beyond run_depth do not exist in this round
+	// dense over (unit, read of this round): reads beyond run_depth do not exist in this round - except for the adapter-only
+	// pseudo unit (always full depth), whose further reads are appended behind the regular ones of its group
 	const size_t dense = gwarp * lanes_per_warp + lane;
-	const uint32_t u = unit_first + static_cast<uint32_t>(dense / sp.run_depth), k = static_cast<uint32_t>(dense % sp.run_depth);
+	const size_t regular = static_cast<size_t>(unit_end - unit_first) * sp.run_depth;
+	uint32_t u, k;
+	if(dense < regular){ u = unit_first + static_cast<uint32_t>(dense / sp.run_depth); k = static_cast<uint32_t>(dense % sp.run_depth); }
+	else{ u = sp.n_blocks; k = sp.run_depth + static_cast<uint32_t>(dense - regular); }
+	const bool in_range = dense < regular || (sp.n_units > sp.n_blocks && unit_end == sp.n_units && k < sp.depth);
 	const size_t gidx = static_cast<size_t>(u) * sp.depth + k;
 	bool have = false;
 	ReadJob job{};
-	if(lane < lanes_per_warp && u < unit_end){
+	if(lane < lanes_per_warp && in_range){
 		const SpecBlock &b = sp.blocks[u];
 		have = !b.done && k < b.n_jobs;
 		if(have){ job = sp.jobs[gidx]; }
@@ -1286,6 +1291,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		e.total_pairs = coverage_to_number_pairs(coverage, e.total_size, average_read_length, adapter_part);
 	}
 	e.adapter_only_pairs = std::round(static_cast<double>(e.total_pairs) * p.insert_lengths[0] / (p.total_number_reads / 2));
+	if(const char *env = getenv("RSQ_FORCE_ADAPTER_ONLY")){ e.adapter_only_pairs = std::min<uint64_t>(e.total_pairs, atoll(env)); }   // test hook: the golden profiles have none
 	e.total_pairs -= e.adapter_only_pairs;
 	e.sys_gc_range = static_cast<uint32_t>((sum_read_length + reads / 2) / reads) / 2;
 
@@ -1726,7 +1732,8 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 						if(u1 == u0){ continue; }
 						cudaStream_t gs = e.spec_streams[gi];
 						k_spec_scan<<<(u1 - u0 + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, gs>>>(c, sp, e.d_blocks.p, first_desc, u0, u1);
-						const size_t warps = (static_cast<size_t>(u1 - u0) * sp.run_depth + lanes - 1) / lanes;
+						const size_t extra = (sp.n_units > sp.n_blocks && u1 == sp.n_units && sp.depth > sp.run_depth) ? sp.depth - sp.run_depth : 0;
+						const size_t warps = (static_cast<size_t>(u1 - u0) * sp.run_depth + extra + lanes - 1) / lanes;
 						const size_t shmem_reads = static_cast<size_t>(kSpecReadWarps) * lanes * stride * sizeof(double);
 						k_spec_reads<<<static_cast<unsigned>((warps + kSpecReadWarps - 1) / kSpecReadWarps), kSpecReadWarps * 32, shmem_reads, gs>>>(c, sp, stride, lanes, u0, u1);
 						e.launches += 2;

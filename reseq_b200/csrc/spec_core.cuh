@@ -424,7 +424,8 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	uint32_t emitted = 0;
 	bool full = false, failed = false;
 	const uint64_t draws_limit = draws + sp.scan_budget;
-	const uint32_t D_run = sp.run_depth < D ? sp.run_depth : D;
+	// the adapter-only pairs are ONE serial stream however large the run is: always speculate as deep as the buffers allow
+	const uint32_t D_run = (u >= sp.n_blocks) ? D : (sp.run_depth < D ? sp.run_depth : D);
 	while(!finished && !full && !failed){
 		if(hit.active){
 			if(hit.in_reads){

@@ -76,6 +76,25 @@ def test_block_batches_concatenate_to_the_whole_run(rb, engine, golden, monkeypa
     assert rep.pairs == r1.count(b"\n") // 4
 
 
+def test_adapter_only_pairs_serial_and_speculative_agree(rb, engine, golden, monkeypatch):
+    """SimulateAdapterOnlyPairs (insert length 0: reads made of adapter, poly-A tail and overrun bases).  The golden profiles
+    contain no such pairs, so they are forced on and the two kernel forms are compared with each other (k_adapter_only vs the
+    pseudo unit of the speculative kernels, which always runs at full depth)."""
+    monkeypatch.setenv("RSQ_FORCE_ADAPTER_ONLY", "333")
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    outs = []
+    for path, depth in (("serial", None), ("spec", "3"), ("spec", None)):
+        monkeypatch.setenv("RSQ_SIM_PATH", path)
+        if depth:
+            monkeypatch.setenv("RSQ_SPEC_DEPTH", depth)
+        else:
+            monkeypatch.delenv("RSQ_SPEC_DEPTH", raising=False)
+        r1, r2, rep = _simulate(engine, ref, seed=42, coverage=20.0)
+        assert rep.adapter_only_pairs == 333 and r1.count(b":Adapter:") == 333
+        outs.append((r1, r2))
+    assert outs[0] == outs[1] == outs[2]
+
+
 def test_speculation_overflow_falls_back_to_the_serial_kernel(rb, engine, golden, monkeypatch):
     """A read that needs more draws than assumed + margin cannot be finished by the read kernel; the batch is then redone by
     k_simulate.  With the margin forced to 0 the first deletion triggers that path (batches of 16 blocks: some fall back, some do not)."""
