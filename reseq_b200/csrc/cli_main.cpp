@@ -150,6 +150,19 @@ int run_illumina_pe(const Args &a){
 	info("Storing simulated data in " + out1 + " and " + out2);
 	for(const std::string &o : {out1, out2}){ FILE *f = fopen(o.c_str(), "wb"); if(!f){ return err("Could not open '" + o + "' for writing."); } fclose(f); }
 
+	if(gpus == 1){
+		// one device: the drop-in call streams batch after batch into the two files (runs larger than HBM or host memory work)
+		const auto t1 = std::chrono::steady_clock::now();
+		rsq_sim_report rep;
+		const int rc1 = rsq_simulate(prof, ref, &opt, 0, out1.c_str(), out2.c_str(), &rep);
+		const std::string msg = rc1 ? rsq_last_error() : "";
+		rsq_profile_free(prof); rsq_reference_free(ref);
+		if(rc1){ err(msg); err("An error occurred in the process: Terminating simulation"); return 1; }
+		const double secs1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+		info("Generated " + std::to_string(rep.pairs) + " read pairs (aim " + std::to_string(rep.total_pairs_aim) + ") in " + std::to_string(secs1) + " s on 1 GPU(s).");
+		info("Simulation finished succesfully");
+		return 0;
+	}
 	std::vector<rsq_engine *> engines(gpus, nullptr);
 	std::vector<rsq_sim_report> reports(gpus);
 	std::vector<std::string> errors(gpus);
