@@ -427,7 +427,7 @@ __global__ void k_spec_block_out(SpecCtx sp, BlockOut *out){
 	if(u >= sp.n_units){ return; }
 	const SpecBlock &b = sp.blocks[u];
 	BlockOut o; o.head[0] = b.chain_head; o.head[1] = b.chain_head; o.bytes[0] = b.bytes[0]; o.bytes[1] = b.bytes[1];
-	o.pairs = b.reads / 2u; o.pad = b.rounds; o.scan_draws = b.scan_draws;
+	o.pairs = sp.em_recs ? b.reads : b.reads / 2u; o.pad = b.rounds; o.scan_draws = b.scan_draws;   // seqToIllumina counts reads
 	out[u] = o;
 }
 
@@ -781,7 +781,6 @@ __global__ void k_gather(const BlockOut *out, uint32_t n, Arena arena, const uns
 }
 
 // seqToIllumina: one warp per batch of records (Simulator::ErrorModelOnlyThread + ApplyErrorsAndQualityToFastaInput)
-struct EmRecord { uint64_t seq_off; uint32_t len; uint32_t seg; uint32_t fragment_length; uint32_t id_off; uint32_t id_len; uint32_t pad; };
 
 struct EmSink {
 	DeviceSink inner;
@@ -941,7 +940,7 @@ struct rsq_engine {
 	double reusable_bytes() const;
 	// speculative two-phase path
 	uint32_t max_n0_reads = 0;             // largest candidate count of the tables FillRead draws from
-	uint32_t max_name_len = 0;
+	uint32_t max_name_len = 0, em_max_id_len = 0;
 	DevBuf<SpecBlock> d_spec_blocks; DevBuf<SpecSnap> d_spec_snaps; DevBuf<ReadJob> d_spec_jobs;
 	DevBuf<uint64_t> d_spec_words; DevBuf<unsigned char> d_spec_slots; DevBuf<uint8_t> d_spec_conv; DevBuf<uint32_t> d_slab_next, d_slab_count, d_spec_counters;
 	PinnedBuf h_spec_counters;
@@ -1632,7 +1631,8 @@ static void fill_simulate_report(rsq_engine &e, rsq_sim_report *rep, float ms_si
 // One batch of this shard's blocks [u_begin, u_begin + u_count) (+ the adapter-only pairs behind the last one): on return the
 // FASTQ text of the batch is in e.d_out_batch[par][0/1], its sizes in `res`.  false: a read outran the speculation margin.
 struct BatchResult { uint64_t bytes[2] = {0, 0}; uint64_t pairs = 0, draws = 0; float ms_sim = 0, ms_gather = 0; uint32_t rounds = 0, depth = 0; };
-static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_count, bool with_adapter_only, uint32_t depth_cap, int par, BatchResult &res){
+static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_count, bool with_adapter_only, uint32_t depth_cap, int par, BatchResult &res,
+                                const SpecCtx *records = nullptr){
 	cudaStream_t s = e.stream;
 	SimCtx &c = e.ctx;
 	int dev_sms = 0; RSQ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e.device));
@@ -1642,6 +1642,10 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	sp.n_units = u_count + (with_adapter_only ? 1 : 0);
 	sp.adapter_only_pairs = with_adapter_only ? e.adapter_only_pairs : 0;
 	sp.adapter_only_seed = e.adapter_only_seed;
+	if(records){   // seqToIllumina: the units are batches of input records
+		sp.em_recs = records->em_recs; sp.em_n = records->em_n; sp.em_batch = records->em_batch; sp.em_seeds = records->em_seeds;
+		sp.em_seq = records->em_seq; sp.em_sys = records->em_sys; sp.em_ids = records->em_ids;
+	}
 	const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);   // ReadLengths().to(): one past the longest read
 	sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
 	sp.margin = getenv("RSQ_SPEC_MARGIN") ? std::min<uint32_t>(kSpecMargin, atoi(getenv("RSQ_SPEC_MARGIN"))) : kSpecMargin;   // tests: 0 forces the serial fallback
@@ -1658,7 +1662,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	if(fixed_depth){ depth = fixed_depth; }
 	if(const char *env = getenv("RSQ_SPEC_MAX_DEPTH")){ depth = std::max<uint32_t>(fixed_depth, std::min(32, std::max(1, atoi(env)))); }
 	sp.depth = depth;
-	const double draws_per_read = static_cast<double>(e.total_size) * (c.insert_to - c.insert_from) / (2.0 * std::max<uint64_t>(1, e.total_pairs));
+	const double draws_per_read = records ? 0.0 : static_cast<double>(e.total_size) * (c.insert_to - c.insert_from) / (2.0 * std::max<uint64_t>(1, e.total_pairs));
 	const double budget_factor = getenv("RSQ_SPEC_BUDGET") ? atof(getenv("RSQ_SPEC_BUDGET")) : 1.5;
 	uint32_t lanes = 32;
 	auto choose = [&](uint64_t active, double p_hold){
@@ -1667,7 +1671,8 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 		for(uint32_t d : cand){
 			if(d > depth){ break; }
 			const double prog = p_hold >= 0.9999 ? d : (1.0 - std::pow(p_hold, static_cast<double>(d))) / (1.0 - p_hold);
-			const double cost = std::max(1.0 + 0.12 * d, 5.0e-5 * static_cast<double>(active) * (1.5 + d));
+			const double latency = records ? 0.6 + 0.01 * d : 1.0 + 0.12 * d;   // seqToIllumina units have no scan in front of their reads
+			const double cost = std::max(latency, 5.0e-5 * static_cast<double>(active) * (1.5 + d));
 			if(prog / cost > best){ best = prog / cost; best_d = d; }
 		}
 		if(fixed_depth){ best_d = fixed_depth; }
@@ -1687,7 +1692,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	e.d_spec_words.alloc(n_tiles * sp.words_per_job * 32);
 	sp.blocks = e.d_spec_blocks.p; sp.snaps = e.d_spec_snaps.p; sp.jobs = e.d_spec_jobs.p; sp.words = e.d_spec_words.p;
 	if(c.meth_loaded){ e.d_spec_conv.alloc(static_cast<size_t>(sp.n_units) * kConvSlots * 2 * kMaxOrgLen); sp.conv = e.d_spec_conv.p; }
-	const uint32_t id_prefix = c.base_id_len + 10 + 1 + 20 + 1 + 10 + 1 + std::max<uint32_t>(e.max_name_len, 7) + 1 + 10 + 1 + 5 + 11;
+	const uint32_t id_prefix = records ? e.em_max_id_len + 1 : c.base_id_len + 10 + 1 + 20 + 1 + 10 + 1 + std::max<uint32_t>(e.max_name_len, 7) + 1 + 10 + 1 + 5 + 11;
 	sp.id_cap = std::min<uint32_t>(kIdCap, (id_prefix + kCigarCap + 2 + 10 + 15) & ~15u);
 	sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
 	e.d_spec_counters.alloc(8); e.h_spec_counters.ensure(8 * sizeof(uint32_t));
@@ -1704,7 +1709,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	const size_t shmem_reads_max = static_cast<size_t>(kSpecReadWarps) * 32 * stride * sizeof(double);
 	RSQ_CUDA(cudaFuncSetAttribute(k_spec_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem_reads_max)));
 	const double share = e.n_blocks_sim ? static_cast<double>(u_count) / e.n_blocks_sim : 0.0;
-	uint64_t expected_reads = static_cast<uint64_t>(2.0 * (e.total_pairs * share + sp.adapter_only_pairs) * 1.15) + 2048;
+	uint64_t expected_reads = records ? records->em_n + 2048ull : static_cast<uint64_t>(2.0 * (e.total_pairs * share + sp.adapter_only_pairs) * 1.15) + 2048;
 	float ms_sim = 0;
 	uint32_t rounds = 0;
 	for(int attempt = 0; ; ++attempt){
@@ -2099,35 +2104,65 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 			run_sys_chains(e, chains, lens, 1u << 30, 0, passes);
 		}
 	}
-	const uint32_t batch = 10000;
+	// ErrorModelOnlyThread hands out batches of 10000 records, one master-stream seed each (RSQ_EM_BATCH: smaller batches for the
+	// serial-vs-speculative consistency test; the reference itself cannot get past its first batch)
+	const uint32_t batch = getenv("RSQ_EM_BATCH") ? std::max(1, atoi(getenv("RSQ_EM_BATCH"))) : 10000;
 	const uint32_t n_batches = (recs.size() + batch - 1) / batch;
 	DevBuf<uint64_t> d_seeds; d_seeds.alloc(n_batches);
 	k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, d_seeds.p, n_batches); ++e.launches;
 	DevBuf<EmRecord> d_recs; d_recs.upload(recs, s);
 	DevBuf<uint8_t> d_seq, d_dom, d_rate; d_seq.upload(hseq, s); d_dom.upload(hdom, s); d_rate.upload(hrate, s);
 	DevBuf<char> d_ids; d_ids.upload(hid.data(), hid.size() + 1, s);
-	const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, c.max_read_len);
-	const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta;
-	RSQ_CUDA(cudaFuncSetAttribute(k_error_model, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
-	Arena a;
-	uint64_t expected = static_cast<uint64_t>(recs.size() * (2.0 * c.max_read_len + 200.0 + hid.size() / std::max<size_t>(1, recs.size())) * 1.3);
 	float ms_sim = 0;
-	for(int attempt = 0; ; ++attempt){
-		setup_arena(e, a, expected, n_batches);
-		e.d_block_out.alloc(n_batches + 1);
-		RSQ_CUDA(cudaMemsetAsync(e.d_block_out.p, 0, (n_batches + 1) * sizeof(BlockOut), s));
-		e.d_next_block.alloc(1); e.d_next_block.zero(s);
-		EventTimer tm(s); tm.start();
-		k_error_model<<<(n_batches + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, shmem, s>>>(c, d_recs.p, recs.size(), batch, d_seeds.p, n_batches, d_seq.p, d_dom.p, d_rate.p, d_ids.p, a, e.d_block_out.p, e.d_next_block.p, e.max_n0, scratch);
-		++e.launches;
-		ms_sim = tm.stop();
-		RSQ_CUDA(cudaGetLastError());
-		const uint32_t flag = read_error_flag(e);
-		if(flag == kErrArenaFull && attempt < 3){ expected *= 2; e.d_error_flag.zero(s); continue; }
-		if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
-		break;
+	bool done = false;
+	{
+		// speculative two-phase kernels: every batch is a unit whose reads run in lock step with those of the other batches
+		// (RSQ_SIM_PATH=serial: one warp per batch)
+		const char *path = getenv("RSQ_SIM_PATH");
+		if(!(path && std::string(path) == "serial")){
+			std::vector<uint8_t> hsys(2 * hdom.size());
+			for(size_t i = 0; i < hdom.size(); ++i){ hsys[2 * i] = hdom[i]; hsys[2 * i + 1] = hrate[i]; }
+			DevBuf<uint8_t> d_sys; d_sys.upload(hsys, s);
+			SpecCtx em{};
+			em.em_recs = d_recs.p; em.em_n = static_cast<uint32_t>(recs.size()); em.em_batch = batch; em.em_seeds = d_seeds.p;
+			em.em_seq = d_seq.p; em.em_sys = d_sys.p; em.em_ids = d_ids.p;
+			e.em_max_id_len = 0; for(const auto &r : recs){ e.em_max_id_len = std::max(e.em_max_id_len, r.id_len); }
+			if(e.em_max_id_len + 1 + kCigarCap + 12 <= static_cast<uint32_t>(kIdCap)){
+				BatchResult res;
+				done = simulate_spec_batch(e, 0, n_batches, false, 32, 0, res, &em);
+				if(done){
+					ms_sim = res.ms_sim; e.last_par = 0; e.streamed_to_host = false;
+					e.out_bytes[0] = res.bytes[0]; e.out_bytes[1] = res.bytes[1]; e.out_pairs = res.pairs; e.out_draws = 0;
+					e.spec_rounds = res.rounds; e.spec_depth = res.depth;
+					if(rep){ rep->ms_gather = res.ms_gather; rep->spec_rounds = res.rounds; rep->spec_depth = res.depth; }
+				}
+			}
+			RSQ_CUDA(cudaStreamSynchronize(s));   // d_sys goes out of scope
+		}
 	}
-	gather(e, a, n_batches, rep);
+	if(!done){
+		const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, c.max_read_len);
+		const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta;
+		RSQ_CUDA(cudaFuncSetAttribute(k_error_model, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
+		Arena a;
+		uint64_t expected = static_cast<uint64_t>(recs.size() * (2.0 * c.max_read_len + 200.0 + hid.size() / std::max<size_t>(1, recs.size())) * 1.3);
+		for(int attempt = 0; ; ++attempt){
+			setup_arena(e, a, expected, n_batches);
+			e.d_block_out.alloc(n_batches + 1);
+			RSQ_CUDA(cudaMemsetAsync(e.d_block_out.p, 0, (n_batches + 1) * sizeof(BlockOut), s));
+			e.d_next_block.alloc(1); e.d_next_block.zero(s);
+			EventTimer tm(s); tm.start();
+			k_error_model<<<(n_batches + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, shmem, s>>>(c, d_recs.p, recs.size(), batch, d_seeds.p, n_batches, d_seq.p, d_dom.p, d_rate.p, d_ids.p, a, e.d_block_out.p, e.d_next_block.p, e.max_n0, scratch);
+			++e.launches;
+			ms_sim = tm.stop();
+			RSQ_CUDA(cudaGetLastError());
+			const uint32_t flag = read_error_flag(e);
+			if(flag == kErrArenaFull && attempt < 3){ expected *= 2; e.d_error_flag.zero(s); continue; }
+			if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
+			break;
+		}
+		gather(e, a, n_batches, rep);
+	}
 	download(e, rep);
 	RSQ_CUDA(cudaStreamSynchronize(s));
 	FILE *o = fopen(out_path, "wb");

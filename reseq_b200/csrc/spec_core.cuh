@@ -100,12 +100,15 @@ template<class G> RSQ_HD void ring_seed(const G &g, MtRing &r, uint64_t seed){
 // ----------------------------------------------------------------------------------------------------------------
 // Shared data of the two phases
 // ----------------------------------------------------------------------------------------------------------------
+// seqToIllumina input record (Simulator::ApplyErrorsAndQualityToFastaInput): sequence, per-base systematic errors, id text
+struct EmRecord { uint64_t seq_off; uint32_t len; uint32_t seg; uint32_t fragment_length; uint32_t id_off; uint32_t id_len; uint32_t pad; };
+
 struct ReadJob {
 	uint32_t ref_id;
 	uint32_t start_pos, end_pos;   // fragment [start, end) on the forward strand (0,0: adapter-only pair)
 	uint32_t fragment_length;
 	uint32_t block_id;             // id printed in the record name
-	uint32_t flags;                // bit 0 segment, bit 1 strand, bits 8.. tile index
+	uint32_t flags;                // bit 0 segment, bit 1 strand, bit 2 seqToIllumina record (ref_id = record index), bits 8.. tile index
 	uint64_t read_number;
 	uint32_t assumed;              // draws the scan assumed this read consumes
 	uint32_t consumed;             // draws it consumed (phase B)
@@ -161,6 +164,9 @@ struct SpecCtx {
 	unsigned long long *stat;      // [0] reads emitted, [1] reads verified (the host tunes the depth with their ratio)
 	// adapter-only pseudo block (Simulator::SimulateAdapterOnlyPairs), unit index n_blocks when present
 	uint32_t n_blocks; uint32_t adapter_only_pairs; uint64_t adapter_only_seed;
+	// seqToIllumina: unit u = batch u of em_batch input records with its own stream (seed em_seeds[u]); no scan, one read per record
+	const EmRecord *em_recs; uint32_t em_n, em_batch; const uint64_t *em_seeds;
+	const uint8_t *em_seq, *em_sys; const char *em_ids;   // bases; (dominant error, rate) pairs; id text
 };
 
 RSQ_HD uint32_t spec_alloc_slab(const SpecCtx &sp){
@@ -250,7 +256,8 @@ template<class G> RSQ_HD uint64_t emit_words(const G &g, MtRing &r, uint64_t *ds
 // Emits the slice of one read under the no-InDel hypothesis (mirrors the draw order of Simulator::FillRead) and returns
 // the assumed consumption.  Any deviation of the real read is caught by the verification, so this only has to be right
 // in the common case.
-template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing &r, uint64_t *dst, uint32_t cap, uint32_t margin, uint32_t seg, uint32_t fragment_length){
+template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing &r, uint64_t *dst, uint32_t cap, uint32_t margin, uint32_t seg, uint32_t fragment_length,
+                                            uint32_t given_org_len = kSpecNone){
 	uint32_t k = 0;
 	uint32_t read_length = c.read_len_from[seg];
 	if(1 != c.read_len_count[seg]){
@@ -258,7 +265,7 @@ template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing 
 		read_length = read_length_from(c, seg, fragment_length, u);
 	}
 	if(read_length > c.max_read_len){ read_length = c.max_read_len; }
-	const uint32_t org_len = fragment_length ? fragment_org_len(c, seg, fragment_length) : 0u;
+	const uint32_t org_len = given_org_len != kSpecNone ? given_org_len : (fragment_length ? fragment_org_len(c, seg, fragment_length) : 0u);
 	const uint32_t n_part = read_length < org_len ? read_length : org_len;
 	uint32_t adapter_id = 0;
 	const AdapterSet &as = c.adapters[seg];
@@ -365,7 +372,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		// commit the records of the verified prefix: slots fill .. fill + v - 1
 		uint32_t b0 = 0, b1 = 0;
 		for(uint32_t j = g.lane(); j < v; j += G::kSize){
-			if(jobs[j].flags & 1u){ b1 += jobs[j].rec_len; } else{ b0 += jobs[j].rec_len; }
+			if((jobs[j].flags & 5u) == 1u){ b1 += jobs[j].rec_len; } else{ b0 += jobs[j].rec_len; }   // seqToIllumina records all go to the one output
 		}
 		b0 = g.reduce_add(b0); b1 = g.reduce_add(b1);
 		fill += v;
@@ -399,7 +406,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	if(pending_skip){
 		// the snapshot stands in front of the read whose assumption failed: walk over it with its measured consumption
 		ring_skip(g, ring, pending_skip);
-		++hit.pair_stage;
+		if(sp.em_recs){ ++pos; } else{ ++hit.pair_stage; }
 	}
 	if(finished){
 		if(g.lane() == 0){
@@ -408,12 +415,13 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		}
 		return;
 	}
-	const bool adapter_only = u >= sp.n_blocks;
+	const bool records = sp.em_recs != nullptr;
+	const bool adapter_only = !records && u >= sp.n_blocks;
 	BlockDesc b{};
-	if(!adapter_only){ b = descs[first_desc + u]; }
-	const uint32_t L = adapter_only ? 0u : c.seq_len[b.ref_id];
-	const uint64_t off = adapter_only ? 0u : c.seq_off[b.ref_id];
-	const uint32_t group = adapter_only ? 0u : c.coverage_group[b.ref_id];
+	if(!adapter_only && !records){ b = descs[first_desc + u]; }
+	const uint32_t L = (adapter_only || records) ? 0u : c.seq_len[b.ref_id];
+	const uint64_t off = (adapter_only || records) ? 0u : c.seq_off[b.ref_id];
+	const uint32_t group = (adapter_only || records) ? 0u : c.coverage_group[b.ref_id];
 	const double *thr = c.thr + static_cast<size_t>(group) * c.insert_to * 2;
 	const uint64_t *thr_int = c.thr_int + static_cast<size_t>(group) * c.insert_to;
 	const double *binom_p0 = c.binom_p0 + static_cast<size_t>(group) * c.insert_to;
@@ -425,7 +433,41 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	bool full = false, failed = false;
 	const uint64_t draws_limit = draws + sp.scan_budget;
 	// the adapter-only pairs are ONE serial stream however large the run is: always speculate as deep as the buffers allow
-	const uint32_t D_run = (u >= sp.n_blocks) ? D : (sp.run_depth < D ? sp.run_depth : D);
+	const uint32_t D_run = adapter_only ? D : (sp.run_depth < D ? sp.run_depth : D);
+	if(records){
+		// seqToIllumina (Simulator::ErrorModelOnlyThread): no scan - pos is the next input record of this batch, len the end of the batch
+		while(pos < len && emitted < D_run && !failed){
+			const EmRecord rec = sp.em_recs[pos];
+			hit.tile = 0;
+			if(1 < c.num_tiles){ hit.tile = discrete_lookup(c.tile_pick, canonical(ring_next(g, ring))); }
+			const uint32_t p = fill + emitted;
+			uint32_t slab = p < 32u ? cur_slab : next_slab;
+			if(slab == kSpecNone){
+				if(g.lane() == 0){ slab = spec_alloc_slab(sp); }
+#if defined(__CUDA_ARCH__)
+				slab = __shfl_sync(0xffffffffu, slab, 0);
+#endif
+				if(slab == kSpecNone){ failed = true; break; }
+				if(p < 32u){ cur_slab = slab; } else{ next_slab = slab; }
+			}
+			save_snapshot(g, ring, out_snaps[emitted], pos, len, false, hit, cur_meth, read_number, draws);
+			const size_t gidx = static_cast<size_t>(u) * D + emitted;
+			uint64_t *dst = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
+			const uint32_t org_len = rec.len < c.max_org_len ? rec.len : c.max_org_len;
+			const uint32_t assumed = plan_read(g, c, ring, dst, sp.words_per_job, sp.margin, rec.seg, rec.fragment_length, org_len);
+			if(g.lane() == 0){
+				ReadJob j;
+				j.ref_id = pos; j.start_pos = 0; j.end_pos = 0; j.fragment_length = rec.fragment_length; j.block_id = 0;
+				j.flags = rec.seg | 4u | (hit.tile << 8);
+				j.read_number = 0; j.assumed = assumed; j.consumed = kSpecOverflow; j.rec_len = 0; j.slot = slab * 32u + (p & 31u);
+				j.conv_index = kSpecNone; j.pad = 0;
+				jobs[emitted] = j;
+			}
+			++emitted; ++pos;
+		}
+		finished = pos >= len;
+		full = !finished;
+	}
 	while(!finished && !full && !failed){
 		if(hit.active){
 			if(hit.in_reads){
@@ -611,14 +653,20 @@ RSQ_HD void spec_init_unit(const SimCtx &c, const SpecCtx &sp, const BlockDesc *
 	blk.chain_head = kSpecNone; blk.chain_tail = kSpecNone;
 	blk.reads = 0; blk.rounds = 0; blk.bytes[0] = 0; blk.bytes[1] = 0; blk.scan_draws = 0;
 	SpecSnap &s = sp.snaps[static_cast<size_t>(u) * 2u * (sp.depth + 1u)];
-	const bool adapter_only = u >= sp.n_blocks;
-	uint64_t x = adapter_only ? sp.adapter_only_seed : descs[first_desc + u].seed;
+	const bool records = sp.em_recs != nullptr;
+	const bool adapter_only = !records && u >= sp.n_blocks;
+	uint64_t x = records ? sp.em_seeds[u] : (adapter_only ? sp.adapter_only_seed : descs[first_desc + u].seed);
 	s.mt[0] = x;
 	for(int i = 1; i < kMtN; ++i){ x = 6364136223846793005ull * (x ^ (x >> 62)) + static_cast<uint64_t>(i); s.mt[i] = x; }
 	s.mt_off = kMtN;   // the whole generation is consumed: the first ring_ensure produces generation 1
-	s.finished = 0; s.read_number = 0; s.scan_draws = 0; s.cur_meth = adapter_only ? 0 : descs[first_desc + u].first_meth;
+	s.finished = 0; s.read_number = 0; s.scan_draws = 0; s.cur_meth = (adapter_only || records) ? 0 : descs[first_desc + u].first_meth;
 	SpecHit h{};
-	if(adapter_only){
+	if(records){
+		const uint64_t first = static_cast<uint64_t>(u) * sp.em_batch, last = first + sp.em_batch;
+		s.pos = static_cast<uint32_t>(first); s.len = static_cast<uint32_t>(last < sp.em_n ? last : sp.em_n);
+		if(s.pos >= s.len){ spec_unit_done(sp, &blk.done); }
+	}
+	else if(adapter_only){
 		s.pos = 0; s.len = 0;
 		h.active = 1; h.in_reads = 1; h.fragment_length = 0; h.n_chosen = 1; h.counts_left = sp.adapter_only_pairs;
 		if(0 == sp.adapter_only_pairs){ spec_unit_done(sp, &blk.done); }
@@ -647,7 +695,7 @@ struct ReadMachine {
 	// output
 	uint8_t *seq_out, *qual_out; char *id; int id_len, id_cap, cigar_len;
 	// job
-	uint32_t seg, tile, fragment_length;
+	uint32_t seg, tile, fragment_length, record_out;
 	// original sequence of the current part: base = comp ? 3 - org[step * pos] : org[step * pos]; sys[2 * pos] / [2 * pos + 1]
 	const uint8_t *org; int32_t org_step; uint32_t org_comp; const uint8_t *sys;
 	uint32_t org_pos, org_len;
@@ -711,8 +759,17 @@ struct ReadMachine {
 		read_length = c.read_len_from[seg];
 		if(1 != c.read_len_count[seg]){ read_length = read_length_from(c, seg, fragment_length, next_u()); }
 		if(read_length > c.max_read_len){ read_length = c.max_read_len; spec_flag(c, kErrOrgOverflow); }
+		const bool record_job = (j.flags & 4u) != 0u;
+		record_out = record_job ? 1u : 0u;
 		// CreateReadId up to the CIGAR (everything the read itself does not change)
-		{
+		if(record_job){   // seqToIllumina: the input id, a blank, then CIGAR and error count
+			SingleLane one;
+			const EmRecord rec = sp.em_recs[j.ref_id];
+			int n = put_str(one, id, 0, id_cap, sp.em_ids + rec.id_off, rec.id_len);
+			n = put_char(one, id, n, id_cap, ' ');
+			id_len = n;
+		}
+		else{
 			SingleLane one;
 			uint32_t print_start = 0, print_end = 0;
 			if(fragment_length){
@@ -738,7 +795,7 @@ struct ReadMachine {
 		}
 		// GetOrgSeq without variants
 		org_len = 0; org_pos = 0; org = c.ref; org_step = 1; org_comp = 0; sys = c.sys_fwd;
-		if(fragment_length){
+		if(fragment_length && !record_job){
 			org_len = fragment_org_len(c, seg, fragment_length);
 			if(c.read_len_to[seg] + c.max_len_deletion > c.max_org_len && fragment_length > c.max_org_len){ spec_flag(c, kErrOrgOverflow); }
 			const uint64_t off = c.seq_off[j.ref_id];
@@ -747,6 +804,12 @@ struct ReadMachine {
 			if(!reversed){ org = c.ref + off + j.start_pos; sys = c.sys_fwd + 2 * (off + j.start_pos); }
 			else{ org = c.ref + off + j.end_pos - 1; org_step = -1; org_comp = 1; sys = c.sys_rev + 2 * (off + (L - j.end_pos)); }
 			if(j.conv_index != kSpecNone){ org = sp.conv + static_cast<size_t>(j.conv_index) * kMaxOrgLen; org_step = 1; org_comp = 0; }   // bisulfite-converted end
+		}
+		if(record_job){
+			const EmRecord rec = sp.em_recs[j.ref_id];
+			org = sp.em_seq + rec.seq_off; org_step = 1; org_comp = 0; sys = sp.em_sys + 2 * rec.seq_off;
+			org_len = rec.len < c.max_org_len ? rec.len : c.max_org_len;
+			if(rec.len > c.max_org_len){ spec_flag(c, kErrOrgOverflow); }
 		}
 		adapter_id = 0; tail_left = 0;
 		const uint32_t seq_length = read_length < org_len ? read_length : org_len;
@@ -813,7 +876,7 @@ struct ReadMachine {
 		n = put_uint(one, id, n, id_cap, num_errors);
 		if(n > id_cap){ spec_flag(c, kErrRecordTooLong); n = id_cap; }
 		uint32_t *hdr = reinterpret_cast<uint32_t *>(slot);
-		hdr[0] = static_cast<uint32_t>(n); hdr[1] = read_length; hdr[2] = seg; hdr[3] = 0;
+		hdr[0] = static_cast<uint32_t>(n); hdr[1] = read_length; hdr[2] = record_out ? 0u : seg; hdr[3] = 0;
 		return 1u + n + 1u + read_length + 3u + read_length + 1u;
 	}
 };

@@ -189,11 +189,30 @@ def test_dropin_simulate_call_writes_files(rb, golden, workdir, monkeypatch, bat
     assert open(o2, "rb").read() == open(golden["r2"], "rb").read()
 
 
-def test_error_model_bit_exact(engine, golden, workdir):
-    out = os.path.join(workdir, "em_gpu.fq")
+@pytest.mark.parametrize("path", ["spec", "serial"])
+def test_error_model_bit_exact(engine, golden, workdir, monkeypatch, path):
+    """seqToIllumina (ApplyErrorsAndQualityToFastaInput) against the reference's output, on the speculative kernels (the batch of
+    input records is one unit of reads in lock step) and on the serial kernel (one warp per batch)."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    out = os.path.join(workdir, f"em_gpu_{path}.fq")
     rep = engine.apply_error_model(golden["em_in"], out, 7)
     assert open(out, "rb").read() == open(golden["em_out"], "rb").read()
     assert rep.pairs == 9000
+    assert (rep.spec_rounds > 0) == (path == "spec")
+
+
+def test_error_model_batches_serial_and_speculative_agree(engine, golden, workdir, monkeypatch):
+    """Several batches = several units of the speculative kernels.  The reference cannot run more than one batch (its writer waits
+    for a counter nobody increments, Simulator.cpp:184-213), so the batch size is shrunk and the two kernel forms are compared."""
+    monkeypatch.setenv("RSQ_EM_BATCH", "700")
+    outs = []
+    for path in ("serial", "spec"):
+        monkeypatch.setenv("RSQ_SIM_PATH", path)
+        out = os.path.join(workdir, f"em_batches_{path}.fq")
+        rep = engine.apply_error_model(golden["em_in"], out, 7)
+        assert rep.pairs == 9000 and rep.blocks == 13
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] and outs[0].count(b"\n") == 4 * 9000
 
 
 def test_error_model_rejects_malformed_header(engine, workdir):
