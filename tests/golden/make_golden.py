@@ -11,6 +11,8 @@ Run in the build container (needs /root/reference for the TruSeq adapter files a
                                         Estimate + PrepareResult for that profile (dump_tables profile)
   profile150r.{reseq,reseq.ipf,flat}.xz same pipeline with a realistic InDel rate in the synthetic SAM (2e-5 per base for insertions and
                                         for deletions instead of 8e-4): the bench profile; profile150 stays the InDel stress profile
+  profile150t.{reseq,reseq.ipf,flat}.xz same pipeline, `--tiles`, from a SAM with Casava-1.8 read names on three tiles and 20 % of the reads 144
+                                        instead of 150 bases long: per-tile tables, tile and read-length draws
   simref_small.fa                       small multi-contig reference with N runs and one too-short contig
   sim_small_seed42_R{1,2}.fq.xz         `reseq illuminaPE -j 1 --seed 42 -c 20` on simref_small.fa
   simref_small_meth.bed, sim_small_meth_seed42_R{1,2}.fq.xz   same run with `--methylation` (bisulfite C->T conversions)
@@ -98,6 +100,23 @@ def main():
     shutil.copy(raw_r + ".ipf", prof_r + ".ipf")
     run([DUMP, "profile", prof_r, os.path.join(tmp, "profile150r.flat")])
     for name in ("profile150r.reseq", "profile150r.reseq.ipf", "profile150r.flat"):
+        xz(os.path.join(tmp, name), os.path.join(HERE, name + ".xz"))
+
+    # three tiles, two read lengths
+    sam_t = os.path.join(tmp, "prof_t.sam")
+    run([py, SYN, "sam", ref, sam_t, "--pairs", "24000", "--seed", "13", "--read-len", "150", "--indel-rate", "0.0002",
+         "--tiles", "1101,1102,2205", "--alt-len", "144", "--alt-frac", "0.2"])
+    raw_t = os.path.join(tmp, "raw_t.reseq")
+    run([ORACLE, "illuminaPE", "-j", "8", "-b", sam_t, "-r", ref, "--adapterFile", ADAPTERS + ".fa", "--adapterMatrix", ADAPTERS + ".mat",
+         "--statsOnly", "--tiles", "-S", raw_t])
+    log = run([ORACLE, "illuminaPE", "-j", "8", "-s", raw_t, "-r", ref, "--stopAfterEstimation"])
+    if "did not reach precision aim" in log:
+        raise SystemExit("IPF did not converge for every table of the tile profile")
+    prof_t = os.path.join(tmp, "profile150t.reseq")
+    run([DUMP, "patch", raw_t, prof_t, "5"])
+    shutil.copy(raw_t + ".ipf", prof_t + ".ipf")
+    run([DUMP, "profile", prof_t, os.path.join(tmp, "profile150t.flat")])
+    for name in ("profile150t.reseq", "profile150t.reseq.ipf", "profile150t.flat"):
         xz(os.path.join(tmp, name), os.path.join(HERE, name + ".xz"))
 
     small = os.path.join(HERE, "simref_small.fa")

@@ -284,6 +284,25 @@ def test_realistic_indel_profile_against_reference_binary(rb, golden, oracle, wo
     assert r2 == open(o2, "rb").read()
 
 
+@pytest.mark.parametrize("path", ["spec", "serial"])
+def test_tiles_and_read_lengths_profile_against_reference_binary(rb, golden, oracle, workdir, monkeypatch, path):
+    """profile150t: three tiles (a tile is drawn per pair, GeneralRandomDistributions::TileId, and selects the quality / base-call
+    tables) and two read lengths per segment (GeneralRandomDistributions::ReadLength draws one per read)."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    eng = rb.Engine(rb.Profile.load_flat(golden["flat_t"]), 0)
+    try:
+        ref = rb.Reference.load_fasta(golden["small_ref"])
+        r1, r2, _ = _simulate(eng, ref, seed=11, coverage=25.0)
+    finally:
+        eng.close()
+    o1, o2 = run_oracle_sim(oracle, golden["reseq_t"], golden["small_ref"], 11, 25.0, os.path.join(workdir, "ora_t_" + path))
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+    tiles = {line.split(b":")[4] for line in r1.split(b"\n")[0::4] if line}
+    assert tiles == {b"1101", b"1102", b"2205"}
+    assert {len(s) for s in r1.split(b"\n")[1::4]} == {144, 150}
+
+
 def test_other_reference_and_prefix_against_reference_binary(rb, engine, golden, oracle, workdir):
     fa = os.path.join(workdir, "other.fa")
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic.py"), "reference", fa, "--sizes", "61000,1001,2500", "--seed", "99",

@@ -87,6 +87,22 @@ def test_speculative_two_phase_templates_match_reference(oracle, golden, twin, w
     assert filecmp.cmp(prefix + "_2.fq", golden["r2"], shallow=False)
 
 
+@pytest.mark.parametrize("spec_depth", [None, "4"])
+def test_templates_match_reference_with_tiles_and_read_lengths(oracle, golden, twin, workdir, spec_depth):
+    """Three tiles and two read lengths per segment (profile150t): tile draw per pair, read-length draw per read."""
+    stage = os.path.join(workdir, "stage_t.flat")
+    if not os.path.exists(stage):
+        subprocess.run([oracle["dump"], "sim", golden["reseq_t"], golden["small_ref"], "11", "25", stage], check=True, timeout=600,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r1, r2 = run_oracle_sim(oracle, golden["reseq_t"], golden["small_ref"], 11, 25, os.path.join(workdir, "ora_t"))
+    prefix = os.path.join(workdir, "twin_t" + (spec_depth or ""))
+    env = dict(os.environ, RSQ_TWIN_SPEC=spec_depth) if spec_depth else dict(os.environ)
+    res = subprocess.run([twin, stage, "11", prefix, "66"], capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0 and "error_flag=0" in res.stdout, res.stdout
+    assert filecmp.cmp(prefix + "_1.fq", r1, shallow=False)
+    assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
+
+
 def test_speculative_adapter_only_pairs_match_serial_templates(oracle, golden, twin, workdir):
     """Adapter-only pairs (SimulateAdapterOnlyPairs; none in the golden profile) forced on: serial and speculative forms agree."""
     stage = os.path.join(workdir, "stage_spec.flat")

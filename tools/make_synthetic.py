@@ -139,7 +139,9 @@ def simulate_read(rng, template, read_len, seg):
     return "".join(seq), qual, cigar, tpos
 
 
-def gen_sam(ref_path, out_path, pairs, read_len, seed):
+def gen_sam(ref_path, out_path, pairs, read_len, seed, tiles=None, alt_len=0, alt_frac=0.0):
+    """tiles: list of tile numbers -> Casava >= 1.8 read names (instrument:run:flowcell:lane:TILE:x:y) and a tile-dependent
+    quality level; alt_len/alt_frac: that share of the reads is `alt_len` bases long instead of read_len (both lengths end up in the profile)."""
     rng = np.random.default_rng(seed)
     names, seqs = read_fasta(ref_path)
     lens = np.array([len(s) for s in seqs], dtype=np.int64)
@@ -167,9 +169,11 @@ def gen_sam(ref_path, out_path, pairs, read_len, seed):
         fwd_template = frag + (ADAPTER1 if strand == 0 else ADAPTER2) + polya
         rev_template = revcomp(frag) + (ADAPTER2 if strand == 0 else ADAPTER1) + polya
         # the forward-mapping read is segment `strand`; the reverse-mapping read the other one
-        fseq, fqual, fcig, _ = simulate_read(rng, fwd_template, read_len, strand)
-        rseq, rqual, rcig, _ = simulate_read(rng, rev_template, read_len, 1 - strand)
-        if len(fseq) < read_len or len(rseq) < read_len:
+        len_f = alt_len if (alt_len and rng.random() < alt_frac) else read_len
+        len_r = alt_len if (alt_len and rng.random() < alt_frac) else read_len
+        fseq, fqual, fcig, _ = simulate_read(rng, fwd_template, len_f, strand)
+        rseq, rqual, rcig, _ = simulate_read(rng, rev_template, len_r, 1 - strand)
+        if len(fseq) < len_f or len(rseq) < len_r:
             continue
 
         def ref_span(cig):
@@ -186,6 +190,13 @@ def gen_sam(ref_path, out_path, pairs, read_len, seed):
         cig_f = "".join(f"{n}{op}" for op, n in fcig)
         cig_r = "".join(f"{n}{op}" for op, n in rcig_ref)
         qname = f"sim{n_done}"
+        if tiles:
+            tile_idx = int(rng.integers(0, len(tiles)))
+            qname = f"SYN1:7:FCSYN:1:{tiles[tile_idx]}:{int(rng.integers(1000, 20000))}:{n_done + 1000}"
+            if tile_idx:   # later tiles are a bit worse: the per-tile tables differ
+                fqual = [max(2, q - 2 * tile_idx) if (i % 3 == 0) else q for i, q in enumerate(fqual)]
+                rqual = [max(2, q - 2 * tile_idx) if (i % 3 == 0) else q for i, q in enumerate(rqual)]
+                rqual_ref = rqual[::-1]
         flag_f = 1 | 2 | 32 | (64 if strand == 0 else 128)
         flag_r = 1 | 2 | 16 | (128 if strand == 0 else 64)
         tlen = flen
@@ -241,6 +252,9 @@ def main():
     b.add_argument("--read-len", type=int, default=150)
     b.add_argument("--seed", type=int, default=11)
     b.add_argument("--indel-rate", type=float, default=0.0008, help="per-base rate of insertions, and of deletions")
+    b.add_argument("--tiles", default="", help="comma separated tile numbers (Casava 1.8 read names)")
+    b.add_argument("--alt-len", type=int, default=0)
+    b.add_argument("--alt-frac", type=float, default=0.0)
     c = sub.add_parser("fragments")
     c.add_argument("ref")
     c.add_argument("sys")
@@ -254,7 +268,7 @@ def main():
     elif args.cmd == "sam":
         global INDEL_RATE
         INDEL_RATE = args.indel_rate
-        gen_sam(args.ref, args.out, args.pairs, args.read_len, args.seed)
+        gen_sam(args.ref, args.out, args.pairs, args.read_len, args.seed, [int(t) for t in args.tiles.split(",")] if args.tiles else None, args.alt_len, args.alt_frac)
     else:
         gen_fragments(args.ref, args.sys, args.out, args.n, args.len, args.seed)
 
