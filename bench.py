@@ -6,7 +6,8 @@
 
 One step = one pass of the hot path over the whole workload: systematic-error drawing for both strands,
 the (position x fragment length) scan, read generation and the ordered FASTQ gather.
-  value : pairs / device time of those kernels (CUDA events), inputs (reference, tables, normalisation) resident in HBM
+  value : pairs / device time of those kernels (CUDA events: bias normalisation as far as it is not hidden behind the systematic
+          errors, systematic errors, simulate, gather), inputs (reference bases, probability tables) resident in HBM
   e2e   : pairs / wall time of the C-ABI calls prepare + simulate + download with HOST buffers in and out
           (reference bases host->device, FASTQ text device->pinned host, every step)
 N > 1 (torchrun): the run's SimBlocks are split into N contiguous shards, one per rank/GPU ("strong" scaling:
@@ -219,7 +220,7 @@ def run_b200(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    dev_ms = sum(r["ms_syserr"] + r["ms_simulate"] + r["ms_gather"] for r in reps)
+    dev_ms = sum(r["ms_bias"] + r["ms_syserr"] + r["ms_simulate"] + r["ms_gather"] for r in reps)
     sim_ms = sum(r["ms_simulate"] for r in reps)
     pairs = sum(r["pairs"] for r in reps)
     positions = sum(r["positions"] for r in reps)
