@@ -8,10 +8,13 @@
 //   sys_fwd, sys_rev    2 bytes / base / strand       -> (dominant error, rate) of SetSystematicErrors
 //   master      raw mt19937_64 outputs of one SimUnit (2*blocks + 4*L words), reused per sequence
 //   blocks      BlockDesc[] (seed, ref, start, id)
-//   arena       fixed-size chunks of FASTQ text, per (block, segment) chains; gathered into two
-//               contiguous buffers in block order, then copied to pinned host memory.
-// Kernels: k_surroundings, k_sum_bias, k_master_stream, k_sys_chunks (+k_sys_check), k_adapter_sys,
-//          k_build_blocks, k_simulate (warp per SimBlock), k_block_offsets, k_gather, k_error_model.
+//   per batch of SimBlocks (speculative path, spec_core.cuh): snapshots, read jobs, stream slices, record slots in slabs of 32
+//               chained per block; the FASTQ text of a batch is gathered in block order into one of two device buffers and
+//               pulled to the host by the writer threads (ChunkWriter) while the next batch is simulated
+//   arena       serial path only: fixed-size chunks of FASTQ text, per (block, segment) chains
+// Kernels: k_surroundings, k_gc_*, k_sum_bias, k_master_seed/_stream/_jump_gen/_jump_xor, k_sys_chunks_lanes (k_sys_chunks) + k_sys_check,
+//          k_build_blocks, k_spec_init/_scan/_reads/_block_out/_gather (product path), k_simulate + k_adapter_only + k_gather and
+//          k_error_model (serial forms: cross-check and fallback), k_block_offsets.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -934,7 +937,7 @@ struct rsq_engine {
 	DevBuf<unsigned char> d_out_batch[2][2];
 	PinnedBuf h_ring[4]; cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
 	HostBig h_big[2];   // text of runs that arrive in several batches (ordinary memory: pinning tens of GB takes longer than the run)
-	cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr; cudaEvent_t ev_out[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+	cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr; cudaEvent_t ev_out[2] = {nullptr, nullptr};
 	FILE *sink_files[2] = {nullptr, nullptr};
 	bool streamed_to_host = false; int last_par = 0;
 	double reusable_bytes() const;
@@ -947,7 +950,7 @@ struct rsq_engine {
 	uint32_t spec_rounds = 0, spec_depth = 0;
 	std::vector<cudaStream_t> spec_streams; std::vector<cudaEvent_t> spec_events;
 
-	~rsq_engine(){ for(int i = 0; i < 4; ++i){ if(ev_ring[i]){ cudaEventDestroy(ev_ring[i]); } } for(int i = 0; i < 2; ++i){ if(ev_out[i]){ cudaEventDestroy(ev_out[i]); } if(ev_copied[i]){ cudaEventDestroy(ev_copied[i]); } } if(copy_stream){ cudaStreamDestroy(copy_stream); } if(copy_stream2){ cudaStreamDestroy(copy_stream2); } for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
+	~rsq_engine(){ for(int i = 0; i < 4; ++i){ if(ev_ring[i]){ cudaEventDestroy(ev_ring[i]); } } for(int i = 0; i < 2; ++i){ if(ev_out[i]){ cudaEventDestroy(ev_out[i]); } } if(copy_stream){ cudaStreamDestroy(copy_stream); } if(copy_stream2){ cudaStreamDestroy(copy_stream2); } for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
 };
 
 double rsq_engine::reusable_bytes() const {
@@ -1532,7 +1535,6 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 // reset counters with a contiguous run of the master stream (no block seeds, no adapters).
 static void create_sys_profile(rsq_engine &e, const Genome &g, uint64_t seed, const char *out_path){
 	cudaStream_t s = e.stream;
-	const Profile &p = e.prof;
 	e.launches = 0; e.d_error_flag.zero(s);
 	for(const auto &q : g.seqs){ for(uint8_t b : q){ if(b > 3){ throw std::runtime_error("Reference contains ambiguous bases(e.g. N). Please replace them, remove them from the scaffolds or split scaffolds into contigs."); } } }
 	// The reference never initialises sys_gc_range_ on this path (it is only set inside Simulate / SimulateErrorModelOnly,
@@ -1950,7 +1952,7 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	const bool to_files = e.sink_files[0] != nullptr;
 	const bool stream_host = !to_files && n_batches > 1;
 	if(!e.copy_stream){ RSQ_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking)); }
-	for(int i = 0; i < 2; ++i){ if(!e.ev_out[i]){ RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_out[i], cudaEventDisableTiming)); RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_copied[i], cudaEventDisableTiming)); } }
+	for(int i = 0; i < 2; ++i){ if(!e.ev_out[i]){ RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_out[i], cudaEventDisableTiming)); } }
 	ChunkWriter writer[2];
 	const bool streaming = to_files || stream_host;
 	if(streaming){
