@@ -10,8 +10,10 @@ the (position x fragment length) scan, read generation and the ordered FASTQ gat
           errors, systematic errors, simulate, gather), inputs (reference bases, probability tables) resident in HBM
   e2e   : pairs / wall time of the C-ABI calls prepare + simulate + download with HOST buffers in and out
           (reference bases host->device, FASTQ text device->pinned host, every step)
-N > 1 (torchrun): the run's SimBlocks are split into N contiguous shards, one per rank/GPU ("strong" scaling:
-the workload is fixed); only pair counts and times cross ranks (NCCL all-reduce).
+N > 1 (torchrun): weak scaling - the reference grows to N sequences of the C2 length (N x 4.64 Mbp, 30x), whose SimBlocks are split
+into N contiguous shards, one per rank/GPU (per-GPU work fixed); no collective on the data path, only pair counts and times
+cross ranks (NCCL all-reduce).  Every rank still runs the prologue (normalisation, master stream, systematic errors) for the
+whole reference.
 --impl reference: the reference's own CPU Simulator (oracle/_ref/reseq_oracle, built from the unmodified sources)
 with all host threads, each step on a bounded slice of the same workload.
 """
@@ -54,6 +56,12 @@ def unxz(name, tmp):
 def workload_sequence(length=REF_LEN):
     import make_synthetic
     return make_synthetic.gen_reference([length], 1234)[0]
+
+
+def workload_sequences(n, length=REF_LEN):
+    """N sequences of the C2 length; the first one is the N=1 workload."""
+    import make_synthetic
+    return make_synthetic.gen_reference([length] * n, 1234)
 
 
 def hbm_peak():
@@ -169,8 +177,8 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "simulated read-pairs/s (2x150)", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * statistics.mean(secs), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: 4,641,652 bp synthetic E. coli-sized reference, 2x150 synthetic profile, 30x coverage, seed 42"},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C2: 4,641,652 bp synthetic E. coli-sized reference, 2x150 synthetic profile ({PROFILE}), 30x coverage, seed 42"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -198,12 +206,13 @@ def run_b200(args):
 
     tmp = tempfile.mkdtemp(prefix="rsq_bench_")
     prof = rb.Profile.load_flat(unxz(PROFILE + ".flat.xz", tmp))
-    seq = workload_sequence().encode()
+    seqs = [q.encode() for q in workload_sequences(world)]
+    names = ["ecoli_sized synthetic"] + [f"ecoli_sized{i + 1} synthetic" for i in range(1, world)]
     eng = rb.Engine(prof, local_rank)
 
     def step():
         # host buffers in (reference bases), host buffers out (FASTQ text in pinned memory)
-        ref = rb.Reference.from_memory(["ecoli_sized synthetic"], [seq])
+        ref = rb.Reference.from_memory(names, seqs)
         eng.prepare(ref, seed=SEED, coverage=COVERAGE, shard_index=rank, shard_count=world)
         eng.simulate()
         rep = eng.download()
@@ -246,15 +255,16 @@ def run_b200(args):
         line = {
             "metric": "simulated read-pairs/s (2x150)", "value": pairs_all / (dev_ms / 1000.0), "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2: 4,641,652 bp synthetic E. coli-sized reference, 2x150 synthetic profile ({PROFILE}), 30x coverage, seed 42",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2: 4,641,652 bp synthetic E. coli-sized reference, 2x150 synthetic profile ({PROFILE}), 30x coverage, seed 42"
+                                   + (f"; x{world} sequences of that length for {world} GPUs (weak scaling: one sequence's worth of SimBlocks per GPU)" if world > 1 else ""),
                        "simulation_path": f"speculative two-phase, {reps[-1]['spec_rounds']} rounds, first depth {reps[-1]['spec_depth']}" if spec else "serial (one warp per SimBlock)",
                        "l2": "per-step working set (reference 4.6 MB + 2x9.3 MB systematic errors + 74 MB surroundings + ~340 MB FASTQ arena) exceeds the 126 MB L2; "
                              "every step re-uploads the reference and rewrites all of it",
                        "pairs_per_step": pairs_all / args.steps, "blocks_per_step": sum(r["blocks"] for r in reps) / args.steps,
                        "device_ms_breakdown_rank0": {k: sum(r[k] for r in reps) / args.steps for k in ("ms_upload", "ms_bias", "ms_syserr", "ms_simulate", "ms_gather", "ms_download")},
                        "scan_draws_per_s": sum(r["scan_draws"] for r in reps) / (sim_ms / 1000.0) if sim_ms else None},
-            "e2e": {"value": pairs_all / wall, "unit": "pairs/s", "h2d_bytes_per_step": len(seq), "d2h_bytes_per_step": d2h_all / args.steps,
+            "e2e": {"value": pairs_all / wall, "unit": "pairs/s", "h2d_bytes_per_step": world * sum(len(q) for q in seqs), "d2h_bytes_per_step": d2h_all / args.steps,
                     "ms_per_step": 1000 * wall / args.steps},
             "gpu_launches": int(launches_all),
             "clocks": clocks,

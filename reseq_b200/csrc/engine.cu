@@ -910,7 +910,7 @@ struct rsq_engine {
 	DevBuf<double> d_sur_start, d_sur_end, d_thr, d_binom_p0;
 	DevBuf<uint64_t> d_thr_int;
 	DevBuf<char> d_names;
-	DevBuf<uint64_t> d_master_state, d_master, d_jump_states, d_jump_poly, d_jump_seq;
+	DevBuf<uint64_t> d_master_state, d_master, d_jump_states, d_jump_poly, d_jump_seq, d_jump_scratch;
 	DevBuf<BlockDesc> d_blocks;
 	DevBuf<SysChain> d_sys_chains; DevBuf<SysChunk> d_sys_chunks; DevBuf<uint32_t> d_sys_dirty, d_gc_tiles;
 	DevBuf<BiasParamDev> d_bias_params; DevBuf<double> d_bias_sums, d_bias_max;
@@ -1118,6 +1118,37 @@ static void master_generate(rsq_engine &e, uint64_t *out, uint64_t n){
 	// remainder from the state behind the last segment
 	RSQ_CUDA(cudaMemcpyAsync(e.d_master_state.p, e.d_jump_states.p + segments * kMasterStateWords, kMasterStateWords * 8, cudaMemcpyDeviceToDevice, s));
 	k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, out + segments * J, n - segments * J); ++e.launches;
+}
+
+// Advances the master stream by n outputs without producing them: the remainder below 1024 (and the first 1024, so that the
+// window holds generated words) by the serial recurrence into scratch, the rest bit by bit with the jump polynomials for 2^10 .. 2^36.
+static void master_skip(rsq_engine &e, uint64_t n){
+	cudaStream_t s = e.stream;
+	if(!n){ return; }
+	uint64_t serial = n % 1024;
+	if(n >= 1024){ serial += 1024; }
+	if(serial){
+		e.d_jump_scratch.alloc(2048);
+		k_master_stream<<<1, kMasterThreads, 0, s>>>(e.d_master_state.p, e.d_master_state.p, e.d_jump_scratch.p, serial); ++e.launches;
+	}
+	uint64_t rest = n - serial;
+	if(!rest){ return; }
+	if(rest >> (kMtJumpLog2[kMtJumpTables - 1] + 1)){ throw std::runtime_error("master stream skip beyond the largest jump polynomial"); }
+	if(!e.d_jump_poly.p){
+		std::vector<uint64_t> polys(static_cast<size_t>(kMtJumpTables) * kMtN);
+		std::memcpy(polys.data(), kMtJumpPoly, polys.size() * 8);
+		e.d_jump_poly.upload(polys, s);
+		RSQ_CUDA(cudaFuncSetAttribute(k_master_jump_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, kJumpSeqWords * 8));
+		e.d_jump_seq.alloc(kJumpSeqWords);
+	}
+	e.d_jump_states.alloc(2 * kMasterStateWords);
+	for(int t = 0; t < kMtJumpTables; ++t){
+		if(!((rest >> kMtJumpLog2[t]) & 1ull)){ continue; }
+		k_master_jump_gen<<<1, kMasterThreads, kJumpSeqWords * 8, s>>>(e.d_master_state.p, e.d_jump_seq.p, e.d_jump_states.p);
+		k_master_jump_xor<<<(kMtN + kJumpPolyWordsPerCta - 1) / kJumpPolyWordsPerCta, 320, 0, s>>>(e.d_jump_seq.p, e.d_jump_poly.p + static_cast<size_t>(t) * kMtN, e.d_jump_states.p);
+		RSQ_CUDA(cudaMemcpyAsync(e.d_master_state.p, e.d_jump_states.p, kMasterStateWords * 8, cudaMemcpyDeviceToDevice, s));
+		e.launches += 2;
+	}
 }
 
 // Systematic errors of a set of chains: speculative chunks + exact fix-up passes.
@@ -1452,11 +1483,28 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	e.d_blocks.alloc(nb_total);
 	uint32_t next_block_id = 1, first = 0;
 	std::vector<uint8_t> decoded;
+	// this engine's shard of the run: systematic errors and block seeds are only needed for the sequences it has blocks in
+	// (fragments never span sequences); the master-stream draws of the others are skipped by jump-ahead
+	const uint32_t lookahead_blocks = 1 + c.insert_to / 1000;
+	const uint32_t n_sim_blocks = nb_total > lookahead_blocks ? nb_total - lookahead_blocks : 0;
+	const uint32_t shard_count_pre = opt.shard_count ? opt.shard_count : 1;
+	if(opt.shard_index >= shard_count_pre){ throw std::runtime_error("shard_index out of range"); }
+	const uint64_t shard_lo = static_cast<uint64_t>(n_sim_blocks) * opt.shard_index / shard_count_pre;
+	const uint64_t shard_hi = static_cast<uint64_t>(n_sim_blocks) * (opt.shard_index + 1) / shard_count_pre;
 	for(size_t i = 0; i < g.seqs.size(); ++i){
 		const uint32_t L = g.seqs[i].size();
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
 		const uint64_t n_draws = 2ull * nb + (from_file ? 0ull : 4ull * L);
+		const bool needed = shard_count_pre == 1 || (first < shard_hi && shard_lo < static_cast<uint64_t>(first) + nb);
+		if(!needed && !from_file){
+			master_skip(e, n_draws);
+			const uint8_t *hseq = g.seqs[i].data();
+			carried = dominant_before(hseq, L, true, L, carried);
+			carried = dominant_before(hseq, L, false, L, carried);
+			next_block_id += nb; first += nb;
+			continue;
+		}
 		master_generate(e, e.d_master.p, n_draws);
 		if(from_file){
 			// CreateUnit: LoadSysErrorRecord (reverse strand) ... LoadSysErrorRecord (forward strand), strictly in file order

@@ -359,13 +359,18 @@ def test_cli_dropin(golden, workdir, library):
     assert res.returncode == 1 and "does not replace" in res.stderr
 
 
-def test_shards_concatenate_to_the_whole_run(rb, engine, golden):
+@pytest.mark.parametrize("shards", [3, 7])
+def test_shards_concatenate_to_the_whole_run(rb, engine, golden, shards):
+    """A shard only computes systematic errors and block seeds for the sequences it has SimBlocks in; the master-stream draws
+    of the other sequences are skipped by jump-ahead (master_skip).  simref_small has four sequences (30 + 22 + 0 + 15 blocks),
+    so with 3 and 7 shards every shard skips at least one sequence, in front of, between and behind the ones it needs."""
     ref = rb.Reference.load_fasta(golden["small_ref"])
     w1, w2, rep = _simulate(engine, ref, seed=42, coverage=20.0)
     whole = (w1, w2, int(rep.pairs))   # the engine reuses one report object
+    assert w1 == open(golden["r1"], "rb").read()
     parts1, parts2, pairs = b"", b"", 0
-    for i in range(3):
-        a, b, rep = _simulate(engine, ref, seed=42, coverage=20.0, shard_index=i, shard_count=3)
+    for i in range(shards):
+        a, b, rep = _simulate(engine, ref, seed=42, coverage=20.0, shard_index=i, shard_count=shards)
         parts1 += a
         parts2 += b
         pairs += rep.pairs
