@@ -50,7 +50,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build() and os.path.exists(CLI):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + ["-lz"]   # zlib: gzip FASTQ/FASTA/BED either side of the path
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode:
         sys.stderr.write(res.stdout + res.stderr)

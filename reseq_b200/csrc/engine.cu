@@ -938,7 +938,7 @@ struct rsq_engine {
 	PinnedBuf h_ring[4]; cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
 	HostBig h_big[2];   // text of runs that arrive in several batches (ordinary memory: pinning tens of GB takes longer than the run)
 	cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr; cudaEvent_t ev_out[2] = {nullptr, nullptr};
-	FILE *sink_files[2] = {nullptr, nullptr};
+	TextSink *sink_files[2] = {nullptr, nullptr};   // rsq_simulate: the two FASTQ files (plain or gzip by name)
 	bool streamed_to_host = false; int last_par = 0;
 	double reusable_bytes() const;
 	// speculative two-phase path
@@ -1211,8 +1211,9 @@ static void run_sys_chains(rsq_engine &e, const std::vector<SysChain> &chains, c
 // FASTQ written by CreateSystematicErrorProfile: (id, dominant errors, compressed rates) per record
 struct SysErrorRecord { std::string id, dom, rate; };
 static std::vector<SysErrorRecord> read_sys_error_file(const std::string &path){
-	std::ifstream f(path);
-	if(!f){ throw std::runtime_error("Could not open '" + path + "' for reading."); }
+	TextInput in(path);
+	if(!in.is_open()){ throw std::runtime_error("Could not open '" + path + "' for reading."); }
+	std::istream &f = in.stream();
 	std::vector<SysErrorRecord> recs;
 	std::string id, seq, plus, qual;
 	while(std::getline(f, id)){
@@ -1590,16 +1591,16 @@ static void create_sys_profile(rsq_engine &e, const Genome &g, uint64_t seed, co
 	// whatever the stack held.  In the reference build of this image every value >= ~2*10^4 reproduces its output; we use
 	// the largest uintReadLen, i.e. "all bases seen so far, at most 65535".
 	e.sys_gc_range = 65535;
-	FILE *o = fopen(out_path, "wb");
-	if(!o){ throw std::runtime_error(std::string("Could not open '") + out_path + "' for writing."); }
-	try{
+	TextSink o;
+	if(!o.open(out_path)){ throw std::runtime_error(std::string("Could not open '") + out_path + "' for writing."); }
+	{
 		e.d_master_state.alloc(kMtN + 1);
 		k_master_seed<<<1, 32, 0, s>>>(e.d_master_state.p, seed); ++e.launches;
 		uint32_t carried = 0;
 		std::vector<uint8_t> host; std::string text;
 		for(size_t i = 0; i < g.seqs.size(); ++i){
 			const uint32_t L = g.seqs[i].size();
-			if(!L){ fprintf(o, "@%s reverse\n\n+\n\n@%s forward\n\n+\n\n", g.ids[i].c_str(), g.ids[i].c_str()); continue; }
+			if(!L){ const std::string t = "@" + g.ids[i] + " reverse\n\n+\n\n@" + g.ids[i] + " forward\n\n+\n\n"; if(!o.write(t.data(), t.size())){ throw std::runtime_error("Could not write systematic error profile"); } continue; }
 			e.d_ref.alloc(L + 1);
 			RSQ_CUDA(cudaMemcpyAsync(e.d_ref.p, g.seqs[i].data(), L, cudaMemcpyHostToDevice, s));
 			e.d_master.alloc(4ull * L);
@@ -1627,14 +1628,13 @@ static void create_sys_profile(rsq_engine &e, const Genome &g, uint64_t seed, co
 					qual[pos] = static_cast<char>(q + 33);
 				}
 				dom[L] = '\n'; dom[L + 1] = '+'; dom[L + 2] = '\n'; qual[L] = '\n';
-				if(fwrite(text.data(), 1, text.size(), o) != text.size()){ throw std::runtime_error("Could not write systematic error profile"); }
+				if(!o.write(text.data(), text.size())){ throw std::runtime_error("Could not write systematic error profile"); }
 			}
 		}
 		const uint32_t flag = read_error_flag(e);
 		if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
 	}
-	catch(...){ fclose(o); throw; }
-	fclose(o);
+	if(!o.close()){ throw std::runtime_error("Could not write systematic error profile"); }
 	e.prepared = false;
 }
 
@@ -1932,7 +1932,7 @@ constexpr int kRingSlots = 4;
 struct ChunkWriter {   // one per segment (first / second reads): two files, two threads
 	int device = 0;
 	cudaStream_t copy_stream = nullptr;
-	FILE *f = nullptr;                  // file sink
+	TextSink *f = nullptr;              // file sink (compresses on the host cores when the name asks for it)
 	HostBig *mem = nullptr;             // memory sink (sized in advance)
 	std::thread th;
 	std::mutex m; std::condition_variable cv;
@@ -1944,7 +1944,7 @@ struct ChunkWriter {   // one per segment (first / second reads): two files, two
 	void consume(int slot, uint64_t n, uint64_t dst){
 		if(cudaEventSynchronize(ev[slot]) != cudaSuccess){ error = "copying FASTQ text to the host failed"; return; }
 		if(mem){ std::memcpy(mem->data() + dst, ring[slot].p, n); }
-		else if(!discard && error.empty() && fwrite(ring[slot].p, 1, n, f) != n){ error = "Could not write records to the output file"; }
+		else if(!discard && error.empty() && !f->write(ring[slot].p, n)){ error = "Could not write records to the output file"; }
 	}
 	void run(){
 		cudaSetDevice(device);
@@ -2084,8 +2084,9 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 	SimCtx &c = e.ctx;
 	e.launches = 0; e.d_error_flag.zero(s);
 	// read records (SeqAn FASTA semantics: id = header without '>', sequence = DnaString: non-ACGTU -> A)
-	std::ifstream f(in_path);
-	if(!f){ throw std::runtime_error(std::string("Could not open '") + in_path + "' for reading."); }
+	TextInput in(in_path);
+	if(!in.is_open()){ throw std::runtime_error(std::string("Could not open '") + in_path + "' for reading."); }
+	std::istream &f = in.stream();
 	std::vector<std::string> ids; std::vector<std::string> seqs;
 	{
 		std::string line;
@@ -2215,10 +2216,9 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 	}
 	download(e, rep);
 	RSQ_CUDA(cudaStreamSynchronize(s));
-	FILE *o = fopen(out_path, "wb");
-	if(!o){ throw std::runtime_error(std::string("Could not open '") + out_path + "' for writing."); }
-	fwrite(e.h_out[0].p, 1, e.out_bytes[0], o);
-	fclose(o);
+	TextSink o;
+	if(!o.open(out_path)){ throw std::runtime_error(std::string("Could not open '") + out_path + "' for writing."); }
+	if(!o.write(e.h_out[0].p, e.out_bytes[0]) || !o.close()){ throw std::runtime_error(std::string("Could not write records to '") + out_path + "'"); }
 	if(rep){ rep->ms_simulate = ms_sim; rep->pairs = e.out_pairs; rep->bytes[0] = e.out_bytes[0]; rep->bytes[1] = 0; rep->blocks = n_batches; rep->kernel_launches = e.launches; }
 }
 
@@ -2390,11 +2390,11 @@ int rsq_engine_write(const rsq_engine *engine, const char *first_reads_path, con
 	if(!engine->downloaded){ throw std::runtime_error("rsq_engine_download has not been called"); }
 	const char *paths[2] = {first_reads_path, second_reads_path};
 	for(int seg = 0; seg < 2; ++seg){
-		FILE *o = fopen(paths[seg], "ab");
-		if(!o){ throw std::runtime_error(std::string("Could not open '") + paths[seg] + "' for writing."); }
-		const size_t w = fwrite(engine->streamed_to_host ? engine->h_big[seg].data() : engine->h_out[seg].p, 1, engine->out_bytes[seg], o);
-		fclose(o);
-		if(w != engine->out_bytes[seg]){ throw std::runtime_error(std::string("Could not write records to '") + paths[seg] + "'"); }
+		TextSink o;
+		if(!o.open(paths[seg], true)){ throw std::runtime_error(std::string("Could not open '") + paths[seg] + "' for writing."); }
+		if(!o.write(engine->streamed_to_host ? engine->h_big[seg].data() : engine->h_out[seg].p, engine->out_bytes[seg]) || !o.close()){
+			throw std::runtime_error(std::string("Could not write records to '") + paths[seg] + "'");
+		}
 	}
 	return 0;
 	RSQ_CATCH(1)
@@ -2406,16 +2406,22 @@ int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq
 	rsq_engine *e = rsq_engine_create(profile, device);
 	if(!e){ return 1; }
 	stage_log("rsq_simulate: engine created");
-	for(const char *path : {first_reads_path, second_reads_path}){ FILE *o = fopen(path, "wb"); if(!o){ set_error("Could not open '%s' for writing.", path); rsq_engine_destroy(e); return 1; } fclose(o); }
+	TextSink sinks[2];
+	try{
+		const char *paths[2] = {first_reads_path, second_reads_path};
+		for(int seg = 0; seg < 2; ++seg){ if(!sinks[seg].open(paths[seg])){ set_error("Could not open '%s' for writing.", paths[seg]); rsq_engine_destroy(e); return 1; } }
+	}
+	catch(const std::exception &ex){ set_error("%s", ex.what()); rsq_engine_destroy(e); return 1; }
 	rsq_sim_report local; rsq_sim_report *rep = report ? report : &local;
 	int rc = rsq_engine_prepare(e, ref, opt, rep);
 	if(!rc){
 		// the batches of the run are appended to the two files by a writer thread while the GPU works on the next one
-		e->sink_files[0] = fopen(first_reads_path, "ab"); e->sink_files[1] = fopen(second_reads_path, "ab");
-		if(!e->sink_files[0] || !e->sink_files[1]){ set_error("Could not open '%s' for writing.", e->sink_files[0] ? second_reads_path : first_reads_path); rc = 1; }
-		if(!rc){ rc = rsq_engine_simulate(e, rep); }
-		for(int seg = 0; seg < 2; ++seg){ if(e->sink_files[seg]){ if(fclose(e->sink_files[seg]) && !rc){ set_error("Could not write records to '%s'", seg ? second_reads_path : first_reads_path); rc = 1; } e->sink_files[seg] = nullptr; } }
+		// (plain text, or gzip members compressed on the host cores when the file name ends in .gz)
+		e->sink_files[0] = &sinks[0]; e->sink_files[1] = &sinks[1];
+		rc = rsq_engine_simulate(e, rep);
+		e->sink_files[0] = e->sink_files[1] = nullptr;
 	}
+	for(int seg = 0; seg < 2; ++seg){ if(!sinks[seg].close() && !rc){ set_error("Could not write records to '%s'", seg ? second_reads_path : first_reads_path); rc = 1; } }
 	if(rc){ remove(first_reads_path); remove(second_reads_path); }
 	rsq_engine_destroy(e);
 	stage_log("rsq_simulate: engine destroyed");

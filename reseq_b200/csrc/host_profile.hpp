@@ -26,6 +26,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include "text_io.hpp"
 
 namespace rsq {
 
@@ -321,8 +322,9 @@ struct Genome {
 	// Reference::PrepareMethylationFile + ReadMethylation (Reference.cpp:1132-1322) for a single-allele run:
 	// extended bedGraph lines "<sequence> <start> <end> <methylation>", grouped by sequence in reference order.
 	void read_methylation(const std::string &path){
-		std::ifstream f(path);
-		if(!f){ throw std::runtime_error("Unable to open methylation file " + path); }
+		TextInput in(path);   // BedFileIn reads gzip-compressed files as well
+		if(!in.is_open()){ throw std::runtime_error("Unable to open methylation file " + path); }
+		std::istream &f = in.stream();
 		std::string line;
 		if(!std::getline(f, line)){ throw std::runtime_error("Methylation file is empty: " + path); }
 		while((line.empty() || !line.compare(0, 5, "track")) && std::getline(f, line));
@@ -403,8 +405,9 @@ struct Genome {
 	uint64_t total_size() const { uint64_t s = 0; for(const auto &q : seqs){ s += q.size(); } return s; }
 
 	void read_fasta(const std::string &path){
-		std::ifstream f(path);
-		if(!f){ throw std::runtime_error("Could not open " + path + " for reading."); }
+		TextInput in(path);   // SeqFileIn reads gzip-compressed FASTA as well (recognised by its magic bytes)
+		if(!in.is_open()){ throw std::runtime_error("Could not open " + path + " for reading."); }
+		std::istream &f = in.stream();
 		ids.clear(); seqs.clear();
 		std::string line;
 		while(std::getline(f, line)){
@@ -420,6 +423,7 @@ struct Genome {
 				}
 			}
 		}
+		if(in.corrupt()){ throw std::runtime_error("Could not read " + path + ": corrupt or truncated gzip stream."); }
 		if(seqs.empty()){ throw std::runtime_error(path + " does not contain any reference sequences."); }
 	}
 

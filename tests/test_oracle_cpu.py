@@ -13,7 +13,7 @@ TWIN_DIR = os.path.join(ROOT, "tests", "host_twin")
 
 
 def _compile(src, out, extra=()):
-    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", *extra, "-o", out, os.path.join(TWIN_DIR, src)], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", *extra, "-o", out, os.path.join(TWIN_DIR, src), "-lz"], check=True)
     return out
 
 
