@@ -37,7 +37,8 @@ def golden(workdir):
                       ("em_in", "em_frags.fa.xz"), ("em_out", "em_seed7.fq.xz"),
                       ("meth_r1", "sim_small_meth_seed42_R1.fq.xz"), ("meth_r2", "sim_small_meth_seed42_R2.fq.xz"),
                       ("flat_r", "profile150r.flat.xz"), ("reseq_r", "profile150r.reseq.xz"), ("ipf_r", "profile150r.reseq.ipf.xz"),
-                      ("flat_t", "profile150t.flat.xz"), ("reseq_t", "profile150t.reseq.xz"), ("ipf_t", "profile150t.reseq.ipf.xz")):
+                      ("flat_t", "profile150t.flat.xz"), ("reseq_t", "profile150t.reseq.xz"), ("ipf_t", "profile150t.reseq.ipf.xz"),
+                      ("flat_250", "profile250.flat.xz"), ("reseq_250", "profile250.reseq.xz"), ("ipf_250", "profile250.reseq.ipf.xz")):
         out[key] = _unxz(name, workdir)
     return out
 

@@ -13,6 +13,7 @@ Run in the build container (needs /root/reference for the TruSeq adapter files a
                                         for deletions instead of 8e-4): the bench profile; profile150 stays the InDel stress profile
   profile150t.{reseq,reseq.ipf,flat}.xz same pipeline, `--tiles`, from a SAM with Casava-1.8 read names on three tiles and 20 % of the reads 144
                                         instead of 150 bases long: per-tile tables, tile and read-length draws
+  profile250.{reseq,reseq.ipf,flat}.xz  same pipeline from a SAM with 2x250 reads (the read length of BASELINE config C4), InDel rate 1e-4
   simref_small.fa                       small multi-contig reference with N runs and one too-short contig
   sim_small_seed42_R{1,2}.fq.xz         `reseq illuminaPE -j 1 --seed 42 -c 20` on simref_small.fa
   simref_small_meth.bed, sim_small_meth_seed42_R{1,2}.fq.xz   same run with `--methylation` (bisulfite C->T conversions)
@@ -117,6 +118,22 @@ def main():
     shutil.copy(raw_t + ".ipf", prof_t + ".ipf")
     run([DUMP, "profile", prof_t, os.path.join(tmp, "profile150t.flat")])
     for name in ("profile150t.reseq", "profile150t.reseq.ipf", "profile150t.flat"):
+        xz(os.path.join(tmp, name), os.path.join(HERE, name + ".xz"))
+
+    # 2x250 reads (config C4's read length)
+    sam_l = os.path.join(tmp, "prof_250.sam")
+    run([py, SYN, "sam", ref, sam_l, "--pairs", "20000", "--seed", "17", "--read-len", "250", "--indel-rate", "0.0001"])
+    raw_l = os.path.join(tmp, "raw_250.reseq")
+    run([ORACLE, "illuminaPE", "-j", "8", "-b", sam_l, "-r", ref, "--adapterFile", ADAPTERS + ".fa", "--adapterMatrix", ADAPTERS + ".mat",
+         "--statsOnly", "-S", raw_l])
+    log = run([ORACLE, "illuminaPE", "-j", "8", "-s", raw_l, "-r", ref, "--stopAfterEstimation"])
+    if "did not reach precision aim" in log:
+        raise SystemExit("IPF did not converge for every table of the 2x250 profile")
+    prof_l = os.path.join(tmp, "profile250.reseq")
+    run([DUMP, "patch", raw_l, prof_l, "5"])
+    shutil.copy(raw_l + ".ipf", prof_l + ".ipf")
+    run([DUMP, "profile", prof_l, os.path.join(tmp, "profile250.flat")])
+    for name in ("profile250.reseq", "profile250.reseq.ipf", "profile250.flat"):
         xz(os.path.join(tmp, name), os.path.join(HERE, name + ".xz"))
 
     small = os.path.join(HERE, "simref_small.fa")

@@ -333,6 +333,26 @@ def test_tiles_and_read_lengths_profile_against_reference_binary(rb, golden, ora
     assert {len(s) for s in r1.split(b"\n")[1::4]} == {144, 150}
 
 
+@pytest.mark.parametrize("path,meth", [("spec", False), ("serial", False), ("spec", True)])
+def test_250_base_reads_against_reference_binary(rb, golden, oracle, workdir, monkeypatch, path, meth):
+    """profile250: 2x250 reads, the read length of BASELINE config C4 (Drosophila, methylation BED): longer stream slices, record slots
+    and CIGARs; with bisulfite conversion on the speculative path."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    eng = rb.Engine(rb.Profile.load_flat(golden["flat_250"]), 0)
+    try:
+        ref = rb.Reference.load_fasta(golden["small_ref"])
+        if meth:
+            ref.load_methylation(golden["meth_bed"])
+        r1, r2, _ = _simulate(eng, ref, seed=9, coverage=15.0)
+    finally:
+        eng.close()
+    extra = ("--methylation", golden["meth_bed"]) if meth else ()
+    o1, o2 = run_oracle_sim(oracle, golden["reseq_250"], golden["small_ref"], 9, 15.0, os.path.join(workdir, f"ora_250_{path}_{int(meth)}"), extra=extra)
+    assert r1 == open(o1, "rb").read()
+    assert r2 == open(o2, "rb").read()
+    assert {len(s) for s in r1.split(b"\n")[1::4]} == {250}
+
+
 def test_other_reference_and_prefix_against_reference_binary(rb, engine, golden, oracle, workdir):
     fa = os.path.join(workdir, "other.fa")
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic.py"), "reference", fa, "--sizes", "61000,1001,2500", "--seed", "99",

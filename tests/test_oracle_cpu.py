@@ -103,6 +103,25 @@ def test_templates_match_reference_with_tiles_and_read_lengths(oracle, golden, t
     assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
 
 
+@pytest.mark.parametrize("spec_depth,meth", [(None, False), ("6", False), (None, True), ("32", True)])
+def test_templates_match_reference_with_250_base_reads(oracle, golden, twin, workdir, spec_depth, meth):
+    """profile250: 2x250 reads (BASELINE config C4's read length; longer stream slices, CIGARs and record slots), with and without
+    bisulfite conversion, serial and speculative form."""
+    stage = os.path.join(workdir, "stage_250.flat")
+    if not os.path.exists(stage):
+        subprocess.run([oracle["dump"], "sim", golden["reseq_250"], golden["small_ref"], "9", "15", stage], check=True, timeout=600,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    extra = ("--methylation", golden["meth_bed"]) if meth else ()
+    r1, r2 = run_oracle_sim(oracle, golden["reseq_250"], golden["small_ref"], 9, 15, os.path.join(workdir, f"ora_250_{int(meth)}"), extra=extra)
+    assert {len(s) for s in open(r1, "rb").read().split(b"\n")[1::4]} == {250}
+    prefix = os.path.join(workdir, f"twin_250_{spec_depth}_{int(meth)}")
+    env = dict(os.environ, RSQ_TWIN_SPEC=spec_depth) if spec_depth else dict(os.environ)
+    res = subprocess.run([twin, stage, "9", prefix, "66"] + ([golden["meth_bed"]] if meth else []), capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0 and "error_flag=0" in res.stdout, res.stdout
+    assert filecmp.cmp(prefix + "_1.fq", r1, shallow=False)
+    assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
+
+
 def test_speculative_adapter_only_pairs_match_serial_templates(oracle, golden, twin, workdir):
     """Adapter-only pairs (SimulateAdapterOnlyPairs; none in the golden profile) forced on: serial and speculative forms agree."""
     stage = os.path.join(workdir, "stage_spec.flat")
