@@ -189,36 +189,6 @@ def test_dropin_simulate_call_writes_files(rb, golden, workdir, monkeypatch, bat
     assert open(o2, "rb").read() == open(golden["r2"], "rb").read()
 
 
-@pytest.mark.parametrize("batch", [None, "7"])
-def test_dropin_simulate_call_gzip_files(rb, golden, workdir, monkeypatch, batch):
-    """Output names ending in .gz are written gzip-compressed like SeqAn's SeqFileOut does (members deflated on the host cores by the
-    writer threads); the reference is read from a .fa.gz.  The inflated text is the reference's golden FASTQ."""
-    import gzip
-    if batch:
-        monkeypatch.setenv("RSQ_BATCH_UNITS", batch)
-    fa_gz = os.path.join(workdir, "small_ref_copy.fa.gz")
-    with open(golden["small_ref"], "rb") as f, gzip.open(fa_gz, "wb") as o:
-        o.write(f.read())
-    prof = rb.Profile.load_flat(golden["flat"])
-    ref = rb.Reference.load_fasta(fa_gz)
-    o1, o2 = os.path.join(workdir, f"gz{batch}_1.fq.gz"), os.path.join(workdir, f"gz{batch}_2.fq.gz")
-    rb.simulate(prof, ref, o1, o2, seed=42, coverage=20.0)
-    assert open(o1, "rb").read(2) == b"\x1f\x8b"
-    assert gzip.open(o1).read() == open(golden["r1"], "rb").read()
-    assert subprocess.run(["gzip", "-dc", o2], capture_output=True, check=True).stdout == open(golden["r2"], "rb").read()
-    assert os.path.getsize(o1) < 0.6 * os.path.getsize(golden["r1"])
-
-
-def test_error_model_gzip_in_and_out(engine, golden, workdir):
-    import gzip
-    em_gz = os.path.join(workdir, "em_in.fa.gz")
-    with open(golden["em_in"], "rb") as f, gzip.open(em_gz, "wb") as o:
-        o.write(f.read())
-    out = os.path.join(workdir, "em_out.fq.gz")
-    engine.apply_error_model(em_gz, out, 7)
-    assert gzip.open(out).read() == open(golden["em_out"], "rb").read()
-
-
 @pytest.mark.parametrize("path", ["spec", "serial"])
 def test_error_model_bit_exact(engine, golden, workdir, monkeypatch, path):
     """seqToIllumina (ApplyErrorsAndQualityToFastaInput) against the reference's output, on the speculative kernels (the batch of
@@ -331,26 +301,6 @@ def test_tiles_and_read_lengths_profile_against_reference_binary(rb, golden, ora
     tiles = {line.split(b":")[4] for line in r1.split(b"\n")[0::4] if line}
     assert tiles == {b"1101", b"1102", b"2205"}
     assert {len(s) for s in r1.split(b"\n")[1::4]} == {144, 150}
-
-
-@pytest.mark.parametrize("path,meth", [("spec", False), ("serial", False), ("spec", True)])
-def test_250_base_reads_against_reference_binary(rb, golden, oracle, workdir, monkeypatch, path, meth):
-    """profile250: 2x250 reads, the read length of BASELINE config C4 (Drosophila, methylation BED): longer stream slices, record slots
-    and CIGARs; with bisulfite conversion on the speculative path."""
-    monkeypatch.setenv("RSQ_SIM_PATH", path)
-    eng = rb.Engine(rb.Profile.load_flat(golden["flat_250"]), 0)
-    try:
-        ref = rb.Reference.load_fasta(golden["small_ref"])
-        if meth:
-            ref.load_methylation(golden["meth_bed"])
-        r1, r2, _ = _simulate(eng, ref, seed=9, coverage=15.0)
-    finally:
-        eng.close()
-    extra = ("--methylation", golden["meth_bed"]) if meth else ()
-    o1, o2 = run_oracle_sim(oracle, golden["reseq_250"], golden["small_ref"], 9, 15.0, os.path.join(workdir, f"ora_250_{path}_{int(meth)}"), extra=extra)
-    assert r1 == open(o1, "rb").read()
-    assert r2 == open(o2, "rb").read()
-    assert {len(s) for s in r1.split(b"\n")[1::4]} == {250}
 
 
 def test_other_reference_and_prefix_against_reference_binary(rb, engine, golden, oracle, workdir):
