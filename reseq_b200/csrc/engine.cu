@@ -36,6 +36,7 @@
 #include "spec_core.cuh"
 #include "bias_core.cuh"
 #include "archive_reader.hpp"
+#include "deflate_core.cuh"
 
 namespace rsq {
 
@@ -743,6 +744,45 @@ __global__ void k_adapter_only(SimCtx c, uint64_t seed, uint32_t count, Arena ar
 }
 
 // Exclusive prefix sums of the per-slot byte counts (one CTA; slots <= a few million).
+// Device-side gzip of the FASTQ text (deflate_core.cuh): persistent CTAs, one gzip member of dfl::kMember text bytes at a time.
+__global__ void __launch_bounds__(256) k_deflate_members(const uint8_t *text, uint64_t n_bytes, uint32_t n_members, uint32_t *slots, uint32_t *tokens,
+                                                         uint32_t *sizes, const uint32_t *crc_tables /*[256 + 32]*/){
+	extern __shared__ __align__(16) unsigned char dfl_smem[];
+	dfl::Shared &sh = *reinterpret_cast<dfl::Shared *>(dfl_smem);
+	const dfl::DeviceCta cta;
+	for(uint32_t m = blockIdx.x; m < n_members; m += gridDim.x){
+		const uint64_t off = static_cast<uint64_t>(m) * dfl::kMember;
+		const uint32_t n = static_cast<uint32_t>(n_bytes - off < dfl::kMember ? n_bytes - off : dfl::kMember);
+		const uint32_t bytes = dfl::deflate_member(cta, sh, text + off, n, slots + static_cast<size_t>(m) * dfl::kSlotWords,
+		                                           tokens + static_cast<size_t>(blockIdx.x) * dfl::kMember, crc_tables, crc_tables + 256);
+		if(threadIdx.x == 0){ sizes[m] = bytes; }
+	}
+}
+// Members behind each other: CTA m copies its slot to the sum of the sizes in front of it.
+__global__ void __launch_bounds__(256) k_deflate_compact(const uint32_t *slots, const uint32_t *sizes, uint32_t n_members, uint8_t *out, unsigned long long *total){
+	__shared__ unsigned long long offset;
+	const uint32_t m = blockIdx.x;
+	if(threadIdx.x == 0){
+		unsigned long long o = 0;
+		for(uint32_t i = 0; i < m; ++i){ o += sizes[i]; }
+		offset = o;
+		if(m + 1 == n_members){ *total = o + sizes[m]; }
+	}
+	__syncthreads();
+	const uint32_t n = sizes[m];
+	const uint8_t *src = reinterpret_cast<const uint8_t *>(slots + static_cast<size_t>(m) * dfl::kSlotWords);
+	uint8_t *dst = out + offset;
+	const uint32_t head = static_cast<uint32_t>((4u - (offset & 3u)) & 3u) < n ? static_cast<uint32_t>((4u - (offset & 3u)) & 3u) : n;
+	for(uint32_t i = threadIdx.x; i < head; i += blockDim.x){ dst[i] = src[i]; }
+	// aligned 32-bit stores; the source is read bytewise (its alignment differs from the destination's)
+	const uint32_t words = (n - head) / 4u;
+	for(uint32_t w = threadIdx.x; w < words; w += blockDim.x){
+		const uint8_t *q = src + head + 4u * w;
+		reinterpret_cast<uint32_t *>(dst + head)[w] = q[0] | (static_cast<uint32_t>(q[1]) << 8) | (static_cast<uint32_t>(q[2]) << 16) | (static_cast<uint32_t>(q[3]) << 24);
+	}
+	for(uint32_t i = head + 4u * words + threadIdx.x; i < n; i += blockDim.x){ dst[i] = src[i]; }
+}
+
 __global__ void k_block_offsets(const BlockOut *out, uint32_t n, unsigned long long *offsets /*[2][n+1]*/, unsigned long long *totals /*[4]: bytes0, bytes1, pairs, draws*/){
 	__shared__ unsigned long long part[4][1024];
 	const uint32_t t = threadIdx.x, nt = blockDim.x;
@@ -938,6 +978,8 @@ struct rsq_engine {
 	PinnedBuf h_ring[4]; cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
 	HostBig h_big[2];   // text of runs that arrive in several batches (ordinary memory: pinning tens of GB takes longer than the run)
 	cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr; cudaEvent_t ev_out[2] = {nullptr, nullptr};
+	// device-side gzip (RSQ_GZIP=device, .gz sinks): per writer a slot per member, token scratch per CTA, the compacted members
+	DevBuf<uint32_t> d_dfl_slots[2], d_dfl_tokens[2], d_dfl_sizes[2], d_dfl_crc; DevBuf<uint8_t> d_dfl_out[2]; DevBuf<unsigned long long> d_dfl_total[2];
 	TextSink *sink_files[2] = {nullptr, nullptr};   // rsq_simulate: the two FASTQ files (plain or gzip by name)
 	bool streamed_to_host = false; int last_par = 0;
 	double reusable_bytes() const;
@@ -1490,14 +1532,34 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	const uint32_t n_sim_blocks = nb_total > lookahead_blocks ? nb_total - lookahead_blocks : 0;
 	const uint32_t shard_count_pre = opt.shard_count ? opt.shard_count : 1;
 	if(opt.shard_index >= shard_count_pre){ throw std::runtime_error("shard_index out of range"); }
-	const uint64_t shard_lo = static_cast<uint64_t>(n_sim_blocks) * opt.shard_index / shard_count_pre;
-	const uint64_t shard_hi = static_cast<uint64_t>(n_sim_blocks) * (opt.shard_index + 1) / shard_count_pre;
+	// Shard boundaries: the even split of the simulated blocks, moved onto the first block of a sequence when one starts within 5 %
+	// of a shard's size - a shard that only holds a sliver of a sequence would still need that sequence's whole systematic-error chains.
+	{
+		std::vector<uint32_t> seq_first;
+		uint32_t fb = 0;
+		for(size_t i = 0; i < g.seqs.size(); ++i){ const uint32_t L = g.seqs[i].size(); if(L < c.insert_to){ continue; } seq_first.push_back(fb); fb += (L + 999) / 1000; }
+		const uint64_t tol = std::max<uint64_t>(1, n_sim_blocks / (20ull * shard_count_pre));
+		auto boundary = [&](uint32_t k) -> uint64_t {
+			if(k == 0){ return 0; }
+			if(k >= shard_count_pre){ return n_sim_blocks; }
+			const uint64_t even = static_cast<uint64_t>(n_sim_blocks) * k / shard_count_pre;
+			uint64_t best = even, best_d = tol + 1;
+			for(uint32_t f : seq_first){
+				const uint64_t d = f > even ? f - even : even - f;
+				if(f > 0 && f < n_sim_blocks && d < best_d){ best = f; best_d = d; }
+			}
+			return best;
+		};
+		e.shard_first = static_cast<uint32_t>(boundary(opt.shard_index));
+		e.shard_n = static_cast<uint32_t>(std::max<uint64_t>(boundary(opt.shard_index + 1), e.shard_first) - e.shard_first);
+	}
+	const uint64_t shard_lo = e.shard_first, shard_hi = static_cast<uint64_t>(e.shard_first) + e.shard_n;
 	for(size_t i = 0; i < g.seqs.size(); ++i){
 		const uint32_t L = g.seqs[i].size();
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
 		const uint64_t n_draws = 2ull * nb + (from_file ? 0ull : 4ull * L);
-		const bool needed = shard_count_pre == 1 || (first < shard_hi && shard_lo < static_cast<uint64_t>(first) + nb);
+		const bool needed = shard_count_pre == 1 || (e.shard_n && first < shard_hi && shard_lo < static_cast<uint64_t>(first) + nb);
 		if(!needed && !from_file){
 			master_skip(e, n_draws);
 			const uint8_t *hseq = g.seqs[i].data();
@@ -1567,8 +1629,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	stage_log("prepare: device stages (bias, master stream, systematic errors)");
 	const uint32_t sc = opt.shard_count ? opt.shard_count : 1, si = opt.shard_index;
 	if(si >= sc){ throw std::runtime_error("shard_index out of range"); }
-	e.shard_first = static_cast<uint64_t>(e.n_blocks_sim) * si / sc;
-	e.shard_n = static_cast<uint64_t>(e.n_blocks_sim) * (si + 1) / sc - e.shard_first;
+	if(static_cast<uint64_t>(e.shard_first) + e.shard_n > e.n_blocks_sim){ throw std::runtime_error("internal error: shard range beyond the simulated blocks"); }
 	e.shard_has_adapter_only = (si + 1 == sc) && e.adapter_only_pairs;
 	RSQ_CUDA(cudaGetLastError());
 	const uint32_t flag = read_error_flag(e);
@@ -1929,6 +1990,7 @@ static void simulate_serial_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_co
 // - all of it while the GPU is busy with the next batch.
 constexpr size_t kRingChunk = 64u << 20;
 constexpr int kRingSlots = 4;
+constexpr size_t kDeflatePiece = 32u << 20;   // text per launch of the deflate kernels (256 members)
 struct ChunkWriter {   // one per segment (first / second reads): two files, two threads
 	int device = 0;
 	cudaStream_t copy_stream = nullptr;
@@ -1941,6 +2003,28 @@ struct ChunkWriter {   // one per segment (first / second reads): two files, two
 	uint64_t batches_done = 0;
 	bool discard = getenv("RSQ_DISCARD_OUTPUT") != nullptr;   // throughput probes of runs larger than the disk: the text reaches host memory, not the file
 	PinnedBuf *ring = nullptr; cudaEvent_t *ev = nullptr; int n_slots = 2;
+	// device-side gzip: the writer launches the deflate kernels on its copy stream and only the members cross PCIe
+	struct Deflate { uint32_t *slots, *tokens, *sizes; const uint32_t *crc; uint8_t *out; unsigned long long *total; int ctas; } dfl = {};
+	bool device_gzip = false;
+	void deflate_batch(const Batch &j){
+		for(uint64_t off = 0; off < j.bytes && error.empty(); off += kDeflatePiece){
+			const uint64_t n = std::min<uint64_t>(kDeflatePiece, j.bytes - off);
+			const uint32_t n_members = static_cast<uint32_t>((n + dfl::kMember - 1) / dfl::kMember);
+			k_deflate_members<<<std::min<uint32_t>(n_members, dfl.ctas), 256, sizeof(dfl::Shared), copy_stream>>>(j.src + off, n, n_members, dfl.slots, dfl.tokens, dfl.sizes, dfl.crc);
+			k_deflate_compact<<<n_members, 256, 0, copy_stream>>>(dfl.slots, dfl.sizes, n_members, dfl.out, dfl.total);
+			unsigned long long total = 0;
+			if(cudaMemcpyAsync(&total, dfl.total, sizeof total, cudaMemcpyDeviceToHost, copy_stream) != cudaSuccess || cudaStreamSynchronize(copy_stream) != cudaSuccess){
+				error = std::string("compressing FASTQ text on the device failed: ") + cudaGetErrorString(cudaGetLastError()); return;
+			}
+			for(uint64_t done = 0; done < total; done += kRingChunk){
+				const uint64_t part = std::min<uint64_t>(kRingChunk, total - done);
+				if(cudaMemcpyAsync(ring[0].p, dfl.out + done, part, cudaMemcpyDeviceToHost, copy_stream) != cudaSuccess || cudaStreamSynchronize(copy_stream) != cudaSuccess){
+					error = "copying compressed FASTQ text to the host failed"; return;
+				}
+				if(!discard && !f->write_members(ring[0].p, part, done ? 0 : n, done ? 0 : n_members)){ error = "Could not write records to the output file"; return; }
+			}
+		}
+	}
 	void consume(int slot, uint64_t n, uint64_t dst){
 		if(cudaEventSynchronize(ev[slot]) != cudaSuccess){ error = "copying FASTQ text to the host failed"; return; }
 		if(mem){ std::memcpy(mem->data() + dst, ring[slot].p, n); }
@@ -1952,6 +2036,12 @@ struct ChunkWriter {   // one per segment (first / second reads): two files, two
 			Batch j;
 			{ std::unique_lock<std::mutex> l(m); cv.wait(l, [&]{ return stop || !q.empty(); }); if(q.empty()){ return; } j = q.front(); q.pop_front(); }
 			cudaStreamWaitEvent(copy_stream, j.ready, 0);
+			if(device_gzip){
+				deflate_batch(j);
+				{ std::lock_guard<std::mutex> l(m); ++batches_done; }
+				cv.notify_all();
+				continue;
+			}
 			struct Piece { int slot; uint64_t n, dst; };
 			std::deque<Piece> inflight;
 			int slot = 0;
@@ -2010,7 +2100,24 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 		for(int seg = 0; seg < 2; ++seg){
 			ChunkWriter &w = writer[seg];
 			w.ring = e.h_ring + 2 * seg; w.ev = e.ev_ring + 2 * seg; w.device = e.device; w.copy_stream = seg ? e.copy_stream2 : e.copy_stream;
-			if(to_files){ w.f = e.sink_files[seg]; }
+			if(to_files){
+				w.f = e.sink_files[seg];
+				const char *gz_mode = getenv("RSQ_GZIP");
+				if(w.f->compressed() && gz_mode && std::string(gz_mode) == "device"){
+					if(!e.d_dfl_crc.p){
+						std::vector<uint32_t> tables(256 + 32);
+						dfl::crc_make_table(tables.data()); dfl::crc_make_shift_operator(tables.data() + 256, dfl::kCrcPiece);
+						e.d_dfl_crc.upload(tables, s);
+						RSQ_CUDA(cudaStreamSynchronize(s));
+						RSQ_CUDA(cudaFuncSetAttribute(k_deflate_members, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(dfl::Shared))));
+					}
+					const size_t piece_members = kDeflatePiece / dfl::kMember;
+					e.d_dfl_slots[seg].alloc(piece_members * dfl::kSlotWords); e.d_dfl_out[seg].alloc(piece_members * dfl::kSlotBytes);
+					e.d_dfl_tokens[seg].alloc(static_cast<size_t>(dev_sms) * dfl::kMember); e.d_dfl_sizes[seg].alloc(piece_members); e.d_dfl_total[seg].alloc(1);
+					w.dfl = {e.d_dfl_slots[seg].p, e.d_dfl_tokens[seg].p, e.d_dfl_sizes[seg].p, e.d_dfl_crc.p, e.d_dfl_out[seg].p, e.d_dfl_total[seg].p, dev_sms};
+					w.device_gzip = true;
+				}
+			}
 			else{ e.h_big[seg].resize(static_cast<size_t>(est)); w.mem = &e.h_big[seg]; }
 			w.th = std::thread([&w]{ w.run(); });
 		}

@@ -98,6 +98,13 @@ public:
 		return true;
 	}
 
+	// Appends gzip members that were made elsewhere (the device deflate kernels): `n` bytes of file data standing for `text` bytes.
+	bool write_members(const void *data, size_t n, uint64_t text, uint64_t members){
+		if(!f_ || !gz_){ return false; }
+		text_bytes_ += text; file_bytes_ += n; members_ += members;
+		return std::fwrite(data, 1, n, f_) == n;
+	}
+
 	// Flushes and closes; false on a write error.  An empty compressed file still gets one (empty) gzip member.
 	bool close(){
 		if(!f_){ return true; }

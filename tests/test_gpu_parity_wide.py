@@ -14,11 +14,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("gz_mode", ["host", "device"])
 @pytest.mark.parametrize("batch", [None, "7"])
-def test_dropin_simulate_call_gzip_files(rb, golden, workdir, monkeypatch, batch):
+def test_dropin_simulate_call_gzip_files(rb, golden, workdir, monkeypatch, batch, gz_mode):
     """Output names ending in .gz are written gzip-compressed like SeqAn's SeqFileOut does (members deflated on the host cores by the
     writer threads); the reference is read from a .fa.gz.  The inflated text is the reference's golden FASTQ."""
     import gzip
+    monkeypatch.setenv("RSQ_GZIP", gz_mode)   # device: k_deflate_members makes the gzip members on the GPU (deflate_core.cuh)
     if batch:
         monkeypatch.setenv("RSQ_BATCH_UNITS", batch)
     fa_gz = os.path.join(workdir, "small_ref_copy.fa.gz")
@@ -26,7 +28,7 @@ def test_dropin_simulate_call_gzip_files(rb, golden, workdir, monkeypatch, batch
         o.write(f.read())
     prof = rb.Profile.load_flat(golden["flat"])
     ref = rb.Reference.load_fasta(fa_gz)
-    o1, o2 = os.path.join(workdir, f"gz{batch}_1.fq.gz"), os.path.join(workdir, f"gz{batch}_2.fq.gz")
+    o1, o2 = os.path.join(workdir, f"gz{batch}{gz_mode}_1.fq.gz"), os.path.join(workdir, f"gz{batch}{gz_mode}_2.fq.gz")
     rb.simulate(prof, ref, o1, o2, seed=42, coverage=20.0)
     assert open(o1, "rb").read(2) == b"\x1f\x8b"
     assert gzip.open(o1).read() == open(golden["r1"], "rb").read()
@@ -80,3 +82,32 @@ def test_250_base_reads_against_reference_binary(rb, golden, oracle, workdir, mo
     assert r1 == open(o1, "rb").read()
     assert r2 == open(o2, "rb").read()
     assert {len(s) for s in r1.split(b"\n")[1::4]} == {250}
+
+
+def test_device_gzip_at_full_size(rb, golden, workdir, monkeypatch):
+    """BASELINE config C2's size through the drop-in call with .gz names and the device deflate kernels: ~2 x 170 MB of text in
+    ~2600 gzip members per file; the inflated files equal the plain files of the same run."""
+    import gzip
+    import hashlib
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synthetic
+    seq = make_synthetic.gen_reference([4_641_652], 1234)[0]
+    ref = rb.Reference.from_memory(["ecoli_sized synthetic"], [seq.encode()])
+    prof = rb.Profile.load_flat(golden["flat_r"])
+    p1, p2 = os.path.join(workdir, "full_1.fq"), os.path.join(workdir, "full_2.fq")
+    rb.simulate(prof, ref, p1, p2, seed=42, coverage=30.0)
+    monkeypatch.setenv("RSQ_GZIP", "device")
+    z1, z2 = os.path.join(workdir, "full_1.fq.gz"), os.path.join(workdir, "full_2.fq.gz")
+    rb.simulate(prof, ref, z1, z2, seed=42, coverage=30.0)
+    for plain, packed in ((p1, z1), (p2, z2)):
+        want = hashlib.sha256(open(plain, "rb").read()).hexdigest()
+        with gzip.open(packed) as f:
+            h = hashlib.sha256()
+            while True:
+                chunk = f.read(1 << 24)
+                if not chunk:
+                    break
+                h.update(chunk)
+        assert h.hexdigest() == want
+        assert os.path.getsize(packed) < 0.45 * os.path.getsize(plain)
+    assert subprocess.run(["gzip", "-t", z1]).returncode == 0

@@ -105,3 +105,52 @@ def test_reference_binary_reads_our_gzip_members(text_io, oracle, golden, workdi
     assert gzip.open(fa_gz).read() == src
     r1, r2 = run_oracle_sim(oracle, golden["reseq"], fa_gz, 42, 20, os.path.join(workdir, "ora_gzmembers"))
     assert open(r1, "rb").read() == open(golden["r1"], "rb").read()
+
+
+@pytest.fixture(scope="module")
+def deflate_twin(workdir):
+    exe = os.path.join(workdir, "deflate_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(TWIN_DIR, "deflate_check.cpp")], check=True)
+    return exe
+
+
+def _fib_bytes():
+    """Byte counts growing like Fibonacci numbers: an unrestricted Huffman code would be deeper than deflate's 15 bits."""
+    import random
+    fib = [1, 1]
+    while len(fib) < 30:
+        fib.append(fib[-1] + fib[-2])
+    data = list(b"".join(bytes([i]) * min(f, 60000) for i, f in enumerate(fib)))
+    random.Random(1).shuffle(data)
+    return bytes(data)[:131072]
+
+
+@pytest.mark.parametrize("case", ["fastq", "one_byte", "run", "random", "member_exact", "member_plus_one", "crc_piece_511", "crc_piece_513",
+                                  "slice_edge", "length_limit"])
+def test_device_deflate_member_code_on_the_cpu_twin(deflate_twin, fastq_text, workdir, case):
+    """deflate_core.cuh (the code of k_deflate_members) instantiated with one thread: every member is a valid gzip member (header, one
+    dynamic-Huffman block, CRC-32 built from 512-byte pieces with the GF(2) shift operator, ISIZE) and inflates to the input."""
+    import random
+    rnd = random.Random(7)
+    data = {
+        "fastq": lambda: fastq_text[1][:2_000_000],
+        "one_byte": lambda: b"A",
+        "run": lambda: b"I" * 300_000,
+        "random": lambda: os.urandom(300_000),
+        "member_exact": lambda: (b"ACGT" * 40000)[:131072],
+        "member_plus_one": lambda: (b"ACGTTGCA" * 40000)[:131073],
+        "crc_piece_511": lambda: bytes(rnd.choice(b"ACGT") for _ in range(511)),
+        "crc_piece_513": lambda: bytes(rnd.choice(b"ACGTN!#IJ") for _ in range(513)),
+        "slice_edge": lambda: bytes(rnd.choice(b"ACGT") for _ in range(16384 + 3)),
+        "length_limit": _fib_bytes,
+    }[case]()
+    src, out = os.path.join(workdir, f"dfl_{case}.in"), os.path.join(workdir, f"dfl_{case}.gz")
+    open(src, "wb").write(data)
+    res = subprocess.run([deflate_twin, src, out], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert gzip.open(out).read() == data
+    assert subprocess.run(["gzip", "-t", out]).returncode == 0
+    if case == "fastq":
+        assert os.path.getsize(out) < 0.4 * len(data)   # zlib level 1 reaches 0.31 on this text, level 6 0.23
+    if case == "random":
+        assert os.path.getsize(out) < 1.01 * len(data) + 400
