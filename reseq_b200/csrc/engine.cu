@@ -978,7 +978,7 @@ struct rsq_engine {
 	PinnedBuf h_ring[4]; cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
 	HostBig h_big[2];   // text of runs that arrive in several batches (ordinary memory: pinning tens of GB takes longer than the run)
 	cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr; cudaEvent_t ev_out[2] = {nullptr, nullptr};
-	// device-side gzip (RSQ_GZIP=device, .gz sinks): per writer a slot per member, token scratch per CTA, the compacted members
+	// device-side gzip (.gz sinks unless RSQ_GZIP=host): per writer a slot per member, token scratch per CTA, the compacted members
 	DevBuf<uint32_t> d_dfl_slots[2], d_dfl_tokens[2], d_dfl_sizes[2], d_dfl_crc; DevBuf<uint8_t> d_dfl_out[2]; DevBuf<unsigned long long> d_dfl_total[2];
 	TextSink *sink_files[2] = {nullptr, nullptr};   // rsq_simulate: the two FASTQ files (plain or gzip by name)
 	bool streamed_to_host = false; int last_par = 0;
@@ -2103,7 +2103,7 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 			if(to_files){
 				w.f = e.sink_files[seg];
 				const char *gz_mode = getenv("RSQ_GZIP");
-				if(w.f->compressed() && gz_mode && std::string(gz_mode) == "device"){
+				if(w.f->compressed() && !(gz_mode && std::string(gz_mode) == "host")){   // RSQ_GZIP=host: zlib on the host cores (text_io.hpp)
 					if(!e.d_dfl_crc.p){
 						std::vector<uint32_t> tables(256 + 32);
 						dfl::crc_make_table(tables.data()); dfl::crc_make_shift_operator(tables.data() + 256, dfl::kCrcPiece);

@@ -25,9 +25,12 @@ def main():
     seq = make_synthetic.gen_reference([4_641_652], 1234)[0]
     ref = rb.Reference.from_memory(["ecoli_sized synthetic"], [seq.encode()])
     out = []
-    for name, env, suffix in (("plain", {}, ".fq"), ("plain", {}, ".fq"), ("gzip device", {"RSQ_GZIP": "device"}, ".fq.gz"), ("gzip device", {"RSQ_GZIP": "device"}, ".fq.gz"),
+    modes = (("plain", {}, ".fq"), ("plain", {}, ".fq"), ("gzip device", {"RSQ_GZIP": "device"}, ".fq.gz"), ("gzip device", {"RSQ_GZIP": "device"}, ".fq.gz"),
                               ("gzip host level 1", {"RSQ_GZIP": "host", "RSQ_GZIP_LEVEL": "1"}, ".fq.gz"),
-                              ("gzip host default level", {"RSQ_GZIP": "host"}, ".fq.gz")):
+                              ("gzip host default level", {"RSQ_GZIP": "host"}, ".fq.gz"))
+    if len(sys.argv) > 2 and sys.argv[1] == "--once":   # one run of one mode (for ncu)
+        modes = tuple(m for m in modes if m[0] == sys.argv[2])[:1]
+    for name, env, suffix in modes:
         for k in ("RSQ_GZIP", "RSQ_GZIP_LEVEL"):
             os.environ.pop(k, None)
         os.environ.update(env)
