@@ -24,10 +24,13 @@ def main():
     ap.add_argument("--seqs", type=int, default=4)
     ap.add_argument("--coverage", type=float, default=30.0)
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--profile", default=None, help="golden profile base name (tests/golden/<name>.flat.xz), e.g. profile250; default: the bench profile")
+    ap.add_argument("--methylation", action="store_true", help="bisulfite run: one unmethylated region of ~600 bp per 10 kb, methylation ~ U(0,1) (BASELINE config C4)")
+    ap.add_argument("--gz", action="store_true", help="with --files: .fq.gz output names (device-side gzip)")
     ap.add_argument("--files", action="store_true", help="drop-in call rsq_simulate (text streamed through the writer thread; set RSQ_DISCARD_OUTPUT=1 for runs larger than the disk)")
     args = ap.parse_args()
     tmp = tempfile.mkdtemp(prefix="rsq_scale_")
-    prof = rb.Profile.load_flat(bench.unxz(bench.PROFILE + ".flat.xz", tmp))
+    prof = rb.Profile.load_flat(bench.unxz((args.profile or bench.PROFILE) + ".flat.xz", tmp))
     eng = rb.Engine(prof, 0)
     for mbp in args.mbp:
         total = int(mbp * 1e6)
@@ -35,17 +38,26 @@ def main():
         t0 = time.perf_counter()
         seqs = make_synthetic.gen_reference(sizes, 4321)
         ref = rb.Reference.from_memory([f"chr{i + 1} synthetic" for i in range(len(seqs))], [s.encode() for s in seqs])
+        if args.methylation:
+            import random
+            rnd = random.Random(9)
+            bed = os.path.join(tmp, f"meth_{mbp}.bed")
+            with open(bed, "w") as f:
+                for i, size in enumerate(sizes):
+                    for start in range(2000, size - 2000, 10000):
+                        f.write(f"chr{i + 1}\t{start}\t{start + rnd.randint(100, 1100)}\t{rnd.random():.3f}\n")
+            ref.load_methylation(bed)
         t_gen = time.perf_counter() - t0
         best = None
         if args.files:
-            out = [os.path.join(tmp, "probe_R1.fq"), os.path.join(tmp, "probe_R2.fq")]
+            out = [os.path.join(tmp, "probe_R1.fq" + (".gz" if args.gz else "")), os.path.join(tmp, "probe_R2.fq" + (".gz" if args.gz else ""))]
             t0 = time.perf_counter()
             rep = rb.simulate(prof, ref, out[0], out[1], seed=42, coverage=args.coverage).as_dict()
             wall = time.perf_counter() - t0
             sizes_on_disk = [os.path.getsize(o) for o in out]
             for o in out:
                 os.remove(o)
-            print(json.dumps({"mbp": mbp, "seqs": args.seqs, "coverage": args.coverage, "gen_ref_s": round(t_gen, 1), "wall_rsq_simulate_s": round(wall, 2),
+            print(json.dumps({"mbp": mbp, "seqs": args.seqs, "coverage": args.coverage, "profile": args.profile or bench.PROFILE, "methylation": args.methylation, "gz": args.gz, "gen_ref_s": round(t_gen, 1), "wall_rsq_simulate_s": round(wall, 2),
                               "pairs_per_s_e2e": round(rep["pairs"] / wall), "bytes_on_disk": sizes_on_disk, "report": rep}), flush=True)
             continue
         for _ in range(args.repeat):
