@@ -34,6 +34,7 @@ constexpr uint32_t kLit = 286, kDist = 30, kMaxBits = 15;
 constexpr uint32_t kCrcPiece = 512;
 constexpr uint32_t kSlotBytes = 2u * kMember + 256u;   // output slot of a member: <= 15 bits per token + headers, rounded up
 constexpr uint32_t kSlotWords = kSlotBytes / 4u;
+constexpr uint32_t kHeaderWords = 64;   // gzip header + block header + code length table: 10 B + 1338 bits < 256 B
 
 struct Shared {
 	uint32_t freq_lit[288], freq_dist[32];
@@ -61,6 +62,7 @@ struct DeviceCta {
 	__device__ __forceinline__ void sync_warp() const { __syncwarp(); }
 	__device__ __forceinline__ uint32_t shfl(uint32_t v, uint32_t src) const { return __shfl_sync(0xffffffffu, v, src); }
 	__device__ __forceinline__ uint32_t shfl_up(uint32_t v, uint32_t d) const { return __shfl_up_sync(0xffffffffu, v, d); }
+	__device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
 	__device__ __forceinline__ void atomic_add(uint32_t *p, uint32_t v) const { atomicAdd(p, v); }
 	__device__ __forceinline__ void atomic_or(uint32_t *p, uint32_t v) const { atomicOr(p, v); }
 };
@@ -76,6 +78,7 @@ struct SerialCta {
 	void sync_warp() const {}
 	uint32_t shfl(uint32_t v, uint32_t) const { return v; }
 	uint32_t shfl_up(uint32_t v, uint32_t) const { return v; }
+	uint32_t ballot(bool p) const { return p ? 1u : 0u; }
 	void atomic_add(uint32_t *p, uint32_t v) const { *p += v; }
 	void atomic_or(uint32_t *p, uint32_t v) const { *p |= v; }
 };
@@ -225,10 +228,46 @@ DFL_HD void token_bits(const Shared &s, uint32_t tok, uint64_t &value, uint32_t 
 }
 
 DFL_HD uint32_t load4(const uint8_t *p){ return p[0] | (static_cast<uint32_t>(p[1]) << 8) | (static_cast<uint32_t>(p[2]) << 16) | (static_cast<uint32_t>(p[3]) << 24); }
+DFL_HD uint32_t popc(uint32_t x){
+#if defined(__CUDA_ARCH__)
+	return static_cast<uint32_t>(__popc(x));
+#else
+	return static_cast<uint32_t>(__builtin_popcount(x));
+#endif
+}
+DFL_HD uint32_t first_bit(uint32_t x){   // x != 0
+#if defined(__CUDA_ARCH__)
+	return static_cast<uint32_t>(__ffs(static_cast<int>(x))) - 1u;
+#else
+	return static_cast<uint32_t>(__builtin_ctz(x));
+#endif
+}
+// Unaligned 32-bit little-endian reads from aligned words: a stream keeps the aligned word it stands in and pulls the next one.
+// Reads whole aligned words, i.e. up to 3 bytes in front of / behind the range it is asked about (the text buffers are
+// allocations of whole words, so these bytes exist).
+struct WordStream {
+	const uint32_t *w; uint32_t cur, shift;
+	DFL_HD explicit WordStream(const uint8_t *p){
+		const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+		w = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3)); shift = static_cast<uint32_t>(a & 3u) * 8u; cur = *w;
+	}
+	DFL_HD uint32_t next(){
+		if(!shift){ const uint32_t v = cur; cur = *++w; return v; }   // (reads one word ahead; see above)
+		const uint32_t nxt = *++w;
+		const uint32_t v = (cur >> shift) | (nxt << (32u - shift));
+		cur = nxt;
+		return v;
+	}
+};
 DFL_HD uint32_t match_length(const uint8_t *a, const uint8_t *b, uint32_t max_len){
+	WordStream sa(a), sb(b);
 	uint32_t n = 0;
-	while(n < max_len && a[n] == b[n]){ ++n; }
-	return n;
+	while(n < max_len){
+		const uint32_t x = sa.next() ^ sb.next();
+		if(x){ n += first_bit(x) >> 3; break; }
+		n += 4u;
+	}
+	return n < max_len ? n : max_len;
 }
 
 // One member: in[0, n) (1 <= n <= kMember) -> out slot (kSlotWords words); tokens: kMember words of scratch owned by this CTA.
@@ -242,8 +281,7 @@ template<class C> DFL_HD uint32_t deflate_member(const C &c, Shared &s, const ui
 	for(uint32_t i = tid; i < 32; i += nt){ s.freq_dist[i] = 0; }
 	for(uint32_t i = tid; i < 256; i += nt){ s.crc_table[i] = crc_table[i]; }
 	for(uint32_t i = tid; i < kSlices * kHashSize; i += nt){ (&s.hash[0][0])[i] = 0; }
-	const uint32_t clear_words = (2u * n + 256u) / 4u < kSlotWords ? (2u * n + 256u) / 4u : kSlotWords;
-	for(uint32_t i = tid; i < clear_words; i += nt){ out[i] = 0; }
+	for(uint32_t i = tid; i < kHeaderWords; i += nt){ out[i] = 0; }   // the rest of the slot is cleared once the member's size is known
 	c.sync();
 	// ---- parse ----
 	const uint32_t n_slices = (n + kSlice - 1) / kSlice;
@@ -267,13 +305,21 @@ template<class C> DFL_HD uint32_t deflate_member(const C &c, Shared &s, const ui
 				if(pos > s0 && len < max_len && in[pos - 1] == in[pos]){ const uint32_t l1 = match_length(in + pos - 1, in + pos, max_len); if(l1 > len){ len = l1; dist = 1; } }
 				if(len < kMinMatch){ len = 0; }
 			}
-			// greedy walk over the window; every lane follows the same path
-			uint32_t cur = 0;
-			while(cur < C::kLanes && p + cur < s1){
-				const uint32_t l = c.shfl(len, cur);
-				if(lane == cur){ tok[count] = l ? token_match(len, dist) : in[pos]; }
-				cur += l ? l : 1u; ++count;
+			// greedy walk over the window, from match to match (everything between two taken matches is a literal);
+			// every lane follows the same path, the taken positions then write their tokens side by side
+			const uint32_t in_window = (s1 - p < C::kLanes) ? s1 - p : C::kLanes;
+			const uint32_t valid = in_window >= 32u ? 0xffffffffu : (1u << in_window) - 1u;
+			const uint32_t with_match = c.ballot(len != 0);
+			uint32_t taken = 0, cur = 0;
+			while(cur < in_window){
+				const uint32_t rest = with_match & ~((1u << cur) - 1u);
+				if(!rest){ taken |= valid & ~((1u << cur) - 1u); cur = in_window; break; }
+				const uint32_t m = first_bit(rest);
+				taken |= (m >= 31u ? 0xffffffffu : (1u << (m + 1u)) - 1u) & ~((1u << cur) - 1u);
+				cur = m + c.shfl(len, m);
 			}
+			if((taken >> lane) & 1u){ tok[count + popc(taken & ((1u << lane) - 1u))] = len ? token_match(len, dist) : in[pos]; }
+			count += popc(taken);
 			p += cur;
 		}
 		if(c.lane() == 0){ s.slice_tokens[sl] = count; }
@@ -332,6 +378,11 @@ template<class C> DFL_HD uint32_t deflate_member(const C &c, Shared &s, const ui
 		uint64_t pos = s.eob_pos;
 		for(uint32_t sl = 0; sl < n_slices; ++sl){ s.slice_pos[sl] = pos; pos += s.slice_bits[sl]; }
 		s.eob_pos = pos;
+	}
+	c.sync();
+	{	// data bits + end of block (<= 15) + padding + trailer (64) + the two words put_bits may touch behind its position
+		const uint32_t end_word = static_cast<uint32_t>((s.eob_pos + 15u + 7u + 64u) >> 5) + 3u;
+		for(uint32_t i = kHeaderWords + tid; i < end_word && i < kSlotWords; i += nt){ out[i] = 0; }
 	}
 	c.sync();
 	// ---- emit ----

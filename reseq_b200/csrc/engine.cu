@@ -1718,7 +1718,7 @@ static void gather(rsq_engine &e, const Arena &a, uint32_t slots, rsq_sim_report
 	RSQ_CUDA(cudaMemcpyAsync(totals, e.d_totals.p, sizeof totals, cudaMemcpyDeviceToHost, s));
 	RSQ_CUDA(cudaStreamSynchronize(s));
 	e.out_bytes[0] = totals[0]; e.out_bytes[1] = totals[1]; e.out_pairs = totals[2]; e.out_draws = totals[3];
-	e.d_out_batch[0][0].alloc(totals[0] + 1); e.d_out_batch[0][1].alloc(totals[1] + 1);
+	e.d_out_batch[0][0].alloc(totals[0] + 16); e.d_out_batch[0][1].alloc(totals[1] + 16);
 	e.last_par = 0; e.streamed_to_host = false;
 	if(slots){ k_gather<<<2 * slots, 128, 0, s>>>(e.d_block_out.p, slots, a, e.d_offsets.p, e.d_out_batch[0][0].p, e.d_out_batch[0][1].p); ++e.launches; }
 	const float ms = tm.stop();
@@ -1917,7 +1917,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	RSQ_CUDA(cudaMemcpyAsync(totals, e.d_totals.p, sizeof totals, cudaMemcpyDeviceToHost, s));
 	RSQ_CUDA(cudaStreamSynchronize(s));
 	res.bytes[0] = totals[0]; res.bytes[1] = totals[1]; res.pairs = totals[2]; res.draws = totals[3];
-	e.d_out_batch[par][0].alloc(totals[0] + 1); e.d_out_batch[par][1].alloc(totals[1] + 1);
+	e.d_out_batch[par][0].alloc(totals[0] + 16); e.d_out_batch[par][1].alloc(totals[1] + 16);
 	if(slots){ k_spec_gather<<<2 * slots, 128, 0, s>>>(sp, e.d_offsets.p, e.d_out_batch[par][0].p, e.d_out_batch[par][1].p); ++e.launches; }
 	res.ms_gather = tm.stop();
 	RSQ_CUDA(cudaGetLastError());
@@ -1975,7 +1975,7 @@ static void simulate_serial_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_co
 		RSQ_CUDA(cudaMemcpyAsync(totals, e.d_totals.p, sizeof totals, cudaMemcpyDeviceToHost, s));
 		RSQ_CUDA(cudaStreamSynchronize(s));
 		res.bytes[0] = totals[0]; res.bytes[1] = totals[1]; res.pairs = totals[2]; res.draws = totals[3];
-		e.d_out_batch[par][0].alloc(totals[0] + 1); e.d_out_batch[par][1].alloc(totals[1] + 1);
+		e.d_out_batch[par][0].alloc(totals[0] + 16); e.d_out_batch[par][1].alloc(totals[1] + 16);
 		if(slots){ k_gather<<<2 * slots, 128, 0, s>>>(e.d_block_out.p, slots, a, e.d_offsets.p, e.d_out_batch[par][0].p, e.d_out_batch[par][1].p); ++e.launches; }
 		res.ms_gather = tg.stop();
 		RSQ_CUDA(cudaGetLastError());
@@ -2113,8 +2113,10 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 					}
 					const size_t piece_members = kDeflatePiece / dfl::kMember;
 					e.d_dfl_slots[seg].alloc(piece_members * dfl::kSlotWords); e.d_dfl_out[seg].alloc(piece_members * dfl::kSlotBytes);
-					e.d_dfl_tokens[seg].alloc(static_cast<size_t>(dev_sms) * dfl::kMember); e.d_dfl_sizes[seg].alloc(piece_members); e.d_dfl_total[seg].alloc(1);
-					w.dfl = {e.d_dfl_slots[seg].p, e.d_dfl_tokens[seg].p, e.d_dfl_sizes[seg].p, e.d_dfl_crc.p, e.d_dfl_out[seg].p, e.d_dfl_total[seg].p, dev_sms};
+					// one wave: a CTA per member of a piece where the SMs hold them (3 CTAs per SM by shared memory), 512 KiB of token scratch each
+					const int deflate_ctas = static_cast<int>(std::min<size_t>(piece_members, 2 * static_cast<size_t>(dev_sms)));
+					e.d_dfl_tokens[seg].alloc(static_cast<size_t>(deflate_ctas) * dfl::kMember); e.d_dfl_sizes[seg].alloc(piece_members); e.d_dfl_total[seg].alloc(1);
+					w.dfl = {e.d_dfl_slots[seg].p, e.d_dfl_tokens[seg].p, e.d_dfl_sizes[seg].p, e.d_dfl_crc.p, e.d_dfl_out[seg].p, e.d_dfl_total[seg].p, deflate_ctas};
 					w.device_gzip = true;
 				}
 			}

@@ -13,7 +13,13 @@ int main(int argc, char **argv){
 	if(argc != 3){ fprintf(stderr, "usage: deflate_check <in> <out.gz>\n"); return 64; }
 	using namespace rsq::dfl;
 	std::ifstream f(argv[1], std::ios::binary);
-	const std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+	const std::string file_text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+	// the member code reads whole aligned words (WordStream): keep the text in a word buffer with slack on both sides, at an
+	// odd offset so that unaligned streams are exercised
+	std::vector<uint32_t> backing(file_text.size() / 4 + 8);
+	char *text_ptr = reinterpret_cast<char *>(backing.data()) + 5;
+	std::memcpy(text_ptr, file_text.data(), file_text.size());
+	struct View { const char *p; size_t n; const char *data() const { return p; } size_t size() const { return n; } } text{text_ptr, file_text.size()};
 	std::vector<uint32_t> crc_table(256), crc_shift(32);
 	crc_make_table(crc_table.data());
 	crc_make_shift_operator(crc_shift.data(), kCrcPiece);
