@@ -2422,7 +2422,7 @@ rsq_reference *rsq_reference_from_memory(uint32_t n_seqs, const char *const *ids
 	for(uint32_t i = 0; i < n_seqs; ++i){
 		r->g.ids.emplace_back(ids[i]);
 		std::vector<uint8_t> s(lengths[i]);
-		for(uint64_t k = 0; k < lengths[i]; ++k){ s[k] = Genome::code(bases[i][k]); }
+		Genome::encode(bases[i], lengths[i], s.data());
 		r->g.seqs.push_back(std::move(s));
 	}
 	if(!n_seqs){ throw std::runtime_error("reference does not contain any sequences"); }

@@ -25,6 +25,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 #include "text_io.hpp"
 
@@ -401,6 +402,18 @@ struct Genome {
 		default: return 4;
 		}
 	}
+	// code() over a whole sequence: table lookup, split over the host cores for chromosome-sized inputs
+	static void encode(const char *bases, size_t n, uint8_t *out){
+		uint8_t table[256];
+		for(int ch = 0; ch < 256; ++ch){ table[ch] = code(static_cast<char>(ch)); }
+		auto run = [&](size_t lo, size_t hi){ for(size_t k = lo; k < hi; ++k){ out[k] = table[static_cast<unsigned char>(bases[k])]; } };
+		const size_t kPerThread = 1u << 20;
+		const size_t n_threads = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), n / kPerThread);
+		if(n_threads < 2){ run(0, n); return; }
+		std::vector<std::thread> pool;
+		for(size_t t = 0; t < n_threads; ++t){ pool.emplace_back(run, n * t / n_threads, n * (t + 1) / n_threads); }
+		for(auto &th : pool){ th.join(); }
+	}
 	std::string first_part(size_t i) const { return ids[i].substr(0, ids[i].find(' ')); }
 	uint64_t total_size() const { uint64_t s = 0; for(const auto &q : seqs){ s += q.size(); } return s; }
 
@@ -476,6 +489,13 @@ struct Genome {
 				}
 				else{
 					++start;
+					// eight bases at a time while none of them is an N (code 4: bit 2 set)
+					while(start + 8 <= len){
+						uint64_t w;
+						std::memcpy(&w, seq.data() + start, 8);
+						if(w & 0x0404040404040404ull){ break; }
+						start += 8;
+					}
 				}
 			}
 		}

@@ -3,6 +3,7 @@ the lane-group templates (instantiated with one lane) reproduce the reference's 
 import filecmp
 import os
 import subprocess
+import sys
 
 import pytest
 
@@ -159,3 +160,22 @@ def test_templates_match_reference_with_methylation(oracle, golden, twin, workdi
     assert res.returncode == 0, res.stdout
     assert filecmp.cmp(prefix + "_1.fq", golden["meth_r1"], shallow=False)
     assert filecmp.cmp(prefix + "_2.fq", golden["meth_r2"], shallow=False)
+
+
+def test_replace_n_matches_reference(oracle, golden, workdir):
+    """Reference::ReplaceN (Reference.cpp:813-891): short N runs drawn from mt19937_64(seed), long runs filled with the neighbouring
+    repeat; the host code (word-wise skip over N-free stretches) against the reference's in-memory sequences."""
+    import numpy as np
+    from reseq_b200.flatfile import read_flat
+    exe = _compile("replace_n_check.cpp", os.path.join(workdir, "replace_n_check"))
+    fa = os.path.join(workdir, "n_rich.fa")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synthetic.py"), "reference", fa, "--sizes", "40000,9000,23000", "--seed", "77",
+                    "--n-rate", "0.02", "--prefix", "n"], check=True)
+    for ref, seed in ((golden["small_ref"], 42), (fa, 5)):
+        stage = os.path.join(workdir, f"stage_replace_n_{seed}.flat")
+        subprocess.run([oracle["dump"], "sim", golden["reseq"], ref, str(seed), "5", stage], check=True, timeout=600, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        st = read_flat(stage)
+        want = np.concatenate([st[k] for k in sorted((k for k in st if k.startswith("sim.ref.")), key=lambda k: int(k.split(".")[-1]))])
+        got = np.frombuffer(subprocess.run([exe, ref, str(seed)], capture_output=True, check=True).stdout, dtype=np.uint8)
+        assert got.size == want.size and np.array_equal(got, want.astype(np.uint8))
+        assert got.max() <= 3
