@@ -37,6 +37,7 @@
 #include "bias_core.cuh"
 #include "archive_reader.hpp"
 #include "deflate_core.cuh"
+#include "em_input.hpp"
 
 namespace rsq {
 
@@ -2192,51 +2193,11 @@ static void apply_error_model(rsq_engine &e, const char *in_path, const char *ou
 	const Profile &p = e.prof;
 	SimCtx &c = e.ctx;
 	e.launches = 0; e.d_error_flag.zero(s);
-	// read records (SeqAn FASTA semantics: id = header without '>', sequence = DnaString: non-ACGTU -> A)
-	TextInput in(in_path);
-	if(!in.is_open()){ throw std::runtime_error(std::string("Could not open '") + in_path + "' for reading."); }
-	std::istream &f = in.stream();
-	std::vector<std::string> ids; std::vector<std::string> seqs;
-	{
-		std::string line;
-		while(std::getline(f, line)){
-			if(!line.empty() && line.back() == '\r'){ line.pop_back(); }
-			if(!line.empty() && line[0] == '>'){ ids.push_back(line.substr(1)); seqs.emplace_back(); }
-			else if(!seqs.empty()){ for(char ch : line){ if(ch != ' ' && ch != '\t'){ seqs.back().push_back(ch); } } }
-		}
-	}
-	if(ids.empty()){ throw std::runtime_error(std::string(in_path) + " does not contain any sequences."); }
-	std::vector<EmRecord> recs(ids.size());
-	std::vector<uint8_t> hseq, hdom, hrate; std::string hid;
-	uint32_t max_len = 0;
-	for(size_t i = 0; i < ids.size(); ++i){
-		const std::string &id = ids[i]; const size_t L = seqs[i].size();
-		if(id.size() <= 2 * L + 2){ throw std::runtime_error("Read description is too short to contain systematic error information and a sequence id: " + id); }
-		size_t end_pos = id.size() - 2 * L - 3;
-		if(';' != id[end_pos + 1] || ';' != id[end_pos + 2 + L]){ throw std::runtime_error("The two systematic error entries are not separated by a semicolon from themselves or the rest of the ReSeq information: " + id); }
-		EmRecord r{}; r.seq_off = hseq.size(); r.len = L;
-		for(size_t pos = 0; pos < L; ++pos){
-			hseq.push_back(Genome::code(seqs[i][pos]) & 3);
-			hdom.push_back(Genome::code(id[end_pos + 2 + pos]));
-			uint8_t rate = static_cast<uint8_t>(id[id.size() - L + pos] - 33);
-			if(86 < rate){ rate += rate - 86; }
-			hrate.push_back(rate);
-		}
-		while(end_pos && ' ' != id[end_pos]){ --end_pos; }
-		if(0 == end_pos){ throw std::runtime_error("No sequence id found that is separated by a space from the ReSeq information: " + id); }
-		r.id_off = hid.size(); r.id_len = end_pos; hid.append(id, 0, end_pos);
-		if('1' == id[end_pos + 1]){ r.seg = 0; }
-		else if('2' == id[end_pos + 1]){ r.seg = 1; }
-		else{ throw std::runtime_error(std::string("Template segment is ") + id[end_pos + 1] + " not 1 or 2: " + id); }
-		if(';' != id[end_pos + 2]){ throw std::runtime_error("The template segment and fragment length are not separated by a semicolon: " + id); }
-		const std::string fl = id.substr(end_pos + 3, id.size() - 2 * L - 2 - (end_pos + 3));
-		size_t used = 0; int v = 0;
-		try{ v = std::stoi(fl, &used); }catch(...){ used = 0; }
-		if(used < fl.size() || fl.empty()){ throw std::runtime_error("Fragment length '" + fl + "' is not a pure integer: " + id); }
-		r.fragment_length = v;
-		recs[i] = r;
-		max_len = std::max<uint32_t>(max_len, L);
-	}
+	// read records (SeqAn FASTA semantics: id = header without '>', sequence = DnaString: non-ACGTU -> A); em_input.hpp
+	EmInput input = read_em_input(in_path);
+	std::vector<EmRecord> &recs = input.recs;
+	std::vector<uint8_t> &hseq = input.seq, &hdom = input.dom, &hrate = input.rate; std::string &hid = input.ids;
+	const uint32_t max_len = input.max_len;
 	if(max_len > kMaxOrgLen){ throw std::runtime_error("input fragments longer than " + std::to_string(kMaxOrgLen) + " bases are not supported by this build"); }
 	// sys_gc_range + adapter systematic errors from the master stream, then one seed per 10000-record batch
 	// The reference never initialises sys_gc_range_ on this path (it is only set inside Simulate / SimulateErrorModelOnly,
