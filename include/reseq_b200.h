@@ -44,6 +44,19 @@ rsq_reference *rsq_reference_from_memory(uint32_t n_seqs, const char *const *ids
 /* Reference::PrepareMethylationFile + ReadMethylation (Reference.cpp:1132-1322), `--methylation <bed>`: extended bedGraph
  * "<sequence> <start> <end> <methylation>"; reads simulated from this reference get bisulfite C->T conversions. */
 int rsq_reference_load_methylation(rsq_reference *ref, const char *bed_path);
+/* Reference::PrepareVariantFile + ReadFirstVariants + ReadVariants + InsertVariant (Reference.cpp:96-113, 126-426, 1005-1078;
+ * Reference.h:115-139), `-V/--vcfSim <vcf>`: contigs checked against the reference, genotype columns -> allele bit sets, records
+ * split into single-position variants sorted deletion/substitution/insertion.  The whole file is read (the reference pages it in per
+ * sequence, Simulator.cpp:938, 1278); a file the reference rejects anywhere is rejected here with the same diagnostics.
+ * This revision loads, validates and exposes the variants; rsq_engine_prepare refuses a reference that carries them (the
+ * variant-aware kernels are the next step), so a run never silently ignores a VCF. */
+int rsq_reference_load_variants(rsq_reference *ref, const char *vcf_path);
+uint32_t rsq_reference_num_alleles(const rsq_reference *ref);      /* Reference::NumAlleles (1 without variants) */
+uint64_t rsq_reference_num_variants(const rsq_reference *ref, uint32_t seq);   /* Reference::Variants(seq).size() */
+/* Reference::Variants(seq), flattened: position[k], replacement bases (codes 0..3) bases[bases_off[k] .. bases_off[k+1]),
+ * allele bits 0-63 / 64-127.  bases_off needs capacity + 1 entries. */
+int rsq_reference_variants(const rsq_reference *ref, uint32_t seq, uint64_t capacity, uint32_t *position, uint32_t *bases_off,
+                           uint64_t *allele_lo, uint64_t *allele_hi, uint8_t *bases, uint64_t bases_capacity);
 uint64_t rsq_reference_total_size(const rsq_reference *ref);       /* Reference::TotalSize */
 uint32_t rsq_reference_num_sequences(const rsq_reference *ref);    /* Reference::NumberSequences */
 void rsq_reference_free(rsq_reference *ref);

@@ -10,6 +10,7 @@
 //   dump_tables profile <stats.reseq> <out.flat>                      profile + LogArrayResult tables
 //   dump_tables patch <in.reseq> <out.reseq> <seed>                    synthetic GC / surroundings / dispersion biases
 //   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat>   + normalisation, thresholds, seeds, sys-errors
+//   dump_tables variants <ref.fa> <in.vcf> <out.txt>                  Reference::variants_ after reading the whole VCF
 //
 // Private members are reached by re-declaring access for this translation unit only.
 #include <algorithm>
@@ -214,6 +215,29 @@ int main(int argc, char **argv){
 		fd.fragment_surroundings_bias_.CombinePositions(separated);
 		fd.dispersion_parameters_ = {{0.25, 0.75}};
 		if(!stats.Save(argv[3])){ return 1; }
+		return 0;
+	}
+	if(mode == "variants" && argc >= 5){
+		// Reference::PrepareVariantFile + ReadFirstVariants + ReadVariants (Reference.cpp:126-426, 1005-1078), as Simulate calls
+		// them (Simulator.cpp:2750-2751, 938, 1278), but for all sequences at once. One text line per variant:
+		// "<seq> <position> <var_seq or -> <allele bits 0-63, hex> <allele bits 64-127, hex>"; exit code 1 + no lines when the reference rejects the file.
+		Reference ref;
+		if(!ref.ReadFasta(argv[2])){ return 1; }
+		std::ofstream out(argv[4]);
+		if(!ref.PrepareVariantFile(argv[3]) || !ref.ReadFirstVariants() || !ref.ReadVariants(ref.NumberSequences())){
+			out << "rejected\n";
+			return 1;
+		}
+		out << "alleles " << ref.NumAlleles() << "\n";
+		for(uintRefSeqId s = 0; s < ref.NumberSequences(); ++s){
+			for(const auto &v : ref.Variants(s)){
+				std::string vs;
+				for(auto b : v.var_seq_){ vs += static_cast<char>(b); }
+				char bits[64];
+				snprintf(bits, sizeof(bits), "%llx %llx", static_cast<unsigned long long>(v.allele_[0]), static_cast<unsigned long long>(v.allele_[1]));
+				out << s << ' ' << v.position_ << ' ' << (vs.empty() ? std::string("-") : vs) << ' ' << bits << "\n";
+			}
+		}
 		return 0;
 	}
 	if(mode == "sim" && argc >= 7){

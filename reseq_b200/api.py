@@ -49,6 +49,11 @@ SIGNATURES = {
     "rsq_reference_load_fasta": (C.c_void_p, [C.c_char_p]),
     "rsq_reference_from_memory": (C.c_void_p, [C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_uint64)]),
     "rsq_reference_load_methylation": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "rsq_reference_load_variants": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "rsq_reference_num_alleles": (C.c_uint32, [C.c_void_p]),
+    "rsq_reference_num_variants": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+    "rsq_reference_variants": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.c_uint64]),
     "rsq_reference_total_size": (C.c_uint64, [C.c_void_p]),
     "rsq_reference_num_sequences": (C.c_uint32, [C.c_void_p]),
     "rsq_reference_free": (None, [C.c_void_p]),
@@ -168,6 +173,32 @@ class Reference:
         lib = load_library()
         if lib.rsq_reference_load_methylation(self._h, os.fsencode(bed_path)):
             raise _err(lib)
+
+    def load_variants(self, vcf_path):
+        """Reference::PrepareVariantFile/ReadFirstVariants/ReadVariants (-V/--vcfSim): loads and validates the whole VCF."""
+        lib = load_library()
+        if lib.rsq_reference_load_variants(self._h, os.fsencode(vcf_path)):
+            raise _err(lib)
+
+    @property
+    def num_alleles(self):
+        return load_library().rsq_reference_num_alleles(self._h)
+
+    def variants(self, seq):
+        """Reference::Variants(seq) as a list of (position, replacement bases, allele bit set as a Python int)."""
+        lib = load_library()
+        n = lib.rsq_reference_num_variants(self._h, seq)
+        cap_bases = 1 << 20
+        while True:
+            pos, off = (C.c_uint32 * max(n, 1))(), (C.c_uint32 * (n + 1))()
+            lo, hi = (C.c_uint64 * max(n, 1))(), (C.c_uint64 * max(n, 1))()
+            bases = (C.c_uint8 * cap_bases)()
+            if lib.rsq_reference_variants(self._h, seq, n, pos, off, lo, hi, bases, cap_bases) == 0:
+                break
+            if cap_bases >= 1 << 30:
+                raise _err(lib)
+            cap_bases <<= 4
+        return [(pos[k], "".join("ACGT"[b] for b in bases[off[k]:off[k + 1]]), lo[k] | (hi[k] << 64)) for k in range(n)]
 
     @property
     def total_size(self):

@@ -1,7 +1,8 @@
 // reseq-b200: command line shell over libreseq_b200.so that keeps the reference's `reseq illuminaPE` /
 // `reseq seqToIllumina` simulation options (reference reseq/main.cpp:694-1137; README.md:133-231) for the hot path.
-// Profile creation (-b/--bamIn), IPF fitting and variants (-V) are outside this path: those options are
-// rejected with a message instead of being silently ignored.
+// Profile creation (-b/--bamIn) and IPF fitting are outside this path: those options are rejected with a message instead of
+// being silently ignored. -V/--vcfSim files are read and checked like the reference does; simulating with them is refused by
+// the engine until its variant-aware kernels exist.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -67,7 +68,7 @@ void usage(){
 }
 
 int reject_unsupported(const Args &a){
-	for(const char *k : {"bamIn", "vcfSim", "vcfIn", "adapterFile", "adapterMatrix"}){
+	for(const char *k : {"bamIn", "vcfIn", "adapterFile", "adapterMatrix"}){
 		if(a.has(k)){ return err(std::string("option --") + k + " belongs to a part of ReSeq this engine does not replace (stats creation, variants); run it with the reference implementation"); }
 	}
 	for(const char *k : {"statsOnly", "stopAfterEstimation"}){ if(a.flags.count(k)){ return err(std::string("option --") + k + " is a stats/IPF step; use the reference implementation"); } }
@@ -114,6 +115,8 @@ int run_illumina_pe(const Args &a){
 	rsq_reference *ref = rsq_reference_load_fasta(ref_path.c_str());
 	if(!ref){ return err(rsq_last_error()); }
 	if(a.has("methylation") && rsq_reference_load_methylation(ref, a.get("methylation").c_str())){ rsq_reference_free(ref); return err(rsq_last_error()); }
+	// -V: read and checked like Reference::PrepareVariantFile/ReadVariants; the engine then refuses the run (variant-aware kernels: next revision)
+	if(a.has("vcfSim") && rsq_reference_load_variants(ref, a.get("vcfSim").c_str())){ rsq_reference_free(ref); return err(rsq_last_error()); }
 	rsq_profile *prof = load_profile(a);
 	if(!prof){ rsq_reference_free(ref); return 1; }
 	rsq_sim_options opt{};

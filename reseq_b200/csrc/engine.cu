@@ -2398,6 +2398,37 @@ int rsq_reference_load_methylation(rsq_reference *ref, const char *bed_path){
 	RSQ_CATCH(1)
 }
 
+int rsq_reference_load_variants(rsq_reference *ref, const char *vcf_path){
+	RSQ_TRY
+	ref->g.read_variants(vcf_path);
+	return 0;
+	RSQ_CATCH(1)
+}
+uint32_t rsq_reference_num_alleles(const rsq_reference *ref){ return ref->g.variants.num_alleles; }
+uint64_t rsq_reference_num_variants(const rsq_reference *ref, uint32_t seq){
+	return seq < ref->g.variants.variants.size() ? ref->g.variants.variants[seq].size() : 0;
+}
+int rsq_reference_variants(const rsq_reference *ref, uint32_t seq, uint64_t capacity, uint32_t *position, uint32_t *bases_off,
+                           uint64_t *allele_lo, uint64_t *allele_hi, uint8_t *bases, uint64_t bases_capacity){
+	RSQ_TRY
+	if(seq >= ref->g.variants.variants.size()){ throw std::runtime_error("rsq_reference_variants: no variants loaded for this sequence"); }
+	const auto &vars = ref->g.variants.variants[seq];
+	uint64_t n_bases = 0;
+	for(const auto &v : vars){ n_bases += v.var_seq.size(); }
+	if(vars.size() > capacity || n_bases > bases_capacity){ throw std::runtime_error("rsq_reference_variants: destination too small"); }
+	uint32_t off = 0;
+	for(size_t k = 0; k < vars.size(); ++k){
+		position[k] = vars[k].position;
+		bases_off[k] = off;
+		allele_lo[k] = vars[k].allele[0];
+		allele_hi[k] = vars[k].allele[1];
+		for(uint8_t b : vars[k].var_seq){ bases[off++] = b; }
+	}
+	bases_off[vars.size()] = off;
+	return 0;
+	RSQ_CATCH(1)
+}
+
 uint64_t rsq_reference_total_size(const rsq_reference *ref){ return ref->g.total_size(); }
 uint32_t rsq_reference_num_sequences(const rsq_reference *ref){ return ref->g.seqs.size(); }
 void rsq_reference_free(rsq_reference *ref){ delete ref; }
@@ -2425,6 +2456,11 @@ int rsq_engine_prepare(rsq_engine *engine, const rsq_reference *ref, const rsq_s
 	RSQ_TRY
 	RSQ_CUDA(cudaSetDevice(engine->device));
 	if(report){ std::memset(report, 0, sizeof *report); }
+	if(ref->g.variants.loaded()){
+		// the VCF is loaded and validated like the reference does; the variant-aware halves of the kernels
+		// (allele choice, per-allele bias modifiers, spliced sequences, SysErrorVariant) are not built - no silent reference-only run.
+		throw std::runtime_error("this reference carries variants (rsq_reference_load_variants): variant-aware simulation is not part of this engine revision");
+	}
 	prepare(*engine, ref->g, *opt, report);
 	return 0;
 	RSQ_CATCH(1)

@@ -28,6 +28,7 @@
 #include <thread>
 #include <vector>
 #include "text_io.hpp"
+#include "variants.hpp"
 
 namespace rsq {
 
@@ -314,6 +315,14 @@ template<class It> inline std::vector<double> discrete_cp(It b, It e){
 struct Genome {
 	std::vector<std::string> ids;               // full header lines
 	std::vector<std::vector<uint8_t>> seqs;     // Dna5 codes: A0 C1 G2 T3 N4
+
+	// Reference::variants_ / num_alleles_, filled by read_variants() (variants.hpp)
+	VariantSet variants;
+	void read_variants(const std::string &path){
+		std::vector<std::string> first_parts;
+		for(size_t i = 0; i < ids.size(); ++i){ first_parts.push_back(first_part(i)); }
+		variants.read(path, first_parts, seqs);
+	}
 
 	// Reference::unmethylated_regions_ / unmethylation_ (allele 0), filled by read_methylation()
 	bool methylation_loaded = false;

@@ -1,0 +1,167 @@
+#!/usr/bin/env python3
+"""Golden fixtures for the VCF loader (reseq_b200/csrc/variants.hpp): synthetic VCFs over tests/golden/simref_small.fa and what the
+UNMODIFIED reference holds in Reference::variants_ after reading them (oracle/_ref/dump_tables variants, built by oracle/Makefile).
+
+    python tests/golden/make_variants_golden.py        (needs oracle/_ref/dump_tables, i.e. /root/reference at build time)
+
+Writes simref_small_var*.vcf and simref_small_var*.variants.txt ("rejected" when the reference refuses the file) next to this script."""
+import os
+import random
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+DUMP = os.path.join(ROOT, "oracle", "_ref", "dump_tables")
+REF = os.path.join(HERE, "simref_small.fa")
+
+
+def header(names, n_samples):
+    lines = ["##fileformat=VCFv4.2", "##source=reseq_b200 tests/golden/make_variants_golden.py"]
+    lines += [f"##contig=<ID={n},length={ln}>" for n, ln in names]
+    lines += ['##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">']
+    lines += ["#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{k}" for k in range(n_samples))]
+    return lines
+
+
+def other(rng, base):
+    return rng.choice([b for b in "ACGT" if b != base])
+
+
+def records(rng, seqs, ploidies, per_seq):
+    """Position-sorted, non-overlapping records of every shape ReadVariants distinguishes; N stretches are avoided (the
+    reference compares REF after ReplaceN, the dump does not run ReplaceN)."""
+    out = []
+    for (name, _), seq in zip(NAMES, seqs):
+        pos = rng.randrange(0, 40)
+        for _ in range(per_seq):
+            pos += rng.randrange(1, 2 * len(seq) // per_seq // 3 + 2)
+            kind = rng.choice(["snp", "snp", "mnp", "ins", "del", "complex_long", "complex_short", "multi", "lower", "same"])
+            rlen = {"snp": 1, "mnp": 3, "ins": 1, "del": rng.randrange(2, 9), "complex_long": 3, "complex_short": 4, "multi": 2, "lower": 1, "same": 2}[kind]
+            if pos + rlen + 1 >= len(seq):
+                break
+            ref = seq[pos:pos + rlen]
+            if "N" in ref:
+                pos += rlen
+                continue
+            if kind == "snp":
+                alts = [other(rng, ref)]
+            elif kind == "mnp":
+                alts = [other(rng, ref[0]) + ref[1] + other(rng, ref[2])]
+            elif kind == "ins":
+                alts = [ref + "".join(rng.choice("ACGT") for _ in range(rng.randrange(1, 12)))]
+            elif kind == "del":
+                alts = [ref[0]]
+            elif kind == "complex_long":
+                alts = [other(rng, ref[0]) + ref[1] + ref[2] + "".join(rng.choice("ACGT") for _ in range(2))]
+            elif kind == "complex_short":
+                alts = [ref[0] + other(rng, ref[1])]
+            elif kind == "multi":
+                alts = [ref[0] + other(rng, ref[1]), ref + "ACT", ref[0], ref + "ACT"[:2] + "G"]
+            elif kind == "lower":
+                alts = [other(rng, ref).lower()]
+            else:
+                alts = [ref[0] + other(rng, ref[1]), ref]   # second alternative equals the reference: nothing to insert for it
+            gts = []
+            for ploidy in ploidies:
+                sep = rng.choice("|/")
+                gts.append(sep.join(str(rng.randrange(0, len(alts) + 1)) for _ in range(ploidy)) + rng.choice(["", ":12", ":3:0.5"]))
+            out.append((name, pos + 1, ref, ",".join(alts), gts))
+            pos += rlen
+    return out
+
+
+def write_vcf(path, recs, n_samples, names=None):
+    with open(path, "w") as f:
+        f.write("\n".join(header(names or NAMES, n_samples)) + "\n")
+        for name, pos, ref, alt, gts in recs:
+            f.write(f"{name}\t{pos}\t.\t{ref}\t{alt}\t{30 + pos % 7}\tPASS\tDP=20\tGT" + "".join("\t" + g for g in gts) + "\n")
+
+
+def dump(vcf):
+    out = vcf[:-4] + ".variants.txt"
+    rc = subprocess.run([DUMP, "variants", REF, vcf, out], stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL).returncode
+    text = open(out).read()
+    assert (rc != 0) == text.startswith("rejected"), (vcf, rc)
+    return text
+
+
+def main():
+    global NAMES
+    ids, seqs = [], []
+    for line in open(REF):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            ids.append(line[1:].split(" ")[0])
+            seqs.append([])
+        else:
+            seqs[-1].append(line.upper())
+    seqs = ["".join(s) for s in seqs]
+    NAMES = [(i, len(s)) for i, s in zip(ids, seqs)]
+
+    rng = random.Random(20261017)
+    good = records(rng, seqs, [2, 2, 1], 60)                 # three populations, 5 alleles
+    write_vcf(os.path.join(HERE, "simref_small_var.vcf"), good, 3)
+    wide = records(rng, seqs, [1] * 70, 12)                  # 70 haploid populations: allele bits beyond the first word
+    write_vcf(os.path.join(HERE, "simref_small_var70.vcf"), wide, 70)
+    base = records(rng, seqs, [2], 8)
+
+    def variant(tag, edit, names=None):
+        recs = [list(r) for r in base]
+        edit(recs)
+        write_vcf(os.path.join(HERE, f"simref_small_var_bad_{tag}.vcf"), recs, 1, names)
+
+    def swap(recs):
+        recs[2], recs[3] = recs[3], recs[2]
+
+    def overlap(recs):
+        recs[1][2] = seqs[0][recs[1][1] - 1:recs[2][1]]      # REF runs into the next record
+        recs[1][3] = recs[1][2][0]
+
+    def wrong_ref(recs):
+        recs[4][2] = other(rng, recs[4][2][0]) + recs[4][2][1:]
+
+    def alt_n(recs):
+        recs[0][3] = "N"
+        recs[0][4] = ["0|1"]
+
+    def gt_index(recs):
+        recs[5][4] = ["0|9"]
+
+    def gt_few(recs):
+        recs[3][4] = ["1"]
+
+    def gt_many(recs):
+        recs[3][4] = ["1|0|1"]
+
+    def gt_char(recs):
+        recs[3][4] = [".|1"]
+
+    def seq_order(recs):
+        recs.append(list(recs[0]))
+
+    def past_end(recs):
+        recs[7][1] = NAMES[0][1] + 5
+
+    variant("unsorted", swap)
+    variant("overlap", overlap)
+    variant("wrong_ref", wrong_ref)
+    variant("alt_n", alt_n)
+    variant("gt_index", gt_index)
+    variant("gt_few", gt_few)
+    variant("gt_many", gt_many)
+    variant("gt_char", gt_char)
+    variant("seq_order", seq_order)
+    variant("past_end", past_end)
+    variant("contig_names", lambda recs: None, [("chrX", NAMES[0][1])] + NAMES[1:])
+    variant("contig_count", lambda recs: None, NAMES[:3])
+    write_vcf(os.path.join(HERE, "simref_small_var_base.vcf"), base, 1)   # the unedited base file: accepted
+
+    for name in sorted(os.listdir(HERE)):
+        if name.startswith("simref_small_var") and name.endswith(".vcf"):
+            text = dump(os.path.join(HERE, name))
+            print(f"{name}: {'rejected' if text.startswith('rejected') else str(text.count(chr(10)) - 1) + ' variants'}")
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,16 @@ def test_malformed_methylation_file_is_an_error(rb, golden, workdir):
         ref.load_methylation(bad)
 
 
+def test_reference_with_variants_is_refused_not_silently_simulated(rb, engine, golden):
+    """-V: the VCF is loaded and checked (tests/test_variants_cpu.py); until the variant-aware kernels exist a run must fail loudly."""
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    ref.load_variants(os.path.join(golden["dir"], "simref_small_var.vcf"))
+    assert ref.num_alleles == 5
+    with pytest.raises(rb.RsqError, match="variant-aware simulation"):
+        engine.prepare(ref, seed=42, coverage=20.0)
+    _simulate(engine, rb.Reference.load_fasta(golden["small_ref"]), seed=42, coverage=20.0)   # the engine stays usable
+
+
 def test_systematic_error_profile_write_and_read_against_reference_binary(rb, engine, golden, oracle, workdir):
     """--writeSysError (Simulator::CreateSystematicErrorProfile) and --readSysError (ReadSystematicErrors)."""
     fa = os.path.join(workdir, "sysref.fa")
