@@ -4,7 +4,11 @@ UNMODIFIED reference holds in Reference::variants_ after reading them (oracle/_r
 
     python tests/golden/make_variants_golden.py        (needs oracle/_ref/dump_tables, i.e. /root/reference at build time)
 
-Writes simref_small_var*.vcf and simref_small_var*.variants.txt ("rejected" when the reference refuses the file) next to this script."""
+Writes simref_small_var*.vcf and simref_small_var*.variants.txt ("rejected" when the reference refuses the file) next to this script,
+and sim_small_var{,_base}_seed42_R{1,2}.fq.xz: what `reseq illuminaPE -V <vcf>` (oracle/_ref/reseq_oracle, profile150, seed 42, coverage 20,
+one thread) writes for the 5-allele and the 2-allele file - the parity target of the variant-aware kernels."""
+import lzma
+import tempfile
 import os
 import random
 import subprocess
@@ -13,6 +17,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 DUMP = os.path.join(ROOT, "oracle", "_ref", "dump_tables")
+RESEQ = os.path.join(ROOT, "oracle", "_ref", "reseq_oracle")
 REF = os.path.join(HERE, "simref_small.fa")
 
 
@@ -163,5 +168,21 @@ def main():
             print(f"{name}: {'rejected' if text.startswith('rejected') else str(text.count(chr(10)) - 1) + ' variants'}")
 
 
+def simulate_with_reference():
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in ("profile150.reseq", "profile150.reseq.ipf"):
+            with lzma.open(os.path.join(HERE, name + ".xz")) as f, open(os.path.join(tmp, name), "wb") as o:
+                o.write(f.read())
+        for tag in ("var", "var_base"):
+            r1, r2 = os.path.join(tmp, tag + "_R1.fq"), os.path.join(tmp, tag + "_R2.fq")
+            subprocess.run([RESEQ, "illuminaPE", "-j", "1", "--verbosity", "1", "-s", os.path.join(tmp, "profile150.reseq"), "-R", REF, "--ipfIterations", "0",
+                            "--seed", "42", "-c", "20", "-1", r1, "-2", r2, "-V", os.path.join(HERE, f"simref_small_{tag}.vcf")],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            for path, seg in ((r1, "R1"), (r2, "R2")):
+                with open(path, "rb") as f, lzma.open(os.path.join(HERE, f"sim_small_{tag}_seed42_{seg}.fq.xz"), "wb", preset=9 | lzma.PRESET_EXTREME) as o:
+                    o.write(f.read())
+
+
 if __name__ == "__main__":
     main()
+    simulate_with_reference()

@@ -117,3 +117,22 @@ def test_c_abi_rejections_carry_the_reference_diagnostics(library):
         assert text in str(info.value), tag
     with pytest.raises(rb.RsqError):
         ref.load_variants(os.path.join(GOLDEN, "does_not_exist.vcf"))
+
+
+def test_reference_made_fastq_targets_for_variant_runs():
+    """Parity targets of the variant-aware kernels (not built yet): FASTQ the unmodified reference wrote with -V for the 5- and the 2-allele
+    file. Checked here only for what CreateReadId promises (Simulator.cpp:596-632): `_allele<a>` with a < NumAlleles in every id, pairs in step."""
+    import lzma
+    import re
+    for tag, alleles in (("var", 5), ("var_base", 2)):
+        ids = []
+        for seg in ("R1", "R2"):
+            text = lzma.open(os.path.join(GOLDEN, f"sim_small_{tag}_seed42_{seg}.fq.xz")).read().decode().split("\n")
+            ids.append([line for line in text[0::4] if line])
+        assert len(ids[0]) == len(ids[1]) > 4000
+        seen = set()
+        for a, b in zip(*ids):
+            m = re.match(r"@ReseqRead\d+_\d+_allele(\d+):", a)
+            assert m and a.split(":")[0] == b.split(":")[0]
+            seen.add(int(m.group(1)))
+        assert seen == set(range(alleles))
