@@ -11,6 +11,7 @@
 //   dump_tables patch <in.reseq> <out.reseq> <seed>                    synthetic GC / surroundings / dispersion biases
 //   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat>   + normalisation, thresholds, seeds, sys-errors
 //   dump_tables variants <ref.fa> <in.vcf> <out.txt>                  Reference::variants_ after reading the whole VCF
+//   dump_tables varseq <ref.fa> <in.vcf> <seed> <n> <out.txt>         n seeded calls of Reference::ReferenceSequence (variant overload) + results
 //
 // Private members are reached by re-declaring access for this translation unit only.
 #include <algorithm>
@@ -237,6 +238,60 @@ int main(int argc, char **argv){
 				snprintf(bits, sizeof(bits), "%llx %llx", static_cast<unsigned long long>(v.allele_[0]), static_cast<unsigned long long>(v.allele_[1]));
 				out << s << ' ' << v.position_ << ' ' << (vs.empty() ? std::string("-") : vs) << ' ' << bits << "\n";
 			}
+		}
+		return 0;
+	}
+	if(mode == "varseq" && argc >= 7){
+		// Reference::ReferenceSequence(insert_string, seq, start, frag_length, reversed, variants, {first variant, posCurrentlyAt}, allele)
+		// (Reference.cpp:498-567) on seeded arguments of the kind Simulator::GetOrgSeq passes (Simulator.cpp:1909-1914): the first variant
+		// at/after the start (forward) or the last one before it (reverse), or a start inside the replacement of an insertion.
+		// One line per call: "call <seq> <start> <len> <reversed> <first variant> <posCurrentlyAt> <allele> <result>".
+		Reference ref;
+		if(!ref.ReadFasta(argv[2])){ return 1; }
+		if(!ref.PrepareVariantFile(argv[3]) || !ref.ReadFirstVariants() || !ref.ReadVariants(ref.NumberSequences())){ return 1; }
+		std::mt19937_64 gen(std::stoull(argv[4]));
+		const size_t n_calls = std::stoull(argv[5]);
+		std::ofstream out(argv[6]);
+		for(size_t call = 0; call < n_calls; ++call){
+			const uintRefSeqId s = gen() % ref.NumberSequences();
+			const auto &vars = ref.Variants(s);
+			if(vars.empty()){ --call; continue; }
+			const uintSeqLen L = ref.SequenceLength(s);
+			const bool reversed = gen() & 1;
+			uintSeqLen len = (gen() % 8 == 0) ? 1 + gen() % 6 : 20 + gen() % 300;
+			uintAlleleId allele = gen() % ref.NumAlleles();
+			uintSeqLen start;
+			intVariantId first;
+			uintSeqLen first_pos = 0;
+			const intVariantId pick = gen() % vars.size();
+			if(gen() % 3 == 0 && length(vars.at(pick).var_seq_) > 1){
+				// start inside an insertion's replacement (the allele must carry it)
+				allele = vars.at(pick).FirstAllele();
+				first = pick;
+				first_pos = 1 + gen() % (length(vars.at(pick).var_seq_) - 1);
+				start = reversed ? vars.at(pick).position_ + 1 : vars.at(pick).position_;
+			}
+			else{
+				// start near a variant so that variants fall inside the returned sequence
+				const uintSeqLen jitter = gen() % 64;
+				if(reversed){
+					start = std::min<uintSeqLen>(L, vars.at(pick).position_ + 1 + jitter);
+					first = -1;
+					for(intVariantId v = 0; v < static_cast<intVariantId>(vars.size()) && vars.at(v).position_ < start; ++v){ first = v; }
+				}
+				else{
+					start = vars.at(pick).position_ > jitter ? vars.at(pick).position_ - jitter : 0;
+					first = vars.size();
+					for(intVariantId v = vars.size(); v-- && vars.at(v).position_ >= start; ){ first = v; }
+				}
+			}
+			if(reversed ? start < len + 400 : start + len + 400 > L){ --call; continue; }   // keep the walk inside the sequence
+			bool has_n = false;
+			for(uintSeqLen p = reversed ? start - len - 400 : start; p < (reversed ? start : start + len + 400); ++p){ has_n |= ref.ReferenceSequence(s)[p] == 'N'; }
+			if(has_n){ --call; continue; }   // the simulator only sees the reference after ReplaceN
+			seqan::DnaString res;
+			ref.ReferenceSequence(res, s, start, len, reversed, vars, {first, first_pos}, allele);
+			out << "call " << s << ' ' << start << ' ' << len << ' ' << reversed << ' ' << first << ' ' << first_pos << ' ' << allele << ' ' << res << "\n";
 		}
 		return 0;
 	}

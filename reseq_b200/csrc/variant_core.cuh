@@ -1,0 +1,86 @@
+// Variant-aware building blocks of the simulation path, written for both sides like core.cuh:
+// the same source runs in the host test harness (tests/host_twin/variant_core_check.cpp) and in device code.
+//
+//   VariantView                      the flattened Reference::variants_ of one reference sequence (variants.hpp: FlatVariants)
+//   splice_reference                 Reference::ReferenceSequence, variant overload (reference Reference.cpp:498-567): the first
+//                                    `frag_length` bases of allele `allele` reading forward from `start_pos`, or the reverse
+//                                    complement reading backwards from `start_pos` (exclusive), starting inside a variant's
+//                                    replacement when `first_variant_pos` is set - the a8 half of Simulator::GetOrgSeq
+//                                    (Simulator.cpp:1909-1914)
+//
+// Not consumed by a kernel yet: rsq_engine_prepare refuses references with variants until the scan and read kernels take alleles.
+#pragma once
+#include "core.cuh"
+
+namespace rsq {
+
+struct VariantView {
+	const uint32_t *position;    // [n] sorted; same position: deletion, substitution, insertions by length
+	const uint32_t *bases_off;   // [n + 1]
+	const uint8_t *bases;        // replacement bases, codes 0..3
+	const uint64_t *allele_lo, *allele_hi;
+	uint32_t n;
+	RSQ_HD bool in_allele(uint32_t var, uint32_t allele) const { return ((allele < 64 ? allele_lo[var] : allele_hi[var]) >> (allele & 63u)) & 1u; }   // Variant::InAllele
+	RSQ_HD uint32_t length(uint32_t var) const { return bases_off[var + 1] - bases_off[var]; }
+	RSQ_HD uint8_t base(uint32_t var, uint32_t k) const { return bases[bases_off[var] + k]; }
+};
+
+// out: codes 0..3 (a Dna5 'N' of the unprocessed reference becomes A like SeqAn's Dna5 -> Dna conversion; ReplaceN leaves none).
+// first_variant / first_variant_pos: the pair {id, posCurrentlyAt} of VariantBiasVarModifiers::StartVariant / EndVariant.
+// Returns the number of bases written (frag_length unless the sequence ends first).
+RSQ_HD uint32_t splice_reference(uint8_t *out, const uint8_t *seq, const VariantView &vars, uint32_t start_pos, uint32_t frag_length, bool reversed,
+                                 int32_t first_variant, uint32_t first_variant_pos, uint32_t allele){
+	uint32_t len = 0;   // length(insert_string); the reference lets it overshoot by a replacement and cuts afterwards - here writes are clipped
+	auto put = [&](uint8_t b){ if(len < frag_length){ out[len] = b & 3u; } ++len; };
+	uint32_t cur_start = start_pos;
+	int32_t cur_var = first_variant;
+	if(reversed){
+		auto put_ref_rc = [&](uint64_t from, uint32_t to){ for(uint64_t p = to; p > from; --p){ put(3u - (seq[p - 1] & 3u)); } };   // ReverseComplementorDna(infix(ref, from, to))
+		if(first_variant_pos){
+			for(uint32_t k = first_variant_pos; k > 0; --k){ put(3u - vars.base(cur_var, k - 1)); }   // prefix(var_seq_, posCurrentlyAt), reverse complemented
+			--cur_var;
+			--cur_start;
+		}
+		for( ; cur_var >= 0 && len < frag_length; --cur_var){
+			if(vars.in_allele(cur_var, allele)){
+				if(static_cast<uint64_t>(cur_start - vars.position[cur_var]) > static_cast<uint64_t>(frag_length) - len){
+					put_ref_rc(static_cast<uint64_t>(cur_start) + len - frag_length, cur_start);   // variant lies behind the returned sequence
+				}
+				else{
+					put_ref_rc(vars.position[cur_var] + 1u, cur_start);
+					for(uint32_t k = vars.length(cur_var); k > 0; --k){ put(3u - vars.base(cur_var, k - 1)); }
+					cur_start = vars.position[cur_var];
+				}
+			}
+		}
+		if(cur_var == -1 && len < frag_length){
+			put_ref_rc(static_cast<uint64_t>(cur_start) + len - frag_length, cur_start);
+		}
+	}
+	else{
+		auto put_ref = [&](uint32_t from, uint64_t to){ for(uint64_t p = from; p < to; ++p){ put(seq[p]); } };
+		if(first_variant_pos){
+			for(uint32_t k = first_variant_pos; k < vars.length(cur_var); ++k){ put(vars.base(cur_var, k)); }   // suffix(var_seq_, posCurrentlyAt)
+			++cur_var;
+			++cur_start;
+		}
+		for( ; static_cast<uint32_t>(cur_var) < vars.n && len < frag_length; ++cur_var){
+			if(vars.in_allele(cur_var, allele)){
+				if(static_cast<uint64_t>(vars.position[cur_var] - cur_start) >= static_cast<uint64_t>(frag_length) - len){
+					put_ref(cur_start, static_cast<uint64_t>(cur_start) + frag_length - len);
+				}
+				else{
+					put_ref(cur_start, vars.position[cur_var]);
+					for(uint32_t k = 0; k < vars.length(cur_var); ++k){ put(vars.base(cur_var, k)); }
+					cur_start = vars.position[cur_var] + 1u;
+				}
+			}
+		}
+		if(static_cast<uint32_t>(cur_var) == vars.n && len < frag_length){
+			put_ref(cur_start, static_cast<uint64_t>(cur_start) + frag_length - len);
+		}
+	}
+	return len < frag_length ? len : frag_length;
+}
+
+} // namespace rsq

@@ -6,7 +6,8 @@ UNMODIFIED reference holds in Reference::variants_ after reading them (oracle/_r
 
 Writes simref_small_var*.vcf and simref_small_var*.variants.txt ("rejected" when the reference refuses the file) next to this script,
 and sim_small_var{,_base}_seed42_R{1,2}.fq.xz: what `reseq illuminaPE -V <vcf>` (oracle/_ref/reseq_oracle, profile150, seed 42, coverage 20,
-one thread) writes for the 5-allele and the 2-allele file - the parity target of the variant-aware kernels."""
+one thread) writes for the 5-allele and the 2-allele file - the parity target of the variant-aware kernels (SURVEY §8 row a6);
+simref_small_var{,70}.varseq.txt.xz: 800 seeded calls each of the variant overload of Reference::ReferenceSequence with the reference's results."""
 import lzma
 import tempfile
 import os
@@ -183,6 +184,17 @@ def simulate_with_reference():
                     o.write(f.read())
 
 
+def spliced_sequences():
+    """simref_small_var{,70}.varseq.txt.xz: seeded calls of Reference::ReferenceSequence (variant overload) with their results."""
+    for tag, seed in (("var", 7), ("var70", 8)):
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "calls.txt")
+            subprocess.run([DUMP, "varseq", REF, os.path.join(HERE, f"simref_small_{tag}.vcf"), str(seed), "800", out], check=True)
+            with open(out, "rb") as f, lzma.open(os.path.join(HERE, f"simref_small_{tag}.varseq.txt.xz"), "wb", preset=9) as o:
+                o.write(f.read())
+
+
 if __name__ == "__main__":
     main()
     simulate_with_reference()
+    spliced_sequences()

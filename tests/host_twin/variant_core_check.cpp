@@ -1,0 +1,70 @@
+// TEST HARNESS: splice_reference (reseq_b200/csrc/variant_core.cuh) driven by text commands on stdin, one result line per call.
+//   load <ref.fa> <in.vcf>                      sequences + variants through Genome::read_fasta / VariantSet::read (flattened layout)
+//   seq <ACGT...>                               a single sequence 0 without variants
+//   var <position> <bases or -> <lo> <hi>       append a variant to sequence 0 (hex allele words)
+//   call <seq> <start> <len> <reversed> <first variant> <posCurrentlyAt> <allele>
+#include <cstdio>
+#include <iostream>
+#include <sstream>
+#include "../../reseq_b200/csrc/host_profile.hpp"
+#include "../../reseq_b200/csrc/variant_core.cuh"
+
+int main(){
+	rsq::Genome g;
+	std::vector<rsq::FlatVariants> flat;   // one per sequence
+	std::string line;
+	try{
+		while(std::getline(std::cin, line)){
+			std::istringstream in(line);
+			std::string cmd;
+			in >> cmd;
+			if(cmd == "load"){
+				std::string fa, vcf;
+				in >> fa >> vcf;
+				g = rsq::Genome();
+				g.read_fasta(fa);
+				g.read_variants(vcf);
+				flat.clear();
+				for(const auto &per_seq : g.variants.variants){
+					rsq::VariantSet one;
+					one.variants.push_back(per_seq);
+					flat.push_back(one.flatten());
+				}
+			}
+			else if(cmd == "seq"){
+				std::string bases;
+				in >> bases;
+				g = rsq::Genome();
+				g.ids.push_back("s");
+				g.seqs.emplace_back(bases.size());
+				rsq::Genome::encode(bases.data(), bases.size(), g.seqs[0].data());
+				flat.assign(1, rsq::FlatVariants());
+				flat[0].bases_off.push_back(0);
+			}
+			else if(cmd == "var"){
+				uint32_t pos; std::string bases, lo, hi;
+				in >> pos >> bases >> lo >> hi;
+				auto &f = flat.at(0);
+				f.position.push_back(pos);
+				if(bases != "-"){ for(char ch : bases){ f.bases.push_back(rsq::Genome::code(ch)); } }
+				f.bases_off.push_back(f.bases.size());
+				f.allele_lo.push_back(std::stoull(lo, nullptr, 16));
+				f.allele_hi.push_back(std::stoull(hi, nullptr, 16));
+			}
+			else if(cmd == "call"){
+				uint32_t s, start, len, reversed, first_pos, allele; int32_t first;
+				in >> s >> start >> len >> reversed >> first >> first_pos >> allele;
+				const auto &f = flat.at(s);
+				rsq::VariantView view{f.position.data(), f.bases_off.data(), f.bases.data(), f.allele_lo.data(), f.allele_hi.data(), static_cast<uint32_t>(f.position.size())};
+				std::vector<uint8_t> out(len + 1, 9);
+				const uint32_t n = rsq::splice_reference(out.data(), g.seqs.at(s).data(), view, start, len, reversed, first, first_pos, allele);
+				if(out[len] != 9){ throw std::runtime_error("splice_reference wrote past frag_length"); }
+				std::string text;
+				for(uint32_t k = 0; k < n; ++k){ text += "ACGT"[out[k]]; }
+				puts(text.c_str());
+			}
+		}
+	}
+	catch(const std::exception &ex){ fprintf(stderr, "%s\n", ex.what()); return 1; }
+	return 0;
+}

@@ -1,0 +1,63 @@
+"""splice_reference (reseq_b200/csrc/variant_core.cuh): the variant overload of Reference::ReferenceSequence (Reference.cpp:498-567), i.e.
+the variant-aware half of Simulator::GetOrgSeq. Host/device source exercised on the CPU.
+
+Pinned by the reference's own known answers (ReferenceTest.cpp:286-334) and by 2 x 800 seeded calls answered by the unmodified reference
+(`oracle/_ref/dump_tables varseq`, committed as tests/golden/simref_small_var{,70}.varseq.txt.xz)."""
+import lzma
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# reference-test.fa sequence 0 (ReferenceTest.cpp:274); the calls below only touch its first and last 12 bases
+SEQ0 = ("AGCTTTTCATTCTGACTGCAACGGGCAATATGTCTCTGTGTGGATTAAAAAAAGAGTGTCTGATAGCAGCTTCTGAACTGGTTACCTGCCGTGAGTAAATTAAAATTTTATTGACTTAGGTCACTAAATACTTTAACCAATATAGGCATAGCGCACAGACAGATAAAAATTACAGAGTACACAACATCCATGAAACG"
+        "CATTAGCACCACCATTACCACCACCATCACCATTACCACAGGTAACGGTGCGGGCTGACGCGTACAGGAAACACAGAAAAAAGCCCGCACCTGACAGTGCGGGCTTTTTTTTTCGACCAAAGGTAACGAGGTAACAACCATGCGAGTGTTGAAGTTCGGCGGTACATCAGTGGCAAATGCAGAACGTTTTCTGCGTGTTGCC"
+        "GATATTCTGGAAAGCAATGCCAGGCAGGGGCAGGTGGCCACCGTCCTCTCTGCCCCCGCCAAAATCACCAACCACCTGGTGGCGATGATTGAAAAAACCAT")
+# test_variants of ReferenceTest.cpp:286-289 (+ 317): {position, var_seq, allele bits}
+VARS = [(2, "-", 2), (4, "TAG", 3), (9, "C", 1)]
+LAST = (499, "TAG", 3)
+# (start, len, reversed, first variant, posCurrentlyAt, allele) -> expected, ReferenceTest.cpp:290-334
+KAT = [((0, 12, 0, 0, 0, 0), "AGCTTAGTTCAC"), ((0, 11, 0, 0, 0, 1), "AGTTAGTTCAT"), ((4, 8, 0, 1, 0, 1), "TAGTTCAT"), ((4, 7, 0, 1, 1, 1), "AGTTCAT"),
+       ((4, 6, 0, 1, 2, 1), "GTTCAT"), ((10, 12, 1, 2, 0, 0), "GTGAACTAAGCT"), ((10, 11, 1, 2, 0, 1), "ATGAACTAACT"), ((5, 7, 1, 1, 0, 0), "CTAAGCT"),
+       ((5, 6, 1, 1, 2, 0), "TAAGCT"), ((5, 5, 1, 1, 1, 0), "AAGCT")]
+KAT_WITH_LAST = [((500, 12, 1, 3, 0, 0), "CTATGGTTTTTT"), ((4, 1, 0, 1, 0, 1), "T"), ((4, 1, 0, 1, 1, 1), "A"), ((4, 1, 0, 1, 2, 1), "G"),
+                 ((5, 1, 1, 1, 0, 0), "C"), ((5, 1, 1, 1, 2, 0), "T"), ((5, 1, 1, 1, 1, 0), "A")]
+
+
+@pytest.fixture(scope="module")
+def splice(workdir):
+    exe = os.path.join(workdir, "variant_core_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "host_twin", "variant_core_check.cpp"), "-lz"], check=True)
+
+    def run(commands):
+        return subprocess.run([exe], input="\n".join(commands) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")[:-1]
+    return run
+
+
+def test_reference_known_answers(splice):
+    assert len(SEQ0) == 500
+    cmds = ["seq " + SEQ0] + [f"var {p} {b} {bits:x} 0" for p, b, bits in VARS] + ["call 0 " + " ".join(map(str, c)) for c, _ in KAT]
+    cmds += ["var {} {} {:x} 0".format(*LAST)] + ["call 0 " + " ".join(map(str, c)) for c, _ in KAT_WITH_LAST]
+    assert splice(cmds) == [want for _, want in KAT + KAT_WITH_LAST]
+
+
+def test_without_variants_equals_the_plain_overload(splice):
+    """Reference.cpp:483-496: infix / reverse complement of the infix."""
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    got = splice(["seq " + SEQ0, "call 0 0 10 0 0 0 0", "call 0 500 10 1 -1 0 0", "call 0 137 150 0 0 0 0", "call 0 300 150 1 -1 0 0"])
+    assert got[0] == "AGCTTTTCAT" and got[1] == "ATGGTTTTTT"   # ReferenceTest.cpp:279-284
+    assert got[2] == SEQ0[137:287]
+    assert got[3] == "".join(comp[b] for b in reversed(SEQ0[150:300]))
+
+
+@pytest.mark.parametrize("tag", ["var", "var70"])
+def test_seeded_calls_match_the_reference(splice, tag):
+    lines = lzma.open(os.path.join(GOLDEN, f"simref_small_{tag}.varseq.txt.xz")).read().decode().strip().split("\n")
+    assert len(lines) == 800
+    calls = [" ".join(line.split(" ")[:8]) for line in lines]
+    assert sum(c.split(" ")[6] != "0" for c in calls) > 15 and {c.split(" ")[4] for c in calls} == {"0", "1"}   # starts inside insertions, both directions
+    got = splice([f"load {os.path.join(GOLDEN, 'simref_small.fa')} {os.path.join(GOLDEN, f'simref_small_{tag}.vcf')}"] + calls)
+    assert got == [line.split(" ")[8] for line in lines]
