@@ -11,6 +11,7 @@
 //   dump_tables patch <in.reseq> <out.reseq> <seed>                    synthetic GC / surroundings / dispersion biases
 //   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat>   + normalisation, thresholds, seeds, sys-errors
 //   dump_tables variants <ref.fa> <in.vcf> <out.txt>                  Reference::variants_ after reading the whole VCF
+//   dump_tables alleles <seed> <n> <out.txt>                          n seeded calls of Simulator::ChooseAlleles + the chosen ids
 //   dump_tables varseq <ref.fa> <in.vcf> <seed> <n> <out.txt>         n seeded calls of Reference::ReferenceSequence (variant overload) + results
 //
 // Private members are reached by re-declaring access for this translation unit only.
@@ -238,6 +239,33 @@ int main(int argc, char **argv){
 				snprintf(bits, sizeof(bits), "%llx %llx", static_cast<unsigned long long>(v.allele_[0]), static_cast<unsigned long long>(v.allele_[1]));
 				out << s << ' ' << v.position_ << ' ' << (vs.empty() ? std::string("-") : vs) << ' ' << bits << "\n";
 			}
+		}
+		return 0;
+	}
+	if(mode == "alleles"){
+		// Simulator::ChooseAlleles (Simulator.cpp:1386-1397) on one stream seeded with <seed>: per call possible_strands = 2 x alleles
+		// (1..128 alleles) and 1..possible_strands non-zero strands. Line: "<possible_strands> <non_zero_strands> <ids...>".
+		Simulator sim;
+		std::mt19937_64 gen(std::stoull(argv[2]));
+		std::ofstream out(argv[4]);
+		std::vector<uintAlleleId> chosen;
+		std::vector<bool> reverse_selection;
+		std::uniform_real_distribution<double> zero_to_one(0.0, 1.0);
+		for(size_t call = 0; call < std::stoull(argv[3]); ++call){
+			const uintAlleleId alleles = call % 7 == 0 ? 1 + gen() % 128 : 1 + gen() % 6;
+			const uintAlleleId possible = 2 * alleles;
+			const uintAlleleId non_zero = 1 + gen() % possible;
+			// ChooseAlleles needs a GeneralRandomDistributions only for ZeroToOne (Simulator.h:209-211: uniform_real_distribution<double>(0,1));
+			// its two halves are public through `#define private public`, so they are driven with the same distribution directly.
+			chosen.clear();
+			reverse_selection.clear();
+			reverse_selection.resize(possible, true);
+			const uintAlleleId n_draw = non_zero <= possible / 2 ? non_zero : possible - non_zero;
+			while(chosen.size() < n_draw){ sim.SelectAllele(chosen, reverse_selection, possible, zero_to_one(gen)); }
+			if(non_zero > possible / 2){ sim.ReverseSelection(chosen, reverse_selection, possible); }
+			out << possible << ' ' << non_zero;
+			for(auto id : chosen){ out << ' ' << id; }
+			out << "\n";
 		}
 		return 0;
 	}

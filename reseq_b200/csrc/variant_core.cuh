@@ -7,6 +7,8 @@
 //                                    complement reading backwards from `start_pos` (exclusive), starting inside a variant's
 //                                    replacement when `first_variant_pos` is set - the a8 half of Simulator::GetOrgSeq
 //                                    (Simulator.cpp:1909-1914)
+//   choose_alleles                   Simulator::ChooseAlleles / DrawNAlleles / SelectAllele / ReverseSelection (Simulator.cpp:1341-1397)
+//                                    for any number of (allele, strand) ids; the kernels' built-in form is the 2-id case
 //
 // Not consumed by a kernel yet: rsq_engine_prepare refuses references with variants until the scan and read kernels take alleles.
 #pragma once
@@ -81,6 +83,30 @@ RSQ_HD uint32_t splice_reference(uint8_t *out, const uint8_t *seq, const Variant
 		}
 	}
 	return len < frag_length ? len : frag_length;
+}
+
+// Sampling `non_zero_strands` of `possible_strands` (= 2 x possible alleles, <= 256) ids without replacement, in the reference's order:
+// up to half are drawn directly, more than half by drawing the complement and listing what is left in ascending order.
+// `uniform()` is GeneralRandomDistributions::ZeroToOne on the block's stream; one value per drawn id. Returns the number of ids in `chosen`.
+template<class Uniform> RSQ_HD uint32_t choose_alleles(uint16_t *chosen, uint32_t non_zero_strands, uint32_t possible_strands, Uniform &&uniform){
+	uint64_t open[4] = {~0ull, ~0ull, ~0ull, ~0ull};   // reverse_selection: bit set = id not chosen yet
+	auto is_open = [&](uint32_t id){ return (open[id >> 6] >> (id & 63u)) & 1ull; };
+	const bool direct = non_zero_strands <= possible_strands / 2;
+	const uint32_t n_draw = direct ? non_zero_strands : possible_strands - non_zero_strands;
+	uint32_t n = 0;
+	while(n < n_draw){
+		// SelectAllele
+		uint32_t id = static_cast<uint16_t>(mul_rn(uniform(), static_cast<double>(possible_strands - n)));
+		uint32_t correction = 0;
+		for(uint32_t k = 0; k < n; ++k){ if(chosen[k] <= id){ ++correction; } }
+		while(correction){ if(is_open(++id)){ --correction; } }
+		chosen[n++] = static_cast<uint16_t>(id);
+		open[id >> 6] &= ~(1ull << (id & 63u));
+	}
+	if(direct){ return n; }
+	n = 0;   // ReverseSelection
+	for(uint32_t id = 0; id < possible_strands; ++id){ if(is_open(id)){ chosen[n++] = static_cast<uint16_t>(id); } }
+	return n;
 }
 
 } // namespace rsq

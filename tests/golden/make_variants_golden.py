@@ -194,7 +194,17 @@ def spliced_sequences():
                 o.write(f.read())
 
 
+def allele_choices():
+    """choose_alleles_seed11.txt.xz: 1500 seeded calls of Simulator::SelectAllele/ReverseSelection as ChooseAlleles combines them."""
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "alleles.txt")
+        subprocess.run([DUMP, "alleles", "11", "1500", out], check=True)
+        with open(out, "rb") as f, lzma.open(os.path.join(HERE, "choose_alleles_seed11.txt.xz"), "wb", preset=9) as o:
+            o.write(f.read())
+
+
 if __name__ == "__main__":
     main()
     simulate_with_reference()
     spliced_sequences()
+    allele_choices()

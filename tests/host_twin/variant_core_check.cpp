@@ -2,9 +2,11 @@
 //   load <ref.fa> <in.vcf>                      sequences + variants through Genome::read_fasta / VariantSet::read (flattened layout)
 //   seq <ACGT...>                               a single sequence 0 without variants
 //   var <position> <bases or -> <lo> <hi>       append a variant to sequence 0 (hex allele words)
+//   alleles <seed> <n>                          replays `oracle/dump_tables alleles <seed> <n>`: same stream, same argument draws, choose_alleles
 //   call <seq> <start> <len> <reversed> <first variant> <posCurrentlyAt> <allele>
 #include <cstdio>
 #include <iostream>
+#include <random>
 #include <sstream>
 #include "../../reseq_b200/csrc/host_profile.hpp"
 #include "../../reseq_b200/csrc/variant_core.cuh"
@@ -50,6 +52,31 @@ int main(){
 				f.bases_off.push_back(f.bases.size());
 				f.allele_lo.push_back(std::stoull(lo, nullptr, 16));
 				f.allele_hi.push_back(std::stoull(hi, nullptr, 16));
+			}
+			else if(cmd == "alleles"){
+				uint64_t seed, n_calls;
+				in >> seed >> n_calls;
+				std::mt19937_64 gen(seed);
+				std::uniform_real_distribution<double> zero_to_one(0.0, 1.0);   // GeneralRandomDistributions::ZeroToOne
+				for(uint64_t call = 0; call < n_calls; ++call){
+					const uint32_t alleles = call % 7 == 0 ? 1 + gen() % 128 : 1 + gen() % 6;
+					const uint32_t possible = 2 * alleles;
+					const uint32_t non_zero = 1 + gen() % possible;
+					uint16_t chosen[256];
+					const uint32_t n = rsq::choose_alleles(chosen, non_zero, possible, [&](){ return zero_to_one(gen); });
+					printf("%u %u", possible, non_zero);
+					for(uint32_t k = 0; k < n; ++k){ printf(" %u", chosen[k]); }
+					putchar('\n');
+				}
+			}
+			else if(cmd == "select"){   // SimulatorTest::TestSelectAllele: every id of `possible` drawn with random value 0.5
+				uint32_t possible;
+				in >> possible;
+				uint16_t chosen[256];
+				// (the direct branch draws at most half of the ids: the first half of the reference's known answer)
+				const uint32_t n = rsq::choose_alleles(chosen, possible / 2, possible, [](){ return 0.5; });
+				for(uint32_t k = 0; k < n; ++k){ printf(k ? " %u" : "%u", chosen[k]); }
+				putchar('\n');
 			}
 			else if(cmd == "call"){
 				uint32_t s, start, len, reversed, first_pos, allele; int32_t first;

@@ -61,3 +61,16 @@ def test_seeded_calls_match_the_reference(splice, tag):
     assert sum(c.split(" ")[6] != "0" for c in calls) > 15 and {c.split(" ")[4] for c in calls} == {"0", "1"}   # starts inside insertions, both directions
     got = splice([f"load {os.path.join(GOLDEN, 'simref_small.fa')} {os.path.join(GOLDEN, f'simref_small_{tag}.vcf')}"] + calls)
     assert got == [line.split(" ")[8] for line in lines]
+
+
+def test_choose_alleles_known_answers(splice):
+    """SimulatorTest.cpp:89-114 TestSelectAllele: random value 0.5 throughout gives [1, 0] for 2 and [2, 1, 3, 0] for 4 ids; the direct
+    branch of ChooseAlleles draws at most half of them."""
+    assert splice(["select 2", "select 4"]) == ["1", "2 1"]
+
+
+def test_choose_alleles_matches_the_reference(splice):
+    want = lzma.open(os.path.join(GOLDEN, "choose_alleles_seed11.txt.xz")).read().decode().strip().split("\n")
+    assert len(want) == 1500 and max(int(line.split(" ")[0]) for line in want) == 256
+    assert any(int(line.split(" ")[1]) > int(line.split(" ")[0]) // 2 for line in want)   # complement branch covered
+    assert splice(["alleles 11 1500"]) == want
