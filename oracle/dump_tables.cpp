@@ -12,6 +12,7 @@
 //   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat>   + normalisation, thresholds, seeds, sys-errors
 //   dump_tables variants <ref.fa> <in.vcf> <out.txt>                  Reference::variants_ after reading the whole VCF
 //   dump_tables alleles <seed> <n> <out.txt>                          n seeded calls of Simulator::ChooseAlleles + the chosen ids
+//   dump_tables syserrvar <seed> <n_blocks> <n_walks> <out.txt>       seeded SimBlock chain with SysErrorVariants + walks of GetSysErrorFromBlock
 //   dump_tables varseq <ref.fa> <in.vcf> <seed> <n> <out.txt>         n seeded calls of Reference::ReferenceSequence (variant overload) + results
 //
 // Private members are reached by re-declaring access for this translation unit only.
@@ -265,6 +266,60 @@ int main(int argc, char **argv){
 			if(non_zero > possible / 2){ sim.ReverseSelection(chosen, reverse_selection, possible); }
 			out << possible << ' ' << non_zero;
 			for(auto id : chosen){ out << ' ' << id; }
+			out << "\n";
+		}
+		return 0;
+	}
+	if(mode == "syserrvar" && argc >= 6){
+		// Simulator::GetSysErrorFromBlock (Simulator.cpp:240-292) over a chain of SimBlocks with seeded sys_errors_ / err_variants_ (3 alleles).
+		// "b <len> <n variants>", "s <4 hex digits per position: dominant error, rate>", "v <position> <allele bits> <n errors> <hex>" describe the
+		// chain; "walk <block> <block_pos> <cur_var> <allele> <steps> <4 hex digits per step>" is what the reference returns step by step.
+		Simulator sim;
+		std::mt19937_64 gen(std::stoull(argv[2]));
+		const size_t n_blocks = std::stoull(argv[3]);
+		std::ofstream out(argv[5]);
+		auto hex4 = [](unsigned dom, unsigned rate){ char b[8]; snprintf(b, sizeof b, "%02x%02x", dom, rate); return std::string(b); };
+		std::vector<Simulator::SimBlock *> blocks;
+		for(size_t b = 0; b < n_blocks; ++b){
+			auto *blk = new Simulator::SimBlock(b, b * 1000, NULL, 0);
+			const size_t len = b + 1 == n_blocks ? 1 + gen() % 1000 : (b % 5 == 3 ? 1 + gen() % 40 : 1000);
+			for(size_t p = 0; p < len; ++p){ blk->sys_errors_.emplace_back(seqan::Dna5(gen() % 5), gen() % 101); }
+			uintSeqLen pos = gen() % 30;
+			while(pos < len){
+				std::vector<std::pair<seqan::Dna5, uintPercent>> errs;
+				const unsigned kind = gen() % 4;
+				const size_t n_err = kind == 0 ? 0 : (kind == 3 ? 2 + gen() % 5 : 1);
+				for(size_t k = 0; k < n_err; ++k){ errs.emplace_back(seqan::Dna5(gen() % 5), gen() % 101); }
+				blk->err_variants_.emplace_back(pos, errs, std::array<uintAlleleBitArray, 2>{{1 + gen() % 7, 0}});
+				pos += gen() % 4 == 0 ? 0 : (gen() % 3 == 0 ? 1 : 1 + gen() % 60);   // same position, neighbours, gaps
+			}
+			if(!blocks.empty()){ blocks.back()->next_block_ = blk; }
+			blocks.push_back(blk);
+			out << "b " << len << ' ' << blk->err_variants_.size() << "\ns ";
+			for(auto &e : blk->sys_errors_){ out << hex4(static_cast<unsigned>(seqan::ordValue(e.first)), e.second); }
+			out << "\n";
+			for(auto &v : blk->err_variants_){
+				out << "v " << v.position_ << ' ' << v.allele_[0] << ' ' << v.var_errors_.size() << ' ';
+				for(auto &e : v.var_errors_){ out << hex4(static_cast<unsigned>(seqan::ordValue(e.first)), e.second); }
+				out << "\n";
+			}
+		}
+		for(size_t w = 0; w < std::stoull(argv[4]); ++w){
+			const size_t b0 = gen() % (n_blocks - 1);
+			const Simulator::SimBlock *block = blocks[b0];
+			uintSeqLen block_pos = gen() % block->sys_errors_.size();
+			intVariantId cur_var = 0;
+			while(cur_var < static_cast<intVariantId>(block->err_variants_.size()) && block->err_variants_.at(cur_var).position_ < block_pos){ ++cur_var; }
+			uintSeqLen var_pos = 0;
+			const uintAlleleId allele = gen() % 3;
+			const size_t steps = 50 + gen() % 400;
+			out << "walk " << b0 << ' ' << block_pos << ' ' << cur_var << ' ' << allele << ' ' << steps << ' ';
+			for(size_t k = 0; k < steps && block; ++k){
+				seqan::Dna5 dom;
+				uintPercent rate;
+				sim.GetSysErrorFromBlock(dom, rate, block, block_pos, cur_var, var_pos, allele);
+				out << hex4(static_cast<unsigned>(seqan::ordValue(dom)), rate);
+			}
 			out << "\n";
 		}
 		return 0;

@@ -9,6 +9,8 @@
 //                                    (Simulator.cpp:1909-1914)
 //   choose_alleles                   Simulator::ChooseAlleles / DrawNAlleles / SelectAllele / ReverseSelection (Simulator.cpp:1341-1397)
 //                                    for any number of (allele, strand) ids; the kernels' built-in form is the 2-id case
+//   sys_error_with_variants          Simulator::GetSysErrorFromBlock + IncrementBlockPos (Simulator.cpp:232-292): the systematic error of
+//                                    the next base of allele `allele`, walking the per-block SysErrorVariant lists (Simulator.h:91-106)
 //
 // Not consumed by a kernel yet: rsq_engine_prepare refuses references with variants until the scan and read kernels take alleles.
 #pragma once
@@ -83,6 +85,69 @@ RSQ_HD uint32_t splice_reference(uint8_t *out, const uint8_t *seq, const Variant
 		}
 	}
 	return len < frag_length ? len : frag_length;
+}
+
+// SimBlock::sys_errors_ / err_variants_ of one strand of one sequence, flattened: block b owns sys[block_start[b] .. block_start[b+1]) and the
+// variants [var_first[b], var_first[b+1]); a variant's position counts from the block start; an entry is dominant error | rate << 8.
+struct SysErrorVariantView {
+	const uint16_t *sys;
+	const uint32_t *block_start;   // [n_blocks + 1]
+	const uint32_t *var_first;     // [n_blocks + 1]
+	const uint32_t *position;      // [n_var]
+	const uint32_t *err_off;       // [n_var + 1] into errs (var_errors_: empty = deletion, 1 = substitution, more = insertion)
+	const uint16_t *errs;
+	const uint64_t *allele_lo, *allele_hi;
+	RSQ_HD bool in_allele(uint32_t var, uint32_t allele) const { return ((allele < 64 ? allele_lo[var] : allele_hi[var]) >> (allele & 63u)) & 1u; }
+};
+struct SysErrorCursor { uint32_t block, block_pos; int32_t cur_var; uint32_t var_pos; };   // block, block_pos, cur_var, var_pos of the reference
+
+// Returns dominant error | rate << 8 and advances the cursor exactly like the reference - including its two oddities: inside an insertion
+// (var_pos > 0) the values come from sys_errors_[block_pos], not from var_errors_[var_pos], and a substitution advances cur_var twice.
+RSQ_HD uint16_t sys_error_with_variants(const SysErrorVariantView &v, SysErrorCursor &c, uint32_t allele){
+	auto increment_block_pos = [&](){   // IncrementBlockPos (cur_var already advanced by the caller where the reference passes ++cur_var)
+		if(v.block_start[c.block + 1] - v.block_start[c.block] <= ++c.block_pos){ ++c.block; c.block_pos = 0; c.cur_var = 0; }
+	};
+	uint16_t res = 0;
+	bool no_variant = true;
+	if(c.var_pos){
+		no_variant = false;
+		res = v.sys[v.block_start[c.block] + c.block_pos];
+		const uint32_t var = v.var_first[c.block] + c.cur_var;
+		if(++c.var_pos >= v.err_off[var + 1] - v.err_off[var]){
+			c.var_pos = 0;
+			++c.cur_var;
+			increment_block_pos();
+		}
+	}
+	else{
+		while(static_cast<uint32_t>(c.cur_var) < v.var_first[c.block + 1] - v.var_first[c.block] && v.position[v.var_first[c.block] + c.cur_var] <= c.block_pos){
+			const uint32_t var = v.var_first[c.block] + c.cur_var;
+			if(v.in_allele(var, allele)){
+				const uint32_t n_err = v.err_off[var + 1] - v.err_off[var];
+				if(n_err == 0){   // deletion
+					++c.cur_var;
+					increment_block_pos();
+				}
+				else{
+					no_variant = false;
+					res = v.errs[v.err_off[var]];
+					if(n_err == 1){   // substitution
+						++c.cur_var;
+						increment_block_pos();
+						++c.cur_var;
+					}
+					else{ c.var_pos = 1; }   // insertion
+					break;
+				}
+			}
+			else{ ++c.cur_var; }
+		}
+	}
+	if(no_variant){
+		res = v.sys[v.block_start[c.block] + c.block_pos];
+		increment_block_pos();
+	}
+	return res;
 }
 
 // Sampling `non_zero_strands` of `possible_strands` (= 2 x possible alleles, <= 256) ids without replacement, in the reference's order:

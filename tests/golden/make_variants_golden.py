@@ -203,8 +203,18 @@ def allele_choices():
             o.write(f.read())
 
 
+def sys_error_walks():
+    """sys_error_variants_seed5.txt.xz: a seeded SimBlock chain with SysErrorVariants and 300 walks of Simulator::GetSysErrorFromBlock."""
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "walks.txt")
+        subprocess.run([DUMP, "syserrvar", "5", "12", "300", out], check=True)
+        with open(out, "rb") as f, lzma.open(os.path.join(HERE, "sys_error_variants_seed5.txt.xz"), "wb", preset=9) as o:
+            o.write(f.read())
+
+
 if __name__ == "__main__":
     main()
     simulate_with_reference()
     spliced_sequences()
     allele_choices()
+    sys_error_walks()

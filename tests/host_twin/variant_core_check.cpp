@@ -3,8 +3,10 @@
 //   seq <ACGT...>                               a single sequence 0 without variants
 //   var <position> <bases or -> <lo> <hi>       append a variant to sequence 0 (hex allele words)
 //   alleles <seed> <n>                          replays `oracle/dump_tables alleles <seed> <n>`: same stream, same argument draws, choose_alleles
+//   sysfile <path>                              chain description of `oracle/dump_tables syserrvar` -> its "walk" lines recomputed by sys_error_with_variants
 //   call <seq> <start> <len> <reversed> <first variant> <posCurrentlyAt> <allele>
 #include <cstdio>
+#include <fstream>
 #include <iostream>
 #include <random>
 #include <sstream>
@@ -67,6 +69,51 @@ int main(){
 					printf("%u %u", possible, non_zero);
 					for(uint32_t k = 0; k < n; ++k){ printf(" %u", chosen[k]); }
 					putchar('\n');
+				}
+			}
+			else if(cmd == "sysfile"){
+				std::string path;
+				in >> path;
+				std::ifstream f(path);
+				std::vector<uint16_t> sys, errs;
+				std::vector<uint32_t> block_start{0}, var_first{0}, position, err_off{0};
+				std::vector<uint64_t> lo, hi;
+				auto entry = [](const std::string &hex, size_t k){ return static_cast<uint16_t>(std::stoul(hex.substr(4 * k, 2), nullptr, 16) | (std::stoul(hex.substr(4 * k + 2, 2), nullptr, 16) << 8)); };
+				std::string l;
+				while(std::getline(f, l)){
+					std::istringstream li(l);
+					std::string tag;
+					li >> tag;
+					if(tag == "b"){
+						uint32_t len, n_var;
+						li >> len >> n_var;
+						block_start.push_back(block_start.back() + len);
+						var_first.push_back(var_first.back() + n_var);
+					}
+					else if(tag == "s"){
+						std::string hex;
+						li >> hex;
+						for(size_t k = 0; k < hex.size() / 4; ++k){ sys.push_back(entry(hex, k)); }
+					}
+					else if(tag == "v"){
+						uint32_t pos, n_err; uint64_t bits; std::string hex;
+						li >> pos >> bits >> n_err >> hex;
+						position.push_back(pos); lo.push_back(bits); hi.push_back(0);
+						for(size_t k = 0; k < n_err; ++k){ errs.push_back(entry(hex, k)); }
+						err_off.push_back(errs.size());
+					}
+					else if(tag == "walk"){
+						rsq::SysErrorVariantView view{sys.data(), block_start.data(), var_first.data(), position.data(), err_off.data(), errs.data(), lo.data(), hi.data()};
+						rsq::SysErrorCursor c{0, 0, 0, 0};
+						uint32_t allele, steps;
+						li >> c.block >> c.block_pos >> c.cur_var >> allele >> steps;
+						printf("walk %u %u %d %u %u ", c.block, c.block_pos, c.cur_var, allele, steps);
+						for(uint32_t k = 0; k < steps && c.block + 1 < block_start.size(); ++k){
+							const uint16_t e = rsq::sys_error_with_variants(view, c, allele);
+							printf("%02x%02x", e & 0xffu, e >> 8);
+						}
+						putchar('\n');
+					}
 				}
 			}
 			else if(cmd == "select"){   // SimulatorTest::TestSelectAllele: every id of `possible` drawn with random value 0.5

@@ -74,3 +74,14 @@ def test_choose_alleles_matches_the_reference(splice):
     assert len(want) == 1500 and max(int(line.split(" ")[0]) for line in want) == 256
     assert any(int(line.split(" ")[1]) > int(line.split(" ")[0]) // 2 for line in want)   # complement branch covered
     assert splice(["alleles 11 1500"]) == want
+
+
+def test_sys_error_walks_match_the_reference(splice, workdir):
+    """Simulator::GetSysErrorFromBlock (Simulator.cpp:240-292) over a chain of blocks with deletions, substitutions and insertions of three
+    alleles, same-position and neighbouring variants, short blocks: every step of 300 walks as the unmodified reference returned it."""
+    text = lzma.open(os.path.join(GOLDEN, "sys_error_variants_seed5.txt.xz")).read().decode()
+    path = os.path.join(workdir, "sys_error_variants.txt")
+    open(path, "w").write(text)
+    want = [line for line in text.split("\n") if line.startswith("walk ")]
+    assert len(want) == 300 and sum(line.startswith("v ") for line in text.split("\n")) > 200
+    assert splice([f"sysfile {path}"]) == want
