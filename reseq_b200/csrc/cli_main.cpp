@@ -69,7 +69,7 @@ void usage(){
 
 int reject_unsupported(const Args &a){
 	for(const char *k : {"bamIn", "vcfIn", "adapterFile", "adapterMatrix"}){
-		if(a.has(k)){ return err(std::string("option --") + k + " belongs to a part of ReSeq this engine does not replace (stats creation, variants); run it with the reference implementation"); }
+		if(a.has(k)){ return err(std::string("option --") + k + " belongs to a part of ReSeq this engine does not replace (stats creation); run it with the reference implementation"); }
 	}
 	for(const char *k : {"statsOnly", "stopAfterEstimation"}){ if(a.flags.count(k)){ return err(std::string("option --") + k + " is a stats/IPF step; use the reference implementation"); } }
 	if(a.has("ipfIterations") && a.get("ipfIterations") != "0"){ return err("this engine does not fit probabilities: pass a converged X.reseq.ipf (and --ipfIterations 0)"); }
