@@ -13,6 +13,7 @@
 //   dump_tables variants <ref.fa> <in.vcf> <out.txt>                  Reference::variants_ after reading the whole VCF
 //   dump_tables alleles <seed> <n> <out.txt>                          n seeded calls of Simulator::ChooseAlleles + the chosen ids
 //   dump_tables syserrvar <seed> <n_blocks> <n_walks> <out.txt>       seeded SimBlock chain with SysErrorVariants + walks of GetSysErrorFromBlock
+//   dump_tables biasmod <ref.fa> <in.vcf> <seed> <seq> <from> <n> <len_from> <len_to> <out.txt>   trace of VariantBiasVarModifiers over start positions
 //   dump_tables varseq <ref.fa> <in.vcf> <seed> <n> <out.txt>         n seeded calls of Reference::ReferenceSequence (variant overload) + results
 //
 // Private members are reached by re-declaring access for this translation unit only.
@@ -321,6 +322,67 @@ int main(int argc, char **argv){
 				out << hex4(static_cast<unsigned>(seqan::ordValue(dom)), rate);
 			}
 			out << "\n";
+		}
+		return 0;
+	}
+	if(mode == "biasmod" && argc >= 11){
+		// The variant bookkeeping of Simulator::SimulateFromGivenBlock (Simulator.cpp:2287-2353) without the random stream of a block: for
+		// every start position of [from, from+n) the do-while over inserted start bases, PrepareBiasModForCurrentStartPos, GetPossibleAlleles,
+		// then - for a seeded sparse ascending choice of fragment lengths and alleles, the way hits arrive - PrepareBiasModForCurrentFragmentLength,
+		// GetGCPercent, StartVariant/EndVariant, and CheckForInsertedBasesToStartFrom at the end of a pass.
+		//   "s <sequence after ReplaceN>"
+		//   "p <start> <first_variant_id> <start_variant_pos> <possible alleles...>"
+		//   "f <length> <allele> <end_pos_shift> <gc_perc or -> <start surrounding x3> <end surrounding x3> <StartVariant id pos> <EndVariant id pos>"
+		Reference ref;
+		if(!ref.ReadFasta(argv[2])){ return 1; }
+		const uintSeed seed = std::stoull(argv[4]);
+		ref.ReplaceN(seed);   // Simulator.cpp:2690 runs before the VCF is opened (2750)
+		if(!ref.PrepareVariantFile(argv[3]) || !ref.ReadFirstVariants() || !ref.ReadVariants(ref.NumberSequences())){ return 1; }
+		std::mt19937_64 gen(seed);
+		const uintRefSeqId seq = std::stoul(argv[5]);
+		const uintSeqLen from = std::stoul(argv[6]), n_pos = std::stoul(argv[7]), len_from = std::stoul(argv[8]), len_to = std::stoul(argv[9]);
+		std::ofstream out(argv[10]);
+		Simulator sim;
+		const auto &vars = ref.Variants(seq);
+		intVariantId first_var = 0;
+		while(first_var < static_cast<intVariantId>(vars.size()) && vars.at(first_var).position_ < from){ ++first_var; }
+		Simulator::VariantBiasVarModifiers bias_mod(first_var, ref.NumAlleles());
+		Surrounding surrounding_start;
+		ref.ForwardSurrounding(surrounding_start, seq, (0 < from ? from - 1 : ref.SequenceLength(seq) - 1));
+		std::vector<uintAlleleId> possible_alleles;
+		out << "s ";   // the sequence the reference works on (after ReplaceN)
+		for(auto b : ref.ReferenceSequence(seq)){ out << static_cast<char>(b); }
+		out << "\n";
+		for(uintSeqLen start = from; start < from + n_pos && start < ref.SequenceLength(seq); ++start){
+			surrounding_start.UpdateForward(ref.ReferenceSequence(seq), start);
+			do{
+				sim.PrepareBiasModForCurrentStartPos(bias_mod, seq, ref, start, len_from, surrounding_start);
+				sim.GetPossibleAlleles(possible_alleles, ref, bias_mod, start, seq);
+				out << "p " << start << ' ' << bias_mod.first_variant_id_ << ' ' << bias_mod.start_variant_pos_;
+				for(auto a : possible_alleles){ out << ' ' << a; }
+				out << "\n";
+				for(uintSeqLen len = len_from; len < len_to; ++len){
+					if(gen() % 24){ continue; }
+					for(auto allele : possible_alleles){
+						if(gen() % 2){ continue; }
+						sim.PrepareBiasModForCurrentFragmentLength(bias_mod, seq, ref, start, len, allele);
+						const uintSeqLen end = start + len + bias_mod.end_pos_shift_.at(allele);
+						out << "f " << len << ' ' << allele << ' ' << bias_mod.end_pos_shift_.at(allele) << ' ';
+						if(end < ref.SequenceLength(seq)){ out << static_cast<unsigned>(sim.GetGCPercent(bias_mod, seq, ref, end, len, allele)); }
+						else{ out << '-'; }
+						for(auto v : bias_mod.surrounding_start_.at(allele).sur_){ out << ' ' << v; }
+						for(auto v : bias_mod.surrounding_end_.at(allele).sur_){ out << ' ' << v; }
+						const auto sv = bias_mod.StartVariant();
+						out << ' ' << sv.first << ' ' << sv.second;
+						if(end < ref.SequenceLength(seq)){
+							const auto ev = bias_mod.EndVariant(vars, end, allele);
+							out << ' ' << ev.first << ' ' << ev.second;
+						}
+						out << "\n";
+					}
+				}
+				sim.CheckForInsertedBasesToStartFrom(bias_mod, seq, start, ref);
+			} while(bias_mod.start_variant_pos_);
 		}
 		return 0;
 	}

@@ -212,9 +212,23 @@ def sys_error_walks():
             o.write(f.read())
 
 
+def bias_modifier_traces():
+    """bias_mod_trace_seq{0,1}.txt.xz: Simulator's VariantBiasVarModifiers bookkeeping (PrepareBiasModForCurrentStartPos, GetPossibleAlleles,
+    PrepareBiasModForCurrentFragmentLength, GetGCPercent, Start/EndVariant, CheckForInsertedBasesToStartFrom) driven over start positions
+    the way SimulateFromGivenBlock does, for simref_small_var.vcf (5 alleles), with the sequence after ReplaceN in the first line."""
+    for seq, start, n in ((0, 0, 1500), (1, 9000, 1000)):
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "trace.txt")
+            subprocess.run([DUMP, "biasmod", REF, os.path.join(HERE, "simref_small_var.vcf"), "42", str(seq), str(start), str(n), "50", "400", out], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            with open(out, "rb") as f, lzma.open(os.path.join(HERE, f"bias_mod_trace_seq{seq}.txt.xz"), "wb", preset=9 | lzma.PRESET_EXTREME) as o:
+                o.write(f.read())
+
+
 if __name__ == "__main__":
     main()
     simulate_with_reference()
     spliced_sequences()
     allele_choices()
     sys_error_walks()
+    bias_modifier_traces()

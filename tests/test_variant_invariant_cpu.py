@@ -1,0 +1,104 @@
+"""The design check for variant-aware simulation: what Simulator's incremental VariantBiasVarModifiers bookkeeping
+(Simulator.cpp:1399-1896: gc_mod_, end_pos_shift_, surrounding_start_/end_, unhandled variants) yields per (start position, inserted start
+base, fragment length, allele) equals plain lookups in the *materialised allele sequence* - the reference with the allele's variants applied -
+through one coordinate map. The reference's own test states this for a handful of positions (SimulatorTest.cpp:116-195); here it is checked
+on every line of two traces written by the unmodified reference (`oracle/_ref/dump_tables biasmod`, tests/golden/bias_mod_trace_seq?.txt.xz:
+2500 start positions, ~90 000 (length, allele) evaluations, 5 alleles with deletions, substitutions, insertions, multi-allelic sites).
+
+    off_a[p]   index in allele a's sequence of the first base standing for reference position p
+    start      off_a[start] + start_variant_pos                       (start inside an insertion: its 2nd, 3rd, ... base)
+    GC %       Percent(GC of allele_seq[start : start + length], length)            = GetGCPercent
+    surroundings  forward surrounding at start, reverse surrounding at start + length - 1   = bias_mod.surrounding_start_/end_
+    end        smallest p with off_a[p] >= start + length                = cur_start_position + length + end_pos_shift_
+    possible alleles  all but those deleting the start base; inside an insertion only its carriers   = GetPossibleAlleles
+
+So the kernels need per allele a GC prefix, the two per-base surrounding-bias arrays and the map - the arrays they already use for the
+reference - instead of a port of the incremental state machine."""
+import bisect
+import lzma
+import os
+
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def load_variants(seq):
+    out = []
+    for line in open(os.path.join(GOLDEN, "simref_small_var.variants.txt")).read().strip().split("\n")[1:]:
+        s, pos, bases, lo, hi = line.split(" ")
+        if int(s) == seq:
+            out.append((int(pos), "" if bases == "-" else bases, int(lo, 16) | (int(hi, 16) << 64)))
+    return out
+
+
+def allele_sequence(ref, variants, allele):
+    by_pos = {}
+    for pos, bases, bits in variants:
+        if (bits >> allele) & 1:
+            assert pos not in by_pos   # one variant per position and allele (overlapping records are rejected on load)
+            by_pos[pos] = bases
+    parts, off, n = [], [], 0
+    for p, base in enumerate(ref):
+        off.append(n)
+        rep = by_pos.get(p, base)
+        parts.append(rep)
+        n += len(rep)
+    off.append(n)
+    return "".join(parts), off
+
+
+def forward_surrounding(seq, pos):   # SurroundingBase::Set/Forward (SurroundingBase.hpp:64-81, 196-201): 3 x 10-mer codes of pos-10 .. pos+19
+    length, start = len(seq), pos + len(seq) - 10
+    return [sum(CODE[seq[(start + block * 10 + k) % length]] << (2 * (9 - k)) for k in range(10)) for block in range(3)]
+
+
+def reverse_surrounding(seq, pos):   # the same on the reverse complement, anchored at the fragment's last base
+    length = len(seq)
+    start = (length - pos - 1) + length - 10
+    return [sum((3 - CODE[seq[length - 1 - (start + block * 10 + k) % length]]) << (2 * (9 - k)) for k in range(10)) for block in range(3)]
+
+
+@pytest.mark.parametrize("seq_id", [0, 1])
+def test_bias_modifiers_equal_lookups_in_the_allele_sequence(seq_id):
+    lines = lzma.open(os.path.join(GOLDEN, f"bias_mod_trace_seq{seq_id}.txt.xz")).read().decode().strip().split("\n")
+    ref = lines[0].split(" ")[1]
+    variants = load_variants(seq_id)
+    alleles = {a: allele_sequence(ref, variants, a) for a in range(5)}
+    checked = {"gc": 0, "surroundings": 0, "end": 0, "alleles": 0, "inside_insertion": 0}
+    start = svp = None
+    for line in lines[1:]:
+        t = line.split(" ")
+        if t[0] == "p":
+            start, first_var, svp = int(t[1]), int(t[2]), int(t[3])
+            at_start = first_var < len(variants) and variants[first_var][0] == start
+            want = []
+            for a in range(5):
+                carries = at_start and (variants[first_var][2] >> a) & 1
+                skipped = at_start and ((variants[first_var][1] == "" and carries) or (variants[first_var][1] != "" and svp and not carries))   # AlleleSkipped, Simulator.h:401-413
+                if not skipped:
+                    want.append(a)
+            assert [int(x) for x in t[4:]] == want, line
+            checked["alleles"] += 1
+            checked["inside_insertion"] += svp > 0
+            continue
+        length, allele, shift = int(t[1]), int(t[2]), int(t[3])
+        aseq, off = alleles[allele]
+        mod_start = off[start] + svp
+        end = start + length + shift
+        if end < len(ref):
+            assert bisect.bisect_left(off, mod_start + length) == end, line
+            checked["end"] += 1
+        if mod_start < 40 or mod_start + length + 40 > len(aseq):
+            continue   # circular surroundings at the sequence ends are not part of this check
+        if t[4] != "-":
+            gc = sum(c in "GC" for c in aseq[mod_start:mod_start + length])
+            assert ((gc * 100 + length // 2) // length) & 0xff == int(t[4]), line   # utilities::Percent (utilities.hpp:450-452, 552-554)
+            checked["gc"] += 1
+        assert forward_surrounding(aseq, mod_start) == [int(x) for x in t[5:8]], line
+        assert reverse_surrounding(aseq, mod_start + length - 1) == [int(x) for x in t[8:11]], line
+        checked["surroundings"] += 1
+    assert checked["gc"] > 30000 and checked["end"] > 30000 and checked["alleles"] >= 1000
+    if seq_id == 0:
+        assert checked["inside_insertion"] > 2
