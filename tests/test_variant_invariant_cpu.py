@@ -102,3 +102,38 @@ def test_bias_modifiers_equal_lookups_in_the_allele_sequence(seq_id):
     assert checked["gc"] > 30000 and checked["end"] > 30000 and checked["alleles"] >= 1000
     if seq_id == 0:
         assert checked["inside_insertion"] > 2
+
+
+@pytest.mark.parametrize("tag", ["var", "var70"])
+def test_spliced_sequences_are_slices_of_the_allele_sequence(tag):
+    """Reference::ReferenceSequence, variant overload (what GetOrgSeq calls): forward = allele_seq[off[start] + posCurrentlyAt : + length];
+    reverse = reverse complement of the `length` bases in front of off[start] (or of off[insertion] + posCurrentlyAt when the fragment ends
+    inside an insertion). 2 x 800 calls answered by the unmodified reference (tests/golden/simref_small_var{,70}.varseq.txt.xz)."""
+    seqs = []
+    for line in open(os.path.join(GOLDEN, "simref_small.fa")):
+        if line.startswith(">"):
+            seqs.append([])
+        else:
+            seqs[-1].append(line.strip().upper())
+    seqs = ["".join(s) for s in seqs]
+    per_seq = {}
+    for line in open(os.path.join(GOLDEN, f"simref_small_{tag}.variants.txt")).read().strip().split("\n")[1:]:
+        s, pos, bases, lo, hi = line.split(" ")
+        per_seq.setdefault(int(s), []).append((int(pos), "" if bases == "-" else bases, int(lo, 16) | (int(hi, 16) << 64)))
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    cache = {}
+    calls = lzma.open(os.path.join(GOLDEN, f"simref_small_{tag}.varseq.txt.xz")).read().decode().strip().split("\n")
+    for line in calls:
+        t = line.split(" ")
+        s, start, length, rev, first, first_pos, allele = map(int, t[1:8])
+        if (s, allele) not in cache:
+            cache[(s, allele)] = allele_sequence(seqs[s], per_seq.get(s, []), allele)
+        aseq, off = cache[(s, allele)]
+        if rev:
+            x = off[per_seq[s][first][0]] + first_pos if first_pos else off[start]
+            want = "".join(comp[c] for c in reversed(aseq[x - length:x]))
+        else:
+            x = off[start] + first_pos
+            want = aseq[x:x + length]
+        assert want == t[8], line[:80]
+    assert len(calls) == 800
