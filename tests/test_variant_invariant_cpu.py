@@ -137,3 +137,37 @@ def test_spliced_sequences_are_slices_of_the_allele_sequence(tag):
             want = aseq[x:x + length]
         assert want == t[8], line[:80]
     assert len(calls) == 800
+
+
+@pytest.mark.parametrize("seq_id,first_pos", [(0, 0), (1, 9000)])
+def test_start_enumeration_with_inserted_bases(seq_id, first_pos):
+    """The scan's outer loop with variants (Simulator.cpp:2287-2353 do-while + CheckForInsertedBasesToStartFrom, 1875-1896): every reference
+    position is a start once (start_variant_pos 0, which covers the first base of an insertion there), then once more per further inserted
+    base of every insertion at that position, longest-sorted order of Reference::InsertVariant; first_variant_id_ always names the first
+    variant at or behind the start that is not yet consumed. Checked against the (start, first variant, inserted base) sequence of the trace."""
+    lines = lzma.open(os.path.join(GOLDEN, f"bias_mod_trace_seq{seq_id}.txt.xz")).read().decode().strip().split("\n")
+    got = [tuple(int(x) for x in line.split(" ")[1:4]) for line in lines[1:] if line.startswith("p ")]
+    variants = load_variants(seq_id)
+    first = 0
+    while first < len(variants) and variants[first][0] < first_pos:
+        first += 1
+    want = []
+    for start in range(first_pos, got[-1][0] + 1):
+        svp = 0
+        while True:
+            want.append((start, first, svp))
+            if first < len(variants) and variants[first][0] == start:   # CheckForInsertedBasesToStartFrom
+                if svp:
+                    svp += 1
+                    if svp >= len(variants[first][1]):
+                        svp = 0
+                        first += 1
+                else:
+                    while first < len(variants) and variants[first][0] == start and len(variants[first][1]) < 2:
+                        first += 1
+                if svp == 0 and first < len(variants) and variants[first][0] == start:
+                    svp = 1
+            if not svp:
+                break
+    assert got == want
+    assert seq_id != 0 or len(got) > got[-1][0] - first_pos + 1   # insertions add starts
