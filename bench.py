@@ -196,8 +196,12 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: NCCL prints its version banner (and torchrun children anything else) straight to file
+    # descriptor 1, so the descriptor is pointed at stderr for the whole run and the line goes to a saved copy of the original
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL writes its version banner / debug lines to stdout by default; stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -282,7 +286,8 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": p / gen_s, "unit": "pairs/s", "cores": cores, "kind": "reference",
                                     "sample": f"reference binary (unmodified sources) on the whole workload ({REF_LEN} bp at {COVERAGE}x), -j {cores}, FASTQ to tmpfs, "
                                               f"read-generation interval {gen_s:.1f} s ({p} pairs)"}
-        print(json.dumps(line))
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
+    os.close(result_fd)
     if world > 1:
         dist.destroy_process_group()
     eng.close()

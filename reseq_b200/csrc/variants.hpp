@@ -11,6 +11,7 @@
 // (Simulator.cpp:938, 1278) and frees them behind itself; HBM holds the whole set, so the file is read once. A file
 // the reference would reject at any point of its run is rejected here up front with the same diagnostics.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <limits>
@@ -35,6 +36,15 @@ struct FlatVariants {                  // device layout: sequences back to back,
 	std::vector<uint32_t> bases_off;   // [n_var + 1] into bases
 	std::vector<uint8_t> bases;        // replacement bases, codes 0..3
 	std::vector<uint64_t> allele_lo, allele_hi;   // [n_var]
+};
+
+// The materialised sequence of one allele of one reference sequence and the coordinate map the variant-aware scan works with
+// (tests/test_variant_invariant_cpu.py: GC, surroundings, end position and fragment ends of an allele are plain lookups here).
+struct AlleleSequence {
+	std::vector<uint8_t> bases;    // the reference with the allele's variants applied
+	std::vector<uint32_t> off;     // [L + 1] index in `bases` of the first base standing for reference position p (off[L] = size)
+	// smallest reference position p with off[p] >= index: the reference's cur_end_position for a fragment ending at `index` (exclusive)
+	uint32_t ref_position(uint32_t index) const { return std::lower_bound(off.begin(), off.end(), index) - off.begin(); }
 };
 
 class VariantSet {
@@ -303,6 +313,29 @@ public:
 		}
 		if(in.corrupt()){ err("Could not read vcf record: corrupt or truncated gzip stream."); ++errors; }
 		if(errors){ variants.clear(); variant_positions.clear(); fail_collected(); }
+	}
+
+	// Applies the variants of `allele` to `seq` (one variant per position and allele: overlapping records are rejected by read()).
+	AlleleSequence materialise(uint32_t seq_id, const std::vector<uint8_t> &seq, uint32_t allele) const {
+		AlleleSequence a;
+		a.bases.reserve(seq.size() + seq.size() / 64);
+		a.off.resize(seq.size() + 1);
+		const auto &vars = variants.at(seq_id);
+		size_t v = 0;
+		for(uint32_t p = 0; p < seq.size(); ++p){
+			a.off[p] = a.bases.size();
+			const Variant *mine = nullptr;
+			for(; v < vars.size() && vars[v].position == p; ++v){
+				if(vars[v].in_allele(allele)){
+					if(mine){ throw std::runtime_error("two variants of one allele at position " + std::to_string(p)); }
+					mine = &vars[v];
+				}
+			}
+			if(mine){ a.bases.insert(a.bases.end(), mine->var_seq.begin(), mine->var_seq.end()); }
+			else{ a.bases.push_back(seq[p]); }
+		}
+		a.off[seq.size()] = a.bases.size();
+		return a;
 	}
 
 	FlatVariants flatten() const {

@@ -171,3 +171,28 @@ def test_start_enumeration_with_inserted_bases(seq_id, first_pos):
                 break
     assert got == want
     assert seq_id != 0 or len(got) > got[-1][0] - first_pos + 1   # insertions add starts
+
+
+def test_product_materialisation_matches_the_checked_model(workdir):
+    """VariantSet::materialise (reseq_b200/csrc/variants.hpp) builds the allele sequence + coordinate map the relations above were checked on."""
+    import subprocess
+    root = os.path.dirname(GOLDEN)
+    exe = os.path.join(workdir, "variants_check_m")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(root, "host_twin", "variants_check.cpp"), "-lz"], check=True)
+    seqs = []
+    for line in open(os.path.join(GOLDEN, "simref_small.fa")):
+        if line.startswith(">"):
+            seqs.append([])
+        else:
+            seqs[-1].append(line.strip().upper())
+    seqs = ["".join(s) for s in seqs]
+    for seq_id, allele in ((0, 0), (0, 4), (1, 2), (3, 1)):
+        out = subprocess.run([exe, os.path.join(GOLDEN, "simref_small.fa"), os.path.join(GOLDEN, "simref_small_var.vcf"), "allele", str(seq_id), str(allele)],
+                             check=True, capture_output=True, text=True).stdout.strip().split("\n")
+        aseq, off = allele_sequence(seqs[seq_id], load_variants(seq_id), allele)
+        assert out[0] == aseq
+        assert [tuple(map(int, line.split(" "))) for line in out[1:] if not line.startswith("i ")] == [(p, off[p]) for p in range(1, len(off)) if off[p] != off[p - 1] + 1]
+        for line in out[1:]:
+            if line.startswith("i "):
+                _, idx, pos = line.split(" ")
+                assert bisect.bisect_left(off, int(idx)) == int(pos)
