@@ -11,10 +11,14 @@
 //                                    for any number of (allele, strand) ids; the kernels' built-in form is the 2-id case
 //   sys_error_with_variants          Simulator::GetSysErrorFromBlock + IncrementBlockPos (Simulator.cpp:232-292): the systematic error of
 //                                    the next base of allele `allele`, walking the per-block SysErrorVariant lists (Simulator.h:91-106)
+//   allele_fragment                  what the scan needs for a hit of allele a at (start position, inserted start base, fragment length):
+//                                    GC percent, start and end surrounding, end position - PrepareBiasModForCurrentStartPos/FragmentLength,
+//                                    GetGCPercent and end_pos_shift_ of the reference (Simulator.cpp:1399-1873) as lookups in the
+//                                    materialised allele sequence (variants.hpp: AlleleSequence)
 //
 // Not consumed by a kernel yet: rsq_engine_prepare refuses references with variants until the scan and read kernels take alleles.
 #pragma once
-#include "core.cuh"
+#include "bias_core.cuh"
 
 namespace rsq {
 
@@ -148,6 +152,32 @@ RSQ_HD uint16_t sys_error_with_variants(const SysErrorVariantView &v, SysErrorCu
 		increment_block_pos();
 	}
 	return res;
+}
+
+// One allele of one reference sequence: its materialised bases, the map from reference positions and a GC prefix over the allele's bases.
+struct AlleleView {
+	const uint8_t *bases;       // [n_bases]
+	const uint32_t *off;        // [ref_len + 1]
+	const uint32_t *gc_prefix;  // [n_bases + 1] number of G/C in bases[0 .. i)
+	uint32_t n_bases, ref_len;
+};
+struct AlleleFragment { uint32_t gc_percent, end_position; uint32_t sur_start[3], sur_end[3]; };
+
+// start_variant_pos: 0, or the inserted base of the insertion at `start` the fragment starts from (the allele carries that insertion).
+// end_position is the reference's cur_end_position = cur_start_position + fragment_length + end_pos_shift_: the smallest reference
+// position whose first allele base lies at or behind the fragment's end.
+RSQ_HD void allele_fragment(const AlleleView &a, uint32_t start, uint32_t start_variant_pos, uint32_t fragment_length, AlleleFragment &f){
+	const uint32_t first = a.off[start] + start_variant_pos, end = first + fragment_length;
+	uint32_t lo = start, hi = a.ref_len;   // lower bound of `end` in off[start .. ref_len]
+	while(lo < hi){
+		const uint32_t mid = lo + (hi - lo) / 2;
+		if(a.off[mid] < end){ lo = mid + 1; } else{ hi = mid; }
+	}
+	f.end_position = lo;
+	const uint32_t gc = a.gc_prefix[end < a.n_bases ? end : a.n_bases] - a.gc_prefix[first];
+	f.gc_percent = ((gc * 100u + fragment_length / 2u) / fragment_length) & 0xffu;   // utilities::Percent into uintPercent
+	forward_surrounding(a.bases, a.n_bases, first, f.sur_start);
+	reverse_surrounding(a.bases, a.n_bases, end - 1u, f.sur_end);
 }
 
 // Sampling `non_zero_strands` of `possible_strands` (= 2 x possible alleles, <= 256) ids without replacement, in the reference's order:

@@ -4,6 +4,8 @@
 //   var <position> <bases or -> <lo> <hi>       append a variant to sequence 0 (hex allele words)
 //   alleles <seed> <n>                          replays `oracle/dump_tables alleles <seed> <n>`: same stream, same argument draws, choose_alleles
 //   sysfile <path>                              chain description of `oracle/dump_tables syserrvar` -> its "walk" lines recomputed by sys_error_with_variants
+//   trace <ref.fa> <in.vcf> <seq> <trace file>  `oracle/dump_tables biasmod` trace: every "f" line recomputed by allele_fragment on VariantSet::materialise
+//                                               of the traced (post-ReplaceN) sequence; prints "<lines checked> <mismatches>" (+ the first mismatches)
 //   call <seq> <start> <len> <reversed> <first variant> <posCurrentlyAt> <allele>
 #include <cstdio>
 #include <fstream>
@@ -115,6 +117,49 @@ int main(){
 						putchar('\n');
 					}
 				}
+			}
+			else if(cmd == "trace"){
+				std::string fa, vcf, path; uint32_t seq;
+				in >> fa >> vcf >> seq >> path;
+				rsq::Genome tg;
+				tg.read_fasta(fa);
+				tg.read_variants(vcf);   // checked against the raw reference; the traced sequence below only differs where that one has N
+				std::ifstream f(path);
+				std::string l;
+				std::getline(f, l);
+				std::vector<uint8_t> bases(l.size() - 2);
+				rsq::Genome::encode(l.data() + 2, bases.size(), bases.data());
+				std::vector<rsq::AlleleSequence> alleles;
+				std::vector<std::vector<uint32_t>> gc_prefix;
+				for(uint32_t a = 0; a < tg.variants.num_alleles; ++a){
+					alleles.push_back(tg.variants.materialise(seq, bases, a));
+					std::vector<uint32_t> pre(alleles.back().bases.size() + 1, 0);
+					for(size_t k = 0; k < alleles.back().bases.size(); ++k){ pre[k + 1] = pre[k] + (alleles.back().bases[k] == 1 || alleles.back().bases[k] == 2); }
+					gc_prefix.push_back(std::move(pre));
+				}
+				uint32_t start = 0, svp = 0;
+				uint64_t checked = 0, bad = 0;
+				while(std::getline(f, l)){
+					std::istringstream li(l);
+					std::string tag;
+					li >> tag;
+					if(tag == "p"){ int32_t first_var; li >> start >> first_var >> svp; continue; }
+					uint32_t len, allele; int32_t shift; std::string gc;
+					uint32_t sur[6];
+					li >> len >> allele >> shift >> gc;
+					for(auto &v : sur){ li >> v; }
+					const auto &as = alleles.at(allele);
+					rsq::AlleleView view{as.bases.data(), as.off.data(), gc_prefix[allele].data(), static_cast<uint32_t>(as.bases.size()), static_cast<uint32_t>(bases.size())};
+					const uint32_t first = as.off[start] + svp;
+					if(first < 40 || first + len + 40 > as.bases.size()){ continue; }   // circular surroundings at the sequence ends: not part of this check
+					rsq::AlleleFragment fr;
+					rsq::allele_fragment(view, start, svp, len, fr);
+					bool ok = fr.end_position == start + len + shift && (gc == "-" || fr.gc_percent == std::stoul(gc));
+					for(int k = 0; k < 3; ++k){ ok = ok && fr.sur_start[k] == sur[k] && fr.sur_end[k] == sur[3 + k]; }
+					++checked;
+					if(!ok && ++bad <= 3){ fprintf(stderr, "mismatch at start %u +%u: %s\n", start, svp, l.c_str()); }
+				}
+				printf("%llu %llu\n", (unsigned long long)checked, (unsigned long long)bad);
 			}
 			else if(cmd == "select"){   // SimulatorTest::TestSelectAllele: every id of `possible` drawn with random value 0.5
 				uint32_t possible;
