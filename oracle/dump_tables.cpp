@@ -13,7 +13,7 @@
 //   dump_tables variants <ref.fa> <in.vcf> <out.txt>                  Reference::variants_ after reading the whole VCF
 //   dump_tables alleles <seed> <n> <out.txt>                          n seeded calls of Simulator::ChooseAlleles + the chosen ids
 //   dump_tables syserrvar <seed> <n_blocks> <n_walks> <out.txt>       seeded SimBlock chain with SysErrorVariants + walks of GetSysErrorFromBlock
-//   dump_tables biasmod <ref.fa> <in.vcf> <seed> <seq> <from> <n> <len_from> <len_to> <out.txt>   trace of VariantBiasVarModifiers over start positions
+//   dump_tables biasmod <ref.fa> <in.vcf> <seed> <seq> <from> <n> <len_from> <len_to> <out.txt> [sparsity]   trace of VariantBiasVarModifiers over start positions
 //   dump_tables varseq <ref.fa> <in.vcf> <seed> <n> <out.txt>         n seeded calls of Reference::ReferenceSequence (variant overload) + results
 //
 // Private members are reached by re-declaring access for this translation unit only.
@@ -342,6 +342,7 @@ int main(int argc, char **argv){
 		const uintRefSeqId seq = std::stoul(argv[5]);
 		const uintSeqLen from = std::stoul(argv[6]), n_pos = std::stoul(argv[7]), len_from = std::stoul(argv[8]), len_to = std::stoul(argv[9]);
 		std::ofstream out(argv[10]);
+		const uint64_t sparsity = argc > 11 ? std::stoull(argv[11]) : 24;   // one fragment length in <sparsity> is evaluated (1 = every length)
 		Simulator sim;
 		const auto &vars = ref.Variants(seq);
 		intVariantId first_var = 0;
@@ -362,7 +363,7 @@ int main(int argc, char **argv){
 				for(auto a : possible_alleles){ out << ' ' << a; }
 				out << "\n";
 				for(uintSeqLen len = len_from; len < len_to; ++len){
-					if(gen() % 24){ continue; }
+					if(gen() % sparsity){ continue; }
 					for(auto allele : possible_alleles){
 						if(gen() % 2){ continue; }
 						sim.PrepareBiasModForCurrentFragmentLength(bias_mod, seq, ref, start, len, allele);

@@ -216,12 +216,14 @@ def bias_modifier_traces():
     """bias_mod_trace_seq{0,1}.txt.xz: Simulator's VariantBiasVarModifiers bookkeeping (PrepareBiasModForCurrentStartPos, GetPossibleAlleles,
     PrepareBiasModForCurrentFragmentLength, GetGCPercent, Start/EndVariant, CheckForInsertedBasesToStartFrom) driven over start positions
     the way SimulateFromGivenBlock does, for simref_small_var.vcf (5 alleles), with the sequence after ReplaceN in the first line."""
-    for seq, start, n in ((0, 0, 1500), (1, 9000, 1000)):
+    # the third trace evaluates EVERY fragment length 50..124 for the starts around a substitution, two deletions and a 5-base insertion
+    # (positions 3842-3893 of chr1): fragments ending inside the insertion, starts on its inserted bases
+    for name, seq, start, n, len_to, sparsity in (("seq0", 0, 0, 1500, 400, 24), ("seq1", 1, 9000, 1000, 400, 24), ("seq0_dense", 0, 3780, 120, 125, 1)):
         with tempfile.TemporaryDirectory() as tmp:
             out = os.path.join(tmp, "trace.txt")
-            subprocess.run([DUMP, "biasmod", REF, os.path.join(HERE, "simref_small_var.vcf"), "42", str(seq), str(start), str(n), "50", "400", out], check=True,
-                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            with open(out, "rb") as f, lzma.open(os.path.join(HERE, f"bias_mod_trace_seq{seq}.txt.xz"), "wb", preset=9 | lzma.PRESET_EXTREME) as o:
+            subprocess.run([DUMP, "biasmod", REF, os.path.join(HERE, "simref_small_var.vcf"), "42", str(seq), str(start), str(n), "50", str(len_to), out, str(sparsity)],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            with open(out, "rb") as f, lzma.open(os.path.join(HERE, f"bias_mod_trace_{name}.txt.xz"), "wb", preset=9 | lzma.PRESET_EXTREME) as o:
                 o.write(f.read())
 
 

@@ -60,9 +60,9 @@ def reverse_surrounding(seq, pos):   # the same on the reverse complement, ancho
     return [sum((3 - CODE[seq[length - 1 - (start + block * 10 + k) % length]]) << (2 * (9 - k)) for k in range(10)) for block in range(3)]
 
 
-@pytest.mark.parametrize("seq_id", [0, 1])
-def test_bias_modifiers_equal_lookups_in_the_allele_sequence(seq_id):
-    lines = lzma.open(os.path.join(GOLDEN, f"bias_mod_trace_seq{seq_id}.txt.xz")).read().decode().strip().split("\n")
+@pytest.mark.parametrize("seq_id,name", [(0, "seq0"), (1, "seq1"), (0, "seq0_dense")])
+def test_bias_modifiers_equal_lookups_in_the_allele_sequence(seq_id, name):
+    lines = lzma.open(os.path.join(GOLDEN, f"bias_mod_trace_{name}.txt.xz")).read().decode().strip().split("\n")
     ref = lines[0].split(" ")[1]
     variants = load_variants(seq_id)
     alleles = {a: allele_sequence(ref, variants, a) for a in range(5)}
@@ -99,8 +99,11 @@ def test_bias_modifiers_equal_lookups_in_the_allele_sequence(seq_id):
         assert forward_surrounding(aseq, mod_start) == [int(x) for x in t[5:8]], line
         assert reverse_surrounding(aseq, mod_start + length - 1) == [int(x) for x in t[8:11]], line
         checked["surroundings"] += 1
-    assert checked["gc"] > 30000 and checked["end"] > 30000 and checked["alleles"] >= 1000
-    if seq_id == 0:
+    if name == "seq0_dense":
+        assert checked["gc"] > 20000 and checked["inside_insertion"] == 4
+    else:
+        assert checked["gc"] > 30000 and checked["end"] > 30000 and checked["alleles"] >= 1000
+    if name == "seq0":
         assert checked["inside_insertion"] > 2
 
 
@@ -196,3 +199,40 @@ def test_product_materialisation_matches_the_checked_model(workdir):
             if line.startswith("i "):
                 _, idx, pos = line.split(" ")
                 assert bisect.bisect_left(off, int(idx)) == int(pos)
+
+
+@pytest.mark.parametrize("seq_id,name,inside", [(0, "seq0", 0), (1, "seq1", 0), (0, "seq0_dense", 272)])
+def test_end_variant_in_allele_coordinates(seq_id, name, inside):
+    """VariantBiasVarModifiers::EndVariant (Simulator.h:70-87), the cursor CreateReads hands to the reverse read (Simulator.cpp:687-688):
+    a fragment ending strictly inside an insertion of its allele names that insertion and the number of its bases inside the fragment;
+    otherwise the last variant of the sequence in front of the end position, whatever its alleles. (A fragment lying completely inside the
+    insertion it starts in - shorter than the insertion - has its own branch in the reference and is not covered by the traces.)"""
+    lines = lzma.open(os.path.join(GOLDEN, f"bias_mod_trace_{name}.txt.xz")).read().decode().strip().split("\n")
+    ref = lines[0].split(" ")[1]
+    variants = load_variants(seq_id)
+    positions = [v[0] for v in variants]
+    alleles = {a: allele_sequence(ref, variants, a) for a in range(5)}
+    seen_inside = 0
+    start = first_var = svp = None
+    for line in lines[1:]:
+        t = line.split(" ")
+        if t[0] == "p":
+            start, first_var, svp = int(t[1]), int(t[2]), int(t[3])
+            continue
+        assert (int(t[11]), int(t[12])) == (first_var, svp)   # StartVariant
+        if len(t) < 15:
+            continue
+        length, allele, shift = int(t[1]), int(t[2]), int(t[3])
+        _, off = alleles[allele]
+        mod_end = off[start] + svp + length
+        want = None
+        q = bisect.bisect_left(off, mod_end) - 1   # last reference position whose bases start in front of the fragment's end
+        for vid in range(bisect.bisect_left(positions, q), bisect.bisect_right(positions, q)):
+            _, bases, bits = variants[vid]
+            if (bits >> allele) & 1 and off[q] < mod_end < off[q] + len(bases):
+                want = (vid, mod_end - off[q])
+                seen_inside += 1
+        if want is None:
+            want = (bisect.bisect_left(positions, start + length + shift) - 1, 0)
+        assert want == (int(t[13]), int(t[14])), line
+    assert seen_inside == inside
