@@ -218,10 +218,12 @@ def bias_modifier_traces():
     the way SimulateFromGivenBlock does, for simref_small_var.vcf (5 alleles), with the sequence after ReplaceN in the first line."""
     # the third trace evaluates EVERY fragment length 50..124 for the starts around a substitution, two deletions and a 5-base insertion
     # (positions 3842-3893 of chr1): fragments ending inside the insertion, starts on its inserted bases
-    for name, seq, start, n, len_to, sparsity in (("seq0", 0, 0, 1500, 400, 24), ("seq1", 1, 9000, 1000, 400, 24), ("seq0_dense", 0, 3780, 120, 125, 1)):
+    # the fourth runs over the multi-allelic site of the 70-allele file (deletion, substitution and two different insertions at chr1:5115)
+    for name, tag, seq, start, n, len_to, sparsity in (("seq0", "var", 0, 0, 1500, 400, 24), ("seq1", "var", 1, 9000, 1000, 400, 24),
+                                                      ("seq0_dense", "var", 0, 3780, 120, 125, 1), ("var70", "var70", 0, 4900, 230, 300, 40)):
         with tempfile.TemporaryDirectory() as tmp:
             out = os.path.join(tmp, "trace.txt")
-            subprocess.run([DUMP, "biasmod", REF, os.path.join(HERE, "simref_small_var.vcf"), "42", str(seq), str(start), str(n), "50", str(len_to), out, str(sparsity)],
+            subprocess.run([DUMP, "biasmod", REF, os.path.join(HERE, f"simref_small_{tag}.vcf"), "42", str(seq), str(start), str(n), "50", str(len_to), out, str(sparsity)],
                            check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             with open(out, "rb") as f, lzma.open(os.path.join(HERE, f"bias_mod_trace_{name}.txt.xz"), "wb", preset=9 | lzma.PRESET_EXTREME) as o:
                 o.write(f.read())

@@ -87,12 +87,13 @@ def test_sys_error_walks_match_the_reference(splice, workdir):
     assert splice([f"sysfile {path}"]) == want
 
 
-@pytest.mark.parametrize("seq_id,name,lines", [(0, "seq0", 53611), (1, "seq1", 36594), (0, "seq0_dense", 22564)])
+@pytest.mark.parametrize("seq_id,name,lines", [(0, "seq0", 53611), (1, "seq1", 36594), (0, "seq0_dense", 22564), (0, "var70", 52376)])
 def test_allele_fragment_reproduces_the_reference_traces(splice, workdir, seq_id, name, lines):
     """allele_fragment (variant_core.cuh) on VariantSet::materialise: GC percent, start / end surrounding and end position of every traced
     (start, inserted base, length, allele) evaluation of the unmodified reference's VariantBiasVarModifiers (oracle/dump_tables biasmod)."""
     path = os.path.join(workdir, f"bias_mod_trace_{name}.txt")
     with lzma.open(os.path.join(GOLDEN, f"bias_mod_trace_{name}.txt.xz")) as f, open(path, "wb") as o:
         o.write(f.read())
-    got = splice([f"trace {os.path.join(GOLDEN, 'simref_small.fa')} {os.path.join(GOLDEN, 'simref_small_var.vcf')} {seq_id} {path}"])
+    vcf = os.path.join(GOLDEN, "simref_small_var70.vcf" if name == "var70" else "simref_small_var.vcf")   # var70: allele bits beyond the first word
+    got = splice([f"trace {os.path.join(GOLDEN, 'simref_small.fa')} {vcf} {seq_id} {path}"])
     assert got == [f"{lines} 0"]

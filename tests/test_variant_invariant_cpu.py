@@ -24,9 +24,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
 
 
-def load_variants(seq):
+def load_variants(seq, tag="var"):
     out = []
-    for line in open(os.path.join(GOLDEN, "simref_small_var.variants.txt")).read().strip().split("\n")[1:]:
+    for line in open(os.path.join(GOLDEN, f"simref_small_{tag}.variants.txt")).read().strip().split("\n")[1:]:
         s, pos, bases, lo, hi = line.split(" ")
         if int(s) == seq:
             out.append((int(pos), "" if bases == "-" else bases, int(lo, 16) | (int(hi, 16) << 64)))
@@ -60,12 +60,13 @@ def reverse_surrounding(seq, pos):   # the same on the reverse complement, ancho
     return [sum((3 - CODE[seq[length - 1 - (start + block * 10 + k) % length]]) << (2 * (9 - k)) for k in range(10)) for block in range(3)]
 
 
-@pytest.mark.parametrize("seq_id,name", [(0, "seq0"), (1, "seq1"), (0, "seq0_dense")])
+@pytest.mark.parametrize("seq_id,name", [(0, "seq0"), (1, "seq1"), (0, "seq0_dense"), (0, "var70")])
 def test_bias_modifiers_equal_lookups_in_the_allele_sequence(seq_id, name):
+    n_alleles, tag = (70, "var70") if name == "var70" else (5, "var")
     lines = lzma.open(os.path.join(GOLDEN, f"bias_mod_trace_{name}.txt.xz")).read().decode().strip().split("\n")
     ref = lines[0].split(" ")[1]
-    variants = load_variants(seq_id)
-    alleles = {a: allele_sequence(ref, variants, a) for a in range(5)}
+    variants = load_variants(seq_id, tag)
+    alleles = {a: allele_sequence(ref, variants, a) for a in range(n_alleles)}
     checked = {"gc": 0, "surroundings": 0, "end": 0, "alleles": 0, "inside_insertion": 0}
     start = svp = None
     for line in lines[1:]:
@@ -74,7 +75,7 @@ def test_bias_modifiers_equal_lookups_in_the_allele_sequence(seq_id, name):
             start, first_var, svp = int(t[1]), int(t[2]), int(t[3])
             at_start = first_var < len(variants) and variants[first_var][0] == start
             want = []
-            for a in range(5):
+            for a in range(n_alleles):
                 carries = at_start and (variants[first_var][2] >> a) & 1
                 skipped = at_start and ((variants[first_var][1] == "" and carries) or (variants[first_var][1] != "" and svp and not carries))   # AlleleSkipped, Simulator.h:401-413
                 if not skipped:
@@ -99,7 +100,9 @@ def test_bias_modifiers_equal_lookups_in_the_allele_sequence(seq_id, name):
         assert forward_surrounding(aseq, mod_start) == [int(x) for x in t[5:8]], line
         assert reverse_surrounding(aseq, mod_start + length - 1) == [int(x) for x in t[8:11]], line
         checked["surroundings"] += 1
-    if name == "seq0_dense":
+    if name == "var70":
+        assert checked["gc"] > 50000 and checked["inside_insertion"] == 6   # two different insertions at one position, three inserted bases each
+    elif name == "seq0_dense":
         assert checked["gc"] > 20000 and checked["inside_insertion"] == 4
     else:
         assert checked["gc"] > 30000 and checked["end"] > 30000 and checked["alleles"] >= 1000
