@@ -14,6 +14,7 @@
 //   dump_tables alleles <seed> <n> <out.txt>                          n seeded calls of Simulator::ChooseAlleles + the chosen ids
 //   dump_tables syserrvar <seed> <n_blocks> <n_walks> <out.txt>       seeded SimBlock chain with SysErrorVariants + walks of GetSysErrorFromBlock
 //   dump_tables biasmod <ref.fa> <in.vcf> <seed> <seq> <from> <n> <len_from> <len_to> <out.txt> [sparsity]   trace of VariantBiasVarModifiers over start positions
+//   dump_tables negbin <seed> <n> <out.txt>                           seeded fragment counts per allele: GetDispersion + NegativeBinomial as GetFragmentCounts combines them
 //   dump_tables varseq <ref.fa> <in.vcf> <seed> <n> <out.txt>         n seeded calls of Reference::ReferenceSequence (variant overload) + results
 //
 // Private members are reached by re-declaring access for this translation unit only.
@@ -241,6 +242,28 @@ int main(int argc, char **argv){
 				snprintf(bits, sizeof(bits), "%llx %llx", static_cast<unsigned long long>(v.allele_[0]), static_cast<unsigned long long>(v.allele_[1]));
 				out << s << ' ' << v.position_ << ' ' << (vs.empty() ? std::string("-") : vs) << ' ' << bits << "\n";
 			}
+		}
+		return 0;
+	}
+	if(mode == "negbin"){
+		// The tail of FragmentDistributionStats::GetFragmentCounts (FragmentDistributionStats.cpp:3617-3626) with an allele count:
+		// dispersion = GetDispersion(mean, a, b) / alleles; mean /= alleles; NegativeBinomial(mean/(mean+dispersion), dispersion, u).
+		// Line: "<mean bits> <a bits> <b bits> <alleles> <u bits> <count>" (doubles as hex bit patterns).
+		std::mt19937_64 gen(std::stoull(argv[2]));
+		std::ofstream out(argv[4]);
+		std::uniform_real_distribution<double> zero_to_one(0.0, 1.0);
+		auto bits = [](double v){ uint64_t b; std::memcpy(&b, &v, 8); char t[20]; snprintf(t, sizeof t, "%016llx", static_cast<unsigned long long>(b)); return std::string(t); };
+		for(size_t call = 0; call < std::stoull(argv[3]); ++call){
+			const double mean0 = std::exp(-9.0 + 13.0 * zero_to_one(gen));   // 1e-4 .. 55
+			const double a = call % 5 == 0 ? 0.0 : zero_to_one(gen), b = call % 5 == 0 ? 1e-100 : 0.1 + 2.0 * zero_to_one(gen);
+			const uintAlleleId alleles = call % 3 == 0 ? 1 : 1 + gen() % 128;
+			const double thr = zero_to_one(gen);
+			const double u = thr + zero_to_one(gen) * (1 - thr);   // adjusted_random of SimulateFromGivenBlock
+			double mean = mean0;
+			double dispersion = BiasCalculationVectors::GetDispersion(mean, a, b) / alleles;
+			mean /= alleles;
+			const uintDupCount count = FragmentDistributionStats::NegativeBinomial(mean / (mean + dispersion), dispersion, u);
+			out << bits(mean0) << ' ' << bits(a) << ' ' << bits(b) << ' ' << alleles << ' ' << bits(u) << ' ' << count << "\n";
 		}
 		return 0;
 	}

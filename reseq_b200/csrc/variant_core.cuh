@@ -15,6 +15,8 @@
 //                                    GC percent, start and end surrounding, end position - PrepareBiasModForCurrentStartPos/FragmentLength,
 //                                    GetGCPercent and end_pos_shift_ of the reference (Simulator.cpp:1399-1873) as lookups in the
 //                                    materialised allele sequence (variants.hpp: AlleleSequence)
+//   allele_fragment_counts           the tail of FragmentDistributionStats::GetFragmentCounts with an allele count
+//                                    (FragmentDistributionStats.cpp:3602-3626, 900-907): NB(mean / alleles, Dispersion(mean) / alleles)
 //
 // Not consumed by a kernel yet: rsq_engine_prepare refuses references with variants until the scan and read kernels take alleles.
 #pragma once
@@ -178,6 +180,28 @@ RSQ_HD void allele_fragment(const AlleleView &a, uint32_t start, uint32_t start_
 	f.gc_percent = ((gc * 100u + fragment_length / 2u) / fragment_length) & 0xffu;   // utilities::Percent into uintPercent
 	forward_surrounding(a.bases, a.n_bases, first, f.sur_start);
 	reverse_surrounding(a.bases, a.n_bases, end - 1u, f.sur_end);
+}
+
+// mean = bias * bias_normalization of the allele's fragment; (disp_a, disp_b) = dispersion_parameters_. sim_core.cuh's fragment_counts is
+// the alleles == 1 form of this (both divisions exact there). `runaway` mirrors its guard against a count that wraps uintDupCount.
+RSQ_HD uint32_t allele_fragment_counts(double mean, double disp_a, double disp_b, uint32_t alleles, double probability_chosen, bool &runaway){
+	double r = mean / add_rn(disp_a, mul_rn(disp_b, mean));   // BiasCalculationVectors::GetDispersion
+	const double cap = mul_rn(mean, 1e10);
+	if(r > cap){ r = cap; }
+	const double n = static_cast<double>(alleles);
+	r = r / n;
+	mean = mean / n;
+	const double p = mean / add_rn(mean, r);
+	double probability_count = pow_glibc(sub_rn(1.0, p), r);   // NegativeBinomial
+	double probability_left = sub_rn(probability_chosen, probability_count);
+	uint32_t count = 0;
+	while(0.0 < probability_left){
+		count = (count + 1) & 0xffffu;   // uintDupCount
+		probability_count = mul_rn(probability_count, mul_rn(p, add_rn(sub_rn(r, 1.0) / static_cast<double>(static_cast<int>(count)), 1.0)));
+		probability_left = sub_rn(probability_left, probability_count);
+		if(count == 0xffffu){ runaway = true; break; }
+	}
+	return count;
 }
 
 // Sampling `non_zero_strands` of `possible_strands` (= 2 x possible alleles, <= 256) ids without replacement, in the reference's order:

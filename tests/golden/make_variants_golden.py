@@ -229,6 +229,15 @@ def bias_modifier_traces():
                 o.write(f.read())
 
 
+def allele_fragment_counts():
+    """fragment_counts_alleles_seed3.txt.xz: 2500 seeded (mean, dispersion parameters, allele count, uniform) -> count of the reference."""
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "negbin.txt")
+        subprocess.run([DUMP, "negbin", "3", "2500", out], check=True)
+        with open(out, "rb") as f, lzma.open(os.path.join(HERE, "fragment_counts_alleles_seed3.txt.xz"), "wb", preset=9) as o:
+            o.write(f.read())
+
+
 if __name__ == "__main__":
     main()
     simulate_with_reference()
@@ -236,3 +245,4 @@ if __name__ == "__main__":
     allele_choices()
     sys_error_walks()
     bias_modifier_traces()
+    allele_fragment_counts()

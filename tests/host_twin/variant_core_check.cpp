@@ -6,8 +6,10 @@
 //   sysfile <path>                              chain description of `oracle/dump_tables syserrvar` -> its "walk" lines recomputed by sys_error_with_variants
 //   trace <ref.fa> <in.vcf> <seq> <trace file>  `oracle/dump_tables biasmod` trace: every "f" line recomputed by allele_fragment on VariantSet::materialise
 //                                               of the traced (post-ReplaceN) sequence; prints "<lines checked> <mismatches>" (+ the first mismatches)
+//   negbin <path>                               lines of `oracle/dump_tables negbin` recomputed by allele_fragment_counts: "<lines> <mismatches>"
 //   call <seq> <start> <len> <reversed> <first variant> <posCurrentlyAt> <allele>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <random>
@@ -160,6 +162,22 @@ int main(){
 					if(!ok && ++bad <= 3){ fprintf(stderr, "mismatch at start %u +%u: %s\n", start, svp, l.c_str()); }
 				}
 				printf("%llu %llu\n", (unsigned long long)checked, (unsigned long long)bad);
+			}
+			else if(cmd == "negbin"){
+				std::string path;
+				in >> path;
+				std::ifstream f(path);
+				std::string m, a, b, u;
+				uint32_t alleles, want;
+				uint64_t n = 0, bad = 0;
+				auto dbl = [](const std::string &hex){ const uint64_t bits = std::stoull(hex, nullptr, 16); double v; memcpy(&v, &bits, 8); return v; };
+				while(f >> m >> a >> b >> alleles >> u >> want){
+					bool runaway = false;
+					const uint32_t got = rsq::allele_fragment_counts(dbl(m), dbl(a), dbl(b), alleles, dbl(u), runaway);
+					++n;
+					if(got != want && ++bad <= 3){ fprintf(stderr, "mismatch: %s %s %s %u %s -> %u, reference %u\n", m.c_str(), a.c_str(), b.c_str(), alleles, u.c_str(), got, want); }
+				}
+				printf("%llu %llu\n", (unsigned long long)n, (unsigned long long)bad);
 			}
 			else if(cmd == "select"){   // SimulatorTest::TestSelectAllele: every id of `possible` drawn with random value 0.5
 				uint32_t possible;

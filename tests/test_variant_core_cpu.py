@@ -97,3 +97,14 @@ def test_allele_fragment_reproduces_the_reference_traces(splice, workdir, seq_id
     vcf = os.path.join(GOLDEN, "simref_small_var70.vcf" if name == "var70" else "simref_small_var.vcf")   # var70: allele bits beyond the first word
     got = splice([f"trace {os.path.join(GOLDEN, 'simref_small.fa')} {vcf} {seq_id} {path}"])
     assert got == [f"{lines} 0"]
+
+
+def test_fragment_counts_per_allele_match_the_reference(splice, workdir):
+    """allele_fragment_counts: GetDispersion / alleles, mean / alleles, NegativeBinomial by CDF inversion (FragmentDistributionStats.cpp:900-907,
+    3602-3626) for 1..128 alleles, Poisson-limit dispersion parameters included; bit patterns in, counts out, as the unmodified reference computed them."""
+    path = os.path.join(workdir, "fragment_counts_alleles.txt")
+    with lzma.open(os.path.join(GOLDEN, "fragment_counts_alleles_seed3.txt.xz")) as f, open(path, "wb") as o:
+        o.write(f.read())
+    lines = open(path).read().strip().split("\n")
+    assert len(lines) == 2500 and sum(line.split(" ")[5] != "0" for line in lines) > 300 and max(int(line.split(" ")[3]) for line in lines) == 128
+    assert splice([f"negbin {path}"]) == ["2500 0"]
