@@ -9,7 +9,8 @@
 //
 //   dump_tables profile <stats.reseq> <out.flat>                      profile + LogArrayResult tables
 //   dump_tables patch <in.reseq> <out.reseq> <seed>                    synthetic GC / surroundings / dispersion biases
-//   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat>   + normalisation, thresholds, seeds, sys-errors
+//   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat> [max_blocks] [in.vcf]   + normalisation, thresholds, seeds, sys-errors
+//                                                                     (with a VCF: thresholds for its allele count, first_variant_id_ and err_variants_ of every block)
 //   dump_tables variants <ref.fa> <in.vcf> <out.txt>                  Reference::variants_ after reading the whole VCF
 //   dump_tables alleles <seed> <n> <out.txt>                          n seeded calls of Simulator::ChooseAlleles + the chosen ids
 //   dump_tables syserrvar <seed> <n_blocks> <n_walks> <out.txt>       seeded SimBlock chain with SysErrorVariants + walks of GetSysErrorFromBlock
@@ -473,6 +474,7 @@ int main(int argc, char **argv){
 		uintSeed seed = std::stoull(argv[4]);
 		double coverage = std::stod(argv[5]);
 		size_t max_blocks = argc > 7 ? std::stoull(argv[7]) : static_cast<size_t>(-1);
+		const char *vcf = argc > 8 ? argv[8] : nullptr;
 		FlatWriter w(argv[6]);
 
 		// --- Simulator::Simulate prologue, statement by statement (Simulator.cpp:2687-2797) ---
@@ -497,6 +499,11 @@ int main(int argc, char **argv){
 		sim.num_adapter_only_pairs_ = round( static_cast<double>(sim.total_pairs_)*stats.FragmentDistribution().InsertLengths()[0]/(stats.TotalNumberReads()/2) );
 		sim.total_pairs_ -= sim.num_adapter_only_pairs_;
 		sim.simulation_error_ = false;
+		if(vcf){   // Simulator.cpp:2747-2759
+			if(!ref.PrepareVariantFile(vcf) || !ref.ReadFirstVariants()){ return 1; }
+			sim.sys_dom_base_per_allele_.resize(ref.NumAlleles());
+		}
+		w.s64("sim.num_alleles", ref.NumAlleles());
 		sim.bias_normalization_ = stats.FragmentDistribution().CalculateBiasNormalization(sim.coverage_groups_, sim.non_zero_thresholds_, ref, 1, sim.total_pairs_);
 		sim.sys_gc_range_ = utilities::Divide(sum_read_length,reads)/2;
 		for(auto seg=2; seg--;){
@@ -542,18 +549,35 @@ int main(int argc, char **argv){
 		// --- all blocks, in creation order (Simulator.cpp:2823-2826 + GetNextBlock) ---
 		std::vector<uint64_t> seeds; std::vector<int64_t> ids, starts, refids;
 		std::vector<uint8_t> fwd, rev;
+		// SysErrorVariants of every block, forward then its reverse partner: per variant {block index, strand (0 forward, 1 reverse), position_,
+		// allele bits 0-63, allele bits 64-127, number of var_errors_}, the (dominant error, rate) pairs concatenated in var_errs
+		std::vector<int64_t> var_rec, first_var_fwd, first_var_rev; std::vector<uint8_t> var_errs;
 		size_t nblocks = 0;
 		while(nblocks < max_blocks && sim.CreateBlock(ref, stats, est)){
 			++nblocks;
+			// the reference pages the variants of later sequences in from GetNextBlock (Simulator.cpp:1276-1285); CreateUnit loads what it needs itself (938)
 		}
+		size_t bi = 0;
 		for(auto unit = sim.first_unit_; unit; unit = unit->next_unit_){
-			for(Simulator::SimBlock *b = unit->first_block_; b; b = b->next_block_){
+			for(Simulator::SimBlock *b = unit->first_block_; b; b = b->next_block_, ++bi){
 				seeds.push_back(b->seed_); ids.push_back(b->id_); starts.push_back(b->start_pos_); refids.push_back(unit->ref_seq_id_);
 				for(auto &p : b->sys_errors_){ fwd.push_back(static_cast<uint8_t>(p.first)); fwd.push_back(p.second); }
 				// partner (reverse) block: its sys_errors_ run in reverse-strand order for the same forward interval
 				for(auto &p : b->partner_block_->sys_errors_){ rev.push_back(static_cast<uint8_t>(p.first)); rev.push_back(p.second); }
+				first_var_fwd.push_back(b->first_variant_id_); first_var_rev.push_back(b->partner_block_->first_variant_id_);
+				for(int strand = 0; strand < 2; ++strand){
+					for(auto &v : (strand ? b->partner_block_ : b)->err_variants_){
+						var_rec.push_back(bi); var_rec.push_back(strand); var_rec.push_back(v.position_);
+						var_rec.push_back(static_cast<int64_t>(v.allele_[0])); var_rec.push_back(static_cast<int64_t>(v.allele_[1])); var_rec.push_back(v.var_errors_.size());
+						for(auto &e : v.var_errors_){ var_errs.push_back(static_cast<uint8_t>(e.first)); var_errs.push_back(e.second); }
+					}
+				}
 			}
 		}
+		w.i64("sim.err_variants", var_rec);
+		w.u8("sim.err_variant_errors", var_errs);
+		w.i64("sim.block_first_variant_fwd", first_var_fwd);
+		w.i64("sim.block_first_variant_rev", first_var_rev);
 		w.u64("sim.block_seed", seeds);
 		w.i64("sim.block_id", ids);
 		w.i64("sim.block_start", starts);

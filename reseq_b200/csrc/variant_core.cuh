@@ -228,4 +228,313 @@ template<class Uniform> RSQ_HD uint32_t choose_alleles(uint16_t *chosen, uint32_
 	return n;
 }
 
+
+// ===================================================================================================================
+// Variant-aware simulation on the engine's layout (what the kernels consume)
+// ===================================================================================================================
+// Reference::variants_ of all sequences, flattened (variants.hpp: FlatVariants), and what Simulator derives from them per run.
+struct VarCtx {
+	uint32_t loaded;                 // Reference::VariantsLoaded()
+	uint32_t num_alleles;            // Reference::NumAlleles()
+	const uint32_t *seq_first;       // [n_seqs + 1] first variant of each sequence
+	const uint32_t *position;        // [n_var]
+	const uint32_t *bases_off;       // [n_var + 1]
+	const uint8_t *bases;
+	const uint64_t *allele_lo, *allele_hi;
+	// SysErrorVariant::var_errors_ (Simulator.h:91-106) of the forward / reverse SimBlock holding the variant: (dominant error, rate) of replacement
+	// base i at 2 * (bases_off[v] + i); reverse: i counts in reverse-strand order (the order SetSystematicErrorVariantsReverse draws them in)
+	const uint8_t *errs_fwd, *errs_rev;
+	// SimBlock::first_variant_id_: per sequence ceil(L / 1000) + 1 entries starting at block_first_off[seq]; entry b = first variant (counted inside
+	// the sequence) with position >= 1000 * b.  Forward block b starts from entry b, its reverse partner from entry b + 1 minus one.
+	const uint32_t *block_first;
+	const uint32_t *block_first_off; // [n_seqs]
+	const double *sur_tab[3];        // fragment_surroundings_bias_: surroundings of fragments that touch a variant are evaluated per hit
+	const double *binom_all;         // unused slot kept for layout stability
+	RSQ_HD VariantView view(uint32_t seq) const {
+		VariantView v;
+		const uint32_t f = seq_first[seq];
+		v.position = position + f; v.bases_off = bases_off + f; v.bases = bases; v.allele_lo = allele_lo + f; v.allele_hi = allele_hi + f; v.n = seq_first[seq + 1] - f;
+		return v;
+	}
+};
+
+RSQ_HD uint32_t var_lower_bound(const VariantView &v, uint32_t p){   // first variant with position >= p
+	uint32_t lo = 0, hi = v.n;
+	while(lo < hi){ const uint32_t mid = lo + (hi - lo) / 2; if(v.position[mid] < p){ lo = mid + 1; } else{ hi = mid; } }
+	return lo;
+}
+// The variant of `allele` at reference position p (one per position and allele), or -1.  vi: any index <= the first variant at p; left at the first variant with position >= p.
+RSQ_HD int32_t allele_variant_at(const VariantView &v, uint32_t &vi, uint32_t p, uint32_t allele){
+	while(vi < v.n && v.position[vi] < p){ ++vi; }
+	for(uint32_t t = vi; t < v.n && v.position[t] == p; ++t){ if(v.in_allele(t, allele)){ return static_cast<int32_t>(t); } }
+	return -1;
+}
+
+// Simulator::AlleleSkipped (Simulator.h:401-413): alleles that delete the start base, and - on the passes that start from an inserted base -
+// alleles that do not carry that insertion
+RSQ_HD bool allele_skipped(const VariantView &v, uint32_t first_var, uint32_t start_variant_pos, uint32_t pos, uint32_t allele){
+	if(first_var < v.n && v.position[first_var] == pos){
+		if(0 == v.length(first_var)){ return v.in_allele(first_var, allele); }
+		else if(start_variant_pos){ return !v.in_allele(first_var, allele); }
+	}
+	return false;
+}
+RSQ_HD uint32_t count_possible_alleles(const VariantView &v, uint32_t num_alleles, uint32_t first_var, uint32_t start_variant_pos, uint32_t pos){
+	if(!(first_var < v.n && v.position[first_var] == pos)){ return num_alleles; }
+	uint32_t n = 0;
+	for(uint32_t a = 0; a < num_alleles; ++a){ n += allele_skipped(v, first_var, start_variant_pos, pos, a) ? 0u : 1u; }
+	return n;
+}
+RSQ_HD uint32_t nth_possible_allele(const VariantView &v, uint32_t num_alleles, uint32_t first_var, uint32_t start_variant_pos, uint32_t pos, uint32_t k){
+	if(!(first_var < v.n && v.position[first_var] == pos)){ return k; }
+	for(uint32_t a = 0; a < num_alleles; ++a){
+		if(!allele_skipped(v, first_var, start_variant_pos, pos, a)){ if(0 == k){ return a; } --k; }
+	}
+	return 0;
+}
+// Simulator::CheckForInsertedBasesToStartFrom (Simulator.cpp:1875-1896): the start position is visited once more per further inserted base
+RSQ_HD void next_start_pass(const VariantView &v, uint32_t pos, uint32_t &first_var, uint32_t &start_variant_pos){
+	if(first_var < v.n && v.position[first_var] == pos){
+		if(start_variant_pos){
+			if(++start_variant_pos >= v.length(first_var)){ start_variant_pos = 0; ++first_var; }
+		}
+		else{
+			while(first_var < v.n && v.position[first_var] == pos && 2 > v.length(first_var)){ ++first_var; }
+		}
+		if(0 == start_variant_pos){
+			if(first_var < v.n && v.position[first_var] == pos){ start_variant_pos = 1; }
+		}
+	}
+}
+
+// A point between two bases of an allele's sequence: in front of reference position p, or - inside an insertion the allele carries at p -
+// behind the first k (0 < k < its length) bases of that insertion `ins`.
+struct AllelePoint { uint32_t p; uint32_t k; int32_t ins; };
+
+// The next n bases of the allele behind the point.  Beyond the sequence end the reference rolls around into its own first bases and ignores
+// variants there (Simulator.cpp:1601, 1706).
+RSQ_HD void allele_bases_forward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out){
+	uint32_t i = 0, p = at.p;
+	if(at.k){
+		for(uint32_t j = at.k; j < v.length(at.ins) && i < n; ++j){ out[i++] = v.base(at.ins, j); }
+		++p;
+	}
+	uint32_t vi = var_lower_bound(v, p);
+	while(i < n){
+		if(p >= L){ out[i++] = seq[(p - L) % L]; ++p; continue; }
+		const int32_t t = allele_variant_at(v, vi, p, allele);
+		if(t < 0){ out[i++] = seq[p]; }
+		else{ for(uint32_t j = 0; j < v.length(t) && i < n; ++j){ out[i++] = v.base(t, j); } }
+		++p;
+	}
+}
+// The n bases of the allele in front of the point, nearest first.  In front of the sequence start: the reference's last bases, variants ignored.
+RSQ_HD void allele_bases_backward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out){
+	uint32_t i = 0;
+	if(at.k){ for(uint32_t j = at.k; j-- > 0 && i < n; ){ out[i++] = v.base(at.ins, j); } }
+	int64_t q = static_cast<int64_t>(at.p) - 1;
+	uint32_t vi = var_lower_bound(v, at.p);   // one behind the last variant with position < p
+	while(i < n){
+		if(q < 0){ out[i++] = seq[static_cast<uint32_t>((static_cast<int64_t>(L) + q % static_cast<int64_t>(L)) % static_cast<int64_t>(L))]; --q; continue; }
+		while(vi > 0 && v.position[vi - 1] > static_cast<uint32_t>(q)){ --vi; }
+		int32_t t = -1;
+		for(uint32_t u = vi; u > 0 && v.position[u - 1] == static_cast<uint32_t>(q); --u){ if(v.in_allele(u - 1, allele)){ t = static_cast<int32_t>(u - 1); break; } }
+		if(t < 0){ out[i++] = seq[q]; }
+		else{ for(uint32_t j = v.length(t); j-- > 0 && i < n; ){ out[i++] = v.base(t, j); } }
+		--q;
+	}
+}
+
+// What SimulateFromGivenBlock needs for one (start position, inserted start base, fragment length, allele): PrepareBiasModForCurrentStartPos /
+// ...FragmentLength, GetGCPercent, end_pos_shift_ and EndVariant of the reference (Simulator.cpp:1399-1873, Simulator.h:68-88) evaluated directly on
+// the allele's sequence (tests/test_variant_invariant_cpu.py states the relations and checks them on traces of the unmodified reference).
+struct AlleleHit {
+	uint32_t end_position;            // cur_end_position = cur_start_position + fragment_length + end_pos_shift_
+	uint32_t gc_percent;              // GetGCPercent
+	int32_t end_var; uint32_t end_var_pos;   // EndVariant: {id, posCurrentlyAt}
+	AllelePoint end;                  // the point behind the fragment's last base
+	uint32_t valid;                   // the fragment ends inside the sequence (cur_end_position < SequenceLength)
+};
+RSQ_HD uint32_t count_gc_bases(const VariantView &v, uint32_t var, uint32_t from, uint32_t to){
+	uint32_t gc = 0;
+	for(uint32_t j = from; j < to; ++j){ const uint32_t b = v.base(var, j); gc += (b == 1u || b == 2u) ? 1u : 0u; }
+	return gc;
+}
+// gcp: G/C prefix counts of the reference sequence ([L + 1]).  first_var / start_variant_pos: VariantBiasVarModifiers::StartVariant.
+RSQ_HD void allele_hit(const VariantView &v, const uint32_t *gcp, uint32_t L, uint32_t allele, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos,
+                       uint32_t fl, AlleleHit &h){
+	uint32_t consumed = 0, gc = 0, p = pos;
+	h.valid = 0; h.end_var = -1; h.end_var_pos = 0; h.end = AllelePoint{0, 0, -1}; h.end_position = L; h.gc_percent = 0;
+	bool done = false, inside = false;
+	if(start_variant_pos){
+		const uint32_t len = v.length(first_var);
+		const uint32_t take = (len - start_variant_pos) < fl ? (len - start_variant_pos) : fl;
+		gc += count_gc_bases(v, first_var, start_variant_pos, start_variant_pos + take);
+		consumed = take;
+		p = pos + 1;
+		if(consumed == fl){
+			done = true;
+			h.end_position = pos + 1;
+			if(start_variant_pos + take < len){ h.end = AllelePoint{pos, start_variant_pos + take, static_cast<int32_t>(first_var)}; }
+			else{ h.end = AllelePoint{pos + 1, 0, -1}; }
+			// EndVariant: a fragment of one base names the start insertion (second branch), longer ones inside it fall through to the last variant in front
+			// of the end position (third branch)
+			if(1 == fl){ h.end_var = static_cast<int32_t>(first_var); h.end_var_pos = start_variant_pos + 1; inside = true; }
+		}
+	}
+	uint32_t vi = var_lower_bound(v, p);
+	while(!done){
+		// the allele's next variant at or behind p
+		uint32_t t = vi;
+		while(t < v.n && !v.in_allele(t, allele)){ ++t; }
+		const uint32_t q = t < v.n ? v.position[t] : L;
+		const uint32_t seg = q - p;
+		if(consumed + seg >= fl){
+			const uint32_t k = fl - consumed;
+			gc += gcp[p + k] - gcp[p];
+			h.end_position = p + k; h.end = AllelePoint{p + k, 0, -1};
+			break;
+		}
+		if(q >= L){ return; }   // runs off the sequence
+		gc += gcp[q] - gcp[p]; consumed += seg;
+		const uint32_t len = v.length(t);
+		const uint32_t take = len < fl - consumed ? len : fl - consumed;
+		gc += count_gc_bases(v, t, 0, take);
+		consumed += take;
+		if(consumed == fl){
+			h.end_position = q + 1;
+			if(take < len){ h.end = AllelePoint{q, take, static_cast<int32_t>(t)}; h.end_var = static_cast<int32_t>(t); h.end_var_pos = take; inside = true; }
+			else{ h.end = AllelePoint{q + 1, 0, -1}; }
+			break;
+		}
+		p = q + 1;
+		vi = t + 1;
+		while(vi < v.n && v.position[vi] <= q){ ++vi; }
+	}
+	if(h.end_position >= L){ return; }
+	h.valid = 1;
+	h.gc_percent = ((gc * 100u + fl / 2u) / fl) & 0xffu;   // utilities::Percent on uintSeqLen into uintPercent
+	if(!inside){ h.end_var = static_cast<int32_t>(var_lower_bound(v, h.end_position)) - 1; h.end_var_pos = 0; }
+}
+
+RSQ_HD uint32_t pack_10mer(const uint8_t *b){ uint32_t s = 0; for(uint32_t k = 0; k < 10; ++k){ s = (s << 2) + (b[k] & 3u); } return s; }
+// Surrounding codes of an allele's fragment: bias_mod.surrounding_start_ at its first base, bias_mod.surrounding_end_ at its last base
+RSQ_HD void allele_start_surrounding(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t code[3]){
+	uint8_t w[30], back[10];
+	const AllelePoint at{pos, start_variant_pos, start_variant_pos ? static_cast<int32_t>(first_var) : -1};
+	allele_bases_backward(v, seq, L, allele, at, 10, back);
+	for(uint32_t k = 0; k < 10; ++k){ w[k] = back[9 - k]; }
+	allele_bases_forward(v, seq, L, allele, at, 20, w + 10);
+	code[0] = pack_10mer(w); code[1] = pack_10mer(w + 10); code[2] = pack_10mer(w + 20);
+}
+RSQ_HD void allele_end_surrounding(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, const AllelePoint &end, uint32_t code[3]){
+	uint8_t w[30], fwd[10], back[20];
+	allele_bases_forward(v, seq, L, allele, end, 10, fwd);
+	allele_bases_backward(v, seq, L, allele, end, 20, back);
+	for(uint32_t k = 0; k < 10; ++k){ w[k] = 3u - fwd[9 - k]; }
+	for(uint32_t k = 0; k < 20; ++k){ w[10 + k] = 3u - back[k]; }
+	code[0] = pack_10mer(w); code[1] = pack_10mer(w + 10); code[2] = pack_10mer(w + 20);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Systematic errors of a read with variants: Simulator::GetSysErrorFromBlock / IncrementBlockPos (Simulator.cpp:232-292) and the deletion
+// branch of FillReadPart (Simulator.cpp:380-392) on the engine's flat per-position arrays.  Forward SimBlock b of a sequence covers
+// [1000 b, min(1000 (b + 1), L)); its reverse partner holds the same interval in reverse-strand order and is followed by block b - 1.
+// ---------------------------------------------------------------------------------------------------------------
+struct SysWalkCtx {
+	const uint8_t *sys;          // sys_fwd / sys_rev of the sequence: 2 bytes per position, strand order
+	const uint8_t *errs;         // VarCtx::errs_fwd / errs_rev
+	const uint32_t *block_first; // VarCtx::block_first of the sequence
+	VariantView v;
+	uint32_t L; uint32_t reverse;
+};
+struct SysWalk { uint32_t block, block_pos; int32_t cur_var; uint32_t var_pos; };   // block, block_pos, cur_var, var_pos of the reference
+
+RSQ_HD uint32_t sysw_block_end(const SysWalkCtx &c, uint32_t b){ const uint64_t e = 1000ull * (b + 1ull); return e < c.L ? static_cast<uint32_t>(e) : c.L; }
+RSQ_HD uint32_t sysw_block_size(const SysWalkCtx &c, uint32_t b){ return sysw_block_end(c, b) - 1000u * b; }
+RSQ_HD const uint8_t *sysw_entry(const SysWalkCtx &c, const SysWalk &w){   // block->sys_errors_.at(block_pos)
+	const uint64_t idx = c.reverse ? static_cast<uint64_t>(c.L - sysw_block_end(c, w.block)) + w.block_pos : 1000ull * w.block + w.block_pos;
+	return c.sys + 2ull * idx;
+}
+RSQ_HD uint32_t sysw_n_vars(const SysWalkCtx &c, uint32_t b){ return c.block_first[b + 1] - c.block_first[b]; }
+RSQ_HD uint32_t sysw_var(const SysWalkCtx &c, uint32_t b, uint32_t k){ return c.reverse ? c.block_first[b + 1] - 1u - k : c.block_first[b] + k; }   // err_variants_.at(k)
+RSQ_HD uint32_t sysw_var_position(const SysWalkCtx &c, uint32_t b, uint32_t var){ return c.reverse ? sysw_block_end(c, b) - 1u - c.v.position[var] : c.v.position[var] - 1000u * b; }
+RSQ_HD void sysw_increment(const SysWalkCtx &c, SysWalk &w){   // IncrementBlockPos (cur_var advanced by the caller where the reference passes ++cur_var)
+	if(sysw_block_size(c, w.block) <= ++w.block_pos){ w.block = c.reverse ? w.block - 1u : w.block + 1u; w.block_pos = 0; w.cur_var = 0; }
+}
+// returns dominant error | rate << 8
+RSQ_HD uint32_t sysw_next(const SysWalkCtx &c, SysWalk &w, uint32_t allele){
+	uint32_t res = 0;
+	bool no_variant = true;
+	if(w.var_pos){
+		no_variant = false;
+		const uint8_t *e = sysw_entry(c, w);   // the reference reads sys_errors_[block_pos] here, not var_errors_[var_pos]
+		res = e[0] | (static_cast<uint32_t>(e[1]) << 8);
+		const uint32_t var = sysw_var(c, w.block, static_cast<uint32_t>(w.cur_var));
+		if(++w.var_pos >= c.v.length(var)){
+			w.var_pos = 0;
+			++w.cur_var;
+			sysw_increment(c, w);
+		}
+	}
+	else{
+		while(static_cast<uint32_t>(w.cur_var) < sysw_n_vars(c, w.block) && w.cur_var >= 0){
+			const uint32_t var = sysw_var(c, w.block, static_cast<uint32_t>(w.cur_var));
+			if(!(sysw_var_position(c, w.block, var) <= w.block_pos)){ break; }
+			if(c.v.in_allele(var, allele)){
+				const uint32_t n_err = c.v.length(var);
+				if(0 == n_err){   // deletion
+					++w.cur_var;
+					sysw_increment(c, w);
+				}
+				else{
+					no_variant = false;
+					const uint8_t *e = c.errs + 2ull * c.v.bases_off[var];
+					res = e[0] | (static_cast<uint32_t>(e[1]) << 8);
+					if(1 == n_err){   // substitution: the reference advances cur_var twice
+						++w.cur_var;
+						sysw_increment(c, w);
+						++w.cur_var;
+					}
+					else{ w.var_pos = 1; }   // insertion
+					break;
+				}
+			}
+			else{ ++w.cur_var; }
+		}
+	}
+	if(no_variant){
+		const uint8_t *e = sysw_entry(c, w);
+		res = e[0] | (static_cast<uint32_t>(e[1]) << 8);
+		sysw_increment(c, w);
+	}
+	return res;
+}
+// FillReadPart's deletion branch: the error rate of sys_errors_[block_pos], then the position advances without looking at the variants
+RSQ_HD uint32_t sysw_deletion(const SysWalkCtx &c, SysWalk &w){
+	const uint32_t rate = sysw_entry(c, w)[1];
+	if(w.var_pos){
+		const uint32_t var = sysw_var(c, w.block, static_cast<uint32_t>(w.cur_var));
+		if(++w.var_pos >= c.v.length(var)){ w.var_pos = 0; }
+	}
+	if(0 == w.var_pos && sysw_block_size(c, w.block) <= ++w.block_pos){ w.block = c.reverse ? w.block - 1u : w.block + 1u; w.block_pos = 0; w.cur_var = 0; }
+	return rate;
+}
+// CreateReads (Simulator.cpp:653-689): where the two reads of a fragment start in the block chains.  start_var / end_var: StartVariant / EndVariant.
+RSQ_HD SysWalk sysw_forward_start(const SysWalkCtx &c, uint32_t start_block, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos){
+	SysWalk w;
+	w.block = start_block; w.block_pos = pos - 1000u * start_block;
+	w.cur_var = static_cast<int32_t>(first_var) - static_cast<int32_t>(c.block_first[start_block]); w.var_pos = start_variant_pos;
+	return w;
+}
+RSQ_HD SysWalk sysw_reverse_start(const SysWalkCtx &c, uint32_t start_block, uint32_t end_position, int32_t end_var, uint32_t end_var_pos){
+	SysWalk w;
+	uint32_t b = start_block;
+	while(sysw_block_end(c, b) < end_position){ ++b; }
+	w.block = b; w.block_pos = sysw_block_end(c, b) - end_position;
+	w.cur_var = static_cast<int32_t>(c.block_first[b + 1]) - 1 - end_var;
+	w.var_pos = end_var_pos ? c.v.length(static_cast<uint32_t>(end_var)) - end_var_pos : 0u;
+	return w;
+}
+
 } // namespace rsq

@@ -68,6 +68,12 @@ def oracle():
     return {"reseq": exe, "dump": dump}
 
 
+@pytest.fixture(scope="session")
+def oracle_optional():
+    exe, dump = _oracle_paths()
+    return {"reseq": exe, "dump": dump} if os.path.exists(exe) and os.path.exists(dump) else None
+
+
 def run_oracle_sim(oracle, profile, ref, seed, coverage, out_prefix, threads=1, extra=()):
     r1, r2 = out_prefix + "_R1.fq", out_prefix + "_R2.fq"
     cmd = [oracle["reseq"], "illuminaPE", "-j", str(threads), "--verbosity", "1", "-s", profile, "-R", ref, "--ipfIterations", "0",

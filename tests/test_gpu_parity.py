@@ -402,6 +402,35 @@ def test_too_short_reference_is_an_error(rb, engine):
         engine.prepare(ref, seed=1, coverage=5.0)
 
 
+@pytest.mark.parametrize("prof,key", [("profile150", "flat"), ("profile150r", "flat_r")])
+def test_full_size_equals_the_reference(rb, golden, oracle_optional, workdir, prof, key):
+    """BASELINE config C2 at full size (the workload bench.py times): the engine's FASTQ has the sha256 of what the unmodified reference
+    wrote with `-j 1` for the same synthetic 4 641 652-bp sequence, profile, seed and coverage (tests/golden/fullsize_c2_sha256.json, made
+    by tests/golden/make_fullsize_hashes.py).  This is the only size at which the jump-ahead master stream (segments of 2^16..2^22 draws)
+    and the deep speculation windows are active.  RSQ_LIVE_ORACLE=1 additionally runs the reference binary on this box (3-4 minutes)."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synthetic
+    want = json.load(open(os.path.join(golden["dir"], "fullsize_c2_sha256.json")))[prof]
+    seq = make_synthetic.gen_reference([want["size"]], want["ref_seed"])[0]
+    ref = rb.Reference.from_memory(["ecoli_sized synthetic"], [seq.encode()])
+    eng = rb.Engine(rb.Profile.load_flat(golden[key]), 0)
+    try:
+        r1, r2, rep = _simulate(eng, ref, seed=want["seed"], coverage=want["coverage"])
+    finally:
+        eng.close()
+    assert rep.pairs == want["pairs"] and [len(r1), len(r2)] == want["bytes"]
+    assert hashlib.sha256(r1).hexdigest() == want["r1"]
+    assert hashlib.sha256(r2).hexdigest() == want["r2"]
+    assert rep.spec_rounds > 0
+    if oracle_optional and os.environ.get("RSQ_LIVE_ORACLE"):
+        fa = os.path.join(workdir, "full_" + prof + ".fa")
+        with open(fa, "w") as f:
+            f.write(">ecoli_sized synthetic\n" + seq + "\n")
+        o1, o2 = run_oracle_sim(oracle_optional, golden["reseq_r" if prof.endswith("r") else "reseq"], fa, want["seed"], want["coverage"], os.path.join(workdir, "full_" + prof))
+        assert open(o1, "rb").read() == r1 and open(o2, "rb").read() == r2
+
+
 def test_full_size_properties(rb, engine, workdir, monkeypatch):
     """BASELINE config 2 size (4.64 Mbp, 30x): determinism, record structure, pairing, pair count near the aim."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
