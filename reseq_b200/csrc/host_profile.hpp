@@ -697,8 +697,9 @@ struct Normalization {
 	std::vector<uint32_t> coverage_groups;
 	uint32_t num_groups = 0;
 	std::vector<double> thresholds;     // [group][len][2]
-	std::vector<double> binom_p0;       // [group][len]   pow(1-(1-thr0), 2)
+	std::vector<double> binom_p0;       // [group][len]   pow(1-(1-thr0), 2 * alleles): Binomial's first term when every allele is possible
 	std::vector<uint64_t> thr_int;      // [group][len]
+	std::vector<double> binom_pow;      // [group][len][2 * alleles + 1]   pow(1-(1-thr0), N) for N possible strands (runs with variants only)
 };
 
 // Smallest raw 64-bit draw x whose canonical value (double(x)*2^-64, clamped) is >= thr; UINT64_MAX with
@@ -717,7 +718,7 @@ inline uint64_t raw_threshold(double thr){
 // Everything of CalculateBiasNormalization after the per-(ref, length) sums are known.
 // sums/max_bias are indexed like `params` (1-thread order: ref id descending, sample length ascending).
 inline bool finish_normalization(Normalization &out, const Profile &p, const std::vector<double> &ref_seq_bias, const Spline &spline_in, const std::vector<BiasParam> &params,
-                                 const std::vector<double> &sums, const std::vector<double> &max_bias, uint64_t total_reads){
+                                 const std::vector<double> &sums, const std::vector<double> &max_bias, uint64_t total_reads, uint32_t num_alleles = 1, bool with_variants = false){
 	Spline spline = spline_in;
 	const uint32_t to = p.insert_lengths.to();
 	out.num_groups = split_coverage_groups(out.coverage_groups, ref_seq_bias);
@@ -753,24 +754,28 @@ inline bool finish_normalization(Normalization &out, const Profile &p, const std
 	out.thresholds.assign(static_cast<size_t>(out.num_groups) * to * 2, 1.0);
 	out.binom_p0.assign(static_cast<size_t>(out.num_groups) * to, 1.0);
 	out.thr_int.assign(static_cast<size_t>(out.num_groups) * to, UINT64_MAX);
+	out.binom_pow.assign(with_variants ? static_cast<size_t>(out.num_groups) * to * (2 * num_alleles + 1) : 0, 1.0);
 	for(uint32_t g = 0; g < out.num_groups; ++g){
 		for(uint32_t len = 0; len < to; ++len){
 			auto &t = thr[g][len];
 			if(0.0 == t[0]){ t[0] = 1.0; t[1] = 1.0; }
 			else{
-				// CalculateNonZeroThreshold(full, max_bias, NumAlleles()=1)
+				// CalculateNonZeroThreshold(full, max_bias, NumAlleles())
 				double max_mean = full * t[0];
-				double max_dispersion = get_dispersion(max_mean, p.dispersion_parameters[0], p.dispersion_parameters[1]) / 1;
-				max_mean /= 1;
+				double max_dispersion = get_dispersion(max_mean, p.dispersion_parameters[0], p.dispersion_parameters[1]) / num_alleles;
+				max_mean /= num_alleles;
 				t[0] = std::pow(max_dispersion / (max_dispersion + max_mean), max_dispersion);
-				t[1] = std::pow(t[0], 2 * 1);
+				t[1] = std::pow(t[0], 2 * num_alleles);
 			}
 			const size_t i = static_cast<size_t>(g) * to + len;
 			out.thresholds[2 * i] = t[0];
 			out.thresholds[2 * i + 1] = t[1];
 			const double pp = 1 - t[0];                // DrawNumberNonZeroStrands: p = 1 - zero_probability
-			out.binom_p0[i] = std::pow(1 - pp, 2);     // Binomial: pow(1-p, N) with N = 2*#alleles
+			out.binom_p0[i] = std::pow(1 - pp, static_cast<uint16_t>(2 * num_alleles));     // Binomial: pow(1-p, N) with N = 2*#alleles (uintAlleleId)
 			out.thr_int[i] = raw_threshold(t[1]);
+			if(with_variants){   // fewer strands are possible where alleles delete the start base or do not carry the insertion a fragment starts in
+				for(uint32_t n = 0; n <= 2 * num_alleles; ++n){ out.binom_pow[i * (2 * num_alleles + 1) + n] = std::pow(1 - pp, static_cast<uint16_t>(n)); }
+			}
 		}
 	}
 	out.bias_normalization = full;

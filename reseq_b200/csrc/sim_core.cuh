@@ -13,6 +13,7 @@
 // Variants (VCF) and methylation are not handled by this revision; the host refuses such runs.
 #pragma once
 #include "core.cuh"
+#include "variant_core.cuh"
 
 namespace rsq {
 
@@ -22,6 +23,8 @@ struct BlockDesc {
 	uint32_t block_id;   // id printed in the read names (forward SimBlock::id_)
 	int32_t first_meth;  // SimBlock::first_methylation_id_
 	uint64_t seed;
+	uint32_t first_var;  // SimBlock::first_variant_id_ (counted inside the sequence)
+	uint32_t pad;
 };
 
 struct AdapterSet {            // per template segment
@@ -89,7 +92,12 @@ struct SimCtx {
 	const uint32_t *meth_off;          // [n_seqs+1] first region of each sequence
 	const uint32_t *meth_start;        // region.first
 	const uint32_t *meth_end;          // region.second
-	const double *meth_rate;           // 1 - methylation = C->T conversion probability
+	const double *meth_rate;           // 1 - methylation = C->T conversion probability (allele 0, or the only column)
+	uint32_t meth_alleles;             // Reference::Unmethylation(seq, allele): columns of meth_rate, 1 or Reference::NumAlleles() (sequences with one column repeat it)
+	uint32_t meth_rate_stride;         // doubles between the columns of two alleles
+	// --- variants (Reference::variants_, SimBlock::err_variants_) ---
+	VarCtx var;
+	const double *binom_pow;           // [group][insert_to][2 * num_alleles + 1]: pow(thr0, N) of Binomial for N possible strands (host libm); null without variants
 };
 
 enum : uint32_t { kErrCigarOverflow = 1, kErrCountRunaway = 2, kErrArenaFull = 4, kErrOrgOverflow = 8, kErrRecordTooLong = 16, kErrReferenceOutOfRange = 32 };
@@ -769,15 +777,42 @@ RSQ_HD uint32_t dominant_before(const uint8_t *seq, uint32_t L, bool reverse, ui
 // raw draw k (0: dominant error, 1: error rate) of chain coordinate p.  Reverse-strand and adapter chains own a
 // contiguous run of the master stream (2 draws per base); the forward strand is interleaved with one block
 // seed per 1000 bases (Simulator::CreateBlock draws the seed, then the block's 2*1000 values).
-RSQ_HD uint64_t chain_raw(const uint64_t *raw, bool seed_interleaved, uint32_t p, uint32_t k){
+// With variants every SimBlock is followed by the draws of its variants' replacement bases (SetSystematicErrorVariantsForward / Reverse, 2 per
+// base), so the blocks' places in the stream come from a table: blk_off[b] = index of block b's seed (forward) / of its first position draw (reverse).
+RSQ_HD uint64_t chain_raw(const uint64_t *raw, bool seed_interleaved, uint32_t p, uint32_t k, const uint64_t *blk_off = nullptr, uint32_t L = 0, bool reverse = false){
+	if(blk_off){
+		if(reverse){
+			const uint32_t f = L - 1u - p, b = f / 1000u;
+			const uint64_t e = 1000ull * (b + 1ull) < L ? 1000ull * (b + 1ull) : L;
+			return raw[blk_off[b] + 2ull * (e - 1ull - f) + k];
+		}
+		const uint32_t b = p / 1000u;
+		return raw[blk_off[b] + 1ull + 2ull * (p - 1000u * b) + k];
+	}
 	const size_t i = seed_interleaved ? static_cast<size_t>(p / 1000u) * 2001u + 1u + 2u * (p % 1000u) + k : 2u * static_cast<size_t>(p) + k;
 	return raw[i];
+}
+// CoverageStats::UpdateDistances (CoverageStats.cpp:379-396)
+RSQ_HD void update_distances(SysState &st, uint32_t error_rate, uint32_t reset_distance){
+	if(st.distance){
+		if(st.start_rate < error_rate){ st.distance = 0; st.start_rate = error_rate; }
+		else if(++st.distance >= reset_distance){ st.distance = 0; st.start_rate = 0; }
+	}
+	else if(error_rate){ st.distance = 1; st.start_rate = error_rate; }
+}
+// (distance_to_start_of_error_region_, start_error_rate_) in front of SimBlock b of a strand - what CreateBlock / CreateUnit copy into
+// tmp_distance_to_start_of_error_region / tmp_start_error_rate for the block's variants (Simulator.cpp:990-993, 1236-1239)
+RSQ_HD bool chain_block_start(uint32_t L, bool reverse, uint32_t p, uint32_t &block){
+	const uint32_t f = reverse ? L - 1u - p : p;
+	block = f / 1000u;
+	return reverse ? ((f + 1u) % 1000u == 0u || f + 1u == L) : (f % 1000u == 0u);
 }
 
 template<class G>
 RSQ_HD SysState sys_error_chain(const G &g, const Tables &tab, double *prob, const uint8_t *seq, uint32_t L, bool reverse,
                                 uint32_t begin, uint32_t end, SysState st, uint32_t carried_dom, uint32_t sys_gc_range, uint32_t reset_distance,
-                                const uint64_t *raw, bool seed_interleaved, uint8_t *out /* indexed by chain coordinate; null: warm-up only */){
+                                const uint64_t *raw, bool seed_interleaved, uint8_t *out /* indexed by chain coordinate; null: warm-up only */,
+                                const uint64_t *blk_off = nullptr, uint32_t *bstate = nullptr){
 	// GC window state before `begin` (Simulator::UpdateGC): previous min(begin, range) bases
 	uint32_t gc_bases = begin < sys_gc_range ? begin : sys_gc_range;
 	uint32_t gc = 0;
@@ -794,8 +829,12 @@ RSQ_HD SysState sys_error_chain(const G &g, const Tables &tab, double *prob, con
 		const uint32_t dom_base = dominant_from_window(hist, nwin, carried_dom);
 		const uint32_t gc_percent = gc_bases ? percent_u16(gc, gc_bases) : 50u;
 		const uint32_t dist = (st.distance + 9) / 10;
-		const double u1 = canonical(chain_raw(raw, seed_interleaved, p, 0));
-		const double u2 = canonical(chain_raw(raw, seed_interleaved, p, 1));
+		if(bstate && out){
+			uint32_t blk;
+			if(chain_block_start(L, reverse, p, blk) && g.lane() == 0){ bstate[blk] = st.distance | (st.start_rate << 24); }
+		}
+		const double u1 = canonical(chain_raw(raw, seed_interleaved, p, 0, blk_off, L, reverse));
+		const double u2 = canonical(chain_raw(raw, seed_interleaved, p, 1, blk_off, L, reverse));
 		uint32_t dom_error = draw(g, tab, tab.dom_error(ref_base, last_base, dom_base), dist, gc_percent, st.start_rate, 0, u1, prob, zero);
 		if(zero){ dom_error = 4; }
 		uint32_t error_rate = draw(g, tab, tab.error_rate(ref_base, dom_error), dist, gc_percent, st.start_rate, 0, u2, prob, zero);
@@ -808,12 +847,7 @@ RSQ_HD SysState sys_error_chain(const G &g, const Tables &tab, double *prob, con
 		last_base = ref_base;
 		hist = ((hist << 2) | ref_base) & 0x3ffu;
 		if(nwin < 5){ ++nwin; }
-		// CoverageStats::UpdateDistances (CoverageStats.cpp:379-396)
-		if(st.distance){
-			if(st.start_rate < error_rate){ st.distance = 0; st.start_rate = error_rate; }
-			else if(++st.distance >= reset_distance){ st.distance = 0; st.start_rate = 0; }
-		}
-		else if(error_rate){ st.distance = 1; st.start_rate = error_rate; }
+		update_distances(st, error_rate, reset_distance);
 		// UpdateGC
 		if(ref_base == 1 || ref_base == 2){ ++gc; }
 		if(gc_bases < sys_gc_range){ ++gc_bases; }
@@ -823,6 +857,66 @@ RSQ_HD SysState sys_error_chain(const G &g, const Tables &tab, double *prob, con
 		}
 	}
 	return st;
+}
+
+
+// Simulator::SetSystematicErrorVariantsForward / Reverse (Simulator.cpp:1011-1147, 769-909) for the variants of ONE SimBlock of one strand:
+// walks the block's error rates from the state in front of the block (variants cannot start an error region, and the state stands still while a
+// variant's bases are drawn), takes the GC content of the sys_gc_range bases in front of the variant (the variants' own bases do not count),
+// and draws (dominant error, rate) per replacement base with the context the host prepared (variant_syserr.hpp: base | last base << 2 |
+// dominant base << 5).  raw: the block's variant draws in the master stream, two per base.
+struct VarDrawCtx {
+	const uint8_t *ctx;          // context bytes of this strand (VariantSysContext::fwd / rev)
+	uint8_t *errs;               // VarCtx::errs_fwd / errs_rev (out)
+	const uint8_t *sys;          // sys_fwd / sys_rev of the sequence
+	const uint32_t *gcp;         // G/C prefix counts of the sequence
+	const uint32_t *block_first; // VarCtx::block_first of the sequence
+	VariantView v;
+	uint32_t L, reverse, sys_gc_range, reset_distance;
+};
+template<class G>
+RSQ_HD void draw_variant_errors_block(const G &g, const Tables &tab, double *prob, const VarDrawCtx &c, uint32_t block, SysState st, const uint64_t *raw){
+	SysWalkCtx w{}; w.sys = c.sys; w.errs = nullptr; w.block_first = c.block_first; w.v = c.v; w.L = c.L; w.reverse = c.reverse;
+	const uint32_t n_vars = sysw_n_vars(w, block);
+	uint32_t cursor = 0;
+	uint64_t r = 0;
+	bool zero;
+	for(uint32_t k = 0; k < n_vars; ++k){
+		const uint32_t var = sysw_var(w, block, k);
+		const uint32_t vp = sysw_var_position(w, block, var);
+		for(; cursor < vp; ++cursor){
+			SysWalk at{block, cursor, 0, 0};
+			update_distances(st, sysw_entry(w, at)[1], c.reset_distance);
+		}
+		const uint32_t P = c.v.position[var];
+		uint32_t gc_bases, gc;
+		if(c.reverse){
+			const uint32_t rev_pos = c.L - P - 1u;
+			gc_bases = rev_pos < c.sys_gc_range ? rev_pos : c.sys_gc_range;
+			gc = c.gcp[P + 1u + gc_bases] - c.gcp[P + 1u];
+		}
+		else{
+			gc_bases = P < c.sys_gc_range ? P : c.sys_gc_range;
+			gc = c.gcp[P] - c.gcp[P - gc_bases];
+		}
+		const uint32_t gc_percent = gc_bases ? percent_u16(gc, gc_bases) : 50u;
+		const uint32_t dist = (st.distance + 9) / 10;
+		const uint32_t len = c.v.length(var);
+		for(uint32_t i = 0; i < len; ++i){
+			const uint32_t cb = c.ctx[c.v.bases_off[var] + i];
+			const uint32_t base = cb & 3u, last_base = (cb >> 2) & 7u, dom_base = (cb >> 5) & 3u;
+			const double u1 = canonical(raw[r]), u2 = canonical(raw[r + 1]);
+			r += 2;
+			uint32_t dom_error = draw(g, tab, tab.dom_error(base, last_base, dom_base), dist, gc_percent, st.start_rate, 0, u1, prob, zero);
+			if(zero){ dom_error = 4; }
+			uint32_t error_rate = draw(g, tab, tab.error_rate(base, dom_error), dist, gc_percent, st.start_rate, 0, u2, prob, zero);
+			if(zero){ error_rate = 0; }
+			if(g.lane() == 0){
+				c.errs[2ull * (c.v.bases_off[var] + i)] = static_cast<uint8_t>(dom_error);
+				c.errs[2ull * (c.v.bases_off[var] + i) + 1] = static_cast<uint8_t>(error_rate & 0xffu);
+			}
+		}
+	}
 }
 
 }  // namespace rsq

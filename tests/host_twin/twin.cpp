@@ -3,7 +3,7 @@
 // a GPU.  The shipped library never contains or calls this; the GPU tests check the very same templates
 // instantiated for 32-lane warps.
 //
-//   twin <stage.flat from oracle/_ref/dump_tables sim> <seed> <out_prefix> [max_blocks] [methylation.bed]
+//   twin <stage.flat from oracle/_ref/dump_tables sim> <seed> <out_prefix> [max_blocks] [methylation.bed or -] [variants.vcf]
 // Recomputes: ReplaceN'd reference (taken from the dump), surroundings bias + normalisation + thresholds,
 // master stream -> adapter / reverse / forward systematic errors + block seeds, then simulates every block
 // and writes <out_prefix>_1.fq / _2.fq.  Prints mismatches against the dump's stage values.
@@ -16,6 +16,7 @@
 #include "../../reseq_b200/csrc/sim_core.cuh"
 #include "../../reseq_b200/csrc/spec_core.cuh"
 #include "../../reseq_b200/csrc/bias_core.cuh"
+#include "../../reseq_b200/csrc/variant_syserr.hpp"
 
 using namespace rsq;
 
@@ -62,7 +63,8 @@ int main(int argc, char **argv){
 	const uint64_t seed = strtoull(argv[2], nullptr, 10);
 	const std::string prefix = argv[3];
 	const size_t max_blocks = argc > 4 ? strtoull(argv[4], nullptr, 10) : static_cast<size_t>(-1);
-	const char *bed = argc > 5 ? argv[5] : nullptr;
+	const char *bed = (argc > 5 && std::string(argv[5]) != "-") ? argv[5] : nullptr;
+	const char *vcf = argc > 6 ? argv[6] : nullptr;
 	Profile p; p.from_flat(f);
 	int bad = 0;
 
@@ -74,7 +76,10 @@ int main(int argc, char **argv){
 		const auto &idr = f.get("sim.ref_id." + std::to_string(s));
 		g.ids.emplace_back(reinterpret_cast<const char *>(idr.bytes.data()), idr.count);
 	}
+	if(vcf){ g.read_variants(vcf); }
 	if(bed){ g.read_methylation(bed); }
+	const uint32_t num_alleles = g.variants.num_alleles;
+	FlatVariants flat_vars; VariantSysContext var_ctx; std::vector<uint8_t> errs_fwd, errs_rev; std::vector<uint32_t> block_first, block_first_off;
 	DeviceLikeStorage st;
 	std::vector<uint32_t> moff{0}, mstart, mend; std::vector<double> mrate;
 	std::vector<std::vector<double>> cp_keep; cp_keep.reserve(4096);
@@ -189,7 +194,7 @@ int main(int argc, char **argv){
 		maxb[i] = mx;
 	}
 	Normalization norm;
-	finish_normalization(norm, p, p.ref_seq_bias, spline, params, sums, maxb, total_pairs);
+	finish_normalization(norm, p, p.ref_seq_bias, spline, params, sums, maxb, total_pairs, num_alleles, vcf != nullptr);
 	{
 		const double ref_norm = f.scalar_d("sim.bias_normalization");
 		if(ref_norm != norm.bias_normalization){ printf("MISMATCH bias_normalization: oracle %a twin %a\n", ref_norm, norm.bias_normalization); ++bad; }
@@ -202,6 +207,29 @@ int main(int argc, char **argv){
 	}
 	c.bias_normalization = norm.bias_normalization; c.coverage_group = norm.coverage_groups.data();
 	c.thr = norm.thresholds.data(); c.thr_int = norm.thr_int.data(); c.binom_p0 = norm.binom_p0.data();
+	if(vcf){
+		// Reference::variants_ flattened + SimBlock::first_variant_id_ of every block + the host half of SetSystematicErrorVariants*
+		flat_vars = g.variants.flatten();
+		flat_vars.position.push_back(0); flat_vars.allele_lo.push_back(0); flat_vars.allele_hi.push_back(0); flat_vars.bases.push_back(0);
+		var_ctx = variant_sys_context(g.seqs, g.variants, flat_vars);
+		errs_fwd.assign(2 * flat_vars.bases.size() + 2, 0); errs_rev.assign(2 * flat_vars.bases.size() + 2, 0);
+		for(size_t s = 0; s < g.seqs.size(); ++s){
+			block_first_off.push_back(block_first.size());
+			const uint32_t nb = (g.seqs[s].size() + 999) / 1000;
+			const auto &vars = g.variants.variants[s];
+			uint32_t v = 0;
+			for(uint32_t b = 0; b <= nb; ++b){
+				while(v < vars.size() && vars[v].position < 1000ull * b){ ++v; }
+				block_first.push_back(b == nb ? vars.size() : v);
+			}
+		}
+		c.var.loaded = 1; c.var.num_alleles = num_alleles;
+		c.var.seq_first = flat_vars.seq_first.data(); c.var.position = flat_vars.position.data(); c.var.bases_off = flat_vars.bases_off.data(); c.var.bases = flat_vars.bases.data();
+		c.var.allele_lo = flat_vars.allele_lo.data(); c.var.allele_hi = flat_vars.allele_hi.data();
+		c.var.errs_fwd = errs_fwd.data(); c.var.errs_rev = errs_rev.data(); c.var.block_first = block_first.data(); c.var.block_first_off = block_first_off.data();
+		for(int b = 0; b < 3; ++b){ c.var.sur_tab[b] = p.fragment_surroundings_bias[b].data(); }
+		c.binom_pow = norm.binom_pow.data();
+	}
 
 	// ---- master stream ----
 	const uint32_t sys_gc_range = f.scalar_i("sim.sys_gc_range");
@@ -234,9 +262,42 @@ int main(int argc, char **argv){
 		const uint32_t L = g.seqs[s].size();
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
+		const uint8_t *seq = g.seqs[s].data();
+		if(vcf){
+			// master stream of a unit with variants: nb seeds of the reverse blocks; per reverse block (last one first) 2 draws per position, then
+			// 2 per replacement base of its variants; per forward block its seed, 2 per position, 2 per replacement base
+			const uint32_t *bf = block_first.data() + block_first_off[s];
+			const uint32_t vf = flat_vars.seq_first[s];
+			std::vector<uint64_t> rev_off(nb), fwd_off(nb), vb(nb);
+			for(uint32_t b = 0; b < nb; ++b){ vb[b] = flat_vars.bases_off[vf + bf[b + 1]] - flat_vars.bases_off[vf + bf[b]]; }
+			uint64_t at = nb;
+			for(uint32_t b = nb; b--; ){ rev_off[b] = at; at += 2ull * (std::min<uint64_t>(1000ull * (b + 1), L) - 1000ull * b) + 2 * vb[b]; }
+			for(uint32_t b = 0; b < nb; ++b){ fwd_off[b] = at; at += 1 + 2ull * (std::min<uint64_t>(1000ull * (b + 1), L) - 1000ull * b) + 2 * vb[b]; }
+			std::vector<uint64_t> raw(at);
+			for(auto &r : raw){ r = master(); }
+			std::vector<uint32_t> bstate_rev(nb, 0), bstate_fwd(nb, 0);
+			sys_error_chain(lane, c.tab, prob.data(), seq, L, true, 0, L, SysState{0, 0}, carried, sys_gc_range, p.reset_distance, raw.data(), false, st.sys_rev.data() + 2 * st.seq_off[s], rev_off.data(), bstate_rev.data());
+			carried = dominant_before(seq, L, true, L, carried);
+			sys_error_chain(lane, c.tab, prob.data(), seq, L, false, 0, L, SysState{0, 0}, carried, sys_gc_range, p.reset_distance, raw.data(), true, st.sys_fwd.data() + 2 * st.seq_off[s], fwd_off.data(), bstate_fwd.data());
+			carried = dominant_before(seq, L, false, L, carried);
+			for(int strand = 0; strand < 2; ++strand){
+				VarDrawCtx dc{}; dc.ctx = strand ? var_ctx.rev.data() : var_ctx.fwd.data(); dc.errs = strand ? errs_rev.data() : errs_fwd.data();
+				dc.sys = (strand ? st.sys_rev.data() : st.sys_fwd.data()) + 2 * st.seq_off[s]; dc.gcp = st.gc_prefix.data() + st.seq_off[s] + s; dc.block_first = bf;
+				dc.v = c.var.view(s); dc.L = L; dc.reverse = strand; dc.sys_gc_range = sys_gc_range; dc.reset_distance = p.reset_distance;
+				for(uint32_t b = 0; b < nb; ++b){
+					const uint32_t bs = (strand ? bstate_rev : bstate_fwd)[b];
+					const uint64_t size = std::min<uint64_t>(1000ull * (b + 1), L) - 1000ull * b;
+					draw_variant_errors_block(lane, c.tab, prob.data(), dc, b, SysState{bs & 0xffffffu, bs >> 24}, raw.data() + (strand ? rev_off[b] + 2 * size : fwd_off[b] + 1 + 2 * size));
+				}
+			}
+			for(uint32_t b = 0; b < nb; ++b){
+				BlockDesc d{}; d.ref_id = s; d.start_pos = b * 1000; d.block_id = next_block_id++; d.first_meth = g.first_methylation_id(s, b * 1000); d.seed = raw[fwd_off[b]]; d.first_var = bf[b];
+				blocks.push_back(d);
+			}
+			continue;
+		}
 		std::vector<uint64_t> raw(2 * static_cast<size_t>(nb) + 4 * static_cast<size_t>(L));
 		for(auto &r : raw){ r = master(); }
-		const uint8_t *seq = g.seqs[s].data();
 		SysState end_rev = sys_error_chain(lane, c.tab, prob.data(), seq, L, true, 0, L, SysState{0, 0}, carried, sys_gc_range, p.reset_distance, raw.data() + nb, false, st.sys_rev.data() + 2 * st.seq_off[s]);
 		(void)end_rev;
 		carried = dominant_before(seq, L, true, L, carried);
@@ -274,6 +335,39 @@ int main(int argc, char **argv){
 			}
 		}
 		if(rb || ri != rr.count){ printf("MISMATCH sys_rev: %zu bytes differ (%zu vs %" PRIu64 ")\n", rb, ri, rr.count); ++bad; }
+		if(vcf && f.has("sim.err_variants")){
+			// SimBlock::err_variants_ of every block as the reference built them: position_, allele bits and the drawn var_errors_
+			const auto &rec = f.get("sim.err_variants"); const auto &er = f.get("sim.err_variant_errors");
+			const int64_t *r = rec.as<int64_t>(); const uint8_t *ev = er.as<uint8_t>();
+			size_t eoff = 0, vbad = 0, seen = 0;
+			std::vector<uint32_t> next_in_block(2 * blocks.size(), 0);
+			for(size_t i = 0; i + 5 < rec.count; i += 6, ++seen){
+				const size_t bi = r[i]; const int strand = r[i + 1];
+				const BlockDesc &bd = blocks.at(bi);
+				SysWalkCtx w{}; w.block_first = block_first.data() + block_first_off[bd.ref_id]; w.v = c.var.view(bd.ref_id); w.L = st.seq_len[bd.ref_id]; w.reverse = strand;
+				const uint32_t b = bd.start_pos / 1000, k = next_in_block[2 * bi + strand]++;
+				bool ok = k < sysw_n_vars(w, b);
+				if(ok){
+					const uint32_t var = sysw_var(w, b, k);
+					ok = sysw_var_position(w, b, var) == static_cast<uint32_t>(r[i + 2]) && w.v.allele_lo[var] == static_cast<uint64_t>(r[i + 3]) && w.v.allele_hi[var] == static_cast<uint64_t>(r[i + 4]) && w.v.length(var) == static_cast<uint32_t>(r[i + 5]);
+					if(ok){ ok = 0 == memcmp(ev + eoff, (strand ? errs_rev.data() : errs_fwd.data()) + 2 * static_cast<size_t>(w.v.bases_off[var]), 2 * r[i + 5]); }
+				}
+				if(!ok){ if(vbad < 5){ printf("  err_variant diff: block %zu strand %d variant %u (position_ %" PRId64 ")\n", bi, strand, k, r[i + 2]); } ++vbad; }
+				eoff += 2 * r[i + 5];
+			}
+			for(size_t bi = 0; bi < blocks.size(); ++bi){
+				SysWalkCtx w{}; w.block_first = block_first.data() + block_first_off[blocks[bi].ref_id];
+				const uint32_t b = blocks[bi].start_pos / 1000;
+				if(next_in_block[2 * bi] != sysw_n_vars(w, b) || next_in_block[2 * bi + 1] != sysw_n_vars(w, b)){ if(vbad < 5){ printf("  err_variant count differs in block %zu\n", bi); } ++vbad; }
+			}
+			const auto &ff = f.get("sim.block_first_variant_fwd"); const auto &fr = f.get("sim.block_first_variant_rev");
+			for(size_t bi = 0; bi < blocks.size() && bi < ff.count; ++bi){
+				const uint32_t *bf = block_first.data() + block_first_off[blocks[bi].ref_id]; const uint32_t b = blocks[bi].start_pos / 1000;
+				if(ff.as<int64_t>()[bi] != static_cast<int64_t>(bf[b]) || fr.as<int64_t>()[bi] != static_cast<int64_t>(bf[b + 1]) - 1){ if(vbad < 5){ printf("  first_variant_id_ differs in block %zu: %" PRId64 " %" PRId64 " vs %u %d\n", bi, ff.as<int64_t>()[bi], fr.as<int64_t>()[bi], bf[b], static_cast<int>(bf[b + 1]) - 1); } ++vbad; }
+			}
+			if(vbad){ printf("MISMATCH err_variants: %zu of %zu differ\n", vbad, seen); ++bad; }
+			else{ printf("err_variants: %zu variants x 2 strands equal the reference's\n", seen / 2); }
+		}
 	}
 
 	// ---- simulate ----
