@@ -194,10 +194,12 @@ template<class G> RSQ_HD void cigar_append(const G &g, const Scratch &s, ReadSta
 	par.cigar_len = put_char(g, s.cigar, par.cigar_len, kCigarCap, op);
 }
 
-// Simulator::FillReadPart without variants.  `org_len` bases are staged in s.org / s.sdom / s.srate.
+// Simulator::FillReadPart.  `org_len` bases are staged in s.org; their systematic errors in s.sdom / s.srate, or - for a read that touches
+// variants - behind the cursor `w` (GetSysErrorFromBlock over the block's SysErrorVariants).
 template<class G>
 RSQ_HD void fill_read_part(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, ReadState &par,
-                           uint32_t seg, uint32_t tile, uint32_t org_pos, uint32_t org_len, char base_cigar_element){
+                           uint32_t seg, uint32_t tile, uint32_t org_pos, uint32_t org_len, char base_cigar_element,
+                           const SysWalkCtx *wc = nullptr, SysWalk *w = nullptr, uint32_t allele = 0){
 	uint32_t cigar_element_length = 0;
 	char cigar_element = base_cigar_element;
 	bool zero;
@@ -208,8 +210,9 @@ RSQ_HD void fill_read_part(const G &g, const SimCtx &c, const Scratch &s, Mt &mt
 		if(zero){ indel = 0; }
 
 		if(indel == 0){
-			const uint32_t dom_error = s.sdom[org_pos];
-			par.error_rate = s.srate[org_pos];
+			uint32_t dom_error;
+			if(w){ const uint32_t e = sysw_next(*wc, *w, allele); dom_error = e & 0xffu; par.error_rate = e >> 8; }
+			else{ dom_error = s.sdom[org_pos]; par.error_rate = s.srate[org_pos]; }
 
 			u = mt_uniform(g, mt);
 			const uint32_t qtab = c.tab.quality(seg, tile, ref_base);
@@ -243,7 +246,7 @@ RSQ_HD void fill_read_part(const G &g, const SimCtx &c, const Scratch &s, Mt &mt
 			++org_pos;
 		}
 		else if(indel == 1){
-			par.error_rate = s.srate[org_pos];
+			par.error_rate = w ? sysw_deletion(*wc, *w) : s.srate[org_pos];
 			if('D' == cigar_element){
 				++cigar_element_length;
 				++par.indel_pos;
@@ -326,7 +329,8 @@ template<class G> RSQ_HD uint32_t stage_adapter(const G &g, const SimCtx &c, con
 // Simulator::FillRead.  On entry s.org/sdom/srate hold `org_len` bases of the fragment as this read sees it.
 template<class G>
 RSQ_HD void fill_read(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, ReadState &par,
-                      uint32_t seg, uint32_t tile, uint32_t fragment_length, uint32_t org_len){
+                      uint32_t seg, uint32_t tile, uint32_t fragment_length, uint32_t org_len,
+                      const SysWalkCtx *wc = nullptr, const SysWalk *w_start = nullptr, uint32_t allele = 0){
 	par.read_pos = 0; par.previous_indel_type = 0; par.indel_pos = 0; par.base_call = 5; par.gc_seq = 0;
 	par.qual = 1; par.error_rate = 0; par.num_errors = 0; par.cigar_len = 0; par.seq_qual = 0;
 	par.read_length = draw_read_length(g, c, mt, seg, fragment_length);
@@ -340,10 +344,14 @@ RSQ_HD void fill_read(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, Rea
 		for(uint32_t i = g.lane(); i < seq_length; i += G::kSize){
 			const uint32_t b = s.org[i];
 			gc += (b == 1 || b == 2) ? 1u : 0u;
-			err += s.srate[i];
+			if(!w_start){ err += s.srate[i]; }
 		}
 		gc = g.reduce_add(gc);
 		err = g.reduce_add(err);
+		if(w_start){   // the cursor's own walk over the first seq_length bases (Simulator.cpp:483-500)
+			SysWalk pre = *w_start;
+			for(uint32_t i = 0; i < seq_length; ++i){ err += sysw_next(*wc, pre, allele) >> 8; }
+		}
 		par.gc_seq = percent_u16(gc, seq_length);
 		mean_error_rate = divide_u32(err, seq_length);
 	}
@@ -371,7 +379,11 @@ RSQ_HD void fill_read(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, Rea
 		par.seq_qual = sq & 0xffu;
 	}
 
-	fill_read_part(g, c, s, mt, par, seg, tile, 0, org_len, 'M');
+	{
+		SysWalk w{};
+		if(w_start){ w = *w_start; }
+		fill_read_part(g, c, s, mt, par, seg, tile, 0, org_len, 'M', wc, w_start ? &w : nullptr, allele);
+	}
 
 	if(par.read_pos < par.read_length){
 		if(0 == adapter_id){
@@ -460,15 +472,91 @@ RSQ_HD uint32_t fragment_counts(const SimCtx &c, uint32_t ref_id, uint32_t fragm
 	return count;
 }
 
+// GetFragmentCounts with Reference::NumAlleles() alleles (runs with variants): mean and dispersion are divided by the allele count
+RSQ_HD uint32_t fragment_counts_alleles(const SimCtx &c, uint32_t ref_id, uint32_t fragment_length, uint32_t gc, double sur_start, double sur_end,
+                                        double probability_chosen, uint32_t alleles, bool &runaway){
+	double bias = mul_rn(c.ref_seq_bias[ref_id], c.il_bias[fragment_length]);
+	bias = mul_rn(bias, c.gc_bias[gc]);
+	bias = mul_rn(bias, sur_start);
+	bias = mul_rn(bias, sur_end);
+	if(!(0.0 < bias)){ return 0; }
+	return allele_fragment_counts(mul_rn(bias, c.bias_normalization), c.disp_a, c.disp_b, alleles, probability_chosen, runaway);
+}
+
+// One chosen (allele, strand) of a hit in a run with variants (SimulateFromGivenBlock, Simulator.cpp:2311-2330): end position, GC and
+// surroundings of the allele's fragment, then the count draw.  Hits with no variant of any allele within reach of the fragment and its
+// surroundings take the reference's own per-position arrays; the others are evaluated on the allele's sequence (allele_hit).
+struct VarEval {
+	uint32_t allele, end_position, counts, slow;
+	int32_t end_var; uint32_t end_var_pos;       // VariantBiasVarModifiers::EndVariant (slow hits)
+};
+// uniform(): the next ZeroToOne of the block's stream.  Returns false when the fragment does not end inside the sequence (no draw is consumed).
+template<class Uniform>
+RSQ_HD bool eval_allele_hit(const SimCtx &c, const VariantView &v, uint32_t ref_id, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t fl,
+                            uint32_t allele, double thr0, Uniform &&uniform, VarEval &e, bool &runaway){
+	const uint32_t L = c.seq_len[ref_id];
+	const uint64_t off = c.seq_off[ref_id];
+	const uint32_t *gcp = c.gc_prefix + off + ref_id;
+	e.allele = allele; e.counts = 0; e.end_var = -1; e.end_var_pos = 0;
+	const uint32_t lo = pos >= 32u ? pos - 32u : 0u;
+	const uint32_t idx = var_lower_bound(v, lo);
+	e.slow = (start_variant_pos || (idx < v.n && v.position[idx] <= pos + fl + 32u)) ? 1u : 0u;
+	uint32_t gc_perc; double sur_start, sur_end;
+	if(e.slow){
+		AlleleHit h;
+		allele_hit(v, gcp, L, allele, pos, first_var, start_variant_pos, fl, h);
+		if(!h.valid){ return false; }
+		e.end_position = h.end_position; e.end_var = h.end_var; e.end_var_pos = h.end_var_pos;
+		gc_perc = h.gc_percent;
+		uint32_t code[3];
+		allele_start_surrounding(v, c.ref + off, L, allele, pos, first_var, start_variant_pos, code);
+		sur_start = surrounding_bias(c.var.sur_tab[0], c.var.sur_tab[1], c.var.sur_tab[2], code);
+		allele_end_surrounding(v, c.ref + off, L, allele, h.end, code);
+		sur_end = surrounding_bias(c.var.sur_tab[0], c.var.sur_tab[1], c.var.sur_tab[2], code);
+	}
+	else{
+		e.end_position = pos + fl;
+		if(!(e.end_position < L)){ return false; }
+		gc_perc = percent_u32(gcp[e.end_position] - gcp[pos], fl);
+		sur_start = c.sur_start[off + pos]; sur_end = c.sur_end[off + e.end_position - 1];
+	}
+	const double rv = uniform();
+	const double adjusted_random = add_rn(thr0, mul_rn(rv, sub_rn(1.0, thr0)));
+	e.counts = fragment_counts_alleles(c, ref_id, fl, gc_perc, sur_start, sur_end, adjusted_random, c.var.num_alleles, runaway);
+	return true;
+}
+// GetOrgSeq with variants (Simulator.cpp:1909-1914): the two ends of the allele's fragment, spliced.  Lane-uniform; lane 0 stores.
+template<class G>
+RSQ_HD void splice_fragment_ends(const G &g, const SimCtx &c, const VariantView &v, uint32_t ref_id, uint32_t strand, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos,
+                                 uint32_t fl, const VarEval &e, uint8_t *frag_fwd, uint8_t *frag_rev){
+	g.sync();
+	if(g.lane() == 0){
+		const uint8_t *seq = c.ref + c.seq_off[ref_id];
+		uint32_t n = c.read_len_to[strand ? 1 : 0] + c.max_len_deletion;   // forward end: the read of segment `strand`
+		if(fl < n){ n = fl; }
+		if(n > c.max_org_len){ n = c.max_org_len; }
+		splice_reference(frag_fwd, seq, v, pos, n, false, static_cast<int32_t>(first_var), start_variant_pos, e.allele);
+		n = c.read_len_to[strand ? 0 : 1] + c.max_len_deletion;
+		if(fl < n){ n = fl; }
+		if(n > c.max_org_len){ n = c.max_org_len; }
+		splice_reference(frag_rev, seq, v, e.end_position, n, true, e.end_var, e.end_var_pos, e.allele);
+	}
+	g.sync();
+}
+
 // Simulator::CreateReadId
 template<class G>
 RSQ_HD int format_read_id(const G &g, const SimCtx &c, const Scratch &s, uint32_t block_number, uint64_t read_number,
-                          uint32_t start_pos, uint32_t end_pos, uint32_t tile, uint32_t ref_id, const ReadState &par){
+                          uint32_t start_pos, uint32_t end_pos, uint32_t tile, uint32_t ref_id, const ReadState &par, uint32_t allele = 0){
 	int n = 0;
 	n = put_str(g, s.id, n, kIdCap, c.base_id, c.base_id_len);
 	n = put_uint(g, s.id, n, kIdCap, block_number);
 	n = put_char(g, s.id, n, kIdCap, '_');
 	n = put_uint(g, s.id, n, kIdCap, read_number);
+	if(start_pos && 1 < c.var.num_alleles && c.var.loaded){   // Simulator.cpp:612
+		n = put_str(g, s.id, n, kIdCap, "_allele", 7);
+		n = put_uint(g, s.id, n, kIdCap, allele);
+	}
 	n = put_char(g, s.id, n, kIdCap, ':');
 	n = put_uint(g, s.id, n, kIdCap, start_pos);
 	n = put_char(g, s.id, n, kIdCap, ':');
@@ -528,10 +616,11 @@ RSQ_HD uint32_t stage_fragment_read(const G &g, const SimCtx &c, const Scratch &
 
 // Simulator::CreateReads for `counts` copies of one fragment (start_block != NULL case), or for the
 // adapter-only pairs (fragment_length == 0).
+struct VarRead { uint32_t allele, slow, first_var, start_variant_pos; int32_t end_var; uint32_t end_var_pos; uint32_t start_block; };   // a hit's allele + StartVariant / EndVariant
 template<class G, class Sink>
 RSQ_HD void create_reads(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, Sink &sink, uint32_t counts, bool strand,
                          uint32_t ref_id, uint32_t fragment_length, uint64_t &read_number, uint32_t block_id,
-                         uint32_t start_position_forward, uint32_t end_position_forward, bool converted = false){
+                         uint32_t start_position_forward, uint32_t end_position_forward, bool converted = false, const VarRead *vr = nullptr){
 	uint32_t print_start = 0, print_end = 0;
 	if(fragment_length){
 		if(strand){ print_start = end_position_forward; print_end = start_position_forward + 1; }
@@ -549,8 +638,18 @@ RSQ_HD void create_reads(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, 
 				org_len = stage_fragment_read(g, c, s, ref_id, seg, reversed, start_position_forward, end_position_forward, fragment_length, converted ? s.frag[reversed ? 1 : 0] : nullptr);
 			}
 			ReadState par;
-			fill_read(g, c, s, mt, par, seg, tile, fragment_length, org_len);
-			const int id_len = format_read_id(g, c, s, block_id, read_number, print_start, print_end, c.tile_names[tile], ref_id, par);
+			if(vr && vr->slow && fragment_length){
+				// reads of a fragment that touches variants walk the SimBlocks' SysErrorVariants (CreateReads, Simulator.cpp:680-689)
+				const bool reversed = (seg != static_cast<uint32_t>(strand));
+				SysWalkCtx wc{};
+				wc.sys = (reversed ? c.sys_rev : c.sys_fwd) + 2 * c.seq_off[ref_id]; wc.errs = reversed ? c.var.errs_rev : c.var.errs_fwd;
+				wc.block_first = c.var.block_first + c.var.block_first_off[ref_id]; wc.v = c.var.view(ref_id); wc.L = c.seq_len[ref_id]; wc.reverse = reversed ? 1u : 0u;
+				const SysWalk w = reversed ? sysw_reverse_start(wc, vr->start_block, end_position_forward, vr->end_var, vr->end_var_pos)
+				                           : sysw_forward_start(wc, vr->start_block, start_position_forward, vr->first_var, vr->start_variant_pos);
+				fill_read(g, c, s, mt, par, seg, tile, fragment_length, org_len, &wc, &w, vr->allele);
+			}
+			else{ fill_read(g, c, s, mt, par, seg, tile, fragment_length, org_len); }
+			const int id_len = format_read_id(g, c, s, block_id, read_number, print_start, print_end, c.tile_names[tile], ref_id, par, vr ? vr->allele : 0u);
 			sink.write_record(g, seg, s.id, id_len, s.seq, s.qual, par.read_length);
 		}
 		sink.pair_done(g);
@@ -627,6 +726,129 @@ RSQ_HD void ct_conversion(const G &g, const SimCtx &c, Rng &rng, uint8_t *read, 
 			}
 			if(static_cast<uint32_t>(++cur_meth) < n_regions){
 				read_pos = (read_pos + first[cur_meth] - ref_pos) & 0xffffu;
+				ref_pos = first[cur_meth];
+			}
+		}
+	}
+}
+
+// Simulator::CTConversion, variant overload (Simulator.cpp:2004-2217): the same conversion with the walk over the reference kept in step with the
+// allele's variants (insertions stand at one reference position, deletions skip one).  first_variant / first_variant_pos: StartVariant (forward
+// end) or EndVariant (reverse end).  The reference reads its local `deletion` before ever writing it; in its build here the flag starts out false.
+template<class G, class Rng>
+RSQ_HD void ct_conversion_var(const G &g, const SimCtx &c, Rng &rng, uint8_t *read, uint32_t read_len, uint32_t seq_id, uint32_t start_pos, uint32_t allele,
+                              int32_t cur_methylation_start, bool reversed, const VariantView &v, int32_t first_variant, uint32_t first_variant_pos){
+	const uint32_t r0 = c.meth_off[seq_id];
+	const int64_t n_regions = c.meth_off[seq_id + 1] - r0;
+	const uint32_t *first = c.meth_start + r0, *second = c.meth_end + r0;
+	const double *rate = c.meth_rate + r0 + (c.meth_alleles > 1 ? static_cast<size_t>(allele) * c.meth_rate_stride : 0u);
+	int64_t cur_meth = cur_methylation_start;
+	uint32_t read_pos = 0;   // uintReadLen
+	uint32_t ref_pos = start_pos;
+	int64_t cur_var = first_variant;
+	const int64_t n_var = v.n;
+	uint32_t var_bases_left = 0;
+	bool deletion = false;
+	auto var_pos = [&](int64_t i) -> uint32_t { return v.position[i]; };
+	auto var_len = [&](int64_t i) -> uint32_t { return v.length(static_cast<uint32_t>(i)); };
+	auto in_allele = [&](int64_t i) -> bool { return v.in_allele(static_cast<uint32_t>(i), allele); };
+	auto convert = [&](){
+		if(1 == read[read_pos]){
+			const double u = rng.next(g);
+			if(u < rate[cur_meth]){
+				g.sync();
+				if(g.lane() == 0){ read[read_pos] = 3; }
+				g.sync();
+			}
+		}
+	};
+	auto add = [&](uint32_t n){ read_pos = (read_pos + n) & 0xffffu; };
+	if(reversed){
+		if(0 <= cur_var && cur_var < n_var && var_pos(cur_var) == ref_pos && 1 < var_len(cur_var) && in_allele(cur_var)){ var_bases_left = var_len(cur_var) - first_variant_pos; }
+		while(cur_meth < n_regions && cur_meth >= 0 && first[cur_meth] <= ref_pos){ ++cur_meth; }
+		--cur_meth;
+		if(0 <= cur_meth && cur_meth < n_regions && second[cur_meth] <= ref_pos){
+			if(var_bases_left){ add(var_bases_left); var_bases_left = 0; --ref_pos; --cur_var; }
+			while(0 <= cur_var && second[cur_meth] <= var_pos(cur_var) && read_pos < read_len){
+				if(in_allele(cur_var)){
+					add(ref_pos - var_pos(cur_var));
+					add(var_len(cur_var));
+					ref_pos = var_pos(cur_var) - 1u;
+				}
+				--cur_var;
+			}
+			add(ref_pos - (second[cur_meth] - 1u));
+			ref_pos = second[cur_meth] - 1u;
+		}
+		while(0 <= cur_meth && cur_meth < n_regions && read_pos < read_len){
+			while(ref_pos >= first[cur_meth] && ref_pos != 0xffffffffu && read_pos < read_len){
+				if(0 == var_bases_left){
+					while(0 <= cur_var && var_pos(cur_var) == ref_pos && !in_allele(cur_var)){ --cur_var; }
+					if(0 <= cur_var && var_pos(cur_var) == ref_pos){
+						if(0 == var_len(cur_var)){ deletion = true; --cur_var; }
+						else{ var_bases_left = var_len(cur_var); }
+					}
+				}
+				if(deletion){ deletion = false; }
+				else{ convert(); }
+				if(var_bases_left){ if(0 == --var_bases_left){ --cur_var; } }
+				if(0 == var_bases_left){ --ref_pos; }
+				add(1);
+			}
+			if(0 <= --cur_meth && second[cur_meth] <= ref_pos){
+				while(0 <= cur_var && second[cur_meth] <= var_pos(cur_var) && read_pos < read_len){
+					if(in_allele(cur_var)){
+						add(ref_pos - var_pos(cur_var));
+						add(var_len(cur_var));
+						ref_pos = var_pos(cur_var) - 1u;
+					}
+					--cur_var;
+				}
+				add(ref_pos - (second[cur_meth] - 1u));
+				ref_pos = second[cur_meth] - 1u;
+			}
+		}
+	}
+	else{
+		if(cur_var >= 0 && cur_var < n_var && var_pos(cur_var) == ref_pos && 1 < var_len(cur_var) && in_allele(cur_var)){ var_bases_left = var_len(cur_var) - first_variant_pos; }
+		if(cur_meth >= 0 && cur_meth < n_regions && first[cur_meth] > ref_pos){
+			if(var_bases_left){ add(var_bases_left); var_bases_left = 0; ++ref_pos; ++cur_var; }
+			while(cur_var < n_var && first[cur_meth] > var_pos(cur_var) && read_pos < read_len){
+				if(in_allele(cur_var)){
+					add(var_pos(cur_var) - ref_pos);
+					add(var_len(cur_var));
+					ref_pos = var_pos(cur_var) + 1u;
+				}
+				++cur_var;
+			}
+			add(first[cur_meth] - ref_pos);
+			ref_pos = first[cur_meth];
+		}
+		while(cur_meth >= 0 && cur_meth < n_regions && read_pos < read_len){
+			while(ref_pos < second[cur_meth] && read_pos < read_len){
+				if(0 == var_bases_left){
+					while(cur_var < n_var && var_pos(cur_var) == ref_pos && !in_allele(cur_var)){ ++cur_var; }
+					if(cur_var < n_var && var_pos(cur_var) == ref_pos){
+						if(0 == var_len(cur_var)){ deletion = true; ++cur_var; }
+						else{ var_bases_left = var_len(cur_var); }
+					}
+				}
+				if(deletion){ deletion = false; }
+				else{ convert(); }
+				if(var_bases_left){ if(0 == --var_bases_left){ ++cur_var; } }
+				if(0 == var_bases_left){ ++ref_pos; }
+				add(1);
+			}
+			if(++cur_meth < n_regions && first[cur_meth] > ref_pos){
+				while(cur_var < n_var && first[cur_meth] > var_pos(cur_var) && read_pos < read_len){
+					if(in_allele(cur_var)){
+						add(var_pos(cur_var) - ref_pos);
+						add(var_len(cur_var));
+						ref_pos = var_pos(cur_var) + 1u;
+					}
+					++cur_var;
+				}
+				add(first[cur_meth] - ref_pos);
 				ref_pos = first[cur_meth];
 			}
 		}
@@ -732,6 +954,118 @@ RSQ_HD void simulate_block(const G &g, const SimCtx &c, const Scratch &s, Sink &
 				}
 			}
 		}
+	}
+	if(scan_draws && g.lane() == 0){ *scan_draws = draws; }
+}
+
+// Simulator::SimulateFromGivenBlock for a reference with variants (-V): every start position is visited once more per inserted base of the
+// insertions there, the number of strands with fragments is drawn over the alleles possible at that start, the chosen (allele, strand) ids
+// follow ChooseAlleles, and every chosen allele's fragment is evaluated on its own sequence.  chosen: 2 * num_alleles uint16_t of group-shared memory.
+template<bool kMeth, class G, class Sink>
+RSQ_HD void simulate_block_var(const G &g, const SimCtx &c, const Scratch &s, Sink &sink, const BlockDesc &b, unsigned long long *scan_draws, uint16_t *chosen){
+	Mt mt; mt.s = s.mt; mt.idx = kMtN;
+	mt_seed(g, mt, b.seed);
+	const uint32_t L = c.seq_len[b.ref_id];
+	const uint32_t group = c.coverage_group[b.ref_id];
+	const double *thr = c.thr + static_cast<size_t>(group) * c.insert_to * 2;
+	const uint64_t *thr_int = c.thr_int + static_cast<size_t>(group) * c.insert_to;
+	const uint32_t A = c.var.num_alleles, n_pow = 2u * A + 1u;
+	const double *binom_pow = c.binom_pow + static_cast<size_t>(group) * c.insert_to * n_pow;
+	const VariantView v = c.var.view(b.ref_id);
+	uint64_t read_number = 0;
+	unsigned long long draws = 0;
+	uint32_t end = b.start_pos + 1000u;
+	if(end > L){ end = L; }
+	int32_t cur_methylation_start = b.first_meth;
+	uint32_t first_var = b.first_var, start_variant_pos = 0;
+	for(uint32_t pos = b.start_pos; pos < end; ++pos){
+		if(kMeth){
+			const uint32_t r0 = c.meth_off[b.ref_id], nr = c.meth_off[b.ref_id + 1] - r0;
+			if(cur_methylation_start >= 0 && static_cast<uint32_t>(cur_methylation_start) < nr && c.meth_end[r0 + cur_methylation_start] <= pos){ ++cur_methylation_start; }
+		}
+		do{
+			const uint32_t n_possible = count_possible_alleles(v, A, first_var, start_variant_pos, pos);
+			uint32_t len = c.insert_from;
+			while(len < c.insert_to){
+				if(mt.idx >= kMtN){ mt_regen(g, mt); }
+				uint32_t n = c.insert_to - len;
+				if(n > static_cast<uint32_t>(G::kSize)){ n = G::kSize; }
+				if(n > static_cast<uint32_t>(kMtN - mt.idx)){ n = kMtN - mt.idx; }
+				const uint32_t lane = g.lane();
+				uint64_t x = 0;
+				bool hit = false;
+				if(lane < n){
+					x = mt_temper(mt.s[mt.idx + lane]);
+					hit = x >= thr_int[len + lane];
+				}
+				const unsigned mask = g.ballot(hit);
+				if(mask == 0){
+					mt.idx += n; len += n; draws += n;
+					continue;
+				}
+#if defined(__CUDA_ARCH__)
+				const uint32_t first = __ffs(mask) - 1;
+#else
+				const uint32_t first = 0;
+#endif
+				const uint32_t fragment_length = len + first;
+				x = mt_temper(mt.s[mt.idx + first]);
+				mt.idx += first + 1; len = fragment_length + 1; draws += first + 1;
+
+				const double probability_chosen = canonical(x);
+				const double thr0 = thr[2 * fragment_length], thr1 = thr[2 * fragment_length + 1];
+				if(!(probability_chosen >= thr1)){ continue; }
+				const uint32_t non_zero_strands = binomial_count(2u * n_possible, sub_rn(1.0, thr0), binom_pow[static_cast<size_t>(fragment_length) * n_pow + 2u * n_possible], probability_chosen);
+				if(!non_zero_strands){ continue; }
+				auto uniform = [&]() -> double { return mt_uniform(g, mt); };
+				g.sync();
+				const uint32_t n_chosen = choose_alleles(chosen, non_zero_strands, 2u * n_possible, uniform);
+				g.sync();
+				for(uint32_t ci = 0; ci < n_chosen; ++ci){
+					const uint32_t id = chosen[ci];
+					const uint32_t allele = nth_possible_allele(v, A, first_var, start_variant_pos, pos, id / 2u);
+					const bool strand = id & 1u;
+					VarEval e;
+					bool runaway = false;
+					if(!eval_allele_hit(c, v, b.ref_id, pos, first_var, start_variant_pos, fragment_length, allele, thr0, uniform, e, runaway)){ continue; }
+					if(runaway && g.lane() == 0){ *c.error_flag |= kErrCountRunaway; }
+					if(!e.counts){ continue; }
+					const bool staged = e.slow || kMeth;
+					if(e.slow){ splice_fragment_ends(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fragment_length, e, s.frag[0], s.frag[1]); }
+					else if(kMeth){
+						const uint64_t off = c.seq_off[b.ref_id];
+						for(uint32_t rev = 0; rev < 2; ++rev){
+							const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
+							uint32_t nn = c.read_len_to[seg] + c.max_len_deletion;
+							if(fragment_length < nn){ nn = fragment_length; }
+							if(nn > c.max_org_len){ nn = c.max_org_len; }
+							g.sync();
+							for(uint32_t i = g.lane(); i < nn; i += G::kSize){
+								s.frag[rev][i] = rev ? static_cast<uint8_t>(3 - c.ref[off + e.end_position - 1 - i]) : c.ref[off + pos + i];
+							}
+							g.sync();
+						}
+					}
+					if(kMeth){
+						// CTConversion, variant overload: forward end from StartVariant, reverse end from EndVariant
+						const int32_t end_var = e.slow ? e.end_var : static_cast<int32_t>(var_lower_bound(v, e.end_position)) - 1;
+						for(uint32_t rev = 0; rev < 2; ++rev){
+							const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
+							uint32_t nn = c.read_len_to[seg] + c.max_len_deletion;
+							if(fragment_length < nn){ nn = fragment_length; }
+							if(nn > c.max_org_len){ nn = c.max_org_len; }
+							MtSource rng{mt};
+							ct_conversion_var(g, c, rng, s.frag[rev], nn, b.ref_id, rev ? e.end_position : pos, allele, cur_methylation_start, rev != 0, v,
+							                  rev ? end_var : static_cast<int32_t>(first_var), rev ? e.end_var_pos : start_variant_pos);
+						}
+						g.sync();
+					}
+					VarRead vr{allele, e.slow, first_var, start_variant_pos, e.end_var, e.end_var_pos, b.start_pos / 1000u};
+					create_reads(g, c, s, mt, sink, e.counts, strand, b.ref_id, fragment_length, read_number, b.block_id, pos, e.end_position, staged, &vr);
+				}
+			}
+			next_start_pass(v, pos, first_var, start_variant_pos);
+		}while(start_variant_pos);
 	}
 	if(scan_draws && g.lane() == 0){ *scan_draws = draws; }
 }

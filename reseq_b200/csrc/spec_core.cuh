@@ -108,13 +108,15 @@ struct ReadJob {
 	uint32_t start_pos, end_pos;   // fragment [start, end) on the forward strand (0,0: adapter-only pair)
 	uint32_t fragment_length;
 	uint32_t block_id;             // id printed in the record name
-	uint32_t flags;                // bit 0 segment, bit 1 strand, bit 2 seqToIllumina record (ref_id = record index), bits 8.. tile index
+	uint32_t flags;                // bit 0 segment, bit 1 strand, bit 2 seqToIllumina record (ref_id = record index), bit 3 fragment touches variants, bits 8-23 tile index, bits 24-30 allele
 	uint64_t read_number;
 	uint32_t assumed;              // draws the scan assumed this read consumes
 	uint32_t consumed;             // draws it consumed (phase B)
 	uint32_t rec_len;              // bytes of its FASTQ record (phase B)
 	uint32_t slot;                 // output slot
-	uint32_t conv_index;           // bisulfite runs: which converted fragment end this read starts from (kSpecNone: the reference itself)
+	uint32_t conv_index;           // bisulfite runs / fragments touching variants: which staged fragment end this read starts from (kSpecNone: the reference itself)
+	int32_t var_id;                // fragments touching variants: StartVariant (read on the forward strand) / EndVariant (read on the reverse strand) ...
+	uint32_t var_pos;              // ... {id, posCurrentlyAt}
 	uint32_t pad;
 };
 
@@ -122,13 +124,16 @@ struct SpecHit {                   // where inside SimulateFromGivenBlock's / Cr
 	uint32_t active, in_reads, fragment_length, n_chosen, chosen0, chosen1, ci, counts_left, strand;
 	uint32_t pair_stage;           // reads of the current pair already handled (0..2)
 	uint32_t tile;                 // tile drawn for the current pair
-	uint32_t conv_slot, conv_next; // bisulfite runs: slot of this hit's converted fragment ends / next slot to hand out
+	uint32_t conv_slot, conv_next; // bisulfite runs / variants: slot of this hit's staged fragment ends / next slot to hand out
+	// runs with variants: the chosen (allele, strand) whose reads are being emitted
+	uint32_t allele, end_pos, slow; int32_t end_var; uint32_t end_var_pos;
 };
 struct SpecSnap {                  // resumable state of one unit's stream
 	uint32_t pos, len;
 	uint32_t finished, mt_off;
 	SpecHit hit;
 	int32_t cur_meth;
+	uint32_t first_var, start_variant_pos;   // VariantBiasVarModifiers::first_variant_id_ / start_variant_pos_
 	uint64_t read_number, scan_draws;
 	uint64_t mt[kMtN];
 };
@@ -156,7 +161,9 @@ struct SpecCtx {
 	SpecSnap *snaps;               // [n_units][2 banks][D + 1]: in front of every emitted read + behind the last one
 	ReadJob *jobs;                 // [n_units * D]
 	uint64_t *words;               // [ceil(n_units * D / 32)][K][32] tempered stream words, lane-interleaved per tile of 32 reads
-	uint8_t *conv;                 // bisulfite runs: [n_units][kConvSlots][2][kMaxOrgLen] converted forward / reverse fragment ends
+	uint8_t *conv;                 // bisulfite runs / variants: [n_units][kConvSlots][2][kMaxOrgLen] staged (spliced, converted) forward / reverse fragment ends
+	uint16_t *snap_chosen;         // variants: [n_units][2 banks][D + 1][chosen_stride] the chosen (allele, strand) ids of the hit a snapshot stands in
+	uint32_t chosen_stride;        // 2 * num_alleles
 	// output slots, handed out in slabs of 32
 	unsigned char *slots; uint32_t slot_stride, id_cap, seq_off, qual_off;
 	uint32_t n_slabs; uint32_t *next_slab; uint32_t *slab_next; uint32_t *slab_count;
@@ -304,16 +311,18 @@ template<class G> RSQ_HD uint32_t first_lane(const G &g, unsigned mask){
 #endif
 }
 
+struct ScanVarState { uint32_t first_var, start_variant_pos; const uint16_t *chosen_live; uint16_t *chosen_out; uint32_t n_chosen; };
 template<class G> RSQ_HD void save_snapshot(const G &g, MtRing &ring, SpecSnap &out, uint32_t pos, uint32_t len, bool finished, const SpecHit &hit,
-                                            int32_t cur_meth, uint64_t read_number, uint64_t draws){
+                                            int32_t cur_meth, uint64_t read_number, uint64_t draws, const ScanVarState &vs = ScanVarState{0, 0, nullptr, nullptr, 0}){
 	ring_ensure(g, ring, 1);
 	const uint32_t half = ring.cur >= static_cast<uint32_t>(kMtN) ? kMtN : 0u;
 	g.sync();
 	for(uint32_t i = g.lane(); i < static_cast<uint32_t>(kMtN); i += G::kSize){ out.mt[i] = ring.w[half + i]; }
 	if(g.lane() == 0){
 		out.pos = pos; out.len = len; out.finished = finished ? 1u : 0u; out.mt_off = ring.cur - half; out.hit = hit; out.cur_meth = cur_meth;
-		out.read_number = read_number; out.scan_draws = draws;
+		out.read_number = read_number; out.scan_draws = draws; out.first_var = vs.first_var; out.start_variant_pos = vs.start_variant_pos;
 	}
+	if(vs.chosen_out){ for(uint32_t i = g.lane(); i < vs.n_chosen; i += G::kSize){ vs.chosen_out[i] = vs.chosen_live[i]; } }
 	g.sync();
 }
 
@@ -332,7 +341,8 @@ RSQ_HD void spec_link_slab(const SpecCtx &sp, SpecBlock &blk, uint32_t slab, uin
 //   3. scan on and emit up to `depth` new reads, leaving a snapshot in front of each and one behind the last.
 // Snapshots live in two banks of depth + 1 entries per unit; a round reads the committed one from one bank and writes the other.
 template<class G>
-RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t u, uint64_t *ring_mem){
+RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t u, uint64_t *ring_mem,
+                        uint16_t *chosen_live = nullptr /* runs with variants: 2 * num_alleles entries of group-shared memory */){
 	SpecBlock &blk = sp.blocks[u];
 	if(blk.done){ return; }
 	const uint32_t D = sp.depth;
@@ -402,6 +412,14 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	int32_t cur_meth = snap.cur_meth;
 	uint64_t read_number = snap.read_number, draws = snap.scan_draws;
 	bool finished = snap.finished != 0;
+	const bool with_var = c.var.loaded != 0 && sp.em_recs == nullptr && u < sp.n_blocks;
+	uint32_t first_var = snap.first_var, start_variant_pos = snap.start_variant_pos;
+	uint16_t *chosen_bank_out = nullptr;
+	if(with_var){
+		const uint16_t *chosen_in = sp.snap_chosen + (static_cast<size_t>(u) * 2u * (D + 1u) + bank * (D + 1u) + idx) * sp.chosen_stride;
+		chosen_bank_out = sp.snap_chosen + (static_cast<size_t>(u) * 2u * (D + 1u) + (bank ^ 1u) * (D + 1u)) * sp.chosen_stride;
+		for(uint32_t i = g.lane(); i < hit.n_chosen && i < sp.chosen_stride; i += G::kSize){ chosen_live[i] = chosen_in[i]; }
+	}
 	g.sync();
 	if(pending_skip){
 		// the snapshot stands in front of the read whose assumption failed: walk over it with its measured consumption
@@ -460,7 +478,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 				j.ref_id = pos; j.start_pos = 0; j.end_pos = 0; j.fragment_length = rec.fragment_length; j.block_id = 0;
 				j.flags = rec.seg | 4u | (hit.tile << 8);
 				j.read_number = 0; j.assumed = assumed; j.consumed = kSpecOverflow; j.rec_len = 0; j.slot = slab * 32u + (p & 31u);
-				j.conv_index = kSpecNone; j.pad = 0;
+				j.conv_index = kSpecNone; j.var_id = 0; j.var_pos = 0; j.pad = 0;
 				jobs[emitted] = j;
 			}
 			++emitted; ++pos;
@@ -492,16 +510,24 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 							if(slab == kSpecNone){ failed = true; break; }
 							if(p < 32u){ cur_slab = slab; } else{ next_slab = slab; }
 						}
-						save_snapshot(g, ring, out_snaps[emitted], pos, len, false, hit, cur_meth, read_number, draws);
+						save_snapshot(g, ring, out_snaps[emitted], pos, len, false, hit, cur_meth, read_number, draws,
+						              ScanVarState{first_var, start_variant_pos, chosen_live, with_var ? chosen_bank_out + static_cast<size_t>(emitted) * sp.chosen_stride : nullptr, hit.n_chosen});
 						const size_t gidx = static_cast<size_t>(u) * D + emitted;
 						uint64_t *dst = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
 						const uint32_t assumed = plan_read(g, c, ring, dst, sp.words_per_job, sp.margin, seg, hit.fragment_length);
 						if(g.lane() == 0){
 							ReadJob j;
-							j.ref_id = b.ref_id; j.start_pos = adapter_only ? 0u : pos; j.end_pos = adapter_only ? 0u : pos + hit.fragment_length;
+							const bool reversed = seg != hit.strand;
+							const bool staged = !adapter_only && (c.meth_loaded || (with_var && hit.slow));
+							j.ref_id = b.ref_id; j.start_pos = adapter_only ? 0u : pos; j.end_pos = adapter_only ? 0u : (with_var ? hit.end_pos : pos + hit.fragment_length);
 							j.fragment_length = hit.fragment_length; j.block_id = b.block_id; j.flags = seg | (hit.strand << 1) | (hit.tile << 8);
 							j.read_number = read_number; j.assumed = assumed; j.consumed = kSpecOverflow; j.rec_len = 0; j.slot = slab * 32u + (p & 31u);
-							j.conv_index = (c.meth_loaded && !adapter_only) ? static_cast<uint32_t>((static_cast<size_t>(u) * kConvSlots + hit.conv_slot) * 2u + ((seg != hit.strand) ? 1u : 0u)) : kSpecNone; j.pad = 0;
+							j.conv_index = staged ? static_cast<uint32_t>((static_cast<size_t>(u) * kConvSlots + hit.conv_slot) * 2u + (reversed ? 1u : 0u)) : kSpecNone;
+							j.var_id = 0; j.var_pos = 0; j.pad = 0;
+							if(with_var){
+								j.flags |= (hit.allele << 24) | (hit.slow ? 8u : 0u);
+								j.var_id = reversed ? hit.end_var : static_cast<int32_t>(first_var); j.var_pos = reversed ? hit.end_var_pos : start_variant_pos;
+							}
 							jobs[emitted] = j;
 						}
 						++emitted; ++hit.pair_stage;
@@ -513,7 +539,53 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 				hit.in_reads = 0; ++hit.ci;
 				if(adapter_only){ finished = true; break; }
 			}
-			if(hit.ci < hit.n_chosen){
+			if(with_var && hit.ci < hit.n_chosen){
+				// one chosen (allele, strand) of a hit in a run with variants (Simulator.cpp:2311-2345)
+				const VariantView v = c.var.view(b.ref_id);
+				const uint32_t id = chosen_live[hit.ci];
+				const uint32_t strand = id & 1u, fl = hit.fragment_length;
+				const uint32_t allele = nth_possible_allele(v, c.var.num_alleles, first_var, start_variant_pos, pos, id / 2u);
+				auto uniform = [&]() -> double { return canonical(ring_next(g, ring)); };
+				VarEval e;
+				bool runaway = false;
+				if(eval_allele_hit(c, v, b.ref_id, pos, first_var, start_variant_pos, fl, allele, thr[2 * fl], uniform, e, runaway)){
+					if(runaway && g.lane() == 0){ spec_flag(c, kErrCountRunaway); }
+					if(e.counts){
+						hit.allele = allele; hit.end_pos = e.end_position; hit.slow = e.slow; hit.end_var = e.end_var; hit.end_var_pos = e.end_var_pos;
+						if(e.slow || c.meth_loaded){
+							hit.conv_slot = hit.conv_next; hit.conv_next = (hit.conv_next + 1u) % kConvSlots;
+							uint8_t *frag0 = sp.conv + ((static_cast<size_t>(u) * kConvSlots + hit.conv_slot) * 2u) * kMaxOrgLen, *frag1 = frag0 + kMaxOrgLen;
+							if(e.slow){ splice_fragment_ends(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fl, e, frag0, frag1); }
+							else{
+								for(uint32_t rev = 0; rev < 2; ++rev){
+									const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
+									const uint32_t n = fragment_org_len(c, seg, fl);
+									uint8_t *frag = rev ? frag1 : frag0;
+									g.sync();
+									for(uint32_t i = g.lane(); i < n; i += G::kSize){
+										frag[i] = rev ? static_cast<uint8_t>(3 - c.ref[off + e.end_position - 1 - i]) : c.ref[off + pos + i];
+									}
+									g.sync();
+								}
+							}
+							if(c.meth_loaded){
+								const int32_t end_var = e.slow ? e.end_var : static_cast<int32_t>(var_lower_bound(v, e.end_position)) - 1;
+								for(uint32_t rev = 0; rev < 2; ++rev){
+									const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
+									RingSource rng{ring};
+									ct_conversion_var(g, c, rng, rev ? frag1 : frag0, fragment_org_len(c, seg, fl), b.ref_id, rev ? e.end_position : pos, allele, cur_meth, rev != 0, v,
+									                  rev ? end_var : static_cast<int32_t>(first_var), rev ? e.end_var_pos : start_variant_pos);
+								}
+								g.sync();
+							}
+						}
+						hit.in_reads = 1; hit.counts_left = e.counts; hit.strand = strand; hit.pair_stage = 0; continue;
+					}
+				}
+				++hit.ci;
+				continue;
+			}
+			if(!with_var && hit.ci < hit.n_chosen){
 				const uint32_t strand = (hit.ci ? hit.chosen1 : hit.chosen0) & 1u;
 				const uint32_t fl = hit.fragment_length;
 				const uint32_t cur_end = pos + fl;
@@ -557,7 +629,12 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		bool found = false;
 		while(true){
 			if(len >= insert_to){
-				++pos; len = insert_from;
+				len = insert_from;
+				if(with_var){   // CheckForInsertedBasesToStartFrom: once more from the same position per further inserted base
+					next_start_pass(c.var.view(b.ref_id), pos, first_var, start_variant_pos);
+					if(start_variant_pos){ continue; }
+				}
+				++pos;
 				if(pos >= end){ finished = true; break; }
 				if(c.meth_loaded){   // SimulateFromGivenBlock: the first region that does not end in front of this position
 					const uint32_t r0 = c.meth_off[b.ref_id], nr = c.meth_off[b.ref_id + 1] - r0;
@@ -611,6 +688,22 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		const double probability_chosen = canonical(x_hit);
 		const double thr0 = thr[2 * fragment_length], thr1 = thr[2 * fragment_length + 1];
 		if(!(probability_chosen >= thr1)){ continue; }
+		if(with_var){
+			// DrawNumberNonZeroStrands over the alleles possible at this start + ChooseAlleles (Simulator.cpp:2302-2309)
+			const VariantView v = c.var.view(b.ref_id);
+			const uint32_t n_possible = count_possible_alleles(v, c.var.num_alleles, first_var, start_variant_pos, pos);
+			const uint32_t n_pow = 2u * c.var.num_alleles + 1u;
+			const double pow_term = c.binom_pow[(static_cast<size_t>(group) * insert_to + fragment_length) * n_pow + 2u * n_possible];
+			const uint32_t non_zero_strands = binomial_count(2u * n_possible, sub_rn(1.0, thr0), pow_term, probability_chosen);
+			if(!non_zero_strands){ continue; }
+			hit.active = 1; hit.in_reads = 0; hit.fragment_length = fragment_length; hit.ci = 0; hit.counts_left = 0; hit.strand = 0; hit.pair_stage = 0; hit.tile = 0;
+			hit.chosen0 = 0; hit.chosen1 = 0;
+			auto uniform = [&]() -> double { return canonical(ring_next(g, ring)); };
+			g.sync();
+			hit.n_chosen = choose_alleles(chosen_live, non_zero_strands, 2u * n_possible, uniform);
+			g.sync();
+			continue;
+		}
 		const uint32_t non_zero_strands = binomial_count(2, sub_rn(1.0, thr0), binom_p0[fragment_length], probability_chosen);
 		if(!non_zero_strands){ continue; }
 		hit.active = 1; hit.in_reads = 0; hit.fragment_length = fragment_length; hit.ci = 0; hit.counts_left = 0; hit.strand = 0; hit.pair_stage = 0; hit.tile = 0;
@@ -627,7 +720,8 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		return;
 	}
 	// ---- tentative snapshot behind the new reads ----
-	save_snapshot(g, ring, out_snaps[D], pos, len, finished, hit, cur_meth, read_number, draws);
+	save_snapshot(g, ring, out_snaps[D], pos, len, finished, hit, cur_meth, read_number, draws,
+	              ScanVarState{first_var, start_variant_pos, chosen_live, with_var ? chosen_bank_out + static_cast<size_t>(D) * sp.chosen_stride : nullptr, hit.n_chosen});
 	if(g.lane() == 0){
 		blk.snap_bank = bank; blk.snap_idx = idx; blk.pending_skip = pending_skip;
 		blk.n_jobs = emitted; blk.fill = fill; blk.cur_slab = cur_slab; blk.next_slab = next_slab; blk.rounds += 1;
@@ -660,6 +754,7 @@ RSQ_HD void spec_init_unit(const SimCtx &c, const SpecCtx &sp, const BlockDesc *
 	for(int i = 1; i < kMtN; ++i){ x = 6364136223846793005ull * (x ^ (x >> 62)) + static_cast<uint64_t>(i); s.mt[i] = x; }
 	s.mt_off = kMtN;   // the whole generation is consumed: the first ring_ensure produces generation 1
 	s.finished = 0; s.read_number = 0; s.scan_draws = 0; s.cur_meth = (adapter_only || records) ? 0 : descs[first_desc + u].first_meth;
+	s.first_var = (adapter_only || records) ? 0u : descs[first_desc + u].first_var; s.start_variant_pos = 0;
 	SpecHit h{};
 	if(records){
 		const uint64_t first = static_cast<uint64_t>(u) * sp.em_batch, last = first + sp.em_batch;
@@ -706,6 +801,14 @@ struct ReadMachine {
 	uint32_t adapter_id, tail_left;
 	// per step
 	uint32_t ref_base, dom_error, indel;
+	// fragments touching variants: GetSysErrorFromBlock cursor over the SimBlocks' SysErrorVariants instead of sys[]
+	uint32_t var_slow, allele, var_ref_id, var_reversed; SysWalk walk;
+	RSQ_HD SysWalkCtx walk_ctx(const SimCtx &c) const {
+		SysWalkCtx wc;
+		wc.sys = (var_reversed ? c.sys_rev : c.sys_fwd) + 2 * c.seq_off[var_ref_id]; wc.errs = var_reversed ? c.var.errs_rev : c.var.errs_fwd;
+		wc.block_first = c.var.block_first + c.var.block_first_off[var_ref_id]; wc.v = c.var.view(var_ref_id); wc.L = c.seq_len[var_ref_id]; wc.reverse = var_reversed;
+		return wc;
+	}
 
 	RSQ_HD void load_window(){
 		w0 = words[static_cast<size_t>(k) * 32u]; w1 = words[static_cast<size_t>(k + 1u) * 32u];
@@ -735,12 +838,23 @@ struct ReadMachine {
 		org_len = adapter_length(c, seg, adapter_id);
 		if(c.adapters[seg].off[adapter_id + 1] - off > c.max_org_len){ spec_flag(c, kErrOrgOverflow); }
 	}
-	RSQ_HD void gc_and_error(uint32_t n, uint32_t &mean_error_rate){
+	RSQ_HD void gc_and_error(const SimCtx &c, uint32_t n, uint32_t &mean_error_rate){
 		uint32_t gc = 0, err = 0;
-		for(uint32_t i = 0; i < n; ++i){
-			const uint32_t b = org_base(i);
-			gc += (b == 1 || b == 2) ? 1u : 0u;
-			err += sys[2 * i + 1];
+		if(var_slow){
+			const SysWalkCtx wc = walk_ctx(c);
+			SysWalk pre = walk;
+			for(uint32_t i = 0; i < n; ++i){
+				const uint32_t b = org_base(i);
+				gc += (b == 1 || b == 2) ? 1u : 0u;
+				err += sysw_next(wc, pre, allele) >> 8;
+			}
+		}
+		else{
+			for(uint32_t i = 0; i < n; ++i){
+				const uint32_t b = org_base(i);
+				gc += (b == 1 || b == 2) ? 1u : 0u;
+				err += sys[2 * i + 1];
+			}
 		}
 		gc_seq = percent_u16(gc, n);
 		mean_error_rate = divide_u32(err, n);
@@ -751,7 +865,8 @@ struct ReadMachine {
 		// only assumed + margin words of the slice were written by the scan
 		words = slice; k = 0; kcap = j.assumed + sp.margin < sp.words_per_job ? j.assumed + sp.margin : sp.words_per_job; overflow = 0;
 		load_window();
-		seg = j.flags & 1u; tile = j.flags >> 8; fragment_length = j.fragment_length;
+		seg = j.flags & 1u; tile = (j.flags >> 8) & 0xffffu; fragment_length = j.fragment_length;
+		allele = (j.flags >> 24) & 0x7fu; var_slow = 0; var_ref_id = 0; var_reversed = 0; walk = SysWalk{0, 0, 0, 0};
 		const bool strand = (j.flags >> 1) & 1u;
 		id = reinterpret_cast<char *>(slot + 16); id_cap = static_cast<int>(sp.id_cap); cigar_len = 0;
 		seq_out = slot + sp.seq_off; qual_out = slot + sp.qual_off;
@@ -781,6 +896,7 @@ struct ReadMachine {
 			n = put_uint(one, id, n, id_cap, j.block_id);
 			n = put_char(one, id, n, id_cap, '_');
 			n = put_uint(one, id, n, id_cap, j.read_number);
+			if(print_start && c.var.loaded && 1 < c.var.num_alleles){ n = put_str(one, id, n, id_cap, "_allele", 7); n = put_uint(one, id, n, id_cap, allele); }
 			n = put_char(one, id, n, id_cap, ':');
 			n = put_uint(one, id, n, id_cap, print_start);
 			n = put_char(one, id, n, id_cap, ':');
@@ -803,7 +919,12 @@ struct ReadMachine {
 			const bool reversed = (seg != static_cast<uint32_t>(strand));
 			if(!reversed){ org = c.ref + off + j.start_pos; sys = c.sys_fwd + 2 * (off + j.start_pos); }
 			else{ org = c.ref + off + j.end_pos - 1; org_step = -1; org_comp = 1; sys = c.sys_rev + 2 * (off + (L - j.end_pos)); }
-			if(j.conv_index != kSpecNone){ org = sp.conv + static_cast<size_t>(j.conv_index) * kMaxOrgLen; org_step = 1; org_comp = 0; }   // bisulfite-converted end
+			if(j.conv_index != kSpecNone){ org = sp.conv + static_cast<size_t>(j.conv_index) * kMaxOrgLen; org_step = 1; org_comp = 0; }   // staged end (bisulfite-converted and / or spliced)
+			if(j.flags & 8u){   // CreateReads with variants (Simulator.cpp:680-689): where this read starts in the block chain of its strand
+				var_slow = 1; var_ref_id = j.ref_id; var_reversed = reversed ? 1u : 0u;
+				const SysWalkCtx wc = walk_ctx(c);
+				walk = reversed ? sysw_reverse_start(wc, j.start_pos / 1000u, j.end_pos, j.var_id, j.var_pos) : sysw_forward_start(wc, j.start_pos / 1000u, j.start_pos, static_cast<uint32_t>(j.var_id), j.var_pos);
+			}
 		}
 		if(record_job){
 			const EmRecord rec = sp.em_recs[j.ref_id];
@@ -814,11 +935,12 @@ struct ReadMachine {
 		adapter_id = 0; tail_left = 0;
 		const uint32_t seq_length = read_length < org_len ? read_length : org_len;
 		uint32_t mean_error_rate = 0;
-		if(seq_length){ gc_and_error(seq_length, mean_error_rate); }
+		if(seq_length){ gc_and_error(c, seq_length, mean_error_rate); }
 		else{
 			if(c.adapters[seg].pick.n){ adapter_id = discrete_lookup(c.adapters[seg].pick, next_u()); }
+			var_slow = 0;
 			stage_adapter(c);
-			gc_and_error(org_len, mean_error_rate);
+			gc_and_error(c, org_len, mean_error_rate);
 			org_len = 0;   // FillReadPart over the (empty) fragment part
 		}
 		phase = kPhFrag; base_cigar = 'M'; cigar_element = 'M'; cigar_element_length = 0;
@@ -842,6 +964,7 @@ struct ReadMachine {
 						adapter_pos = (sc.n ? discrete_lookup(sc, next_u()) : 0u) + as.start_cut_from[adapter_id];
 					}
 					stage_adapter(c);
+					var_slow = 0;   // adapter bases take their systematic errors from adapter_sys_error_
 					org_pos = adapter_pos;
 					phase = kPhAdapter; base_cigar = 'S'; cigar_element = 'S'; cigar_element_length = 0;
 				}
@@ -918,8 +1041,11 @@ RSQ_HD void run_read_machine(const SimCtx &c, const SpecCtx &sp, bool have_job, 
 		const bool q_any = q_part || m.phase == kPhTail || m.phase == kPhOverrun;
 		uint32_t t2 = 0; double u2 = 0.0;
 		if(part && indel == 0u){
-			m.dom_error = m.sys[2 * m.org_pos];
-			m.error_rate = m.sys[2 * m.org_pos + 1];
+			if(m.var_slow){ const SysWalkCtx wc = m.walk_ctx(c); const uint32_t e = sysw_next(wc, m.walk, m.allele); m.dom_error = e & 0xffu; m.error_rate = e >> 8; }
+			else{
+				m.dom_error = m.sys[2 * m.org_pos];
+				m.error_rate = m.sys[2 * m.org_pos + 1];
+			}
 		}
 		if(q_any){
 			u2 = m.next_u();
@@ -962,7 +1088,8 @@ RSQ_HD void run_read_machine(const SimCtx &c, const SpecCtx &sp, bool have_job, 
 			}
 		}
 		else if(part){   // deletion
-			m.error_rate = m.sys[2 * m.org_pos + 1];
+			if(m.var_slow){ const SysWalkCtx wc = m.walk_ctx(c); m.error_rate = sysw_deletion(wc, m.walk); }
+			else{ m.error_rate = m.sys[2 * m.org_pos + 1]; }
 			if('D' == m.cigar_element){ ++m.cigar_element_length; ++m.indel_pos; }
 			else{
 				m.cigar_append(m.cigar_element, m.cigar_element_length);

@@ -396,8 +396,10 @@ int main(int argc, char **argv){
 		std::vector<SpecBlock> sblocks(sp.n_units); std::vector<SpecSnap> snaps(2 * static_cast<size_t>(sp.n_units) * (sp.depth + 1));
 		std::vector<ReadJob> jobs(static_cast<size_t>(sp.n_units) * sp.depth);
 		std::vector<uint64_t> words(((jobs.size() + 31) / 32) * sp.words_per_job * 32);
-		std::vector<uint8_t> conv(bed ? static_cast<size_t>(sp.n_units) * kConvSlots * 2 * kMaxOrgLen : 0);
+		std::vector<uint8_t> conv((bed || vcf) ? static_cast<size_t>(sp.n_units) * kConvSlots * 2 * kMaxOrgLen : 0);
 		sp.blocks = sblocks.data(); sp.snaps = snaps.data(); sp.jobs = jobs.data(); sp.words = words.data(); sp.conv = conv.data();
+		std::vector<uint16_t> snap_chosen(vcf ? 2 * static_cast<size_t>(sp.n_units) * (sp.depth + 1) * 2 * num_alleles : 0), chosen_live(2 * num_alleles + 2);
+		sp.snap_chosen = snap_chosen.data(); sp.chosen_stride = 2 * num_alleles;
 		sp.id_cap = kIdCap; sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
 		sp.n_slabs = sp.n_units * 8 + 64;
 		std::vector<unsigned char> slots(static_cast<size_t>(sp.n_slabs) * 32 * sp.slot_stride);
@@ -414,7 +416,7 @@ int main(int argc, char **argv){
 		auto any_fn = [](bool p){ return p; };
 		while(true){
 			if(getenv("RSQ_TWIN_VARY_DEPTH")){ sp.run_depth = 1 + (rounds * 7) % sp.depth; }   // the product grows the depth as units finish
-			for(uint32_t u = 0; u < sp.n_units; ++u){ scan_window(lane, c, sp, blocks.data(), 0, u, ring_mem.data()); }
+			for(uint32_t u = 0; u < sp.n_units; ++u){ scan_window(lane, c, sp, blocks.data(), 0, u, ring_mem.data(), chosen_live.data()); }
 			if(n_done == sp.n_units){ break; }
 			++rounds;
 			for(uint32_t u = 0; u < sp.n_units; ++u){
@@ -449,7 +451,9 @@ int main(int argc, char **argv){
 	else{
 		for(size_t i = 0; i < nsim; ++i){
 			unsigned long long d = 0;
-			if(bed){ simulate_block<true>(lane, c, s, sink, blocks[i], &d); } else{ simulate_block<false>(lane, c, s, sink, blocks[i], &d); }
+			std::vector<uint16_t> chosen(2 * num_alleles + 2);
+			if(vcf){ if(bed){ simulate_block_var<true>(lane, c, s, sink, blocks[i], &d, chosen.data()); } else{ simulate_block_var<false>(lane, c, s, sink, blocks[i], &d, chosen.data()); } }
+			else if(bed){ simulate_block<true>(lane, c, s, sink, blocks[i], &d); } else{ simulate_block<false>(lane, c, s, sink, blocks[i], &d); }
 			total_draws += d;
 			fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
 			sink.out[0].clear(); sink.out[1].clear();
