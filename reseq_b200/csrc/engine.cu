@@ -38,6 +38,7 @@
 #include "archive_reader.hpp"
 #include "deflate_core.cuh"
 #include "em_input.hpp"
+#include "variant_syserr.hpp"
 
 namespace rsq {
 
@@ -325,6 +326,8 @@ __global__ void k_master_seed(uint64_t *state, uint64_t seed){
 
 struct SysChain {
 	const uint8_t *seq; uint32_t L; uint32_t reverse; const uint64_t *raw; uint32_t seed_interleaved; uint8_t *out; uint32_t carried_dom; uint32_t pad;
+	const uint64_t *blk_off;   // runs with variants: where every SimBlock's draws start in raw (chain_raw); null otherwise
+	uint32_t *bstate;          // runs with variants: distance state in front of every SimBlock (for the draws of its variants)
 };
 struct SysChunk {
 	uint32_t chain; uint32_t begin; uint32_t end; uint32_t warm_from;
@@ -345,10 +348,10 @@ __global__ void k_sys_chunks(Tables tab, const SysChain *chains, SysChunk *chunk
 	const SysChain ch = chains[ck.chain];
 	SysState st{ck.in_dist, ck.in_rate};
 	if(ck.warm_from < ck.begin){
-		st = sys_error_chain(g, tab, prob, ch.seq, ch.L, ch.reverse != 0, ck.warm_from, ck.begin, SysState{0, 0}, ch.carried_dom, sys_gc_range, reset_distance, ch.raw, ch.seed_interleaved != 0, nullptr);
+		st = sys_error_chain(g, tab, prob, ch.seq, ch.L, ch.reverse != 0, ck.warm_from, ck.begin, SysState{0, 0}, ch.carried_dom, sys_gc_range, reset_distance, ch.raw, ch.seed_interleaved != 0, nullptr, ch.blk_off);
 		if(g.lane() == 0){ chunks[c].in_dist = st.distance; chunks[c].in_rate = st.start_rate; chunks[c].warm_from = ck.begin; }
 	}
-	st = sys_error_chain(g, tab, prob, ch.seq, ch.L, ch.reverse != 0, ck.begin, ck.end, st, ch.carried_dom, sys_gc_range, reset_distance, ch.raw, ch.seed_interleaved != 0, ch.out);
+	st = sys_error_chain(g, tab, prob, ch.seq, ch.L, ch.reverse != 0, ck.begin, ck.end, st, ch.carried_dom, sys_gc_range, reset_distance, ch.raw, ch.seed_interleaved != 0, ch.out, ch.blk_off, ch.bstate);
 	if(g.lane() == 0){ chunks[c].out_dist = st.distance; chunks[c].out_rate = st.start_rate; chunks[c].dirty = 0; }
 }
 
@@ -365,12 +368,32 @@ __global__ void k_sys_check(SysChunk *chunks, uint32_t n_chunks, uint32_t *n_dir
 }
 
 __global__ void k_build_blocks(BlockDesc *blocks, uint32_t first, uint32_t nb, uint32_t ref_id, uint32_t first_block_id, const uint64_t *fwd_raw,
-                               const int32_t *first_meth /* per block of the run, or null */, uint32_t seed_stride /* 2001, or 1 with --readSysError */){
+                               const int32_t *first_meth /* per block of the run, or null */, uint32_t seed_stride /* 2001, or 1 with --readSysError */,
+                               const uint64_t *fwd_off = nullptr /* runs with variants: index of every block's seed in fwd_raw */, const uint32_t *block_first = nullptr){
 	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
 	if(b >= nb){ return; }
 	BlockDesc d; d.ref_id = ref_id; d.start_pos = b * 1000u; d.block_id = first_block_id + b; d.first_meth = first_meth ? first_meth[first + b] : 0;
-	d.seed = fwd_raw[static_cast<size_t>(b) * seed_stride];
+	d.seed = fwd_off ? fwd_raw[fwd_off[b]] : fwd_raw[static_cast<size_t>(b) * seed_stride];
+	d.first_var = block_first ? block_first[b] : 0u; d.pad = 0;
 	blocks[first + b] = d;
+}
+
+// Simulator::SetSystematicErrorVariantsForward / Reverse (sim_core.cuh: draw_variant_errors_block): one thread per (SimBlock, strand) of a sequence.
+// The draws are few (two per replacement base), the walk over the block's error rates in front of every variant is the work.
+__global__ void __launch_bounds__(128)
+k_var_sys_errors(Tables tab, VarDrawCtx fwd, VarDrawCtx rev, uint32_t nb, const uint32_t *bstate_fwd, const uint32_t *bstate_rev, const uint64_t *raw,
+                 const uint64_t *fwd_off, const uint64_t *rev_off){
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= 2u * nb){ return; }
+	const uint32_t strand = i >= nb ? 1u : 0u, b = strand ? i - nb : i;
+	const VarDrawCtx &dc = strand ? rev : fwd;
+	if(dc.block_first[b + 1] == dc.block_first[b]){ return; }
+	double prob[kMaxN0 + 4];
+	SingleLane one;
+	const uint32_t bs = (strand ? bstate_rev : bstate_fwd)[b];
+	const uint64_t e = 1000ull * (b + 1ull) < dc.L ? 1000ull * (b + 1ull) : dc.L;
+	const uint64_t size = e - 1000ull * b;
+	draw_variant_errors_block(one, tab, prob, dc, b, SysState{bs & 0xffffffu, bs >> 24}, raw + (strand ? rev_off[b] + 2ull * size : fwd_off[b] + 1ull + 2ull * size));
 }
 
 struct Arena {
@@ -452,7 +475,11 @@ k_simulate(SimCtx c, const BlockDesc *blocks, uint32_t first_block, uint32_t n_b
 		DeviceSink sink; sink.init(arena);
 		unsigned long long draws = 0;
 		const BlockDesc b = blocks[first_block + i];
-		simulate_block<kMeth>(g, c, s, sink, b, &draws);
+		if(c.var.loaded){
+			// runs with variants: the chosen (allele, strand) ids of a hit live behind the warp's scratch
+			simulate_block_var<kMeth>(g, c, s, sink, b, &draws, reinterpret_cast<uint16_t *>(smem + static_cast<size_t>(kWarpsPerCta) * scratch_per_warp) + static_cast<size_t>(warp) * 2u * c.var.num_alleles);
+		}
+		else{ simulate_block<kMeth>(g, c, s, sink, b, &draws); }
 		draws = __shfl_sync(0xffffffffu, draws, 0);
 		if(g.lane() == 0){
 			BlockOut o; o.head[0] = sink.head0; o.head[1] = sink.head1; o.bytes[0] = sink.bytes0; o.bytes[1] = sink.bytes1;
@@ -471,14 +498,16 @@ __global__ void k_spec_init(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32
 	if(u < sp.n_units){ spec_init_unit(c, sp, descs, first_desc, u); }
 }
 
+template<bool kVar>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_spec_scan(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){
 	__shared__ uint64_t rings[kWarpsPerCta][2 * kMtN];
+	extern __shared__ __align__(16) unsigned char scan_dyn[];   // runs with variants: 2 * num_alleles chosen (allele, strand) ids per warp
 	WarpGroup g;
 	const uint32_t warp = threadIdx.x >> 5;
 	const uint32_t u = unit_first + blockIdx.x * kWarpsPerCta + warp;
 	if(u >= unit_end){ return; }
-	scan_window(g, c, sp, descs, first_desc, u, rings[warp]);
+	scan_window<kVar>(g, c, sp, descs, first_desc, u, rings[warp], reinterpret_cast<uint16_t *>(scan_dyn) + static_cast<size_t>(warp) * sp.chosen_stride);
 }
 
 // LogArrayResult::Draw for up to 32 independent reads at once (lanes 0 .. n_rows-1 own one read each).  The likelihood
@@ -602,8 +631,12 @@ k_sys_chunks_lanes(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_
 			dom_base = dominant_from_window(hist, nwin, ch.carried_dom);
 			gc_percent = gc_bases ? percent_u16(gc, gc_bases) : 50u;
 			dist = (st.distance + 9) / 10;
-			u1 = canonical(chain_raw(ch.raw, interleaved, p, 0));
-			u2 = canonical(chain_raw(ch.raw, interleaved, p, 1));
+			if(ch.bstate && p >= ck.begin){
+				uint32_t blk;
+				if(chain_block_start(ch.L, reverse, p, blk)){ ch.bstate[blk] = st.distance | (st.start_rate << 24); }
+			}
+			u1 = canonical(chain_raw(ch.raw, interleaved, p, 0, ch.blk_off, ch.L, reverse));
+			u2 = canonical(chain_raw(ch.raw, interleaved, p, 1, ch.blk_off, ch.L, reverse));
 			t1 = tab.dom_error(ref_base, last_base, dom_base);
 		}
 		uint32_t dom_error = coop_draw(tab, buf, stride, lanes_per_warp, active, t1, dist, gc_percent, st.start_rate, 0, u1, zero);
@@ -644,6 +677,7 @@ k_sys_chunks_lanes(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_
 // Lanes 0 .. lanes_per_warp-1 of a warp own one read each; the other lanes only help with the likelihood products.
 // Few reads per warp = short latency per round (small genomes), 32 = fewest instructions per read (large ones).
 constexpr int kSpecReadWarps = 4;
+template<bool kVar>
 __global__ void __launch_bounds__(kSpecReadWarps * 32)
 k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -674,7 +708,7 @@ k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uin
 		return coop_draw(c.tab, buf, stride, lanes_per_warp, active, table, i0, i1, i2, i3, u, zero);
 	};
 	auto any_fn = [](bool p) -> bool { return __any_sync(0xffffffffu, p); };
-	run_read_machine(c, sp, have, job, slice, slot, draw_fn, any_fn, consumed, rec_len);
+	run_read_machine<kVar>(c, sp, have, job, slice, slot, draw_fn, any_fn, consumed, rec_len);
 	if(have){ sp.jobs[gidx].consumed = consumed; sp.jobs[gidx].rec_len = rec_len; }
 }
 
@@ -956,6 +990,13 @@ struct rsq_engine {
 	DevBuf<SysChain> d_sys_chains; DevBuf<SysChunk> d_sys_chunks; DevBuf<uint32_t> d_sys_dirty, d_gc_tiles;
 	DevBuf<BiasParamDev> d_bias_params; DevBuf<double> d_bias_sums, d_bias_max;
 	DevBuf<uint32_t> d_meth_off, d_meth_start, d_meth_end; DevBuf<double> d_meth_rate; DevBuf<int32_t> d_block_meth;
+	// variants (Reference::variants_ flattened, SimBlock::first_variant_id_, SysErrorVariant::var_errors_ of both strands)
+	DevBuf<uint32_t> d_var_seq_first, d_var_position, d_var_bases_off, d_var_block_first, d_var_block_first_off, d_var_bstate;
+	DevBuf<uint8_t> d_var_bases, d_var_errs_fwd, d_var_errs_rev, d_var_ctx_fwd, d_var_ctx_rev;
+	DevBuf<uint64_t> d_var_allele_lo, d_var_allele_hi, d_var_blk_off;
+	DevBuf<double> d_binom_pow;
+	DevBuf<uint16_t> d_spec_chosen;
+	uint32_t num_alleles = 1; bool with_var = false;
 	PinnedBuf h_ref_stage;
 	std::vector<uint64_t> h_seq_off;
 	uint64_t total_size = 0;
@@ -1292,6 +1333,12 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	e.genome.replace_n(opt.seed);
 	stage_log("prepare: genome copy + ReplaceN");
 	Genome &g = e.genome;
+	e.with_var = g.variants.loaded();
+	e.num_alleles = e.with_var ? g.variants.num_alleles : 1;
+	if(e.with_var){ g.variants.check_deferred(g.seqs); }   // REF columns that stood on an N: the reference opens the VCF after ReplaceN (Simulator.cpp:2690, 2750)
+	if(e.with_var && g.methylation_loaded && g.methylation_alleles_max > 1 && g.methylation_alleles_max != e.num_alleles){
+		throw std::runtime_error(std::to_string(g.methylation_alleles_max) + " alleles specified (must be either 1 or same as in variant file[" + std::to_string(e.num_alleles) + "]) in the methylation file");
+	}
 	// FragmentDistributionStats::UpdateRefSeqBias (FragmentDistributionStats.cpp:3352-3502)
 	e.run_ref_seq_bias = p.ref_seq_bias;
 	uint64_t master_draws_before = 0;     // master-stream outputs consumed on the host (kDraw only)
@@ -1411,6 +1458,37 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	c.ref_seq_bias = e.d_ref_seq_bias.p;
 	e.d_sur_start.alloc(total); e.d_sur_end.alloc(total);
 	c.sur_start = e.d_sur_start.p; c.sur_end = e.d_sur_end.p;
+	// --- variants: flat lists, first variant of every SimBlock, host half of SetSystematicErrorVariants* (variant_syserr.hpp) ---
+	c.var = VarCtx{};
+	c.binom_pow = nullptr;
+	FlatVariants fv; std::vector<uint32_t> block_first, block_first_off;
+	if(e.with_var){
+		fv = g.variants.flatten();
+		const VariantSysContext vctx = variant_sys_context(g.seqs, g.variants, fv);
+		for(size_t i = 0; i < g.seqs.size(); ++i){
+			block_first_off.push_back(block_first.size());
+			const uint32_t nb = (g.seqs[i].size() + 999) / 1000;
+			const auto &vars = g.variants.variants[i];
+			uint32_t v = 0;
+			for(uint32_t b = 0; b <= nb; ++b){
+				while(v < vars.size() && vars[v].position < 1000ull * b){ ++v; }
+				block_first.push_back(b == nb ? vars.size() : v);
+			}
+		}
+		fv.position.push_back(0); fv.allele_lo.push_back(0); fv.allele_hi.push_back(0); fv.bases.push_back(0);   // never empty
+		e.d_var_seq_first.upload(fv.seq_first, s); e.d_var_position.upload(fv.position, s); e.d_var_bases_off.upload(fv.bases_off, s); e.d_var_bases.upload(fv.bases, s);
+		e.d_var_allele_lo.upload(fv.allele_lo, s); e.d_var_allele_hi.upload(fv.allele_hi, s);
+		e.d_var_block_first.upload(block_first, s); e.d_var_block_first_off.upload(block_first_off, s);
+		e.d_var_ctx_fwd.upload(vctx.fwd, s); e.d_var_ctx_rev.upload(vctx.rev, s);
+		e.d_var_errs_fwd.alloc(2 * fv.bases.size() + 2); e.d_var_errs_fwd.zero(s); e.d_var_errs_rev.alloc(2 * fv.bases.size() + 2); e.d_var_errs_rev.zero(s);
+		RSQ_CUDA(cudaStreamSynchronize(s));   // vctx is a local
+		c.var.loaded = 1; c.var.num_alleles = e.num_alleles;
+		c.var.seq_first = e.d_var_seq_first.p; c.var.position = e.d_var_position.p; c.var.bases_off = e.d_var_bases_off.p; c.var.bases = e.d_var_bases.p;
+		c.var.allele_lo = e.d_var_allele_lo.p; c.var.allele_hi = e.d_var_allele_hi.p; c.var.errs_fwd = e.d_var_errs_fwd.p; c.var.errs_rev = e.d_var_errs_rev.p;
+		c.var.block_first = e.d_var_block_first.p; c.var.block_first_off = e.d_var_block_first_off.p;
+		for(int b = 0; b < 3; ++b){ c.var.sur_tab[b] = e.d_sur_tab[b].p; }
+		stage_log("prepare: variants flattened and uploaded");
+	}
 	if(rep){ rep->ms_upload = tm.stop(); } else { tm.stop(); }
 
 	// --- CalculateBiasNormalization: surroundings + per (ref, sampled length) sums on device ---
@@ -1461,6 +1539,20 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 			moff.push_back(mstart.size());
 		}
 		mstart.push_back(0); mend.push_back(0); mrate.push_back(0.0);
+		// Reference::Unmethylation(seq, allele): one column per allele when the file gives them (sequences with a single column repeat it)
+		c.meth_alleles = g.methylation_alleles_max > 1 ? g.methylation_alleles_max : 1; c.meth_rate_stride = static_cast<uint32_t>(mrate.size());
+		if(c.meth_alleles > 1){
+			const size_t stride = mrate.size();
+			mrate.resize(stride * c.meth_alleles, 0.0);
+			for(uint32_t a = 1; a < c.meth_alleles; ++a){
+				for(size_t i = 0; i < g.seqs.size(); ++i){
+					for(size_t r = 0; r < g.unmethylated_regions[i].size(); ++r){
+						const auto &cols = g.unmethylation_alleles[i];
+						mrate[a * stride + moff[i] + r] = cols.size() > 1 ? cols.at(a).at(r) : g.unmethylation[i].at(r);
+					}
+				}
+			}
+		}
 		e.d_meth_off.upload(moff, s); e.d_meth_start.upload(mstart, s); e.d_meth_end.upload(mend, s); e.d_meth_rate.upload(mrate, s);
 		c.meth_off = e.d_meth_off.p; c.meth_start = e.d_meth_start.p; c.meth_end = e.d_meth_end.p; c.meth_rate = e.d_meth_rate.p;
 		for(size_t i = 0; i < g.seqs.size(); ++i){
@@ -1514,17 +1606,24 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	std::vector<SysErrorRecord> sys_records;
 	if(from_file){ sys_records = read_sys_error_file(opt.sys_error_file); }
 	size_t next_record = 0;
-	uint64_t max_unit_draws = 0; uint32_t nb_total = 0;
+	uint64_t max_unit_draws = 0; uint32_t nb_total = 0, nb_max = 0;
+	if(from_file && e.with_var){
+		throw std::runtime_error("--readSysError together with a variant file is not supported by this engine revision (the distance state in front of every SimBlock comes from the systematic-error chains)");
+	}
+	// master-stream draws of a unit: one seed per reverse block, 2 per position and strand, one seed per forward block - and with variants 2 per
+	// replacement base and strand (SetSystematicErrorVariantsReverse / Forward, Simulator.cpp:836-844, 1075-1083)
+	auto variant_bases = [&](size_t i) -> uint64_t { return e.with_var ? fv.bases_off[fv.seq_first[i + 1]] - fv.bases_off[fv.seq_first[i]] : 0ull; };
 	for(size_t i = 0; i < g.seqs.size(); ++i){
 		const uint32_t L = g.seqs[i].size();
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
-		nb_total += nb;
-		max_unit_draws = std::max<uint64_t>(max_unit_draws, 2ull * nb + (from_file ? 0ull : 4ull * L));
+		nb_total += nb; nb_max = std::max(nb_max, nb);
+		max_unit_draws = std::max<uint64_t>(max_unit_draws, 2ull * nb + (from_file ? 0ull : 4ull * L + 4ull * variant_bases(i)));
 	}
 	if(!nb_total){ throw std::runtime_error("All reference sequences are too short for simulating."); }
 	e.d_master.alloc(max_unit_draws + 1);
 	e.d_blocks.alloc(nb_total);
+	if(e.with_var){ e.d_var_blk_off.alloc(2ull * nb_max); e.d_var_bstate.alloc(2ull * nb_max); }
 	uint32_t next_block_id = 1, first = 0;
 	std::vector<uint8_t> decoded;
 	// this engine's shard of the run: systematic errors and block seeds are only needed for the sequences it has blocks in
@@ -1559,7 +1658,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		const uint32_t L = g.seqs[i].size();
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
-		const uint64_t n_draws = 2ull * nb + (from_file ? 0ull : 4ull * L);
+		const uint64_t n_draws = 2ull * nb + (from_file ? 0ull : 4ull * L + 4ull * variant_bases(i));
 		const bool needed = shard_count_pre == 1 || (e.shard_n && first < shard_hi && shard_lo < static_cast<uint64_t>(first) + nb);
 		if(!needed && !from_file){
 			master_skip(e, n_draws);
@@ -1585,6 +1684,42 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 				RSQ_CUDA(cudaStreamSynchronize(s));
 			}
 			k_build_blocks<<<(nb + 127) / 128, 128, 0, s>>>(e.d_blocks.p, first, nb, i, next_block_id, e.d_master.p + nb, g.methylation_loaded ? e.d_block_meth.p : nullptr, 1u); ++e.launches;
+		}
+		else if(e.with_var){
+			// every SimBlock's draws are followed by those of its variants: the blocks' places in the unit's stream come from tables
+			const uint8_t *hseq = g.seqs[i].data();
+			const uint32_t *bf = block_first.data() + block_first_off[i];
+			const uint32_t vf = fv.seq_first[i];
+			std::vector<uint64_t> blk_off(2ull * nb);   // [0, nb): reverse blocks (first position draw), [nb, 2 nb): forward blocks (seed)
+			uint64_t at = nb;
+			auto vb = [&](uint32_t b) -> uint64_t { return fv.bases_off[vf + bf[b + 1]] - fv.bases_off[vf + bf[b]]; };
+			auto size_of = [&](uint32_t b) -> uint64_t { return std::min<uint64_t>(1000ull * (b + 1), L) - 1000ull * b; };
+			for(uint32_t b = nb; b--; ){ blk_off[b] = at; at += 2 * size_of(b) + 2 * vb(b); }
+			for(uint32_t b = 0; b < nb; ++b){ blk_off[nb + b] = at; at += 1 + 2 * size_of(b) + 2 * vb(b); }
+			if(at != n_draws){ throw std::runtime_error("internal error: master stream layout of a unit with variants"); }
+			RSQ_CUDA(cudaMemcpyAsync(e.d_var_blk_off.p, blk_off.data(), blk_off.size() * 8, cudaMemcpyHostToDevice, s));
+			RSQ_CUDA(cudaMemsetAsync(e.d_var_bstate.p, 0, 2ull * nb * 4, s));
+			std::vector<SysChain> chains(2); std::vector<std::pair<uint32_t, uint32_t>> lens{{L, 0}, {L, 0}};
+			chains[0].seq = e.d_ref.p + seq_off[i]; chains[0].L = L; chains[0].reverse = 1; chains[0].raw = e.d_master.p; chains[0].seed_interleaved = 0;
+			chains[0].out = e.d_sys_rev.p + 2 * seq_off[i]; chains[0].carried_dom = carried; chains[0].blk_off = e.d_var_blk_off.p; chains[0].bstate = e.d_var_bstate.p;
+			carried = dominant_before(hseq, L, true, L, carried);
+			chains[1].seq = e.d_ref.p + seq_off[i]; chains[1].L = L; chains[1].reverse = 0; chains[1].raw = e.d_master.p; chains[1].seed_interleaved = 1;
+			chains[1].out = e.d_sys_fwd.p + 2 * seq_off[i]; chains[1].carried_dom = carried; chains[1].blk_off = e.d_var_blk_off.p + nb; chains[1].bstate = e.d_var_bstate.p + nb;
+			carried = dominant_before(hseq, L, false, L, carried);
+			uint32_t passes = 0;
+			run_sys_chains(e, chains, lens, 8192, 1024, passes);
+			passes_total = std::max(passes_total, passes);
+			if(fv.seq_first[i + 1] > vf){
+				VarDrawCtx dfw{}, drv{};
+				dfw.ctx = e.d_var_ctx_fwd.p; dfw.errs = e.d_var_errs_fwd.p; dfw.sys = e.d_sys_fwd.p + 2 * seq_off[i]; dfw.gcp = e.d_gc_prefix.p + seq_off[i] + i;
+				dfw.block_first = e.d_var_block_first.p + block_first_off[i];
+				dfw.v.position = e.d_var_position.p + vf; dfw.v.bases_off = e.d_var_bases_off.p + vf; dfw.v.bases = e.d_var_bases.p; dfw.v.allele_lo = e.d_var_allele_lo.p + vf; dfw.v.allele_hi = e.d_var_allele_hi.p + vf;
+				dfw.v.n = fv.seq_first[i + 1] - vf; dfw.L = L; dfw.reverse = 0; dfw.sys_gc_range = e.sys_gc_range; dfw.reset_distance = p.reset_distance;
+				drv = dfw; drv.ctx = e.d_var_ctx_rev.p; drv.errs = e.d_var_errs_rev.p; drv.sys = e.d_sys_rev.p + 2 * seq_off[i]; drv.reverse = 1;
+				k_var_sys_errors<<<(2 * nb + 127) / 128, 128, 0, s>>>(c.tab, dfw, drv, nb, e.d_var_bstate.p + nb, e.d_var_bstate.p, e.d_master.p, e.d_var_blk_off.p + nb, e.d_var_blk_off.p); ++e.launches;
+			}
+			k_build_blocks<<<(nb + 127) / 128, 128, 0, s>>>(e.d_blocks.p, first, nb, i, next_block_id, e.d_master.p, g.methylation_loaded ? e.d_block_meth.p : nullptr, 0u,
+			                                              e.d_var_blk_off.p + nb, e.d_var_block_first.p + block_first_off[i]); ++e.launches;
 		}
 		else{
 			const uint8_t *hseq = g.seqs[i].data();
@@ -1621,8 +1756,9 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		std::memcpy(sums.data(), e.h_bias_results.p, sums.size() * 8);
 		std::memcpy(maxb.data(), e.h_bias_results.p + sums.size() * 8, maxb.size() * 8);
 	}
-	if(!finish_normalization(e.norm, p, rsb, spline, params, sums, maxb, e.total_pairs)){ throw std::runtime_error("bias normalisation is zero"); }
+	if(!finish_normalization(e.norm, p, rsb, spline, params, sums, maxb, e.total_pairs, e.num_alleles, e.with_var)){ throw std::runtime_error("bias normalisation is zero"); }
 	e.d_thr.upload(e.norm.thresholds, s); e.d_thr_int.upload(e.norm.thr_int, s); e.d_binom_p0.upload(e.norm.binom_p0, s); e.d_cov_group.upload(e.norm.coverage_groups, s);
+	if(e.with_var){ e.d_binom_pow.upload(e.norm.binom_pow, s); c.binom_pow = e.d_binom_pow.p; }
 	c.thr = e.d_thr.p; c.thr_int = e.d_thr_int.p; c.binom_p0 = e.d_binom_p0.p; c.coverage_group = e.d_cov_group.p; c.bias_normalization = e.norm.bias_normalization;
 	RSQ_CUDA(cudaStreamSynchronize(s));
 	ms_bias += tm.stop();
@@ -1803,8 +1939,12 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	e.d_spec_blocks.alloc(sp.n_units); e.d_spec_snaps.alloc(2 * static_cast<size_t>(sp.n_units) * (depth + 1)); e.d_spec_jobs.alloc(n_tiles * 32);
 	e.d_spec_words.alloc(n_tiles * sp.words_per_job * 32);
 	sp.blocks = e.d_spec_blocks.p; sp.snaps = e.d_spec_snaps.p; sp.jobs = e.d_spec_jobs.p; sp.words = e.d_spec_words.p;
-	if(c.meth_loaded){ e.d_spec_conv.alloc(static_cast<size_t>(sp.n_units) * kConvSlots * 2 * kMaxOrgLen); sp.conv = e.d_spec_conv.p; }
-	const uint32_t id_prefix = records ? e.em_max_id_len + 1 : c.base_id_len + 10 + 1 + 20 + 1 + 10 + 1 + std::max<uint32_t>(e.max_name_len, 7) + 1 + 10 + 1 + 5 + 11;
+	const bool with_var = c.var.loaded != 0 && !records;
+	if(c.meth_loaded || with_var){ e.d_spec_conv.alloc(static_cast<size_t>(sp.n_units) * kConvSlots * 2 * kMaxOrgLen); sp.conv = e.d_spec_conv.p; }
+	sp.chosen_stride = with_var ? 2 * c.var.num_alleles : 0;
+	if(with_var){ e.d_spec_chosen.alloc(2 * static_cast<size_t>(sp.n_units) * (depth + 1) * sp.chosen_stride); sp.snap_chosen = e.d_spec_chosen.p; }
+	const size_t scan_shmem = with_var ? static_cast<size_t>(kWarpsPerCta) * sp.chosen_stride * sizeof(uint16_t) : 0;
+	const uint32_t id_prefix = records ? e.em_max_id_len + 1 : c.base_id_len + 10 + 1 + 20 + (with_var ? 10 : 0) + 1 + 10 + 1 + std::max<uint32_t>(e.max_name_len, 7) + 1 + 10 + 1 + 5 + 11;
 	sp.id_cap = std::min<uint32_t>(kIdCap, (id_prefix + kCigarCap + 2 + 10 + 15) & ~15u);
 	sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
 	e.d_spec_counters.alloc(8); e.h_spec_counters.ensure(8 * sizeof(uint32_t));
@@ -1819,7 +1959,9 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	}
 	const uint32_t stride = ((e.max_n0_reads + 3u) & ~3u) + 1u;
 	const size_t shmem_reads_max = static_cast<size_t>(kSpecReadWarps) * 32 * stride * sizeof(double);
-	RSQ_CUDA(cudaFuncSetAttribute(k_spec_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem_reads_max)));
+	auto scan_kernel = with_var ? k_spec_scan<true> : k_spec_scan<false>;
+	auto reads_kernel = with_var ? k_spec_reads<true> : k_spec_reads<false>;
+	RSQ_CUDA(cudaFuncSetAttribute(reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem_reads_max)));
 	const double share = e.n_blocks_sim ? static_cast<double>(u_count) / e.n_blocks_sim : 0.0;
 	uint64_t expected_reads = records ? records->em_n + 2048ull : static_cast<uint64_t>(2.0 * (e.total_pairs * share + sp.adapter_only_pairs) * 1.15) + 2048;
 	float ms_sim = 0;
@@ -1848,11 +1990,11 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 						const uint32_t u0 = static_cast<uint64_t>(sp.n_units) * gi / n_groups, u1 = static_cast<uint64_t>(sp.n_units) * (gi + 1) / n_groups;
 						if(u1 == u0){ continue; }
 						cudaStream_t gs = e.spec_streams[gi];
-						k_spec_scan<<<(u1 - u0 + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, gs>>>(c, sp, e.d_blocks.p, first_desc, u0, u1);
+						scan_kernel<<<(u1 - u0 + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, scan_shmem, gs>>>(c, sp, e.d_blocks.p, first_desc, u0, u1);
 						const size_t extra = (sp.n_units > sp.n_blocks && u1 == sp.n_units && sp.depth > sp.run_depth) ? sp.depth - sp.run_depth : 0;
 						const size_t warps = (static_cast<size_t>(u1 - u0) * sp.run_depth + extra + lanes - 1) / lanes;
 						const size_t shmem_reads = static_cast<size_t>(kSpecReadWarps) * lanes * stride * sizeof(double);
-						k_spec_reads<<<static_cast<unsigned>((warps + kSpecReadWarps - 1) / kSpecReadWarps), kSpecReadWarps * 32, shmem_reads, gs>>>(c, sp, stride, lanes, u0, u1);
+						reads_kernel<<<static_cast<unsigned>((warps + kSpecReadWarps - 1) / kSpecReadWarps), kSpecReadWarps * 32, shmem_reads, gs>>>(c, sp, stride, lanes, u0, u1);
 						e.launches += 2;
 					}
 				}
@@ -1932,7 +2074,7 @@ static void simulate_serial_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_co
 	const bool meth = c.meth_loaded != 0;
 	const uint32_t slots = u_count + (with_adapter_only ? 1 : 0);
 	const uint32_t scratch = scratch_bytes(e.max_n0, c.max_org_len, c.max_read_len);
-	const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta;
+	const size_t shmem = static_cast<size_t>(scratch) * kWarpsPerCta + (c.var.loaded ? static_cast<size_t>(kWarpsPerCta) * 2 * c.var.num_alleles * sizeof(uint16_t) : 0);
 	auto kernel = meth ? k_simulate<true> : k_simulate<false>;
 	RSQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
 	RSQ_CUDA(cudaFuncSetAttribute(k_adapter_only, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scratch)));
@@ -2079,7 +2221,8 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	const double rec_bytes = 2.0 * max_rl + 160.0;
 	auto unit_bytes = [&](uint32_t depth){
 		return 2.0 * (depth + 1) * sizeof(SpecSnap) + depth * (sizeof(ReadJob) + 8.0 * (3 * max_rl + 8 + kSpecMargin))
-		       + 1.2 * reads_per_block * (rec_bytes + 250.0) + 2.0 * 1.1 * reads_per_block * rec_bytes + 256.0 + (meth ? kConvSlots * 2.0 * kMaxOrgLen : 0.0);
+		       + 1.2 * reads_per_block * (rec_bytes + 250.0) + 2.0 * 1.1 * reads_per_block * rec_bytes + 256.0 + ((meth || c.var.loaded) ? kConvSlots * 2.0 * kMaxOrgLen : 0.0)
+		       + (c.var.loaded ? 2.0 * (depth + 1) * 4.0 * c.var.num_alleles : 0.0);
 	};
 	size_t free_b = 0, total_b = 0; RSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
 	const double budget = 0.85 * (static_cast<double>(free_b) + e.reusable_bytes());
@@ -2456,11 +2599,6 @@ int rsq_engine_prepare(rsq_engine *engine, const rsq_reference *ref, const rsq_s
 	RSQ_TRY
 	RSQ_CUDA(cudaSetDevice(engine->device));
 	if(report){ std::memset(report, 0, sizeof *report); }
-	if(ref->g.variants.loaded()){
-		// the VCF is loaded and validated like the reference does; the variant-aware halves of the kernels
-		// (allele choice, per-allele bias modifiers, spliced sequences, SysErrorVariant) are not built - no silent reference-only run.
-		throw std::runtime_error("this reference carries variants (rsq_reference_load_variants): variant-aware simulation is not part of this engine revision");
-	}
 	prepare(*engine, ref->g, *opt, report);
 	return 0;
 	RSQ_CATCH(1)

@@ -324,10 +324,13 @@ struct Genome {
 		variants.read(path, first_parts, seqs);
 	}
 
-	// Reference::unmethylated_regions_ / unmethylation_ (allele 0), filled by read_methylation()
+	// Reference::unmethylated_regions_ / unmethylation_, filled by read_methylation(): unmethylation = the first column (allele 0),
+	// unmethylation_alleles[seq][allele] = every column when a sequence's lines carry one value per allele (Reference.cpp:1231-1275: 1 or NumAlleles())
 	bool methylation_loaded = false;
 	std::vector<std::vector<std::pair<uint32_t, uint32_t>>> unmethylated_regions;
 	std::vector<std::vector<double>> unmethylation;
+	std::vector<std::vector<std::vector<double>>> unmethylation_alleles;
+	uint32_t methylation_alleles_max = 1;
 
 	// Reference::PrepareMethylationFile + ReadMethylation (Reference.cpp:1132-1322) for a single-allele run:
 	// extended bedGraph lines "<sequence> <start> <end> <methylation>", grouped by sequence in reference order.
@@ -342,6 +345,9 @@ struct Genome {
 		std::string cur_seq = line.substr(0, line.find_first_of(" \t"));
 		unmethylated_regions.assign(seqs.size(), {});
 		unmethylation.assign(seqs.size(), {});
+		unmethylation_alleles.assign(seqs.size(), {});
+		methylation_alleles_max = 1;
+		const uint32_t allowed = variants.loaded() ? variants.num_alleles : 1;   // NumAlleles() when the VCF was loaded first (the reference opens it first, Simulator.cpp:2747-2772)
 		bool eof = false;
 		for(size_t sid = 0; sid < seqs.size(); ++sid){
 			if(eof || first_part(sid) != cur_seq){ continue; }
@@ -365,18 +371,30 @@ struct Genome {
 				regions.emplace_back(region_start, static_cast<uint32_t>(v));
 				uint32_t allele = 0;
 				first_space = line.find_first_not_of(" \t", second_space);
+				auto &cols = unmethylation_alleles[sid];
+				const uint32_t num_alleles_seq = regions.size() == 1 ? allowed : static_cast<uint32_t>(cols.size());   // first line of a sequence: up to NumAlleles(); later: as in its first line
 				while(first_space < line.size()){
-					if(allele >= 1){ throw std::runtime_error("More alleles specified than in variant file [1] in line:\n" + line); }
+					if(allele >= num_alleles_seq){
+						if(allele >= allowed){ throw std::runtime_error("More alleles specified than in variant file [" + std::to_string(allowed) + "] in line:\n" + line); }
+						throw std::runtime_error("More alleles specified than in last line [" + std::to_string(num_alleles_seq) + "] in line:\n" + line);
+					}
 					second_space = line.find_first_of(" \t", first_space);
 					double d;
 					try{ d = std::stod(line.substr(first_space, second_space)); }
-					catch(const std::exception &e){ throw std::runtime_error("Could not convert field 4 to double for line:\n" + line); }
-					if(0.0 > d || d > 1.0){ throw std::runtime_error("Field 4 is not between 0 and 1:\n" + line); }
-					unmethylation[sid].push_back(1.0 - d);
+					catch(const std::exception &e){ throw std::runtime_error("Could not convert field " + std::to_string(4 + allele) + " to double for line:\n" + line); }
+					if(0.0 > d || d > 1.0){ throw std::runtime_error("Field " + std::to_string(4 + allele) + " is not between 0 and 1:\n" + line); }
+					if(cols.size() <= allele){ cols.resize(allele + 1); }
+					cols[allele].push_back(1.0 - d);
+					if(0 == allele){ unmethylation[sid].push_back(1.0 - d); }
 					++allele;
 					first_space = line.find_first_not_of(" \t", second_space);
 				}
-				if(1 != allele){ throw std::runtime_error("0 alleles specified (must be either 1 or same as in variant file[1]) in line:\n" + line); }
+				if(regions.size() == 1){
+					if(1 != allele && allowed != allele){ throw std::runtime_error(std::to_string(allele) + " alleles specified (must be either 1 or same as in variant file[" + std::to_string(allowed) + "]) in line:\n" + line); }
+					cols.resize(allele);
+				}
+				else if(cols.size() != allele){ throw std::runtime_error(std::to_string(allele) + " alleles specified (must be either identical in all lines of a sequence [" + std::to_string(cols.size()) + "]) in line:\n" + line); }
+				methylation_alleles_max = std::max<uint32_t>(methylation_alleles_max, allele);
 				while(std::getline(f, line) && line.empty());
 				if(!f.fail()){
 					const size_t sp = line.find_first_of(" \t");

@@ -340,7 +340,7 @@ RSQ_HD void spec_link_slab(const SpecCtx &sp, SpecBlock &blk, uint32_t slab, uin
 //      taken in front of the deviating read plus its measured consumption,
 //   3. scan on and emit up to `depth` new reads, leaving a snapshot in front of each and one behind the last.
 // Snapshots live in two banks of depth + 1 entries per unit; a round reads the committed one from one bank and writes the other.
-template<class G>
+template<bool kVar, class G>
 RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t u, uint64_t *ring_mem,
                         uint16_t *chosen_live = nullptr /* runs with variants: 2 * num_alleles entries of group-shared memory */){
 	SpecBlock &blk = sp.blocks[u];
@@ -412,7 +412,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	int32_t cur_meth = snap.cur_meth;
 	uint64_t read_number = snap.read_number, draws = snap.scan_draws;
 	bool finished = snap.finished != 0;
-	const bool with_var = c.var.loaded != 0 && sp.em_recs == nullptr && u < sp.n_blocks;
+	const bool with_var = kVar && c.var.loaded != 0 && sp.em_recs == nullptr && u < sp.n_blocks;   // kVar: the instantiation for runs with variants (keeps the plain one lean)
 	uint32_t first_var = snap.first_var, start_variant_pos = snap.start_variant_pos;
 	uint16_t *chosen_bank_out = nullptr;
 	if(with_var){
@@ -783,7 +783,7 @@ RSQ_HD void spec_init_unit(const SimCtx &c, const SpecCtx &sp, const BlockDesc *
 // ----------------------------------------------------------------------------------------------------------------
 enum : uint32_t { kPhFrag = 0, kPhAdapter = 1, kPhTail = 2, kPhOverrun = 3, kPhDone = 4 };
 
-struct ReadMachine {
+template<bool kVar> struct ReadMachineT {
 	// stream slice
 	const uint64_t *words; uint32_t k, kcap; uint32_t overflow;
 	uint64_t w0, w1, w2, w3;   // words k .. k+3, loaded ahead of their use (the slice streams from HBM/L2 exactly once)
@@ -840,7 +840,7 @@ struct ReadMachine {
 	}
 	RSQ_HD void gc_and_error(const SimCtx &c, uint32_t n, uint32_t &mean_error_rate){
 		uint32_t gc = 0, err = 0;
-		if(var_slow){
+		if(kVar && var_slow){
 			const SysWalkCtx wc = walk_ctx(c);
 			SysWalk pre = walk;
 			for(uint32_t i = 0; i < n; ++i){
@@ -896,7 +896,7 @@ struct ReadMachine {
 			n = put_uint(one, id, n, id_cap, j.block_id);
 			n = put_char(one, id, n, id_cap, '_');
 			n = put_uint(one, id, n, id_cap, j.read_number);
-			if(print_start && c.var.loaded && 1 < c.var.num_alleles){ n = put_str(one, id, n, id_cap, "_allele", 7); n = put_uint(one, id, n, id_cap, allele); }
+			if(kVar && print_start && c.var.loaded && 1 < c.var.num_alleles){ n = put_str(one, id, n, id_cap, "_allele", 7); n = put_uint(one, id, n, id_cap, allele); }
 			n = put_char(one, id, n, id_cap, ':');
 			n = put_uint(one, id, n, id_cap, print_start);
 			n = put_char(one, id, n, id_cap, ':');
@@ -920,7 +920,7 @@ struct ReadMachine {
 			if(!reversed){ org = c.ref + off + j.start_pos; sys = c.sys_fwd + 2 * (off + j.start_pos); }
 			else{ org = c.ref + off + j.end_pos - 1; org_step = -1; org_comp = 1; sys = c.sys_rev + 2 * (off + (L - j.end_pos)); }
 			if(j.conv_index != kSpecNone){ org = sp.conv + static_cast<size_t>(j.conv_index) * kMaxOrgLen; org_step = 1; org_comp = 0; }   // staged end (bisulfite-converted and / or spliced)
-			if(j.flags & 8u){   // CreateReads with variants (Simulator.cpp:680-689): where this read starts in the block chain of its strand
+			if(kVar && (j.flags & 8u)){   // CreateReads with variants (Simulator.cpp:680-689): where this read starts in the block chain of its strand
 				var_slow = 1; var_ref_id = j.ref_id; var_reversed = reversed ? 1u : 0u;
 				const SysWalkCtx wc = walk_ctx(c);
 				walk = reversed ? sysw_reverse_start(wc, j.start_pos / 1000u, j.end_pos, j.var_id, j.var_pos) : sysw_forward_start(wc, j.start_pos / 1000u, j.start_pos, static_cast<uint32_t>(j.var_id), j.var_pos);
@@ -1006,11 +1006,11 @@ struct ReadMachine {
 
 // The lock-step body shared by the device kernel and the host twin.  DrawFn(active, table, i0, i1, i2, i3, u, zero) -> value
 // is LogArrayResult::Draw for every lane whose `active` is set (all lanes of a group call it together).
-template<class DrawFn, class AnyFn>
+template<bool kVar, class DrawFn, class AnyFn>
 RSQ_HD void run_read_machine(const SimCtx &c, const SpecCtx &sp, bool have_job, const ReadJob &job, const uint64_t *slice, unsigned char *slot,
                              DrawFn &&draw_fn, AnyFn &&any_fn, uint32_t &consumed, uint32_t &rec_len){
-	ReadMachine m;
-	m.phase = kPhDone; m.overflow = 0; m.k = 0;
+	ReadMachineT<kVar> m;
+	m.phase = kPhDone; m.overflow = 0; m.k = 0; m.var_slow = 0;
 	uint32_t mean_error_rate = 0;
 	if(have_job){ mean_error_rate = m.begin(c, sp, job, slice, slot); }
 	bool zero = false;
@@ -1041,7 +1041,7 @@ RSQ_HD void run_read_machine(const SimCtx &c, const SpecCtx &sp, bool have_job, 
 		const bool q_any = q_part || m.phase == kPhTail || m.phase == kPhOverrun;
 		uint32_t t2 = 0; double u2 = 0.0;
 		if(part && indel == 0u){
-			if(m.var_slow){ const SysWalkCtx wc = m.walk_ctx(c); const uint32_t e = sysw_next(wc, m.walk, m.allele); m.dom_error = e & 0xffu; m.error_rate = e >> 8; }
+			if(kVar && m.var_slow){ const SysWalkCtx wc = m.walk_ctx(c); const uint32_t e = sysw_next(wc, m.walk, m.allele); m.dom_error = e & 0xffu; m.error_rate = e >> 8; }
 			else{
 				m.dom_error = m.sys[2 * m.org_pos];
 				m.error_rate = m.sys[2 * m.org_pos + 1];
@@ -1088,7 +1088,7 @@ RSQ_HD void run_read_machine(const SimCtx &c, const SpecCtx &sp, bool have_job, 
 			}
 		}
 		else if(part){   // deletion
-			if(m.var_slow){ const SysWalkCtx wc = m.walk_ctx(c); m.error_rate = sysw_deletion(wc, m.walk); }
+			if(kVar && m.var_slow){ const SysWalkCtx wc = m.walk_ctx(c); m.error_rate = sysw_deletion(wc, m.walk); }
 			else{ m.error_rate = m.sys[2 * m.org_pos + 1]; }
 			if('D' == m.cigar_element){ ++m.cigar_element_length; ++m.indel_pos; }
 			else{

@@ -57,6 +57,17 @@ public:
 	std::vector<std::vector<Variant>> variants;             // Reference::variants_
 	std::vector<std::vector<uint32_t>> variant_positions;   // Reference::variant_positions_ (positions_only)
 	uint64_t ref_checks_deferred = 0;  // REF bases that lie on N of the unprocessed reference (compared after ReplaceN)
+	struct DeferredCheck { uint32_t seq, position; uint8_t base; };
+	std::vector<DeferredCheck> deferred;   // those bases: the reference reads the VCF after ReplaceN (Simulator.cpp:2690, 2750), so the engine re-checks them then
+	// Throws like read() does when a REF base that stood on an N of the unprocessed reference differs from what ReplaceN put there.
+	void check_deferred(const std::vector<std::vector<uint8_t>> &replaced) const {
+		for(const auto &d : deferred){
+			if(replaced.at(d.seq).at(d.position) != d.base){
+				throw std::runtime_error(std::string("The specified reference in vcf file '") + "ACGTN"[d.base] + "' is not identical with the specified reference sequence " + std::to_string(d.seq) +
+				                         " at position " + std::to_string(d.position) + ": '" + "ACGTN"[replaced[d.seq][d.position]] + "' (a base ReplaceN filled in for an N).");
+			}
+		}
+	}
 	std::string diagnostics;           // what the reference prints through printErr, one line each
 
 	bool loaded() const { return !variants.empty() || !variant_positions.empty(); }
@@ -64,7 +75,7 @@ public:
 	// seq_ids: Reference::ReferenceIdFirstPart of every sequence; seqs: Dna5 codes (A0 C1 G2 T3 N4).
 	// Throws std::runtime_error carrying the diagnostics when the reference would return false.
 	void read(const std::string &path, const std::vector<std::string> &seq_ids, const std::vector<std::vector<uint8_t>> &seqs, bool positions_only = false){
-		variants.clear(); variant_positions.clear(); diagnostics.clear(); ref_checks_deferred = 0; num_alleles = 1; num_populations = 0;
+		variants.clear(); variant_positions.clear(); diagnostics.clear(); ref_checks_deferred = 0; deferred.clear(); num_alleles = 1; num_populations = 0;
 		TextInput in(path);   // VcfFileIn opens gzip-compressed files as well
 		if(!in.is_open()){ fail("Could not open vcf file '" + path + "'."); }
 		std::istream &f = in.stream();
@@ -169,7 +180,7 @@ public:
 					const auto &s = seqs[rec.rid];
 					bool same = end_pos <= s.size();
 					for(uint32_t k = 0; same && k < vcf_ref.size(); ++k){
-						if(s[start_pos + k] > 3){ ++ref_checks_deferred; }   // ReplaceN runs first in the reference (Simulator.cpp:2690, 2750)
+						if(s[start_pos + k] > 3){ ++ref_checks_deferred; deferred.push_back({rec.rid, start_pos + k, vcf_ref[k]}); }   // ReplaceN runs first in the reference (Simulator.cpp:2690, 2750)
 						else if(s[start_pos + k] != vcf_ref[k]){ same = false; }
 					}
 					if(!same){

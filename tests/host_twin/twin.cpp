@@ -172,6 +172,19 @@ int main(int argc, char **argv){
 			moff.push_back(mstart.size());
 		}
 		mstart.push_back(0); mend.push_back(0); mrate.push_back(0.0);
+		c.meth_alleles = g.methylation_alleles_max > 1 ? g.methylation_alleles_max : 1; c.meth_rate_stride = mrate.size();
+		if(c.meth_alleles > 1){
+			const size_t stride = mrate.size();
+			mrate.resize(stride * c.meth_alleles, 0.0);
+			for(uint32_t a = 1; a < c.meth_alleles; ++a){
+				for(size_t i = 0; i < g.seqs.size(); ++i){
+					for(size_t r = 0; r < g.unmethylated_regions[i].size(); ++r){
+						const auto &cols = g.unmethylation_alleles[i];
+						mrate[a * stride + moff[i] + r] = cols.size() > 1 ? cols.at(a).at(r) : g.unmethylation[i].at(r);
+					}
+				}
+			}
+		}
 		c.meth_loaded = 1; c.meth_off = moff.data(); c.meth_start = mstart.data(); c.meth_end = mend.data(); c.meth_rate = mrate.data();
 	}
 
@@ -416,7 +429,7 @@ int main(int argc, char **argv){
 		auto any_fn = [](bool p){ return p; };
 		while(true){
 			if(getenv("RSQ_TWIN_VARY_DEPTH")){ sp.run_depth = 1 + (rounds * 7) % sp.depth; }   // the product grows the depth as units finish
-			for(uint32_t u = 0; u < sp.n_units; ++u){ scan_window(lane, c, sp, blocks.data(), 0, u, ring_mem.data(), chosen_live.data()); }
+			for(uint32_t u = 0; u < sp.n_units; ++u){ if(vcf){ scan_window<true>(lane, c, sp, blocks.data(), 0, u, ring_mem.data(), chosen_live.data()); } else{ scan_window<false>(lane, c, sp, blocks.data(), 0, u, ring_mem.data(), chosen_live.data()); } }
 			if(n_done == sp.n_units){ break; }
 			++rounds;
 			for(uint32_t u = 0; u < sp.n_units; ++u){
@@ -425,7 +438,8 @@ int main(int argc, char **argv){
 					const size_t gidx = static_cast<size_t>(u) * sp.depth + i;
 					ReadJob &j = jobs[gidx];
 					const uint64_t *slice = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
-					run_read_machine(c, sp, true, j, slice, sp.slots + static_cast<size_t>(j.slot) * sp.slot_stride, draw_fn, any_fn, j.consumed, j.rec_len);
+					if(vcf){ run_read_machine<true>(c, sp, true, j, slice, sp.slots + static_cast<size_t>(j.slot) * sp.slot_stride, draw_fn, any_fn, j.consumed, j.rec_len); }
+					else{ run_read_machine<false>(c, sp, true, j, slice, sp.slots + static_cast<size_t>(j.slot) * sp.slot_stride, draw_fn, any_fn, j.consumed, j.rec_len); }
 					++jobs_run; jobs_ok += j.consumed == j.assumed;
 				}
 			}

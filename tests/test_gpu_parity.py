@@ -137,16 +137,6 @@ def test_malformed_methylation_file_is_an_error(rb, golden, workdir):
         ref.load_methylation(bad)
 
 
-def test_reference_with_variants_is_refused_not_silently_simulated(rb, engine, golden):
-    """-V: the VCF is loaded and checked (tests/test_variants_cpu.py); until the variant-aware kernels exist a run must fail loudly."""
-    ref = rb.Reference.load_fasta(golden["small_ref"])
-    ref.load_variants(os.path.join(golden["dir"], "simref_small_var.vcf"))
-    assert ref.num_alleles == 5
-    with pytest.raises(rb.RsqError, match="variant-aware simulation"):
-        engine.prepare(ref, seed=42, coverage=20.0)
-    _simulate(engine, rb.Reference.load_fasta(golden["small_ref"]), seed=42, coverage=20.0)   # the engine stays usable
-
-
 def test_systematic_error_profile_write_and_read_against_reference_binary(rb, engine, golden, oracle, workdir):
     """--writeSysError (Simulator::CreateSystematicErrorProfile) and --readSysError (ReadSystematicErrors)."""
     fa = os.path.join(workdir, "sysref.fa")
@@ -251,7 +241,7 @@ def test_stage_arrays_match_reference(rb, engine, golden, oracle, workdir, monke
     assert rep.total_pairs_aim == st["sim.total_pairs"][0]
     thr = engine.fetch("thresholds", "float64")
     assert np.array_equal(thr, st["sim.thresholds.0"])
-    blocks = engine.fetch("blocks", "uint64").reshape(-1, 3)
+    blocks = engine.fetch("blocks", "uint64").reshape(-1, 4)   # BlockDesc: ref id | start, block id | first methylation id, seed, first variant id | pad
     assert np.array_equal(blocks[:, 2], st["sim.block_seed"])
     fwd = engine.fetch("sys_fwd").reshape(-1, 2)
     rev = engine.fetch("sys_rev").reshape(-1, 2)

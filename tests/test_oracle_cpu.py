@@ -179,3 +179,43 @@ def test_replace_n_matches_reference(oracle, golden, workdir):
         got = np.frombuffer(subprocess.run([exe, ref, str(seed)], capture_output=True, check=True).stdout, dtype=np.uint8)
         assert got.size == want.size and np.array_equal(got, want.astype(np.uint8))
         assert got.max() <= 3
+
+
+@pytest.mark.parametrize("tag,spec_depth", [("var", None), ("var", "1"), ("var", "8"), ("var_base", None), ("var_base", "32")])
+def test_templates_match_reference_with_variants(oracle, golden, twin, workdir, tag, spec_depth):
+    """-V (SURVEY section 8 row a6 + the variant halves of a4/a8/a14/a15/a18): thresholds for the file's allele count, block seeds with the variants'
+    draws in the master stream, SimBlock::err_variants_ of every block and strand (SetSystematicErrorVariantsForward/Reverse), and the FASTQ
+    the unmodified reference wrote for the 5-allele / 2-allele golden VCF - serial and speculative form of the templates."""
+    import lzma
+    vcf = os.path.join(golden["dir"], f"simref_small_{tag}.vcf")
+    stage = os.path.join(workdir, f"stage_{tag}.flat")
+    if not os.path.exists(stage):
+        subprocess.run([oracle["dump"], "sim", golden["reseq"], golden["small_ref"], "42", "20", stage, "1000000", vcf], check=True, timeout=600,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    prefix = os.path.join(workdir, f"twin_{tag}_{spec_depth}")
+    env = dict(os.environ, RSQ_TWIN_SPEC=spec_depth) if spec_depth else dict(os.environ)
+    res = subprocess.run([twin, stage, "42", prefix, "66", "-", vcf], capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stdout
+    assert "stage_mismatches=0" in res.stdout and "error_flag=0" in res.stdout and "strands equal the reference's" in res.stdout
+    for k in (1, 2):
+        want = lzma.open(os.path.join(golden["dir"], f"sim_small_{tag}_seed42_R{k}.fq.xz")).read()
+        assert open(f"{prefix}_{k}.fq", "rb").read() == want
+
+
+@pytest.mark.parametrize("spec_depth", [None, "6"])
+def test_templates_match_reference_with_70_alleles_and_methylation(oracle, golden, twin, workdir, spec_depth):
+    """70 haploid populations (allele bits in the second 64-bit word, up to 140 (allele, strand) ids per hit) together with --methylation:
+    ChooseAlleles beyond two ids and the variant overload of CTConversion, against a live run of the reference binary."""
+    vcf = os.path.join(golden["dir"], "simref_small_var70.vcf")
+    stage = os.path.join(workdir, "stage_var70.flat")
+    if not os.path.exists(stage):
+        subprocess.run([oracle["dump"], "sim", golden["reseq"], golden["small_ref"], "7", "15", stage, "1000000", vcf], check=True, timeout=600,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r1, r2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], 7, 15, os.path.join(workdir, "ora_var70m"), extra=("-V", vcf, "--methylation", golden["meth_bed"]))
+    prefix = os.path.join(workdir, f"twin_var70m_{spec_depth}")
+    env = dict(os.environ, RSQ_TWIN_SPEC=spec_depth) if spec_depth else dict(os.environ)
+    res = subprocess.run([twin, stage, "7", prefix, "66", golden["meth_bed"], vcf], capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stdout
+    assert "stage_mismatches=0" in res.stdout and "error_flag=0" in res.stdout
+    assert filecmp.cmp(prefix + "_1.fq", r1, shallow=False)
+    assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
