@@ -92,6 +92,54 @@ def dump(vcf):
     return text
 
 
+def write_ends_vcf(path, ids, seqs):
+    """simref_small_var_ends.vcf: variants on the first and last bases of every sequence (surroundings that roll around the sequence ends, fragments
+    that cannot end inside the sequence) and insertions of 30-140 bases (longer than a read; fragments that start, end or lie completely inside one)."""
+    rng = random.Random(5)
+
+    def other(b):
+        return rng.choice([x for x in "ACGT" if x != b])
+    lines = ["##fileformat=VCFv4.2"] + [f"##contig=<ID={n},length={len(s)}>" for n, s in zip(ids, seqs)]
+    lines += ['##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">', "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts0\ts1"]
+    for n, s in zip(ids, seqs):
+        L = len(s)
+        if L < 2000:
+            continue
+        pos_list = sorted(set(p for p in [0, 3, 7, 12, 18, 25, 31, 40, 500, 1001, 1999, 2000, L - 45, L - 33, L - 28, L - 21, L - 15, L - 9, L - 5, L - 2, L - 1] if 0 <= p < L))
+        last = -1
+        for p in pos_list:
+            if p <= last:
+                continue
+            kind = rng.choice(["snp", "ins", "del", "longins", "multi"])
+            if "N" in s[p:p + 4]:
+                continue
+            end = p
+            if kind == "snp":
+                ref = s[p]
+                alt = other(ref)
+            elif kind == "ins":
+                ref = s[p]
+                alt = ref + "".join(rng.choice("ACGT") for _ in range(rng.randrange(1, 6)))
+            elif kind == "longins":
+                ref = s[p]
+                alt = ref + "".join(rng.choice("ACGT") for _ in range(rng.randrange(30, 140)))
+            elif kind == "del":
+                k = rng.randrange(2, 5)
+                if p + k >= L:
+                    continue
+                ref = s[p:p + k]
+                alt = ref[0]
+                end = p + k - 1
+            else:
+                ref = s[p]
+                alt = other(ref) + "," + ref + "GG"
+            nalt = alt.count(",") + 1
+            gts = ["|".join(str(rng.randrange(0, nalt + 1)) for _ in range(2)) for _ in range(2)]
+            lines.append(f"{n}\t{p + 1}\t.\t{ref}\t{alt}\t30\tPASS\tDP=20\tGT\t" + "\t".join(gts))
+            last = end
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
 def main():
     global NAMES
     ids, seqs = [], []
@@ -104,6 +152,7 @@ def main():
             seqs[-1].append(line.upper())
     seqs = ["".join(s) for s in seqs]
     NAMES = [(i, len(s)) for i, s in zip(ids, seqs)]
+    write_ends_vcf(os.path.join(HERE, "simref_small_var_ends.vcf"), ids, seqs)
 
     rng = random.Random(20261017)
     good = records(rng, seqs, [2, 2, 1], 60)                 # three populations, 5 alleles

@@ -414,7 +414,7 @@ int main(int argc, char **argv){
 		std::vector<uint16_t> snap_chosen(vcf ? 2 * static_cast<size_t>(sp.n_units) * (sp.depth + 1) * 2 * num_alleles : 0), chosen_live(2 * num_alleles + 2);
 		sp.snap_chosen = snap_chosen.data(); sp.chosen_stride = 2 * num_alleles;
 		sp.id_cap = kIdCap; sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
-		sp.n_slabs = sp.n_units * 8 + 64;
+		sp.n_slabs = sp.n_units * 40 + 64;   // 32 reads each: enough for 60x runs of the small fixtures
 		std::vector<unsigned char> slots(static_cast<size_t>(sp.n_slabs) * 32 * sp.slot_stride);
 		std::vector<uint32_t> slab_next(sp.n_slabs), slab_count(sp.n_slabs);
 		uint32_t next_slab = 0, n_done = 0;

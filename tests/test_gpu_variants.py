@@ -82,9 +82,11 @@ def test_engine_switches_between_variant_and_plain_runs(rb, engine, golden):
     assert [r1, r2] == want
 
 
-@pytest.mark.parametrize("tag,seed,coverage,path", [("var70", 7, 15.0, "spec"), ("var70", 7, 15.0, "serial"), ("var", 1234, 28.0, "spec"), ("var_base", 5, 40.0, "spec")])
+@pytest.mark.parametrize("tag,seed,coverage,path", [("var70", 7, 15.0, "spec"), ("var70", 7, 15.0, "serial"), ("var", 1234, 28.0, "spec"), ("var_base", 5, 40.0, "spec"),
+                                                    ("var_ends", 3, 60.0, "spec"), ("var_ends", 3, 60.0, "serial")])
 def test_variants_against_reference_binary(rb, engine, golden, oracle, workdir, monkeypatch, tag, seed, coverage, path):
-    """70 haploid populations (allele bits beyond the first 64-bit word) and further seeds: the reference binary's own run with -V."""
+    """70 haploid populations (allele bits beyond the first 64-bit word), further seeds, and var_ends: variants on the first and last bases of every
+    sequence plus insertions longer than a read (tests/golden/make_variants_golden.py::write_ends_vcf) - the reference binary's own run with -V."""
     monkeypatch.setenv("RSQ_SIM_PATH", path)
     vcf = os.path.join(golden["dir"], f"simref_small_{tag}.vcf")
     o1, o2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], seed, coverage, os.path.join(workdir, f"ora_{tag}_{seed}"), extra=("-V", vcf))

@@ -219,3 +219,22 @@ def test_templates_match_reference_with_70_alleles_and_methylation(oracle, golde
     assert "stage_mismatches=0" in res.stdout and "error_flag=0" in res.stdout
     assert filecmp.cmp(prefix + "_1.fq", r1, shallow=False)
     assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
+
+
+@pytest.mark.parametrize("spec_depth", [None, "8"])
+def test_templates_match_reference_with_variants_at_sequence_ends(oracle, golden, twin, workdir, spec_depth):
+    """Variants on the first and last bases of every sequence (surroundings roll around into the reference's other end and ignore variants there,
+    Simulator.cpp:1601, 1706) and insertions of 30-140 bases (fragments starting, ending or lying inside one), at 60x so that they are hit."""
+    vcf = os.path.join(golden["dir"], "simref_small_var_ends.vcf")
+    stage = os.path.join(workdir, "stage_var_ends.flat")
+    if not os.path.exists(stage):
+        subprocess.run([oracle["dump"], "sim", golden["reseq"], golden["small_ref"], "3", "60", stage, "1000000", vcf], check=True, timeout=600,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r1, r2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], 3, 60, os.path.join(workdir, "ora_var_ends"), extra=("-V", vcf))
+    prefix = os.path.join(workdir, f"twin_var_ends_{spec_depth}")
+    env = dict(os.environ, RSQ_TWIN_SPEC=spec_depth) if spec_depth else dict(os.environ)
+    res = subprocess.run([twin, stage, "3", prefix, "66", "-", vcf], capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stdout
+    assert "stage_mismatches=0" in res.stdout and "error_flag=0" in res.stdout
+    assert filecmp.cmp(prefix + "_1.fq", r1, shallow=False)
+    assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
