@@ -9,6 +9,7 @@
 //
 //   dump_tables profile <stats.reseq> <out.flat>                      profile + LogArrayResult tables
 //   dump_tables patch <in.reseq> <out.reseq> <seed>                    synthetic GC / surroundings / dispersion biases
+//   dump_tables patch_adapter_only <in.reseq> <out.reseq> <count>      sets InsertLengths()[0] = count: pairs made of adapters only (Simulator::SimulateAdapterOnlyPairs)
 //   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat> [max_blocks] [in.vcf]   + normalisation, thresholds, seeds, sys-errors
 //                                                                     (with a VCF: thresholds for its allele count, first_variant_id_ and err_variants_ of every block)
 //   dump_tables variants <ref.fa> <in.vcf> <out.txt>                  Reference::variants_ after reading the whole VCF
@@ -220,6 +221,15 @@ int main(int argc, char **argv){
 		for(auto &v : separated){ v = (static_cast<double>(gen() % 17) - 8.0) / 16.0; }
 		fd.fragment_surroundings_bias_.CombinePositions(separated);
 		fd.dispersion_parameters_ = {{0.25, 0.75}};
+		if(!stats.Save(argv[3])){ return 1; }
+		return 0;
+	}
+	if(mode == "patch_adapter_only" && argc >= 5){
+		// None of the synthetic data sets has read pairs without a fragment, so their profiles never send the reference into
+		// SimulateAdapterOnlyPairs (Simulator.cpp:2359-2382).  This gives a profile such pairs and writes it back with DataStats::Save.
+		DataStats stats(NULL);
+		if(!stats.Load(argv[2])){ return 1; }
+		stats.fragment_distribution_.insert_lengths_[0] = std::stoull(argv[4]);
 		if(!stats.Save(argv[3])){ return 1; }
 		return 0;
 	}

@@ -38,8 +38,13 @@ def golden(workdir):
                       ("meth_r1", "sim_small_meth_seed42_R1.fq.xz"), ("meth_r2", "sim_small_meth_seed42_R2.fq.xz"),
                       ("flat_r", "profile150r.flat.xz"), ("reseq_r", "profile150r.reseq.xz"), ("ipf_r", "profile150r.reseq.ipf.xz"),
                       ("flat_t", "profile150t.flat.xz"), ("reseq_t", "profile150t.reseq.xz"), ("ipf_t", "profile150t.reseq.ipf.xz"),
-                      ("flat_250", "profile250.flat.xz"), ("reseq_250", "profile250.reseq.xz"), ("ipf_250", "profile250.reseq.ipf.xz")):
+                      ("flat_250", "profile250.flat.xz"), ("reseq_250", "profile250.reseq.xz"), ("ipf_250", "profile250.reseq.ipf.xz"),
+                      ("reseq_a", "profile150a.reseq.xz")):
         out[key] = _unxz(name, workdir)
+    # profile150a = profile150 with InsertLengths()[0] = 700 (oracle/dump_tables patch_adapter_only): adapter-only pairs; same .ipf (same creation time)
+    out["ipf_a"] = out["reseq_a"] + ".ipf"
+    if not os.path.exists(out["ipf_a"]):
+        shutil.copyfile(out["ipf"], out["ipf_a"])
     return out
 
 

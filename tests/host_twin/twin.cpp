@@ -392,6 +392,9 @@ int main(int argc, char **argv){
 	unsigned long long total_draws = 0;
 	int64_t n_adapter_only = f.scalar_i("sim.num_adapter_only_pairs");
 	if(getenv("RSQ_TWIN_ADAPTER_ONLY")){ n_adapter_only = atoll(getenv("RSQ_TWIN_ADAPTER_ONLY")); }   // serial-vs-speculative consistency checks
+	// the adapter-only pairs follow the last simulated block: all blocks, or all but the look-ahead blocks the reference creates and never simulates
+	const size_t lookahead_blocks = 1 + c.insert_to / 1000;
+	const bool run_adapter_only = n_adapter_only && (nsim == blocks.size() || nsim + lookahead_blocks == blocks.size());
 	const char *spec_env = getenv("RSQ_TWIN_SPEC");
 	if(spec_env){
 		// two-phase speculative form (spec_core.cuh) with one-lane groups: rounds of scan_window + ReadMachine
@@ -402,7 +405,7 @@ int main(int argc, char **argv){
 		const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);
 		sp.words_per_job = 3 * max_rl + 8 + kSpecMargin; sp.margin = kSpecMargin;
 		sp.n_blocks = nsim;
-		const bool with_adapter_only = n_adapter_only && nsim == blocks.size();
+		const bool with_adapter_only = run_adapter_only;
 		sp.n_units = nsim + (with_adapter_only ? 1 : 0);
 		sp.adapter_only_pairs = with_adapter_only ? n_adapter_only : 0;
 		sp.adapter_only_seed = with_adapter_only ? master() : 0;
@@ -472,7 +475,7 @@ int main(int argc, char **argv){
 			fwrite(sink.out[0].data(), 1, sink.out[0].size(), o1); fwrite(sink.out[1].data(), 1, sink.out[1].size(), o2);
 			sink.out[0].clear(); sink.out[1].clear();
 		}
-		if(n_adapter_only && nsim == blocks.size()){
+		if(run_adapter_only){
 			Mt mt; mt.s = s.mt; mt.idx = kMtN;
 			mt_seed(lane, mt, master());
 			uint64_t read_number = 0;

@@ -78,16 +78,18 @@ def test_flat_profile_roundtrip(library, golden, workdir):
         assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
 
 
-def test_reseq_archive_loader_matches_reference_memory_image(library, golden, workdir):
+@pytest.mark.parametrize("suffix", ["", "_r", "_t", "_250"])
+def test_reseq_archive_loader_matches_reference_memory_image(library, golden, workdir, suffix):
     """rsq_profile_load(X.reseq, X.reseq.ipf) == what the reference holds after DataStats::Load + PrepareProcessing +
-    ProbabilityEstimates::Estimate(0 iterations) + PrepareResult (golden flat file written by oracle/dump_tables)."""
+    ProbabilityEstimates::Estimate(0 iterations) + PrepareResult (golden flat file written by oracle/dump_tables), for all four golden
+    profiles: profile150, profile150r (bench), profile150t (three tiles, two read lengths), profile250."""
     import numpy as np
     import reseq_b200 as rb
     from reseq_b200.flatfile import read_flat
-    prof = rb.Profile.load(golden["reseq"], golden["ipf"])
-    out = os.path.join(workdir, "from_archive.flat")
+    prof = rb.Profile.load(golden["reseq" + suffix], golden["ipf" + suffix])
+    out = os.path.join(workdir, f"from_archive{suffix}.flat")
     prof.save_flat(out)
-    a, b = read_flat(golden["flat"]), read_flat(out)
+    a, b = read_flat(golden["flat" + suffix]), read_flat(out)
     assert set(a) == set(b)
     for k in a:
         assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k

@@ -76,6 +76,28 @@ def test_block_batches_concatenate_to_the_whole_run(rb, engine, golden, monkeypa
     assert rep.pairs == r1.count(b"\n") // 4
 
 
+@pytest.mark.parametrize("path,shards", [("spec", 1), ("serial", 1), ("spec", 3)])
+def test_adapter_only_pairs_against_reference_binary(rb, golden, oracle, workdir, monkeypatch, path, shards):
+    """Simulator::SimulateAdapterOnlyPairs (Simulator.cpp:2359-2382) against the reference: profile150a has InsertLengths()[0] > 0 (oracle/dump_tables
+    patch_adapter_only), loaded here through the .reseq/.ipf archive reader; the adapter-only pairs follow the last block (the last shard)."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    o1, o2 = run_oracle_sim(oracle, golden["reseq_a"], golden["small_ref"], 42, 20.0, os.path.join(workdir, "ora_ao_gpu"))
+    want = [open(o1, "rb").read(), open(o2, "rb").read()]
+    assert want[0].count(b":Adapter:") > 100
+    eng = rb.Engine(rb.Profile.load(golden["reseq_a"], golden["ipf_a"]), 0)
+    try:
+        ref = rb.Reference.load_fasta(golden["small_ref"])
+        got = [b"", b""]
+        for k in range(shards):
+            r1, r2, rep = _simulate(eng, ref, seed=42, coverage=20.0, shard_index=k, shard_count=shards)
+            got[0] += r1
+            got[1] += r2
+        assert rep.adapter_only_pairs > 100
+    finally:
+        eng.close()
+    assert got == want
+
+
 def test_adapter_only_pairs_serial_and_speculative_agree(rb, engine, golden, monkeypatch):
     """SimulateAdapterOnlyPairs (insert length 0: reads made of adapter, poly-A tail and overrun bases).  The golden profiles
     contain no such pairs, so they are forced on and the two kernel forms are compared with each other (k_adapter_only vs the
@@ -390,6 +412,48 @@ def test_too_short_reference_is_an_error(rb, engine):
     ref = rb.Reference.from_memory(["tiny"], [b"ACGT" * 50])
     with pytest.raises(rb.RsqError, match="too short"):
         engine.prepare(ref, seed=1, coverage=5.0)
+
+
+def test_c1_real_ecoli_sequence_equals_the_reference(rb, golden, workdir):
+    """BASELINE config C1/C2 on the reference's own E. coli fixture (test/ecoli-GCF_000005845.2_ASM584v2_genomic.fa, committed xz-compressed):
+    2x150 profile150r, 30x, seed 42 - sha256 of the unmodified reference's `-j 1` FASTQ (tests/golden/fullsize_c2_sha256.json, entry
+    ecoli_profile150r).  The FASTA goes through the engine's own reader (80-column lines, full header line as id)."""
+    import json
+    import lzma
+    want = json.load(open(os.path.join(golden["dir"], "fullsize_c2_sha256.json")))["ecoli_profile150r"]
+    fa = os.path.join(workdir, "ecoli.fa")
+    with lzma.open(os.path.join(golden["dir"], "ecoli_GCF_000005845.2.fa.xz")) as src, open(fa, "wb") as dst:
+        dst.write(src.read())
+    ref = rb.Reference.load_fasta(fa)
+    assert ref.total_size == want["size"]
+    eng = rb.Engine(rb.Profile.load_flat(golden["flat_r"]), 0)
+    try:
+        r1, r2, rep = _simulate(eng, ref, seed=want["seed"], coverage=want["coverage"])
+    finally:
+        eng.close()
+    assert rep.pairs == want["pairs"] and [len(r1), len(r2)] == want["bytes"]
+    assert hashlib.sha256(r1).hexdigest() == want["r1"] and hashlib.sha256(r2).hexdigest() == want["r2"]
+    assert b":NC_000913.3:" in r1[:200]
+
+
+def test_c1_four_pair_profile_fails_like_the_reference(rb, golden, workdir):
+    """BASELINE config C1 literally (profile of test/ecoli-SRR490124-4pairs.bam, built by the reference's own stats + IPF code and committed as
+    c1_ecoli4pairs.reseq*): four read pairs do not give two usable insert lengths, and the reference refuses to simulate from it -
+    `Sampling insert lengths did not find at least two usable lengths.` (FragmentDistributionStats.cpp:1686).  Same answer here."""
+    import lzma
+    paths = []
+    for ext in (".reseq", ".reseq.ipf"):
+        dst = os.path.join(workdir, "c1" + ext)
+        with lzma.open(os.path.join(golden["dir"], "c1_ecoli4pairs" + ext + ".xz")) as src, open(dst, "wb") as o:
+            o.write(src.read())
+        paths.append(dst)
+    eng = rb.Engine(rb.Profile.load(*paths), 0)
+    try:
+        ref = rb.Reference.load_fasta(golden["small_ref"])
+        with pytest.raises(rb.RsqError, match="Sampling insert lengths did not find at least two usable lengths"):
+            eng.prepare(ref, seed=42, coverage=2.0)
+    finally:
+        eng.close()
 
 
 @pytest.mark.parametrize("prof,key", [("profile150", "flat"), ("profile150r", "flat_r")])

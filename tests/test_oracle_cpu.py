@@ -238,3 +238,36 @@ def test_templates_match_reference_with_variants_at_sequence_ends(oracle, golden
     assert "stage_mismatches=0" in res.stdout and "error_flag=0" in res.stdout
     assert filecmp.cmp(prefix + "_1.fq", r1, shallow=False)
     assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
+
+
+def test_oracle_passes_the_references_own_unit_tests(oracle, workdir):
+    """`reseq test` of the oracle binary (the reference's gtest suites compiled in from its unmodified sources, main.cpp:1138-1196): three tiers,
+    13 + 17 + 24 = 54 tests.  Needs the reference's test/ fixtures, so it only runs where /root/reference exists (the build container)."""
+    if not os.path.isdir("/root/reference/test"):
+        pytest.skip("/root/reference/test (fixtures of the reference's own tests) is absent on this box")
+    res = subprocess.run([oracle["reseq"], "test"], capture_output=True, text=True, timeout=900, cwd=workdir, env=dict(os.environ, RESEQ_FOLDER="/root/reference"))
+    out = res.stdout + res.stderr
+    import re
+    passed = [int(n) for n in re.findall(r"\[  PASSED  \] (\d+) tests", out)]
+    assert res.returncode == 0, out[-2000:]
+    assert "FAILED" not in out
+    assert passed == [13, 17, 24], passed
+
+
+@pytest.mark.parametrize("spec_depth", [None, "8"])
+def test_adapter_only_pairs_match_reference(oracle, golden, twin, workdir, spec_depth):
+    """Simulator::SimulateAdapterOnlyPairs (Simulator.cpp:2359-2382) against the reference itself: profile150a has InsertLengths()[0] = 700
+    (oracle/dump_tables patch_adapter_only), so 3.5 % of the pairs are adapter + poly-A tail + overrun bases only, written behind the last block."""
+    stage = os.path.join(workdir, "stage_ao.flat")
+    if not os.path.exists(stage):
+        subprocess.run([oracle["dump"], "sim", golden["reseq_a"], golden["small_ref"], "42", "20", stage], check=True, timeout=600,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r1, r2 = run_oracle_sim(oracle, golden["reseq_a"], golden["small_ref"], 42, 20, os.path.join(workdir, "ora_ao"))
+    assert open(r1, "rb").read().count(b":Adapter:") > 100
+    prefix = os.path.join(workdir, f"twin_ao_{spec_depth}")
+    env = dict(os.environ, RSQ_TWIN_SPEC=spec_depth) if spec_depth else dict(os.environ)
+    res = subprocess.run([twin, stage, "42", prefix, "66"], capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stdout
+    assert "stage_mismatches=0" in res.stdout and "error_flag=0" in res.stdout
+    assert filecmp.cmp(prefix + "_1.fq", r1, shallow=False)
+    assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
