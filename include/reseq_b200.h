@@ -96,10 +96,26 @@ typedef struct rsq_sim_report {
 	float ms_upload, ms_bias, ms_syserr, ms_simulate, ms_gather, ms_download;
 	/* speculative two-phase simulation (0/0 when the serial kernel ran): rounds of scan + read kernels, reads emitted per unit and round */
 	uint32_t spec_rounds, spec_depth;
+	/* multi-GPU group (rsq_engine_join_group / rsq_simulate_multi): read pairs of the whole run (all-reduced over NCCL; = pairs for a single engine),
+	 * engines in the group, first SimBlock of this engine's shard */
+	uint64_t group_pairs;
+	uint32_t group_world, shard_first;
 } rsq_sim_report;
 
 rsq_engine *rsq_engine_create(const rsq_profile *profile, int device);
 void rsq_engine_destroy(rsq_engine *engine);
+
+/* --- multi-GPU ------------------------------------------------------------------------------------
+ * The reference runs `-j N` worker threads over one shared block queue (Simulator.cpp:2384-2401, 2830-2836); here one engine per GPU takes a
+ * contiguous range of SimBlocks.  Engines joined into a group (NCCL over NVLink, libnccl.so.2 bound at run time) split the prologue as well:
+ * each uploads and prepares only the sequences its blocks lie in, the per-(sequence, fragment length) bias sums of CalculateBiasNormalization
+ * (FragmentDistributionStats.cpp:3527-3533 threads the same list) are computed by the sequence's owner and all-reduced, and the read-pair counts
+ * are all-reduced behind the data path (rsq_sim_report.group_pairs).  shard_index / shard_count of rsq_sim_options are then rank / world.
+ * One process per GPU (torchrun, mpirun): rank 0 calls rsq_group_unique_id, ships the 128 bytes to the other ranks by any means, every rank calls
+ * rsq_engine_join_group on its engine.  One process for all GPUs of a box: rsq_simulate_multi. */
+int rsq_group_unique_id(void *id_out, uint64_t capacity /* >= 128 */);
+int rsq_engine_join_group(rsq_engine *engine, const void *unique_id, int rank, int world);
+int rsq_engine_leave_group(rsq_engine *engine);
 
 /* Simulator::Simulate prologue (Simulator.cpp:2687-2826): ReplaceN, UpdateRefSeqBias, pair counts,
  * CalculateBiasNormalization, adapter + genome systematic errors, block seeds.  Copies `ref`; uploads to HBM. */
@@ -117,6 +133,13 @@ int rsq_engine_write(const rsq_engine *engine, const char *first_reads_path, con
  * write on device `device`; on failure the output files are removed like the reference does (Simulator.cpp:2888-2893). */
 int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq_sim_options *opt, int device,
                  const char *first_reads_path, const char *second_reads_path, rsq_sim_report *report);
+
+/* The same on n_gpus devices of one box (devices: their CUDA ordinals, NULL = 0 .. n_gpus-1): one engine and one host thread per GPU, joined
+ * into a group (see above); every engine streams its shard's FASTQ to disk while it simulates, shard 0 into the two files themselves, the
+ * others into hidden files next to them that are appended in shard order at the end - byte for byte the files of the single-GPU call.
+ * `report` holds the sums (pairs, bytes, blocks, launches) and the maxima over the engines (device times). */
+int rsq_simulate_multi(const rsq_profile *profile, const rsq_reference *ref, const rsq_sim_options *opt, int n_gpus, const int *devices,
+                       const char *first_reads_path, const char *second_reads_path, rsq_sim_report *report);
 
 /* Drop-in for `bool Simulator::CreateSystematicErrorProfile(out, ref, stats, estimates, seed)` (Simulator.cpp:2597-2653,
  * `--writeSysError`): per sequence the systematic errors of the whole reverse strand, then of the whole forward strand. */

@@ -23,7 +23,8 @@ class SimReport(C.Structure):
                 ("bias_normalization", C.c_double), ("syserr_passes", C.c_uint32), ("kernel_launches", C.c_uint32),
                 ("ms_upload", C.c_float), ("ms_bias", C.c_float), ("ms_syserr", C.c_float), ("ms_simulate", C.c_float),
                 ("ms_gather", C.c_float), ("ms_download", C.c_float),
-                ("spec_rounds", C.c_uint32), ("spec_depth", C.c_uint32)]
+                ("spec_rounds", C.c_uint32), ("spec_depth", C.c_uint32),
+                ("group_pairs", C.c_uint64), ("group_world", C.c_uint32), ("shard_first", C.c_uint32)]
 
     def as_dict(self):
         out = {}
@@ -65,6 +66,10 @@ SIGNATURES = {
     "rsq_engine_output": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "rsq_engine_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "rsq_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SimOptions), C.c_int, C.c_char_p, C.c_char_p, C.POINTER(SimReport)]),
+    "rsq_simulate_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SimOptions), C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_char_p, C.POINTER(SimReport)]),
+    "rsq_group_unique_id": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rsq_engine_join_group": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "rsq_engine_leave_group": (C.c_int, [C.c_void_p]),
     "rsq_create_systematic_error_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p]),
     "rsq_apply_error_model": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(SimReport)]),
     "rsq_engine_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -249,6 +254,16 @@ class Engine:
             raise _err(self._lib)
         return self.report
 
+    def join_group(self, unique_id, rank, world):
+        """This engine becomes rank `rank` of `world` engines of one run (NCCL over NVLink): prepare() then takes shard rank/world."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        if self._lib.rsq_engine_join_group(self._h, buf, rank, world):
+            raise _err(self._lib)
+
+    def leave_group(self):
+        if self._lib.rsq_engine_leave_group(self._h):
+            raise _err(self._lib)
+
     def download(self):
         if self._lib.rsq_engine_download(self._h, C.byref(self.report)):
             raise _err(self._lib)
@@ -286,6 +301,28 @@ class Engine:
         if self._lib.rsq_engine_fetch(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), n.value, C.byref(n)):
             raise _err(self._lib)
         return buf.view(dtype)
+
+
+def group_unique_id():
+    """128 bytes that rank 0 hands to every engine of a multi-GPU group (ncclGetUniqueId)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    if lib.rsq_group_unique_id(buf, 128):
+        raise _err(lib)
+    return buf.raw
+
+
+def simulate_multi(profile, reference, first_reads_path, second_reads_path, seed, n_gpus, coverage=0.0, num_read_pairs=0, ref_bias_model=1,
+                   record_base_identifier=None, devices=None):
+    """rsq_simulate_multi: the drop-in call on n_gpus devices of this box (one engine + one host thread per GPU)."""
+    lib = load_library()
+    opt = SimOptions(seed, coverage, num_read_pairs, ref_bias_model,
+                     record_base_identifier.encode() if record_base_identifier else None, 0, 1, None, None)
+    rep = SimReport()
+    dev = (C.c_int * n_gpus)(*devices) if devices else None
+    if lib.rsq_simulate_multi(profile._h, reference._h, C.byref(opt), n_gpus, dev, os.fsencode(first_reads_path), os.fsencode(second_reads_path), C.byref(rep)):
+        raise _err(lib)
+    return rep
 
 
 def simulate(profile, reference, first_reads_path, second_reads_path, seed, coverage=0.0, num_read_pairs=0, ref_bias_model=1,

@@ -40,7 +40,39 @@
 #include "em_input.hpp"
 #include "variant_syserr.hpp"
 
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is bound at run time (libnccl.so.2), so single-GPU use does not need it
+
 namespace rsq {
+
+// NCCL entry points used by the multi-GPU data plane (engines of one run joined into a group: rsq_engine_join_group)
+struct NcclApi {
+	decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+	decltype(&ncclCommInitRank) CommInitRank = nullptr;
+	decltype(&ncclCommDestroy) CommDestroy = nullptr;
+	decltype(&ncclAllReduce) AllReduce = nullptr;
+	decltype(&ncclBroadcast) Broadcast = nullptr;
+	decltype(&ncclGetErrorString) GetErrorString = nullptr;
+	bool ok = false;
+};
+static NcclApi &nccl_api(){
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, []{
+		void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);   // the copy a host program (e.g. PyTorch) already loaded is reused
+		if(!h){ h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL); }
+		if(!h){ return; }
+		api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+		api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+		api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+		api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+		api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(h, "ncclBroadcast"));
+		api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+		api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Broadcast && api.GetErrorString;
+	});
+	return api;
+}
+#define RSQ_NCCL(call) do{ ncclResult_t r_ = (call); if(r_ != ncclSuccess){ throw std::runtime_error(std::string(#call) + ": " + nccl_api().GetErrorString(r_)); } }while(0)
 
 static thread_local std::string g_last_error;
 static void set_error(const char *fmt, ...){
@@ -997,6 +1029,11 @@ struct rsq_engine {
 	DevBuf<double> d_binom_pow;
 	DevBuf<uint16_t> d_spec_chosen;
 	uint32_t num_alleles = 1; bool with_var = false;
+	// multi-GPU group (rsq_engine_join_group): this engine is rank group_rank of group_world engines of ONE run; prepare() then only uploads and
+	// prepares the sequences its shard holds blocks in, the per-(sequence, length) bias sums are computed by the sequence's owner and all-reduced
+	ncclComm_t comm = nullptr; int group_rank = 0, group_world = 1;
+	DevBuf<double> d_group_scratch;
+	uint64_t group_pairs = 0;
 	PinnedBuf h_ref_stage;
 	std::vector<uint64_t> h_seq_off;
 	uint64_t total_size = 0;
@@ -1034,7 +1071,7 @@ struct rsq_engine {
 	uint32_t spec_rounds = 0, spec_depth = 0;
 	std::vector<cudaStream_t> spec_streams; std::vector<cudaEvent_t> spec_events;
 
-	~rsq_engine(){ for(int i = 0; i < 4; ++i){ if(ev_ring[i]){ cudaEventDestroy(ev_ring[i]); } } for(int i = 0; i < 2; ++i){ if(ev_out[i]){ cudaEventDestroy(ev_out[i]); } } if(copy_stream){ cudaStreamDestroy(copy_stream); } if(copy_stream2){ cudaStreamDestroy(copy_stream2); } for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
+	~rsq_engine(){ if(comm && nccl_api().ok){ nccl_api().CommDestroy(comm); } for(int i = 0; i < 4; ++i){ if(ev_ring[i]){ cudaEventDestroy(ev_ring[i]); } } for(int i = 0; i < 2; ++i){ if(ev_out[i]){ cudaEventDestroy(ev_out[i]); } } if(copy_stream){ cudaStreamDestroy(copy_stream); } if(copy_stream2){ cudaStreamDestroy(copy_stream2); } for(auto ev : spec_events){ cudaEventDestroy(ev); } for(auto st : spec_streams){ cudaStreamDestroy(st); } if(ev_fork){ cudaEventDestroy(ev_fork); } if(ev_join){ cudaEventDestroy(ev_join); } if(stream2){ cudaStreamDestroy(stream2); } if(stream){ cudaStreamDestroy(stream); } }
 };
 
 double rsq_engine::reusable_bytes() const {
@@ -1419,25 +1456,75 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	e.total_pairs -= e.adapter_only_pairs;
 	e.sys_gc_range = static_cast<uint32_t>((sum_read_length + reads / 2) / reads) / 2;
 
-	// --- upload reference ---
+	// --- this engine's shard of the run (block range), and which sequences it has to hold ---
+	// Shard boundaries: the even split of the simulated blocks, moved onto the first block of a sequence when one starts within 5 % of a shard's
+	// size - a shard that only holds a sliver of a sequence would still need that sequence's whole systematic-error chains.
+	const bool grouped = e.comm != nullptr;
+	const uint32_t shard_count_pre = grouped ? static_cast<uint32_t>(e.group_world) : (opt.shard_count ? opt.shard_count : 1);
+	const uint32_t shard_index_pre = grouped ? static_cast<uint32_t>(e.group_rank) : opt.shard_index;
+	if(shard_index_pre >= shard_count_pre){ throw std::runtime_error("shard_index out of range"); }
+	std::vector<uint32_t> seq_first_block(g.seqs.size(), 0), seq_blocks(g.seqs.size(), 0);
+	uint32_t nb_total_pre = 0;
+	for(size_t i = 0; i < g.seqs.size(); ++i){
+		const uint32_t L = g.seqs[i].size();
+		if(L < c.insert_to){ continue; }
+		seq_first_block[i] = nb_total_pre; seq_blocks[i] = (L + 999) / 1000; nb_total_pre += seq_blocks[i];
+	}
+	if(!nb_total_pre){ throw std::runtime_error("All reference sequences are too short for simulating."); }
+	const uint32_t lookahead_blocks = 1 + c.insert_to / 1000;
+	const uint32_t n_sim_blocks = nb_total_pre > lookahead_blocks ? nb_total_pre - lookahead_blocks : 0;
+	auto shard_boundary = [&](uint32_t k) -> uint64_t {
+		if(k == 0){ return 0; }
+		if(k >= shard_count_pre){ return n_sim_blocks; }
+		const uint64_t tol = std::max<uint64_t>(1, n_sim_blocks / (20ull * shard_count_pre));
+		const uint64_t even = static_cast<uint64_t>(n_sim_blocks) * k / shard_count_pre;
+		uint64_t best = even, best_d = tol + 1;
+		for(size_t i = 0; i < g.seqs.size(); ++i){
+			if(!seq_blocks[i]){ continue; }
+			const uint64_t f = seq_first_block[i];
+			const uint64_t d = f > even ? f - even : even - f;
+			if(f > 0 && f < n_sim_blocks && d < best_d){ best = f; best_d = d; }
+		}
+		return best;
+	};
+	e.shard_first = static_cast<uint32_t>(shard_boundary(shard_index_pre));
+	e.shard_n = static_cast<uint32_t>(std::max<uint64_t>(shard_boundary(shard_index_pre + 1), e.shard_first) - e.shard_first);
+	// a sequence is needed by the shards that hold blocks of it; in a group its bias sums are computed by the first of them (its owner)
+	auto shard_needs = [&](uint32_t k, size_t i) -> bool {
+		const uint64_t lo = shard_boundary(k), hi = std::max<uint64_t>(shard_boundary(k + 1), lo);
+		return seq_blocks[i] && hi > lo && seq_first_block[i] < hi && lo < static_cast<uint64_t>(seq_first_block[i]) + seq_blocks[i];
+	};
+	std::vector<uint8_t> needed(g.seqs.size(), 1);
+	std::vector<int32_t> owner(g.seqs.size(), 0);
+	if(grouped){
+		for(size_t i = 0; i < g.seqs.size(); ++i){
+			needed[i] = shard_needs(shard_index_pre, i) ? 1 : 0;
+			owner[i] = -1;
+			for(uint32_t k = 0; k < shard_count_pre && owner[i] < 0; ++k){ if(shard_needs(k, i)){ owner[i] = static_cast<int32_t>(k); } }
+			if(owner[i] < 0){ owner[i] = static_cast<int32_t>(i % shard_count_pre); }   // sequences nobody simulates (too short, look-ahead only): spread their sums
+			if(owner[i] == static_cast<int32_t>(shard_index_pre)){ needed[i] = 1; }
+		}
+	}
+
+	// --- upload reference: the sequences this engine needs, laid out behind each other ---
 	stage_log("prepare: ref bias, counts");
 	tm.start();
 	std::vector<uint64_t> seq_off; std::vector<uint32_t> seq_len, name_off{0}; std::string names;
 	uint64_t total = 0;
 	for(size_t i = 0; i < g.seqs.size(); ++i){
-		seq_off.push_back(total); seq_len.push_back(g.seqs[i].size()); total += g.seqs[i].size();
+		seq_off.push_back(total); seq_len.push_back(g.seqs[i].size()); total += needed[i] ? g.seqs[i].size() : 0;
 		names += g.first_part(i); name_off.push_back(names.size());
 	}
 	e.h_seq_off = seq_off;
 	e.h_ref_stage.ensure(total + 1);
-	for(size_t i = 0; i < g.seqs.size(); ++i){ std::memcpy(e.h_ref_stage.p + seq_off[i], g.seqs[i].data(), g.seqs[i].size()); }
+	for(size_t i = 0; i < g.seqs.size(); ++i){ if(needed[i]){ std::memcpy(e.h_ref_stage.p + seq_off[i], g.seqs[i].data(), g.seqs[i].size()); } }
 	stage_log("prepare: pinned staging of the reference");
 	e.d_ref.alloc(total + 1);
 	RSQ_CUDA(cudaMemcpyAsync(e.d_ref.p, e.h_ref_stage.p, total, cudaMemcpyHostToDevice, s));
 	e.d_gc_prefix.alloc(total + g.seqs.size() + 1);
 	{ uint32_t max_tiles = 1; for(const auto &q : g.seqs){ max_tiles = std::max<uint32_t>(max_tiles, (q.size() + kGcTile - 1) / kGcTile); } e.d_gc_tiles.alloc(max_tiles); }
 	for(size_t i = 0; i < g.seqs.size(); ++i){
-		const uint32_t L = g.seqs[i].size();
+		const uint32_t L = needed[i] ? g.seqs[i].size() : 0;
 		const uint32_t tiles = (L + kGcTile - 1) / kGcTile;
 		uint32_t *gp = e.d_gc_prefix.p + seq_off[i] + i;
 		if(!tiles){ RSQ_CUDA(cudaMemsetAsync(gp, 0, 4, s)); continue; }
@@ -1494,7 +1581,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	// --- CalculateBiasNormalization: surroundings + per (ref, sampled length) sums on device ---
 	tm.start();
 	for(size_t i = 0; i < g.seqs.size(); ++i){
-		const uint32_t L = g.seqs[i].size();
+		const uint32_t L = needed[i] ? g.seqs[i].size() : 0;
 		if(!L){ continue; }
 		k_surroundings<<<(L + 255) / 256, 256, 0, s>>>(e.d_ref.p + seq_off[i], L, e.d_sur_tab[0].p, e.d_sur_tab[1].p, e.d_sur_tab[2].p, e.d_sur_start.p + seq_off[i], e.d_sur_end.p + seq_off[i]);
 		++e.launches;
@@ -1513,7 +1600,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	// The ordered sums run on a second stream: they only feed the thresholds, which nothing needs before k_simulate,
 	// so they overlap with the master stream and the systematic-error chains below.
 	std::vector<double> sums(params.size(), 0.0), maxb(params.size(), 0.0);
-	if(!params.empty()){
+	if(!params.empty() && !grouped){
 		DevBuf<BiasParamDev> &d_params = e.d_bias_params; d_params.upload(dparams, s);
 		DevBuf<double> &d_sums = e.d_bias_sums, &d_max = e.d_bias_max; d_sums.alloc(params.size()); d_max.alloc(params.size());
 		e.h_bias_results.ensure(2 * params.size() * sizeof(double));
@@ -1523,6 +1610,35 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		++e.launches;
 		RSQ_CUDA(cudaMemcpyAsync(e.h_bias_results.p, d_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
 		RSQ_CUDA(cudaMemcpyAsync(e.h_bias_results.p + sums.size() * 8, d_max.p, maxb.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
+		RSQ_CUDA(cudaEventRecord(e.ev_join, e.stream2));
+	}
+	if(!params.empty() && grouped){
+		// The chains of a sequence run on the engine that owns it (the first shard holding blocks of it); every engine contributes its sums and
+		// maxima to one zero-initialised array and an all-reduce over NVLink hands everyone the whole set (x + 0.0 == x exactly, so the sum of the
+		// contributions is the owner's value bit for bit).  The reference threads the same (sequence, length) list (FragmentDistributionStats.cpp:3527-3533).
+		std::vector<BiasParamDev> mine; std::vector<uint32_t> mine_index;
+		for(size_t k = 0; k < params.size(); ++k){ if(owner[params[k].ref_id] == static_cast<int32_t>(shard_index_pre)){ mine.push_back(dparams[k]); mine_index.push_back(k); } }
+		DevBuf<double> &d_all = e.d_group_scratch; d_all.alloc(2 * params.size());
+		e.h_bias_results.ensure(2 * params.size() * sizeof(double));
+		RSQ_CUDA(cudaEventRecord(e.ev_fork, s));
+		RSQ_CUDA(cudaStreamWaitEvent(e.stream2, e.ev_fork, 0));
+		RSQ_CUDA(cudaMemsetAsync(d_all.p, 0, 2 * params.size() * 8, e.stream2));
+		if(!mine.empty()){
+			DevBuf<BiasParamDev> &d_params = e.d_bias_params; d_params.upload(mine, e.stream2);
+			DevBuf<double> &d_sums = e.d_bias_sums, &d_max = e.d_bias_max; d_sums.alloc(mine.size()); d_max.alloc(mine.size());
+			k_sum_bias<<<mine.size(), 128, 0, e.stream2>>>(d_params.p, mine.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
+			++e.launches;
+			std::vector<double> hs(mine.size()), hm(mine.size());
+			RSQ_CUDA(cudaMemcpyAsync(hs.data(), d_sums.p, hs.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
+			RSQ_CUDA(cudaMemcpyAsync(hm.data(), d_max.p, hm.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
+			RSQ_CUDA(cudaStreamSynchronize(e.stream2));
+			std::vector<double> contrib(2 * params.size(), 0.0);
+			for(size_t k = 0; k < mine.size(); ++k){ contrib[mine_index[k]] = hs[k]; contrib[params.size() + mine_index[k]] = hm[k]; }
+			RSQ_CUDA(cudaMemcpyAsync(d_all.p, contrib.data(), contrib.size() * 8, cudaMemcpyHostToDevice, e.stream2));
+			RSQ_CUDA(cudaStreamSynchronize(e.stream2));
+		}
+		RSQ_NCCL(nccl_api().AllReduce(d_all.p, d_all.p, 2 * params.size(), ncclDouble, ncclSum, e.comm, e.stream2));
+		RSQ_CUDA(cudaMemcpyAsync(e.h_bias_results.p, d_all.p, 2 * params.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
 		RSQ_CUDA(cudaEventRecord(e.ev_join, e.stream2));
 	}
 	float ms_bias = tm.stop();
@@ -1626,41 +1742,17 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	if(e.with_var){ e.d_var_blk_off.alloc(2ull * nb_max); e.d_var_bstate.alloc(2ull * nb_max); }
 	uint32_t next_block_id = 1, first = 0;
 	std::vector<uint8_t> decoded;
-	// this engine's shard of the run: systematic errors and block seeds are only needed for the sequences it has blocks in
+	// this engine's shard of the run (computed above): systematic errors and block seeds are only needed for the sequences it has blocks in
 	// (fragments never span sequences); the master-stream draws of the others are skipped by jump-ahead
-	const uint32_t lookahead_blocks = 1 + c.insert_to / 1000;
-	const uint32_t n_sim_blocks = nb_total > lookahead_blocks ? nb_total - lookahead_blocks : 0;
-	const uint32_t shard_count_pre = opt.shard_count ? opt.shard_count : 1;
-	if(opt.shard_index >= shard_count_pre){ throw std::runtime_error("shard_index out of range"); }
-	// Shard boundaries: the even split of the simulated blocks, moved onto the first block of a sequence when one starts within 5 %
-	// of a shard's size - a shard that only holds a sliver of a sequence would still need that sequence's whole systematic-error chains.
-	{
-		std::vector<uint32_t> seq_first;
-		uint32_t fb = 0;
-		for(size_t i = 0; i < g.seqs.size(); ++i){ const uint32_t L = g.seqs[i].size(); if(L < c.insert_to){ continue; } seq_first.push_back(fb); fb += (L + 999) / 1000; }
-		const uint64_t tol = std::max<uint64_t>(1, n_sim_blocks / (20ull * shard_count_pre));
-		auto boundary = [&](uint32_t k) -> uint64_t {
-			if(k == 0){ return 0; }
-			if(k >= shard_count_pre){ return n_sim_blocks; }
-			const uint64_t even = static_cast<uint64_t>(n_sim_blocks) * k / shard_count_pre;
-			uint64_t best = even, best_d = tol + 1;
-			for(uint32_t f : seq_first){
-				const uint64_t d = f > even ? f - even : even - f;
-				if(f > 0 && f < n_sim_blocks && d < best_d){ best = f; best_d = d; }
-			}
-			return best;
-		};
-		e.shard_first = static_cast<uint32_t>(boundary(opt.shard_index));
-		e.shard_n = static_cast<uint32_t>(std::max<uint64_t>(boundary(opt.shard_index + 1), e.shard_first) - e.shard_first);
-	}
 	const uint64_t shard_lo = e.shard_first, shard_hi = static_cast<uint64_t>(e.shard_first) + e.shard_n;
 	for(size_t i = 0; i < g.seqs.size(); ++i){
 		const uint32_t L = g.seqs[i].size();
 		if(L < c.insert_to){ continue; }
 		const uint32_t nb = (L + 999) / 1000;
 		const uint64_t n_draws = 2ull * nb + (from_file ? 0ull : 4ull * L + 4ull * variant_bases(i));
-		const bool needed = shard_count_pre == 1 || (e.shard_n && first < shard_hi && shard_lo < static_cast<uint64_t>(first) + nb);
-		if(!needed && !from_file){
+		const bool needed_here = shard_count_pre == 1 || (e.shard_n && first < shard_hi && shard_lo < static_cast<uint64_t>(first) + nb);
+		if(!needed_here){
+			if(from_file){ next_record += 2; }   // the two records of this sequence stay unread
 			master_skip(e, n_draws);
 			const uint8_t *hseq = g.seqs[i].data();
 			carried = dominant_before(hseq, L, true, L, carried);
@@ -1764,8 +1856,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	ms_bias += tm.stop();
 	if(rep){ rep->ms_bias = ms_bias; rep->bias_normalization = e.norm.bias_normalization; rep->ms_syserr = ms_syserr; }
 	stage_log("prepare: device stages (bias, master stream, systematic errors)");
-	const uint32_t sc = opt.shard_count ? opt.shard_count : 1, si = opt.shard_index;
-	if(si >= sc){ throw std::runtime_error("shard_index out of range"); }
+	const uint32_t sc = shard_count_pre, si = shard_index_pre;
 	if(static_cast<uint64_t>(e.shard_first) + e.shard_n > e.n_blocks_sim){ throw std::runtime_error("internal error: shard range beyond the simulated blocks"); }
 	e.shard_has_adapter_only = (si + 1 == sc) && e.adapter_only_pairs;
 	RSQ_CUDA(cudaGetLastError());
@@ -2312,6 +2403,17 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	stage_log("simulate: copies and writer drained");
 	if(rep){ rep->ms_gather = ms_gather; }
 	fill_simulate_report(e, rep, ms_sim);
+	e.group_pairs = e.out_pairs;
+	if(e.comm){   // read pairs of the whole run: the one number the engines of a group exchange behind the data path
+		unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(e.d_totals.p);
+		unsigned long long mine = e.out_pairs;
+		RSQ_CUDA(cudaMemcpyAsync(d_cnt, &mine, 8, cudaMemcpyHostToDevice, s));
+		RSQ_NCCL(nccl_api().AllReduce(d_cnt, d_cnt, 1, ncclUint64, ncclSum, e.comm, s));
+		RSQ_CUDA(cudaMemcpyAsync(&mine, d_cnt, 8, cudaMemcpyDeviceToHost, s));
+		RSQ_CUDA(cudaStreamSynchronize(s));
+		e.group_pairs = mine;
+	}
+	if(rep){ rep->group_pairs = e.group_pairs; rep->group_world = e.comm ? e.group_world : 1; rep->shard_first = e.shard_first; }
 	stage_log("simulate: report");
 }
 
@@ -2595,6 +2697,40 @@ rsq_engine *rsq_engine_create(const rsq_profile *profile, int device){
 
 void rsq_engine_destroy(rsq_engine *engine){ if(engine){ cudaSetDevice(engine->device); delete engine; } }
 
+int rsq_group_unique_id(void *id_out, uint64_t capacity){
+	RSQ_TRY
+	if(!nccl_api().ok){ throw std::runtime_error("libnccl.so.2 could not be loaded: engines cannot be joined into a multi-GPU group"); }
+	if(capacity < sizeof(ncclUniqueId)){ throw std::runtime_error("rsq_group_unique_id: buffer too small (" + std::to_string(sizeof(ncclUniqueId)) + " bytes needed)"); }
+	ncclUniqueId id;
+	RSQ_NCCL(nccl_api().GetUniqueId(&id));
+	std::memcpy(id_out, &id, sizeof id);
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_engine_join_group(rsq_engine *engine, const void *unique_id, int rank, int world){
+	RSQ_TRY
+	if(!nccl_api().ok){ throw std::runtime_error("libnccl.so.2 could not be loaded: engines cannot be joined into a multi-GPU group"); }
+	if(world < 1 || rank < 0 || rank >= world){ throw std::runtime_error("rsq_engine_join_group: rank out of range"); }
+	RSQ_CUDA(cudaSetDevice(engine->device));
+	if(engine->comm){ nccl_api().CommDestroy(engine->comm); engine->comm = nullptr; }
+	ncclUniqueId id;
+	std::memcpy(&id, unique_id, sizeof id);
+	RSQ_NCCL(nccl_api().CommInitRank(&engine->comm, world, id, rank));
+	engine->group_rank = rank; engine->group_world = world;
+	return 0;
+	RSQ_CATCH(1)
+}
+
+int rsq_engine_leave_group(rsq_engine *engine){
+	RSQ_TRY
+	RSQ_CUDA(cudaSetDevice(engine->device));
+	if(engine->comm){ nccl_api().CommDestroy(engine->comm); engine->comm = nullptr; }
+	engine->group_rank = 0; engine->group_world = 1;
+	return 0;
+	RSQ_CATCH(1)
+}
+
 int rsq_engine_prepare(rsq_engine *engine, const rsq_reference *ref, const rsq_sim_options *opt, rsq_sim_report *report){
 	RSQ_TRY
 	RSQ_CUDA(cudaSetDevice(engine->device));
@@ -2670,6 +2806,100 @@ int rsq_simulate(const rsq_profile *profile, const rsq_reference *ref, const rsq
 	rsq_engine_destroy(e);
 	stage_log("rsq_simulate: engine destroyed");
 	return rc;
+}
+
+// Appends the file `from` to the open descriptor of `to` (64 MiB at a time); false on an I/O error.
+static bool append_file(FILE *to, const std::string &from){
+	FILE *in = std::fopen(from.c_str(), "rb");
+	if(!in){ return false; }
+	std::vector<char> buf(64u << 20);
+	bool ok = true;
+	while(ok){
+		const size_t n = std::fread(buf.data(), 1, buf.size(), in);
+		if(!n){ ok = !std::ferror(in); break; }
+		ok = std::fwrite(buf.data(), 1, n, to) == n;
+	}
+	std::fclose(in);
+	return ok;
+}
+
+int rsq_simulate_multi(const rsq_profile *profile, const rsq_reference *ref, const rsq_sim_options *opt, int n_gpus, const int *devices,
+                       const char *first_reads_path, const char *second_reads_path, rsq_sim_report *report){
+	if(n_gpus <= 1){ return rsq_simulate(profile, ref, opt, devices ? devices[0] : 0, first_reads_path, second_reads_path, report); }
+	RSQ_TRY
+	stage_log("rsq_simulate_multi: enter");
+	int have = 0;
+	if(cudaGetDeviceCount(&have) != cudaSuccess || have < n_gpus){ throw std::runtime_error("rsq_simulate_multi: " + std::to_string(n_gpus) + " CUDA devices requested, " + std::to_string(have) + " visible"); }
+	unsigned char id[128];
+	if(rsq_group_unique_id(id, sizeof id)){ throw std::runtime_error(g_last_error); }
+	// Shard 0 writes the two files themselves, the others hidden files next to them (same extension: gzip or plain is chosen by name) that are
+	// appended in shard order once everything is through - the bytes of the 1-thread run of the reference.
+	auto shard_path = [&](const char *path, int k) -> std::string {
+		if(k == 0){ return path; }
+		const std::string p = path;
+		const size_t slash = p.find_last_of('/');
+		const std::string dir = slash == std::string::npos ? "" : p.substr(0, slash + 1), base = slash == std::string::npos ? p : p.substr(slash + 1);
+		return dir + ".rsq_shard" + std::to_string(k) + "_" + base;
+	};
+	std::vector<rsq_sim_report> reps(n_gpus);
+	std::vector<std::string> errors(n_gpus);
+	std::vector<std::thread> pool;
+	for(int k = 0; k < n_gpus; ++k){
+		pool.emplace_back([&, k]{
+			const int dev = devices ? devices[k] : k;
+			rsq_engine *e = rsq_engine_create(profile, dev);
+			if(!e){ errors[k] = g_last_error; }
+			// every engine has to enter the communicator, or the others wait forever: a failed creation ends the run through the error below
+			if(e && rsq_engine_join_group(e, id, k, n_gpus)){ errors[k] = g_last_error; }
+			TextSink sinks[2];
+			const std::string p1 = shard_path(first_reads_path, k), p2 = shard_path(second_reads_path, k);
+			if(errors[k].empty()){
+				try{
+					if(!sinks[0].open(p1)){ errors[k] = "Could not open '" + p1 + "' for writing."; }
+					else if(!sinks[1].open(p2)){ errors[k] = "Could not open '" + p2 + "' for writing."; }
+				}
+				catch(const std::exception &ex){ errors[k] = ex.what(); }
+			}
+			if(e && errors[k].empty()){
+				int rc = rsq_engine_prepare(e, ref, opt, &reps[k]);
+				if(!rc){
+					e->sink_files[0] = &sinks[0]; e->sink_files[1] = &sinks[1];
+					rc = rsq_engine_simulate(e, &reps[k]);
+					e->sink_files[0] = e->sink_files[1] = nullptr;
+				}
+				if(rc){ errors[k] = g_last_error; }
+			}
+			for(int seg = 0; seg < 2; ++seg){ if(sinks[seg].is_open() && !sinks[seg].close() && errors[k].empty()){ errors[k] = "Could not write records to '" + (seg ? p2 : p1) + "'"; } }
+			if(e){ rsq_engine_destroy(e); }
+		});
+	}
+	for(auto &th : pool){ th.join(); }
+	std::string error;
+	for(int k = 0; k < n_gpus && error.empty(); ++k){ error = errors[k]; }
+	if(error.empty()){
+		const char *paths[2] = {first_reads_path, second_reads_path};
+		for(int seg = 0; seg < 2 && error.empty(); ++seg){
+			FILE *to = std::fopen(paths[seg], "ab");
+			if(!to){ error = std::string("Could not open '") + paths[seg] + "' for writing."; break; }
+			for(int k = 1; k < n_gpus && error.empty(); ++k){ if(!append_file(to, shard_path(paths[seg], k))){ error = std::string("Could not write records to '") + paths[seg] + "'"; } }
+			if(std::fclose(to) && error.empty()){ error = std::string("Could not write records to '") + paths[seg] + "'"; }
+		}
+	}
+	for(int k = 1; k < n_gpus; ++k){ remove(shard_path(first_reads_path, k).c_str()); remove(shard_path(second_reads_path, k).c_str()); }
+	if(!error.empty()){ remove(first_reads_path); remove(second_reads_path); throw std::runtime_error(error); }
+	if(report){
+		*report = reps[0];
+		for(int k = 1; k < n_gpus; ++k){
+			report->pairs += reps[k].pairs; report->bytes[0] += reps[k].bytes[0]; report->bytes[1] += reps[k].bytes[1]; report->blocks += reps[k].blocks;
+			report->positions += reps[k].positions; report->scan_draws += reps[k].scan_draws; report->kernel_launches += reps[k].kernel_launches;
+			report->ms_upload = std::max(report->ms_upload, reps[k].ms_upload); report->ms_bias = std::max(report->ms_bias, reps[k].ms_bias);
+			report->ms_syserr = std::max(report->ms_syserr, reps[k].ms_syserr); report->ms_simulate = std::max(report->ms_simulate, reps[k].ms_simulate);
+			report->ms_gather = std::max(report->ms_gather, reps[k].ms_gather); report->spec_rounds = std::max(report->spec_rounds, reps[k].spec_rounds);
+		}
+	}
+	stage_log("rsq_simulate_multi: done");
+	return 0;
+	RSQ_CATCH(1)
 }
 
 int rsq_create_systematic_error_profile(rsq_engine *engine, const rsq_reference *ref, uint64_t seed, const char *fastq_out_path){

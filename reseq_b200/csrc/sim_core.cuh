@@ -487,60 +487,79 @@ RSQ_HD uint32_t fragment_counts_alleles(const SimCtx &c, uint32_t ref_id, uint32
 // surroundings of the allele's fragment, then the count draw.  Hits with no variant of any allele within reach of the fragment and its
 // surroundings take the reference's own per-position arrays; the others are evaluated on the allele's sequence (allele_hit).
 struct VarEval {
-	uint32_t allele, end_position, counts, slow;
-	int32_t end_var; uint32_t end_var_pos;       // VariantBiasVarModifiers::EndVariant (slow hits)
+	uint32_t allele, end_position, counts;
+	uint32_t slow;                               // bit 0: the read on the forward strand walks variants, bit 1: the read on the reverse strand does
+	int32_t end_var; uint32_t end_var_pos;       // VariantBiasVarModifiers::EndVariant (when the fragment was evaluated on the allele's sequence)
 };
 // uniform(): the next ZeroToOne of the block's stream.  Returns false when the fragment does not end inside the sequence (no draw is consumed).
+// Every part falls back to the reference's own arrays when no variant of any allele lies within its reach: the fragment itself (end position, GC),
+// each of the two surroundings, each of the two reads.
 template<class Uniform>
 RSQ_HD bool eval_allele_hit(const SimCtx &c, const VariantView &v, uint32_t ref_id, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t fl,
                             uint32_t allele, double thr0, Uniform &&uniform, VarEval &e, bool &runaway){
 	const uint32_t L = c.seq_len[ref_id];
 	const uint64_t off = c.seq_off[ref_id];
 	const uint32_t *gcp = c.gc_prefix + off + ref_id;
-	e.allele = allele; e.counts = 0; e.end_var = -1; e.end_var_pos = 0;
-	const uint32_t lo = pos >= 32u ? pos - 32u : 0u;
-	const uint32_t idx = var_lower_bound(v, lo);
-	e.slow = (start_variant_pos || (idx < v.n && v.position[idx] <= pos + fl + 32u)) ? 1u : 0u;
-	uint32_t gc_perc; double sur_start, sur_end;
-	if(e.slow){
+	e.allele = allele; e.counts = 0; e.end_var = -1; e.end_var_pos = 0; e.slow = 0;
+	const uint32_t hint = var_seek(v, first_var, pos);   // first variant at or behind the start position
+	const bool in_fragment = start_variant_pos || (hint < v.n && v.position[hint] <= pos + fl);
+	uint32_t gc_perc, end_hint = hint;
+	AllelePoint end{pos + fl, 0, -1};
+	if(in_fragment){
 		AlleleHit h;
 		allele_hit(v, gcp, L, allele, pos, first_var, start_variant_pos, fl, h);
 		if(!h.valid){ return false; }
 		e.end_position = h.end_position; e.end_var = h.end_var; e.end_var_pos = h.end_var_pos;
-		gc_perc = h.gc_percent;
-		uint32_t code[3];
-		allele_start_surrounding(v, c.ref + off, L, allele, pos, first_var, start_variant_pos, code);
-		sur_start = surrounding_bias(c.var.sur_tab[0], c.var.sur_tab[1], c.var.sur_tab[2], code);
-		allele_end_surrounding(v, c.ref + off, L, allele, h.end, code);
-		sur_end = surrounding_bias(c.var.sur_tab[0], c.var.sur_tab[1], c.var.sur_tab[2], code);
+		gc_perc = h.gc_percent; end = h.end; end_hint = h.end_hint;
 	}
 	else{
 		e.end_position = pos + fl;
 		if(!(e.end_position < L)){ return false; }
 		gc_perc = percent_u32(gcp[e.end_position] - gcp[pos], fl);
-		sur_start = c.sur_start[off + pos]; sur_end = c.sur_end[off + e.end_position - 1];
+		e.end_var = static_cast<int32_t>(hint) - 1;
 	}
+	const uint32_t ep = e.end_position;
+	double sur_start, sur_end;
+	if(start_variant_pos || var_in_range(v, hint, pos >= 11u ? pos - 11u : 0u, pos + 20u)){
+		uint32_t code[3];
+		allele_start_surrounding(v, c.ref + off, L, allele, pos, first_var, start_variant_pos, code);
+		sur_start = surrounding_bias(c.var.sur_tab[0], c.var.sur_tab[1], c.var.sur_tab[2], code);
+	}
+	else{ sur_start = c.sur_start[off + pos]; }
+	if(end.k || var_in_range(v, end_hint, ep >= 22u ? ep - 22u : 0u, ep + 11u)){
+		uint32_t code[3];
+		allele_end_surrounding(v, c.ref + off, L, allele, end, code, end_hint);
+		sur_end = surrounding_bias(c.var.sur_tab[0], c.var.sur_tab[1], c.var.sur_tab[2], code);
+	}
+	else{ sur_end = c.sur_end[off + ep - 1]; }
 	const double rv = uniform();
 	const double adjusted_random = add_rn(thr0, mul_rn(rv, sub_rn(1.0, thr0)));
 	e.counts = fragment_counts_alleles(c, ref_id, fl, gc_perc, sur_start, sur_end, adjusted_random, c.var.num_alleles, runaway);
+	if(e.counts){
+		// which of the two reads has to walk variants (spliced bases, SysErrorVariant cursor): any variant of any allele within the read's bases
+		const uint32_t n_max = (c.read_len_to[0] > c.read_len_to[1] ? c.read_len_to[0] : c.read_len_to[1]) + c.max_len_deletion + 2u;
+		const uint32_t n = fl + 2u < n_max ? fl + 2u : n_max;
+		if(start_variant_pos || var_in_range(v, hint, pos, pos + n)){ e.slow |= 1u; }
+		if(end.k || e.end_var_pos || var_in_range(v, end_hint, ep >= n ? ep - n : 0u, ep)){ e.slow |= 2u; }
+	}
 	return true;
 }
 // GetOrgSeq with variants (Simulator.cpp:1909-1914): the two ends of the allele's fragment, spliced.  Lane-uniform; lane 0 stores.
 template<class G>
 RSQ_HD void splice_fragment_ends(const G &g, const SimCtx &c, const VariantView &v, uint32_t ref_id, uint32_t strand, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos,
-                                 uint32_t fl, const VarEval &e, uint8_t *frag_fwd, uint8_t *frag_rev){
+                                 uint32_t fl, const VarEval &e, uint8_t *frag_fwd, uint8_t *frag_rev, uint32_t which = 3u /* bit 0 forward end, bit 1 reverse end */){
 	g.sync();
-	if(g.lane() == 0){
-		const uint8_t *seq = c.ref + c.seq_off[ref_id];
-		uint32_t n = c.read_len_to[strand ? 1 : 0] + c.max_len_deletion;   // forward end: the read of segment `strand`
-		if(fl < n){ n = fl; }
-		if(n > c.max_org_len){ n = c.max_org_len; }
-		splice_reference(frag_fwd, seq, v, pos, n, false, static_cast<int32_t>(first_var), start_variant_pos, e.allele);
-		n = c.read_len_to[strand ? 0 : 1] + c.max_len_deletion;
-		if(fl < n){ n = fl; }
-		if(n > c.max_org_len){ n = c.max_org_len; }
-		splice_reference(frag_rev, seq, v, e.end_position, n, true, e.end_var, e.end_var_pos, e.allele);
-	}
+	const uint8_t *seq = c.ref + c.seq_off[ref_id];
+	uint32_t n_fwd = c.read_len_to[strand ? 1 : 0] + c.max_len_deletion;   // forward end: the read of segment `strand`
+	if(fl < n_fwd){ n_fwd = fl; }
+	if(n_fwd > c.max_org_len){ n_fwd = c.max_org_len; }
+	uint32_t n_rev = c.read_len_to[strand ? 0 : 1] + c.max_len_deletion;
+	if(fl < n_rev){ n_rev = fl; }
+	if(n_rev > c.max_org_len){ n_rev = c.max_org_len; }
+	if((which & 1u) && (e.slow & 1u)){ if(g.lane() == 0){ splice_reference(frag_fwd, seq, v, pos, n_fwd, false, static_cast<int32_t>(first_var), start_variant_pos, e.allele); } }
+	else if(which & 1u){ for(uint32_t i = g.lane(); i < n_fwd; i += G::kSize){ frag_fwd[i] = seq[pos + i]; } }
+	if((which & 2u) && (e.slow & 2u)){ if(g.lane() == 0){ splice_reference(frag_rev, seq, v, e.end_position, n_rev, true, e.end_var, e.end_var_pos, e.allele); } }
+	else if(which & 2u){ for(uint32_t i = g.lane(); i < n_rev; i += G::kSize){ frag_rev[i] = static_cast<uint8_t>(3u - seq[e.end_position - 1u - i]); } }
 	g.sync();
 }
 
@@ -638,8 +657,8 @@ RSQ_HD void create_reads(const G &g, const SimCtx &c, const Scratch &s, Mt &mt, 
 				org_len = stage_fragment_read(g, c, s, ref_id, seg, reversed, start_position_forward, end_position_forward, fragment_length, converted ? s.frag[reversed ? 1 : 0] : nullptr);
 			}
 			ReadState par;
-			if(vr && vr->slow && fragment_length){
-				// reads of a fragment that touches variants walk the SimBlocks' SysErrorVariants (CreateReads, Simulator.cpp:680-689)
+			if(vr && fragment_length && (vr->slow & ((seg != static_cast<uint32_t>(strand)) ? 2u : 1u))){
+				// a read with variants among its bases walks the SimBlocks' SysErrorVariants (CreateReads, Simulator.cpp:680-689)
 				const bool reversed = (seg != static_cast<uint32_t>(strand));
 				SysWalkCtx wc{};
 				wc.sys = (reversed ? c.sys_rev : c.sys_fwd) + 2 * c.seq_off[ref_id]; wc.errs = reversed ? c.var.errs_rev : c.var.errs_fwd;
@@ -1031,24 +1050,10 @@ RSQ_HD void simulate_block_var(const G &g, const SimCtx &c, const Scratch &s, Si
 					if(runaway && g.lane() == 0){ *c.error_flag |= kErrCountRunaway; }
 					if(!e.counts){ continue; }
 					const bool staged = e.slow || kMeth;
-					if(e.slow){ splice_fragment_ends(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fragment_length, e, s.frag[0], s.frag[1]); }
-					else if(kMeth){
-						const uint64_t off = c.seq_off[b.ref_id];
-						for(uint32_t rev = 0; rev < 2; ++rev){
-							const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
-							uint32_t nn = c.read_len_to[seg] + c.max_len_deletion;
-							if(fragment_length < nn){ nn = fragment_length; }
-							if(nn > c.max_org_len){ nn = c.max_org_len; }
-							g.sync();
-							for(uint32_t i = g.lane(); i < nn; i += G::kSize){
-								s.frag[rev][i] = rev ? static_cast<uint8_t>(3 - c.ref[off + e.end_position - 1 - i]) : c.ref[off + pos + i];
-							}
-							g.sync();
-						}
-					}
+					if(staged){ splice_fragment_ends(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fragment_length, e, s.frag[0], s.frag[1]); }
 					if(kMeth){
 						// CTConversion, variant overload: forward end from StartVariant, reverse end from EndVariant
-						const int32_t end_var = e.slow ? e.end_var : static_cast<int32_t>(var_lower_bound(v, e.end_position)) - 1;
+						const int32_t end_var = e.end_var;
 						for(uint32_t rev = 0; rev < 2; ++rev){
 							const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
 							uint32_t nn = c.read_len_to[seg] + c.max_len_deletion;
@@ -1215,11 +1220,13 @@ RSQ_HD void draw_variant_errors_block(const G &g, const Tables &tab, double *pro
 	uint32_t cursor = 0;
 	uint64_t r = 0;
 	bool zero;
+	SysWalk at{}; at.block = block; at.cur_var = -1;
+	sysw_refresh(w, at);
 	for(uint32_t k = 0; k < n_vars; ++k){
 		const uint32_t var = sysw_var(w, block, k);
 		const uint32_t vp = sysw_var_position(w, block, var);
 		for(; cursor < vp; ++cursor){
-			SysWalk at{block, cursor, 0, 0};
+			at.block_pos = cursor;
 			update_distances(st, sysw_entry(w, at)[1], c.reset_distance);
 		}
 		const uint32_t P = c.v.position[var];

@@ -518,14 +518,15 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 						if(g.lane() == 0){
 							ReadJob j;
 							const bool reversed = seg != hit.strand;
-							const bool staged = !adapter_only && (c.meth_loaded || (with_var && hit.slow));
+							const bool read_slow = with_var && (hit.slow & (reversed ? 2u : 1u)) != 0u;
+							const bool staged = !adapter_only && (c.meth_loaded || read_slow);
 							j.ref_id = b.ref_id; j.start_pos = adapter_only ? 0u : pos; j.end_pos = adapter_only ? 0u : (with_var ? hit.end_pos : pos + hit.fragment_length);
 							j.fragment_length = hit.fragment_length; j.block_id = b.block_id; j.flags = seg | (hit.strand << 1) | (hit.tile << 8);
 							j.read_number = read_number; j.assumed = assumed; j.consumed = kSpecOverflow; j.rec_len = 0; j.slot = slab * 32u + (p & 31u);
 							j.conv_index = staged ? static_cast<uint32_t>((static_cast<size_t>(u) * kConvSlots + hit.conv_slot) * 2u + (reversed ? 1u : 0u)) : kSpecNone;
 							j.var_id = 0; j.var_pos = 0; j.pad = 0;
 							if(with_var){
-								j.flags |= (hit.allele << 24) | (hit.slow ? 8u : 0u);
+								j.flags |= (hit.allele << 24) | (read_slow ? 8u : 0u);
 								j.var_id = reversed ? hit.end_var : static_cast<int32_t>(first_var); j.var_pos = reversed ? hit.end_var_pos : start_variant_pos;
 							}
 							jobs[emitted] = j;
@@ -555,21 +556,10 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 						if(e.slow || c.meth_loaded){
 							hit.conv_slot = hit.conv_next; hit.conv_next = (hit.conv_next + 1u) % kConvSlots;
 							uint8_t *frag0 = sp.conv + ((static_cast<size_t>(u) * kConvSlots + hit.conv_slot) * 2u) * kMaxOrgLen, *frag1 = frag0 + kMaxOrgLen;
-							if(e.slow){ splice_fragment_ends(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fl, e, frag0, frag1); }
-							else{
-								for(uint32_t rev = 0; rev < 2; ++rev){
-									const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
-									const uint32_t n = fragment_org_len(c, seg, fl);
-									uint8_t *frag = rev ? frag1 : frag0;
-									g.sync();
-									for(uint32_t i = g.lane(); i < n; i += G::kSize){
-										frag[i] = rev ? static_cast<uint8_t>(3 - c.ref[off + e.end_position - 1 - i]) : c.ref[off + pos + i];
-									}
-									g.sync();
-								}
-							}
+							// the ends whose reads walk variants are spliced; with methylation both ends are staged for the conversion
+							splice_fragment_ends(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fl, e, frag0, frag1, c.meth_loaded ? 3u : e.slow);
 							if(c.meth_loaded){
-								const int32_t end_var = e.slow ? e.end_var : static_cast<int32_t>(var_lower_bound(v, e.end_position)) - 1;
+								const int32_t end_var = e.end_var;
 								for(uint32_t rev = 0; rev < 2; ++rev){
 									const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
 									RingSource rng{ring};
@@ -802,7 +792,7 @@ template<bool kVar> struct ReadMachineT {
 	// per step
 	uint32_t ref_base, dom_error, indel;
 	// fragments touching variants: GetSysErrorFromBlock cursor over the SimBlocks' SysErrorVariants instead of sys[]
-	uint32_t var_slow, allele, var_ref_id, var_reversed; SysWalk walk;
+	uint32_t var_slow, allele, var_ref_id, var_reversed; SysWalk walk; const uint8_t *walk_sys;
 	RSQ_HD SysWalkCtx walk_ctx(const SimCtx &c) const {
 		SysWalkCtx wc;
 		wc.sys = (var_reversed ? c.sys_rev : c.sys_fwd) + 2 * c.seq_off[var_ref_id]; wc.errs = var_reversed ? c.var.errs_rev : c.var.errs_fwd;
@@ -841,12 +831,13 @@ template<bool kVar> struct ReadMachineT {
 	RSQ_HD void gc_and_error(const SimCtx &c, uint32_t n, uint32_t &mean_error_rate){
 		uint32_t gc = 0, err = 0;
 		if(kVar && var_slow){
-			const SysWalkCtx wc = walk_ctx(c);
 			SysWalk pre = walk;
 			for(uint32_t i = 0; i < n; ++i){
 				const uint32_t b = org_base(i);
 				gc += (b == 1 || b == 2) ? 1u : 0u;
-				err += sysw_next(wc, pre, allele) >> 8;
+				uint32_t e;
+				if(!sysw_plain_step(walk_sys, pre, e)){ const SysWalkCtx wc = walk_ctx(c); e = sysw_next(wc, pre, allele); }
+				err += e >> 8;
 			}
 		}
 		else{
@@ -866,7 +857,7 @@ template<bool kVar> struct ReadMachineT {
 		words = slice; k = 0; kcap = j.assumed + sp.margin < sp.words_per_job ? j.assumed + sp.margin : sp.words_per_job; overflow = 0;
 		load_window();
 		seg = j.flags & 1u; tile = (j.flags >> 8) & 0xffffu; fragment_length = j.fragment_length;
-		allele = (j.flags >> 24) & 0x7fu; var_slow = 0; var_ref_id = 0; var_reversed = 0; walk = SysWalk{0, 0, 0, 0};
+		allele = (j.flags >> 24) & 0x7fu; var_slow = 0; var_ref_id = 0; var_reversed = 0; walk = SysWalk{}; walk_sys = nullptr;
 		const bool strand = (j.flags >> 1) & 1u;
 		id = reinterpret_cast<char *>(slot + 16); id_cap = static_cast<int>(sp.id_cap); cigar_len = 0;
 		seq_out = slot + sp.seq_off; qual_out = slot + sp.qual_off;
@@ -923,6 +914,7 @@ template<bool kVar> struct ReadMachineT {
 			if(kVar && (j.flags & 8u)){   // CreateReads with variants (Simulator.cpp:680-689): where this read starts in the block chain of its strand
 				var_slow = 1; var_ref_id = j.ref_id; var_reversed = reversed ? 1u : 0u;
 				const SysWalkCtx wc = walk_ctx(c);
+				walk_sys = wc.sys;
 				walk = reversed ? sysw_reverse_start(wc, j.start_pos / 1000u, j.end_pos, j.var_id, j.var_pos) : sysw_forward_start(wc, j.start_pos / 1000u, j.start_pos, static_cast<uint32_t>(j.var_id), j.var_pos);
 			}
 		}
@@ -1041,7 +1033,11 @@ RSQ_HD void run_read_machine(const SimCtx &c, const SpecCtx &sp, bool have_job, 
 		const bool q_any = q_part || m.phase == kPhTail || m.phase == kPhOverrun;
 		uint32_t t2 = 0; double u2 = 0.0;
 		if(part && indel == 0u){
-			if(kVar && m.var_slow){ const SysWalkCtx wc = m.walk_ctx(c); const uint32_t e = sysw_next(wc, m.walk, m.allele); m.dom_error = e & 0xffu; m.error_rate = e >> 8; }
+			if(kVar && m.var_slow){
+				uint32_t e;
+				if(!sysw_plain_step(m.walk_sys, m.walk, e)){ const SysWalkCtx wc = m.walk_ctx(c); e = sysw_next(wc, m.walk, m.allele); }
+				m.dom_error = e & 0xffu; m.error_rate = e >> 8;
+			}
 			else{
 				m.dom_error = m.sys[2 * m.org_pos];
 				m.error_rate = m.sys[2 * m.org_pos + 1];

@@ -263,6 +263,17 @@ RSQ_HD uint32_t var_lower_bound(const VariantView &v, uint32_t p){   // first va
 	while(lo < hi){ const uint32_t mid = lo + (hi - lo) / 2; if(v.position[mid] < p){ lo = mid + 1; } else{ hi = mid; } }
 	return lo;
 }
+// The same from a nearby index (the scan always has one: the first variant at or behind the start position): a few steps instead of a search
+RSQ_HD uint32_t var_seek(const VariantView &v, uint32_t hint, uint32_t p){
+	if(hint > v.n){ hint = v.n; }
+	while(hint > 0 && v.position[hint - 1] >= p){ --hint; }
+	while(hint < v.n && v.position[hint] < p){ ++hint; }
+	return hint;
+}
+RSQ_HD bool var_in_range(const VariantView &v, uint32_t hint, uint32_t lo, uint32_t hi){   // any variant with lo <= position <= hi
+	const uint32_t i = var_seek(v, hint, lo);
+	return i < v.n && v.position[i] <= hi;
+}
 // The variant of `allele` at reference position p (one per position and allele), or -1.  vi: any index <= the first variant at p; left at the first variant with position >= p.
 RSQ_HD int32_t allele_variant_at(const VariantView &v, uint32_t &vi, uint32_t p, uint32_t allele){
 	while(vi < v.n && v.position[vi] < p){ ++vi; }
@@ -312,36 +323,51 @@ RSQ_HD void next_start_pass(const VariantView &v, uint32_t pos, uint32_t &first_
 struct AllelePoint { uint32_t p; uint32_t k; int32_t ins; };
 
 // The next n bases of the allele behind the point.  Beyond the sequence end the reference rolls around into its own first bases and ignores
-// variants there (Simulator.cpp:1601, 1706).
-RSQ_HD void allele_bases_forward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out){
+// variants there (Simulator.cpp:1601, 1706).  hint: an index near the first variant at or behind the point.
+RSQ_HD void allele_bases_forward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint = 0){
 	uint32_t i = 0, p = at.p;
 	if(at.k){
 		for(uint32_t j = at.k; j < v.length(at.ins) && i < n; ++j){ out[i++] = v.base(at.ins, j); }
 		++p;
 	}
-	uint32_t vi = var_lower_bound(v, p);
+	uint32_t vi = var_seek(v, hint, p);
 	while(i < n){
 		if(p >= L){ out[i++] = seq[(p - L) % L]; ++p; continue; }
+		// reference bases up to the next position that carries a variant of any allele
+		const uint32_t q = vi < v.n ? v.position[vi] : L;
+		uint32_t run = (q < L ? q : L) - p;
+		if(run > n - i){ run = n - i; }
+		for(uint32_t k = 0; k < run; ++k){ out[i + k] = seq[p + k]; }
+		i += run; p += run;
+		if(i >= n || p >= L){ continue; }
 		const int32_t t = allele_variant_at(v, vi, p, allele);
 		if(t < 0){ out[i++] = seq[p]; }
 		else{ for(uint32_t j = 0; j < v.length(t) && i < n; ++j){ out[i++] = v.base(t, j); } }
 		++p;
+		while(vi < v.n && v.position[vi] < p){ ++vi; }
 	}
 }
 // The n bases of the allele in front of the point, nearest first.  In front of the sequence start: the reference's last bases, variants ignored.
-RSQ_HD void allele_bases_backward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out){
+RSQ_HD void allele_bases_backward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint = 0){
 	uint32_t i = 0;
 	if(at.k){ for(uint32_t j = at.k; j-- > 0 && i < n; ){ out[i++] = v.base(at.ins, j); } }
 	int64_t q = static_cast<int64_t>(at.p) - 1;
-	uint32_t vi = var_lower_bound(v, at.p);   // one behind the last variant with position < p
+	uint32_t vi = var_seek(v, hint, at.p);   // one behind the last variant with position < p
 	while(i < n){
 		if(q < 0){ out[i++] = seq[static_cast<uint32_t>((static_cast<int64_t>(L) + q % static_cast<int64_t>(L)) % static_cast<int64_t>(L))]; --q; continue; }
-		while(vi > 0 && v.position[vi - 1] > static_cast<uint32_t>(q)){ --vi; }
+		// reference bases down to the next lower position that carries a variant of any allele
+		const int64_t vq = vi > 0 ? static_cast<int64_t>(v.position[vi - 1]) : -1;
+		uint32_t run = static_cast<uint32_t>(q - vq);
+		if(run > n - i){ run = n - i; }
+		for(uint32_t k = 0; k < run; ++k){ out[i + k] = seq[q - k]; }
+		i += run; q -= run;
+		if(i >= n || q < 0){ continue; }
 		int32_t t = -1;
 		for(uint32_t u = vi; u > 0 && v.position[u - 1] == static_cast<uint32_t>(q); --u){ if(v.in_allele(u - 1, allele)){ t = static_cast<int32_t>(u - 1); break; } }
 		if(t < 0){ out[i++] = seq[q]; }
 		else{ for(uint32_t j = v.length(t); j-- > 0 && i < n; ){ out[i++] = v.base(t, j); } }
 		--q;
+		while(vi > 0 && static_cast<int64_t>(v.position[vi - 1]) > q){ --vi; }
 	}
 }
 
@@ -354,6 +380,7 @@ struct AlleleHit {
 	int32_t end_var; uint32_t end_var_pos;   // EndVariant: {id, posCurrentlyAt}
 	AllelePoint end;                  // the point behind the fragment's last base
 	uint32_t valid;                   // the fragment ends inside the sequence (cur_end_position < SequenceLength)
+	uint32_t end_hint;                // an index near the first variant at or behind end_position
 };
 RSQ_HD uint32_t count_gc_bases(const VariantView &v, uint32_t var, uint32_t from, uint32_t to){
 	uint32_t gc = 0;
@@ -382,7 +409,8 @@ RSQ_HD void allele_hit(const VariantView &v, const uint32_t *gcp, uint32_t L, ui
 			if(1 == fl){ h.end_var = static_cast<int32_t>(first_var); h.end_var_pos = start_variant_pos + 1; inside = true; }
 		}
 	}
-	uint32_t vi = var_lower_bound(v, p);
+	uint32_t vi = var_seek(v, first_var, p);
+	h.end_hint = vi;
 	while(!done){
 		// the allele's next variant at or behind p
 		uint32_t t = vi;
@@ -392,7 +420,7 @@ RSQ_HD void allele_hit(const VariantView &v, const uint32_t *gcp, uint32_t L, ui
 		if(consumed + seg >= fl){
 			const uint32_t k = fl - consumed;
 			gc += gcp[p + k] - gcp[p];
-			h.end_position = p + k; h.end = AllelePoint{p + k, 0, -1};
+			h.end_position = p + k; h.end = AllelePoint{p + k, 0, -1}; h.end_hint = t;
 			break;
 		}
 		if(q >= L){ return; }   // runs off the sequence
@@ -405,6 +433,7 @@ RSQ_HD void allele_hit(const VariantView &v, const uint32_t *gcp, uint32_t L, ui
 			h.end_position = q + 1;
 			if(take < len){ h.end = AllelePoint{q, take, static_cast<int32_t>(t)}; h.end_var = static_cast<int32_t>(t); h.end_var_pos = take; inside = true; }
 			else{ h.end = AllelePoint{q + 1, 0, -1}; }
+			h.end_hint = t;
 			break;
 		}
 		p = q + 1;
@@ -414,7 +443,8 @@ RSQ_HD void allele_hit(const VariantView &v, const uint32_t *gcp, uint32_t L, ui
 	if(h.end_position >= L){ return; }
 	h.valid = 1;
 	h.gc_percent = ((gc * 100u + fl / 2u) / fl) & 0xffu;   // utilities::Percent on uintSeqLen into uintPercent
-	if(!inside){ h.end_var = static_cast<int32_t>(var_lower_bound(v, h.end_position)) - 1; h.end_var_pos = 0; }
+	h.end_hint = var_seek(v, h.end_hint, h.end_position);
+	if(!inside){ h.end_var = static_cast<int32_t>(h.end_hint) - 1; h.end_var_pos = 0; }
 }
 
 RSQ_HD uint32_t pack_10mer(const uint8_t *b){ uint32_t s = 0; for(uint32_t k = 0; k < 10; ++k){ s = (s << 2) + (b[k] & 3u); } return s; }
@@ -422,15 +452,15 @@ RSQ_HD uint32_t pack_10mer(const uint8_t *b){ uint32_t s = 0; for(uint32_t k = 0
 RSQ_HD void allele_start_surrounding(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t code[3]){
 	uint8_t w[30], back[10];
 	const AllelePoint at{pos, start_variant_pos, start_variant_pos ? static_cast<int32_t>(first_var) : -1};
-	allele_bases_backward(v, seq, L, allele, at, 10, back);
+	allele_bases_backward(v, seq, L, allele, at, 10, back, first_var);
 	for(uint32_t k = 0; k < 10; ++k){ w[k] = back[9 - k]; }
-	allele_bases_forward(v, seq, L, allele, at, 20, w + 10);
+	allele_bases_forward(v, seq, L, allele, at, 20, w + 10, first_var);
 	code[0] = pack_10mer(w); code[1] = pack_10mer(w + 10); code[2] = pack_10mer(w + 20);
 }
-RSQ_HD void allele_end_surrounding(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, const AllelePoint &end, uint32_t code[3]){
+RSQ_HD void allele_end_surrounding(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, const AllelePoint &end, uint32_t code[3], uint32_t hint = 0){
 	uint8_t w[30], fwd[10], back[20];
-	allele_bases_forward(v, seq, L, allele, end, 10, fwd);
-	allele_bases_backward(v, seq, L, allele, end, 20, back);
+	allele_bases_forward(v, seq, L, allele, end, 10, fwd, hint);
+	allele_bases_backward(v, seq, L, allele, end, 20, back, hint);
 	for(uint32_t k = 0; k < 10; ++k){ w[k] = 3u - fwd[9 - k]; }
 	for(uint32_t k = 0; k < 20; ++k){ w[10 + k] = 3u - back[k]; }
 	code[0] = pack_10mer(w); code[1] = pack_10mer(w + 10); code[2] = pack_10mer(w + 20);
@@ -448,23 +478,47 @@ struct SysWalkCtx {
 	VariantView v;
 	uint32_t L; uint32_t reverse;
 };
-struct SysWalk { uint32_t block, block_pos; int32_t cur_var; uint32_t var_pos; };   // block, block_pos, cur_var, var_pos of the reference
+// block, block_pos, cur_var, var_pos of the reference + what a step needs of the current block: its size, the index of its first entry in the
+// strand's array and the position of err_variants_[cur_var] (0xffffffff: none left) - refreshed whenever block or cur_var change, so that the
+// steps between variants (nearly all of them) cost one load like a run without variants
+struct SysWalk { uint32_t block, block_pos; int32_t cur_var; uint32_t var_pos; uint32_t size, next_bp; uint64_t base_idx; };
 
 RSQ_HD uint32_t sysw_block_end(const SysWalkCtx &c, uint32_t b){ const uint64_t e = 1000ull * (b + 1ull); return e < c.L ? static_cast<uint32_t>(e) : c.L; }
 RSQ_HD uint32_t sysw_block_size(const SysWalkCtx &c, uint32_t b){ return sysw_block_end(c, b) - 1000u * b; }
-RSQ_HD const uint8_t *sysw_entry(const SysWalkCtx &c, const SysWalk &w){   // block->sys_errors_.at(block_pos)
-	const uint64_t idx = c.reverse ? static_cast<uint64_t>(c.L - sysw_block_end(c, w.block)) + w.block_pos : 1000ull * w.block + w.block_pos;
-	return c.sys + 2ull * idx;
-}
 RSQ_HD uint32_t sysw_n_vars(const SysWalkCtx &c, uint32_t b){ return c.block_first[b + 1] - c.block_first[b]; }
 RSQ_HD uint32_t sysw_var(const SysWalkCtx &c, uint32_t b, uint32_t k){ return c.reverse ? c.block_first[b + 1] - 1u - k : c.block_first[b] + k; }   // err_variants_.at(k)
 RSQ_HD uint32_t sysw_var_position(const SysWalkCtx &c, uint32_t b, uint32_t var){ return c.reverse ? sysw_block_end(c, b) - 1u - c.v.position[var] : c.v.position[var] - 1000u * b; }
+RSQ_HD void sysw_refresh_var(const SysWalkCtx &c, SysWalk &w){
+	w.next_bp = 0xffffffffu;
+	if(w.size != 0xffffffffu && w.cur_var >= 0 && static_cast<uint32_t>(w.cur_var) < sysw_n_vars(c, w.block)){
+		w.next_bp = sysw_var_position(c, w.block, sysw_var(c, w.block, static_cast<uint32_t>(w.cur_var)));
+	}
+}
+RSQ_HD void sysw_refresh(const SysWalkCtx &c, SysWalk &w){
+	const uint32_t n_blocks = (c.L + 999u) / 1000u;
+	if(w.block >= n_blocks){ w.size = 0xffffffffu; w.base_idx = 0; w.next_bp = 0xffffffffu; return; }   // block->next_block_ == NULL: nothing is read behind the chain
+	w.size = sysw_block_size(c, w.block);
+	w.base_idx = c.reverse ? static_cast<uint64_t>(c.L - sysw_block_end(c, w.block)) : 1000ull * w.block;
+	sysw_refresh_var(c, w);
+}
+RSQ_HD const uint8_t *sysw_entry(const SysWalkCtx &c, const SysWalk &w){   // block->sys_errors_.at(block_pos)
+	return c.sys + 2ull * (w.base_idx + w.block_pos);
+}
 RSQ_HD void sysw_increment(const SysWalkCtx &c, SysWalk &w){   // IncrementBlockPos (cur_var advanced by the caller where the reference passes ++cur_var)
-	if(sysw_block_size(c, w.block) <= ++w.block_pos){ w.block = c.reverse ? w.block - 1u : w.block + 1u; w.block_pos = 0; w.cur_var = 0; }
+	if(w.size <= ++w.block_pos){ w.block = c.reverse ? w.block - 1u : w.block + 1u; w.block_pos = 0; w.cur_var = 0; sysw_refresh(c, w); }
+}
+// One step between variants: sys: the strand's array (SysWalkCtx::sys).  Returns false when the step has to look at a variant (sysw_next).
+RSQ_HD bool sysw_plain_step(const uint8_t *sys, SysWalk &w, uint32_t &res){
+	if(w.var_pos || w.block_pos >= w.next_bp || w.block_pos + 1u >= w.size){ return false; }
+	const uint8_t *e = sys + 2ull * (w.base_idx + w.block_pos);
+	res = e[0] | (static_cast<uint32_t>(e[1]) << 8);
+	++w.block_pos;
+	return true;
 }
 // returns dominant error | rate << 8
 RSQ_HD uint32_t sysw_next(const SysWalkCtx &c, SysWalk &w, uint32_t allele){
 	uint32_t res = 0;
+	if(sysw_plain_step(c.sys, w, res)){ return res; }
 	bool no_variant = true;
 	if(w.var_pos){
 		no_variant = false;
@@ -478,7 +532,7 @@ RSQ_HD uint32_t sysw_next(const SysWalkCtx &c, SysWalk &w, uint32_t allele){
 		}
 	}
 	else{
-		while(static_cast<uint32_t>(w.cur_var) < sysw_n_vars(c, w.block) && w.cur_var >= 0){
+		while(w.cur_var >= 0 && static_cast<uint32_t>(w.cur_var) < sysw_n_vars(c, w.block)){
 			const uint32_t var = sysw_var(c, w.block, static_cast<uint32_t>(w.cur_var));
 			if(!(sysw_var_position(c, w.block, var) <= w.block_pos)){ break; }
 			if(c.v.in_allele(var, allele)){
@@ -508,6 +562,7 @@ RSQ_HD uint32_t sysw_next(const SysWalkCtx &c, SysWalk &w, uint32_t allele){
 		res = e[0] | (static_cast<uint32_t>(e[1]) << 8);
 		sysw_increment(c, w);
 	}
+	sysw_refresh_var(c, w);
 	return res;
 }
 // FillReadPart's deletion branch: the error rate of sys_errors_[block_pos], then the position advances without looking at the variants
@@ -517,7 +572,7 @@ RSQ_HD uint32_t sysw_deletion(const SysWalkCtx &c, SysWalk &w){
 		const uint32_t var = sysw_var(c, w.block, static_cast<uint32_t>(w.cur_var));
 		if(++w.var_pos >= c.v.length(var)){ w.var_pos = 0; }
 	}
-	if(0 == w.var_pos && sysw_block_size(c, w.block) <= ++w.block_pos){ w.block = c.reverse ? w.block - 1u : w.block + 1u; w.block_pos = 0; w.cur_var = 0; }
+	if(0 == w.var_pos && w.size <= ++w.block_pos){ w.block = c.reverse ? w.block - 1u : w.block + 1u; w.block_pos = 0; w.cur_var = 0; sysw_refresh(c, w); }
 	return rate;
 }
 // CreateReads (Simulator.cpp:653-689): where the two reads of a fragment start in the block chains.  start_var / end_var: StartVariant / EndVariant.
@@ -525,6 +580,7 @@ RSQ_HD SysWalk sysw_forward_start(const SysWalkCtx &c, uint32_t start_block, uin
 	SysWalk w;
 	w.block = start_block; w.block_pos = pos - 1000u * start_block;
 	w.cur_var = static_cast<int32_t>(first_var) - static_cast<int32_t>(c.block_first[start_block]); w.var_pos = start_variant_pos;
+	sysw_refresh(c, w);
 	return w;
 }
 RSQ_HD SysWalk sysw_reverse_start(const SysWalkCtx &c, uint32_t start_block, uint32_t end_position, int32_t end_var, uint32_t end_var_pos){
@@ -534,6 +590,7 @@ RSQ_HD SysWalk sysw_reverse_start(const SysWalkCtx &c, uint32_t start_block, uin
 	w.block = b; w.block_pos = sysw_block_end(c, b) - end_position;
 	w.cur_var = static_cast<int32_t>(c.block_first[b + 1]) - 1 - end_var;
 	w.var_pos = end_var_pos ? c.v.length(static_cast<uint32_t>(end_var)) - end_var_pos : 0u;
+	sysw_refresh(c, w);
 	return w;
 }
 

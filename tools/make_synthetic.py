@@ -52,6 +52,56 @@ def gen_reference(sizes, seed, n_rate=0.0):
     return seqs
 
 
+def write_vcf(path, names, seqs, seed, snp_rate=1e-3, indel_rate=1e-4, max_indel=20, ploidy=2):
+    """Phased diploid VCF for a synthetic reference (BASELINE config C5: 1 SNP per kb, 1 indel of <= 20 bases per 10 kb, 2 alleles): records
+    at least 32 bases apart, genotypes 0|1, 1|0 or 1|1, insertions and deletions in equal shares.  Returns the number of records."""
+    rng = np.random.default_rng(seed)
+    n_rec = 0
+    with open(path, "w") as f:
+        f.write("##fileformat=VCFv4.2\n##source=reseq_b200 tools/make_synthetic.py\n")
+        for name, s in zip(names, seqs):
+            f.write(f"##contig=<ID={name},length={len(s)}>\n")
+        f.write('##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts0\n')
+        gts = ["0|1", "1|0", "1|1"] if ploidy == 2 else ["1"]
+        for name, s in zip(names, seqs):
+            L = len(s)
+            n = int(L * (snp_rate + indel_rate))
+            pos = np.unique(rng.integers(1, max(2, (L - 64) // 32), size=n)) * 32   # sorted, >= 32 apart
+            kinds = rng.random(len(pos)) < indel_rate / (snp_rate + indel_rate)
+            lens = rng.integers(1, max_indel + 1, size=len(pos))
+            ins = rng.random(len(pos)) < 0.5
+            alt_idx = rng.integers(1, 4, size=len(pos))
+            gt_idx = rng.integers(0, len(gts), size=len(pos))
+            ins_bases = rng.integers(0, 4, size=int(lens[kinds & ins].sum()) + 1)
+            ib = 0
+            out = []
+            for k in range(len(pos)):
+                p = int(pos[k])
+                ref = s[p]
+                if ref == "N":
+                    continue
+                if not kinds[k]:
+                    alt = "ACGT"[("ACGT".index(ref) + int(alt_idx[k])) % 4]
+                    out.append(f"{name}\t{p + 1}\t.\t{ref}\t{alt}\t40\tPASS\t.\tGT\t{gts[gt_idx[k]]}\n")
+                elif ins[k]:
+                    n_ins = int(lens[k])
+                    alt = ref + "".join("ACGT"[b] for b in ins_bases[ib:ib + n_ins])
+                    ib += n_ins
+                    out.append(f"{name}\t{p + 1}\t.\t{ref}\t{alt}\t40\tPASS\t.\tGT\t{gts[gt_idx[k]]}\n")
+                else:
+                    refd = s[p:p + 1 + int(lens[k])]
+                    if "N" in refd or len(refd) < 2:
+                        continue
+                    out.append(f"{name}\t{p + 1}\t.\t{refd}\t{ref}\t40\tPASS\t.\tGT\t{gts[gt_idx[k]]}\n")
+                if len(out) >= 100000:
+                    f.write("".join(out))
+                    n_rec += len(out)
+                    out = []
+            f.write("".join(out))
+            n_rec += len(out)
+    return n_rec
+
+
 def write_fasta(path, seqs, prefix="synth"):
     with open(path, "w") as f:
         for i, s in enumerate(seqs):

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--profile", default=None, help="golden profile base name (tests/golden/<name>.flat.xz), e.g. profile250; default: the bench profile")
     ap.add_argument("--methylation", action="store_true", help="bisulfite run: one unmethylated region of ~600 bp per 10 kb, methylation ~ U(0,1) (BASELINE config C4)")
+    ap.add_argument("--vcf", action="store_true", help="variant run (BASELINE config C5): phased diploid VCF with 1 SNP per kb and 1 indel (<= 20 bases) per 10 kb")
     ap.add_argument("--gz", action="store_true", help="with --files: .fq.gz output names (device-side gzip)")
     ap.add_argument("--files", action="store_true", help="drop-in call rsq_simulate (text streamed through the writer thread; set RSQ_DISCARD_OUTPUT=1 for runs larger than the disk)")
     args = ap.parse_args()
@@ -38,6 +39,13 @@ def main():
         t0 = time.perf_counter()
         seqs = make_synthetic.gen_reference(sizes, 4321)
         ref = rb.Reference.from_memory([f"chr{i + 1} synthetic" for i in range(len(seqs))], [s.encode() for s in seqs])
+        n_variants = 0
+        if args.vcf:
+            vcf = os.path.join(tmp, f"var_{mbp}.vcf")
+            n_variants = make_synthetic.write_vcf(vcf, [f"chr{i + 1}" for i in range(len(seqs))], seqs, 77)
+            t_v = time.perf_counter()
+            ref.load_variants(vcf)
+            print(json.dumps({"vcf_records": n_variants, "load_variants_s": round(time.perf_counter() - t_v, 2)}), flush=True)
         if args.methylation:
             import random
             rnd = random.Random(9)
@@ -59,7 +67,7 @@ def main():
             sizes_on_disk = [os.path.getsize(o) for o in out]
             for o in out:
                 os.remove(o)
-            print(json.dumps({"mbp": mbp, "seqs": args.seqs, "coverage": args.coverage, "profile": args.profile or bench.PROFILE, "methylation": args.methylation, "gz": args.gz, "gen_ref_s": round(t_gen, 1), "wall_rsq_simulate_s": round(wall, 2),
+            print(json.dumps({"mbp": mbp, "seqs": args.seqs, "coverage": args.coverage, "profile": args.profile or bench.PROFILE, "methylation": args.methylation, "vcf_records": n_variants, "gz": args.gz, "gen_ref_s": round(t_gen, 1), "wall_rsq_simulate_s": round(wall, 2),
                               "pairs_per_s_e2e": round(rep["pairs"] / wall), "bytes_on_disk": sizes_on_disk, "report": rep}), flush=True)
             continue
         for _ in range(args.repeat):
@@ -70,7 +78,7 @@ def main():
             t2 = time.perf_counter()
             rep = eng.download().as_dict()
             t3 = time.perf_counter()
-            rec = {"mbp": mbp, "seqs": args.seqs, "coverage": args.coverage, "gen_ref_s": round(t_gen, 1), "wall_prepare_s": round(t1 - t0, 3),
+            rec = {"mbp": mbp, "seqs": args.seqs, "coverage": args.coverage, "vcf_records": n_variants, "gen_ref_s": round(t_gen, 1), "wall_prepare_s": round(t1 - t0, 3),
                    "wall_simulate_s": round(t2 - t1, 3), "wall_download_s": round(t3 - t2, 3), "pairs_per_s_e2e": round(rep["pairs"] / (t3 - t0)),
                    "pairs_per_s_device": round(rep["pairs"] / ((rep["ms_syserr"] + rep["ms_simulate"] + rep["ms_gather"]) / 1e3)), "report": rep}
             if best is None or rec["pairs_per_s_e2e"] > best["pairs_per_s_e2e"]:
