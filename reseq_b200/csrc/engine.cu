@@ -531,8 +531,7 @@ __global__ void k_spec_init(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32
 }
 
 template<bool kVar>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_spec_scan(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){
+__device__ __forceinline__ void spec_scan_body(const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){
 	__shared__ uint64_t rings[kWarpsPerCta][2 * kMtN];
 	extern __shared__ __align__(16) unsigned char scan_dyn[];   // runs with variants: 2 * num_alleles chosen (allele, strand) ids per warp
 	WarpGroup g;
@@ -541,6 +540,14 @@ k_spec_scan(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, u
 	if(u >= unit_end){ return; }
 	scan_window<kVar>(g, c, sp, descs, first_desc, u, rings[warp], reinterpret_cast<uint16_t *>(scan_dyn) + static_cast<size_t>(warp) * sp.chosen_stride);
 }
+// The two contexts are __grid_constant__: the out-of-line helpers (snapshots, read plans, allele evaluation ...) take them by reference straight from
+// the constant bank instead of forcing a 1 KB copy into local memory; out of line they are because the scan's code has to stay within the
+// instruction cache (with everything inlined the variant instantiation was 384 KB of SASS and stalled on instruction fetches).
+template<bool kVar> __global__ void k_spec_scan(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end);
+template<> __global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_spec_scan<false>(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){ spec_scan_body<false>(c, sp, descs, first_desc, unit_first, unit_end); }
+template<> __global__ void __launch_bounds__(kWarpsPerCta * 32, 5)   // 96 registers: 20 warps per SM
+k_spec_scan<true>(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){ spec_scan_body<true>(c, sp, descs, first_desc, unit_first, unit_end); }
 
 // LogArrayResult::Draw for up to 32 independent reads at once (lanes 0 .. n_rows-1 own one read each).  The likelihood
 // products of every read are computed cooperatively (the lanes of a group of 8/16/32 take consecutive candidates of one
@@ -710,8 +717,7 @@ k_sys_chunks_lanes(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_
 // Few reads per warp = short latency per round (small genomes), 32 = fewest instructions per read (large ones).
 constexpr int kSpecReadWarps = 4;
 template<bool kVar>
-__global__ void __launch_bounds__(kSpecReadWarps * 32)
-k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){
+__device__ __forceinline__ void spec_reads_body(const SimCtx &c, const SpecCtx &sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){
 	extern __shared__ __align__(16) unsigned char smem[];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	double *buf = reinterpret_cast<double *>(smem) + static_cast<size_t>(warp) * lanes_per_warp * stride;
@@ -743,6 +749,11 @@ k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uin
 	run_read_machine<kVar>(c, sp, have, job, slice, slot, draw_fn, any_fn, consumed, rec_len);
 	if(have){ sp.jobs[gidx].consumed = consumed; sp.jobs[gidx].rec_len = rec_len; }
 }
+template<bool kVar> __global__ void k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end);
+template<> __global__ void __launch_bounds__(kSpecReadWarps * 32)
+k_spec_reads<false>(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){ spec_reads_body<false>(c, sp, stride, lanes_per_warp, unit_first, unit_end); }
+template<> __global__ void __launch_bounds__(kSpecReadWarps * 32, 5)
+k_spec_reads<true>(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){ spec_reads_body<true>(c, sp, stride, lanes_per_warp, unit_first, unit_end); }
 
 // FASTQ text of one (unit, segment): walks the unit's slab chain, a warp assembles one record at a time.
 __global__ void __launch_bounds__(128)
@@ -1570,6 +1581,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		e.d_var_errs_fwd.alloc(2 * fv.bases.size() + 2); e.d_var_errs_fwd.zero(s); e.d_var_errs_rev.alloc(2 * fv.bases.size() + 2); e.d_var_errs_rev.zero(s);
 		RSQ_CUDA(cudaStreamSynchronize(s));   // vctx is a local
 		c.var.loaded = 1; c.var.num_alleles = e.num_alleles;
+		if(const char *env = getenv("RSQ_VAR_PROBE")){ if(std::string(env) == "plain"){ c.var.loaded |= 2u; } }   // timing probe (wrong output): see eval_allele_hit
 		c.var.seq_first = e.d_var_seq_first.p; c.var.position = e.d_var_position.p; c.var.bases_off = e.d_var_bases_off.p; c.var.bases = e.d_var_bases.p;
 		c.var.allele_lo = e.d_var_allele_lo.p; c.var.allele_hi = e.d_var_allele_hi.p; c.var.errs_fwd = e.d_var_errs_fwd.p; c.var.errs_rev = e.d_var_errs_rev.p;
 		c.var.block_first = e.d_var_block_first.p; c.var.block_first_off = e.d_var_block_first_off.p;

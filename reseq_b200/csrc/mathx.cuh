@@ -16,9 +16,11 @@
 #if defined(__CUDACC__)
 #define RSQ_HD __host__ __device__ __forceinline__
 #define RSQ_HD_NOINLINE __host__ __device__
+#define RSQ_HD_COLD __host__ __device__ __forceinline__   // (out-of-line variants of these were measured: slower - call overhead and spills outweigh the smaller code)
 #else
 #define RSQ_HD inline
 #define RSQ_HD_NOINLINE
+#define RSQ_HD_COLD inline __attribute__((noinline))
 #endif
 
 namespace rsq {

@@ -491,74 +491,140 @@ struct VarEval {
 	uint32_t slow;                               // bit 0: the read on the forward strand walks variants, bit 1: the read on the reverse strand does
 	int32_t end_var; uint32_t end_var_pos;       // VariantBiasVarModifiers::EndVariant (when the fragment was evaluated on the allele's sequence)
 };
-// uniform(): the next ZeroToOne of the block's stream.  Returns false when the fragment does not end inside the sequence (no draw is consumed).
+// Geometry of one chosen allele's fragment (no draw involved): end position, GC, both surrounding biases, EndVariant, which reads walk variants.
 // Every part falls back to the reference's own arrays when no variant of any allele lies within its reach: the fragment itself (end position, GC),
-// each of the two surroundings, each of the two reads.
-template<class Uniform>
-RSQ_HD bool eval_allele_hit(const SimCtx &c, const VariantView &v, uint32_t ref_id, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t fl,
-                            uint32_t allele, double thr0, Uniform &&uniform, VarEval &e, bool &runaway){
-	const uint32_t L = c.seq_len[ref_id];
-	const uint64_t off = c.seq_off[ref_id];
-	const uint32_t *gcp = c.gc_prefix + off + ref_id;
+// each of the two surroundings, each of the two reads.  Kept out of line: it is rare next to the scan's draws and must not cost it registers.
+struct VarGeom { uint32_t valid, gc_perc; double sur_start, sur_end; AllelePoint end; uint32_t end_hint; };
+// what the out-of-line evaluation reads of the run (passed by value: a reference to the kernel's SimCtx would force the whole struct into local memory)
+struct VarGeomCtx { const uint8_t *seq; const uint32_t *gcp; const double *sur_start, *sur_end; const double *sur_tab0, *sur_tab1, *sur_tab2; uint32_t L, n_read_max, probe_plain; };
+RSQ_HD_COLD void eval_allele_geometry(const VarGeomCtx gc, const VariantView v, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t fl,
+                                      uint32_t allele, VarEval &e, VarGeom &geo){
+	const uint32_t L = gc.L;
+	const uint32_t *gcp = gc.gcp;
 	e.allele = allele; e.counts = 0; e.end_var = -1; e.end_var_pos = 0; e.slow = 0;
+	geo.valid = 0;
 	const uint32_t hint = var_seek(v, first_var, pos);   // first variant at or behind the start position
-	const bool in_fragment = start_variant_pos || (hint < v.n && v.position[hint] <= pos + fl);
-	uint32_t gc_perc, end_hint = hint;
-	AllelePoint end{pos + fl, 0, -1};
-	if(in_fragment){
+	const bool probe_plain = gc.probe_plain != 0u;   // timing probe only (RSQ_VAR_PROBE=plain): every hit takes the reference's arrays - wrong output
+	const bool in_fragment = !probe_plain && (start_variant_pos || (hint < v.n && v.position[hint] <= pos + fl));
+	geo.end_hint = hint;
+	geo.end = AllelePoint{pos + fl, 0, -1};
+	bool only_substitutions = in_fragment && !start_variant_pos;
+	uint32_t gc_delta_plus = 0, gc_delta_minus = 0;
+	if(only_substitutions){
+		// fragments whose allele carries nothing but substitutions keep the reference's coordinates: end position pos + fl, G/C count corrected per base
+		for(uint32_t t = hint; t < v.n && v.position[t] < pos + fl + 1u && only_substitutions; ++t){
+			if(!v.in_allele(t, allele)){ continue; }
+			if(v.length(t) != 1u){ only_substitutions = false; break; }
+			if(v.position[t] < pos + fl){
+				const uint32_t alt = v.base(t, 0), org = gc.seq[v.position[t]];
+				gc_delta_plus += (alt == 1u || alt == 2u) ? 1u : 0u;
+				gc_delta_minus += (org == 1u || org == 2u) ? 1u : 0u;
+			}
+		}
+	}
+	if(only_substitutions){
+		e.end_position = pos + fl;
+		if(!(e.end_position < L)){ return; }
+		const uint32_t gcn = gcp[e.end_position] - gcp[pos] + gc_delta_plus - gc_delta_minus;
+		geo.gc_perc = ((gcn * 100u + fl / 2u) / fl) & 0xffu;
+		geo.end_hint = var_seek(v, hint, e.end_position);
+		e.end_var = static_cast<int32_t>(geo.end_hint) - 1;
+	}
+	else if(in_fragment){
 		AlleleHit h;
 		allele_hit(v, gcp, L, allele, pos, first_var, start_variant_pos, fl, h);
-		if(!h.valid){ return false; }
+		if(!h.valid){ return; }
 		e.end_position = h.end_position; e.end_var = h.end_var; e.end_var_pos = h.end_var_pos;
-		gc_perc = h.gc_percent; end = h.end; end_hint = h.end_hint;
+		geo.gc_perc = h.gc_percent; geo.end = h.end; geo.end_hint = h.end_hint;
 	}
 	else{
 		e.end_position = pos + fl;
-		if(!(e.end_position < L)){ return false; }
-		gc_perc = percent_u32(gcp[e.end_position] - gcp[pos], fl);
+		if(!(e.end_position < L)){ return; }
+		geo.gc_perc = percent_u32(gcp[e.end_position] - gcp[pos], fl);
 		e.end_var = static_cast<int32_t>(hint) - 1;
 	}
+	geo.valid = 1;
 	const uint32_t ep = e.end_position;
-	double sur_start, sur_end;
-	if(start_variant_pos || var_in_range(v, hint, pos >= 11u ? pos - 11u : 0u, pos + 20u)){
+	if(!probe_plain && (start_variant_pos || var_in_range(v, hint, pos >= 11u ? pos - 11u : 0u, pos + 20u))){
 		uint32_t code[3];
-		allele_start_surrounding(v, c.ref + off, L, allele, pos, first_var, start_variant_pos, code);
-		sur_start = surrounding_bias(c.var.sur_tab[0], c.var.sur_tab[1], c.var.sur_tab[2], code);
+		allele_start_surrounding(v, gc.seq, L, allele, pos, first_var, start_variant_pos, code);
+		geo.sur_start = surrounding_bias(gc.sur_tab0, gc.sur_tab1, gc.sur_tab2, code);
 	}
-	else{ sur_start = c.sur_start[off + pos]; }
-	if(end.k || var_in_range(v, end_hint, ep >= 22u ? ep - 22u : 0u, ep + 11u)){
+	else{ geo.sur_start = gc.sur_start[pos]; }
+	if(!probe_plain && (geo.end.k || var_in_range(v, geo.end_hint, ep >= 22u ? ep - 22u : 0u, ep + 11u))){
 		uint32_t code[3];
-		allele_end_surrounding(v, c.ref + off, L, allele, end, code, end_hint);
-		sur_end = surrounding_bias(c.var.sur_tab[0], c.var.sur_tab[1], c.var.sur_tab[2], code);
+		allele_end_surrounding(v, gc.seq, L, allele, geo.end, code, geo.end_hint);
+		geo.sur_end = surrounding_bias(gc.sur_tab0, gc.sur_tab1, gc.sur_tab2, code);
 	}
-	else{ sur_end = c.sur_end[off + ep - 1]; }
+	else{ geo.sur_end = gc.sur_end[ep - 1]; }
+	if(!probe_plain){
+		// which of the two reads has to walk variants (spliced bases, SysErrorVariant cursor): any variant of any allele within the read's bases
+		const uint32_t n = fl + 2u < gc.n_read_max ? fl + 2u : gc.n_read_max;
+		if(start_variant_pos || var_in_range(v, hint, pos, pos + n)){ e.slow |= 1u; }
+		if(geo.end.k || e.end_var_pos || var_in_range(v, geo.end_hint, ep >= n ? ep - n : 0u, ep)){ e.slow |= 2u; }
+	}
+}
+// uniform(): the next ZeroToOne of the block's stream.  Returns false when the fragment does not end inside the sequence (no draw is consumed).
+template<class Uniform>
+RSQ_HD bool eval_allele_hit(const SimCtx &c, const VariantView &v, uint32_t ref_id, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t fl,
+                            uint32_t allele, double thr0, Uniform &&uniform, VarEval &e, VarGeom &geo, bool &runaway){
+	const uint64_t off = c.seq_off[ref_id];
+	{
+		// nearly two thirds of the hits have no variant of any allele within reach of the fragment and its surroundings: the reference's arrays, no call
+		const uint32_t hint = var_seek(v, first_var, pos);
+		const bool near = start_variant_pos || (c.var.loaded & 2u) == 0u && ((hint < v.n && v.position[hint] <= pos + fl + 12u) || (hint > 0 && v.position[hint - 1] + 12u >= pos));
+		if(!near){
+			const uint32_t L = c.seq_len[ref_id];
+			const uint32_t *gcp = c.gc_prefix + off + ref_id;
+			e.allele = allele; e.counts = 0; e.end_var = static_cast<int32_t>(hint) - 1; e.end_var_pos = 0; e.slow = 0;
+			e.end_position = pos + fl;
+			geo.valid = 0; geo.end = AllelePoint{pos + fl, 0, -1}; geo.end_hint = hint;
+			if(!(e.end_position < L)){ return false; }
+			geo.valid = 1;
+			const double rv = uniform();
+			const double adjusted_random = add_rn(thr0, mul_rn(rv, sub_rn(1.0, thr0)));
+			e.counts = fragment_counts_alleles(c, ref_id, fl, percent_u32(gcp[e.end_position] - gcp[pos], fl), c.sur_start[off + pos], c.sur_end[off + e.end_position - 1], adjusted_random,
+			                                   c.var.num_alleles, runaway);
+			return true;
+		}
+	}
+	VarGeomCtx gc;
+	gc.seq = c.ref + off; gc.gcp = c.gc_prefix + off + ref_id; gc.sur_start = c.sur_start + off; gc.sur_end = c.sur_end + off;
+	gc.sur_tab0 = c.var.sur_tab[0]; gc.sur_tab1 = c.var.sur_tab[1]; gc.sur_tab2 = c.var.sur_tab[2];
+	gc.L = c.seq_len[ref_id]; gc.n_read_max = (c.read_len_to[0] > c.read_len_to[1] ? c.read_len_to[0] : c.read_len_to[1]) + c.max_len_deletion + 2u;
+	gc.probe_plain = (c.var.loaded & 2u) ? 1u : 0u;
+	eval_allele_geometry(gc, v, pos, first_var, start_variant_pos, fl, allele, e, geo);
+	if(!geo.valid){ return false; }
 	const double rv = uniform();
 	const double adjusted_random = add_rn(thr0, mul_rn(rv, sub_rn(1.0, thr0)));
-	e.counts = fragment_counts_alleles(c, ref_id, fl, gc_perc, sur_start, sur_end, adjusted_random, c.var.num_alleles, runaway);
-	if(e.counts){
-		// which of the two reads has to walk variants (spliced bases, SysErrorVariant cursor): any variant of any allele within the read's bases
-		const uint32_t n_max = (c.read_len_to[0] > c.read_len_to[1] ? c.read_len_to[0] : c.read_len_to[1]) + c.max_len_deletion + 2u;
-		const uint32_t n = fl + 2u < n_max ? fl + 2u : n_max;
-		if(start_variant_pos || var_in_range(v, hint, pos, pos + n)){ e.slow |= 1u; }
-		if(end.k || e.end_var_pos || var_in_range(v, end_hint, ep >= n ? ep - n : 0u, ep)){ e.slow |= 2u; }
-	}
+	e.counts = fragment_counts_alleles(c, ref_id, fl, geo.gc_perc, geo.sur_start, geo.sur_end, adjusted_random, c.var.num_alleles, runaway);
+	if(!e.counts){ e.slow = 0; }
 	return true;
 }
-// GetOrgSeq with variants (Simulator.cpp:1909-1914): the two ends of the allele's fragment, spliced.  Lane-uniform; lane 0 stores.
+// GetOrgSeq with variants (Simulator.cpp:1909-1914): the two ends of the allele's fragment - the allele's bases behind its start (StartVariant) and,
+// reverse complemented, in front of its end (EndVariant) - written by the whole lane group.  An end whose read has no variant among its bases
+// is copied from the reference.
 template<class G>
 RSQ_HD void splice_fragment_ends(const G &g, const SimCtx &c, const VariantView &v, uint32_t ref_id, uint32_t strand, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos,
-                                 uint32_t fl, const VarEval &e, uint8_t *frag_fwd, uint8_t *frag_rev, uint32_t which = 3u /* bit 0 forward end, bit 1 reverse end */){
+                                 uint32_t fl, const VarEval &e, const VarGeom &geo, uint8_t *frag_fwd, uint8_t *frag_rev, uint32_t which = 3u /* bit 0 forward end, bit 1 reverse end */){
 	g.sync();
 	const uint8_t *seq = c.ref + c.seq_off[ref_id];
+	const uint32_t L = c.seq_len[ref_id];
 	uint32_t n_fwd = c.read_len_to[strand ? 1 : 0] + c.max_len_deletion;   // forward end: the read of segment `strand`
 	if(fl < n_fwd){ n_fwd = fl; }
 	if(n_fwd > c.max_org_len){ n_fwd = c.max_org_len; }
 	uint32_t n_rev = c.read_len_to[strand ? 0 : 1] + c.max_len_deletion;
 	if(fl < n_rev){ n_rev = fl; }
 	if(n_rev > c.max_org_len){ n_rev = c.max_org_len; }
-	if((which & 1u) && (e.slow & 1u)){ if(g.lane() == 0){ splice_reference(frag_fwd, seq, v, pos, n_fwd, false, static_cast<int32_t>(first_var), start_variant_pos, e.allele); } }
+	if((which & 1u) && (e.slow & 1u)){
+		allele_bases_forward_g(g, v, seq, L, e.allele, AllelePoint{pos, start_variant_pos, start_variant_pos ? static_cast<int32_t>(first_var) : -1}, n_fwd, frag_fwd, first_var);
+	}
 	else if(which & 1u){ for(uint32_t i = g.lane(); i < n_fwd; i += G::kSize){ frag_fwd[i] = seq[pos + i]; } }
-	if((which & 2u) && (e.slow & 2u)){ if(g.lane() == 0){ splice_reference(frag_rev, seq, v, e.end_position, n_rev, true, e.end_var, e.end_var_pos, e.allele); } }
+	if((which & 2u) && (e.slow & 2u)){
+		// EndVariant {id, posCurrentlyAt}: inside an insertion the point lies behind its first posCurrentlyAt bases, else in front of the end position
+		const AllelePoint at = e.end_var_pos ? AllelePoint{e.end_position - 1u, e.end_var_pos, e.end_var} : AllelePoint{e.end_position, 0, -1};
+		allele_bases_backward_g(g, v, seq, L, e.allele, at, n_rev, frag_rev, geo.end_hint, true);
+	}
 	else if(which & 2u){ for(uint32_t i = g.lane(); i < n_rev; i += G::kSize){ frag_rev[i] = static_cast<uint8_t>(3u - seq[e.end_position - 1u - i]); } }
 	g.sync();
 }
@@ -1044,13 +1110,13 @@ RSQ_HD void simulate_block_var(const G &g, const SimCtx &c, const Scratch &s, Si
 					const uint32_t id = chosen[ci];
 					const uint32_t allele = nth_possible_allele(v, A, first_var, start_variant_pos, pos, id / 2u);
 					const bool strand = id & 1u;
-					VarEval e;
+					VarEval e; VarGeom geo;
 					bool runaway = false;
-					if(!eval_allele_hit(c, v, b.ref_id, pos, first_var, start_variant_pos, fragment_length, allele, thr0, uniform, e, runaway)){ continue; }
+					if(!eval_allele_hit(c, v, b.ref_id, pos, first_var, start_variant_pos, fragment_length, allele, thr0, uniform, e, geo, runaway)){ continue; }
 					if(runaway && g.lane() == 0){ *c.error_flag |= kErrCountRunaway; }
 					if(!e.counts){ continue; }
 					const bool staged = e.slow || kMeth;
-					if(staged){ splice_fragment_ends(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fragment_length, e, s.frag[0], s.frag[1]); }
+					if(staged){ splice_fragment_ends(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fragment_length, e, geo, s.frag[0], s.frag[1]); }
 					if(kMeth){
 						// CTConversion, variant overload: forward end from StartVariant, reverse end from EndVariant
 						const int32_t end_var = e.end_var;

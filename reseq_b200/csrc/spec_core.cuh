@@ -37,8 +37,8 @@ struct MtRing {
 	uint32_t avail;    // generated words from cur on; (cur + avail) % 312 == 0
 };
 
-template<class G> RSQ_HD void ring_generate(const G &g, MtRing &r){
-	const uint32_t end = r.cur + r.avail;
+template<class G> RSQ_HD void ring_generate_words(const G &g, uint64_t *w, uint32_t end){
+	MtRing r; r.w = w; r.cur = 0; r.avail = 0;
 	const uint32_t dst = (end >= 2u * kMtN ? end - 2u * kMtN : end) ? kMtN : 0u;   // end is 0, 312 or 624
 	const uint32_t src = dst ? 0u : kMtN;
 	g.sync();
@@ -53,6 +53,9 @@ template<class G> RSQ_HD void ring_generate(const G &g, MtRing &r){
 		}
 		g.sync();
 	}
+}
+template<class G> RSQ_HD void ring_generate(const G &g, MtRing &r){
+	ring_generate_words(g, r.w, r.cur + r.avail);
 	r.avail += kMtN;
 }
 template<class G> RSQ_HD void ring_ensure(const G &g, MtRing &r, uint32_t n){   // n <= 312
@@ -263,8 +266,9 @@ template<class G> RSQ_HD uint64_t emit_words(const G &g, MtRing &r, uint64_t *ds
 // Emits the slice of one read under the no-InDel hypothesis (mirrors the draw order of Simulator::FillRead) and returns
 // the assumed consumption.  Any deviation of the real read is caught by the verification, so this only has to be right
 // in the common case.
-template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing &r, uint64_t *dst, uint32_t cap, uint32_t margin, uint32_t seg, uint32_t fragment_length,
-                                            uint32_t given_org_len = kSpecNone){
+struct RingPos { uint32_t cur, avail, value; };   // what an out-of-line consumer of the stream hands back (the ring itself stays in the caller's registers)
+template<class G> RSQ_HD uint32_t plan_read_inline(const G &g, const SimCtx &c, MtRing &r, uint64_t *dst, uint32_t cap, uint32_t margin, uint32_t seg, uint32_t fragment_length,
+                                                   uint32_t given_org_len){
 	uint32_t k = 0;
 	uint32_t read_length = c.read_len_from[seg];
 	if(1 != c.read_len_count[seg]){
@@ -302,6 +306,18 @@ template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing 
 	if(margin){ emit_words(g, r, dst, km, cap, margin, false); }   // look-ahead only: the next consumer starts at k
 	return k;
 }
+template<class G> RSQ_HD_COLD RingPos plan_read_cold(const G &g, const SimCtx &c, uint64_t *ring_w, uint32_t cur, uint32_t avail, uint64_t *dst, uint32_t cap, uint32_t margin, uint32_t seg,
+                                                     uint32_t fragment_length, uint32_t given_org_len){
+	MtRing r; r.w = ring_w; r.cur = cur; r.avail = avail;
+	const uint32_t k = plan_read_inline(g, c, r, dst, cap, margin, seg, fragment_length, given_org_len);
+	return RingPos{r.cur, r.avail, k};
+}
+template<class G> RSQ_HD uint32_t plan_read(const G &g, const SimCtx &c, MtRing &r, uint64_t *dst, uint32_t cap, uint32_t margin, uint32_t seg, uint32_t fragment_length,
+                                            uint32_t given_org_len = kSpecNone){
+	const RingPos p = plan_read_cold(g, c, r.w, r.cur, r.avail, dst, cap, margin, seg, fragment_length, given_org_len);
+	r.cur = p.cur; r.avail = p.avail;
+	return p.value;
+}
 
 template<class G> RSQ_HD uint32_t first_lane(const G &g, unsigned mask){
 #if defined(__CUDA_ARCH__)
@@ -312,9 +328,9 @@ template<class G> RSQ_HD uint32_t first_lane(const G &g, unsigned mask){
 }
 
 struct ScanVarState { uint32_t first_var, start_variant_pos; const uint16_t *chosen_live; uint16_t *chosen_out; uint32_t n_chosen; };
-template<class G> RSQ_HD void save_snapshot(const G &g, MtRing &ring, SpecSnap &out, uint32_t pos, uint32_t len, bool finished, const SpecHit &hit,
-                                            int32_t cur_meth, uint64_t read_number, uint64_t draws, const ScanVarState &vs = ScanVarState{0, 0, nullptr, nullptr, 0}){
-	ring_ensure(g, ring, 1);
+template<class G> RSQ_HD_COLD void save_snapshot_cold(const G &g, const uint64_t *ring_w, uint32_t ring_cur, SpecSnap &out, uint32_t pos, uint32_t len, bool finished, const SpecHit hit,
+                                                      int32_t cur_meth, uint64_t read_number, uint64_t draws, const ScanVarState vs){
+	MtRing ring; ring.w = const_cast<uint64_t *>(ring_w); ring.cur = ring_cur; ring.avail = 1;
 	const uint32_t half = ring.cur >= static_cast<uint32_t>(kMtN) ? kMtN : 0u;
 	g.sync();
 	for(uint32_t i = g.lane(); i < static_cast<uint32_t>(kMtN); i += G::kSize){ out.mt[i] = ring.w[half + i]; }
@@ -324,6 +340,33 @@ template<class G> RSQ_HD void save_snapshot(const G &g, MtRing &ring, SpecSnap &
 	}
 	if(vs.chosen_out){ for(uint32_t i = g.lane(); i < vs.n_chosen; i += G::kSize){ vs.chosen_out[i] = vs.chosen_live[i]; } }
 	g.sync();
+}
+template<class G> RSQ_HD void save_snapshot(const G &g, MtRing &ring, SpecSnap &out, uint32_t pos, uint32_t len, bool finished, const SpecHit &hit,
+                                            int32_t cur_meth, uint64_t read_number, uint64_t draws, const ScanVarState &vs = ScanVarState{0, 0, nullptr, nullptr, 0}){
+	ring_ensure(g, ring, 1);
+	save_snapshot_cold(g, ring.w, ring.cur, out, pos, len, finished, hit, cur_meth, read_number, draws, vs);
+}
+
+// CTConversion of one staged fragment end with the unit's stream, out of line (bisulfite runs only)
+template<class G> RSQ_HD_COLD RingPos ct_conversion_ring(const G &g, const SimCtx &c, uint64_t *ring_w, uint32_t cur, uint32_t avail, uint8_t *read, uint32_t read_len, uint32_t seq_id,
+                                                         uint32_t start_pos, int32_t cur_methylation_start, bool reversed){
+	MtRing r; r.w = ring_w; r.cur = cur; r.avail = avail;
+	RingSource rng{r};
+	ct_conversion(g, c, rng, read, read_len, seq_id, start_pos, cur_methylation_start, reversed);
+	return RingPos{r.cur, r.avail, 0};
+}
+template<class G> RSQ_HD_COLD RingPos ct_conversion_var_ring(const G &g, const SimCtx &c, uint64_t *ring_w, uint32_t cur, uint32_t avail, uint8_t *read, uint32_t read_len, uint32_t seq_id,
+                                                             uint32_t start_pos, uint32_t allele, int32_t cur_methylation_start, bool reversed, const VariantView v, int32_t first_variant,
+                                                             uint32_t first_variant_pos){
+	MtRing r; r.w = ring_w; r.cur = cur; r.avail = avail;
+	RingSource rng{r};
+	ct_conversion_var(g, c, rng, read, read_len, seq_id, start_pos, allele, cur_methylation_start, reversed, v, first_variant, first_variant_pos);
+	return RingPos{r.cur, r.avail, 0};
+}
+// GetOrgSeq with variants, out of line
+template<class G> RSQ_HD_COLD void splice_fragment_ends_cold(const G &g, const SimCtx &c, const VariantView v, uint32_t ref_id, uint32_t strand, uint32_t pos, uint32_t first_var,
+                                                             uint32_t start_variant_pos, uint32_t fl, const VarEval e, const VarGeom geo, uint8_t *frag_fwd, uint8_t *frag_rev, uint32_t which){
+	splice_fragment_ends(g, c, v, ref_id, strand, pos, first_var, start_variant_pos, fl, e, geo, frag_fwd, frag_rev, which);
 }
 
 // Links a full (or final) slab into the unit's chain.  Lane 0 only.
@@ -415,10 +458,13 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	const bool with_var = kVar && c.var.loaded != 0 && sp.em_recs == nullptr && u < sp.n_blocks;   // kVar: the instantiation for runs with variants (keeps the plain one lean)
 	uint32_t first_var = snap.first_var, start_variant_pos = snap.start_variant_pos;
 	uint16_t *chosen_bank_out = nullptr;
+	uint32_t next_var_pos = 0xffffffffu;   // position of variant first_var (0xffffffff: none left): the per-position checks below stay in registers
+	auto refresh_next_var = [&](const VariantView &vv){ next_var_pos = first_var < vv.n ? vv.position[first_var] : 0xffffffffu; };
 	if(with_var){
 		const uint16_t *chosen_in = sp.snap_chosen + (static_cast<size_t>(u) * 2u * (D + 1u) + bank * (D + 1u) + idx) * sp.chosen_stride;
 		chosen_bank_out = sp.snap_chosen + (static_cast<size_t>(u) * 2u * (D + 1u) + (bank ^ 1u) * (D + 1u)) * sp.chosen_stride;
 		for(uint32_t i = g.lane(); i < hit.n_chosen && i < sp.chosen_stride; i += G::kSize){ chosen_live[i] = chosen_in[i]; }
+		if(!(sp.em_recs != nullptr) && u < sp.n_blocks){ refresh_next_var(c.var.view(descs[first_desc + u].ref_id)); }
 	}
 	g.sync();
 	if(pending_skip){
@@ -547,9 +593,9 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 				const uint32_t strand = id & 1u, fl = hit.fragment_length;
 				const uint32_t allele = nth_possible_allele(v, c.var.num_alleles, first_var, start_variant_pos, pos, id / 2u);
 				auto uniform = [&]() -> double { return canonical(ring_next(g, ring)); };
-				VarEval e;
+				VarEval e; VarGeom geo;
 				bool runaway = false;
-				if(eval_allele_hit(c, v, b.ref_id, pos, first_var, start_variant_pos, fl, allele, thr[2 * fl], uniform, e, runaway)){
+				if(eval_allele_hit(c, v, b.ref_id, pos, first_var, start_variant_pos, fl, allele, thr[2 * fl], uniform, e, geo, runaway)){
 					if(runaway && g.lane() == 0){ spec_flag(c, kErrCountRunaway); }
 					if(e.counts){
 						hit.allele = allele; hit.end_pos = e.end_position; hit.slow = e.slow; hit.end_var = e.end_var; hit.end_var_pos = e.end_var_pos;
@@ -557,14 +603,14 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 							hit.conv_slot = hit.conv_next; hit.conv_next = (hit.conv_next + 1u) % kConvSlots;
 							uint8_t *frag0 = sp.conv + ((static_cast<size_t>(u) * kConvSlots + hit.conv_slot) * 2u) * kMaxOrgLen, *frag1 = frag0 + kMaxOrgLen;
 							// the ends whose reads walk variants are spliced; with methylation both ends are staged for the conversion
-							splice_fragment_ends(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fl, e, frag0, frag1, c.meth_loaded ? 3u : e.slow);
+							splice_fragment_ends_cold(g, c, v, b.ref_id, strand, pos, first_var, start_variant_pos, fl, e, geo, frag0, frag1, c.meth_loaded ? 3u : e.slow);
 							if(c.meth_loaded){
 								const int32_t end_var = e.end_var;
 								for(uint32_t rev = 0; rev < 2; ++rev){
 									const uint32_t seg = rev ? (strand ? 0u : 1u) : (strand ? 1u : 0u);
-									RingSource rng{ring};
-									ct_conversion_var(g, c, rng, rev ? frag1 : frag0, fragment_org_len(c, seg, fl), b.ref_id, rev ? e.end_position : pos, allele, cur_meth, rev != 0, v,
-									                  rev ? end_var : static_cast<int32_t>(first_var), rev ? e.end_var_pos : start_variant_pos);
+									const RingPos rp = ct_conversion_var_ring(g, c, ring.w, ring.cur, ring.avail, rev ? frag1 : frag0, fragment_org_len(c, seg, fl), b.ref_id, rev ? e.end_position : pos, allele,
+									                                          cur_meth, rev != 0, v, rev ? end_var : static_cast<int32_t>(first_var), rev ? e.end_var_pos : start_variant_pos);
+									ring.cur = rp.cur; ring.avail = rp.avail;
 								}
 								g.sync();
 							}
@@ -600,8 +646,8 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 									frag[i] = rev ? static_cast<uint8_t>(3 - c.ref[off + cur_end - 1 - i]) : c.ref[off + pos + i];
 								}
 								g.sync();
-								RingSource rng{ring};
-								ct_conversion(g, c, rng, frag, n, b.ref_id, rev ? cur_end : pos, cur_meth, rev != 0);
+								const RingPos rp = ct_conversion_ring(g, c, ring.w, ring.cur, ring.avail, frag, n, b.ref_id, rev ? cur_end : pos, cur_meth, rev != 0);
+								ring.cur = rp.cur; ring.avail = rp.avail;
 							}
 							g.sync();
 						}
@@ -620,8 +666,10 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		while(true){
 			if(len >= insert_to){
 				len = insert_from;
-				if(with_var){   // CheckForInsertedBasesToStartFrom: once more from the same position per further inserted base
-					next_start_pass(c.var.view(b.ref_id), pos, first_var, start_variant_pos);
+				if(with_var && next_var_pos == pos){   // CheckForInsertedBasesToStartFrom: once more from the same position per further inserted base
+					const VariantView vv = c.var.view(b.ref_id);
+					next_start_pass(vv, pos, first_var, start_variant_pos);
+					refresh_next_var(vv);
 					if(start_variant_pos){ continue; }
 				}
 				++pos;
@@ -681,7 +729,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		if(with_var){
 			// DrawNumberNonZeroStrands over the alleles possible at this start + ChooseAlleles (Simulator.cpp:2302-2309)
 			const VariantView v = c.var.view(b.ref_id);
-			const uint32_t n_possible = count_possible_alleles(v, c.var.num_alleles, first_var, start_variant_pos, pos);
+			const uint32_t n_possible = next_var_pos == pos ? count_possible_alleles(v, c.var.num_alleles, first_var, start_variant_pos, pos) : c.var.num_alleles;
 			const uint32_t n_pow = 2u * c.var.num_alleles + 1u;
 			const double pow_term = c.binom_pow[(static_cast<size_t>(group) * insert_to + fragment_length) * n_pow + 2u * n_possible];
 			const uint32_t non_zero_strands = binomial_count(2u * n_possible, sub_rn(1.0, thr0), pow_term, probability_chosen);
