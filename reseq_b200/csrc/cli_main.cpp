@@ -114,9 +114,9 @@ int run_illumina_pe(const Args &a){
 	info("Reading reference from " + ref_path);
 	rsq_reference *ref = rsq_reference_load_fasta(ref_path.c_str());
 	if(!ref){ return err(rsq_last_error()); }
-	if(a.has("methylation") && rsq_reference_load_methylation(ref, a.get("methylation").c_str())){ rsq_reference_free(ref); return err(rsq_last_error()); }
-	// -V: read and checked like Reference::PrepareVariantFile/ReadVariants; the engine then refuses the run (variant-aware kernels: next revision)
+	// -V before --methylation like Simulator::Simulate opens them (Simulator.cpp:2747-2772): the methylation file may carry one column per allele
 	if(a.has("vcfSim") && rsq_reference_load_variants(ref, a.get("vcfSim").c_str())){ rsq_reference_free(ref); return err(rsq_last_error()); }
+	if(a.has("methylation") && rsq_reference_load_methylation(ref, a.get("methylation").c_str())){ rsq_reference_free(ref); return err(rsq_last_error()); }
 	rsq_profile *prof = load_profile(a);
 	if(!prof){ rsq_reference_free(ref); return 1; }
 	rsq_sim_options opt{};
@@ -153,50 +153,17 @@ int run_illumina_pe(const Args &a){
 	info("Storing simulated data in " + out1 + " and " + out2);
 	for(const std::string &o : {out1, out2}){ FILE *f = fopen(o.c_str(), "wb"); if(!f){ return err("Could not open '" + o + "' for writing."); } fclose(f); }
 
-	if(gpus == 1){
-		// one device: the drop-in call streams batch after batch into the two files (runs larger than HBM or host memory work)
-		const auto t1 = std::chrono::steady_clock::now();
-		rsq_sim_report rep;
-		const int rc1 = rsq_simulate(prof, ref, &opt, 0, out1.c_str(), out2.c_str(), &rep);
-		const std::string msg = rc1 ? rsq_last_error() : "";
-		rsq_profile_free(prof); rsq_reference_free(ref);
-		if(rc1){ err(msg); err("An error occurred in the process: Terminating simulation"); return 1; }
-		const double secs1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
-		info("Generated " + std::to_string(rep.pairs) + " read pairs (aim " + std::to_string(rep.total_pairs_aim) + ") in " + std::to_string(secs1) + " s on 1 GPU(s).");
-		info("Simulation finished succesfully");
-		return 0;
-	}
-	std::vector<rsq_engine *> engines(gpus, nullptr);
-	std::vector<rsq_sim_report> reports(gpus);
-	std::vector<std::string> errors(gpus);
-	std::vector<std::thread> threads;
-	const auto t0 = std::chrono::steady_clock::now();
-	for(int d = 0; d < gpus; ++d){
-		threads.emplace_back([&, d]{
-			rsq_sim_options o = opt; o.shard_index = d; o.shard_count = gpus;
-			engines[d] = rsq_engine_create(prof, d);
-			if(!engines[d] || rsq_engine_prepare(engines[d], ref, &o, &reports[d]) || rsq_engine_simulate(engines[d], &reports[d]) || rsq_engine_download(engines[d], &reports[d])){
-				errors[d] = rsq_last_error();
-			}
-		});
-	}
-	for(auto &t : threads){ t.join(); }
-	int rc = 0;
-	for(int d = 0; d < gpus && !rc; ++d){ if(!errors[d].empty()){ rc = err(errors[d]); } }
-	uint64_t pairs = 0;
-	for(int d = 0; d < gpus && !rc; ++d){   // shards are contiguous block ranges: appending them in order gives the 1-thread order
-		if(rsq_engine_write(engines[d], out1.c_str(), out2.c_str())){ rc = err(rsq_last_error()); }
-		pairs += reports[d].pairs;
-	}
-	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-	for(auto e : engines){ if(e){ rsq_engine_destroy(e); } }
+	// the drop-in call streams batch after batch into the two files (runs larger than HBM or host memory work); with several GPUs every engine
+	// streams its shard and the shard files are appended in order (rsq_simulate_multi)
+	const auto t1 = std::chrono::steady_clock::now();
+	rsq_sim_report rep;
+	const int rc1 = gpus == 1 ? rsq_simulate(prof, ref, &opt, 0, out1.c_str(), out2.c_str(), &rep)
+	                          : rsq_simulate_multi(prof, ref, &opt, gpus, nullptr, out1.c_str(), out2.c_str(), &rep);
+	const std::string msg = rc1 ? rsq_last_error() : "";
 	rsq_profile_free(prof); rsq_reference_free(ref);
-	if(rc){
-		err("An error occurred in the process: Terminating simulation");
-		remove(out1.c_str()); remove(out2.c_str());
-		return 1;
-	}
-	info("Generated " + std::to_string(pairs) + " read pairs (aim " + std::to_string(reports[0].total_pairs_aim) + ") in " + std::to_string(secs) + " s on " + std::to_string(gpus) + " GPU(s).");
+	if(rc1){ err(msg); err("An error occurred in the process: Terminating simulation"); return 1; }
+	const double secs1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+	info("Generated " + std::to_string(rep.pairs) + " read pairs (aim " + std::to_string(rep.total_pairs_aim) + ") in " + std::to_string(secs1) + " s on " + std::to_string(gpus) + " GPU(s).");
 	info("Simulation finished succesfully");
 	return 0;
 }

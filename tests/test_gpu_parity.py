@@ -379,7 +379,7 @@ def test_cli_dropin(golden, workdir, library):
     assert open(em, "rb").read() == open(golden["em_out"], "rb").read()
     res = subprocess.run([build.CLI, "illuminaPE", "-s", golden["reseq"], "-R", golden["small_ref"], "-b", "x.bam"], capture_output=True, text=True)
     assert res.returncode == 1 and "does not replace" in res.stderr
-    # -V: the file is read and checked like the reference does, then the engine refuses the run (no silent reference-only simulation)
+    # -V: the file is read and checked like the reference does
     res = subprocess.run([build.CLI, "illuminaPE", "-s", golden["reseq"], "-R", golden["small_ref"], "-V", "x.vcf"], capture_output=True, text=True)
     assert res.returncode == 1 and "Could not open vcf file 'x.vcf'" in res.stderr
     res = subprocess.run([build.CLI, "illuminaPE", "-s", golden["reseq"], "-R", golden["small_ref"], "-V", os.path.join(golden["dir"], "simref_small_var_bad_overlap.vcf")],
@@ -387,7 +387,10 @@ def test_cli_dropin(golden, workdir, library):
     assert res.returncode == 1 and "overlaps with a previous variant" in res.stderr
     res = subprocess.run([build.CLI, "illuminaPE", "-s", golden["reseq"], "-R", golden["small_ref"], "--ipfIterations", "0", "--seed", "42", "-c", "20",
                           "-1", o1 + ".v", "-2", o2 + ".v", "-V", os.path.join(golden["dir"], "simref_small_var.vcf")], capture_output=True, text=True)
-    assert res.returncode == 1 and "variant-aware simulation" in res.stderr and not os.path.exists(o1 + ".v")
+    import lzma
+    assert res.returncode == 0, res.stderr
+    for path, name in ((o1 + ".v", "sim_small_var_seed42_R1.fq.xz"), (o2 + ".v", "sim_small_var_seed42_R2.fq.xz")):
+        assert open(path, "rb").read() == lzma.open(os.path.join(golden["dir"], name)).read()
 
 
 @pytest.mark.parametrize("shards", [3, 7])
