@@ -48,8 +48,9 @@ int rsq_reference_load_methylation(rsq_reference *ref, const char *bed_path);
  * Reference.h:115-139), `-V/--vcfSim <vcf>`: contigs checked against the reference, genotype columns -> allele bit sets, records
  * split into single-position variants sorted deletion/substitution/insertion.  The whole file is read (the reference pages it in per
  * sequence, Simulator.cpp:938, 1278); a file the reference rejects anywhere is rejected here with the same diagnostics.
- * This revision loads, validates and exposes the variants; rsq_engine_prepare refuses a reference that carries them (the
- * variant-aware kernels are the next step), so a run never silently ignores a VCF. */
+ * rsq_engine_prepare re-validates the REF bases that fell on an N of the unprocessed reference after ReplaceN (the reference
+ * loads variants against the N-replaced sequence) and rsq_simulate / rsq_simulate_multi then simulate reads from the alleles
+ * (`_allele<a>` read ids, Simulator.cpp:1700-2150).  Not supported, refused with a message: `--readSysError` together with -V. */
 int rsq_reference_load_variants(rsq_reference *ref, const char *vcf_path);
 uint32_t rsq_reference_num_alleles(const rsq_reference *ref);      /* Reference::NumAlleles (1 without variants) */
 uint64_t rsq_reference_num_variants(const rsq_reference *ref, uint32_t seq);   /* Reference::Variants(seq).size() */
@@ -113,6 +114,11 @@ void rsq_engine_destroy(rsq_engine *engine);
  * are all-reduced behind the data path (rsq_sim_report.group_pairs).  shard_index / shard_count of rsq_sim_options are then rank / world.
  * One process per GPU (torchrun, mpirun): rank 0 calls rsq_group_unique_id, ships the 128 bytes to the other ranks by any means, every rank calls
  * rsq_engine_join_group on its engine.  One process for all GPUs of a box: rsq_simulate_multi. */
+/* The block ranges the engines take (host only, no GPU needed): boundaries[k] .. boundaries[k + 1] are the SimBlocks of shard k of shard_count
+ * for this profile (its longest insert decides which sequences are simulated and how many look-ahead blocks end the run) and reference;
+ * boundaries needs shard_count + 1 entries.  The even split, with a boundary moved onto a sequence start lying within 5 % of a shard's size.
+ * rsq_engine_prepare uses the same function; rsq_sim_report.shard_first / blocks report the range an engine took. */
+int rsq_shard_plan(const rsq_profile *profile, const rsq_reference *ref, uint32_t shard_count, uint32_t *boundaries);
 int rsq_group_unique_id(void *id_out, uint64_t capacity /* >= 128 */);
 int rsq_engine_join_group(rsq_engine *engine, const void *unique_id, int rank, int world);
 int rsq_engine_leave_group(rsq_engine *engine);
@@ -150,7 +156,7 @@ int rsq_create_systematic_error_profile(rsq_engine *engine, const rsq_reference 
 int rsq_apply_error_model(rsq_engine *engine, const char *fasta_in_path, const char *fastq_out_path, uint64_t seed, rsq_sim_report *report);
 
 /* Stage introspection for parity tests: copies a named device/host array ("sys_fwd", "sys_rev", "adapter_sys",
- * "block_seed", "thresholds", "sur_start", "sur_end", "reference") into dst (up to capacity bytes). */
+ * "blocks" (BlockDesc records, 32 bytes each), "thresholds", "sur_start", "sur_end", "reference") into dst (up to capacity bytes). */
 int rsq_engine_fetch(const rsq_engine *engine, const char *name, void *dst, uint64_t capacity, uint64_t *bytes);
 
 #ifdef __cplusplus

@@ -67,6 +67,7 @@ SIGNATURES = {
     "rsq_engine_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "rsq_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SimOptions), C.c_int, C.c_char_p, C.c_char_p, C.POINTER(SimReport)]),
     "rsq_simulate_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SimOptions), C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_char_p, C.POINTER(SimReport)]),
+    "rsq_shard_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "rsq_group_unique_id": (C.c_int, [C.c_void_p, C.c_uint64]),
     "rsq_engine_join_group": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "rsq_engine_leave_group": (C.c_int, [C.c_void_p]),
@@ -310,6 +311,15 @@ def group_unique_id():
     if lib.rsq_group_unique_id(buf, 128):
         raise _err(lib)
     return buf.raw
+
+
+def shard_plan(profile, reference, shard_count):
+    """rsq_shard_plan: the SimBlock boundaries of shard_count shards, [b0 = 0, b1, ..., b_count] (host only)."""
+    lib = load_library()
+    out = (C.c_uint32 * (shard_count + 1))()
+    if lib.rsq_shard_plan(profile._h, reference._h, shard_count, out):
+        raise _err(lib)
+    return list(out)
 
 
 def simulate_multi(profile, reference, first_reads_path, second_reads_path, seed, n_gpus, coverage=0.0, num_read_pairs=0, ref_bias_model=1,

@@ -39,6 +39,7 @@
 #include "deflate_core.cuh"
 #include "em_input.hpp"
 #include "variant_syserr.hpp"
+#include "shard_plan.hpp"
 
 #include <dlfcn.h>
 #include <nccl.h>   // types and prototypes only: the library is bound at run time (libnccl.so.2), so single-GPU use does not need it
@@ -1355,6 +1356,7 @@ static std::vector<SysErrorRecord> read_sys_error_file(const std::string &path){
 		}
 		recs.push_back({id.substr(1), seq, qual});
 	}
+	if(in.corrupt()){ throw std::runtime_error("Could not read systematic error profile '" + path + "': corrupt or truncated gzip stream"); }
 	return recs;
 }
 // Simulator::ReadSystematicErrors (Simulator.h:326-335)
@@ -1474,37 +1476,14 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	const uint32_t shard_count_pre = grouped ? static_cast<uint32_t>(e.group_world) : (opt.shard_count ? opt.shard_count : 1);
 	const uint32_t shard_index_pre = grouped ? static_cast<uint32_t>(e.group_rank) : opt.shard_index;
 	if(shard_index_pre >= shard_count_pre){ throw std::runtime_error("shard_index out of range"); }
-	std::vector<uint32_t> seq_first_block(g.seqs.size(), 0), seq_blocks(g.seqs.size(), 0);
-	uint32_t nb_total_pre = 0;
-	for(size_t i = 0; i < g.seqs.size(); ++i){
-		const uint32_t L = g.seqs[i].size();
-		if(L < c.insert_to){ continue; }
-		seq_first_block[i] = nb_total_pre; seq_blocks[i] = (L + 999) / 1000; nb_total_pre += seq_blocks[i];
-	}
-	if(!nb_total_pre){ throw std::runtime_error("All reference sequences are too short for simulating."); }
-	const uint32_t lookahead_blocks = 1 + c.insert_to / 1000;
-	const uint32_t n_sim_blocks = nb_total_pre > lookahead_blocks ? nb_total_pre - lookahead_blocks : 0;
-	auto shard_boundary = [&](uint32_t k) -> uint64_t {
-		if(k == 0){ return 0; }
-		if(k >= shard_count_pre){ return n_sim_blocks; }
-		const uint64_t tol = std::max<uint64_t>(1, n_sim_blocks / (20ull * shard_count_pre));
-		const uint64_t even = static_cast<uint64_t>(n_sim_blocks) * k / shard_count_pre;
-		uint64_t best = even, best_d = tol + 1;
-		for(size_t i = 0; i < g.seqs.size(); ++i){
-			if(!seq_blocks[i]){ continue; }
-			const uint64_t f = seq_first_block[i];
-			const uint64_t d = f > even ? f - even : even - f;
-			if(f > 0 && f < n_sim_blocks && d < best_d){ best = f; best_d = d; }
-		}
-		return best;
-	};
-	e.shard_first = static_cast<uint32_t>(shard_boundary(shard_index_pre));
-	e.shard_n = static_cast<uint32_t>(std::max<uint64_t>(shard_boundary(shard_index_pre + 1), e.shard_first) - e.shard_first);
+	std::vector<uint64_t> seq_lengths(g.seqs.size());
+	for(size_t i = 0; i < g.seqs.size(); ++i){ seq_lengths[i] = g.seqs[i].size(); }
+	const ShardPlan plan = make_shard_plan(seq_lengths.data(), seq_lengths.size(), c.insert_to, shard_count_pre);   // shard_plan.hpp (also behind rsq_shard_plan)
+	if(!plan.blocks_total){ throw std::runtime_error("All reference sequences are too short for simulating."); }
+	e.shard_first = static_cast<uint32_t>(plan.first(shard_index_pre));
+	e.shard_n = static_cast<uint32_t>(plan.count(shard_index_pre));
 	// a sequence is needed by the shards that hold blocks of it; in a group its bias sums are computed by the first of them (its owner)
-	auto shard_needs = [&](uint32_t k, size_t i) -> bool {
-		const uint64_t lo = shard_boundary(k), hi = std::max<uint64_t>(shard_boundary(k + 1), lo);
-		return seq_blocks[i] && hi > lo && seq_first_block[i] < hi && lo < static_cast<uint64_t>(seq_first_block[i]) + seq_blocks[i];
-	};
+	auto shard_needs = [&](uint32_t k, size_t i) -> bool { return plan.needs(k, i); };
 	std::vector<uint8_t> needed(g.seqs.size(), 1);
 	std::vector<int32_t> owner(g.seqs.size(), 0);
 	if(grouped){
@@ -2340,6 +2319,8 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	for(int i = 0; i < 2; ++i){ if(!e.ev_out[i]){ RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_out[i], cudaEventDisableTiming)); } }
 	ChunkWriter writer[2];
 	const bool streaming = to_files || stream_host;
+	// declared before any writer thread starts: a throw between the two thread starts (an allocation for segment 1) must still stop and join segment 0's thread
+	struct Joiner { ChunkWriter *w; bool on; ~Joiner(){ for(int seg = 0; on && seg < 2; ++seg){ if(w[seg].th.joinable()){ { std::lock_guard<std::mutex> l(w[seg].m); w[seg].stop = true; } w[seg].cv.notify_all(); w[seg].th.join(); } } } } joiner{writer, streaming};
 	if(streaming){
 		if(!e.copy_stream2){ RSQ_CUDA(cudaStreamCreateWithFlags(&e.copy_stream2, cudaStreamNonBlocking)); }
 		for(int i = 0; i < kRingSlots; ++i){ e.h_ring[i].ensure(kRingChunk); if(!e.ev_ring[i]){ RSQ_CUDA(cudaEventCreateWithFlags(&e.ev_ring[i], cudaEventDisableTiming)); } }
@@ -2371,7 +2352,6 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 			w.th = std::thread([&w]{ w.run(); });
 		}
 	}
-	struct Joiner { ChunkWriter *w; bool on; ~Joiner(){ for(int seg = 0; on && seg < 2; ++seg){ if(w[seg].th.joinable()){ { std::lock_guard<std::mutex> l(w[seg].m); w[seg].stop = true; } w[seg].cv.notify_all(); w[seg].th.join(); } } } } joiner{writer, streaming};
 	auto wait_batches = [&](uint64_t n){ for(int seg = 0; seg < 2; ++seg){ std::unique_lock<std::mutex> l(writer[seg].m); writer[seg].cv.wait(l, [&]{ return writer[seg].batches_done >= n; }); } };
 	float ms_sim = 0, ms_gather = 0;
 	for(uint32_t b = 0; b < n_batches; ++b){
@@ -2708,6 +2688,18 @@ rsq_engine *rsq_engine_create(const rsq_profile *profile, int device){
 }
 
 void rsq_engine_destroy(rsq_engine *engine){ if(engine){ cudaSetDevice(engine->device); delete engine; } }
+
+int rsq_shard_plan(const rsq_profile *profile, const rsq_reference *ref, uint32_t shard_count, uint32_t *boundaries){
+	RSQ_TRY
+	if(!profile || !ref || !boundaries || !shard_count){ throw std::runtime_error("rsq_shard_plan: null argument or zero shards"); }
+	const Genome &g = ref->g;
+	std::vector<uint64_t> lengths(g.seqs.size());
+	for(size_t i = 0; i < g.seqs.size(); ++i){ lengths[i] = g.seqs[i].size(); }
+	const ShardPlan plan = make_shard_plan(lengths.data(), lengths.size(), static_cast<uint32_t>(profile->p.insert_lengths.to()), shard_count);
+	for(uint32_t k = 0; k <= shard_count; ++k){ boundaries[k] = static_cast<uint32_t>(std::max<uint64_t>(plan.boundary(k), k ? boundaries[k - 1] : 0)); }
+	return 0;
+	RSQ_CATCH(1)
+}
 
 int rsq_group_unique_id(void *id_out, uint64_t capacity){
 	RSQ_TRY

@@ -80,3 +80,5 @@ def test_group_of_engines_all_reduces_pair_counts_and_shards_the_prologue(rb, go
     assert res[0][0] + res[1][0] == whole[0] and res[0][1] + res[1][1] == whole[1]
     assert res[0][3] == res[1][3] == res[0][4] + res[1][4] == whole[0].count(b"\n") // 4
     assert res[0][5] == 0 and res[1][5] == res[0][6]
+    plan = rb.shard_plan(prof, ref, 2)    # the host-only function of the same split (tests/test_multirank_cpu.py checks its properties)
+    assert [res[0][5], res[1][5], res[1][5] + res[1][6]] == plan
