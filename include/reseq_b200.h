@@ -156,7 +156,7 @@ int rsq_create_systematic_error_profile(rsq_engine *engine, const rsq_reference 
 int rsq_apply_error_model(rsq_engine *engine, const char *fasta_in_path, const char *fastq_out_path, uint64_t seed, rsq_sim_report *report);
 
 /* Stage introspection for parity tests: copies a named device/host array ("sys_fwd", "sys_rev", "adapter_sys",
- * "blocks" (BlockDesc records, 32 bytes each), "thresholds", "sur_start", "sur_end", "reference") into dst (up to capacity bytes). */
+ * "blocks" (BlockDesc records, 32 bytes each), "spec_blocks" (per-unit counters of the last speculative batch, 80 bytes each), "thresholds", "sur_start", "sur_end", "reference") into dst (up to capacity bytes). */
 int rsq_engine_fetch(const rsq_engine *engine, const char *name, void *dst, uint64_t capacity, uint64_t *bytes);
 
 #ifdef __cplusplus

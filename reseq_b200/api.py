@@ -78,7 +78,8 @@ SIGNATURES = {
 
 
 def lib_path():
-    return os.path.join(HERE, "libreseq_b200.so")
+    """The in-tree library; RSQ_B200_LIB points A/B measurements at another build of the same sources (tools/build_variant.sh)."""
+    return os.environ.get("RSQ_B200_LIB") or os.path.join(HERE, "libreseq_b200.so")
 
 
 def load_library():

@@ -29,6 +29,7 @@ class TextIn {
 	const char *p_ = nullptr, *end_ = nullptr;
 	std::set<const void *> seen_;
 	std::string path_;
+	uint64_t library_version_ = 0;
 
 	void skip_ws(){ while(p_ < end_ && (*p_ == ' ' || *p_ == '\n' || *p_ == '\r' || *p_ == '\t')){ ++p_; } }
 	[[noreturn]] void fail(const char *what) const { throw std::runtime_error("Could not load '" + path_ + "': input stream error (" + what + ")"); }
@@ -48,7 +49,20 @@ public:
 		skip_ws();
 		if(siglen != 22 || static_cast<size_t>(end_ - p_) < 22 || std::string(p_, 22) != "serialization::archive"){ fail("invalid signature"); }
 		p_ += 22;
-		(void)u64();   // library version
+		// Archive library version (Boost 1.53 .. 1.8x write 10 .. 20).  The token rules below were checked against archives of version 17
+		// written by the oracle build's own text_oarchive stand-in (oracle/boost_shim), never against a file from a real Boost build:
+		// anything outside the range whose text dialect is documented to be the same is refused instead of being parsed on a guess.
+		library_version_ = u64();
+		if(library_version_ < 10 || library_version_ > 20){
+			throw std::runtime_error("Could not load '" + path_ + "': Boost archive library version " + std::to_string(library_version_) + " is outside 10..20, the text-archive dialect this loader restates");
+		}
+	}
+	uint64_t library_version() const { return library_version_; }
+	// Self-check after the last member: every serialize() list restated here must have consumed the file exactly.  Left-over tokens mean the
+	// file was written by another revision of the reference (other members) or in another archive dialect.
+	void expect_end(){
+		skip_ws();
+		if(p_ < end_){ throw std::runtime_error("Could not load '" + path_ + "': " + std::to_string(end_ - p_) + " bytes are left behind the last member (written by another ReSeq revision or Boost archive dialect?)"); }
 	}
 	uint64_t u64(){
 		skip_ws();
@@ -386,7 +400,7 @@ inline void load_reseq_profile(Profile &p, const char *stats_path, const char *i
 	std::unique_ptr<ADataStats> ds(new ADataStats);
 	{
 		TextIn in(stats_path);
-		in & *ds;
+		in & *ds;   // (no expect_end: the plotting-only members behind corrected_coverage_ are deliberately not restated)
 	}
 	// --- DataStats members + PrepareProcessing ---
 	for(int seg = 0; seg < 2; ++seg){
@@ -458,6 +472,7 @@ inline void load_reseq_profile(Profile &p, const char *stats_path, const char *i
 	{
 		TextIn in(ipf_path);
 		in & *pe;
+		in.expect_end();
 	}
 	if(pe->stats_creation_time != p.creation_time){
 		throw std::runtime_error(std::string("'") + ipf_path + "' was estimated for a different statistics file (creation time mismatch): the reference would discard it and refit");

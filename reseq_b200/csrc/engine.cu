@@ -531,21 +531,63 @@ __global__ void k_spec_init(SimCtx c, SpecCtx sp, const BlockDesc *descs, uint32
 	if(u < sp.n_units){ spec_init_unit(c, sp, descs, first_desc, u); }
 }
 
+// --- bulk asynchronous copies (TMA unit, cp.async.bulk -> SASS UBLKCP) completing on an mbarrier -------------------------------------
+// Contiguous global -> shared staging without registers: one lane arms the barrier with the byte count and issues the copy, every lane
+// waits on the barrier's phase.  Source, destination and size are multiples of 16 bytes.
+__device__ __forceinline__ uint32_t smem_addr(const void *p){ return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals){
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(arrivals) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy before a copy names the barrier
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes){
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_shared, const void *src_global, uint32_t bytes, uint64_t *bar){
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_addr(dst_shared)), "l"(src_global), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity){
+	asm volatile("{\n.reg .pred p;\nRSQ_MBAR_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra RSQ_MBAR_DONE;\nbra RSQ_MBAR_WAIT;\nRSQ_MBAR_DONE:\n}"
+	             :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
 template<bool kVar>
 __device__ __forceinline__ void spec_scan_body(const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){
 	__shared__ uint64_t rings[kWarpsPerCta][2 * kMtN];
-	extern __shared__ __align__(16) unsigned char scan_dyn[];   // runs with variants: 2 * num_alleles chosen (allele, strand) ids per warp
+	__shared__ __align__(8) uint64_t thr_bar[kWarpsPerCta];
+	// dynamic: per warp its unit's row of threshold high words (c.thr_hi_stride entries, 16-byte rows), then - runs with variants - 2 * num_alleles chosen (allele, strand) ids
+	extern __shared__ __align__(16) unsigned char scan_dyn[];
 	WarpGroup g;
 	const uint32_t warp = threadIdx.x >> 5;
 	const uint32_t u = unit_first + blockIdx.x * kWarpsPerCta + warp;
 	if(u >= unit_end){ return; }
-	scan_window<kVar>(g, c, sp, descs, first_desc, u, rings[warp], reinterpret_cast<uint16_t *>(scan_dyn) + static_cast<size_t>(warp) * sp.chosen_stride);
+	if(sp.blocks[u].done){ return; }
+	// stage the threshold row of this unit's coverage group: the scan reads one entry per draw and nothing else from global memory
+	uint32_t *thr_row = reinterpret_cast<uint32_t *>(scan_dyn) + static_cast<size_t>(warp) * c.thr_hi_stride;
+	const bool scanning = sp.em_recs == nullptr && u < sp.n_blocks;
+	if(scanning){
+		const uint32_t group = c.coverage_group[descs[first_desc + u].ref_id];
+		if((threadIdx.x & 31u) == 0u){
+			mbar_init(&thr_bar[warp], 1);
+			mbar_expect_tx(&thr_bar[warp], c.thr_hi_stride * 4u);
+			bulk_copy_g2s(thr_row, c.thr_hi + static_cast<size_t>(group) * c.thr_hi_stride, c.thr_hi_stride * 4u, &thr_bar[warp]);
+		}
+		__syncwarp();
+		mbar_wait(&thr_bar[warp], 0);
+	}
+	uint16_t *chosen = reinterpret_cast<uint16_t *>(scan_dyn + static_cast<size_t>(kWarpsPerCta) * c.thr_hi_stride * 4u) + static_cast<size_t>(warp) * sp.chosen_stride;
+	scan_window<kVar>(g, c, sp, descs, first_desc, u, rings[warp], chosen, scanning ? thr_row : nullptr);
 }
 // The two contexts are __grid_constant__: the out-of-line helpers (snapshots, read plans, allele evaluation ...) take them by reference straight from
 // the constant bank instead of forcing a 1 KB copy into local memory; out of line they are because the scan's code has to stay within the
 // instruction cache (with everything inlined the variant instantiation was 384 KB of SASS and stalled on instruction fetches).
 template<bool kVar> __global__ void k_spec_scan(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end);
-template<> __global__ void __launch_bounds__(kWarpsPerCta * 32)
+#ifdef RSQ_SCAN_MINBLOCKS   // A/B builds (tools/build_variant.sh): the register budget the compiler works with
+#define RSQ_SCAN_BOUNDS kWarpsPerCta * 32, RSQ_SCAN_MINBLOCKS
+#else
+#define RSQ_SCAN_BOUNDS kWarpsPerCta * 32
+#endif
+template<> __global__ void __launch_bounds__(RSQ_SCAN_BOUNDS)
 k_spec_scan<false>(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){ spec_scan_body<false>(c, sp, descs, first_desc, unit_first, unit_end); }
 template<> __global__ void __launch_bounds__(kWarpsPerCta * 32, 5)   // 96 registers: 20 warps per SM
 k_spec_scan<true>(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){ spec_scan_body<true>(c, sp, descs, first_desc, unit_first, unit_end); }
@@ -554,6 +596,10 @@ k_spec_scan<true>(const __grid_constant__ SimCtx c, const __grid_constant__ Spec
 // products of every read are computed cooperatively (the lanes of a group of 8/16/32 take consecutive candidates of one
 // read: coalesced table rows) and parked in shared memory; each lane then runs the two strictly ordered FP64 sums of
 // its own read.
+#ifndef RSQ_PROD_UNROLL
+#define RSQ_PROD_UNROLL 4   // candidates per lane whose four table-row loads are in flight together (each trip of the product loop waits one L2 round trip)
+#endif
+constexpr int kProdUnroll = RSQ_PROD_UNROLL;
 __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint32_t stride, uint32_t n_rows, bool active, uint32_t table_id,
                                                uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, double u, bool &zero){
 	const unsigned amask = __ballot_sync(0xffffffffu, active);
@@ -585,7 +631,7 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 		const bool four = __shfl_sync(0xffffffffu, nm, src) > 3u;
 		double *row = buf + src * stride;
 		if((amask >> src) & 1u){
-#pragma unroll 4
+#pragma unroll kProdUnroll
 			for(uint32_t idx = i; idx < n4; idx += lpr){
 				double p = 0.0;
 				if(idx < sn0){
@@ -740,18 +786,25 @@ __device__ __forceinline__ void spec_reads_body(const SimCtx &c, const SpecCtx &
 		if(have){ job = sp.jobs[gidx]; }
 	}
 	if(!__any_sync(0xffffffffu, have)){ return; }
-	const uint64_t *slice = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
+	const uint64_t *slice = spec_slice(sp, gidx);
 	unsigned char *slot = sp.slots + static_cast<size_t>(have ? job.slot : 0u) * sp.slot_stride;
+	// behind the product rows of all warps: one slice window per read-owning lane
+	unsigned char *window = smem + static_cast<size_t>(kSpecReadWarps) * lanes_per_warp * stride * sizeof(double) + (static_cast<size_t>(warp) * lanes_per_warp + (lane < lanes_per_warp ? lane : 0u)) * kSpecWindowBytes;
 	uint32_t consumed = 0, rec_len = 0;
 	auto draw_fn = [&](bool active, uint32_t table, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, double u, bool &zero) -> uint32_t {
 		return coop_draw(c.tab, buf, stride, lanes_per_warp, active, table, i0, i1, i2, i3, u, zero);
 	};
 	auto any_fn = [](bool p) -> bool { return __any_sync(0xffffffffu, p); };
-	run_read_machine<kVar>(c, sp, have, job, slice, slot, draw_fn, any_fn, consumed, rec_len);
+	run_read_machine<kVar>(c, sp, have, job, slice, slot, draw_fn, any_fn, consumed, rec_len, window);
 	if(have){ sp.jobs[gidx].consumed = consumed; sp.jobs[gidx].rec_len = rec_len; }
 }
 template<bool kVar> __global__ void k_spec_reads(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end);
-template<> __global__ void __launch_bounds__(kSpecReadWarps * 32)
+#ifdef RSQ_READS_MINBLOCKS
+#define RSQ_READS_BOUNDS kSpecReadWarps * 32, RSQ_READS_MINBLOCKS
+#else
+#define RSQ_READS_BOUNDS kSpecReadWarps * 32
+#endif
+template<> __global__ void __launch_bounds__(RSQ_READS_BOUNDS)
 k_spec_reads<false>(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){ spec_reads_body<false>(c, sp, stride, lanes_per_warp, unit_first, unit_end); }
 template<> __global__ void __launch_bounds__(kSpecReadWarps * 32, 5)
 k_spec_reads<true>(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){ spec_reads_body<true>(c, sp, stride, lanes_per_warp, unit_first, unit_end); }
@@ -1027,7 +1080,7 @@ struct rsq_engine {
 	DevBuf<uint64_t> d_seq_off; DevBuf<uint32_t> d_seq_len, d_gc_prefix, d_name_off, d_cov_group;
 	DevBuf<uint8_t> d_ref, d_sys_fwd, d_sys_rev;
 	DevBuf<double> d_sur_start, d_sur_end, d_thr, d_binom_p0;
-	DevBuf<uint64_t> d_thr_int;
+	DevBuf<uint64_t> d_thr_int; DevBuf<uint32_t> d_thr_hi;
 	DevBuf<char> d_names;
 	DevBuf<uint64_t> d_master_state, d_master, d_jump_states, d_jump_poly, d_jump_seq, d_jump_scratch;
 	DevBuf<BlockDesc> d_blocks;
@@ -1049,7 +1102,7 @@ struct rsq_engine {
 	PinnedBuf h_ref_stage;
 	std::vector<uint64_t> h_seq_off;
 	uint64_t total_size = 0;
-	uint32_t n_blocks_total = 0, n_blocks_sim = 0, shard_first = 0, shard_n = 0;
+	uint32_t n_blocks_total = 0, n_blocks_sim = 0, shard_first = 0, shard_n = 0, spec_units_last = 0;
 	bool shard_has_adapter_only = false;
 	uint64_t adapter_only_seed = 0;
 	uint64_t total_pairs = 0, adapter_only_pairs = 0;
@@ -1840,9 +1893,9 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		std::memcpy(maxb.data(), e.h_bias_results.p + sums.size() * 8, maxb.size() * 8);
 	}
 	if(!finish_normalization(e.norm, p, rsb, spline, params, sums, maxb, e.total_pairs, e.num_alleles, e.with_var)){ throw std::runtime_error("bias normalisation is zero"); }
-	e.d_thr.upload(e.norm.thresholds, s); e.d_thr_int.upload(e.norm.thr_int, s); e.d_binom_p0.upload(e.norm.binom_p0, s); e.d_cov_group.upload(e.norm.coverage_groups, s);
+	e.d_thr.upload(e.norm.thresholds, s); e.d_thr_int.upload(e.norm.thr_int, s); e.d_thr_hi.upload(e.norm.thr_hi, s); e.d_binom_p0.upload(e.norm.binom_p0, s); e.d_cov_group.upload(e.norm.coverage_groups, s);
 	if(e.with_var){ e.d_binom_pow.upload(e.norm.binom_pow, s); c.binom_pow = e.d_binom_pow.p; }
-	c.thr = e.d_thr.p; c.thr_int = e.d_thr_int.p; c.binom_p0 = e.d_binom_p0.p; c.coverage_group = e.d_cov_group.p; c.bias_normalization = e.norm.bias_normalization;
+	c.thr = e.d_thr.p; c.thr_int = e.d_thr_int.p; c.thr_hi = e.d_thr_hi.p; c.thr_hi_stride = e.norm.thr_hi_stride; c.binom_p0 = e.d_binom_p0.p; c.coverage_group = e.d_cov_group.p; c.bias_normalization = e.norm.bias_normalization;
 	RSQ_CUDA(cudaStreamSynchronize(s));
 	ms_bias += tm.stop();
 	if(rep){ rep->ms_bias = ms_bias; rep->bias_normalization = e.norm.bias_normalization; rep->ms_syserr = ms_syserr; }
@@ -1977,32 +2030,35 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 		sp.em_seq = records->em_seq; sp.em_sys = records->em_sys; sp.em_ids = records->em_ids;
 	}
 	const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);   // ReadLengths().to(): one past the longest read
-	sp.words_per_job = 3 * max_rl + 8 + kSpecMargin;
+	sp.words_per_job = (3 * max_rl + 8 + kSpecMargin + 7u) & ~7u;   // whole 64-byte pieces (ReadMachineT::win_issue)
 	sp.margin = getenv("RSQ_SPEC_MARGIN") ? std::min<uint32_t>(kSpecMargin, atoi(getenv("RSQ_SPEC_MARGIN"))) : kSpecMargin;   // tests: 0 forces the serial fallback
 	// Depth (reads speculated per unit and round) and reads per warp are chosen per batch of rounds from a cost model:
 	//   a round costs max(latency, throughput) with latency ~ 1.0 ms + 0.12 ms per read of depth (one lock-step pass over a read
-	//   + the scan in front of `depth` reads) and throughput ~ 5e-5 ms per read in flight plus 1.5 reads' worth of fixed work per
-	//   unit (verification, snapshot restore/save) on a B200 (measured at 4.6 and 60 Mbp);
+	//   + the scan in front of `depth` reads) and throughput ~ 3.2e-5 ms per read in flight plus 3 reads' worth of fixed work per
+	//   unit (verification, snapshot restore/save) on a B200 (measured at 4.6 and 100 Mbp: 5.3 ms per round of 4641 x 32 reads);
 	//   it verifies (1 - p^d) / (1 - p) reads per unit, p = measured share of reads whose assumption held.
 	// Small runs are latency bound (few reads per warp), large ones throughput bound; how deep to speculate mostly depends on p.
 	const uint64_t warps_cap = static_cast<uint64_t>(dev_sms) * 16;
-	const int fixed_depth = getenv("RSQ_SPEC_DEPTH") ? std::min(32, std::max(1, atoi(getenv("RSQ_SPEC_DEPTH")))) : 0;
+	const int fixed_depth = getenv("RSQ_SPEC_DEPTH") ? std::min<int>(depth_cap, std::max(1, atoi(getenv("RSQ_SPEC_DEPTH")))) : 0;
 	const int fixed_lanes = getenv("RSQ_SPEC_LANES") ? atoi(getenv("RSQ_SPEC_LANES")) : 0;
 	uint32_t depth = depth_cap;   // capacity per unit (array stride)
 	if(fixed_depth){ depth = fixed_depth; }
-	if(const char *env = getenv("RSQ_SPEC_MAX_DEPTH")){ depth = std::max<uint32_t>(fixed_depth, std::min(32, std::max(1, atoi(env)))); }
+	if(const char *env = getenv("RSQ_SPEC_MAX_DEPTH")){ depth = std::max<uint32_t>(fixed_depth, std::min<int>(depth_cap, std::max(1, atoi(env)))); }
 	sp.depth = depth;
 	const double draws_per_read = records ? 0.0 : static_cast<double>(e.total_size) * (c.insert_to - c.insert_from) / (2.0 * std::max<uint64_t>(1, e.total_pairs));
 	const double budget_factor = getenv("RSQ_SPEC_BUDGET") ? atof(getenv("RSQ_SPEC_BUDGET")) : 1.5;
+	double lat_fixed = 1.0, lat_per_read = 0.12;
+	if(const char *env = getenv("RSQ_SPEC_LAT")){ sscanf(env, "%lf,%lf", &lat_fixed, &lat_per_read); }   // tuning runs
+	const bool trace = getenv("RSQ_SPEC_TRACE") != nullptr;
 	uint32_t lanes = 32;
 	auto choose = [&](uint64_t active, double p_hold){
 		uint32_t best_d = 2; double best = -1.0;
-		static const uint32_t cand[] = {2, 3, 4, 6, 8, 12, 16, 24, 32};
+		static const uint32_t cand[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
 		for(uint32_t d : cand){
 			if(d > depth){ break; }
 			const double prog = p_hold >= 0.9999 ? d : (1.0 - std::pow(p_hold, static_cast<double>(d))) / (1.0 - p_hold);
-			const double latency = records ? 0.6 + 0.01 * d : 1.0 + 0.12 * d;   // seqToIllumina units have no scan in front of their reads
-			const double cost = std::max(latency, 5.0e-5 * static_cast<double>(active) * (1.5 + d));
+			const double latency = records ? 0.6 + 0.01 * d : lat_fixed + lat_per_read * d;   // seqToIllumina units have no scan in front of their reads
+			const double cost = std::max(latency, 3.2e-5 * static_cast<double>(active) * (3.0 + d));
 			if(prog / cost > best){ best = prog / cost; best_d = d; }
 		}
 		if(fixed_depth){ best_d = fixed_depth; }
@@ -2014,25 +2070,25 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 		lanes = reads <= warps_cap * 8 ? 8 : (reads <= warps_cap * 16 ? 16 : 32);   // 32 once the reads of a round no longer fit one wave anyway
 		if(fixed_lanes){ lanes = fixed_lanes >= 32 ? 32 : (fixed_lanes >= 16 ? 16 : 8); }
 	};
-	choose(sp.n_units, 0.95);
+	choose(sp.n_units, 0.99);   // before the first poll has measured it: InDels are rare in every profile seen so far (E. coli: 58 ms starting deep, 60 ms starting at depth 8)
 	res.depth = sp.run_depth;
 	const size_t n_jobs = static_cast<size_t>(sp.n_units) * depth;
 	const size_t n_tiles = (n_jobs + 31) / 32;
 	e.d_spec_blocks.alloc(sp.n_units); e.d_spec_snaps.alloc(2 * static_cast<size_t>(sp.n_units) * (depth + 1)); e.d_spec_jobs.alloc(n_tiles * 32);
-	e.d_spec_words.alloc(n_tiles * sp.words_per_job * 32);
+	e.d_spec_words.alloc(n_tiles * 32 * sp.words_per_job);
 	sp.blocks = e.d_spec_blocks.p; sp.snaps = e.d_spec_snaps.p; sp.jobs = e.d_spec_jobs.p; sp.words = e.d_spec_words.p;
 	const bool with_var = c.var.loaded != 0 && !records;
 	if(c.meth_loaded || with_var){ e.d_spec_conv.alloc(static_cast<size_t>(sp.n_units) * kConvSlots * 2 * kMaxOrgLen); sp.conv = e.d_spec_conv.p; }
 	sp.chosen_stride = with_var ? 2 * c.var.num_alleles : 0;
 	if(with_var){ e.d_spec_chosen.alloc(2 * static_cast<size_t>(sp.n_units) * (depth + 1) * sp.chosen_stride); sp.snap_chosen = e.d_spec_chosen.p; }
-	const size_t scan_shmem = with_var ? static_cast<size_t>(kWarpsPerCta) * sp.chosen_stride * sizeof(uint16_t) : 0;
+	const size_t scan_shmem = static_cast<size_t>(kWarpsPerCta) * c.thr_hi_stride * sizeof(uint32_t) + (with_var ? static_cast<size_t>(kWarpsPerCta) * sp.chosen_stride * sizeof(uint16_t) : 0);
 	const uint32_t id_prefix = records ? e.em_max_id_len + 1 : c.base_id_len + 10 + 1 + 20 + (with_var ? 10 : 0) + 1 + 10 + 1 + std::max<uint32_t>(e.max_name_len, 7) + 1 + 10 + 1 + 5 + 11;
 	sp.id_cap = std::min<uint32_t>(kIdCap, (id_prefix + kCigarCap + 2 + 10 + 15) & ~15u);
 	sp.seq_off = 16 + sp.id_cap; sp.qual_off = sp.seq_off + ((max_rl + 3) & ~3u); sp.slot_stride = (sp.qual_off + max_rl + 15) & ~15u;
 	e.d_spec_counters.alloc(8); e.h_spec_counters.ensure(8 * sizeof(uint32_t));
 	sp.next_slab = e.d_spec_counters.p; sp.n_done = e.d_spec_counters.p + 1; sp.stat = reinterpret_cast<unsigned long long *>(e.d_spec_counters.p + 2);
 	// units are split into independent groups on their own streams: the scan of one group overlaps the reads of another
-	uint32_t n_groups = 2;
+	uint32_t n_groups = sp.n_units <= 20000u ? 4 : 2;   // small runs: shorter kernels, more of them in flight (E. coli: 62.7 ms with four groups, 64.1 with two)
 	if(const char *env = getenv("RSQ_SPEC_GROUPS")){ n_groups = std::min(4, std::max(1, atoi(env))); }
 	n_groups = std::max<uint32_t>(1, std::min<uint32_t>(n_groups, sp.n_units));
 	while(e.spec_streams.size() < n_groups){
@@ -2040,21 +2096,22 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 		cudaEvent_t ev; RSQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e.spec_events.push_back(ev);
 	}
 	const uint32_t stride = ((e.max_n0_reads + 3u) & ~3u) + 1u;
-	const size_t shmem_reads_max = static_cast<size_t>(kSpecReadWarps) * 32 * stride * sizeof(double);
+	const size_t shmem_reads_max = static_cast<size_t>(kSpecReadWarps) * 32 * (stride * sizeof(double) + kSpecWindowBytes);
 	auto scan_kernel = with_var ? k_spec_scan<true> : k_spec_scan<false>;
 	auto reads_kernel = with_var ? k_spec_reads<true> : k_spec_reads<false>;
 	RSQ_CUDA(cudaFuncSetAttribute(reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem_reads_max)));
+	if(scan_shmem > 24 * 1024){ RSQ_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scan_shmem))); }   // 20 KB of static rings on top
 	const double share = e.n_blocks_sim ? static_cast<double>(u_count) / e.n_blocks_sim : 0.0;
 	uint64_t expected_reads = records ? records->em_n + 2048ull : static_cast<uint64_t>(2.0 * (e.total_pairs * share + sp.adapter_only_pairs) * 1.15) + 2048;
 	float ms_sim = 0;
 	uint32_t rounds = 0;
 	for(int attempt = 0; ; ++attempt){
-		sp.n_slabs = static_cast<uint32_t>(expected_reads / 32 + 2ull * sp.n_units + 64);
+		sp.n_slabs = static_cast<uint32_t>(expected_reads / 32 + 3ull * sp.n_units + 64);
 		e.d_spec_slots.alloc(static_cast<size_t>(sp.n_slabs) * 32 * sp.slot_stride);
 		e.d_slab_next.alloc(sp.n_slabs); e.d_slab_count.alloc(sp.n_slabs);
 		sp.slots = e.d_spec_slots.p; sp.slab_next = e.d_slab_next.p; sp.slab_count = e.d_slab_count.p;
 		e.d_spec_counters.zero(s);
-		choose(sp.n_units, 0.95);
+		choose(sp.n_units, 0.99);   // before the first poll has measured it: InDels are rare in every profile seen so far (E. coli: 58 ms starting deep, 60 ms starting at depth 8)
 		EventTimer tm(s);
 		tm.start();
 		rounds = 0;
@@ -2075,7 +2132,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 						scan_kernel<<<(u1 - u0 + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, scan_shmem, gs>>>(c, sp, e.d_blocks.p, first_desc, u0, u1);
 						const size_t extra = (sp.n_units > sp.n_blocks && u1 == sp.n_units && sp.depth > sp.run_depth) ? sp.depth - sp.run_depth : 0;
 						const size_t warps = (static_cast<size_t>(u1 - u0) * sp.run_depth + extra + lanes - 1) / lanes;
-						const size_t shmem_reads = static_cast<size_t>(kSpecReadWarps) * lanes * stride * sizeof(double);
+						const size_t shmem_reads = static_cast<size_t>(kSpecReadWarps) * lanes * (stride * sizeof(double) + kSpecWindowBytes);
 						reads_kernel<<<static_cast<unsigned>((warps + kSpecReadWarps - 1) / kSpecReadWarps), kSpecReadWarps * 32, shmem_reads, gs>>>(c, sp, stride, lanes, u0, u1);
 						e.launches += 2;
 					}
@@ -2090,6 +2147,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 				RSQ_CUDA(cudaMemcpyAsync(e.h_spec_counters.p, e.d_spec_counters.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 				RSQ_CUDA(cudaEventRecord(e.ev_fork, s));
 				RSQ_CUDA(cudaStreamSynchronize(s));
+				if(trace){ fprintf(stderr, "[spec] rounds=%u run_depth=%u lanes=%u budget=%u done=%u/%u emitted=%llu verified=%llu\n", rounds, sp.run_depth, lanes, sp.scan_budget, *h_done, sp.n_units, (unsigned long long)h_stat[0], (unsigned long long)h_stat[1]); }
 				if(*h_done >= sp.n_units){ break; }
 				{
 					const unsigned long long em = h_stat[0], ve = h_stat[1];
@@ -2129,7 +2187,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 		if(flag){ throw std::runtime_error("device reported: " + describe_flag(flag)); }
 		break;
 	}
-	res.rounds = rounds; res.ms_sim = ms_sim;
+	res.rounds = rounds; res.ms_sim = ms_sim; e.spec_units_last = sp.n_units;
 	// ordered FASTQ text
 	EventTimer tm(s);
 	tm.start();
@@ -2310,6 +2368,9 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 	const double budget = 0.85 * (static_cast<double>(free_b) + e.reusable_bytes());
 	uint32_t depth_cap = 32;
 	uint64_t per_batch = e.shard_n;
+	// (twice the depth per round, RSQ_SPEC_CAP=64, was measured on E. coli: four rounds fewer, but each scan and each lock-step pass over the reads
+	// of a round takes as much longer - 65 ms instead of 64; the capacity stays an option for profiles with rarer InDels)
+	if(const char *env = getenv("RSQ_SPEC_CAP")){ if(!meth && !c.var.loaded && atoi(env) > 32){ depth_cap = kSpecMaxDepth; } }
 	if(unit_bytes(32) * e.shard_n > budget){ depth_cap = 16; per_batch = std::max<uint64_t>(1024, static_cast<uint64_t>(budget / unit_bytes(16))); }
 	if(const char *env = getenv("RSQ_BATCH_UNITS")){ per_batch = std::max(1, atoi(env)); }
 	const uint32_t n_batches = e.shard_n ? static_cast<uint32_t>((e.shard_n + per_batch - 1) / per_batch) : 1;
@@ -2939,6 +3000,7 @@ int rsq_engine_fetch(const rsq_engine *engine, const char *name, void *dst, uint
 	else if(n == "reference"){ src = engine->d_ref.p; nb = engine->total_size; }
 	else if(n == "thresholds"){ src = engine->norm.thresholds.data(); nb = 8 * engine->norm.thresholds.size(); host = true; }
 	else if(n == "blocks"){ src = engine->d_blocks.p; nb = sizeof(BlockDesc) * engine->n_blocks_total; }
+	else if(n == "spec_blocks"){ src = engine->d_spec_blocks.p; nb = sizeof(SpecBlock) * engine->spec_units_last; }   // per-unit counters of the last speculative batch (rounds, reads, scan draws): tuning
 	else{ throw std::runtime_error("unknown stage array '" + n + "'"); }
 	if(bytes){ *bytes = nb; }
 	const uint64_t cnt = std::min(nb, capacity);

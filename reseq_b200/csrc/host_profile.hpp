@@ -717,6 +717,8 @@ struct Normalization {
 	std::vector<double> thresholds;     // [group][len][2]
 	std::vector<double> binom_p0;       // [group][len]   pow(1-(1-thr0), 2 * alleles): Binomial's first term when every allele is possible
 	std::vector<uint64_t> thr_int;      // [group][len]
+	std::vector<uint32_t> thr_hi;       // [group][thr_hi_stride] high words of thr_int (rows padded to 16 bytes with 0xffffffff)
+	uint32_t thr_hi_stride = 0;
 	std::vector<double> binom_pow;      // [group][len][2 * alleles + 1]   pow(1-(1-thr0), N) for N possible strands (runs with variants only)
 };
 
@@ -795,6 +797,11 @@ inline bool finish_normalization(Normalization &out, const Profile &p, const std
 				for(uint32_t n = 0; n <= 2 * num_alleles; ++n){ out.binom_pow[i * (2 * num_alleles + 1) + n] = std::pow(1 - pp, static_cast<uint16_t>(n)); }
 			}
 		}
+	}
+	out.thr_hi_stride = (to + 128u + 3u) & ~3u;   // + 128 entries that no draw reaches: the scan's four-trip filter reads up to 127 entries past the longest insert
+	out.thr_hi.assign(static_cast<size_t>(out.num_groups) * out.thr_hi_stride, 0xffffffffu);
+	for(uint32_t g = 0; g < out.num_groups; ++g){
+		for(uint32_t len = 0; len < to; ++len){ out.thr_hi[static_cast<size_t>(g) * out.thr_hi_stride + len] = static_cast<uint32_t>(out.thr_int[static_cast<size_t>(g) * to + len] >> 32); }
 	}
 	out.bias_normalization = full;
 	return full != 0.0;

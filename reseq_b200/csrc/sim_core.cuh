@@ -69,6 +69,8 @@ struct SimCtx {
 	const uint32_t *coverage_group;    // [n_seqs]
 	const double *thr;                 // [group][insert_to][2]  non_zero_thresholds_
 	const uint64_t *thr_int;           // [group][insert_to]     smallest raw draw x with canonical(x) >= thr[..][1] (filter only)
+	const uint32_t *thr_hi;            // [group][thr_hi_stride] high words of thr_int: the speculative scan's first filter (staged in shared memory)
+	uint32_t thr_hi_stride;            // insert_to + 128 entries of padding (0xffffffff), rounded up to 4 entries (16-byte rows for the bulk copy)
 	const double *binom_p0;            // [group][insert_to]     pow(1-(1-thr0), 2) (Binomial's first term, host libm)
 	// --- reference ---
 	uint32_t n_seqs;

@@ -24,6 +24,11 @@ namespace rsq {
 
 constexpr uint32_t kSpecNone = 0xffffffffu;
 constexpr uint32_t kSpecOverflow = 0xffffffffu;   // ReadJob::consumed when the slice (assumed + margin) was too short
+constexpr uint32_t kSpecMaxDepth = 64;            // reads speculated per unit and round at most (three output slabs of 32 slots)
+#ifndef RSQ_SLICE_WINDOW
+#define RSQ_SLICE_WINDOW 0   // 1: the reads kernel streams its slices through bulk-copy windows in shared memory (measured slower: E. coli 69.4 ms against 59.5, 100 Mbp 1172 ms against 1006 - 144 bytes of shared memory per lane cost a block per SM and every eighth word a barrier wait); 0: through four prefetch registers
+#endif
+constexpr uint32_t kSpecWindowBytes = RSQ_SLICE_WINDOW ? 144 : 0;   // shared memory per lane of the reads kernel for its slice window (ReadMachineT::win)
 constexpr uint32_t kSpecMargin = 32;              // extra stream words copied behind the assumed consumption
 constexpr uint32_t kConvSlots = 20;               // bisulfite-converted fragment ends kept per unit (>= depth / 2 + 3: one per hit of a round + the committed one)
 constexpr uint32_t kErrSpecOverflow = 64;         // error flag: a read needed more than assumed + margin draws
@@ -146,7 +151,8 @@ struct SpecBlock {
 	uint32_t pending_skip;         // ... plus this many stream words (the measured consumption of the read behind it)
 	uint32_t n_jobs;               // reads emitted in the last round (speculative until verified)
 	uint32_t fill;                 // verified records in cur_slab
-	uint32_t cur_slab, next_slab;  // output slabs (32 slots) being filled
+	uint32_t cur_slab, next_slab;  // output slabs (32 slots) being filled: slots fill .. of cur_slab, then next_slab, then next2_slab
+	uint32_t next2_slab, pad;      // (fill < 32 verified + up to kSpecMaxDepth = 64 speculative records reach into a third slab)
 	uint32_t chain_head, chain_tail;
 	uint32_t reads, rounds;
 	unsigned long long bytes[2];
@@ -154,7 +160,7 @@ struct SpecBlock {
 };
 
 struct SpecCtx {
-	uint32_t depth;                // D: capacity per unit and round (reads emitted beyond the verified ones, <= 32); array stride
+	uint32_t depth;                // D: capacity per unit and round (reads emitted beyond the verified ones, <= kSpecMaxDepth); array stride
 	uint32_t run_depth;            // reads to emit per unit in this round (<= depth): grows when few units are left
 	uint32_t scan_budget;          // scan draws per unit and round after which the round ends even with < run_depth reads (bounds stragglers)
 	uint32_t words_per_job;        // K: capacity of a read's stream slice
@@ -163,7 +169,7 @@ struct SpecCtx {
 	SpecBlock *blocks;             // [n_units]
 	SpecSnap *snaps;               // [n_units][2 banks][D + 1]: in front of every emitted read + behind the last one
 	ReadJob *jobs;                 // [n_units * D]
-	uint64_t *words;               // [ceil(n_units * D / 32)][K][32] tempered stream words, lane-interleaved per tile of 32 reads
+	uint64_t *words;               // [n_units * D][K] tempered stream words of every speculated read (spec_slice)
 	uint8_t *conv;                 // bisulfite runs / variants: [n_units][kConvSlots][2][kMaxOrgLen] staged (spliced, converted) forward / reverse fragment ends
 	uint16_t *snap_chosen;         // variants: [n_units][2 banks][D + 1][chosen_stride] the chosen (allele, strand) ids of the hit a snapshot stands in
 	uint32_t chosen_stride;        // 2 * num_alleles
@@ -178,6 +184,9 @@ struct SpecCtx {
 	const EmRecord *em_recs; uint32_t em_n, em_batch; const uint64_t *em_seeds;
 	const uint8_t *em_seq, *em_sys; const char *em_ids;   // bases; (dominant error, rate) pairs; id text
 };
+
+// Stream slice of job gidx: words_per_job consecutive words (a multiple of 8: the reads kernel stages them in 64-byte pieces)
+RSQ_HD uint64_t *spec_slice(const SpecCtx &sp, size_t gidx){ return sp.words + gidx * sp.words_per_job; }
 
 RSQ_HD uint32_t spec_alloc_slab(const SpecCtx &sp){
 #if defined(__CUDA_ARCH__)
@@ -245,7 +254,7 @@ RSQ_HD uint32_t fragment_org_len(const SimCtx &c, uint32_t seg, uint32_t fragmen
 // ----------------------------------------------------------------------------------------------------------------
 // Phase A
 // ----------------------------------------------------------------------------------------------------------------
-// Copies n stream words to the slice (word k of the read lives at dst[k * 32]), consuming them; returns the last one.
+// Copies n stream words to the slice (word k of the read lives at dst[k]), consuming them; returns the last one.
 template<class G> RSQ_HD uint64_t emit_words(const G &g, MtRing &r, uint64_t *dst, uint32_t &k, uint32_t cap, uint32_t n, bool consume = true){
 	uint64_t last = 0;
 	uint32_t kk = k;
@@ -253,7 +262,7 @@ template<class G> RSQ_HD uint64_t emit_words(const G &g, MtRing &r, uint64_t *ds
 		const uint32_t m = n < static_cast<uint32_t>(kMtN) ? n : kMtN;
 		ring_ensure(g, r, m);
 		for(uint32_t i = g.lane(); i < m; i += G::kSize){
-			if(kk + i < cap){ dst[static_cast<size_t>(kk + i) * 32u] = mt_temper(ring_raw(r, i)); }
+			if(kk + i < cap){ dst[kk + i] = mt_temper(ring_raw(r, i)); }
 		}
 		last = mt_temper(ring_raw(r, m - 1u));
 		if(consume){ ring_advance(r, m); }
@@ -376,6 +385,20 @@ RSQ_HD void spec_link_slab(const SpecCtx &sp, SpecBlock &blk, uint32_t slab, uin
 	blk.chain_tail = slab;
 }
 
+// A unit's row of threshold high words (SimCtx::thr_hi).  The kernel stages it in shared memory; the load then names the shared state space
+// (a generic load through a pointer that may be global or shared cannot become LDS and costs the fast loop its overlap).
+struct ThrRow {
+	const uint32_t *p;
+#if defined(__CUDA_ARCH__)
+	uint32_t shared_addr;   // device: always staged (k_spec_scan does it for every unit that scans)
+	__device__ ThrRow(const uint32_t *row, bool) : p(row), shared_addr(static_cast<uint32_t>(__cvta_generic_to_shared(row))) {}
+	__device__ __forceinline__ uint32_t at(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr + 4u * i)); return v; }
+#else
+	ThrRow(const uint32_t *row, bool) : p(row) {}
+	uint32_t at(uint32_t i) const { return p[i]; }
+#endif
+};
+
 // One round of one unit (SimBlock, or the adapter-only pseudo block):
 //   1. verify the reads phase B just ran: the prefix up to and including the first read whose consumption differs
 //      from the assumption is final (its own start was exact); commit its records,
@@ -385,7 +408,8 @@ RSQ_HD void spec_link_slab(const SpecCtx &sp, SpecBlock &blk, uint32_t slab, uin
 // Snapshots live in two banks of depth + 1 entries per unit; a round reads the committed one from one bank and writes the other.
 template<bool kVar, class G>
 RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t u, uint64_t *ring_mem,
-                        uint16_t *chosen_live = nullptr /* runs with variants: 2 * num_alleles entries of group-shared memory */){
+                        uint16_t *chosen_live = nullptr /* runs with variants: 2 * num_alleles entries of group-shared memory */,
+                        const uint32_t *thr_hi_staged = nullptr /* this unit's row of c.thr_hi when the caller staged it in shared memory */){
 	SpecBlock &blk = sp.blocks[u];
 	if(blk.done){ return; }
 	const uint32_t D = sp.depth;
@@ -393,7 +417,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	SpecSnap *unit_snaps = sp.snaps + static_cast<size_t>(u) * 2u * (D + 1u);
 	const uint32_t n_prev = blk.n_jobs;
 	uint32_t bank = blk.snap_bank, idx = blk.snap_idx, pending_skip = blk.pending_skip;
-	uint32_t fill = blk.fill, cur_slab = blk.cur_slab, next_slab = blk.next_slab;
+	uint32_t fill = blk.fill, cur_slab = blk.cur_slab, next_slab = blk.next_slab, next2_slab = blk.next2_slab;
 	g.sync();
 	if(n_prev){
 		uint32_t first_bad = kSpecNone, bad_consumed = 0;
@@ -436,9 +460,11 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 			sp.stat[0] += n_prev; sp.stat[1] += v;
 #endif
 			blk.bytes[0] += b0; blk.bytes[1] += b1; blk.reads += v;
-			if(fill >= 32u){ spec_link_slab(sp, blk, cur_slab, 32u); }
 		}
-		if(fill >= 32u){ cur_slab = next_slab; next_slab = kSpecNone; fill -= 32u; }
+		while(fill >= 32u){   // full slabs join the unit's chain (up to two per round)
+			if(g.lane() == 0){ spec_link_slab(sp, blk, cur_slab, 32u); }
+			cur_slab = next_slab; next_slab = next2_slab; next2_slab = kSpecNone; fill -= 32u;
+		}
 		bank ^= 1u;   // the snapshots of the previous round are in the other bank
 		if(all_ok){ idx = D; pending_skip = 0; }
 		else{ idx = first_bad; pending_skip = bad_consumed; }
@@ -488,6 +514,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	const uint32_t group = (adapter_only || records) ? 0u : c.coverage_group[b.ref_id];
 	const double *thr = c.thr + static_cast<size_t>(group) * c.insert_to * 2;
 	const uint64_t *thr_int = c.thr_int + static_cast<size_t>(group) * c.insert_to;
+	const ThrRow thr_row(thr_hi_staged ? thr_hi_staged : c.thr_hi + static_cast<size_t>(group) * c.thr_hi_stride, thr_hi_staged != nullptr);
 	const double *binom_p0 = c.binom_p0 + static_cast<size_t>(group) * c.insert_to;
 	const uint32_t *gcp = c.gc_prefix + off + b.ref_id;
 	const uint32_t insert_from = c.insert_from, insert_to = c.insert_to;
@@ -505,18 +532,18 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 			hit.tile = 0;
 			if(1 < c.num_tiles){ hit.tile = discrete_lookup(c.tile_pick, canonical(ring_next(g, ring))); }
 			const uint32_t p = fill + emitted;
-			uint32_t slab = p < 32u ? cur_slab : next_slab;
+			uint32_t slab = p < 32u ? cur_slab : (p < 64u ? next_slab : next2_slab);
 			if(slab == kSpecNone){
 				if(g.lane() == 0){ slab = spec_alloc_slab(sp); }
 #if defined(__CUDA_ARCH__)
 				slab = __shfl_sync(0xffffffffu, slab, 0);
 #endif
 				if(slab == kSpecNone){ failed = true; break; }
-				if(p < 32u){ cur_slab = slab; } else{ next_slab = slab; }
+				if(p < 32u){ cur_slab = slab; } else if(p < 64u){ next_slab = slab; } else{ next2_slab = slab; }
 			}
 			save_snapshot(g, ring, out_snaps[emitted], pos, len, false, hit, cur_meth, read_number, draws);
 			const size_t gidx = static_cast<size_t>(u) * D + emitted;
-			uint64_t *dst = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
+			uint64_t *dst = spec_slice(sp, gidx);
 			const uint32_t org_len = rec.len < c.max_org_len ? rec.len : c.max_org_len;
 			const uint32_t assumed = plan_read(g, c, ring, dst, sp.words_per_job, sp.margin, rec.seg, rec.fragment_length, org_len);
 			if(g.lane() == 0){
@@ -547,19 +574,19 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 						if(emitted >= D_run){ full = true; break; }
 						const uint32_t seg = 1u - hit.pair_stage;
 						const uint32_t p = fill + emitted;
-						uint32_t slab = p < 32u ? cur_slab : next_slab;
+						uint32_t slab = p < 32u ? cur_slab : (p < 64u ? next_slab : next2_slab);
 						if(slab == kSpecNone){
 							if(g.lane() == 0){ slab = spec_alloc_slab(sp); }
 #if defined(__CUDA_ARCH__)
 							slab = __shfl_sync(0xffffffffu, slab, 0);
 #endif
 							if(slab == kSpecNone){ failed = true; break; }
-							if(p < 32u){ cur_slab = slab; } else{ next_slab = slab; }
+							if(p < 32u){ cur_slab = slab; } else if(p < 64u){ next_slab = slab; } else{ next2_slab = slab; }
 						}
 						save_snapshot(g, ring, out_snaps[emitted], pos, len, false, hit, cur_meth, read_number, draws,
 						              ScanVarState{first_var, start_variant_pos, chosen_live, with_var ? chosen_bank_out + static_cast<size_t>(emitted) * sp.chosen_stride : nullptr, hit.n_chosen});
 						const size_t gidx = static_cast<size_t>(u) * D + emitted;
-						uint64_t *dst = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
+						uint64_t *dst = spec_slice(sp, gidx);
 						const uint32_t assumed = plan_read(g, c, ring, dst, sp.words_per_job, sp.margin, seg, hit.fragment_length);
 						if(g.lane() == 0){
 							ReadJob j;
@@ -680,18 +707,24 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 				}
 			}
 			const uint32_t lane = g.lane();
-			if(insert_to - len >= 4u * G::kSize){
-				// four independent trips at once (hits are rare: ~1 in several thousand draws): the loads and the tempering of
-				// the four overlap instead of waiting on each other
-				ring_ensure(g, ring, 4u * G::kSize);
+			{
+				// First filter, four independent trips at once (hits are rare: ~1 in several thousand draws, so the loads and the tempering of
+				// the four overlap instead of waiting on each other): only the high word of the tempered draw against the high word of the
+				// threshold.  A draw that fails it cannot be a hit; the trip that holds a candidate goes through the exact test below.
+				uint32_t n4 = insert_to - len;
+				if(n4 > 4u * G::kSize){ n4 = 4u * G::kSize; }
+				ring_ensure(g, ring, n4);
 				bool any_hit = false;
+				// all four loads are unconditional (a branch per trip would serialise them): behind the last length of a position the ring holds
+				// older words and the threshold row its padding of 0xffffffff; what they say is masked out
 #pragma unroll
 				for(uint32_t q = 0; q < 4u; ++q){
-					const uint64_t xq = mt_temper(ring_raw(ring, q * G::kSize + lane));
-					any_hit |= xq >= thr_int[len + q * G::kSize + lane];
+					const uint32_t i = q * G::kSize + lane;
+					const bool cand = mt_temper_hi(ring_raw(ring, i)) >= thr_row.at(len + i);
+					any_hit |= cand & (i < n4);
 				}
 				if(g.ballot(any_hit) == 0){
-					ring_advance(ring, 4u * G::kSize); len += 4u * G::kSize; draws += 4u * G::kSize;
+					ring_advance(ring, n4); len += n4; draws += n4;
 					if(draws >= draws_limit){ full = true; break; }
 					continue;
 				}
@@ -762,7 +795,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	              ScanVarState{first_var, start_variant_pos, chosen_live, with_var ? chosen_bank_out + static_cast<size_t>(D) * sp.chosen_stride : nullptr, hit.n_chosen});
 	if(g.lane() == 0){
 		blk.snap_bank = bank; blk.snap_idx = idx; blk.pending_skip = pending_skip;
-		blk.n_jobs = emitted; blk.fill = fill; blk.cur_slab = cur_slab; blk.next_slab = next_slab; blk.rounds += 1;
+		blk.n_jobs = emitted; blk.fill = fill; blk.cur_slab = cur_slab; blk.next_slab = next_slab; blk.next2_slab = next2_slab; blk.rounds += 1;
 		if(0 == emitted && finished){
 			// nothing left to verify: the state behind the last verified read is exact and the unit is through
 			if(fill){ spec_link_slab(sp, blk, cur_slab, fill); }
@@ -781,7 +814,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 // inside CreateReads with all its pairs left).
 RSQ_HD void spec_init_unit(const SimCtx &c, const SpecCtx &sp, const BlockDesc *descs, uint32_t first_desc, uint32_t u){
 	SpecBlock &blk = sp.blocks[u];
-	blk.done = 0; blk.snap_bank = 0; blk.snap_idx = 0; blk.pending_skip = 0; blk.n_jobs = 0; blk.fill = 0; blk.cur_slab = kSpecNone; blk.next_slab = kSpecNone;
+	blk.done = 0; blk.snap_bank = 0; blk.snap_idx = 0; blk.pending_skip = 0; blk.n_jobs = 0; blk.fill = 0; blk.cur_slab = kSpecNone; blk.next_slab = kSpecNone; blk.next2_slab = kSpecNone; blk.pad = 0;
 	blk.chain_head = kSpecNone; blk.chain_tail = kSpecNone;
 	blk.reads = 0; blk.rounds = 0; blk.bytes[0] = 0; blk.bytes[1] = 0; blk.scan_draws = 0;
 	SpecSnap &s = sp.snaps[static_cast<size_t>(u) * 2u * (sp.depth + 1u)];
@@ -824,7 +857,11 @@ enum : uint32_t { kPhFrag = 0, kPhAdapter = 1, kPhTail = 2, kPhOverrun = 3, kPhD
 template<bool kVar> struct ReadMachineT {
 	// stream slice
 	const uint64_t *words; uint32_t k, kcap; uint32_t overflow;
-	uint64_t w0, w1, w2, w3;   // words k .. k+3, loaded ahead of their use (the slice streams from HBM/L2 exactly once)
+	// Device: the slice streams from HBM through a two-piece window in shared memory, 8 words (64 bytes) per piece, filled by bulk asynchronous
+	// copies (cp.async.bulk, one mbarrier per piece) that this lane issues one piece ahead of its own consumption - no registers wait on the loads.
+	//   window layout at `win` (shared-space address, 144 bytes per lane): piece 0 | piece 1 | mbarrier 0 | mbarrier 1
+	uint32_t win, win_phase, win_pending, kslice;
+	uint64_t w0, w1, w2, w3;   // RSQ_SLICE_WINDOW == 0: words k .. k+3, loaded ahead of their use
 	// output
 	uint8_t *seq_out, *qual_out; char *id; int id_len, id_cap, cigar_len;
 	// job
@@ -848,17 +885,62 @@ template<bool kVar> struct ReadMachineT {
 		return wc;
 	}
 
+#if defined(__CUDA_ARCH__) && RSQ_SLICE_WINDOW
+	__device__ __forceinline__ void win_issue(uint32_t chunk){   // words [8 * chunk, 8 * chunk + 8) into piece chunk & 1
+		const uint32_t h = chunk & 1u, bar = win + 128u + 8u * h;
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 64;" :: "r"(bar) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];"
+		             :: "r"(win + 64u * h), "l"(words + 8u * chunk), "r"(bar) : "memory");
+		win_pending |= 1u << h;
+	}
+	__device__ __forceinline__ void win_wait(uint32_t h){
+		const uint32_t bar = win + 128u + 8u * h, parity = (win_phase >> h) & 1u;
+		asm volatile("{\n.reg .pred p;\nRSQ_WIN_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra RSQ_WIN_DONE;\nbra RSQ_WIN_WAIT;\nRSQ_WIN_DONE:\n}"
+		             :: "r"(bar), "r"(parity) : "memory");
+		win_phase ^= 1u << h; win_pending &= ~(1u << h);
+	}
+#endif
 	RSQ_HD void load_window(){
-		w0 = words[static_cast<size_t>(k) * 32u]; w1 = words[static_cast<size_t>(k + 1u) * 32u];
-		w2 = words[static_cast<size_t>(k + 2u) * 32u]; w3 = words[static_cast<size_t>(k + 3u) * 32u];
+#if defined(__CUDA_ARCH__) && RSQ_SLICE_WINDOW
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(win + 128u) : "memory");
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(win + 136u) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		win_phase = 0; win_pending = 0;
+		win_issue(0);
+		if(8u < kslice){ win_issue(1); }
+#elif defined(__CUDA_ARCH__)
+		w0 = words[k]; w1 = words[k + 1u]; w2 = words[k + 2u]; w3 = words[k + 3u];
+#endif
+	}
+	// a lane leaves no copy in flight behind it (the shared memory may be handed to another block)
+	RSQ_HD void drain_window(){
+#if defined(__CUDA_ARCH__) && RSQ_SLICE_WINDOW
+		if(win_pending & 1u){ win_wait(0); }
+		if(win_pending & 2u){ win_wait(1); }
+#endif
 	}
 	RSQ_HD double next_u(){
 		if(k >= kcap){ overflow = 1; return 0.5; }
-		const uint64_t x = w0;
-		w0 = w1; w1 = w2; w2 = w3;
-		w3 = (k + 4u < kcap) ? words[static_cast<size_t>(k + 4u) * 32u] : 0ull;
+#if defined(__CUDA_ARCH__) && RSQ_SLICE_WINDOW
+		const uint32_t chunk = k >> 3, h = chunk & 1u, i = k & 7u;
+		if(i == 0u){
+			// piece h starts: the other piece was consumed to its last word (its values have been used), refill it with the chunk behind this one
+			if(chunk && (chunk + 1u) * 8u < kslice){ win_issue(chunk + 1u); }
+			win_wait(h);
+		}
+		uint64_t x;
+		asm volatile("ld.shared.u64 %0, [%1];" : "=l"(x) : "r"(win + 64u * h + 8u * i) : "memory");
 		++k;
 		return canonical(x);
+#elif defined(__CUDA_ARCH__)
+		const uint64_t x = w0;
+		w0 = w1; w1 = w2; w2 = w3;
+		w3 = (k + 4u < kcap) ? words[k + 4u] : 0ull;
+		++k;
+		return canonical(x);
+#else
+		return canonical(words[k++]);
+#endif
 	}
 	RSQ_HD uint32_t org_base(uint32_t p) const {
 		const uint32_t b = org[static_cast<int64_t>(org_step) * static_cast<int64_t>(p)];
@@ -900,9 +982,15 @@ template<bool kVar> struct ReadMachineT {
 	}
 
 	// FillRead up to the sequence-quality draw; returns the mean systematic error rate (its second index)
-	RSQ_HD uint32_t begin(const SimCtx &c, const SpecCtx &sp, const ReadJob &j, const uint64_t *slice, unsigned char *slot){
+	RSQ_HD uint32_t begin(const SimCtx &c, const SpecCtx &sp, const ReadJob &j, const uint64_t *slice, unsigned char *slot, void *lane_window){
 		// only assumed + margin words of the slice were written by the scan
 		words = slice; k = 0; kcap = j.assumed + sp.margin < sp.words_per_job ? j.assumed + sp.margin : sp.words_per_job; overflow = 0;
+		kslice = sp.words_per_job;
+#if defined(__CUDA_ARCH__) && RSQ_SLICE_WINDOW
+		win = static_cast<uint32_t>(__cvta_generic_to_shared(lane_window));
+#else
+		(void)lane_window; win = 0; win_phase = 0; win_pending = 0;
+#endif
 		load_window();
 		seg = j.flags & 1u; tile = (j.flags >> 8) & 0xffffu; fragment_length = j.fragment_length;
 		allele = (j.flags >> 24) & 0x7fu; var_slow = 0; var_ref_id = 0; var_reversed = 0; walk = SysWalk{}; walk_sys = nullptr;
@@ -1048,11 +1136,11 @@ template<bool kVar> struct ReadMachineT {
 // is LogArrayResult::Draw for every lane whose `active` is set (all lanes of a group call it together).
 template<bool kVar, class DrawFn, class AnyFn>
 RSQ_HD void run_read_machine(const SimCtx &c, const SpecCtx &sp, bool have_job, const ReadJob &job, const uint64_t *slice, unsigned char *slot,
-                             DrawFn &&draw_fn, AnyFn &&any_fn, uint32_t &consumed, uint32_t &rec_len){
+                             DrawFn &&draw_fn, AnyFn &&any_fn, uint32_t &consumed, uint32_t &rec_len, void *lane_window = nullptr /* device: 144 bytes of shared memory of this lane */){
 	ReadMachineT<kVar> m;
-	m.phase = kPhDone; m.overflow = 0; m.k = 0; m.var_slow = 0;
+	m.phase = kPhDone; m.overflow = 0; m.k = 0; m.var_slow = 0; m.win_pending = 0;
 	uint32_t mean_error_rate = 0;
-	if(have_job){ mean_error_rate = m.begin(c, sp, job, slice, slot); }
+	if(have_job){ mean_error_rate = m.begin(c, sp, job, slice, slot, lane_window); }
 	bool zero = false;
 	{
 		const uint32_t tid = have_job ? c.tab.seq_quality(m.seg, m.tile) : 0u;
@@ -1157,6 +1245,7 @@ RSQ_HD void run_read_machine(const SimCtx &c, const SpecCtx &sp, bool have_job, 
 		}
 	}
 	if(have_job){
+		m.drain_window();
 		rec_len = m.finish(c, slot);
 		consumed = m.overflow ? kSpecOverflow : m.k;
 	}

@@ -219,7 +219,7 @@ int main(int argc, char **argv){
 		}
 	}
 	c.bias_normalization = norm.bias_normalization; c.coverage_group = norm.coverage_groups.data();
-	c.thr = norm.thresholds.data(); c.thr_int = norm.thr_int.data(); c.binom_p0 = norm.binom_p0.data();
+	c.thr = norm.thresholds.data(); c.thr_int = norm.thr_int.data(); c.binom_p0 = norm.binom_p0.data(); c.thr_hi = norm.thr_hi.data(); c.thr_hi_stride = norm.thr_hi_stride;
 	if(vcf){
 		// Reference::variants_ flattened + SimBlock::first_variant_id_ of every block + the host half of SetSystematicErrorVariants*
 		flat_vars = g.variants.flatten();
@@ -403,7 +403,7 @@ int main(int argc, char **argv){
 		sp.run_depth = sp.depth;
 		sp.scan_budget = getenv("RSQ_TWIN_BUDGET") ? atoi(getenv("RSQ_TWIN_BUDGET")) : 4000000000u;
 		const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);
-		sp.words_per_job = 3 * max_rl + 8 + kSpecMargin; sp.margin = kSpecMargin;
+		sp.words_per_job = (3 * max_rl + 8 + kSpecMargin + 7u) & ~7u; sp.margin = kSpecMargin;
 		sp.n_blocks = nsim;
 		const bool with_adapter_only = run_adapter_only;
 		sp.n_units = nsim + (with_adapter_only ? 1 : 0);
@@ -411,7 +411,7 @@ int main(int argc, char **argv){
 		sp.adapter_only_seed = with_adapter_only ? master() : 0;
 		std::vector<SpecBlock> sblocks(sp.n_units); std::vector<SpecSnap> snaps(2 * static_cast<size_t>(sp.n_units) * (sp.depth + 1));
 		std::vector<ReadJob> jobs(static_cast<size_t>(sp.n_units) * sp.depth);
-		std::vector<uint64_t> words(((jobs.size() + 31) / 32) * sp.words_per_job * 32);
+		std::vector<uint64_t> words(jobs.size() * sp.words_per_job);
 		std::vector<uint8_t> conv((bed || vcf) ? static_cast<size_t>(sp.n_units) * kConvSlots * 2 * kMaxOrgLen : 0);
 		sp.blocks = sblocks.data(); sp.snaps = snaps.data(); sp.jobs = jobs.data(); sp.words = words.data(); sp.conv = conv.data();
 		std::vector<uint16_t> snap_chosen(vcf ? 2 * static_cast<size_t>(sp.n_units) * (sp.depth + 1) * 2 * num_alleles : 0), chosen_live(2 * num_alleles + 2);
@@ -440,7 +440,7 @@ int main(int argc, char **argv){
 				for(uint32_t i = 0; i < sblocks[u].n_jobs; ++i){
 					const size_t gidx = static_cast<size_t>(u) * sp.depth + i;
 					ReadJob &j = jobs[gidx];
-					const uint64_t *slice = sp.words + (gidx >> 5) * sp.words_per_job * 32u + (gidx & 31u);
+					const uint64_t *slice = spec_slice(sp, gidx);
 					if(vcf){ run_read_machine<true>(c, sp, true, j, slice, sp.slots + static_cast<size_t>(j.slot) * sp.slot_stride, draw_fn, any_fn, j.consumed, j.rec_len); }
 					else{ run_read_machine<false>(c, sp, true, j, slice, sp.slots + static_cast<size_t>(j.slot) * sp.slot_stride, draw_fn, any_fn, j.consumed, j.rec_len); }
 					++jobs_run; jobs_ok += j.consumed == j.assumed;

@@ -73,7 +73,7 @@ def test_templates_match_reference_stages_and_fastq(oracle, golden, twin, workdi
     assert filecmp.cmp(prefix + "_2.fq", r2, shallow=False)
 
 
-@pytest.mark.parametrize("depth", [1, 5, 32])
+@pytest.mark.parametrize("depth", [1, 5, 32, 64])
 def test_speculative_two_phase_templates_match_reference(oracle, golden, twin, workdir, depth):
     """spec_core.cuh (scan_window + ReadMachine, verification and replay) with one-lane groups: same bytes as the reference."""
     stage = os.path.join(workdir, "stage_spec.flat")
@@ -130,15 +130,16 @@ def test_speculative_adapter_only_pairs_match_serial_templates(oracle, golden, t
         subprocess.run([oracle["dump"], "sim", golden["reseq"], golden["small_ref"], "42", "20", stage], check=True, timeout=600,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     outs = []
-    for name, extra in (("ao_serial", {}), ("ao_spec", {"RSQ_TWIN_SPEC": "6"})):
+    for name, extra in (("ao_serial", {}), ("ao_spec", {"RSQ_TWIN_SPEC": "6"}), ("ao_spec64", {"RSQ_TWIN_SPEC": "64"})):   # 64: three output slabs in flight
         prefix = os.path.join(workdir, name)
         res = subprocess.run([twin, stage, "42", prefix, "100000"], capture_output=True, text=True, timeout=900,
                              env=dict(os.environ, RSQ_TWIN_ADAPTER_ONLY="150", **extra))
         assert res.returncode == 0 and "error_flag=0" in res.stdout, res.stdout
         outs.append(prefix)
     assert b"Adapter" in open(outs[0] + "_1.fq", "rb").read()
-    assert filecmp.cmp(outs[0] + "_1.fq", outs[1] + "_1.fq", shallow=False)
-    assert filecmp.cmp(outs[0] + "_2.fq", outs[1] + "_2.fq", shallow=False)
+    for other in outs[1:]:
+        assert filecmp.cmp(outs[0] + "_1.fq", other + "_1.fq", shallow=False)
+        assert filecmp.cmp(outs[0] + "_2.fq", other + "_2.fq", shallow=False)
 
 
 def test_methylation_golden_is_what_the_reference_writes(oracle, golden, workdir):

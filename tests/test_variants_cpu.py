@@ -41,8 +41,8 @@ def parse(text):
 
 
 def test_fixture_set_is_complete():
-    assert len(VCFS) == 15
-    assert sum(open(v[:-4] + ".variants.txt").read().startswith("rejected") for v in VCFS) == 12
+    assert len(VCFS) == 16
+    assert sum(open(v[:-4] + ".variants.txt").read().startswith("rejected") for v in VCFS) == 12    # accepted: base, var, var70, ends
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_TEST), reason="the reference's test data is only present in the build container")
