@@ -101,6 +101,10 @@ typedef struct rsq_sim_report {
 	 * engines in the group, first SimBlock of this engine's shard */
 	uint64_t group_pairs;
 	uint32_t group_world, shard_first;
+	/* memory plan of rsq_engine_simulate: batches the shard's blocks were simulated in, and the bytes per reference base that stay resident in HBM
+	 * through the simulation (bases, G/C prefix counts, systematic errors of both strands) */
+	uint32_t batches, reserved;
+	double resident_bytes_per_base;
 } rsq_sim_report;
 
 rsq_engine *rsq_engine_create(const rsq_profile *profile, int device);

@@ -24,7 +24,8 @@ class SimReport(C.Structure):
                 ("ms_upload", C.c_float), ("ms_bias", C.c_float), ("ms_syserr", C.c_float), ("ms_simulate", C.c_float),
                 ("ms_gather", C.c_float), ("ms_download", C.c_float),
                 ("spec_rounds", C.c_uint32), ("spec_depth", C.c_uint32),
-                ("group_pairs", C.c_uint64), ("group_world", C.c_uint32), ("shard_first", C.c_uint32)]
+                ("group_pairs", C.c_uint64), ("group_world", C.c_uint32), ("shard_first", C.c_uint32),
+                ("batches", C.c_uint32), ("reserved", C.c_uint32), ("resident_bytes_per_base", C.c_double)]
 
     def as_dict(self):
         out = {}

@@ -116,15 +116,17 @@ template<class T> struct DevBuf {
 constexpr uint32_t kNone = 0xffffffffu;
 constexpr int kWarpsPerCta = 4;
 
-__global__ void k_surroundings(const uint8_t *seq, uint32_t L, const double *t0, const double *t1, const double *t2,
+// positions [p0, p0 + n) of one sequence; sur_start / sur_end point at the entry of position p0
+__global__ void k_surroundings(const uint8_t *seq, uint32_t L, uint32_t p0, uint32_t n, const double *t0, const double *t1, const double *t2,
                                double *sur_start, double *sur_end){
-	const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-	if(pos >= L){ return; }
+	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n){ return; }
+	const uint32_t pos = p0 + idx;
 	uint32_t code[3];
 	forward_surrounding(seq, L, pos, code);
-	sur_start[pos] = surrounding_bias(t0, t1, t2, code);
+	sur_start[idx] = surrounding_bias(t0, t1, t2, code);
 	reverse_surrounding(seq, L, pos, code);
-	sur_end[pos] = surrounding_bias(t0, t1, t2, code);
+	sur_end[idx] = surrounding_bias(t0, t1, t2, code);
 }
 
 // G/C prefix counts of one sequence: entry i = number of G/C in [0, i).  Three small passes
@@ -1103,6 +1105,9 @@ struct rsq_engine {
 	std::vector<uint64_t> h_seq_off;
 	uint64_t total_size = 0;
 	uint32_t n_blocks_total = 0, n_blocks_sim = 0, shard_first = 0, shard_n = 0, spec_units_last = 0;
+	rsq::ShardPlan plan;   // blocks of every sequence (shard_plan.hpp)
+	uint64_t sur_window_max = 0;
+	bool sur_windowed = false;   // simulate(): the per-position surrounding biases are held per batch instead of for the whole reference
 	bool shard_has_adapter_only = false;
 	uint64_t adapter_only_seed = 0;
 	uint64_t total_pairs = 0, adapter_only_pairs = 0;
@@ -1427,7 +1432,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	const Profile &p = e.prof;
 	SimCtx &c = e.ctx;
 	EventTimer tm(s);
-	e.prepared = false; e.downloaded = false; e.launches = 0;
+	e.prepared = false; e.downloaded = false; e.launches = 0; e.sur_windowed = false;
 	e.d_error_flag.zero(s);
 
 	// --- host: ReplaceN, ref-seq bias, pair counts (Simulator.cpp:2687-2743) ---
@@ -1533,6 +1538,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	for(size_t i = 0; i < g.seqs.size(); ++i){ seq_lengths[i] = g.seqs[i].size(); }
 	const ShardPlan plan = make_shard_plan(seq_lengths.data(), seq_lengths.size(), c.insert_to, shard_count_pre);   // shard_plan.hpp (also behind rsq_shard_plan)
 	if(!plan.blocks_total){ throw std::runtime_error("All reference sequences are too short for simulating."); }
+	e.plan = plan;
 	e.shard_first = static_cast<uint32_t>(plan.first(shard_index_pre));
 	e.shard_n = static_cast<uint32_t>(plan.count(shard_index_pre));
 	// a sequence is needed by the shards that hold blocks of it; in a group its bias sums are computed by the first of them (its owner)
@@ -1627,7 +1633,7 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	for(size_t i = 0; i < g.seqs.size(); ++i){
 		const uint32_t L = needed[i] ? g.seqs[i].size() : 0;
 		if(!L){ continue; }
-		k_surroundings<<<(L + 255) / 256, 256, 0, s>>>(e.d_ref.p + seq_off[i], L, e.d_sur_tab[0].p, e.d_sur_tab[1].p, e.d_sur_tab[2].p, e.d_sur_start.p + seq_off[i], e.d_sur_end.p + seq_off[i]);
+		k_surroundings<<<(L + 255) / 256, 256, 0, s>>>(e.d_ref.p + seq_off[i], L, 0, L, e.d_sur_tab[0].p, e.d_sur_tab[1].p, e.d_sur_tab[2].p, e.d_sur_start.p + seq_off[i], e.d_sur_end.p + seq_off[i]);
 		++e.launches;
 	}
 	Spline spline;
@@ -2365,13 +2371,28 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 		       + (c.var.loaded ? 2.0 * (depth + 1) * 4.0 * c.var.num_alleles : 0.0);
 	};
 	size_t free_b = 0, total_b = 0; RSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
-	const double budget = 0.85 * (static_cast<double>(free_b) + e.reusable_bytes());
+	double budget = 0.85 * (static_cast<double>(free_b) + e.reusable_bytes());
 	uint32_t depth_cap = 32;
 	uint64_t per_batch = e.shard_n;
+	// A run that needs several batches does not keep the surrounding biases of the whole reference (16 bytes per base, needed everywhere only by the bias
+	// sums of the prologue): every batch gets the window of positions its blocks can touch, recomputed in front of it (k_surroundings, microseconds).
+	// What stays resident per base is then 1 (bases) + 4 (G/C prefix) + 2 x 2 (systematic errors) bytes.  RSQ_KEEP_STAGES=1 keeps the arrays (stage fetches).
+	double window_bytes = 0.0;
+	e.sur_window_max = 0;
+	if(e.sur_windowed || ((unit_bytes(32) * e.shard_n > budget || getenv("RSQ_SUR_WINDOW")) && !getenv("RSQ_KEEP_STAGES"))){   // (a second simulate call on the same prepare stays windowed)
+		RSQ_CUDA(cudaDeviceSynchronize());
+		e.d_sur_start.release(); e.d_sur_end.release();
+		c.sur_start = nullptr; c.sur_end = nullptr;
+		e.sur_windowed = true;
+		window_bytes = 16.0 * 1000.0;
+		RSQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+		budget = 0.85 * (static_cast<double>(free_b) + e.reusable_bytes());
+	}
+
 	// (twice the depth per round, RSQ_SPEC_CAP=64, was measured on E. coli: four rounds fewer, but each scan and each lock-step pass over the reads
 	// of a round takes as much longer - 65 ms instead of 64; the capacity stays an option for profiles with rarer InDels)
 	if(const char *env = getenv("RSQ_SPEC_CAP")){ if(!meth && !c.var.loaded && atoi(env) > 32){ depth_cap = kSpecMaxDepth; } }
-	if(unit_bytes(32) * e.shard_n > budget){ depth_cap = 16; per_batch = std::max<uint64_t>(1024, static_cast<uint64_t>(budget / unit_bytes(16))); }
+	if((unit_bytes(32) + window_bytes) * e.shard_n > budget){ depth_cap = 16; per_batch = std::max<uint64_t>(1024, static_cast<uint64_t>((budget - 16.0 * (c.insert_to + 4096.0)) / (unit_bytes(16) + window_bytes))); }
 	if(const char *env = getenv("RSQ_BATCH_UNITS")){ per_batch = std::max(1, atoi(env)); }
 	const uint32_t n_batches = e.shard_n ? static_cast<uint32_t>((e.shard_n + per_batch - 1) / per_batch) : 1;
 	const bool to_files = e.sink_files[0] != nullptr;
@@ -2424,6 +2445,34 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 		BatchResult res;
 		bool done = false;
 		stage_log("simulate: batch start");
+		if(e.sur_windowed && u_count){
+			// positions the blocks [B0, B1) of this batch can touch: per sequence from the first block's start to insert_to behind the last block's end
+			const uint64_t B0 = static_cast<uint64_t>(e.shard_first) + u_begin, B1 = B0 + u_count;
+			struct Piece { size_t seq; uint32_t p0, n; };
+			std::vector<Piece> pieces;
+			uint64_t G0 = 0, G1 = 0;
+			for(size_t i = 0; i < e.plan.seq_blocks.size(); ++i){
+				const uint64_t first = e.plan.seq_first_block[i], last = first + e.plan.seq_blocks[i];
+				if(!e.plan.seq_blocks[i] || last <= B0 || first >= B1){ continue; }
+				const uint32_t L = e.genome.seqs[i].size();
+				const uint32_t p0 = static_cast<uint32_t>((std::max(B0, first) - first) * 1000u);
+				const uint32_t p1 = static_cast<uint32_t>(std::min<uint64_t>(L, (std::min(B1, last) - first) * 1000ull + c.insert_to));
+				if(pieces.empty()){ G0 = e.h_seq_off[i] + p0; }
+				G1 = e.h_seq_off[i] + p1;
+				pieces.push_back({i, p0, p1 - p0});
+			}
+			e.d_sur_start.alloc(G1 - G0 + 1); e.d_sur_end.alloc(G1 - G0 + 1);
+			e.sur_window_max = std::max<uint64_t>(e.sur_window_max, G1 - G0);
+			for(const Piece &pc : pieces){
+				const uint64_t at = e.h_seq_off[pc.seq] + pc.p0 - G0;
+				k_surroundings<<<(pc.n + 255) / 256, 256, 0, s>>>(e.d_ref.p + e.h_seq_off[pc.seq], static_cast<uint32_t>(e.genome.seqs[pc.seq].size()), pc.p0, pc.n,
+				                                                 e.d_sur_tab[0].p, e.d_sur_tab[1].p, e.d_sur_tab[2].p, e.d_sur_start.p + at, e.d_sur_end.p + at);
+				++e.launches;
+			}
+			// the kernels index with the offset of the whole layout: bias the pointers by the window's start
+			c.sur_start = reinterpret_cast<const double *>(reinterpret_cast<uintptr_t>(e.d_sur_start.p) - G0 * sizeof(double));
+			c.sur_end = reinterpret_cast<const double *>(reinterpret_cast<uintptr_t>(e.d_sur_end.p) - G0 * sizeof(double));
+		}
 		if(spec){
 			done = simulate_spec_batch(e, u_begin, u_count, with_ao, depth_cap, par, res);
 			if(done){ e.spec_rounds += res.rounds; if(!e.spec_depth){ e.spec_depth = res.depth; } }
@@ -2466,7 +2515,13 @@ static void simulate(rsq_engine &e, rsq_sim_report *rep){
 		RSQ_CUDA(cudaStreamSynchronize(s));
 		e.group_pairs = mine;
 	}
-	if(rep){ rep->group_pairs = e.group_pairs; rep->group_world = e.comm ? e.group_world : 1; rep->shard_first = e.shard_first; }
+	if(rep){
+		rep->group_pairs = e.group_pairs; rep->group_world = e.comm ? e.group_world : 1; rep->shard_first = e.shard_first;
+		rep->batches = n_batches;
+		// bases + G/C prefix counts + systematic errors of both strands (2 x 2 bytes) + surrounding biases (the whole reference, or the largest batch window)
+		const double per_base = static_cast<double>(e.total_size) * (1.0 + 4.0 + 4.0) + 16.0 * static_cast<double>(e.sur_windowed ? e.sur_window_max : e.total_size);
+		rep->resident_bytes_per_base = e.total_size ? per_base / static_cast<double>(e.total_size) : 0.0;
+	}
 	stage_log("simulate: report");
 }
 
@@ -3002,6 +3057,7 @@ int rsq_engine_fetch(const rsq_engine *engine, const char *name, void *dst, uint
 	else if(n == "blocks"){ src = engine->d_blocks.p; nb = sizeof(BlockDesc) * engine->n_blocks_total; }
 	else if(n == "spec_blocks"){ src = engine->d_spec_blocks.p; nb = sizeof(SpecBlock) * engine->spec_units_last; }   // per-unit counters of the last speculative batch (rounds, reads, scan draws): tuning
 	else{ throw std::runtime_error("unknown stage array '" + n + "'"); }
+	if((n == "sur_start" || n == "sur_end") && engine->sur_windowed){ throw std::runtime_error("stage array '" + n + "' is no longer resident: a multi-batch simulate call keeps one batch's window only (RSQ_KEEP_STAGES=1 keeps the whole arrays)"); }
 	if(bytes){ *bytes = nb; }
 	const uint64_t cnt = std::min(nb, capacity);
 	if(dst && cnt){

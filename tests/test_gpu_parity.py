@@ -76,6 +76,27 @@ def test_block_batches_concatenate_to_the_whole_run(rb, engine, golden, monkeypa
     assert rep.pairs == r1.count(b"\n") // 4
 
 
+@pytest.mark.parametrize("path,batch", [("spec", 7), ("spec", 1), ("serial", 5)])
+def test_batches_with_windows_of_surrounding_biases(rb, engine, golden, monkeypatch, path, batch):
+    """Multi-batch runs keep the per-position surrounding biases (16 bytes per base) of one batch only, recomputed in front of it, with the kernels
+    indexing through pointers biased by the window start (RSQ_SUR_WINDOW forces that mode on a small run): same bytes, 9 bytes per base plus one
+    batch's window resident; the second simulate call on the same prepare stays in that mode."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    monkeypatch.setenv("RSQ_BATCH_UNITS", str(batch))
+    monkeypatch.setenv("RSQ_SUR_WINDOW", "1")
+    ref = rb.Reference.load_fasta(golden["small_ref"])
+    engine.prepare(ref, seed=42, coverage=20.0)
+    for _ in range(2):
+        rep = engine.simulate()
+        engine.download()
+        assert engine.output(0) == open(golden["r1"], "rb").read()
+        assert engine.output(1) == open(golden["r2"], "rb").read()
+        assert rep.batches == -(-rep.blocks // batch)
+        assert 9.0 <= rep.resident_bytes_per_base < 9.0 + 16.0 * (batch * 1000 + 2000) / 70000
+    with pytest.raises(rb.RsqError, match="no longer resident"):
+        engine.fetch("sur_start")
+
+
 @pytest.mark.parametrize("path,shards", [("spec", 1), ("serial", 1), ("spec", 3)])
 def test_adapter_only_pairs_against_reference_binary(rb, golden, oracle, workdir, monkeypatch, path, shards):
     """Simulator::SimulateAdapterOnlyPairs (Simulator.cpp:2359-2382) against the reference: profile150a has InsertLengths()[0] > 0 (oracle/dump_tables
