@@ -42,8 +42,8 @@ REF_LEN = 4_641_652          # E. coli K-12 MG1655 (the reference's test/ecoli-G
 ECOLI_XZ = os.path.join(GOLDEN, "ecoli_GCF_000005845.2.fa.xz")
 C5_SEQS, C5_SEQ_LEN, C5_REF_SEED, C5_VCF_SEED = 8, 125_000_000, 4321, 77   # strong-scaling workload: 1 Gbp in 8 sequences + diploid VCF
 ISSUE_PEAK = 148 * 4 * 1.965e9   # warp instructions per second: 148 SMs x 4 schedulers x 1.965 GHz (the ceiling the scan works against)
-SCAN_INST_PER_DRAW = 3.9         # warp instructions of k_spec_scan per scan draw (profiles/r01d_k_spec_scan_ncu_full.md)
-READ_INST_PER_BASE = 72.0        # warp instructions of k_spec_reads per base and read (profiles/r01d_k_spec_reads_ncu_full.md)
+SCAN_INST_PER_DRAW = 3.41        # warp instructions of k_spec_scan per scan draw (profiles/r02y_launches.md: 13.05 G per step / 3.829 G draws)
+READ_INST_PER_BASE = 68.7        # warp instructions of k_spec_reads per base and read (profiles/r02y_launches.md: 9.59 G per step / 930 758 reads / 150)
 COVERAGE = 30.0
 SEED = 42
 BYTES_PER_PAIR = 1420.0      # 740 B FASTQ out + 600 B systematic errors in + 80 B reference in
@@ -335,7 +335,8 @@ def run_b200(args):
                        "pairs_per_step": pairs_all / args.steps, "blocks_per_step": sum(r["blocks"] for r in reps) / args.steps, "vcf_records": n_variants,
                        "group_pairs_per_step_all_reduced_in_library": group_pairs / args.steps,
                        "device_ms_breakdown_rank0": {k: sum(r[k] for r in reps) / args.steps for k in ("ms_upload", "ms_bias", "ms_syserr", "ms_simulate", "ms_gather", "ms_download")},
-                       "scan_draws_per_s": draws / (sim_ms / 1000.0) if sim_ms else None},
+                       "scan_draws_per_s": draws / (sim_ms / 1000.0) if sim_ms else None,
+                       "batches_rank0": reps[-1].get("batches"), "resident_bytes_per_base_rank0": reps[-1].get("resident_bytes_per_base")},
             "e2e": {"value": pairs_all / wall, "unit": "pairs/s", "h2d_bytes_per_step": ref_bases, "d2h_bytes_per_step": d2h_all / args.steps,
                     "ms_per_step": 1000 * wall / args.steps},
             "gpu_launches": int(launches_all),
@@ -347,7 +348,7 @@ def run_b200(args):
                                        "warp_inst_per_s": warp_inst / (sim_ms / 1000.0) if sim_ms else None,
                                        "issue_peak_warp_inst_per_s": ISSUE_PEAK,
                                        "frac_of_issue_peak": warp_inst / (sim_ms / 1000.0) / ISSUE_PEAK if sim_ms else None,
-                                       "model": f"{SCAN_INST_PER_DRAW} warp instructions per scan draw + {READ_INST_PER_BASE} per base and read (ncu, profiles/r01d_*); rank 0, simulate phase"},
+                                       "model": f"{SCAN_INST_PER_DRAW} warp instructions per scan draw + {READ_INST_PER_BASE} per base and read (ncu, profiles/r02y_launches.md); rank 0, simulate phase"},
                          "note": "algorithmic bytes = pairs x 1420 B + positions x 8.25 B over the event time of the simulate phase (every launch of the two kernels of a "
                                  "step); the phase is bound by the per-SimBlock serial mt19937_64 stream and dependent FP64 Draw chains (latency), not by HBM"},
         }

@@ -50,9 +50,9 @@ def main():
         for _ in range(args.repeat):
             eng.prepare(ref, seed=42, coverage=30.0)
             rep = eng.simulate().as_dict()
-            if best is None or rep["ms_simulate"] < best["ms_simulate"]:
+            if best is None or rep["ms_simulate"] + rep["ms_syserr"] < best["ms_simulate"] + best["ms_syserr"]:
                 best = rep
-        print(json.dumps({"setting": setting or "default", "ms_simulate": round(best["ms_simulate"], 2), "rounds": best.get("spec_rounds"), "pairs": best["pairs"],
+        print(json.dumps({"setting": setting or "default", "ms_simulate": round(best["ms_simulate"], 2), "ms_syserr": round(best["ms_syserr"], 2), "syserr_passes": best.get("syserr_passes"), "rounds": best.get("spec_rounds"), "pairs": best["pairs"],
                           "launches": best.get("launches"), "depth": best.get("spec_depth")}), flush=True)
     eng.close()
 
