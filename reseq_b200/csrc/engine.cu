@@ -591,7 +591,10 @@ template<bool kVar> __global__ void k_spec_scan(const __grid_constant__ SimCtx c
 #endif
 template<> __global__ void __launch_bounds__(RSQ_SCAN_BOUNDS)
 k_spec_scan<false>(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){ spec_scan_body<false>(c, sp, descs, first_desc, unit_first, unit_end); }
-template<> __global__ void __launch_bounds__(kWarpsPerCta * 32, 5)   // 96 registers: 20 warps per SM
+#ifndef RSQ_VAR_SCAN_MINBLOCKS
+#define RSQ_VAR_SCAN_MINBLOCKS 5   // 96 registers: 20 warps per SM
+#endif
+template<> __global__ void __launch_bounds__(kWarpsPerCta * 32, RSQ_VAR_SCAN_MINBLOCKS)
 k_spec_scan<true>(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){ spec_scan_body<true>(c, sp, descs, first_desc, unit_first, unit_end); }
 
 // LogArrayResult::Draw for up to 32 independent reads at once (lanes 0 .. n_rows-1 own one read each).  The likelihood
@@ -808,7 +811,10 @@ template<bool kVar> __global__ void k_spec_reads(SimCtx c, SpecCtx sp, uint32_t 
 #endif
 template<> __global__ void __launch_bounds__(RSQ_READS_BOUNDS)
 k_spec_reads<false>(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){ spec_reads_body<false>(c, sp, stride, lanes_per_warp, unit_first, unit_end); }
-template<> __global__ void __launch_bounds__(kSpecReadWarps * 32, 5)
+#ifndef RSQ_VAR_READS_MINBLOCKS
+#define RSQ_VAR_READS_MINBLOCKS 5
+#endif
+template<> __global__ void __launch_bounds__(kSpecReadWarps * 32, RSQ_VAR_READS_MINBLOCKS)
 k_spec_reads<true>(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){ spec_reads_body<true>(c, sp, stride, lanes_per_warp, unit_first, unit_end); }
 
 // FASTQ text of one (unit, segment): walks the unit's slab chain, a warp assembles one record at a time.
