@@ -592,7 +592,7 @@ template<bool kVar> __global__ void k_spec_scan(const __grid_constant__ SimCtx c
 template<> __global__ void __launch_bounds__(RSQ_SCAN_BOUNDS)
 k_spec_scan<false>(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){ spec_scan_body<false>(c, sp, descs, first_desc, unit_first, unit_end); }
 #ifndef RSQ_VAR_SCAN_MINBLOCKS
-#define RSQ_VAR_SCAN_MINBLOCKS 5   // 96 registers: 20 warps per SM
+#define RSQ_VAR_SCAN_MINBLOCKS 4   // 118 registers, 16 warps per SM: 200 Mbp + VCF 4382 ms against 4737 ms with 5 blocks (96 registers, spills) and 4841 ms with 3
 #endif
 template<> __global__ void __launch_bounds__(kWarpsPerCta * 32, RSQ_VAR_SCAN_MINBLOCKS)
 k_spec_scan<true>(const __grid_constant__ SimCtx c, const __grid_constant__ SpecCtx sp, const BlockDesc *descs, uint32_t first_desc, uint32_t unit_first, uint32_t unit_end){ spec_scan_body<true>(c, sp, descs, first_desc, unit_first, unit_end); }
@@ -812,7 +812,7 @@ template<bool kVar> __global__ void k_spec_reads(SimCtx c, SpecCtx sp, uint32_t 
 template<> __global__ void __launch_bounds__(RSQ_READS_BOUNDS)
 k_spec_reads<false>(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){ spec_reads_body<false>(c, sp, stride, lanes_per_warp, unit_first, unit_end); }
 #ifndef RSQ_VAR_READS_MINBLOCKS
-#define RSQ_VAR_READS_MINBLOCKS 5
+#define RSQ_VAR_READS_MINBLOCKS 4   // 122 registers: 4200 ms together with the scan's 4 (5 blocks / 96 registers: 4382 ms)
 #endif
 template<> __global__ void __launch_bounds__(kSpecReadWarps * 32, RSQ_VAR_READS_MINBLOCKS)
 k_spec_reads<true>(SimCtx c, SpecCtx sp, uint32_t stride, uint32_t lanes_per_warp, uint32_t unit_first, uint32_t unit_end){ spec_reads_body<true>(c, sp, stride, lanes_per_warp, unit_first, unit_end); }
