@@ -364,6 +364,18 @@ def run_b200(args):
                                   "device_ms_breakdown": {k: r5[k] for k in ("ms_upload", "ms_bias", "ms_syserr", "ms_simulate", "ms_gather", "ms_download")},
                                   "note": "bench.py --gpus N (N > 1) runs this workload split over N GPUs: value(N) / this value is the strong-scaling speed-up"}
             ref5 = None
+        if world > 1 and kind == "c5":
+            # the committed single-GPU measurement of this very workload (a `strong_ref` of an N = 1 line, copied into profiles/): the denominator of the
+            # strong-scaling speed-up.  The N = 1 line of a scaling series is config C2, a different workload - its value is not comparable with this one.
+            spath = os.path.join(ROOT, "profiles", "strong_ref_n1.json")
+            if os.path.exists(spath):
+                try:
+                    sr = json.load(open(spath))
+                    line["strong_ref"] = {"n_gpus": 1, "value": sr["value"], "unit": "pairs/s", "e2e_value": sr["e2e"]["value"], "source": sr.get("source", "profiles/strong_ref_n1.json"),
+                                          "speedup_device": line["value"] / sr["value"], "speedup_e2e": line["e2e"]["value"] / sr["e2e"]["value"],
+                                          "note": "same workload measured on ONE GPU of this pool with the same build (a committed measurement, not taken in this run)"}
+                except Exception:
+                    pass
         if world == 1 and kind == "c2" and not args.no_cold:
             # the cold drop-in call: engine creation + table upload + prologue + simulation + both FASTQ files written (tmpfs)
             names, seqs, _ = workload_c2()

@@ -9,6 +9,7 @@
 //
 //   dump_tables profile <stats.reseq> <out.flat>                      profile + LogArrayResult tables
 //   dump_tables patch <in.reseq> <out.reseq> <seed>                    synthetic GC / surroundings / dispersion biases
+//   dump_tables errmodel <stats.reseq> <in.fa> <seed> <out.fq>           Simulator::SimulateErrorModelOnly for inputs of several batches (see the mode)
 //   dump_tables patch_adapter_only <in.reseq> <out.reseq> <count>      sets InsertLengths()[0] = count: pairs made of adapters only (Simulator::SimulateAdapterOnlyPairs)
 //   dump_tables sim <stats.reseq> <ref.fa> <seed> <coverage> <out.flat> [max_blocks] [in.vcf]   + normalisation, thresholds, seeds, sys-errors
 //                                                                     (with a VCF: thresholds for its allele count, first_variant_id_ and err_variants_ of every block)
@@ -474,6 +475,19 @@ int main(int argc, char **argv){
 			out << "call " << s << ' ' << start << ' ' << len << ' ' << reversed << ' ' << first << ' ' << first_pos << ' ' << allele << ' ' << res << "\n";
 		}
 		return 0;
+	}
+	if(mode == "errmodel" && argc >= 6){
+		// Simulator::SimulateErrorModelOnly (Simulator.cpp:2900-3014) on inputs of more than one batch of kBatchSizeErrorModelOnly records.
+		// The reference as released waits for written_blocks_ >= cur_block in WriteSingleReads (Simulator.cpp:184-192) and never increments
+		// written_blocks_, so `reseq seqToIllumina` dead-locks on its second batch.  Everything else of the call - one block_seed_gen_() seed
+		// per batch in input order, ApplyErrorsAndQualityToFastaInput, FlushWriteValues - is the reference's own code; with the counter preset
+		// the wait is never entered and one thread writes the batches in order.
+		DataStats stats(NULL);
+		ProbabilityEstimates est;
+		if(!LoadAll(stats, est, argv[2])){ return 1; }
+		Simulator sim;
+		sim.written_blocks_ = std::numeric_limits<uintFragCount>::max();
+		return sim.SimulateErrorModelOnly(argv[5], argv[3], stats, est, 1, std::stoull(argv[4])) ? 0 : 1;
 	}
 	if(mode == "sim" && argc >= 7){
 		Reference ref;

@@ -10,6 +10,8 @@ import pytest
 
 from conftest import run_oracle_sim
 
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -256,6 +258,28 @@ def test_error_model_batches_serial_and_speculative_agree(engine, golden, workdi
         assert rep.pairs == 9000 and rep.blocks == 13
         outs.append(open(out, "rb").read())
     assert outs[0] == outs[1] and outs[0].count(b"\n") == 4 * 9000
+
+
+@pytest.mark.parametrize("path", ["spec", "serial"])
+def test_error_model_three_batches_equal_the_reference(engine, golden, oracle_optional, workdir, monkeypatch, path):
+    """27 000 input records = three batches of kBatchSizeErrorModelOnly, each with its own seed of the master stream: same bytes as the
+    reference's own SimulateErrorModelOnly (hash in tests/golden/em_multibatch_sha256.json; on a box that has the oracle, byte for byte)."""
+    import hashlib
+    import json
+    sys.path.insert(0, GOLDEN_DIR)
+    import make_em_multibatch as mk
+    want = json.load(open(os.path.join(GOLDEN_DIR, "em_multibatch_sha256.json")))
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    fa, out = os.path.join(workdir, "em3.fa"), os.path.join(workdir, f"em3_{path}.fq")
+    assert mk.write_input(fa) == want["records"]
+    rep = engine.apply_error_model(fa, out, want["seed"])
+    data = open(out, "rb").read()
+    assert rep.pairs == want["records"] and rep.blocks == 3
+    assert len(data) == want["bytes"] and hashlib.sha256(data).hexdigest() == want["sha256"]
+    if oracle_optional:
+        ref_out = os.path.join(workdir, "em3_oracle.fq")
+        mk.run_oracle(oracle_optional["dump"], golden["reseq"], fa, ref_out)
+        assert data == open(ref_out, "rb").read()
 
 
 def test_error_model_rejects_malformed_header(engine, workdir):

@@ -11,6 +11,7 @@ from conftest import run_oracle_sim
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TWIN_DIR = os.path.join(ROOT, "tests", "host_twin")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def _compile(src, out, extra=()):
@@ -44,6 +45,26 @@ def test_golden_error_model_is_what_the_reference_writes(oracle, golden, workdir
     subprocess.run([oracle["reseq"], "seqToIllumina", "-j", "1", "--verbosity", "1", "-i", golden["em_in"], "-s", golden["reseq"],
                     "--ipfIterations", "0", "--seed", "7", "-o", out], check=True, timeout=600, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     assert filecmp.cmp(out, golden["em_out"], shallow=False)
+
+
+def test_multibatch_error_model_hash_is_what_the_reference_writes(oracle, golden, workdir):
+    """tests/golden/em_multibatch_sha256.json: 27 000 records = three batches through the reference's own SimulateErrorModelOnly
+    (`dump_tables errmodel`: the counter its writer waits for is preset, see tests/golden/make_em_multibatch.py)."""
+    import hashlib
+    import json
+    sys.path.insert(0, GOLDEN)
+    import make_em_multibatch as mk
+    want = json.load(open(os.path.join(GOLDEN, "em_multibatch_sha256.json")))
+    fa, out = os.path.join(workdir, "em3.fa"), os.path.join(workdir, "em3_oracle.fq")
+    assert mk.write_input(fa) == want["records"]
+    assert hashlib.sha256(open(fa, "rb").read()).hexdigest() == want["input_sha256"]
+    mk.run_oracle(oracle["dump"], golden["reseq"], fa, out)
+    data = open(out, "rb").read()
+    assert len(data) == want["bytes"] and hashlib.sha256(data).hexdigest() == want["sha256"]
+    # the first batch is the single-batch golden run on the same records (ids aside): same seed, same stream
+    first = data.split(b"\n")[:4 * 9000]
+    gold = open(golden["em_out"], "rb").read().split(b"\n")[:4 * 9000]
+    assert [x for i, x in enumerate(first) if i % 4] == [x for i, x in enumerate(gold) if i % 4]
 
 
 @pytest.fixture(scope="module")

@@ -137,7 +137,8 @@ def simulate_read(rng, template, read_len, seg):
     """template: the fragment strand this read is sequenced from (string, already oriented), followed by adapter.
     Returns (seq, qual, cigar-ops list of (op,len) relative to template consumption)."""
     nq = len(QUALS)
-    level = int(rng.integers(5, nq))  # read-wide quality level
+    level = int(rng.integers(nq // 2, nq))  # read-wide quality level
+    step = max(1, nq // 11)   # quality levels per Markov step (1 for the default 11 levels)
     seq = []
     qual = []
     cigar = []
@@ -167,9 +168,9 @@ def simulate_read(rng, template, read_len, seg):
         drift = 0.10 + 0.25 * len(seq) / read_len + (0.05 if seg else 0.0)
         u = rng.random()
         if u < drift and state > 0:
-            state -= 1
+            state = max(0, state - (int(rng.integers(1, step + 1)) if step > 1 else 1))   # (no extra draw for the default levels: the committed fixtures regenerate)
         elif u > 0.80 and state < level:
-            state += 1
+            state = min(level, state + (int(rng.integers(1, step + 1)) if step > 1 else 1))
         q = int(QUALS[state])
         base = template[tpos]
         # systematic error: after "GGC" on the read strand the next base tends to be called as G
@@ -305,6 +306,7 @@ def main():
     b.add_argument("--tiles", default="", help="comma separated tile numbers (Casava 1.8 read names)")
     b.add_argument("--alt-len", type=int, default=0)
     b.add_argument("--alt-frac", type=float, default=0.0)
+    b.add_argument("--quals", type=int, default=0, help="number of distinct base qualities, evenly spread over 2..41 (default: the 11 values of QUALS); 40 = every value like a real HiSeq/NovaSeq run before binning")
     c = sub.add_parser("fragments")
     c.add_argument("ref")
     c.add_argument("sys")
@@ -316,8 +318,10 @@ def main():
     if args.cmd == "reference":
         write_fasta(args.out, gen_reference([int(x) for x in args.sizes.split(",")], args.seed, args.n_rate), args.prefix)
     elif args.cmd == "sam":
-        global INDEL_RATE
+        global INDEL_RATE, QUALS
         INDEL_RATE = args.indel_rate
+        if args.quals:
+            QUALS = np.unique(np.round(np.linspace(2, 41, args.quals)).astype(int))
         gen_sam(args.ref, args.out, args.pairs, args.read_len, args.seed, [int(t) for t in args.tiles.split(",")] if args.tiles else None, args.alt_len, args.alt_frac)
     else:
         gen_fragments(args.ref, args.sys, args.out, args.n, args.len, args.seed)
