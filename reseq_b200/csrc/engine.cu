@@ -40,6 +40,7 @@
 #include "em_input.hpp"
 #include "variant_syserr.hpp"
 #include "shard_plan.hpp"
+#include "ordered_sum.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>   // types and prototypes only: the library is bound at run time (libnccl.so.2), so single-GPU use does not need it
@@ -253,6 +254,118 @@ k_sum_bias(const BiasParamDev *params, uint32_t n_params, const uint64_t *seq_of
 	if(warp && lane == 0){ s_max[warp - 1u] = mx; }
 	__syncthreads();
 	if(threadIdx.x == 0){ sums[i] = tot; max_bias[i] = fmax(fmax(s_max[0], s_max[1]), s_max[2]); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same sums without the chain (ordered_sum.cuh): chunks of a chain run in parallel from approximate start values, an in-order pass
+// joins them exactly.  One thread owns one chunk; a warp evaluates the terms of 32 chunks x 32 positions with coalesced loads into shared
+// memory, then every lane adds the 32 terms of its own chunk in order.
+// ---------------------------------------------------------------------------------------------------
+struct BiasChain { uint32_t ref_id, fragment_length; double general; uint32_t n_pos, n_chunks; uint32_t chunk_first, cta_first; };
+struct BiasTerm {   // one term of Reference::SumBias (same expression as sum_bias_chain)
+	const double *ss, *se; const uint32_t *gp; const double *gc_bias; uint32_t fl; double general;
+	__device__ __forceinline__ double operator()(uint32_t p) const {
+		double bias = mul_rn(general, gc_bias[percent_u32(gp[p + fl] - gp[p], fl)]);
+		bias = mul_rn(bias, ss[p]);
+		return mul_rn(bias, se[p]);
+	}
+};
+__device__ __forceinline__ BiasTerm bias_term_of(const BiasChain &ch, const uint64_t *seq_off, const double *sur_start, const double *sur_end, const uint32_t *gc_prefix, const double *gc_bias){
+	const uint64_t off = seq_off[ch.ref_id];
+	return BiasTerm{sur_start + off, sur_end + off + ch.fragment_length - 1, gc_prefix + off + ch.ref_id, gc_bias, ch.fragment_length, ch.general};
+}
+constexpr uint32_t kBiasChunkCta = 128;   // chunks per CTA (one per thread)
+// kSpec = false: pass A (plain chunk sums + chunk maxima); true: pass C (exact runs from the start values in `start`)
+template<bool kSpec> __global__ void __launch_bounds__(kBiasChunkCta)
+k_bias_chunks(const BiasChain *chains, uint32_t n_chains, uint32_t K, const uint64_t *seq_off, const double *sur_start, const double *sur_end,
+              const uint32_t *gc_prefix, const double *gc_bias, const double *start, double *out, double *chunk_max, uint32_t *tie){
+	__shared__ double s_gc[101];
+	__shared__ double s_terms[kBiasChunkCta / 32][32][33];
+	// which chain this CTA belongs to (few chains: linear search)
+	uint32_t ci = 0;
+	while(ci + 1 < n_chains && chains[ci + 1].cta_first <= blockIdx.x){ ++ci; }
+	const BiasChain ch = chains[ci];
+	for(uint32_t k = threadIdx.x; k < 101; k += blockDim.x){ s_gc[k] = gc_bias[k]; }
+	__syncthreads();
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const BiasTerm term = bias_term_of(ch, seq_off, sur_start, sur_end, gc_prefix, s_gc);
+	const uint32_t c_warp = (blockIdx.x - ch.cta_first) * kBiasChunkCta + warp * 32u;   // first chunk of this warp
+	if(c_warp >= ch.n_chunks){ return; }
+	const uint32_t my_chunk = c_warp + lane;
+	const bool mine = my_chunk < ch.n_chunks;
+	double acc = (kSpec && mine) ? start[ch.chunk_first + my_chunk] : 0.0, mx = 0.0;
+	uint32_t tied = 0;
+	for(uint32_t j = 0; j < K; j += 32u){
+		__syncwarp();
+#pragma unroll 4
+		for(uint32_t cc = 0; cc < 32u; ++cc){
+			const uint32_t chunk = c_warp + cc;
+			const uint64_t p = static_cast<uint64_t>(chunk) * K + j + lane;
+			double x = 0.0;   // behind the chain's last position: + 0.0 is exact and never a tie
+			if(chunk < ch.n_chunks && p < ch.n_pos){ x = term(static_cast<uint32_t>(p)); }
+			s_terms[warp][cc][lane] = x;
+		}
+		__syncwarp();
+		if(mine){
+#pragma unroll 8
+			for(uint32_t i = 0; i < 32u; ++i){
+				const double x = s_terms[warp][lane][i];
+				if(kSpec){ acc = ordered_step(acc, x, tied); }
+				else{ if(x > mx){ mx = x; } acc = add_rn(acc, x); }
+			}
+		}
+	}
+	if(mine){
+		out[ch.chunk_first + my_chunk] = acc;
+		if(kSpec){ tie[ch.chunk_first + my_chunk] = tied; } else{ chunk_max[ch.chunk_first + my_chunk] = mx; }
+	}
+}
+// pass B: a warp per chain - start values g_c = sum of the plain chunk sums in front of chunk c (one addition per chunk), and the chain's maximum
+__global__ void k_bias_scan(const BiasChain *chains, uint32_t n_chains, const double *plain, const double *chunk_max, double *start, double *max_out){
+	const uint32_t ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if(ci >= n_chains){ return; }
+	const BiasChain ch = chains[ci];
+	double g = 0.0, mx = 0.0;
+	for(uint32_t base = 0; base < ch.n_chunks; base += 32u){
+		const uint32_t c = base + lane;
+		const double pv = c < ch.n_chunks ? plain[ch.chunk_first + c] : 0.0;
+		const double mv = c < ch.n_chunks ? chunk_max[ch.chunk_first + c] : 0.0;
+		mx = fmax(mx, mv);
+		double mine = 0.0;
+		for(uint32_t i = 0; i < 32u; ++i){
+			if(i == lane){ mine = g; }
+			g = add_rn(g, __shfl_sync(0xffffffffu, pv, i));
+		}
+		if(c < ch.n_chunks){ start[ch.chunk_first + c] = mine; }
+	}
+	for(int o = 16; o; o >>= 1){ mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+	if(lane == 0){ max_out[ci] = mx; }
+}
+// pass D: a warp per chain walks its chunks in order (all lanes run the same scalar code; the loads of 32 chunks are coalesced)
+__global__ void k_bias_resolve(const BiasChain *chains, uint32_t n_chains, uint32_t K, const uint64_t *seq_off, const double *sur_start, const double *sur_end,
+                               const uint32_t *gc_prefix, const double *gc_bias, const double *start, const double *out, const uint32_t *tie,
+                               double *sums, uint32_t *reran_out){
+	const uint32_t ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if(ci >= n_chains){ return; }
+	const BiasChain ch = chains[ci];
+	const BiasTerm term = bias_term_of(ch, seq_off, sur_start, sur_end, gc_prefix, gc_bias);
+	double s = 0.0;
+	uint32_t reran = 0;
+	for(uint32_t base = 0; base < ch.n_chunks; base += 32u){
+		const uint32_t c = base + lane;
+		const bool have = c < ch.n_chunks;
+		const double gv = have ? start[ch.chunk_first + c] : 0.0, ov = have ? out[ch.chunk_first + c] : 0.0;
+		const uint32_t tv = have ? tie[ch.chunk_first + c] : 0u;
+		const uint32_t n = ch.n_chunks - base < 32u ? ch.n_chunks - base : 32u;
+		for(uint32_t i = 0; i < n; ++i){
+			const double g = __shfl_sync(0xffffffffu, gv, i), o = __shfl_sync(0xffffffffu, ov, i);
+			const uint32_t t = __shfl_sync(0xffffffffu, tv, i);
+			const uint64_t begin = static_cast<uint64_t>(base + i) * K;
+			const uint64_t end = begin + K < ch.n_pos ? begin + K : ch.n_pos;
+			s = chunk_resolve(term, static_cast<uint32_t>(begin), static_cast<uint32_t>(end), s, g, o, t, reran);
+		}
+	}
+	if(lane == 0){ sums[ci] = s; reran_out[ci] = reran; }
 }
 
 // Continuation of the master mt19937_64 (Simulator::block_seed_gen_): state[0..311] is any window of 312
@@ -1088,6 +1201,7 @@ struct rsq_engine {
 	DevBuf<uint64_t> d_seq_off; DevBuf<uint32_t> d_seq_len, d_gc_prefix, d_name_off, d_cov_group;
 	DevBuf<uint8_t> d_ref, d_sys_fwd, d_sys_rev;
 	DevBuf<double> d_sur_start, d_sur_end, d_thr, d_binom_p0;
+	DevBuf<BiasChain> d_bias_chains; DevBuf<double> d_bias_plain, d_bias_start, d_bias_out, d_bias_cmax; DevBuf<uint32_t> d_bias_tie, d_bias_reran;   // chunked SumBias (ordered_sum.cuh)
 	DevBuf<uint64_t> d_thr_int; DevBuf<uint32_t> d_thr_hi;
 	DevBuf<char> d_names;
 	DevBuf<uint64_t> d_master_state, d_master, d_jump_states, d_jump_poly, d_jump_seq, d_jump_scratch;
@@ -1433,6 +1547,46 @@ static void decode_sys_errors(const SysErrorRecord &r, uint8_t *out){
 	}
 }
 
+// Reference::SumBias for a list of (sequence, fragment length) chains on `st`: sums[k], max[k] per chain.  Chunked exact evaluation
+// (ordered_sum.cuh); RSQ_BIAS_PATH=chain keeps the one-chain-per-CTA kernel (cross-check).
+static void run_sum_bias(rsq_engine &e, const std::vector<BiasParamDev> &params, double *d_sums, double *d_max, cudaStream_t st){
+	if(params.empty()){ return; }
+	if(const char *env = getenv("RSQ_BIAS_PATH")){
+		if(std::string(env) == "chain"){
+			e.d_bias_params.upload(params, st);
+			k_sum_bias<<<params.size(), 128, 0, st>>>(e.d_bias_params.p, params.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums, d_max);
+			++e.launches;
+			return;
+		}
+	}
+	std::vector<BiasChain> chains(params.size());
+	uint32_t K = 256;
+	for(const auto &p : params){ if(e.genome.seqs[p.ref_id].size() >= (1u << 25)){ K = 1024; } }   // long chains: fewer chunks for the in-order pass
+	if(const char *env = getenv("RSQ_BIAS_CHUNK")){ K = std::max(32, atoi(env) & ~31); }
+	uint64_t chunk_total = 0, cta_total = 0;
+	for(size_t k = 0; k < params.size(); ++k){
+		BiasChain &c = chains[k];
+		c.ref_id = params[k].ref_id; c.fragment_length = params[k].fragment_length; c.general = params[k].general;
+		c.n_pos = static_cast<uint32_t>(e.genome.seqs[c.ref_id].size()) - c.fragment_length + 1u;
+		c.n_chunks = (c.n_pos + K - 1) / K;
+		c.chunk_first = static_cast<uint32_t>(chunk_total); c.cta_first = static_cast<uint32_t>(cta_total);
+		chunk_total += c.n_chunks; cta_total += (c.n_chunks + kBiasChunkCta - 1) / kBiasChunkCta;
+	}
+	if(chunk_total >= (1ull << 32)){ throw std::runtime_error("bias normalisation: too many chunks"); }
+	e.d_bias_chains.upload(chains, st);
+	e.d_bias_plain.alloc(chunk_total); e.d_bias_start.alloc(chunk_total); e.d_bias_out.alloc(chunk_total); e.d_bias_cmax.alloc(chunk_total);
+	e.d_bias_tie.alloc(chunk_total); e.d_bias_reran.alloc(chains.size());
+	const uint32_t n = chains.size();
+	k_bias_chunks<false><<<static_cast<unsigned>(cta_total), kBiasChunkCta, 0, st>>>(e.d_bias_chains.p, n, K, e.d_seq_off.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p,
+	                                                                             nullptr, e.d_bias_plain.p, e.d_bias_cmax.p, nullptr);
+	k_bias_scan<<<(n + 3) / 4, 128, 0, st>>>(e.d_bias_chains.p, n, e.d_bias_plain.p, e.d_bias_cmax.p, e.d_bias_start.p, d_max);
+	k_bias_chunks<true><<<static_cast<unsigned>(cta_total), kBiasChunkCta, 0, st>>>(e.d_bias_chains.p, n, K, e.d_seq_off.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p,
+	                                                                            e.d_bias_start.p, e.d_bias_out.p, nullptr, e.d_bias_tie.p);
+	k_bias_resolve<<<(n + 3) / 4, 128, 0, st>>>(e.d_bias_chains.p, n, K, e.d_seq_off.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p,
+	                                            e.d_bias_start.p, e.d_bias_out.p, e.d_bias_tie.p, d_sums, e.d_bias_reran.p);
+	e.launches += 4;
+}
+
 static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &opt, rsq_sim_report *rep){
 	cudaStream_t s = e.stream;
 	const Profile &p = e.prof;
@@ -1657,13 +1811,11 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 	// so they overlap with the master stream and the systematic-error chains below.
 	std::vector<double> sums(params.size(), 0.0), maxb(params.size(), 0.0);
 	if(!params.empty() && !grouped){
-		DevBuf<BiasParamDev> &d_params = e.d_bias_params; d_params.upload(dparams, s);
 		DevBuf<double> &d_sums = e.d_bias_sums, &d_max = e.d_bias_max; d_sums.alloc(params.size()); d_max.alloc(params.size());
 		e.h_bias_results.ensure(2 * params.size() * sizeof(double));
 		RSQ_CUDA(cudaEventRecord(e.ev_fork, s));
 		RSQ_CUDA(cudaStreamWaitEvent(e.stream2, e.ev_fork, 0));
-		k_sum_bias<<<params.size(), 128, 0, e.stream2>>>(d_params.p, params.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
-		++e.launches;
+		run_sum_bias(e, dparams, d_sums.p, d_max.p, e.stream2);
 		RSQ_CUDA(cudaMemcpyAsync(e.h_bias_results.p, d_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
 		RSQ_CUDA(cudaMemcpyAsync(e.h_bias_results.p + sums.size() * 8, d_max.p, maxb.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
 		RSQ_CUDA(cudaEventRecord(e.ev_join, e.stream2));
@@ -1680,10 +1832,8 @@ static void prepare(rsq_engine &e, const Genome &ref_in, const rsq_sim_options &
 		RSQ_CUDA(cudaStreamWaitEvent(e.stream2, e.ev_fork, 0));
 		RSQ_CUDA(cudaMemsetAsync(d_all.p, 0, 2 * params.size() * 8, e.stream2));
 		if(!mine.empty()){
-			DevBuf<BiasParamDev> &d_params = e.d_bias_params; d_params.upload(mine, e.stream2);
 			DevBuf<double> &d_sums = e.d_bias_sums, &d_max = e.d_bias_max; d_sums.alloc(mine.size()); d_max.alloc(mine.size());
-			k_sum_bias<<<mine.size(), 128, 0, e.stream2>>>(d_params.p, mine.size(), e.d_seq_off.p, e.d_seq_len.p, e.d_sur_start.p, e.d_sur_end.p, e.d_gc_prefix.p, e.d_gc_bias.p, d_sums.p, d_max.p);
-			++e.launches;
+			run_sum_bias(e, mine, d_sums.p, d_max.p, e.stream2);
 			std::vector<double> hs(mine.size()), hm(mine.size());
 			RSQ_CUDA(cudaMemcpyAsync(hs.data(), d_sums.p, hs.size() * 8, cudaMemcpyDeviceToHost, e.stream2));
 			RSQ_CUDA(cudaMemcpyAsync(hm.data(), d_max.p, hm.size() * 8, cudaMemcpyDeviceToHost, e.stream2));

@@ -78,6 +78,37 @@ def test_block_batches_concatenate_to_the_whole_run(rb, engine, golden, monkeypa
     assert rep.pairs == r1.count(b"\n") // 4
 
 
+@pytest.mark.parametrize("chunk", [None, "32", "1024"])
+def test_chunked_bias_sums_equal_the_chain_kernel(rb, golden, monkeypatch, chunk):
+    """CalculateBiasNormalization: the chunked exact evaluation of Reference::SumBias (k_bias_chunks / _scan / _resolve, ordered_sum.cuh) gives
+    the same normalisation and thresholds, bit for bit, as the kernel that adds a whole chain in order (RSQ_BIAS_PATH=chain) - on the small
+    reference (chains of 800 .. 30 000 terms) and on a 6 Mbp sequence, for several chunk lengths."""
+    import bench
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synthetic
+    prof = rb.Profile.load_flat(golden["flat_r"])
+    refs = [rb.Reference.load_fasta(golden["small_ref"])]
+    seqs = make_synthetic.gen_reference([6_000_000, 1_500_000], 99)
+    refs.append(rb.Reference.from_memory(["a", "b"], [q.encode() for q in seqs]))
+    eng = rb.Engine(prof, 0)
+    try:
+        for ref in refs:
+            got = {}
+            for path in ("chain", "chunks"):
+                if path == "chain":
+                    monkeypatch.setenv("RSQ_BIAS_PATH", "chain")
+                else:
+                    monkeypatch.delenv("RSQ_BIAS_PATH", raising=False)
+                    if chunk:
+                        monkeypatch.setenv("RSQ_BIAS_CHUNK", chunk)
+                rep = eng.prepare(ref, seed=42, coverage=20.0)
+                got[path] = (rep.bias_normalization, eng.fetch("thresholds").tobytes())
+            assert got["chain"][0] == got["chunks"][0]
+            assert got["chain"][1] == got["chunks"][1]
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("path,batch", [("spec", 7), ("spec", 1), ("serial", 5)])
 def test_batches_with_windows_of_surrounding_biases(rb, engine, golden, monkeypatch, path, batch):
     """Multi-batch runs keep the per-position surrounding biases (16 bytes per base) of one batch only, recomputed in front of it, with the kernels

@@ -34,6 +34,15 @@ def test_mt19937_64_jump_polynomials_match_discard(workdir):
     assert out.returncode == 0 and "jump_mismatches=0" in out.stdout, out.stdout
 
 
+def test_chunked_ordered_sum_equals_the_chain(workdir):
+    """csrc/ordered_sum.cuh: the four passes that evaluate Reference::SumBias' strictly ordered FP64 sum in parallel chunks give the bits of the
+    plain chain - forced round-to-even ties, binade boundaries, zeros, 24 orders of magnitude, denormal starts, chunk lengths 1 .. 1024."""
+    exe = _compile("ordered_sum_check.cpp", os.path.join(workdir, "ordered_sum_check"))
+    for seed in ("5", "77", "2026"):
+        out = subprocess.run([exe, seed], capture_output=True, text=True)
+        assert out.returncode == 0 and "mismatches=0" in out.stdout, out.stdout
+
+
 def test_golden_fastq_is_what_the_reference_writes(oracle, golden, workdir):
     r1, r2 = run_oracle_sim(oracle, golden["reseq"], golden["small_ref"], 42, 20, os.path.join(workdir, "pin"))
     assert filecmp.cmp(r1, golden["r1"], shallow=False)
