@@ -376,6 +376,31 @@ def run_b200(args):
                                           "note": "same workload measured on ONE GPU of this pool with the same build (a committed measurement, not taken in this run)"}
                 except Exception:
                     pass
+        qpath = os.path.join(GOLDEN, "profile150q.flat.xz")
+        if world == 1 and kind == "c2" and os.path.exists(qpath) and not args.no_realistic:
+            # the same workload on the profile with realistic tables (every base quality 2..41, two tiles, 2.1 MB of LogArrayResult tables)
+            profq = rb.Profile.load_flat(unxz("profile150q.flat.xz", tmp))
+            engq = rb.Engine(profq, local_rank)
+            refq = make_reference("c2")[0]
+
+            def stepq():
+                engq.prepare(refq, seed=SEED, coverage=COVERAGE)
+                engq.simulate()
+                return engq.download().as_dict()
+            for _ in range(3):
+                stepq()
+            t0 = time.perf_counter()
+            repsq = [stepq() for _ in range(3)]
+            wallq = time.perf_counter() - t0
+            devq = sum(r["ms_bias"] + r["ms_syserr"] + r["ms_simulate"] + r["ms_gather"] for r in repsq)
+            pq = sum(r["pairs"] for r in repsq)
+            line["realistic_profile"] = {"profile": "profile150q: 40 base qualities (2..41), 2 tiles, 2.1 MB of probability tables, InDel rate 2e-5 (tests/golden/make_golden.py); "
+                                                    "parity pinned on the small reference (tests/golden/profile150q_small_sha256.json)",
+                                         "steps": 3, "warmup": 3, "value": pq / (devq / 1000.0), "unit": "pairs/s", "ms_per_step": devq / 3,
+                                         "e2e": {"value": pq / wallq, "ms_per_step": 1000 * wallq / 3}, "pairs_per_step": pq / 3,
+                                         "device_ms_breakdown": {k: sum(r[k] for r in repsq) / 3 for k in ("ms_upload", "ms_bias", "ms_syserr", "ms_simulate", "ms_gather", "ms_download")},
+                                         "spec_rounds": repsq[-1]["spec_rounds"]}
+            engq.close()
         if world == 1 and kind == "c2" and not args.no_cold:
             # the cold drop-in call: engine creation + table upload + prologue + simulation + both FASTQ files written (tmpfs)
             names, seqs, _ = workload_c2()
@@ -412,6 +437,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong-ref", action="store_true", help="N = 1: skip the single step of the strong-scaling workload")
     ap.add_argument("--no-cold", action="store_true", help="N = 1: skip the cold rsq_simulate call")
+    ap.add_argument("--no-realistic", action="store_true", help="N = 1: skip the steps on the realistic-tables profile (profile150q)")
     ap.add_argument("--workload", default=None, choices=["c2", "c5"], help="default: c2 for one GPU, c5 (strong scaling) for several")
     args = ap.parse_args()
     if args.impl == "reference":

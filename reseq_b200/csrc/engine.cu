@@ -477,10 +477,11 @@ struct SysChain {
 	const uint64_t *blk_off;   // runs with variants: where every SimBlock's draws start in raw (chain_raw); null otherwise
 	uint32_t *bstate;          // runs with variants: distance state in front of every SimBlock (for the draws of its variants)
 };
+constexpr uint32_t kSysCheckpoint = 64;   // positions between two checkpoints of a chunk's Markov state (power of two)
 struct SysChunk {
 	uint32_t chain; uint32_t begin; uint32_t end; uint32_t warm_from;
 	uint32_t in_dist, in_rate, out_dist, out_rate;
-	uint32_t dirty; uint32_t first_of_chain; uint32_t pad0, pad1;
+	uint32_t dirty; uint32_t first_of_chain; uint32_t computed /* ran once: its checkpoints are valid */, pad1;
 };
 
 __global__ void k_sys_chunks(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_t n_chunks, uint32_t max_n0,
@@ -797,7 +798,7 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 // then the chunk itself - with both Draws of a position going through coop_draw.
 __global__ void __launch_bounds__(128)
 k_sys_chunks_lanes(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_t n_chunks, uint32_t stride, uint32_t lanes_per_warp,
-                   uint32_t sys_gc_range, uint32_t reset_distance){
+                   uint32_t sys_gc_range, uint32_t reset_distance, uint32_t *checkpoints, uint32_t cp_per_chunk){
 	extern __shared__ __align__(16) unsigned char smem[];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	double *buf = reinterpret_cast<double *>(smem) + static_cast<size_t>(warp) * lanes_per_warp * stride;
@@ -812,6 +813,12 @@ k_sys_chunks_lanes(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_
 	const bool warming = have && ck.warm_from < ck.begin;
 	uint32_t p = have ? ck.warm_from : 0u, end = have ? ck.end : 0u;
 	SysState st{warming ? 0u : ck.in_dist, warming ? 0u : ck.in_rate};
+	// A chunk that is run again (its predecessor ended in another state than assumed) stops as soon as its Markov state equals the one its last
+	// run had at the same position (checkpoints every kSysCheckpoint positions): everything behind that point is what it was, the draws being
+	// a function of the position.  A fix-up pass then costs one checkpoint interval instead of a whole chunk.
+	const bool rerun = have && ck.computed != 0;
+	bool converged = false;
+	uint32_t *cp = checkpoints + static_cast<size_t>(have ? c : 0u) * cp_per_chunk;
 	// state in front of p: GC window (Simulator::UpdateGC), last base, dominant-base window
 	uint32_t gc_bases = 0, gc = 0, last_base = 4u, hist = 0, nwin = 0;
 	if(have){
@@ -825,7 +832,13 @@ k_sys_chunks_lanes(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_
 	}
 	bool zero;
 	while(true){
-		const bool active = have && p < end;
+		bool active = have && p < end;
+		if(active && p > ck.begin && ((p - ck.begin) & (kSysCheckpoint - 1u)) == 0u){
+			const uint32_t k = (p - ck.begin) / kSysCheckpoint - 1u;
+			const uint32_t packed = st.distance | (st.start_rate << 24);
+			if(rerun && cp[k] == packed){ converged = true; have = false; active = false; }
+			else{ cp[k] = packed; }
+		}
 		if(!__any_sync(0xffffffffu, active)){ break; }
 		uint32_t ref_base = 0, dom_base = 0, gc_percent = 50u, dist = 0, t1 = 0;
 		double u1 = 0.0, u2 = 0.0;
@@ -874,8 +887,9 @@ k_sys_chunks_lanes(Tables tab, const SysChain *chains, SysChunk *chunks, uint32_
 	if(have){
 		SysChunk &o = chunks[c];
 		if(warming){ o.in_dist = ck.in_dist; o.in_rate = ck.in_rate; o.warm_from = ck.begin; }
-		o.out_dist = st.distance; o.out_rate = st.start_rate; o.dirty = 0;
+		o.out_dist = st.distance; o.out_rate = st.start_rate; o.dirty = 0; o.computed = 1;
 	}
+	else if(converged){ chunks[c].dirty = 0; }   // the state at the chunk's end is the one of its last run
 }
 
 // Lanes 0 .. lanes_per_warp-1 of a warp own one read each; the other lanes only help with the likelihood products.
@@ -1206,7 +1220,7 @@ struct rsq_engine {
 	DevBuf<char> d_names;
 	DevBuf<uint64_t> d_master_state, d_master, d_jump_states, d_jump_poly, d_jump_seq, d_jump_scratch;
 	DevBuf<BlockDesc> d_blocks;
-	DevBuf<SysChain> d_sys_chains; DevBuf<SysChunk> d_sys_chunks; DevBuf<uint32_t> d_sys_dirty, d_gc_tiles;
+	DevBuf<SysChain> d_sys_chains; DevBuf<SysChunk> d_sys_chunks; DevBuf<uint32_t> d_sys_dirty, d_gc_tiles, d_sys_checkpoints;
 	DevBuf<BiasParamDev> d_bias_params; DevBuf<double> d_bias_sums, d_bias_max;
 	DevBuf<uint32_t> d_meth_off, d_meth_start, d_meth_end; DevBuf<double> d_meth_rate; DevBuf<int32_t> d_block_meth;
 	// variants (Reference::variants_ flattened, SimBlock::first_variant_id_, SysErrorVariant::var_errors_ of both strands)
@@ -1490,6 +1504,8 @@ static void run_sys_chains(rsq_engine &e, const std::vector<SysChain> &chains, c
 	DevBuf<SysChain> &d_chains = e.d_sys_chains; d_chains.upload(chains, e.stream);
 	DevBuf<SysChunk> &d_chunks = e.d_sys_chunks; d_chunks.upload(chunks, e.stream);
 	DevBuf<uint32_t> &d_dirty = e.d_sys_dirty; d_dirty.alloc(1);
+	const uint32_t cp_per_chunk = chunk_len / kSysCheckpoint + 1;
+	e.d_sys_checkpoints.alloc(static_cast<size_t>(chunks.size()) * cp_per_chunk);
 	const uint32_t n = chunks.size();
 	// one lane per chunk (lock step, likelihood products shared by the warp); RSQ_SYS_PATH=warp keeps the one-warp-per-chunk kernel
 	const bool lanes_path = !(getenv("RSQ_SYS_PATH") && std::string(getenv("RSQ_SYS_PATH")) == "warp");
@@ -1503,7 +1519,7 @@ static void run_sys_chains(rsq_engine &e, const std::vector<SysChain> &chains, c
 	while(dirty){
 		if(lanes_path){
 			const uint32_t per_cta = warps * lanes;
-			k_sys_chunks_lanes<<<(n + per_cta - 1) / per_cta, warps * 32, shmem, e.stream>>>(e.ctx.tab, d_chains.p, d_chunks.p, n, stride, lanes, e.sys_gc_range, e.prof.reset_distance);
+			k_sys_chunks_lanes<<<(n + per_cta - 1) / per_cta, warps * 32, shmem, e.stream>>>(e.ctx.tab, d_chains.p, d_chunks.p, n, stride, lanes, e.sys_gc_range, e.prof.reset_distance, e.d_sys_checkpoints.p, cp_per_chunk);
 		}
 		else{
 			k_sys_chunks<<<(n + warps - 1) / warps, warps * 32, shmem, e.stream>>>(e.ctx.tab, d_chains.p, d_chunks.p, n, e.max_n0, e.sys_gc_range, e.prof.reset_distance);

@@ -39,7 +39,7 @@ def golden(workdir):
                       ("flat_r", "profile150r.flat.xz"), ("reseq_r", "profile150r.reseq.xz"), ("ipf_r", "profile150r.reseq.ipf.xz"),
                       ("flat_t", "profile150t.flat.xz"), ("reseq_t", "profile150t.reseq.xz"), ("ipf_t", "profile150t.reseq.ipf.xz"),
                       ("flat_250", "profile250.flat.xz"), ("reseq_250", "profile250.reseq.xz"), ("ipf_250", "profile250.reseq.ipf.xz"),
-                      ("reseq_a", "profile150a.reseq.xz")):
+                      ("reseq_a", "profile150a.reseq.xz"), ("flat_q", "profile150q.flat.xz")):
         out[key] = _unxz(name, workdir)
     # profile150a = profile150 with InsertLengths()[0] = 700 (oracle/dump_tables patch_adapter_only): adapter-only pairs; same .ipf (same creation time)
     out["ipf_a"] = out["reseq_a"] + ".ipf"

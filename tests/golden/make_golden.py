@@ -13,6 +13,9 @@ Run in the build container (needs /root/reference for the TruSeq adapter files a
                                         for deletions instead of 8e-4): the bench profile; profile150 stays the InDel stress profile
   profile150t.{reseq,reseq.ipf,flat}.xz same pipeline, `--tiles`, from a SAM with Casava-1.8 read names on three tiles and 20 % of the reads 144
                                         instead of 150 bases long: per-tile tables, tile and read-length draws
+  profile150q.flat.xz + profile150q_small_sha256.json   the "realistic" bench profile: 60 000 pairs with every base quality 2..41 (40 values), two tiles, InDel rate 2e-5:
+                                        2.1 MB of LogArrayResult tables (profile150r: 0.5 MB).  Its .reseq (89 MB) and .ipf (26 MB) are too large to commit: only the
+                                        flat image the reference holds in memory is, plus the sha256 of the reference's FASTQ for simref_small.fa (seed 42, 20x)
   profile250.{reseq,reseq.ipf,flat}.xz  same pipeline from a SAM with 2x250 reads (the read length of BASELINE config C4), InDel rate 1e-4
   simref_small.fa                       small multi-contig reference with N runs and one too-short contig
   sim_small_seed42_R{1,2}.fq.xz         `reseq illuminaPE -j 1 --seed 42 -c 20` on simref_small.fa
@@ -119,6 +122,29 @@ def main():
     run([DUMP, "profile", prof_t, os.path.join(tmp, "profile150t.flat")])
     for name in ("profile150t.reseq", "profile150t.reseq.ipf", "profile150t.flat"):
         xz(os.path.join(tmp, name), os.path.join(HERE, name + ".xz"))
+
+    # realistic tables: 40 quality values, two tiles (IPF takes ~20 minutes on 16 threads); only the flat image and a pinned run are committed
+    if os.environ.get("RSQ_GOLDEN_REALISTIC"):
+        import hashlib
+        import json
+        sam_q = os.path.join(tmp, "prof_q.sam")
+        run([py, SYN, "sam", ref, sam_q, "--pairs", "60000", "--seed", "19", "--quals", "40", "--tiles", "1101,2204", "--indel-rate", "0.00002"])
+        raw_q = os.path.join(tmp, "raw_q.reseq")
+        run([ORACLE, "illuminaPE", "-j", "16", "-b", sam_q, "-r", ref, "--adapterFile", ADAPTERS + ".fa", "--adapterMatrix", ADAPTERS + ".mat",
+             "--statsOnly", "--tiles", "-S", raw_q])
+        log = run([ORACLE, "illuminaPE", "-j", "16", "-s", raw_q, "-r", ref, "--stopAfterEstimation"])
+        if "did not reach precision aim" in log:
+            raise SystemExit("IPF did not converge for every table of the realistic profile")
+        prof_q = os.path.join(tmp, "profile150q.reseq")
+        run([DUMP, "patch", raw_q, prof_q, "5"])
+        shutil.copy(raw_q + ".ipf", prof_q + ".ipf")
+        run([DUMP, "profile", prof_q, os.path.join(tmp, "profile150q.flat")])
+        xz(os.path.join(tmp, "profile150q.flat"), os.path.join(HERE, "profile150q.flat.xz"))
+        q1, q2 = os.path.join(tmp, "q_R1.fq"), os.path.join(tmp, "q_R2.fq")
+        run([ORACLE, "illuminaPE", "-j", "1", "--verbosity", "1", "-s", prof_q, "-R", os.path.join(HERE, "simref_small.fa"), "--ipfIterations", "0", "--seed", "42", "-c", "20", "-1", q1, "-2", q2])
+        json.dump({"profile": "profile150q", "r1": hashlib.sha256(open(q1, "rb").read()).hexdigest(), "r2": hashlib.sha256(open(q2, "rb").read()).hexdigest(),
+                   "pairs": open(q1, "rb").read().count(b"\n") // 4, "bytes": [os.path.getsize(q1), os.path.getsize(q2)]},
+                  open(os.path.join(HERE, "profile150q_small_sha256.json"), "w"), indent=1, sort_keys=True)
 
     # 2x250 reads (config C4's read length)
     sam_l = os.path.join(tmp, "prof_250.sam")

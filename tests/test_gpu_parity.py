@@ -78,6 +78,23 @@ def test_block_batches_concatenate_to_the_whole_run(rb, engine, golden, monkeypa
     assert rep.pairs == r1.count(b"\n") // 4
 
 
+@pytest.mark.parametrize("path", ["spec", "serial"])
+def test_realistic_tables_profile_equals_the_reference(rb, golden, monkeypatch, path):
+    """profile150q: every base quality 2..41, two tiles, 2.1 MB of probability tables (the bench's second profile).  Only its flat image is
+    committed (the archives are 115 MB); the reference's FASTQ for the small reference is pinned by hash (tests/golden/make_golden.py)."""
+    import json
+    want = json.load(open(os.path.join(GOLDEN_DIR, "profile150q_small_sha256.json")))
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    prof = rb.Profile.load_flat(golden["flat_q"])
+    eng = rb.Engine(prof, 0)
+    try:
+        r1, r2, rep = _simulate(eng, rb.Reference.load_fasta(golden["small_ref"]), seed=42, coverage=20.0)
+    finally:
+        eng.close()
+    assert rep.pairs == want["pairs"] and [len(r1), len(r2)] == want["bytes"]
+    assert hashlib.sha256(r1).hexdigest() == want["r1"] and hashlib.sha256(r2).hexdigest() == want["r2"]
+
+
 @pytest.mark.parametrize("chunk", [None, "32", "1024"])
 def test_chunked_bias_sums_equal_the_chain_kernel(rb, golden, monkeypatch, chunk):
     """CalculateBiasNormalization: the chunked exact evaluation of Reference::SumBias (k_bias_chunks / _scan / _resolve, ordered_sum.cuh) gives
