@@ -17,7 +17,14 @@
 #define RSQ_HD __host__ __device__ __forceinline__
 #define RSQ_HD_NOINLINE __host__ __device__
 #define RSQ_HD_COLD __host__ __device__ __forceinline__   // (out-of-line variants of these were measured: slower - call overhead and spills outweigh the smaller code)
+// helpers that only the variant-aware instantiations call (A/B build switch: out of line keeps those kernels' code smaller)
+#ifdef RSQ_VCOLD_NOINLINE
+#define RSQ_HD_VCOLD __host__ __device__ __noinline__
 #else
+#define RSQ_HD_VCOLD __host__ __device__ __forceinline__
+#endif
+#else
+#define RSQ_HD_VCOLD inline __attribute__((noinline))
 #define RSQ_HD inline
 #define RSQ_HD_NOINLINE
 #define RSQ_HD_COLD inline __attribute__((noinline))

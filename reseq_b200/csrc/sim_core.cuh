@@ -499,7 +499,7 @@ struct VarEval {
 struct VarGeom { uint32_t valid, gc_perc; double sur_start, sur_end; AllelePoint end; uint32_t end_hint; };
 // what the out-of-line evaluation reads of the run (passed by value: a reference to the kernel's SimCtx would force the whole struct into local memory)
 struct VarGeomCtx { const uint8_t *seq; const uint32_t *gcp; const double *sur_start, *sur_end; const double *sur_tab0, *sur_tab1, *sur_tab2; uint32_t L, n_read_max, probe_plain; };
-RSQ_HD_COLD void eval_allele_geometry(const VarGeomCtx gc, const VariantView v, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t fl,
+RSQ_HD_VCOLD void eval_allele_geometry(const VarGeomCtx gc, const VariantView v, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t fl,
                                       uint32_t allele, VarEval &e, VarGeom &geo){
 	const uint32_t L = gc.L;
 	const uint32_t *gcp = gc.gcp;

@@ -364,7 +364,7 @@ template<class G> RSQ_HD_COLD RingPos ct_conversion_ring(const G &g, const SimCt
 	ct_conversion(g, c, rng, read, read_len, seq_id, start_pos, cur_methylation_start, reversed);
 	return RingPos{r.cur, r.avail, 0};
 }
-template<class G> RSQ_HD_COLD RingPos ct_conversion_var_ring(const G &g, const SimCtx &c, uint64_t *ring_w, uint32_t cur, uint32_t avail, uint8_t *read, uint32_t read_len, uint32_t seq_id,
+template<class G> RSQ_HD_VCOLD RingPos ct_conversion_var_ring(const G &g, const SimCtx &c, uint64_t *ring_w, uint32_t cur, uint32_t avail, uint8_t *read, uint32_t read_len, uint32_t seq_id,
                                                              uint32_t start_pos, uint32_t allele, int32_t cur_methylation_start, bool reversed, const VariantView v, int32_t first_variant,
                                                              uint32_t first_variant_pos){
 	MtRing r; r.w = ring_w; r.cur = cur; r.avail = avail;
@@ -373,7 +373,7 @@ template<class G> RSQ_HD_COLD RingPos ct_conversion_var_ring(const G &g, const S
 	return RingPos{r.cur, r.avail, 0};
 }
 // GetOrgSeq with variants, out of line
-template<class G> RSQ_HD_COLD void splice_fragment_ends_cold(const G &g, const SimCtx &c, const VariantView v, uint32_t ref_id, uint32_t strand, uint32_t pos, uint32_t first_var,
+template<class G> RSQ_HD_VCOLD void splice_fragment_ends_cold(const G &g, const SimCtx &c, const VariantView v, uint32_t ref_id, uint32_t strand, uint32_t pos, uint32_t first_var,
                                                              uint32_t start_variant_pos, uint32_t fl, const VarEval e, const VarGeom geo, uint8_t *frag_fwd, uint8_t *frag_rev, uint32_t which){
 	splice_fragment_ends(g, c, v, ref_id, strand, pos, first_var, start_variant_pos, fl, e, geo, frag_fwd, frag_rev, which);
 }

@@ -324,7 +324,7 @@ struct AllelePoint { uint32_t p; uint32_t k; int32_t ins; };
 
 // The next n bases of the allele behind the point.  Beyond the sequence end the reference rolls around into its own first bases and ignores
 // variants there (Simulator.cpp:1601, 1706).  hint: an index near the first variant at or behind the point.
-RSQ_HD_COLD void allele_bases_forward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint = 0){
+RSQ_HD_VCOLD void allele_bases_forward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint = 0){
 	uint32_t i = 0, p = at.p;
 	if(at.k){
 		for(uint32_t j = at.k; j < v.length(at.ins) && i < n; ++j){ out[i++] = v.base(at.ins, j); }
@@ -348,7 +348,7 @@ RSQ_HD_COLD void allele_bases_forward(const VariantView &v, const uint8_t *seq, 
 	}
 }
 // The n bases of the allele in front of the point, nearest first.  In front of the sequence start: the reference's last bases, variants ignored.
-RSQ_HD_COLD void allele_bases_backward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint = 0){
+RSQ_HD_VCOLD void allele_bases_backward(const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint = 0){
 	uint32_t i = 0;
 	if(at.k){ for(uint32_t j = at.k; j-- > 0 && i < n; ){ out[i++] = v.base(at.ins, j); } }
 	int64_t q = static_cast<int64_t>(at.p) - 1;
@@ -374,7 +374,7 @@ RSQ_HD_COLD void allele_bases_backward(const VariantView &v, const uint8_t *seq,
 // The same two walks for a lane group writing to memory all lanes see (staged fragment ends): the runs of reference bases between variants
 // are copied by all lanes, single replacement bases by lane 0; every lane keeps the same bookkeeping.  comp: store 3 - base.
 template<class G>
-RSQ_HD_COLD void allele_bases_forward_g(const G &g, const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint){
+RSQ_HD_VCOLD void allele_bases_forward_g(const G &g, const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint){
 	uint32_t i = 0, p = at.p;
 	if(at.k){
 		if(g.lane() == 0){ uint32_t ii = 0; for(uint32_t j = at.k; j < v.length(at.ins) && ii < n; ++j){ out[ii++] = v.base(at.ins, j); } }
@@ -404,7 +404,7 @@ RSQ_HD_COLD void allele_bases_forward_g(const G &g, const VariantView &v, const 
 	g.sync();
 }
 template<class G>
-RSQ_HD_COLD void allele_bases_backward_g(const G &g, const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint, bool comp){
+RSQ_HD_VCOLD void allele_bases_backward_g(const G &g, const VariantView &v, const uint8_t *seq, uint32_t L, uint32_t allele, AllelePoint at, uint32_t n, uint8_t *out, uint32_t hint, bool comp){
 	const uint32_t cx = comp ? 3u : 0u;   // 3 - b == 3 ^ b for two-bit codes
 	uint32_t i = 0;
 	if(at.k){
@@ -452,7 +452,7 @@ RSQ_HD uint32_t count_gc_bases(const VariantView &v, uint32_t var, uint32_t from
 	return gc;
 }
 // gcp: G/C prefix counts of the reference sequence ([L + 1]).  first_var / start_variant_pos: VariantBiasVarModifiers::StartVariant.
-RSQ_HD_COLD void allele_hit(const VariantView &v, const uint32_t *gcp, uint32_t L, uint32_t allele, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos,
+RSQ_HD_VCOLD void allele_hit(const VariantView &v, const uint32_t *gcp, uint32_t L, uint32_t allele, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos,
                        uint32_t fl, AlleleHit &h){
 	uint32_t consumed = 0, gc = 0, p = pos;
 	h.valid = 0; h.end_var = -1; h.end_var_pos = 0; h.end = AllelePoint{0, 0, -1}; h.end_position = L; h.gc_percent = 0;
@@ -580,7 +580,7 @@ RSQ_HD bool sysw_plain_step(const uint8_t *sys, SysWalk &w, uint32_t &res){
 	return true;
 }
 // returns dominant error | rate << 8 (out of line: the steps between variants are sysw_plain_step)
-RSQ_HD_COLD uint32_t sysw_next(const SysWalkCtx &c, SysWalk &w, uint32_t allele){
+RSQ_HD_VCOLD uint32_t sysw_next(const SysWalkCtx &c, SysWalk &w, uint32_t allele){
 	uint32_t res = 0;
 	if(sysw_plain_step(c.sys, w, res)){ return res; }
 	bool no_variant = true;
@@ -630,7 +630,7 @@ RSQ_HD_COLD uint32_t sysw_next(const SysWalkCtx &c, SysWalk &w, uint32_t allele)
 	return res;
 }
 // FillReadPart's deletion branch: the error rate of sys_errors_[block_pos], then the position advances without looking at the variants
-RSQ_HD_COLD uint32_t sysw_deletion(const SysWalkCtx &c, SysWalk &w){
+RSQ_HD_VCOLD uint32_t sysw_deletion(const SysWalkCtx &c, SysWalk &w){
 	const uint32_t rate = sysw_entry(c, w)[1];
 	if(w.var_pos){
 		const uint32_t var = sysw_var(c, w.block, static_cast<uint32_t>(w.cur_var));
@@ -640,14 +640,14 @@ RSQ_HD_COLD uint32_t sysw_deletion(const SysWalkCtx &c, SysWalk &w){
 	return rate;
 }
 // CreateReads (Simulator.cpp:653-689): where the two reads of a fragment start in the block chains.  start_var / end_var: StartVariant / EndVariant.
-RSQ_HD_COLD SysWalk sysw_forward_start(const SysWalkCtx &c, uint32_t start_block, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos){
+RSQ_HD_VCOLD SysWalk sysw_forward_start(const SysWalkCtx &c, uint32_t start_block, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos){
 	SysWalk w;
 	w.block = start_block; w.block_pos = pos - 1000u * start_block;
 	w.cur_var = static_cast<int32_t>(first_var) - static_cast<int32_t>(c.block_first[start_block]); w.var_pos = start_variant_pos;
 	sysw_refresh(c, w);
 	return w;
 }
-RSQ_HD_COLD SysWalk sysw_reverse_start(const SysWalkCtx &c, uint32_t start_block, uint32_t end_position, int32_t end_var, uint32_t end_var_pos){
+RSQ_HD_VCOLD SysWalk sysw_reverse_start(const SysWalkCtx &c, uint32_t start_block, uint32_t end_position, int32_t end_var, uint32_t end_var_pos){
 	SysWalk w;
 	uint32_t b = start_block;
 	while(sysw_block_end(c, b) < end_position){ ++b; }
