@@ -4,16 +4,17 @@
 //   tables      TableDesc[] + FP64 blob + par0 (every LogArrayResult, ~1-7 MB: L2 resident)
 //   reference   1 byte / base (Dna codes after ReplaceN), concatenated sequences
 //   gc_prefix   u32 / base (+1 per sequence)          -> fragment GC in O(1)
-//   sur_start, sur_end  f64 / base                    -> SurroundingBias::Bias per fragment end
+//   sur_start, sur_end  f64 / base                    -> SurroundingBias::Bias per fragment end (multi-batch runs: one batch's window, see simulate())
 //   sys_fwd, sys_rev    2 bytes / base / strand       -> (dominant error, rate) of SetSystematicErrors
 //   master      raw mt19937_64 outputs of one SimUnit (2*blocks + 4*L words), reused per sequence
-//   blocks      BlockDesc[] (seed, ref, start, id)
+//   blocks      BlockDesc[] (seed, ref, start, id, first methylation region, first variant)
+//   variants    runs with -V: flattened Reference::variants_, per-block first variant, systematic errors + context bytes of replacement bases
 //   per batch of SimBlocks (speculative path, spec_core.cuh): snapshots, read jobs, stream slices, record slots in slabs of 32
 //               chained per block; the FASTQ text of a batch is gathered in block order into one of two device buffers and
 //               pulled to the host by the writer threads (ChunkWriter) while the next batch is simulated
 //   arena       serial path only: fixed-size chunks of FASTQ text, per (block, segment) chains
-// Kernels: k_surroundings, k_gc_*, k_sum_bias, k_master_seed/_stream/_jump_gen/_jump_xor, k_sys_chunks_lanes (k_sys_chunks) + k_sys_check,
-//          k_build_blocks, k_spec_init/_scan/_reads/_block_out/_gather (product path), k_simulate + k_adapter_only + k_gather and
+// Kernels: k_surroundings, k_gc_*, k_bias_chunks/_scan/_resolve (k_sum_bias: chain form), k_master_seed/_stream/_jump_gen/_jump_xor, k_sys_chunks_lanes (k_sys_chunks) + k_sys_check,
+//          k_build_blocks, k_var_sys_errors, k_spec_init/_scan<kVar>/_reads<kVar>/_block_out/_gather (product path), k_deflate_* (gzip output), k_simulate + k_adapter_only + k_gather and
 //          k_error_model (serial forms: cross-check and fallback), k_block_offsets.
 #include <cuda_runtime.h>
 #include <algorithm>

@@ -10,7 +10,7 @@
 // One lane group owns one 1000-bp SimBlock: the block's mt19937_64 stream is consumed strictly in the
 // reference's order (scan draw per (position, fragment length), then the draws of every fragment hit),
 // lanes only share the work *inside* a step: 32 scan draws at a time, the candidates of a Draw, byte copies.
-// Variants (VCF) and methylation are not handled by this revision; the host refuses such runs.
+// Methylation (CTConversion) and variants (simulate_block_var, eval_allele_hit, splice_fragment_ends; building blocks in variant_core.cuh) are part of it.
 #pragma once
 #include "core.cuh"
 #include "variant_core.cuh"

@@ -18,7 +18,9 @@
 //   allele_fragment_counts           the tail of FragmentDistributionStats::GetFragmentCounts with an allele count
 //                                    (FragmentDistributionStats.cpp:3602-3626, 900-907): NB(mean / alleles, Dispersion(mean) / alleles)
 //
-// Not consumed by a kernel yet: rsq_engine_prepare refuses references with variants until the scan and read kernels take alleles.
+// Further down: what the kernels use per hit and per base (VarCtx, start passes over inserted bases, possible alleles, allele walkers,
+// allele_hit, the SysWalk cursor = GetSysErrorFromBlock with the reference's quirks).  k_simulate / k_spec_scan<true> / k_spec_reads<true>
+// consume them (sim_core.cuh: eval_allele_hit, splice_fragment_ends, simulate_block_var; spec_core.cuh: scan_window<true>, ReadMachineT<true>).
 #pragma once
 #include "bias_core.cuh"
 
