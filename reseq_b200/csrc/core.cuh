@@ -18,14 +18,18 @@ namespace rsq {
 #if defined(__CUDACC__)
 struct WarpGroup {
 	static constexpr int kSize = 32;
+	static constexpr bool kCompactCode = false;
 	__device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
 	__device__ __forceinline__ void sync() const { __syncwarp(); }
 	__device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
 	__device__ __forceinline__ uint32_t reduce_add(uint32_t v) const { return __reduce_add_sync(0xffffffffu, v); }
 };
+// the same lanes for instantiations whose code has to stay small (the variant-aware scan): rarely run loops are called, not inlined
+struct WarpGroupCompact : WarpGroup { static constexpr bool kCompactCode = true; };
 #endif
 struct SingleLane {
 	static constexpr int kSize = 1;
+	static constexpr bool kCompactCode = false;
 	RSQ_HD int lane() const { return 0; }
 	RSQ_HD void sync() const {}
 	RSQ_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }

@@ -17,6 +17,7 @@
 //          k_build_blocks, k_var_sys_errors, k_spec_init/_scan<kVar>/_reads<kVar>/_block_out/_gather (product path), k_deflate_* (gzip output), k_simulate + k_adapter_only + k_gather and
 //          k_error_model (serial forms: cross-check and fallback), k_block_offsets.
 #include <cuda_runtime.h>
+#include <type_traits>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -674,7 +675,7 @@ __device__ __forceinline__ void spec_scan_body(const SimCtx &c, const SpecCtx &s
 	__shared__ __align__(8) uint64_t thr_bar[kWarpsPerCta];
 	// dynamic: per warp its unit's row of threshold high words (c.thr_hi_stride entries, 16-byte rows), then - runs with variants - 2 * num_alleles chosen (allele, strand) ids
 	extern __shared__ __align__(16) unsigned char scan_dyn[];
-	WarpGroup g;
+	typename std::conditional<kVar, WarpGroupCompact, WarpGroup>::type g;
 	const uint32_t warp = threadIdx.x >> 5;
 	const uint32_t u = unit_first + blockIdx.x * kWarpsPerCta + warp;
 	if(u >= unit_end){ return; }

@@ -571,35 +571,35 @@ template<class Uniform>
 RSQ_HD bool eval_allele_hit(const SimCtx &c, const VariantView &v, uint32_t ref_id, uint32_t pos, uint32_t first_var, uint32_t start_variant_pos, uint32_t fl,
                             uint32_t allele, double thr0, Uniform &&uniform, VarEval &e, VarGeom &geo, bool &runaway){
 	const uint64_t off = c.seq_off[ref_id];
-	{
-		// nearly two thirds of the hits have no variant of any allele within reach of the fragment and its surroundings: the reference's arrays, no call
-		const uint32_t hint = var_seek(v, first_var, pos);
-		const bool near = start_variant_pos || (c.var.loaded & 2u) == 0u && ((hint < v.n && v.position[hint] <= pos + fl + 12u) || (hint > 0 && v.position[hint - 1] + 12u >= pos));
-		if(!near){
-			const uint32_t L = c.seq_len[ref_id];
-			const uint32_t *gcp = c.gc_prefix + off + ref_id;
-			e.allele = allele; e.counts = 0; e.end_var = static_cast<int32_t>(hint) - 1; e.end_var_pos = 0; e.slow = 0;
-			e.end_position = pos + fl;
-			geo.valid = 0; geo.end = AllelePoint{pos + fl, 0, -1}; geo.end_hint = hint;
-			if(!(e.end_position < L)){ return false; }
-			geo.valid = 1;
-			const double rv = uniform();
-			const double adjusted_random = add_rn(thr0, mul_rn(rv, sub_rn(1.0, thr0)));
-			e.counts = fragment_counts_alleles(c, ref_id, fl, percent_u32(gcp[e.end_position] - gcp[pos], fl), c.sur_start[off + pos], c.sur_end[off + e.end_position - 1], adjusted_random,
-			                                   c.var.num_alleles, runaway);
-			return true;
-		}
+	// nearly two thirds of the hits have no variant of any allele within reach of the fragment and its surroundings: the reference's arrays, no walk.
+	// Both cases end in ONE draw + count evaluation (the Binomial / pow code exists once in the kernel: the variant-aware scan is bound by instruction fetches)
+	const uint32_t hint = var_seek(v, first_var, pos);
+	const bool near = start_variant_pos || (c.var.loaded & 2u) == 0u && ((hint < v.n && v.position[hint] <= pos + fl + 12u) || (hint > 0 && v.position[hint - 1] + 12u >= pos));
+	uint32_t gc_perc;
+	double sur_s, sur_e;
+	if(!near){
+		const uint32_t L = c.seq_len[ref_id];
+		const uint32_t *gcp = c.gc_prefix + off + ref_id;
+		e.allele = allele; e.counts = 0; e.end_var = static_cast<int32_t>(hint) - 1; e.end_var_pos = 0; e.slow = 0;
+		e.end_position = pos + fl;
+		geo.valid = 0; geo.end = AllelePoint{pos + fl, 0, -1}; geo.end_hint = hint;
+		if(!(e.end_position < L)){ return false; }
+		geo.valid = 1;
+		gc_perc = percent_u32(gcp[e.end_position] - gcp[pos], fl); sur_s = c.sur_start[off + pos]; sur_e = c.sur_end[off + e.end_position - 1];
 	}
-	VarGeomCtx gc;
-	gc.seq = c.ref + off; gc.gcp = c.gc_prefix + off + ref_id; gc.sur_start = c.sur_start + off; gc.sur_end = c.sur_end + off;
-	gc.sur_tab0 = c.var.sur_tab[0]; gc.sur_tab1 = c.var.sur_tab[1]; gc.sur_tab2 = c.var.sur_tab[2];
-	gc.L = c.seq_len[ref_id]; gc.n_read_max = (c.read_len_to[0] > c.read_len_to[1] ? c.read_len_to[0] : c.read_len_to[1]) + c.max_len_deletion + 2u;
-	gc.probe_plain = (c.var.loaded & 2u) ? 1u : 0u;
-	eval_allele_geometry(gc, v, pos, first_var, start_variant_pos, fl, allele, e, geo);
-	if(!geo.valid){ return false; }
+	else{
+		VarGeomCtx gc;
+		gc.seq = c.ref + off; gc.gcp = c.gc_prefix + off + ref_id; gc.sur_start = c.sur_start + off; gc.sur_end = c.sur_end + off;
+		gc.sur_tab0 = c.var.sur_tab[0]; gc.sur_tab1 = c.var.sur_tab[1]; gc.sur_tab2 = c.var.sur_tab[2];
+		gc.L = c.seq_len[ref_id]; gc.n_read_max = (c.read_len_to[0] > c.read_len_to[1] ? c.read_len_to[0] : c.read_len_to[1]) + c.max_len_deletion + 2u;
+		gc.probe_plain = (c.var.loaded & 2u) ? 1u : 0u;
+		eval_allele_geometry(gc, v, pos, first_var, start_variant_pos, fl, allele, e, geo);
+		if(!geo.valid){ return false; }
+		gc_perc = geo.gc_perc; sur_s = geo.sur_start; sur_e = geo.sur_end;
+	}
 	const double rv = uniform();
 	const double adjusted_random = add_rn(thr0, mul_rn(rv, sub_rn(1.0, thr0)));
-	e.counts = fragment_counts_alleles(c, ref_id, fl, geo.gc_perc, geo.sur_start, geo.sur_end, adjusted_random, c.var.num_alleles, runaway);
+	e.counts = fragment_counts_alleles(c, ref_id, fl, gc_perc, sur_s, sur_e, adjusted_random, c.var.num_alleles, runaway);
 	if(!e.counts){ e.slow = 0; }
 	return true;
 }
