@@ -493,7 +493,9 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	int32_t cur_meth = snap.cur_meth;
 	uint64_t read_number = snap.read_number, draws = snap.scan_draws;
 	bool finished = snap.finished != 0;
-	const bool with_var = kVar && c.var.loaded != 0 && sp.em_recs == nullptr && u < sp.n_blocks;   // kVar: the instantiation for runs with variants (keeps the plain one lean)
+	// kVar: the instantiation for runs with variants, launched for exactly those (simulate_spec_batch); what it can never reach - seqToIllumina records, the
+	// plain evaluation of a hit - is compiled out of it: it is bound by instruction fetches and every kilobyte of code counts
+	const bool with_var = kVar && u < sp.n_blocks;
 	uint32_t first_var = snap.first_var, start_variant_pos = snap.start_variant_pos;
 	uint16_t *chosen_bank_out = nullptr;
 	uint32_t next_var_pos = 0xffffffffu;   // position of variant first_var (0xffffffff: none left): the per-position checks below stay in registers
@@ -517,7 +519,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 		}
 		return;
 	}
-	const bool records = sp.em_recs != nullptr;
+	const bool records = !kVar && sp.em_recs != nullptr;
 	const bool adapter_only = !records && u >= sp.n_blocks;
 	BlockDesc b{};
 	if(!adapter_only && !records){ b = descs[first_desc + u]; }
@@ -660,7 +662,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 				++hit.ci;
 				continue;
 			}
-			if(!with_var && hit.ci < hit.n_chosen){
+			if(!kVar && hit.ci < hit.n_chosen){
 				const uint32_t strand = (hit.ci ? hit.chosen1 : hit.chosen0) & 1u;
 				const uint32_t fl = hit.fragment_length;
 				const uint32_t cur_end = pos + fl;
