@@ -72,6 +72,19 @@ def test_variant_run_in_shards(rb, engine, golden, shards):
     assert parts == want
 
 
+@pytest.mark.parametrize("path,batch", [("spec", 5), ("spec", 1), ("serial", 9)])
+def test_variant_run_in_batches_with_surroundings_windows(rb, engine, golden, monkeypatch, path, batch):
+    """What a large genome with a VCF does on one GPU: several batches of SimBlocks, each with its own window of per-position surrounding biases
+    (RSQ_SUR_WINDOW forces it on the small reference): the variant-aware evaluation reads the same arrays through the window-biased pointers."""
+    monkeypatch.setenv("RSQ_SIM_PATH", path)
+    monkeypatch.setenv("RSQ_BATCH_UNITS", str(batch))
+    monkeypatch.setenv("RSQ_SUR_WINDOW", "1")
+    want = _golden_fastq(golden, "var")
+    r1, r2, rep = _simulate(engine, _ref_with_vcf(rb, golden, "var"), seed=42, coverage=20.0)
+    assert [r1, r2] == want
+    assert rep.batches == -(-rep.blocks // batch)
+
+
 def test_engine_switches_between_variant_and_plain_runs(rb, engine, golden):
     want = _golden_fastq(golden, "var")
     r1, r2, _ = _simulate(engine, _ref_with_vcf(rb, golden, "var"), seed=42, coverage=20.0)
