@@ -721,6 +721,14 @@ k_spec_scan<true>(const __grid_constant__ SimCtx c, const __grid_constant__ Spec
 #define RSQ_PROD_UNROLL 4   // candidates per lane whose four table-row loads are in flight together (each trip of the product loop waits one L2 round trip)
 #endif
 constexpr int kProdUnroll = RSQ_PROD_UNROLL;
+#ifndef RSQ_COOP_WIDE_FROM
+#define RSQ_COOP_WIDE_FROM 20
+#endif
+constexpr uint32_t kCoopWideFrom = RSQ_COOP_WIDE_FROM;   // candidate lists longer than this get four lanes per read
+#ifndef RSQ_COOP_WIDE_SHIFT
+#define RSQ_COOP_WIDE_SHIFT 2
+#endif
+constexpr uint32_t kCoopWideShift = RSQ_COOP_WIDE_SHIFT;
 __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint32_t stride, uint32_t n_rows, bool active, uint32_t table_id,
                                                uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, double u, bool &zero){
 	const unsigned amask = __ballot_sync(0xffffffffu, active);
@@ -742,8 +750,16 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 	__syncwarp();
 	// 32 / rows-per-pass lanes work on every read of a pass at the same time (one trip of shuffles, all reads of the pass in
 	// flight together); 8 or 16 reads per pass, 32 reads per warp take two passes of 16
-	const uint32_t pass_rows = n_rows <= 8u ? 8u : 16u;
-	const uint32_t lpr_shift = pass_rows == 8u ? 2u : 1u, lpr = 1u << lpr_shift;
+#ifdef RSQ_COOP_LPR_SHIFT   // A/B builds: 2^shift lanes per read and pass (fewer reads per pass = fewer distinct table rows, i.e. L1 wavefronts, per load instruction)
+	const uint32_t lpr_shift = RSQ_COOP_LPR_SHIFT, lpr = 1u << lpr_shift, pass_rows = 32u >> lpr_shift;
+#else
+	// two lanes per read for short candidate lists, four for long ones (a quality draw of a profile with 40 quality values): more lanes per read mean
+	// fewer distinct table rows - L1 wavefronts, the pipe this kernel saturates - per load instruction, but idle lanes when the list is short
+	// (E. coli: 57.9 ms with two lanes on profile150r against 65.6 with four; 122.5 against 103.3 ms on profile150q)
+	uint32_t lpr_shift = n4 > kCoopWideFrom ? kCoopWideShift : 1u;
+	if((32u >> lpr_shift) > n_rows){ lpr_shift = 2u; }   // 8 reads per warp: one pass of 8
+	const uint32_t lpr = 1u << lpr_shift, pass_rows = 32u >> lpr_shift;
+#endif
 	for(uint32_t first = 0; first < n_rows; first += pass_rows){
 		const uint32_t src = first + (lane >> lpr_shift), i = lane & (lpr - 1u);
 		const uint32_t sn0 = __shfl_sync(0xffffffffu, n0, src);
