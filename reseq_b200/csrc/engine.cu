@@ -726,7 +726,7 @@ constexpr int kProdUnroll = RSQ_PROD_UNROLL;
 #endif
 constexpr uint32_t kCoopWideFrom = RSQ_COOP_WIDE_FROM;   // candidate lists longer than this get four lanes per read
 #ifndef RSQ_COOP_WIDE_SHIFT
-#define RSQ_COOP_WIDE_SHIFT 2
+#define RSQ_COOP_WIDE_SHIFT 3   // more than 32 candidates: eight lanes per read (profile150q: 84.5 ms; four lanes 94.7, sixteen 87.8, two 122.5)
 #endif
 constexpr uint32_t kCoopWideShift = RSQ_COOP_WIDE_SHIFT;
 __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint32_t stride, uint32_t n_rows, bool active, uint32_t table_id,
@@ -753,10 +753,10 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 #ifdef RSQ_COOP_LPR_SHIFT   // A/B builds: 2^shift lanes per read and pass (fewer reads per pass = fewer distinct table rows, i.e. L1 wavefronts, per load instruction)
 	const uint32_t lpr_shift = RSQ_COOP_LPR_SHIFT, lpr = 1u << lpr_shift, pass_rows = 32u >> lpr_shift;
 #else
-	// two lanes per read for short candidate lists, four for long ones (a quality draw of a profile with 40 quality values): more lanes per read mean
+	// two lanes per read for short candidate lists, four or eight for long ones (a quality draw of a profile with 40 quality values): more lanes per read mean
 	// fewer distinct table rows - L1 wavefronts, the pipe this kernel saturates - per load instruction, but idle lanes when the list is short
 	// (E. coli: 57.9 ms with two lanes on profile150r against 65.6 with four; 122.5 against 103.3 ms on profile150q)
-	uint32_t lpr_shift = n4 > kCoopWideFrom ? kCoopWideShift : 1u;
+	uint32_t lpr_shift = n4 > 32u ? kCoopWideShift : (n4 > kCoopWideFrom ? 2u : 1u);
 	if((32u >> lpr_shift) > n_rows){ lpr_shift = 2u; }   // 8 reads per warp: one pass of 8
 	const uint32_t lpr = 1u << lpr_shift, pass_rows = 32u >> lpr_shift;
 #endif
