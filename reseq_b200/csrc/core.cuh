@@ -46,7 +46,7 @@ struct TableDesc {
 	uint32_t span[4];    // limits_[n].second - limits_[n].first
 	uint32_t off[4];     // start of dim2_[n] inside the blob (in doubles)
 	uint32_t par0_off;   // start of par0_indeces_ inside the par0 array
-	uint32_t pad;
+	uint32_t stride;     // doubles from one row of a margin to the next: n0, or n0 rounded up to even with a 0.0 behind it (device layout: 16-byte rows)
 };
 
 struct Tables {
@@ -90,10 +90,10 @@ RSQ_HD uint32_t draw(const G &g, const Tables &t, uint32_t table_id, uint32_t i0
 		return 0;
 	}
 	const bool four = d.nm > 3;
-	const double *r0 = t.blob + (d.off[0] + adjust_index(i0, d.from[0], d.span[0]) * n0);
-	const double *r1 = t.blob + (d.off[1] + adjust_index(i1, d.from[1], d.span[1]) * n0);
-	const double *r2 = t.blob + (d.off[2] + adjust_index(i2, d.from[2], d.span[2]) * n0);
-	const double *r3 = four ? t.blob + (d.off[3] + adjust_index(i3, d.from[3], d.span[3]) * n0) : r0;
+	const double *r0 = t.blob + (d.off[0] + adjust_index(i0, d.from[0], d.span[0]) * d.stride);
+	const double *r1 = t.blob + (d.off[1] + adjust_index(i1, d.from[1], d.span[1]) * d.stride);
+	const double *r2 = t.blob + (d.off[2] + adjust_index(i2, d.from[2], d.span[2]) * d.stride);
+	const double *r3 = four ? t.blob + (d.off[3] + adjust_index(i3, d.from[3], d.span[3]) * d.stride) : r0;
 	const uint32_t n4 = (n0 + 3u) & ~3u;
 	g.sync();  // previous consumer of `prob` is done
 	for(uint32_t i = g.lane(); i < n4; i += G::kSize){

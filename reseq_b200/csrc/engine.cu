@@ -718,7 +718,7 @@ k_spec_scan<true>(const __grid_constant__ SimCtx c, const __grid_constant__ Spec
 // read: coalesced table rows) and parked in shared memory; each lane then runs the two strictly ordered FP64 sums of
 // its own read.
 #ifndef RSQ_PROD_UNROLL
-#define RSQ_PROD_UNROLL 4   // candidates per lane whose four table-row loads are in flight together (each trip of the product loop waits one L2 round trip)
+#define RSQ_PROD_UNROLL 4   // (measured: 2 -> E. coli 55.0 ms / realistic tables 87.4 ms / 100 Mbp 983 ms; 4 -> 52.3 / 73.7 / 918) candidate PAIRS per lane whose four 16-byte table-row loads are in flight together (each trip of the product loop waits one L2 round trip)
 #endif
 constexpr int kProdUnroll = RSQ_PROD_UNROLL;
 #ifndef RSQ_COOP_WIDE_FROM
@@ -739,10 +739,10 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 	if(active){
 		const TableDesc d = t.desc[table_id];
 		n0 = d.n0; nm = d.nm; par0_off = d.par0_off;
-		o0 = d.off[0] + adjust_index(i0, d.from[0], d.span[0]) * n0;
-		o1 = d.off[1] + adjust_index(i1, d.from[1], d.span[1]) * n0;
-		o2 = d.off[2] + adjust_index(i2, d.from[2], d.span[2]) * n0;
-		o3 = nm > 3 ? d.off[3] + adjust_index(i3, d.from[3], d.span[3]) * n0 : o0;
+		o0 = d.off[0] + adjust_index(i0, d.from[0], d.span[0]) * d.stride;
+		o1 = d.off[1] + adjust_index(i1, d.from[1], d.span[1]) * d.stride;
+		o2 = d.off[2] + adjust_index(i2, d.from[2], d.span[2]) * d.stride;
+		o3 = nm > 3 ? d.off[3] + adjust_index(i3, d.from[3], d.span[3]) * d.stride : o0;
 	}
 	const uint32_t maxn = __reduce_max_sync(0xffffffffu, n0);
 	if(maxn == 0){ zero = true; return 0; }
@@ -768,16 +768,19 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 		const bool four = __shfl_sync(0xffffffffu, nm, src) > 3u;
 		double *row = buf + src * stride;
 		if((amask >> src) & 1u){
+			// two candidates per lane and trip: rows are 16-byte aligned pairs with a 0.0 behind an odd last candidate (the product of the padding is
+			// the +0.0 the sums expect there); a pair that starts behind the list is not loaded at all
 #pragma unroll kProdUnroll
-			for(uint32_t idx = i; idx < n4; idx += lpr){
-				double p = 0.0;
+			for(uint32_t idx = 2u * i; idx < n4; idx += 2u * lpr){
+				double2 p = make_double2(0.0, 0.0);
 				if(idx < sn0){
-					p = __ldg(t.blob + s0 + idx);
-					p = mul_rn(p, __ldg(t.blob + s1 + idx));
-					p = mul_rn(p, __ldg(t.blob + s2 + idx));
-					if(four){ p = mul_rn(p, __ldg(t.blob + s3 + idx)); }
+					p = __ldg(reinterpret_cast<const double2 *>(t.blob + s0 + idx));
+					const double2 b = __ldg(reinterpret_cast<const double2 *>(t.blob + s1 + idx));
+					const double2 cc = __ldg(reinterpret_cast<const double2 *>(t.blob + s2 + idx));
+					p.x = mul_rn(mul_rn(p.x, b.x), cc.x); p.y = mul_rn(mul_rn(p.y, b.y), cc.y);
+					if(four){ const double2 e = __ldg(reinterpret_cast<const double2 *>(t.blob + s3 + idx)); p.x = mul_rn(p.x, e.x); p.y = mul_rn(p.y, e.y); }
 				}
-				row[idx] = p;
+				row[idx] = p.x; row[idx + 1u] = p.y;
 			}
 		}
 	}
@@ -1315,7 +1318,14 @@ static void upload_profile(rsq_engine &e){
 	e.max_n0 = 0;
 	for(const auto &h : p.tables){
 		TableDesc d{}; d.n0 = h.par0.size(); d.nm = h.nm;
-		for(uint32_t n = 0; n < h.nm; ++n){ d.from[n] = h.from[n]; d.span[n] = h.to[n] - h.from[n]; d.off[n] = blob.size(); blob.insert(blob.end(), h.dim2[n].begin(), h.dim2[n].end()); }
+		d.stride = (d.n0 + 1u) & ~1u;   // rows of 16-byte pairs: the cooperative product loads two candidates per instruction (half the L1 wavefronts)
+		for(uint32_t n = 0; n < h.nm; ++n){
+			d.from[n] = h.from[n]; d.span[n] = h.to[n] - h.from[n]; d.off[n] = blob.size();
+			for(uint32_t r = 0; r < d.span[n]; ++r){
+				blob.insert(blob.end(), h.dim2[n].begin() + static_cast<size_t>(r) * d.n0, h.dim2[n].begin() + static_cast<size_t>(r + 1) * d.n0);
+				if(d.stride != d.n0){ blob.push_back(0.0); }
+			}
+		}
 		d.par0_off = par0.size(); par0.insert(par0.end(), h.par0.begin(), h.par0.end());
 		desc.push_back(d);
 		e.max_n0 = std::max(e.max_n0, d.n0);

@@ -86,7 +86,7 @@ int main(int argc, char **argv){
 	SimCtx c{};
 	// tables
 	for(const auto &h : p.tables){
-		TableDesc d{}; d.n0 = h.par0.size(); d.nm = h.nm;
+		TableDesc d{}; d.n0 = h.par0.size(); d.nm = h.nm; d.stride = d.n0;   // (the engine pads rows to 16 bytes; the one-lane Draw reads either layout)
 		for(uint32_t n = 0; n < h.nm; ++n){ d.from[n] = h.from[n]; d.span[n] = h.to[n] - h.from[n]; d.off[n] = st.blob.size(); st.blob.insert(st.blob.end(), h.dim2[n].begin(), h.dim2[n].end()); }
 		d.par0_off = st.par0.size(); st.par0.insert(st.par0.end(), h.par0.begin(), h.par0.end());
 		st.desc.push_back(d);
