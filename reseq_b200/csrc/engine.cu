@@ -729,6 +729,10 @@ constexpr uint32_t kCoopWideFrom = RSQ_COOP_WIDE_FROM;   // candidate lists long
 #define RSQ_COOP_WIDE_SHIFT 3   // more than 32 candidates: eight lanes per read (profile150q: 84.5 ms; four lanes 94.7, sixteen 87.8, two 122.5)
 #endif
 constexpr uint32_t kCoopWideShift = RSQ_COOP_WIDE_SHIFT;
+#ifndef RSQ_COOP_MID_SHIFT
+#define RSQ_COOP_MID_SHIFT 2
+#endif
+constexpr uint32_t kCoopMidShift = RSQ_COOP_MID_SHIFT;
 __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint32_t stride, uint32_t n_rows, bool active, uint32_t table_id,
                                                uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, double u, bool &zero){
 	const unsigned amask = __ballot_sync(0xffffffffu, active);
@@ -756,7 +760,7 @@ __device__ __forceinline__ uint32_t coop_draw(const Tables &t, double *buf, uint
 	// two lanes per read for short candidate lists, four or eight for long ones (a quality draw of a profile with 40 quality values): more lanes per read mean
 	// fewer distinct table rows - L1 wavefronts, the pipe this kernel saturates - per load instruction, but idle lanes when the list is short
 	// (E. coli: 57.9 ms with two lanes on profile150r against 65.6 with four; 122.5 against 103.3 ms on profile150q)
-	uint32_t lpr_shift = n4 > 32u ? kCoopWideShift : (n4 > kCoopWideFrom ? 2u : 1u);
+	uint32_t lpr_shift = n4 > 32u ? kCoopWideShift : (n4 > kCoopWideFrom ? kCoopMidShift : 1u);
 	if((32u >> lpr_shift) > n_rows){ lpr_shift = 2u; }   // 8 reads per warp: one pass of 8
 	const uint32_t lpr = 1u << lpr_shift, pass_rows = 32u >> lpr_shift;
 #endif
