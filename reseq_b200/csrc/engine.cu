@@ -929,10 +929,10 @@ __device__ __forceinline__ void spec_reads_body(const SimCtx &c, const SpecCtx &
 	// dense over (unit, read of this round): reads beyond run_depth do not exist in this round - except for the adapter-only
 	// pseudo unit (always full depth), whose further reads are appended behind the regular ones of its group
 	const size_t dense = gwarp * lanes_per_warp + lane;
-	const size_t regular = static_cast<size_t>(unit_end - unit_first) * sp.run_depth;
+	const size_t regular = static_cast<size_t>(unit_end - unit_first) * sp.map_depth;
 	uint32_t u, k;
-	if(dense < regular){ u = unit_first + static_cast<uint32_t>(dense / sp.run_depth); k = static_cast<uint32_t>(dense % sp.run_depth); }
-	else{ u = sp.n_blocks; k = sp.run_depth + static_cast<uint32_t>(dense - regular); }
+	if(dense < regular){ u = unit_first + static_cast<uint32_t>(dense / sp.map_depth); k = static_cast<uint32_t>(dense % sp.map_depth); }
+	else{ u = sp.n_blocks; k = sp.map_depth + static_cast<uint32_t>(dense - regular); }
 	const bool in_range = dense < regular || (sp.n_units > sp.n_blocks && unit_end == sp.n_units && k < sp.depth);
 	const size_t gidx = static_cast<size_t>(u) * sp.depth + k;
 	bool have = false;
@@ -2260,12 +2260,17 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 	double lat_fixed = 1.0, lat_per_read = 0.12;
 	if(const char *env = getenv("RSQ_SPEC_LAT")){ sscanf(env, "%lf,%lf", &lat_fixed, &lat_per_read); }   // tuning runs
 	const bool trace = getenv("RSQ_SPEC_TRACE") != nullptr;
+	// Option (RSQ_SPEC_CAP=64 RSQ_SPEC_HOT=1): a unit whose reads come denser than average speculates proportionally deeper (capacity 64 instead of 32),
+	// so that the hot SimBlocks (up to 1.6 x the reads of an average one on E. coli) do not need as many more rounds.  Measured on E. coli: 62.0 ms
+	// against 52.2 ms without - the wider slot range per unit costs more than the few units that finish a round earlier gain.  Off.
+	const bool hot_scaling = depth_cap > 32 && !records && getenv("RSQ_SPEC_HOT") && atoi(getenv("RSQ_SPEC_HOT")) == 1;
+	sp.mean_reads = hot_scaling && e.n_blocks_sim ? static_cast<float>(2.0 * e.total_pairs / e.n_blocks_sim) : 0.0f;
 	uint32_t lanes = 32;
 	auto choose = [&](uint64_t active, double p_hold){
 		uint32_t best_d = 2; double best = -1.0;
 		static const uint32_t cand[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
 		for(uint32_t d : cand){
-			if(d > depth){ break; }
+			if(d > depth || (hot_scaling && d > 32u)){ break; }
 			const double prog = p_hold >= 0.9999 ? d : (1.0 - std::pow(p_hold, static_cast<double>(d))) / (1.0 - p_hold);
 			const double latency = records ? 0.6 + 0.01 * d : lat_fixed + lat_per_read * d;   // seqToIllumina units have no scan in front of their reads
 			const double cost = std::max(latency, 3.2e-5 * static_cast<double>(active) * (3.0 + d));
@@ -2273,6 +2278,7 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 		}
 		if(fixed_depth){ best_d = fixed_depth; }
 		sp.run_depth = best_d;
+		sp.map_depth = hot_scaling ? sp.depth : best_d;
 		const double budget = budget_factor * best_d * draws_per_read + 4096.0;
 		sp.scan_budget = budget > 4.0e9 ? 4000000000u : static_cast<uint32_t>(budget);
 		// reads per warp: as few as keep all reads of the round resident at once
@@ -2340,8 +2346,8 @@ static bool simulate_spec_batch(rsq_engine &e, uint32_t u_begin, uint32_t u_coun
 						if(u1 == u0){ continue; }
 						cudaStream_t gs = e.spec_streams[gi];
 						scan_kernel<<<(u1 - u0 + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, scan_shmem, gs>>>(c, sp, e.d_blocks.p, first_desc, u0, u1);
-						const size_t extra = (sp.n_units > sp.n_blocks && u1 == sp.n_units && sp.depth > sp.run_depth) ? sp.depth - sp.run_depth : 0;
-						const size_t warps = (static_cast<size_t>(u1 - u0) * sp.run_depth + extra + lanes - 1) / lanes;
+						const size_t extra = (sp.n_units > sp.n_blocks && u1 == sp.n_units && sp.depth > sp.map_depth) ? sp.depth - sp.map_depth : 0;
+						const size_t warps = (static_cast<size_t>(u1 - u0) * sp.map_depth + extra + lanes - 1) / lanes;
 						const size_t shmem_reads = static_cast<size_t>(kSpecReadWarps) * lanes * (stride * sizeof(double) + kSpecWindowBytes);
 						reads_kernel<<<static_cast<unsigned>((warps + kSpecReadWarps - 1) / kSpecReadWarps), kSpecReadWarps * 32, shmem_reads, gs>>>(c, sp, stride, lanes, u0, u1);
 						e.launches += 2;

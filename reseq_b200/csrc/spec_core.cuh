@@ -175,6 +175,9 @@ struct SpecCtx {
 	uint32_t depth;                // D: capacity per unit and round (reads emitted beyond the verified ones, <= kSpecMaxDepth); array stride
 	uint32_t run_depth;            // reads to emit per unit in this round (<= depth): grows when few units are left
 	uint32_t scan_budget;          // scan draws per unit and round after which the round ends even with < run_depth reads (bounds stragglers)
+	uint32_t map_depth;            // read slots per unit that k_spec_reads covers (run_depth, or depth when dense units may speculate deeper)
+	float mean_reads;              // expected reads of a SimBlock; > 0: a unit whose reads come denser than that speculates proportionally deeper (up to depth),
+	                               // so that all units get through their block in about the same number of rounds (0: run_depth for every unit)
 	uint32_t words_per_job;        // K: capacity of a read's stream slice
 	uint32_t margin;               // stream words copied behind the assumed consumption (kSpecMargin; tests shrink it to force the fallback)
 	uint32_t n_units;              // blocks (+ the adapter-only pseudo block) of this batch
@@ -428,6 +431,7 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	ReadJob *jobs = sp.jobs + static_cast<size_t>(u) * D;
 	SpecSnap *unit_snaps = sp.snaps + static_cast<size_t>(u) * 2u * (D + 1u);
 	const uint32_t n_prev = blk.n_jobs;
+	const uint32_t reads_before = blk.reads;   // verified reads of this unit before this round (lane 0 adds this round's below)
 	uint32_t bank = blk.snap_bank, idx = blk.snap_idx, pending_skip = blk.pending_skip;
 	uint32_t fill = blk.fill, cur_slab = blk.cur_slab, next_slab = blk.next_slab, next2_slab = blk.next2_slab;
 	g.sync();
@@ -538,7 +542,17 @@ RSQ_HD void scan_window(const G &g, const SimCtx &c, const SpecCtx &sp, const Bl
 	bool full = false, failed = false;
 	const uint64_t draws_limit = draws + sp.scan_budget;
 	// the adapter-only pairs are ONE serial stream however large the run is: always speculate as deep as the buffers allow
-	const uint32_t D_run = adapter_only ? D : (sp.run_depth < D ? sp.run_depth : D);
+	uint32_t D_run = adapter_only ? D : (sp.run_depth < D ? sp.run_depth : D);
+	if(!adapter_only && !records && sp.mean_reads > 0.0f && D_run < D && pos >= b.start_pos + 32u){
+		// reads verified so far over the positions scanned so far, extrapolated to the block: hot blocks (GC / surrounding bias) hold up to twice the
+		// reads of an average one and would need as many more rounds at the same depth - the tail of a small run
+		const float est = static_cast<float>(reads_before) * static_cast<float>(end - b.start_pos) / static_cast<float>(pos - b.start_pos);
+		const float scale = est / sp.mean_reads;
+		if(scale > 1.0f){
+			const uint32_t d = static_cast<uint32_t>(static_cast<float>(D_run) * scale + 0.999f);
+			D_run = d < D ? d : D;
+		}
+	}
 	if(records){
 		// seqToIllumina (Simulator::ErrorModelOnlyThread): no scan - pos is the next input record of this batch, len the end of the batch
 		while(pos < len && emitted < D_run && !failed){

@@ -401,6 +401,7 @@ int main(int argc, char **argv){
 		SpecCtx sp{};
 		sp.depth = std::max(1, atoi(spec_env));
 		sp.run_depth = sp.depth;
+		if(getenv("RSQ_TWIN_MEAN_READS")){ sp.mean_reads = static_cast<float>(atof(getenv("RSQ_TWIN_MEAN_READS"))); sp.run_depth = std::max(1u, sp.depth / 3); }   // dense units speculate deeper than run_depth
 		sp.scan_budget = getenv("RSQ_TWIN_BUDGET") ? atoi(getenv("RSQ_TWIN_BUDGET")) : 4000000000u;
 		const uint32_t max_rl = std::max(c.read_len_to[0], c.read_len_to[1]);
 		sp.words_per_job = (3 * max_rl + 8 + kSpecMargin + 7u) & ~7u; sp.margin = kSpecMargin;

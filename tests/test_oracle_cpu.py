@@ -118,6 +118,22 @@ def test_speculative_two_phase_templates_match_reference(oracle, golden, twin, w
     assert filecmp.cmp(prefix + "_2.fq", golden["r2"], shallow=False)
 
 
+def test_speculation_depth_scaled_by_read_density_matches_reference(oracle, golden, twin, workdir):
+    """SpecCtx::mean_reads: a unit whose reads come denser than the expected number per SimBlock speculates proportionally deeper than run_depth
+    (up to the capacity) - the rule that evens out the number of rounds per unit on small genomes.  Same bytes whatever the rule does."""
+    stage = os.path.join(workdir, "stage_spec.flat")
+    if not os.path.exists(stage):
+        subprocess.run([oracle["dump"], "sim", golden["reseq"], golden["small_ref"], "42", "20", stage], check=True, timeout=600,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for mean in ("40", "400"):
+        prefix = os.path.join(workdir, f"twin_hot{mean}")
+        res = subprocess.run([twin, stage, "42", prefix, "66"], capture_output=True, text=True, timeout=900,
+                             env=dict(os.environ, RSQ_TWIN_SPEC="48", RSQ_TWIN_MEAN_READS=mean))
+        assert res.returncode == 0 and "error_flag=0" in res.stdout, res.stdout
+        assert filecmp.cmp(prefix + "_1.fq", golden["r1"], shallow=False)
+        assert filecmp.cmp(prefix + "_2.fq", golden["r2"], shallow=False)
+
+
 @pytest.mark.parametrize("spec_depth", [None, "4"])
 def test_templates_match_reference_with_tiles_and_read_lengths(oracle, golden, twin, workdir, spec_depth):
     """Three tiles and two read lengths per segment (profile150t): tile draw per pair, read-length draw per read."""
