@@ -349,7 +349,7 @@ def run_b200(args):
                                        "warp_inst_per_s": warp_inst / (sim_ms / 1000.0) if sim_ms else None,
                                        "issue_peak_warp_inst_per_s": ISSUE_PEAK,
                                        "frac_of_issue_peak": warp_inst / (sim_ms / 1000.0) / ISSUE_PEAK if sim_ms else None,
-                                       "model": f"{SCAN_INST_PER_DRAW} warp instructions per scan draw + {READ_INST_PER_BASE} per base and read (ncu, profiles/r02y_launches.md); rank 0, simulate phase"},
+                                       "model": f"{SCAN_INST_PER_DRAW} warp instructions per scan draw + {READ_INST_PER_BASE} per base and read (ncu launch list profiles/r02y_launches.md; the reads kernel issues about 5 % fewer since it loads two candidates per instruction); rank 0, simulate phase"},
                          "note": "algorithmic bytes = pairs x 1420 B + positions x 8.25 B over the event time of the simulate phase (every launch of the two kernels of a "
                                  "step); the phase is bound by the per-SimBlock serial mt19937_64 stream and dependent FP64 Draw chains (latency), not by HBM"},
         }
